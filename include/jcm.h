@@ -1,0 +1,119 @@
+/* jcm.h - C ABI of libjcm.so: the B200 (sm_100a) kernels behind the joint-cnn-mrf hot path.
+ *
+ * The reference (max-andr/joint-cnn-mrf) has no FFI: its boundary is the Python function surface of main.py executing
+ * TensorFlow-1.x ops.  Each entry point below replaces the TF op call sites named in its comment (file:line in the
+ * reference).  The Python package `jcm` (joint-cnn-mrf_b200/jcm) binds these with ctypes and re-exposes the reference's
+ * function names (model, spatial_model, conv_mrf, spatial_softmax, softmax_cross_entropy, ...); INTEGRATION.md shows
+ * the binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (activations NHWC, fp32 unless stated); kernels never
+ *     allocate; `stream` is a cudaStream_t passed as void*; calls are asynchronous on that stream.
+ *   - "operand planes": bf16 NHWC tensors in pairs (hi, lo) with hi + lo == the fp32 value to ~2^-17.  Passing lo == NULL
+ *     selects plain bf16 arithmetic (training config), passing lo selects the 3-term split product ("bf16x3", fp32 config).
+ *   - return value: 0 = ok, < 0 = bad argument / unsupported shape (JCM_E*), > 0 = cudaError_t.  jcm_last_error()
+ *     returns a thread-local message.  There is no CPU fallback anywhere.
+ */
+#ifndef JCM_H_
+#define JCM_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JCM_OK 0
+#define JCM_EINVAL (-1)
+#define JCM_ENOTSUP (-2)
+#define JCM_EWORKSPACE (-3)
+
+const char* jcm_last_error(void);
+int jcm_version(void);
+int jcm_sm_count(void);
+
+/* ---- operand preparation --------------------------------------------------------------------------------------- */
+
+/* x fp32 [B,H,W,3] -> space-to-depth bf16 planes [B,H/2,W/2,16], [B,H/4,W/4,16], [B,H/8,W/8,16] for the three banks.
+ * Replaces tf.image.resize_images(x,[H/2,W/2]) / [H/4,W/4] (main.py:51,60) and prepares the stride-2 conv1_* (main.py:44,52,61). */
+int jcm_prep_input(const float* x, int B, int H, int W, void* full_hi, void* full_lo, void* half_hi, void* half_lo,
+                   void* quarter_hi, void* quarter_lo, void* stream);
+
+/* conv kernel HWIO fp32 [k,k,Cin,Cout] (main.py:138-147 weight_variable layout) -> packed [k*k][Opad][Ipad] bf16 planes.
+ * transpose = 0: forward operand (O = Cout, I = Cin); transpose = 1: data-gradient operand (taps flipped, O = Cin, I = Cout). */
+int jcm_pack_weights(const float* w, int ksize, int Cin, int Cout, int Opad, int Ipad, int transpose, void* out_hi,
+                     void* out_lo, void* stream);
+
+/* conv1_* kernels [5,5,3,Cout] -> [9][Cout][16] matching jcm_prep_input's channel order (5x5 s2 SAME == 3x3 s1 over s2d). */
+int jcm_pack_weights_s2d(const float* w, int Cout, void* out_hi, void* out_lo, void* stream);
+
+/* fp32 -> bf16 hi (+ lo) element-wise; n multiple of 4. */
+int jcm_split_planes(const float* x, long n, void* hi, void* lo, void* stream);
+
+/* ---- part detector --------------------------------------------------------------------------------------------- */
+
+/* y = [relu](conv_SAME_stride1(x, w) + bias): tf.nn.conv2d + bias + tf.nn.relu, main.py:133-135,160-162.
+ * x planes [B,H,W,Cin] (Cin a multiple of 16), w planes [k*k][Cout_pad][Cin], y fp32 [B,H,W,Cout].
+ * TMA-fed implicit GEMM on tcgen05 tensor cores, fp32 accumulation in TMEM. */
+int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, float* y,
+                   int B, int H, int W, int Cin, int Cout, int Cout_pad, int ksize, int relu, void* stream);
+
+/* tf.contrib.layers.batch_norm(decay=0.9, eps=1e-3, center, scale), main.py:128-130 and :112-113.
+ * jcm_bn_stats: per-channel partial sums of x [M,C] into `partial` (jcm_bn_stats_blocks(M,C)*2*C floats).
+ * jcm_bn_finalize: train != 0 -> batch statistics (biased variance), moving stats updated in place when update_moving
+ * (unbiased variance); train == 0 -> moving statistics.  Emits scale = gamma*rstd, shift = beta - mean*scale. */
+int jcm_bn_stats_blocks(long M, int C);
+int jcm_bn_stats(const float* x, long M, int C, float* partial, void* stream);
+int jcm_bn_finalize(const float* partial, long M, int C, const float* gamma, const float* beta, float* moving_mean,
+                    float* moving_var, float eps, float decay, int train, int update_moving, float* scale, float* shift,
+                    float* save_mean, float* save_rstd, void* stream);
+
+/* BN affine (+ tf.nn.max_pool 2x2 s2 SAME, main.py:172-174) -> operand planes and/or fp32. */
+int jcm_bn_apply_pool(const float* a, const float* scale, const float* shift, int B, int H, int W, int C, int pool,
+                      void* out_hi, void* out_lo, float* out_f32, void* stream);
+
+/* (bn(a1) + resize(bn(a2)) + resize(bn(a3))) / 3 with tf.image.resize_images legacy bilinear, main.py:58,67,69-70.
+ * scale_shift = [6][C] = scale1, shift1, scale2, shift2, scale3, shift3. */
+int jcm_upsample_avg3(const float* a1, const float* a2, const float* a3, const float* scale_shift, int B, int H, int W,
+                      int H2, int W2, int H3, int W3, int C, void* out_hi, void* out_lo, float* out_f32, void* stream);
+
+/* ---- heads ----------------------------------------------------------------------------------------------------- */
+
+/* spatial_softmax, main.py:212-217: softmax over S = H*W per (image, joint); logits/out [B,S,K]. */
+int jcm_spatial_softmax(const float* logits, int B, int S, int K, float* out, void* stream);
+
+/* softmax_cross_entropy, main.py:220-240: per_nk[B*K] = -sum_s labels*log_softmax(logits), loss[0] = mean.
+ * labels [B,S,KL] (first K channels used); lse [B*K] optional (saved for the backward pass). */
+int jcm_softmax_ce(const float* logits, const float* labels, int B, int S, int K, int KL, float* per_nk, float* lse,
+                   float* loss, void* stream);
+
+/* evaluation.get_joints_coords, evaluation.py:15-24 (= argmax_hm, main.py:389-397): out int32 [B,2,K] = (row, col) of the
+ * first maximum in row-major order. */
+int jcm_argmax_hw(const float* hm, int B, int H, int W, int K, int* out, void* stream);
+
+/* ---- spatial model ---------------------------------------------------------------------------------------------- */
+
+/* spatial_model + conv_mrf, main.py:77-125, after the bn_sm statistics (use jcm_bn_stats/finalize on heat_map [B*H*W, K+1]).
+ * heat_map [B,H,W,K+1]; energies [P][2H][2W] (pairwise_energies, main.py:482-484), biases [P][H][W] (main.py:486-487);
+ * pair_target / pair_cond int32 [P] on the device, sorted by (target, cond) = the reference's summation order. out [B,H,W,K]. */
+long jcm_spatial_model_workspace(int B, int H, int W, int K, int P);
+int jcm_spatial_model_fwd(const float* heat_map, const float* bn_scale, const float* bn_shift, const float* energies,
+                          const float* biases, const int* pair_target, const int* pair_cond, float* out, void* workspace,
+                          long workspace_bytes, int B, int H, int W, int K, int P, void* stream);
+
+/* conv_mrf(A, B), main.py:77-91, on its own: A [2H,2W], Bmaps [b,H,W] (both used as given) -> out [b,H,W] =
+ * legacy-bilinear resize of the 'valid' convolution.  Workspace: jcm_spatial_model_workspace(b, H, W, 0, 1) bytes. */
+int jcm_conv_mrf_fwd(const float* A, const float* Bmaps, float* out, void* workspace, long workspace_bytes, int b, int H,
+                     int W, void* stream);
+
+/* ---- measurement / test support --------------------------------------------------------------------------------- */
+
+/* FP32 FMA peak loop (packed = 1: FFMA2); flops_out = FLOPs of one launch. scratch: blocks*512 floats. */
+int jcm_fma_peak(float* scratch, int blocks, int iters, int packed, double* flops_out, void* stream);
+
+/* Naive direct convolution on the same operand planes - used only by tests to cross-check the tcgen05 kernel. */
+int jcm_debug_conv2d_naive(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
+                           float* y, int B, int H, int W, int Cin, int Cout, int Cout_pad, int ksize, int relu, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JCM_H_ */

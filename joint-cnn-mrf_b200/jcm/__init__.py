@@ -1,0 +1,8 @@
+"""jcm - the joint-cnn-mrf hot path (part-detector CNN + MRF spatial model + heat-map loss) on hand-written sm_100a
+CUDA kernels.  The functions re-exported here carry the names of the reference's main.py / evaluation.py."""
+from ._lib import lib, JcmError, LIB_PATH  # noqa: F401
+from . import ops  # noqa: F401
+from .graph import (Context, PairwiseParams, JOINT_NAMES, model, spatial_model, conv_mrf, conv2d, batch_norm,  # noqa: F401
+                    max_pool_layer, weight_variable, bias_variable, spatial_softmax, softmax_cross_entropy,
+                    get_joints_coords, det_rate, get_pairwise_distr, init_part_detector, load_params, tower_forward,
+                    n_filters, conv_specs)

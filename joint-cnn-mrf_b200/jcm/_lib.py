@@ -1,0 +1,72 @@
+"""ctypes binding of libjcm.so (include/jcm.h).  No fallback: if the library is missing this raises at import of the
+first op, telling the user to build it (python joint-cnn-mrf_b200/build.py)."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libjcm.so')
+
+_c = ctypes
+_P = _c.c_void_p
+_I = _c.c_int
+_L = _c.c_long
+_F = _c.c_float
+
+# name -> (restype, argtypes); must list every symbol declared in include/jcm.h (tests/test_abi.py checks this)
+SIGNATURES = {
+    'jcm_last_error': (_c.c_char_p, []),
+    'jcm_version': (_I, []),
+    'jcm_sm_count': (_I, []),
+    'jcm_prep_input': (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    'jcm_pack_weights': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    'jcm_pack_weights_s2d': (_I, [_P, _I, _P, _P, _P]),
+    'jcm_split_planes': (_I, [_P, _L, _P, _P, _P]),
+    'jcm_conv2d_fwd': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'jcm_bn_stats_blocks': (_I, [_L, _I]),
+    'jcm_bn_stats': (_I, [_P, _L, _I, _P, _P]),
+    'jcm_bn_finalize': (_I, [_P, _L, _I, _P, _P, _P, _P, _F, _F, _I, _I, _P, _P, _P, _P, _P]),
+    'jcm_bn_apply_pool': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    'jcm_upsample_avg3': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    'jcm_spatial_softmax': (_I, [_P, _I, _I, _I, _P, _P]),
+    'jcm_softmax_ce': (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    'jcm_argmax_hw': (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    'jcm_spatial_model_workspace': (_L, [_I, _I, _I, _I, _I]),
+    'jcm_spatial_model_fwd': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
+    'jcm_conv_mrf_fwd': (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _P]),
+    'jcm_fma_peak': (_I, [_P, _I, _I, _I, _P, _P]),
+    'jcm_debug_conv2d_naive': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+}
+
+_lib = None
+
+
+class JcmError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads libjcm.so once and attaches the signatures."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise JcmError('libjcm.so not found at %s - build it with `python joint-cnn-mrf_b200/build.py` '
+                           '(there is no CPU / PyTorch fallback for the jcm kernels)' % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            if not hasattr(l, name):
+                continue  # later-round symbols may be absent from an older build; test_abi checks the header
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    """Turns a jcm return code into a Python exception (ValueError for argument errors, RuntimeError otherwise)."""
+    if rc == 0:
+        return
+    msg = lib().jcm_last_error().decode('utf-8', 'replace')
+    if rc < 0:
+        raise ValueError('%s failed (%d): %s' % (what, rc, msg))
+    raise JcmError('%s failed (cudaError %d): %s' % (what, rc, msg))

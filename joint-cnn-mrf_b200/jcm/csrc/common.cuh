@@ -1,0 +1,74 @@
+// Shared helpers for the jcm sm_100a kernels (error reporting, PTX wrappers).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#define JCM_OK 0
+#define JCM_EINVAL (-1)
+#define JCM_ENOTSUP (-2)
+#define JCM_EWORKSPACE (-3)
+
+void jcm_set_error(const char* fmt, ...);
+
+#define JCM_CHECK_ARG(cond, ...)                  \
+  do {                                            \
+    if (!(cond)) {                                \
+      jcm_set_error(__VA_ARGS__);                 \
+      return JCM_EINVAL;                          \
+    }                                             \
+  } while (0)
+
+#define JCM_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t e__ = (call);                                                       \
+    if (e__ != cudaSuccess) {                                                       \
+      jcm_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return (int)e__;                                                              \
+    }                                                                               \
+  } while (0)
+
+#define JCM_LAUNCH_CHECK()                                                          \
+  do {                                                                              \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ != cudaSuccess) {                                                       \
+      jcm_set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return (int)e__;                                                              \
+    }                                                                               \
+  } while (0)
+
+static inline int jcm_cdiv(int a, int b) { return (a + b - 1) / b; }
+
+int jcm_num_sms();
+
+// ---------------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 1/alpha * softplus(alpha x), alpha = 5 (reference main.py:106-108), stable form max(z,0)+log1p(exp(-|z|))
+__device__ __forceinline__ float softplus5(float x) {
+  float z = 5.0f * x;
+  return 0.2f * (fmaxf(z, 0.0f) + log1pf(expf(-fabsf(z))));
+}
+// d/dx softplus5 = sigmoid(5x)
+__device__ __forceinline__ float sigmoid5(float x) { return 1.0f / (1.0f + expf(-5.0f * x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// split an fp32 value into bf16 hi + bf16 lo (hi + lo == x to ~2^-17 relative)
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}

@@ -1,0 +1,400 @@
+// Part-detector convolutions as a TMA-fed implicit GEMM on the 5th-gen tensor cores (tcgen05 / TMEM), sm_100a.
+//
+// Replaces the reference's `tf.nn.conv2d(x, W, strides, padding='SAME') + b` (+ `tf.nn.relu`)
+// (reference main.py:133-135, 156-162) for every stride-1 layer; the three stride-2 `conv1_*` layers are
+// mapped onto the same kernel by a space-to-depth transform done in prep.cu (5x5 s2 over 3 ch == 3x3 s1 over 16 ch).
+//
+// GEMM view:  D[m, co] = sum_{tap, ci} X[pix(m) + tap - pad, ci] * Wp[tap, co, ci]
+//   * M tile = 128 output pixels = a TW x TH spatial patch of ONE image (TW*TH == 128). The A operand of tap
+//     (dy,dx) is the same patch shifted by (dy-pad, dx-pad): one 4-D TMA box {kc, TW, TH, 1} per k-block, the
+//     SAME zero padding comes for free from TMA out-of-bounds fill (coordinates may be negative).
+//   * N tile = block_n output channels (16..256), B operand = packed weights [tap][Cout_pad][Cin] (K-major),
+//     3-D TMA box {kc, block_n, 1}.
+//   * K loop = taps x (Cin / kc) x terms.  kc = 64 (SWIZZLE_128B), 32 (SWIZZLE_64B) or 16 (SWIZZLE_32B, the s2d conv1 layers).
+//   * terms = 1: plain bf16 operands (training config).  terms = 3: "bf16x3" split accumulation
+//     (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo) which reproduces fp32 products to ~2^-16 - this is the fp32 config.
+//   * accumulators: fp32 in TMEM, 2 stages x 256 columns, so the epilogue of tile t overlaps the MMAs of t+1.
+//   * warp roles: w0 TMA producer, w1 MMA issuer (one elected lane), w2 TMEM allocator, w4-7 epilogue
+//     (tcgen05.ld -> +bias -> ReLU -> fp32 NHWC store).  Persistent grid, one CTA per SM.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxStages = 8;
+constexpr int kTileM = 128;
+
+struct ConvParams {
+  int B, H, W, Cout;
+  int TW, TH, tiles_x, tiles_y;
+  int n_tiles, block_n;
+  int kc, cblocks, ksize, pad, terms;
+  int stages, a_bytes, b_bytes, stage_bytes;
+  int relu;
+  const float* bias;
+  float* y;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread <-> TMEM lane)
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major operand, rows of `row_bytes` (= swizzle span: 128 or 32 bytes),
+// 8-row core groups `sbo` bytes apart.  Field layout: cute/arch/mma_sm100_desc.hpp (SmemDescriptor).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);           // start address  [0,14)
+  d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major) [16,30)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32; // stride byte offset [32,46)
+  d |= (uint64_t)1 << 46;                           // descriptor version = 1 (Blackwell) [46,48)
+  d |= (uint64_t)(layout_type & 7) << 61;           // 2 = SWIZZLE_128B, 6 = SWIZZLE_32B
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                  const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[kMaxStages]);
+  const uint32_t bar_tfull = smem_u32(&bars[2 * kMaxStages]);
+  const uint32_t bar_tempty = smem_u32(&bars[2 * kMaxStages + 2]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_tfull + 8 * s, 1);
+      mbar_init(bar_tempty + 8 * s, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int m_tiles = p.B * p.tiles_y * p.tiles_x;
+  const int total_tiles = m_tiles * p.n_tiles;
+  const int taps = p.ksize * p.ksize;
+  const int num_kb = taps * p.cblocks * p.terms;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile / m_tiles, mt = tile - nt * m_tiles;
+        const int img = mt / (p.tiles_y * p.tiles_x);
+        const int r = mt - img * (p.tiles_y * p.tiles_x);
+        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        const int x0 = tx * p.TW - p.pad, y0 = ty * p.TH - p.pad;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int dy = tap / p.ksize, dx = tap - dy * p.ksize;
+          for (int cb = 0; cb < p.cblocks; ++cb) {
+            for (int term = 0; term < p.terms; ++term) {
+              mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+              const uint32_t sa = smem_base + stage * p.stage_bytes;
+              const uint32_t sb = sa + p.a_bytes;
+              const uint32_t fb = bar_full + 8 * stage;
+              mbar_expect_tx(fb, p.a_bytes + p.b_bytes);
+              tma_load_4d(sa, term == 1 ? &map_a_lo : &map_a_hi, fb, cb * p.kc, x0 + dx, y0 + dy, img);
+              tma_load_3d(sb, term == 2 ? &map_b_lo : &map_b_hi, fb, cb * p.kc, nt * p.block_n, tap);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = block_n, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      const uint32_t row_bytes = p.kc * 2;                  // 128, 64 or 32 = the swizzle span
+      const uint32_t layout = (p.kc == 64) ? 2u : (p.kc == 32 ? 4u : 6u);  // SWIZZLE_128B : SWIZZLE_64B : SWIZZLE_32B
+      const uint32_t sbo = 8 * row_bytes;
+      const int kk = p.kc / 16;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * p.stage_bytes;
+          const uint64_t adesc = make_smem_desc(sa, sbo, layout);
+          const uint64_t bdesc = make_smem_desc(sa + p.a_bytes, sbo, layout);
+          for (int k = 0; k < kk; ++k) {
+            // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the 16-byte address field
+            tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
+          tc_commit(bar_empty + 8 * stage);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(bar_tfull + 8 * acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;          // accumulator row == pixel index inside the patch
+    const int ly = row / p.TW, lx = row - ly * p.TW;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile / m_tiles, mt = tile - nt * m_tiles;
+      const int img = mt / (p.tiles_y * p.tiles_x);
+      const int r = mt - img * (p.tiles_y * p.tiles_x);
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      const int oy = ty * p.TH + ly, ox = tx * p.TW + lx;
+      const bool valid = (oy < p.H) && (ox < p.W);
+      float* yrow = p.y + ((size_t)((size_t)img * p.H + oy) * p.W + ox) * p.Cout;
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t v[32];
+        tc_ld32(taddr0 + c0, v);
+        tc_ld_wait();
+        const int co0 = nt * p.block_n + c0;
+        if (valid) {
+          if (((p.Cout & 3) == 0) && (co0 + 32 <= p.Cout)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o;
+              float4 b = p.bias ? *reinterpret_cast<const float4*>(p.bias + co0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              o.x = __uint_as_float(v[j + 0]) + b.x;
+              o.y = __uint_as_float(v[j + 1]) + b.y;
+              o.z = __uint_as_float(v[j + 2]) + b.z;
+              o.w = __uint_as_float(v[j + 3]) + b.w;
+              if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              *reinterpret_cast<float4*>(yrow + co0 + j) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int co = co0 + j;
+              if (co < p.Cout && (c0 + j) < p.block_n) {
+                float o = __uint_as_float(v[j]) + (p.bias ? p.bias[co] : 0.f);
+                if (p.relu) o = fmaxf(o, 0.f);
+                yrow[co] = o;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_tmapEncodeTiled get_encode() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_tmapEncodeTiled)p;
+  }
+  return fn;
+}
+
+int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+             const uint32_t* box, CUtensorMapSwizzle swz) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (!enc) {
+    jcm_set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
+    return JCM_ENOTSUP;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                   (const cuuint64_t*)dims, (const cuuint64_t*)strides_bytes, (const cuuint32_t*)box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    jcm_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu %llu, box %u %u %u)", (int)r,
+                  rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], box[0],
+                  box[1], box[2]);
+    return JCM_EINVAL;
+  }
+  return JCM_OK;
+}
+
+}  // namespace
+
+// Chooses the TW x TH (= 128 pixels) patch shape that wastes the fewest accumulator rows on an H x W map.
+static void pick_patch(int H, int W, int* TW, int* TH) {
+  int best = 1 << 30, bw = 16, bh = 8;
+  const int cand[5][2] = {{16, 8}, {8, 16}, {32, 4}, {64, 2}, {128, 1}};
+  for (int i = 0; i < 5; ++i) {
+    int t = jcm_cdiv(W, cand[i][0]) * jcm_cdiv(H, cand[i][1]);
+    if (t < best) { best = t; bw = cand[i][0]; bh = cand[i][1]; }
+  }
+  *TW = bw;
+  *TH = bh;
+}
+
+extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
+                              float* y, int B, int H, int W, int Cin, int Cout, int Cout_pad, int ksize, int relu,
+                              void* stream) {
+  JCM_CHECK_ARG(x_hi && w_hi && y, "jcm_conv2d_fwd: null pointer");
+  JCM_CHECK_ARG((x_lo == nullptr) == (w_lo == nullptr), "jcm_conv2d_fwd: x_lo and w_lo must both be given (bf16x3) or both NULL (bf16)");
+  JCM_CHECK_ARG(B > 0 && H > 0 && W > 0, "jcm_conv2d_fwd: bad shape B=%d H=%d W=%d", B, H, W);
+  JCM_CHECK_ARG(ksize > 0 && (ksize & 1), "jcm_conv2d_fwd: ksize must be odd (SAME, stride 1), got %d", ksize);
+  JCM_CHECK_ARG(Cin >= 16 && (Cin % 16) == 0, "jcm_conv2d_fwd: Cin must be a multiple of 16, got %d", Cin);
+  JCM_CHECK_ARG(Cout > 0 && Cout_pad >= Cout && (Cout_pad % 16) == 0, "jcm_conv2d_fwd: Cout_pad=%d must be >= Cout=%d and a multiple of 16", Cout_pad, Cout);
+  JCM_CHECK_ARG((((uintptr_t)x_hi | (uintptr_t)w_hi | (uintptr_t)x_lo | (uintptr_t)w_lo | (uintptr_t)y) & 15) == 0,
+                "jcm_conv2d_fwd: pointers must be 16-byte aligned");
+
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.H = H; p.W = W; p.Cout = Cout;
+  pick_patch(H, W, &p.TW, &p.TH);
+  p.tiles_x = jcm_cdiv(W, p.TW);
+  p.tiles_y = jcm_cdiv(H, p.TH);
+  p.block_n = Cout_pad <= 256 ? Cout_pad : 256;
+  JCM_CHECK_ARG(Cout_pad % p.block_n == 0, "jcm_conv2d_fwd: Cout_pad=%d must be <= 256 or a multiple of 256", Cout_pad);
+  p.n_tiles = Cout_pad / p.block_n;
+  p.kc = (Cin % 64) == 0 ? 64 : ((Cin % 32) == 0 ? 32 : 16);
+  p.cblocks = Cin / p.kc;
+  p.ksize = ksize;
+  p.pad = (ksize - 1) / 2;
+  p.terms = x_lo ? 3 : 1;
+  p.a_bytes = kTileM * p.kc * 2;
+  p.b_bytes = p.block_n * p.kc * 2;
+  p.stage_bytes = ((p.a_bytes + p.b_bytes + 1023) / 1024) * 1024;
+  p.stages = (200 * 1024) / p.stage_bytes;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  p.relu = relu;
+  p.bias = bias;
+  p.y = y;
+
+  const CUtensorMapSwizzle swz = p.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+    int rc = make_map(&ma_hi, x_hi, 4, dims, str, box, swz);
+    if (rc) return rc;
+    rc = make_map(&ma_lo, x_lo ? x_lo : x_hi, 4, dims, str, box, swz);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout_pad, (uint64_t)(ksize * ksize)};
+    uint64_t str[2] = {(uint64_t)Cin * 2, (uint64_t)Cout_pad * Cin * 2};
+    uint32_t box[3] = {(uint32_t)p.kc, (uint32_t)p.block_n, 1};
+    int rc = make_map(&mb_hi, w_hi, 3, dims, str, box, swz);
+    if (rc) return rc;
+    rc = make_map(&mb_lo, w_lo ? w_lo : w_hi, 3, dims, str, box, swz);
+    if (rc) return rc;
+  }
+
+  const int total_tiles = B * p.tiles_x * p.tiles_y * p.n_tiles;
+  int grid = jcm_num_sms();
+  if (grid > total_tiles) grid = total_tiles;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    JCM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512));
+    attr_set = true;
+  }
+  conv_igemm_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}

@@ -1,0 +1,391 @@
+// HBM-bound glue kernels of the part detector and the loss heads (all NHWC, fp32 in, vectorised float4 access):
+//   jcm_bn_stats / jcm_bn_finalize   per-channel batch statistics -> (scale, shift), moving-average update
+//                                    (reference main.py:128-130,112-113: tf.contrib.layers.batch_norm, decay 0.9,
+//                                     eps 1e-3, biased variance to normalise, unbiased into the moving average)
+//   jcm_bn_apply_pool                BN affine (+ 2x2 s2 SAME max-pool, main.py:172-174) -> bf16 hi/lo operand planes
+//   jcm_upsample_avg3                BN affine on the three bank outputs + legacy-bilinear up-sampling of the 1/2 and 1/4
+//                                    banks + (x1+x2+x3)/3 (main.py:58,67,69-70) -> bf16 hi/lo operand planes
+//   jcm_spatial_softmax              softmax over H*W per (image, joint)   (main.py:212-217)
+//   jcm_softmax_ce                   soft-label cross entropy, mean over (image, joint) (main.py:220-240)
+//   jcm_argmax_hw                    first-max (row, col) per (image, joint) (evaluation.py:15-24)
+#include "common.cuh"
+
+namespace {
+
+constexpr int kStatThreads = 256;
+
+// ------------------------------------------------------------------------------------------- BN statistics
+// x [M, C]; each block reduces a contiguous slab of rows; thread t owns column group (t % G) and row lane (t / G).
+template <int VEC>
+__global__ void bn_stats_kernel(const float* __restrict__ x, long M, int C, float* __restrict__ partial /*[grid][2][C]*/) {
+  extern __shared__ float sh[];  // [kStatThreads][2*VEC]
+  const int G = C / VEC;         // column groups
+  const int lanes = kStatThreads / G;
+  const int g = threadIdx.x % G, rl = threadIdx.x / G;
+  float s[VEC], q[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) { s[v] = 0.f; q[v] = 0.f; }
+  const long rows_per_block = (M + gridDim.x - 1) / gridDim.x;
+  const long r0 = blockIdx.x * rows_per_block;
+  long r1 = r0 + rows_per_block;
+  if (r1 > M) r1 = M;
+  if (rl < lanes) {
+    for (long r = r0 + rl; r < r1; r += lanes) {
+      if (VEC == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(x + r * C + g * 4);
+        s[0] += v.x; q[0] += v.x * v.x;
+        s[1 % VEC] += v.y; q[1 % VEC] += v.y * v.y;
+        s[2 % VEC] += v.z; q[2 % VEC] += v.z * v.z;
+        s[3 % VEC] += v.w; q[3 % VEC] += v.w * v.w;
+      } else {
+        const float v = x[r * C + g];
+        s[0] += v; q[0] += v * v;
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    sh[threadIdx.x * 2 * VEC + v] = s[v];
+    sh[threadIdx.x * 2 * VEC + VEC + v] = q[v];
+  }
+  __syncthreads();
+  // deterministic tree-free reduction: thread c sums its column over the row lanes in order
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int gg = c / VEC, v = c % VEC;
+    float ts = 0.f, tq = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      ts += sh[(l * G + gg) * 2 * VEC + v];
+      tq += sh[(l * G + gg) * 2 * VEC + VEC + v];
+    }
+    partial[((long)blockIdx.x * 2 + 0) * C + c] = ts;
+    partial[((long)blockIdx.x * 2 + 1) * C + c] = tq;
+  }
+}
+
+// train != 0: batch statistics from the partials, moving stats updated in place.  train == 0: moving stats.
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblocks, long M, int C, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ moving_mean, float* __restrict__ moving_var,
+                                   float eps, float decay, int train, int update_moving, float* __restrict__ scale,
+                                   float* __restrict__ shift, float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double mean, var;
+  if (train) {
+    double s = 0.0, q = 0.0;
+    for (int b = 0; b < nblocks; ++b) {
+      s += (double)partial[((long)b * 2 + 0) * C + c];
+      q += (double)partial[((long)b * 2 + 1) * C + c];
+    }
+    mean = s / (double)M;
+    var = q / (double)M - mean * mean;
+    if (var < 0.0) var = 0.0;
+    if (update_moving) {
+      const double unb = M > 1 ? var * ((double)M / (double)(M - 1)) : var;
+      moving_mean[c] = (float)((double)moving_mean[c] * decay + (1.0 - decay) * mean);
+      moving_var[c] = (float)((double)moving_var[c] * decay + (1.0 - decay) * unb);
+    }
+  } else {
+    mean = moving_mean[c];
+    var = moving_var[c];
+  }
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = gamma[c] * rstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - (float)mean * sc;
+  if (save_mean) save_mean[c] = (float)mean;
+  if (save_rstd) save_rstd[c] = rstd;
+}
+
+// ------------------------------------------------------------------------------------------- BN apply (+pool)
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* hi, __nv_bfloat16* lo, long idx4, float4 v) {
+  __align__(8) __nv_bfloat16 h[4];
+  __align__(8) __nv_bfloat16 l[4];
+  split_bf16(v.x, h[0], l[0]);
+  split_bf16(v.y, h[1], l[1]);
+  split_bf16(v.z, h[2], l[2]);
+  split_bf16(v.w, h[3], l[3]);
+  reinterpret_cast<uint2*>(hi)[idx4] = *reinterpret_cast<uint2*>(h);
+  if (lo) reinterpret_cast<uint2*>(lo)[idx4] = *reinterpret_cast<uint2*>(l);
+}
+
+__device__ __forceinline__ float4 affine4(float4 v, float4 sc, float4 sh) {
+  return make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+}
+__device__ __forceinline__ float4 max4(float4 a, float4 b) {
+  return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+
+__global__ void bn_apply_pool_kernel(const float* __restrict__ a, const float* __restrict__ scale, const float* __restrict__ shift,
+                                     int B, int H, int W, int C, int pool, __nv_bfloat16* __restrict__ hi,
+                                     __nv_bfloat16* __restrict__ lo, float* __restrict__ out_f32) {
+  const int Ho = pool ? (H + 1) / 2 : H, Wo = pool ? (W + 1) / 2 : W;
+  const int C4 = C / 4;
+  const long total = (long)B * Ho * Wo * C4;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    long t = i / C4;
+    const int xo = (int)(t % Wo);
+    t /= Wo;
+    const int yo = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    const float4 sc = reinterpret_cast<const float4*>(scale)[c4];
+    const float4 sh = reinterpret_cast<const float4*>(shift)[c4];
+    float4 r;
+    if (!pool) {
+      r = affine4(reinterpret_cast<const float4*>(a)[i], sc, sh);
+    } else {
+      const int y0 = 2 * yo, x0 = 2 * xo;
+      const float* base = a + (((long)n * H + y0) * W + x0) * C + c4 * 4;
+      r = affine4(*reinterpret_cast<const float4*>(base), sc, sh);
+      const bool hx = x0 + 1 < W, hy = y0 + 1 < H;  // SAME pooling: the padded row/column never wins
+      if (hx) r = max4(r, affine4(*reinterpret_cast<const float4*>(base + C), sc, sh));
+      if (hy) r = max4(r, affine4(*reinterpret_cast<const float4*>(base + (long)W * C), sc, sh));
+      if (hx && hy) r = max4(r, affine4(*reinterpret_cast<const float4*>(base + (long)W * C + C), sc, sh));
+    }
+    if (hi) store_planes4(hi, lo, i, r);
+    if (out_f32) reinterpret_cast<float4*>(out_f32)[i] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- upsample + average
+// legacy bilinear (tf.image.resize_images, align_corners=False, no half-pixel offset): src = dst * (in/out) in fp32
+__device__ __forceinline__ void legacy_tap(int dst, int n_in, int n_out, int& lo, int& hi, float& w) {
+  const float scale = (float)n_in / (float)n_out;
+  const float src = (float)dst * scale;
+  lo = (int)floorf(src);
+  hi = min(lo + 1, n_in - 1);
+  w = src - (float)lo;
+}
+__device__ __forceinline__ float4 lerp4(float4 a, float4 b, float w) {
+  return make_float4(a.x + (b.x - a.x) * w, a.y + (b.y - a.y) * w, a.z + (b.z - a.z) * w, a.w + (b.w - a.w) * w);
+}
+__device__ __forceinline__ float4 resize_sample(const float* __restrict__ a, int n, int Hi, int Wi, int C, int c4, int y, int x, int Ho,
+                                                int Wo, float4 sc, float4 sh) {
+  int ylo, yhi, xlo, xhi;
+  float wy, wx;
+  legacy_tap(y, Hi, Ho, ylo, yhi, wy);
+  legacy_tap(x, Wi, Wo, xlo, xhi, wx);
+  const float* b = a + (long)n * Hi * Wi * C + c4 * 4;
+  const float4 tl = affine4(*reinterpret_cast<const float4*>(b + ((long)ylo * Wi + xlo) * C), sc, sh);
+  const float4 tr = affine4(*reinterpret_cast<const float4*>(b + ((long)ylo * Wi + xhi) * C), sc, sh);
+  const float4 bl = affine4(*reinterpret_cast<const float4*>(b + ((long)yhi * Wi + xlo) * C), sc, sh);
+  const float4 br = affine4(*reinterpret_cast<const float4*>(b + ((long)yhi * Wi + xhi) * C), sc, sh);
+  return lerp4(lerp4(tl, tr, wx), lerp4(bl, br, wx), wy);
+}
+
+__global__ void upsample_avg3_kernel(const float* __restrict__ a1, const float* __restrict__ a2, const float* __restrict__ a3,
+                                     const float* __restrict__ ss /* [6][C]: scale1, shift1, scale2, shift2, scale3, shift3 */,
+                                     int B, int H, int W, int H2, int W2, int H3, int W3, int C, __nv_bfloat16* __restrict__ hi,
+                                     __nv_bfloat16* __restrict__ lo, float* __restrict__ out_f32) {
+  const int C4 = C / 4;
+  const long total = (long)B * H * W * C4;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    long t = i / C4;
+    const int x = (int)(t % W);
+    t /= W;
+    const int y = (int)(t % H);
+    const int n = (int)(t / H);
+    const float4* s4 = reinterpret_cast<const float4*>(ss);
+    const float4 v1 = affine4(reinterpret_cast<const float4*>(a1)[i], s4[0 * C4 + c4], s4[1 * C4 + c4]);
+    const float4 v2 = resize_sample(a2, n, H2, W2, C, c4, y, x, H, W, s4[2 * C4 + c4], s4[3 * C4 + c4]);
+    const float4 v3 = resize_sample(a3, n, H3, W3, C, c4, y, x, H, W, s4[4 * C4 + c4], s4[5 * C4 + c4]);
+    float4 r;
+    r.x = (v1.x + v2.x + v3.x) / 3.0f;
+    r.y = (v1.y + v2.y + v3.y) / 3.0f;
+    r.z = (v1.z + v2.z + v3.z) / 3.0f;
+    r.w = (v1.w + v2.w + v3.w) / 3.0f;
+    if (hi) store_planes4(hi, lo, i, r);
+    if (out_f32) reinterpret_cast<float4*>(out_f32)[i] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- softmax / CE / argmax
+__device__ float block_reduce_sum(float v, float* sh) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += sh[i];
+  return r;
+}
+__device__ float block_reduce_max(float v, float* sh) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = -INFINITY;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r = fmaxf(r, sh[i]);
+  return r;
+}
+
+// one block per (image, joint); logits [B, S, K]
+__global__ void spatial_softmax_kernel(const float* __restrict__ logits, int S, int K, float* __restrict__ out) {
+  __shared__ float sh[32];
+  const int n = blockIdx.x / K, k = blockIdx.x % K;
+  const float* src = logits + (long)n * S * K + k;
+  float* dst = out + (long)n * S * K + k;
+  float m = -INFINITY;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) m = fmaxf(m, src[(long)s * K]);
+  m = block_reduce_max(m, sh);
+  float sum = 0.f;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) sum += expf(src[(long)s * K] - m);
+  sum = block_reduce_sum(sum, sh);
+  const float inv = 1.0f / sum;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) dst[(long)s * K] = expf(src[(long)s * K] - m) * inv;
+}
+
+// labels [B, S, KL] (first K channels used). per_nk[n*K+k] = lse * sum(y) - sum(y * x); lse_out optional (for backward)
+__global__ void softmax_ce_kernel(const float* __restrict__ logits, const float* __restrict__ labels, int S, int K, int KL,
+                                  float* __restrict__ per_nk, float* __restrict__ lse_out) {
+  __shared__ float sh[32];
+  const int n = blockIdx.x / K, k = blockIdx.x % K;
+  const float* src = logits + (long)n * S * K + k;
+  const float* lab = labels + (long)n * S * KL + k;
+  float m = -INFINITY;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) m = fmaxf(m, src[(long)s * K]);
+  m = block_reduce_max(m, sh);
+  float sum = 0.f, sy = 0.f, syx = 0.f;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const float xv = src[(long)s * K];
+    const float yv = lab[(long)s * KL];
+    sum += expf(xv - m);
+    sy += yv;
+    syx += yv * xv;
+  }
+  sum = block_reduce_sum(sum, sh);
+  sy = block_reduce_sum(sy, sh);
+  syx = block_reduce_sum(syx, sh);
+  if (threadIdx.x == 0) {
+    const float lse = m + logf(sum);
+    per_nk[blockIdx.x] = lse * sy - syx;
+    if (lse_out) lse_out[blockIdx.x] = lse;
+  }
+}
+
+__global__ void mean_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
+  __shared__ float sh[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)v[i];
+  float r = block_reduce_sum((float)acc, sh);
+  if (threadIdx.x == 0) out[0] = r / (float)n;
+}
+
+// first maximal index in row-major order -> (row, col); out [B, 2, K] int32
+__global__ void argmax_hw_kernel(const float* __restrict__ hm, int S, int W, int K, int* __restrict__ out) {
+  __shared__ float shv[32];
+  __shared__ int shi[32];
+  const int n = blockIdx.x / K, k = blockIdx.x % K;
+  const float* src = hm + (long)n * S * K + k;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const float v = src[(long)s * K];
+    if (v > bv || (v == bv && s < bi)) { bv = v; bi = s; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { shv[threadIdx.x >> 5] = bv; shi[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i)
+      if (shv[i] > bv || (shv[i] == bv && shi[i] < bi)) { bv = shv[i]; bi = shi[i]; }
+    const int row = bi / W;
+    out[((long)n * 2 + 0) * K + k] = row;
+    out[((long)n * 2 + 1) * K + k] = bi - row * W;
+  }
+}
+
+inline int grid_for(long total, int threads) {
+  long g = (total + threads - 1) / threads;
+  long cap = (long)jcm_num_sms() * 16;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" int jcm_bn_stats_blocks(long M, int C) {
+  (void)C;
+  long b = M / 64;
+  if (b < 1) b = 1;
+  long cap = (long)jcm_num_sms() * 4;
+  return (int)(b < cap ? b : cap);
+}
+
+// partial: caller-owned workspace of jcm_bn_stats_blocks(M,C) * 2 * C floats
+extern "C" int jcm_bn_stats(const float* x, long M, int C, float* partial, void* stream) {
+  JCM_CHECK_ARG(x && partial && M > 0 && C > 0, "jcm_bn_stats: bad arguments");
+  const int blocks = jcm_bn_stats_blocks(M, C);
+  if ((C % 4) == 0 && C / 4 <= kStatThreads) {
+    bn_stats_kernel<4><<<blocks, kStatThreads, kStatThreads * 8 * sizeof(float), (cudaStream_t)stream>>>(x, M, C, partial);
+  } else {
+    JCM_CHECK_ARG(C <= kStatThreads, "jcm_bn_stats: C=%d not supported (must be a multiple of 4 <= 1024, or <= 256)", C);
+    bn_stats_kernel<1><<<blocks, kStatThreads, kStatThreads * 2 * sizeof(float), (cudaStream_t)stream>>>(x, M, C, partial);
+  }
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}
+
+extern "C" int jcm_bn_finalize(const float* partial, long M, int C, const float* gamma, const float* beta, float* moving_mean,
+                               float* moving_var, float eps, float decay, int train, int update_moving, float* scale,
+                               float* shift, float* save_mean, float* save_rstd, void* stream) {
+  JCM_CHECK_ARG(gamma && beta && moving_mean && moving_var && scale && shift, "jcm_bn_finalize: null pointer");
+  JCM_CHECK_ARG(!train || partial, "jcm_bn_finalize: training mode needs the partial sums");
+  const int nblocks = train ? jcm_bn_stats_blocks(M, C) : 0;
+  bn_finalize_kernel<<<jcm_cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(partial, nblocks, M, C, gamma, beta, moving_mean, moving_var, eps,
+                                                                         decay, train, update_moving, scale, shift, save_mean, save_rstd);
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}
+
+extern "C" int jcm_bn_apply_pool(const float* a, const float* scale, const float* shift, int B, int H, int W, int C, int pool,
+                                 void* out_hi, void* out_lo, float* out_f32, void* stream) {
+  JCM_CHECK_ARG(a && scale && shift && (out_hi || out_f32), "jcm_bn_apply_pool: null pointer");
+  JCM_CHECK_ARG((C % 4) == 0, "jcm_bn_apply_pool: C must be a multiple of 4, got %d", C);
+  const int Ho = pool ? (H + 1) / 2 : H, Wo = pool ? (W + 1) / 2 : W;
+  const long total = (long)B * Ho * Wo * (C / 4);
+  bn_apply_pool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a, scale, shift, B, H, W, C, pool, (__nv_bfloat16*)out_hi,
+                                                                               (__nv_bfloat16*)out_lo, out_f32);
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}
+
+extern "C" int jcm_upsample_avg3(const float* a1, const float* a2, const float* a3, const float* scale_shift, int B, int H, int W,
+                                 int H2, int W2, int H3, int W3, int C, void* out_hi, void* out_lo, float* out_f32, void* stream) {
+  JCM_CHECK_ARG(a1 && a2 && a3 && scale_shift && (out_hi || out_f32), "jcm_upsample_avg3: null pointer");
+  JCM_CHECK_ARG((C % 4) == 0, "jcm_upsample_avg3: C must be a multiple of 4, got %d", C);
+  const long total = (long)B * H * W * (C / 4);
+  upsample_avg3_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a1, a2, a3, scale_shift, B, H, W, H2, W2, H3, W3, C,
+                                                                               (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32);
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}
+
+extern "C" int jcm_spatial_softmax(const float* logits, int B, int S, int K, float* out, void* stream) {
+  JCM_CHECK_ARG(logits && out && B > 0 && S > 0 && K > 0, "jcm_spatial_softmax: bad arguments");
+  spatial_softmax_kernel<<<B * K, 256, 0, (cudaStream_t)stream>>>(logits, S, K, out);
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}
+
+extern "C" int jcm_softmax_ce(const float* logits, const float* labels, int B, int S, int K, int KL, float* per_nk, float* lse,
+                              float* loss, void* stream) {
+  JCM_CHECK_ARG(logits && labels && per_nk && loss && KL >= K, "jcm_softmax_ce: bad arguments");
+  softmax_ce_kernel<<<B * K, 256, 0, (cudaStream_t)stream>>>(logits, labels, S, K, KL, per_nk, lse);
+  JCM_LAUNCH_CHECK();
+  mean_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(per_nk, B * K, loss);
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}
+
+extern "C" int jcm_argmax_hw(const float* hm, int B, int H, int W, int K, int* out, void* stream) {
+  JCM_CHECK_ARG(hm && out && B > 0 && H > 0 && W > 0 && K > 0, "jcm_argmax_hw: bad arguments");
+  argmax_hw_kernel<<<B * K, 256, 0, (cudaStream_t)stream>>>(hm, H * W, W, K, out);
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}

@@ -1,0 +1,158 @@
+// Operand preparation for the tcgen05 convolution kernel (HBM-bound, coalesced/vectorised):
+//   * jcm_prep_input      x fp32 NHWC [B,H,W,3] -> three space-to-depth bf16 operand tensors (full, 1/2, 1/4 bank).
+//                         Folds the reference's `tf.image.resize_images(x, [H/2,W/2])` / `[H/4,W/4]`
+//                         (main.py:51,60; legacy bilinear at integer factors == exact strided sub-sampling, SURVEY
+//                         Appendix B) into the gather, and turns the 5x5 stride-2 SAME conv1 (main.py:44,52,61;
+//                         TF pads 1 before / 2 after) into a 3x3 stride-1 conv over 16 channels (12 used).
+//   * jcm_pack_weights    HWIO fp32 -> [tap][Cout_pad][Cin_pad] bf16 hi/lo (K-major B operand); optional
+//                         flip+transpose for the data-gradient convolution.
+//   * jcm_pack_weights_s2d  the conv1 weights [5,5,3,C] -> [9][C][16] matching jcm_prep_input's channel order.
+//   * jcm_split_planes    fp32 -> bf16 hi (+ lo) element-wise.
+#include "common.cuh"
+
+namespace {
+
+__global__ void prep_input_kernel(const float* __restrict__ x, int B, int H, int W, int step,
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const int Ho = H / (2 * step), Wo = W / (2 * step);
+  const long total = (long)B * Ho * Wo;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int X = (int)(i % Wo);
+    const long t = i / Wo;
+    const int Y = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    __align__(16) __nv_bfloat16 vh[16];
+    __align__(16) __nv_bfloat16 vl[16];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int sy = s >> 1, sx = s & 1;
+      const float* px = x + (((long)n * H + (long)step * (2 * Y + sy)) * W + (long)step * (2 * X + sx)) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) split_bf16(px[c], vh[s * 3 + c], vl[s * 3 + c]);
+    }
+#pragma unroll
+    for (int c = 12; c < 16; ++c) { vh[c] = __float2bfloat16_rn(0.f); vl[c] = vh[c]; }
+    uint4* dh = reinterpret_cast<uint4*>(hi + i * 16);
+    dh[0] = reinterpret_cast<uint4*>(vh)[0];
+    dh[1] = reinterpret_cast<uint4*>(vh)[1];
+    if (lo) {
+      uint4* dl = reinterpret_cast<uint4*>(lo + i * 16);
+      dl[0] = reinterpret_cast<uint4*>(vl)[0];
+      dl[1] = reinterpret_cast<uint4*>(vl)[1];
+    }
+  }
+}
+
+// out[tap][o][i] (o < Opad, i < Ipad), zero padded.
+//   transpose == 0 (forward):  o = cout, i = cin,  value = W[tap][cin][cout]
+//   transpose == 1 (dgrad):    o = cin,  i = cout, value = W[k*k-1-tap][cin][cout]
+__global__ void pack_weights_kernel(const float* __restrict__ w, int taps, int Cin, int Cout, int Opad, int Ipad,
+                                    int transpose, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const long total = (long)taps * Opad * Ipad;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % Ipad);
+    const long t = idx / Ipad;
+    const int o = (int)(t % Opad);
+    const int tap = (int)(t / Opad);
+    float v = 0.f;
+    if (!transpose) {
+      if (o < Cout && i < Cin) v = w[((long)tap * Cin + i) * Cout + o];
+    } else {
+      if (o < Cin && i < Cout) v = w[((long)(taps - 1 - tap) * Cin + o) * Cout + i];
+    }
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[idx] = h;
+    if (lo) lo[idx] = l;
+  }
+}
+
+// conv1: w [5][5][3][Cout] -> out [3x3][Cout][16];  tap t in 0..4 -> block tap (t+1)/2, sub position (t+1)&1
+// (input row = 2*o - 1 + t under TF SAME padding (1 before, 2 after), see prep_input_kernel's channel order).
+__global__ void pack_weights_s2d_kernel(const float* __restrict__ w, int Cout, __nv_bfloat16* __restrict__ hi,
+                                        __nv_bfloat16* __restrict__ lo) {
+  const int total = 9 * Cout * 16;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int ch = idx & 15;
+    const int co = (idx >> 4) % Cout;
+    const int tap = (idx >> 4) / Cout;
+    const int by = tap / 3, bx = tap % 3;
+    float v = 0.f;
+    if (ch < 12) {
+      const int s = ch / 3, ci = ch % 3;
+      const int sy = s >> 1, sx = s & 1;
+      const int ty = 2 * by + sy - 1, tx = 2 * bx + sx - 1;  // original 5x5 tap
+      if (ty >= 0 && ty < 5 && tx >= 0 && tx < 5) v = w[((ty * 5 + tx) * 3 + ci) * Cout + co];
+    }
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[idx] = h;
+    if (lo) lo[idx] = l;
+  }
+}
+
+__global__ void split_planes_kernel(const float* __restrict__ x, long n4, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    __align__(8) __nv_bfloat16 h[4];
+    __align__(8) __nv_bfloat16 l[4];
+    split_bf16(v.x, h[0], l[0]);
+    split_bf16(v.y, h[1], l[1]);
+    split_bf16(v.z, h[2], l[2]);
+    split_bf16(v.w, h[3], l[3]);
+    reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<uint2*>(h);
+    if (lo) reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
+  }
+}
+
+inline int grid_for(long total, int threads) {
+  long g = (total + threads - 1) / threads;
+  long cap = (long)jcm_num_sms() * 16;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" int jcm_prep_input(const float* x, int B, int H, int W, void* full_hi, void* full_lo, void* half_hi,
+                              void* half_lo, void* quarter_hi, void* quarter_lo, void* stream) {
+  JCM_CHECK_ARG(x && full_hi && half_hi && quarter_hi, "jcm_prep_input: null pointer");
+  JCM_CHECK_ARG(B > 0 && H > 0 && W > 0 && (H % 8) == 0 && (W % 8) == 0, "jcm_prep_input: H and W must be multiples of 8 (got %d x %d)", H, W);
+  void* hi[3] = {full_hi, half_hi, quarter_hi};
+  void* lo[3] = {full_lo, half_lo, quarter_lo};
+  for (int b = 0; b < 3; ++b) {
+    const int step = 1 << b;
+    const long total = (long)B * (H / (2 * step)) * (W / (2 * step));
+    prep_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, step, (__nv_bfloat16*)hi[b],
+                                                                              (__nv_bfloat16*)lo[b]);
+    JCM_LAUNCH_CHECK();
+  }
+  return JCM_OK;
+}
+
+extern "C" int jcm_pack_weights(const float* w, int ksize, int Cin, int Cout, int Opad, int Ipad, int transpose,
+                                void* out_hi, void* out_lo, void* stream) {
+  JCM_CHECK_ARG(w && out_hi, "jcm_pack_weights: null pointer");
+  const int O = transpose ? Cin : Cout, I = transpose ? Cout : Cin;
+  JCM_CHECK_ARG(Opad >= O && Ipad >= I, "jcm_pack_weights: padded dims (%d,%d) smaller than (%d,%d)", Opad, Ipad, O, I);
+  const long total = (long)ksize * ksize * Opad * Ipad;
+  pack_weights_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, ksize * ksize, Cin, Cout, Opad, Ipad, transpose,
+                                                                              (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}
+
+extern "C" int jcm_pack_weights_s2d(const float* w, int Cout, void* out_hi, void* out_lo, void* stream) {
+  JCM_CHECK_ARG(w && out_hi && Cout > 0, "jcm_pack_weights_s2d: bad arguments");
+  pack_weights_s2d_kernel<<<grid_for(9L * Cout * 16, 256), 256, 0, (cudaStream_t)stream>>>(w, Cout, (__nv_bfloat16*)out_hi,
+                                                                                            (__nv_bfloat16*)out_lo);
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}
+
+extern "C" int jcm_split_planes(const float* x, long n, void* hi, void* lo, void* stream) {
+  JCM_CHECK_ARG(x && hi && n > 0 && (n % 4) == 0, "jcm_split_planes: n must be a positive multiple of 4");
+  split_planes_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, n / 4, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}

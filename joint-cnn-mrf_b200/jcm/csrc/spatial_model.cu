@@ -1,0 +1,412 @@
+// Fully-connected MRF "spatial model" forward (reference main.py:77-125), FP32 on the CUDA cores (FFMA2), sm_100a.
+//
+//   out[n,:,:,i] = log(sp(h_i)+d) + sum_{j != i, ascending} log( resize_61x91->60x90( conv_valid(sp(E_ij), sp(h_j)) ) + sp(b_ij) + d )
+//   h = BN_bn_sm(heat_map),  sp(x) = softplus(5x)/5,  d = 1e-6
+//
+// `conv_mrf` (main.py:77-91: transpose + reverse + conv2d VALID + resize_images) is, per (pair, image), the true 2-D
+// 'valid' convolution  C[y,x] = sum_{u<H, v<W} P[y+u, x+v] * Lf[u,v],  P = sp(E_ij) [2H,2W],  Lf[u,v] = sp(h_j)[H-1-u, W-1-v],
+// y in [0,H], x in [0,W]  ->  (H+1)(W+1)HW = 29.98 M MAC for 60x90.  The reference runs K^2 of these as separate
+// conv2d nodes; here all pairs x images run in ONE persistent kernel (sm_conv_kernel):
+//
+//   * task = (pair, group of 4 images, slice of 32 output "strips"); a strip = 7 consecutive x of one output row.
+//     One warp owns one task per pass: each lane keeps 7 x 4 fp32 accumulators as 14 packed f32x2 registers and
+//     slides a 7-wide register window of P along v (one scalar LDS per step), multiplying by the 4 images'
+//     likelihood values fetched with one broadcast LDS.128:  14 FFMA2 (= 28 FMA/lane) per 2 shared-memory loads,
+//     so the FMA pipe, not issue or shared memory, is the limiter.
+//   * the whole prior P (softplus applied while staging) lives in shared memory (row stride chosen so a warp's
+//     32 strips hit 32 different banks); likelihood rows stream through a cp.async double buffer.
+//   * the task list is cut into equal contiguous ranges, one per SM (persistent CTAs, 20 warps = 5 per SM
+//     sub-partition), so quantisation loss is at the granularity of 4 warp-tasks, not of whole pairs.
+//   * sm_prep_kernel applies BN + softplus to the K+1 heat maps once and writes them flipped and image-interleaved
+//     ([cond][group][u][v][4]); sm_finish_kernel does resize + softplus(bias) + delta + log + the ordered sum over j
+//     + the unary term (deterministic: no atomics anywhere).
+#include "common.cuh"
+
+namespace {
+
+constexpr int TX = 7;          // strip width (x positions per lane)
+constexpr int NI = 4;          // images per task
+constexpr int NW = 20;         // warps per CTA
+constexpr int URC = 4;         // likelihood rows per staged chunk
+constexpr float kDelta = 1e-6f;
+
+struct SmDims {
+  int B, H, W, K;      // K predicted joints, K+1 heat-map channels
+  int P;               // number of (target, cond) pairs
+  int G;               // image groups = ceil(B / 4)
+  int Hp, Wp;          // H padded to URC, W padded to TX
+  int XG, tiles, NS;   // strips per output row, strips per image, slices (32 strips) per image
+  int pstride, prows;  // shared-memory layout of the prior
+  int raw;             // 1: operands are used as given (conv_mrf entry point), 0: BN + softplus applied while staging
+};
+
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---------------------------------------------------------------------------------------------- prep
+// Lt[j][g][u][v][e] = sp(scale_j * hm[4g+e, H-1-u, W-1-v, j] + shift_j)   (0 in the padding and for images >= B)
+__global__ void sm_prep_kernel(const float* __restrict__ hm, const float* __restrict__ scale, const float* __restrict__ shift,
+                               SmDims d, float* __restrict__ Lt) {
+  const int KC = d.K + 1;
+  const long total = (long)KC * d.G * d.Hp * d.Wp;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % d.Wp);
+    long t = i / d.Wp;
+    const int u = (int)(t % d.Hp);
+    t /= d.Hp;
+    const int g = (int)(t % d.G);
+    const int j = (int)(t / d.G);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (u < d.H && v < d.W) {
+      const int p = d.H - 1 - u, q = d.W - 1 - v;
+      float r[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int n = 4 * g + e;
+        if (n < d.B) {
+          const float hv = hm[(((long)n * d.H + p) * d.W + q) * KC + j];
+          r[e] = d.raw ? hv : softplus5(fmaf(hv, scale[j], shift[j]));
+        } else {
+          r[e] = 0.f;
+        }
+      }
+      o = make_float4(r[0], r[1], r[2], r[3]);
+    }
+    reinterpret_cast<float4*>(Lt)[i] = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- main kernel
+__global__ void __launch_bounds__(NW * 32, 1)
+sm_conv_kernel(const float* __restrict__ energies /*[P][2H][2W]*/, const float* __restrict__ Lt, const int* __restrict__ pair_cond,
+               SmDims d, float* __restrict__ Cb /*[P][4G][H+1][W+1]*/) {
+  extern __shared__ __align__(16) float smem[];
+  float* Ps = smem;                                   // [prows][pstride]
+  float* Ls = smem + (((size_t)d.prows * d.pstride + 3) & ~(size_t)3);  // [2 buffers][2 groups][URC][Wp][4]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lgroup = URC * d.Wp * 4;                  // floats per (group, chunk)
+  const int lbuf = 2 * lgroup;
+
+  const long tasks_per_pair = (long)d.G * d.NS;
+  const long T = (long)d.P * tasks_per_pair;
+  long t = (long)blockIdx.x * T / gridDim.x;
+  const long t_end = (long)(blockIdx.x + 1) * T / gridDim.x;
+
+  while (t < t_end) {
+    const int pair = (int)(t / tasks_per_pair);
+    const long pair_base = (long)pair * tasks_per_pair;
+    const long seg_end = min(t_end, pair_base + tasks_per_pair);
+    const int j = pair_cond[pair];
+
+    // ---- stage the prior: Ps = softplus(E_pair), zero padding (rows >= 2H, columns >= 2W)
+    __syncthreads();
+    {
+      const float* E = energies + (long)pair * (2 * d.H) * (2 * d.W);
+      const int n = d.prows * d.pstride;
+      for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        const int r = idx / d.pstride, c = idx - r * d.pstride;
+        float pv = 0.f;
+        if (r < 2 * d.H && c < 2 * d.W) {
+          pv = E[(long)r * (2 * d.W) + c];
+          if (!d.raw) pv = softplus5(pv);
+        }
+        Ps[idx] = pv;
+      }
+    }
+    __syncthreads();
+
+    while (t < seg_end) {
+      const int g_lo = (int)((t - pair_base) / d.NS);
+      // a pass covers at most NW tasks and at most two image groups (that is what the likelihood buffers hold)
+      const long pass_end = min(min(seg_end, t + NW), pair_base + (long)(g_lo + 2) * d.NS);
+      const long mytask = t + warp;
+      const bool active = mytask < pass_end;
+      const int g_hi = (int)((pass_end - 1 - pair_base) / d.NS);
+      const int ng = g_hi - g_lo + 1;  // 1 or 2
+      const long rel = (active ? mytask : t) - pair_base;
+      const int g = (int)(rel / d.NS);
+      const int slice = (int)(rel - (long)g * d.NS);
+      int tile = slice * 32 + lane;
+      const bool lane_valid = active && tile < d.tiles;
+      if (tile >= d.tiles) tile = 0;
+      const int y = tile / d.XG, x0 = (tile - y * d.XG) * TX;
+      const int gsel = g - g_lo;
+
+      unsigned long long acc[TX][2];
+#pragma unroll
+      for (int k = 0; k < TX; ++k) { acc[k][0] = 0ull; acc[k][1] = 0ull; }
+
+      const int nchunks = d.Hp / URC;
+      auto stage = [&](int c, int buf) {
+        // copy ng x (URC x Wp x 4 floats) contiguous runs
+        const int per_group16 = lgroup / 4;  // 16-byte packets per group
+        for (int idx = threadIdx.x; idx < ng * per_group16; idx += blockDim.x) {
+          const int gg = idx / per_group16, o = idx - gg * per_group16;
+          const float* src = Lt + ((((long)j * d.G + (g_lo + gg)) * d.Hp + (long)c * URC) * d.Wp) * 4 + (long)o * 4;
+          cp_async16(smem_u32(Ls + buf * lbuf + gg * lgroup + o * 4), src);
+        }
+        cp_async_commit();
+      };
+
+      stage(0, 0);
+      for (int c = 0; c < nchunks; ++c) {
+        if (c + 1 < nchunks) {
+          stage(c + 1, (c + 1) & 1);
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (active) {
+          const float* lbase = Ls + (c & 1) * lbuf + gsel * lgroup;
+#pragma unroll 1
+          for (int ul = 0; ul < URC; ++ul) {
+            const int u = c * URC + ul;
+            const float* prow = Ps + (y + u) * d.pstride + x0;
+            const ulonglong2* lrow = reinterpret_cast<const ulonglong2*>(lbase + ul * d.Wp * 4);
+            unsigned long long win[TX];
+#pragma unroll
+            for (int k = 0; k < TX - 1; ++k) { const float pv = prow[k]; win[k] = pack2(pv, pv); }
+#pragma unroll 1
+            for (int vb = 0; vb < d.Wp; vb += TX) {
+#pragma unroll
+              for (int s = 0; s < TX; ++s) {
+                const float pn = prow[vb + s + TX - 1];
+                win[(s + TX - 1) % TX] = pack2(pn, pn);
+                const ulonglong2 l = lrow[vb + s];
+#pragma unroll
+                for (int k = 0; k < TX; ++k) {
+                  ffma2(acc[k][0], win[(s + k) % TX], l.x);
+                  ffma2(acc[k][1], win[(s + k) % TX], l.y);
+                }
+              }
+            }
+          }
+        }
+        __syncthreads();
+      }
+
+      if (lane_valid) {
+        const int OW = d.W + 1, OH = d.H + 1;
+#pragma unroll
+        for (int k = 0; k < TX; ++k) {
+          const int x = x0 + k;
+          if (x < OW) {
+            float a0, a1, a2, a3;
+            unpack2(acc[k][0], a0, a1);
+            unpack2(acc[k][1], a2, a3);
+            float* o = Cb + (((long)pair * (4 * d.G) + 4 * g) * OH + y) * OW + x;
+            const long istr = (long)OH * OW;
+            o[0] = a0;
+            o[istr] = a1;
+            o[2 * istr] = a2;
+            o[3 * istr] = a3;
+          }
+        }
+      }
+      t = pass_end;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- finish
+__device__ __forceinline__ void legacy_tap(int dst, int n_in, int n_out, int& lo, int& hi, float& w) {
+  const float scale = (float)n_in / (float)n_out;
+  const float src = (float)dst * scale;
+  lo = (int)floorf(src);
+  hi = min(lo + 1, n_in - 1);
+  w = src - (float)lo;
+}
+
+// out[n,y,x,i] = log(sp(bn(hm[n,y,x,i])) + d) + sum over pairs with target i (in list order) log(resize(C) + sp(b) + d)
+__global__ void sm_finish_kernel(const float* __restrict__ hm, const float* __restrict__ scale, const float* __restrict__ shift,
+                                 const float* __restrict__ Cb, const float* __restrict__ biases /*[P][H][W]*/,
+                                 const int* __restrict__ pair_target, SmDims d, float* __restrict__ out) {
+  const long total = (long)d.B * d.H * d.W * d.K;
+  const int KC = d.K + 1, OH = d.H + 1, OW = d.W + 1;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % d.K);
+    long t = idx / d.K;
+    const int x = (int)(t % d.W);
+    t /= d.W;
+    const int y = (int)(t % d.H);
+    const int n = (int)(t / d.H);
+    int ylo, yhi, xlo, xhi;
+    float wy, wx;
+    legacy_tap(y, OH, d.H, ylo, yhi, wy);
+    legacy_tap(x, OW, d.W, xlo, xhi, wx);
+    const float h = fmaf(hm[(((long)n * d.H + y) * d.W + x) * KC + i], scale[i], shift[i]);
+    float m = logf(softplus5(h) + kDelta);
+    for (int p = 0; p < d.P; ++p) {
+      if (pair_target[p] != i) continue;
+      const float* C = Cb + ((long)p * (4 * d.G) + n) * OH * OW;
+      const float tl = C[ylo * OW + xlo], tr = C[ylo * OW + xhi];
+      const float bl = C[yhi * OW + xlo], br = C[yhi * OW + xhi];
+      const float top = tl + (tr - tl) * wx;
+      const float bot = bl + (br - bl) * wx;
+      const float val = top + (bot - top) * wy;
+      m += logf(val + softplus5(biases[((long)p * d.H + y) * d.W + x]) + kDelta);
+    }
+    out[idx] = m;
+  }
+}
+
+// out[n,y,x] = legacy-bilinear resize of C[n] (H+1 x W+1) to H x W   (conv_mrf's tf.image.resize_images, main.py:89)
+__global__ void sm_resize_kernel(const float* __restrict__ Cb, SmDims d, float* __restrict__ out) {
+  const long total = (long)d.B * d.H * d.W;
+  const int OH = d.H + 1, OW = d.W + 1;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % d.W);
+    long t = idx / d.W;
+    const int y = (int)(t % d.H);
+    const int n = (int)(t / d.H);
+    int ylo, yhi, xlo, xhi;
+    float wy, wx;
+    legacy_tap(y, OH, d.H, ylo, yhi, wy);
+    legacy_tap(x, OW, d.W, xlo, xhi, wx);
+    const float* C = Cb + (long)n * OH * OW;
+    const float tl = C[ylo * OW + xlo], tr = C[ylo * OW + xhi];
+    const float bl = C[yhi * OW + xlo], br = C[yhi * OW + xhi];
+    const float top = tl + (tr - tl) * wx;
+    const float bot = bl + (br - bl) * wx;
+    out[idx] = top + (bot - top) * wy;
+  }
+}
+
+int fill_dims(SmDims& d, int B, int H, int W, int K, int P) {
+  d.raw = 0;
+  d.B = B; d.H = H; d.W = W; d.K = K; d.P = P;
+  d.G = jcm_cdiv(B, NI);
+  d.Hp = jcm_cdiv(H, URC) * URC;
+  d.Wp = jcm_cdiv(W, TX) * TX;
+  d.XG = jcm_cdiv(W + 1, TX);
+  d.tiles = (H + 1) * d.XG;
+  d.NS = jcm_cdiv(d.tiles, 32);
+  // prior rows read: y + u <= H + Hp - 1;   columns read: x0 + (TX-1) + v <= XG*TX - 1 + Wp - 1
+  d.prows = H + d.Hp;
+  if (d.prows < 2 * H) d.prows = 2 * H;
+  int need = d.XG * TX + d.Wp - 1;
+  if (need < 2 * W) need = 2 * W;
+  // bank-conflict-free: a warp's 32 consecutive strips (y*XG + xg) must map to addresses == 7*strip (mod 32)
+  const int want = (TX * d.XG) % 32;
+  int ps = need;
+  while (ps % 32 != want) ++ps;
+  d.pstride = ps;
+  return 0;
+}
+
+size_t sm_smem_bytes(const SmDims& d) {
+  return ((((size_t)d.prows * d.pstride + 3) & ~(size_t)3) + (size_t)2 * 2 * URC * d.Wp * 4) * sizeof(float);
+}
+
+}  // namespace
+
+// Workspace (floats): Lt = (K+1)*G*Hp*Wp*4, Cb = P*4G*(H+1)*(W+1)
+extern "C" long jcm_spatial_model_workspace(int B, int H, int W, int K, int P) {
+  SmDims d;
+  fill_dims(d, B, H, W, K, P);
+  const long lt = (long)(K + 1) * d.G * d.Hp * d.Wp * 4;
+  const long cb = (long)P * 4 * d.G * (H + 1) * (W + 1);
+  return (lt + cb) * (long)sizeof(float) + 16;
+}
+
+// heat_map [B,H,W,K+1] fp32 (already concatenated: K part-detector maps + conditioning channel), bn_scale/bn_shift [K+1]
+// (from jcm_bn_finalize), energies [P][2H][2W], biases [P][H][W], pair_target/pair_cond [P] int32 (device), sorted by
+// (target, cond) = the reference's summation order.  out [B,H,W,K].  cbuf_out (optional) receives the address of the raw
+// (H+1)x(W+1) convolution results inside the workspace (kept for the backward pass).
+extern "C" int jcm_spatial_model_fwd(const float* heat_map, const float* bn_scale, const float* bn_shift, const float* energies,
+                                     const float* biases, const int* pair_target, const int* pair_cond, float* out,
+                                     void* workspace, long workspace_bytes, int B, int H, int W, int K, int P, void* stream) {
+  JCM_CHECK_ARG(heat_map && bn_scale && bn_shift && energies && biases && pair_target && pair_cond && out && workspace,
+                "jcm_spatial_model_fwd: null pointer");
+  JCM_CHECK_ARG(B > 0 && H > 1 && W > 1 && K > 0 && P > 0, "jcm_spatial_model_fwd: bad shape");
+  SmDims d;
+  fill_dims(d, B, H, W, K, P);
+  if (workspace_bytes < jcm_spatial_model_workspace(B, H, W, K, P)) {
+    jcm_set_error("jcm_spatial_model_fwd: workspace too small (%ld < %ld bytes)", workspace_bytes,
+                  jcm_spatial_model_workspace(B, H, W, K, P));
+    return JCM_EWORKSPACE;
+  }
+  const size_t smem = sm_smem_bytes(d);
+  if (smem > 227 * 1024) {
+    jcm_set_error("jcm_spatial_model_fwd: heat-map size %dx%d not supported by this build (needs %zu B shared memory)", H, W, smem);
+    return JCM_ENOTSUP;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* Lt = (float*)workspace;
+  float* Cb = Lt + (long)(K + 1) * d.G * d.Hp * d.Wp * 4;
+
+  {
+    const long total = (long)(K + 1) * d.G * d.Hp * d.Wp;
+    int grid = (int)((total + 255) / 256);
+    sm_prep_kernel<<<grid, 256, 0, st>>>(heat_map, bn_scale, bn_shift, d, Lt);
+    JCM_LAUNCH_CHECK();
+  }
+  {
+    JCM_CUDA(cudaFuncSetAttribute(sm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
+    const long T = (long)P * d.G * d.NS;
+    long grid = jcm_num_sms();
+    if (grid > (T + NW - 1) / NW) grid = (T + NW - 1) / NW;
+    sm_conv_kernel<<<(int)grid, NW * 32, smem, st>>>(energies, Lt, pair_cond, d, Cb);
+    JCM_LAUNCH_CHECK();
+  }
+  {
+    const long total = (long)B * H * W * K;
+    int grid = (int)((total + 255) / 256);
+    sm_finish_kernel<<<grid, 256, 0, st>>>(heat_map, bn_scale, bn_shift, Cb, biases, pair_target, d, out);
+    JCM_LAUNCH_CHECK();
+  }
+  return JCM_OK;
+}
+
+// conv_mrf(A, B), main.py:77-91, on its own: A [2H,2W] prior, Bmaps [b,H,W] likelihoods (both used as given, the reference
+// applies softplus before the call) -> out [b,H,W] = resize(conv_valid(A, B_n)).  Workspace: jcm_spatial_model_workspace(b,H,W,0,1).
+extern "C" int jcm_conv_mrf_fwd(const float* A, const float* Bmaps, float* out, void* workspace, long workspace_bytes, int b, int H,
+                                int W, void* stream) {
+  JCM_CHECK_ARG(A && Bmaps && out && workspace && b > 0 && H > 1 && W > 1, "jcm_conv_mrf_fwd: bad arguments");
+  SmDims d;
+  fill_dims(d, b, H, W, 0, 1);
+  d.raw = 1;
+  if (workspace_bytes < jcm_spatial_model_workspace(b, H, W, 0, 1)) {
+    jcm_set_error("jcm_conv_mrf_fwd: workspace too small");
+    return JCM_EWORKSPACE;
+  }
+  const size_t smem = sm_smem_bytes(d);
+  if (smem > 227 * 1024) {
+    jcm_set_error("jcm_conv_mrf_fwd: heat-map size %dx%d not supported by this build (needs %zu B shared memory)", H, W, smem);
+    return JCM_ENOTSUP;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* Lt = (float*)workspace;
+  float* Cb = Lt + (long)d.G * d.Hp * d.Wp * 4;
+  int* zero = (int*)(Cb + (long)4 * d.G * (H + 1) * (W + 1));  // one int: cond index 0 (space reserved by the workspace query)
+  JCM_CUDA(cudaMemsetAsync(zero, 0, sizeof(int), st));
+  const long total = (long)d.G * d.Hp * d.Wp;
+  sm_prep_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(Bmaps, nullptr, nullptr, d, Lt);
+  JCM_LAUNCH_CHECK();
+  JCM_CUDA(cudaFuncSetAttribute(sm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
+  const long T = (long)d.G * d.NS;
+  long grid = jcm_num_sms();
+  if (grid > (T + NW - 1) / NW) grid = (T + NW - 1) / NW;
+  sm_conv_kernel<<<(int)grid, NW * 32, smem, st>>>(A, Lt, zero, d, Cb);
+  JCM_LAUNCH_CHECK();
+  const long tot2 = (long)b * H * W;
+  sm_resize_kernel<<<(int)((tot2 + 255) / 256), 256, 0, st>>>(Cb, d, out);
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}

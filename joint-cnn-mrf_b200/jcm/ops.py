@@ -1,0 +1,239 @@
+"""Thin torch-tensor wrappers over the C ABI (include/jcm.h).  PyTorch is only the buffer/stream provider here:
+every function checks its arguments, allocates the outputs with torch.empty on the inputs' device and launches the
+sm_100a kernels on torch's current stream.  Nothing in this file computes with torch ops."""
+import ctypes
+
+import torch
+
+from ._lib import lib, check
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+BN_EPS = 1e-3     # [TF1] tf.contrib.layers.batch_norm default (reference main.py:113,129)
+BN_DECAY = 0.9    # reference main.py:113,129
+
+
+def _ptr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t, dtype, name):
+    if t is None:
+        raise ValueError('%s is None' % name)
+    if not t.is_cuda:
+        raise ValueError('%s must be a CUDA tensor (jcm has no CPU path)' % name)
+    if t.dtype != dtype:
+        raise ValueError('%s must be %s, got %s' % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError('%s must be contiguous' % name)
+    return t
+
+
+class Planes:
+    """bf16 operand planes (hi, lo) of an NHWC activation or packed weight; lo is None in bf16 mode."""
+    __slots__ = ('hi', 'lo', 'shape')
+
+    def __init__(self, hi, lo):
+        self.hi, self.lo, self.shape = hi, lo, tuple(hi.shape)
+
+
+def _new_planes(shape, device, split):
+    hi = torch.empty(shape, dtype=BF16, device=device)
+    lo = torch.empty(shape, dtype=BF16, device=device) if split else None
+    return Planes(hi, lo)
+
+
+# ------------------------------------------------------------------------------------------------ preparation
+def prep_input(x, split):
+    """x [B,H,W,3] fp32 -> (full, half, quarter) s2d operand planes [B,H/2,W/2,16], [B,H/4,W/4,16], [B,H/8,W/8,16]."""
+    _req(x, F32, 'x')
+    B, H, W, C = x.shape
+    if C != 3:
+        raise ValueError('x must have 3 channels')
+    outs = [_new_planes((B, H // (2 * s), W // (2 * s), 16), x.device, split) for s in (1, 2, 4)]
+    check(lib().jcm_prep_input(_ptr(x), B, H, W, _ptr(outs[0].hi), _ptr(outs[0].lo), _ptr(outs[1].hi), _ptr(outs[1].lo),
+                               _ptr(outs[2].hi), _ptr(outs[2].lo), _stream()), 'jcm_prep_input')
+    return outs
+
+
+def pad16(c):
+    return (c + 15) // 16 * 16
+
+
+def pack_weights(w, split, transpose=False):
+    """HWIO fp32 [k,k,Cin,Cout] -> packed planes [k*k, Opad, Ipad]."""
+    _req(w, F32, 'w')
+    k, k2, cin, cout = w.shape
+    if k != k2:
+        raise ValueError('square kernels only')
+    o, i = (cin, cout) if transpose else (cout, cin)
+    opad = pad16(o)
+    if opad > 256:
+        opad = (opad + 255) // 256 * 256
+    ipad = pad16(i)
+    out = _new_planes((k * k, opad, ipad), w.device, split)
+    check(lib().jcm_pack_weights(_ptr(w), k, cin, cout, opad, ipad, int(transpose), _ptr(out.hi), _ptr(out.lo), _stream()),
+          'jcm_pack_weights')
+    return out
+
+
+def pack_weights_s2d(w, split):
+    """conv1 kernels [5,5,3,Cout] -> [9, Cout, 16]."""
+    _req(w, F32, 'w')
+    if tuple(w.shape[:3]) != (5, 5, 3) or w.shape[3] % 16:
+        raise ValueError('pack_weights_s2d expects [5,5,3,Cout] with Cout a multiple of 16')
+    out = _new_planes((9, w.shape[3], 16), w.device, split)
+    check(lib().jcm_pack_weights_s2d(_ptr(w), w.shape[3], _ptr(out.hi), _ptr(out.lo), _stream()), 'jcm_pack_weights_s2d')
+    return out
+
+
+def split_planes(x, split):
+    _req(x, F32, 'x')
+    out = _new_planes(tuple(x.shape), x.device, split)
+    check(lib().jcm_split_planes(_ptr(x), x.numel(), _ptr(out.hi), _ptr(out.lo), _stream()), 'jcm_split_planes')
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ part detector
+def conv2d_planes(xp, wp, bias, cout, ksize, relu, naive=False):
+    """xp activation planes [B,H,W,Cin], wp packed weight planes [k*k,Cout_pad,Cin] -> fp32 [B,H,W,cout]."""
+    B, H, W, cin = xp.shape
+    taps, cout_pad, cin_w = wp.shape
+    if cin_w != cin or taps != ksize * ksize:
+        raise ValueError('weight planes %s do not match activation planes %s (ksize %d)' % (wp.shape, xp.shape, ksize))
+    if (xp.lo is None) != (wp.lo is None):
+        raise ValueError('activation and weight planes must use the same precision mode')
+    if bias is not None:
+        _req(bias, F32, 'bias')
+    y = torch.empty((B, H, W, cout), dtype=F32, device=xp.hi.device)
+    fn = lib().jcm_debug_conv2d_naive if naive else lib().jcm_conv2d_fwd
+    check(fn(_ptr(xp.hi), _ptr(xp.lo), _ptr(wp.hi), _ptr(wp.lo), _ptr(bias), _ptr(y), B, H, W, cin, cout, cout_pad, ksize,
+             int(relu), _stream()), 'jcm_conv2d_fwd')
+    return y
+
+
+def bn_scale_shift(a, gamma, beta, moving_mean, moving_var, train, update_moving=True, save=False):
+    """Per-channel (scale, shift) of tf.contrib.layers.batch_norm for a [.., C] fp32 tensor (batch stats if train)."""
+    _req(a, F32, 'a')
+    C = a.shape[-1]
+    M = a.numel() // C
+    for t, n in ((gamma, 'gamma'), (beta, 'beta'), (moving_mean, 'moving_mean'), (moving_var, 'moving_variance')):
+        _req(t, F32, n)
+    dev = a.device
+    ss = torch.empty((2, C), dtype=F32, device=dev)
+    saved = torch.empty((2, C), dtype=F32, device=dev) if save else None
+    partial = None
+    if train:
+        nb = lib().jcm_bn_stats_blocks(M, C)
+        partial = torch.empty((nb, 2, C), dtype=F32, device=dev)
+        check(lib().jcm_bn_stats(_ptr(a), M, C, _ptr(partial), _stream()), 'jcm_bn_stats')
+    check(lib().jcm_bn_finalize(_ptr(partial), M, C, _ptr(gamma), _ptr(beta), _ptr(moving_mean), _ptr(moving_var), BN_EPS, BN_DECAY,
+                                int(train), int(update_moving), _ptr(ss[0]), _ptr(ss[1]), _ptr(saved[0] if save else None),
+                                _ptr(saved[1] if save else None), _stream()), 'jcm_bn_finalize')
+    return (ss, saved) if save else ss
+
+
+def bn_apply_pool(a, ss, pool, split, want_planes=True, want_f32=False):
+    _req(a, F32, 'a')
+    B, H, W, C = a.shape
+    Ho, Wo = ((H + 1) // 2, (W + 1) // 2) if pool else (H, W)
+    planes = _new_planes((B, Ho, Wo, C), a.device, split) if want_planes else None
+    f32 = torch.empty((B, Ho, Wo, C), dtype=F32, device=a.device) if want_f32 else None
+    check(lib().jcm_bn_apply_pool(_ptr(a), _ptr(ss[0]), _ptr(ss[1]), B, H, W, C, int(pool), _ptr(planes.hi if planes else None),
+                                  _ptr(planes.lo if planes else None), _ptr(f32), _stream()), 'jcm_bn_apply_pool')
+    if want_planes and want_f32:
+        return planes, f32
+    return planes if want_planes else f32
+
+
+def upsample_avg3(a1, a2, a3, ss6, split, want_planes=True, want_f32=False):
+    for t in (a1, a2, a3):
+        _req(t, F32, 'a')
+    _req(ss6, F32, 'scale_shift')
+    B, H, W, C = a1.shape
+    planes = _new_planes((B, H, W, C), a1.device, split) if want_planes else None
+    f32 = torch.empty((B, H, W, C), dtype=F32, device=a1.device) if want_f32 else None
+    check(lib().jcm_upsample_avg3(_ptr(a1), _ptr(a2), _ptr(a3), _ptr(ss6), B, H, W, a2.shape[1], a2.shape[2], a3.shape[1], a3.shape[2],
+                                  C, _ptr(planes.hi if planes else None), _ptr(planes.lo if planes else None), _ptr(f32), _stream()),
+          'jcm_upsample_avg3')
+    if want_planes and want_f32:
+        return planes, f32
+    return planes if want_planes else f32
+
+
+# ------------------------------------------------------------------------------------------------ heads
+def spatial_softmax(logits):
+    _req(logits, F32, 'logits')
+    B, H, W, K = logits.shape
+    out = torch.empty_like(logits)
+    check(lib().jcm_spatial_softmax(_ptr(logits), B, H * W, K, _ptr(out), _stream()), 'jcm_spatial_softmax')
+    return out
+
+
+def softmax_ce(logits, labels, want_lse=False):
+    """Returns (loss scalar tensor, per-(n,k) losses[, lse])."""
+    _req(logits, F32, 'logits')
+    _req(labels, F32, 'labels')
+    B, H, W, K = logits.shape
+    if tuple(labels.shape[:3]) != (B, H, W) or labels.shape[3] < K:
+        raise ValueError('labels %s do not match logits %s' % (tuple(labels.shape), tuple(logits.shape)))
+    per = torch.empty((B, K), dtype=F32, device=logits.device)
+    lse = torch.empty((B, K), dtype=F32, device=logits.device) if want_lse else None
+    loss = torch.empty((1,), dtype=F32, device=logits.device)
+    check(lib().jcm_softmax_ce(_ptr(logits), _ptr(labels), B, H * W, K, labels.shape[3], _ptr(per), _ptr(lse), _ptr(loss), _stream()),
+          'jcm_softmax_ce')
+    return (loss, per, lse) if want_lse else (loss, per)
+
+
+def argmax_hw(hm):
+    _req(hm, F32, 'hm')
+    B, H, W, K = hm.shape
+    out = torch.empty((B, 2, K), dtype=torch.int32, device=hm.device)
+    check(lib().jcm_argmax_hw(_ptr(hm), B, H, W, K, _ptr(out), _stream()), 'jcm_argmax_hw')
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ spatial model
+def spatial_model_fwd(heat_map, ss, energies, biases, pair_target, pair_cond, n_joints, keep_workspace=False):
+    _req(heat_map, F32, 'heat_map')
+    _req(energies, F32, 'energies')
+    _req(biases, F32, 'biases')
+    B, H, W, KC = heat_map.shape
+    P = energies.shape[0]
+    if KC != n_joints + 1:
+        raise ValueError('heat_map must have n_joints + 1 channels')
+    if tuple(energies.shape) != (P, 2 * H, 2 * W) or tuple(biases.shape) != (P, H, W):
+        raise ValueError('energies/biases shapes %s %s do not match heat maps %dx%d' % (tuple(energies.shape), tuple(biases.shape), H, W))
+    nbytes = lib().jcm_spatial_model_workspace(B, H, W, n_joints, P)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=heat_map.device)
+    out = torch.empty((B, H, W, n_joints), dtype=F32, device=heat_map.device)
+    check(lib().jcm_spatial_model_fwd(_ptr(heat_map), _ptr(ss[0]), _ptr(ss[1]), _ptr(energies), _ptr(biases), _ptr(pair_target),
+                                      _ptr(pair_cond), _ptr(out), _ptr(ws), nbytes, B, H, W, n_joints, P, _stream()),
+          'jcm_spatial_model_fwd')
+    return (out, ws) if keep_workspace else out
+
+
+def conv_mrf_fwd(A, Bm):
+    """A [2H,2W] fp32, Bm [b,H,W] fp32 -> [b,H,W]."""
+    _req(A, F32, 'A')
+    _req(Bm, F32, 'B')
+    b, H, W = Bm.shape
+    if tuple(A.shape) != (2 * H, 2 * W):
+        raise ValueError('A must be [2H,2W]')
+    nbytes = lib().jcm_spatial_model_workspace(b, H, W, 0, 1)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=A.device)
+    out = torch.empty((b, H, W), dtype=F32, device=A.device)
+    check(lib().jcm_conv_mrf_fwd(_ptr(A), _ptr(Bm), _ptr(out), _ptr(ws), nbytes, b, H, W, _stream()), 'jcm_conv_mrf_fwd')
+    return out
+
+
+def fma_peak(blocks, iters, packed):
+    """Launches the FMA loop; returns FLOPs per launch (time it with CUDA events)."""
+    scratch = torch.empty((blocks * 512,), dtype=F32, device='cuda')
+    flops = ctypes.c_double(0.0)
+    check(lib().jcm_fma_peak(_ptr(scratch), blocks, iters, int(packed), ctypes.byref(flops), _stream()), 'jcm_fma_peak')
+    return flops.value

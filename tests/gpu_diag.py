@@ -1,0 +1,276 @@
+"""GPU diagnostic script (run under gpurun): exercises every kernel against the oracle and prints per-stage errors and
+timings.  Not a pytest file - the pytest parity tests are tests/test_gpu_*.py; this one is for fast triage when a
+kernel is wrong (it localises the first diverging stage) and for quick timing sweeps.
+
+    python tests/gpu_diag.py [sections...]     sections: peak conv glue sm model time
+"""
+import os
+import sys
+import time
+import traceback
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, 'joint-cnn-mrf_b200'), os.path.join(ROOT, 'oracle')):
+    sys.path.insert(0, p)
+
+import numpy as np
+import torch
+
+import jcm
+from jcm import ops
+import jcm_oracle as orc
+
+dev = 'cuda'
+
+
+def relerr(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def timeit(fn, n=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return min(ts), float(np.median(ts))
+
+
+def sec_peak():
+    sms = jcm.lib().jcm_sm_count()
+    for packed in (0, 1):
+        fl = [0.0]
+
+        def run():
+            fl[0] = ops.fma_peak(sms * 2, 2000, packed)
+        best, med = timeit(run)
+        print('PEAK packed=%d  %.1f TFLOP/s best, %.1f median (%.3f ms)' % (packed, fl[0] / best / 1e9, fl[0] / med / 1e9, best))
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def sec_conv():
+    g = torch.Generator().manual_seed(0)
+    cases = [  # B, H, W, Cin, Cout, k
+        (1, 16, 24, 64, 64, 5), (2, 20, 33, 16, 64, 3), (1, 16, 24, 32, 32, 5), (1, 15, 23, 128, 256, 9),
+        (2, 60, 90, 64, 128, 5), (1, 30, 45, 256, 512, 9), (1, 60, 90, 128, 7, 9), (1, 9, 200, 64, 16, 3)]
+    for (B, H, W, Cin, Cout, k) in cases:
+        for split in (False, True):
+            try:
+                x = torch.randn(B, H, W, Cin, generator=g).to(dev)
+                w = (torch.randn(k, k, Cin, Cout, generator=g) / np.sqrt(k * k * Cin)).to(dev)
+                b = torch.randn(Cout, generator=g).to(dev)
+                xp = ops.split_planes(x, split)
+                wp = ops.pack_weights(w, split)
+                y = ops.conv2d_planes(xp, wp, b, Cout, k, relu=True)
+                yn = ops.conv2d_planes(xp, wp, b, Cout, k, relu=True, naive=True)
+                torch.cuda.synchronize()
+                if split:
+                    xr, wr = x.double().cpu(), w.double().cpu()
+                else:
+                    xr, wr = bf16_round(x).double().cpu(), bf16_round(w).double().cpu()
+                ref = torch.relu(orc.conv2d(xr, wr, 1) + b.double().cpu())
+                print('CONV B%d %dx%d Cin%d Cout%d k%d split=%d: tc-vs-naive %.2e  tc-vs-oracle %.2e  naive-vs-oracle %.2e' % (
+                    B, H, W, Cin, Cout, k, split, relerr(y, yn), relerr(y, ref), relerr(yn, ref)))
+            except Exception as e:
+                print('CONV case', (B, H, W, Cin, Cout, k, split), 'FAILED:', repr(e))
+                traceback.print_exc()
+    # the space-to-depth conv1
+    try:
+        for split in (False, True):
+            x = torch.rand(2, 48, 80, 3, generator=g).to(dev)
+            w = (torch.randn(5, 5, 3, 64, generator=g) / np.sqrt(75)).to(dev)
+            b = torch.randn(64, generator=g).to(dev)
+            banks = ops.prep_input(x, split)
+            wp = ops.pack_weights_s2d(w, split)
+            xd = x.double().cpu() if split else bf16_round(x).double().cpu()
+            wd = w.double().cpu() if split else bf16_round(w).double().cpu()
+            for bi, step in enumerate((1, 2, 4)):
+                y = ops.conv2d_planes(banks[bi], wp, b, 64, 3, relu=True)
+                ref = torch.relu(orc.conv2d(xd[:, ::step, ::step], wd, 2) + b.double().cpu())
+                print('CONV1 s2d bank %d split=%d: err %.2e  shape %s' % (bi, split, relerr(y, ref), tuple(y.shape)))
+    except Exception as e:
+        print('CONV1 FAILED', repr(e))
+        traceback.print_exc()
+
+
+def sec_glue():
+    g = torch.Generator().manual_seed(1)
+    for (B, H, W, C) in [(2, 45, 31, 64), (1, 15, 23, 512), (3, 10, 12, 8)]:
+        a = torch.relu(torch.randn(B, H, W, C, generator=g)).to(dev)
+        gamma = (torch.rand(C, generator=g) + 0.5).to(dev)
+        beta = torch.randn(C, generator=g).to(dev)
+        for train in (True, False):
+            mm = torch.randn(C, generator=g).to(dev) * 0.1
+            mv = (torch.rand(C, generator=g) + 0.5).to(dev)
+            bn = {'gamma': gamma.double().cpu(), 'beta': beta.double().cpu(), 'moving_mean': mm.double().cpu().clone(),
+                  'moving_variance': mv.double().cpu().clone()}
+            ref = orc.batch_norm(a.double().cpu(), bn, train)
+            ss = ops.bn_scale_shift(a, gamma, beta, mm, mv, train=train)
+            out = ops.bn_apply_pool(a, ss, False, True, want_planes=True, want_f32=True)
+            planes, f32 = out
+            rec = planes.hi.float() + planes.lo.float()
+            refp = orc.max_pool_layer(ref)
+            outp = ops.bn_apply_pool(a, ss, True, False, want_planes=False, want_f32=True)
+            print('BN %s train=%d: f32 %.2e planes %.2e pool %.2e moving_mean %.2e moving_var %.2e' % (
+                (B, H, W, C), train, relerr(f32, ref), relerr(rec, ref), relerr(outp, refp), relerr(mm, bn['moving_mean']),
+                relerr(mv, bn['moving_variance'])))
+    # upsample + average
+    B, C = 2, 64
+    a1 = torch.randn(B, 60, 90, C, generator=g).to(dev)
+    a2 = torch.randn(B, 30, 45, C, generator=g).to(dev)
+    a3 = torch.randn(B, 15, 23, C, generator=g).to(dev)
+    ss6 = torch.randn(6, C, generator=g).to(dev)
+    d = lambda t: t.double().cpu()
+    r1 = d(a1) * d(ss6[0]) + d(ss6[1])
+    r2 = orc.resize_images(d(a2) * d(ss6[2]) + d(ss6[3]), 60, 90)
+    r3 = orc.resize_images(d(a3) * d(ss6[4]) + d(ss6[5]), 60, 90)
+    ref = (r1 + r2 + r3) / 3
+    out = ops.upsample_avg3(a1, a2, a3, ss6, False, want_planes=False, want_f32=True)
+    print('UPSAMPLE_AVG3 err %.2e' % relerr(out, ref))
+    # softmax / CE / argmax
+    B, H, W, K = 3, 60, 90, 7
+    logits = (torch.randn(B, H, W, K, generator=g) * 3).to(dev)
+    labels = torch.from_numpy(orc.synthetic_labels(B, H, W, K + 1, np.random.default_rng(0))).to(dev)
+    sm = ops.spatial_softmax(logits)
+    print('SOFTMAX err %.2e' % relerr(sm, orc.spatial_softmax(d(logits))))
+    loss, per = ops.softmax_ce(logits, labels)
+    print('CE gpu %.6f oracle %.6f' % (float(loss), float(orc.softmax_cross_entropy(d(logits), d(labels)[..., :K]))))
+    am = ops.argmax_hw(sm).cpu().long()
+    print('ARGMAX equal:', bool((am == orc.get_joints_coords(d(sm))).all()))
+
+
+def make_sm_inputs(B, K, H, W, seed=0):
+    rng = np.random.default_rng(seed)
+    names = orc.JOINT_NAMES[:K] + ['torso']
+    if (H, W) == (60, 90):
+        distr = jcm.get_pairwise_distr()
+    else:
+        distr = orc.synthetic_pairwise(names, K, H, W, rng)
+    g = torch.Generator().manual_seed(seed)
+    hm = torch.softmax((3 * torch.randn(B, H * W, K, generator=g)), dim=1).reshape(B, H, W, K)
+    torso = torch.from_numpy(orc.synthetic_labels(B, H, W, 1, rng))
+    cat = torch.cat([hm, torso], dim=3).contiguous()
+    sm64 = orc.init_spatial_model(distr, K, H, W, joint_names=names)
+    # perturb so that nothing is at its symmetric init
+    for k, v in sm64.items():
+        if k.startswith('bias_'):
+            v.add_(torch.rand(v.shape, generator=g).double() * 0.01)
+        if k.startswith('bn_sm') and ('gamma' in k or 'beta' in k):
+            v.add_(torch.randn(v.shape, generator=g).double() * 0.1)
+    return names, cat, sm64
+
+
+def sec_sm():
+    for (B, K, H, W) in [(2, 7, 60, 90), (5, 7, 60, 90), (3, 4, 12, 20), (2, 9, 60, 90)]:
+        try:
+            names, cat, sm64 = make_sm_inputs(B, K, H, W)
+            for train in (False, True):
+                ref = orc.spatial_model(cat.double(), {k: v.clone() for k, v in sm64.items()}, K, train, joint_names=names)
+                smp = jcm.PairwiseParams.from_dict(sm64, names, K)
+                ctx = jcm.Context(n_joints=K, joint_names=names, flag_train=train)
+                out = jcm.spatial_model(cat.to(dev), smp, ctx)
+                torch.cuda.synchronize()
+                am_ref = orc.get_joints_coords(orc.spatial_softmax(ref))
+                am = jcm.get_joints_coords(jcm.spatial_softmax(out)).cpu()
+                print('SM B%d K%d %dx%d train=%d: err %.2e (max |ref| %.3f) argmax equal %s' % (
+                    B, K, H, W, train, relerr(out, ref), float(ref.abs().max()), bool((am == am_ref).all())))
+            # conv_mrf alone vs scipy
+            from scipy import signal
+            A = torch.rand(2 * H, 2 * W, dtype=torch.float64)
+            Bm = torch.rand(3, H, W, dtype=torch.float64)
+            got = jcm.conv_mrf(A.float().view(1, 2 * H, 2 * W, 1).to(dev), Bm.float().view(3, H, W, 1).to(dev)).cpu()
+            refc = orc.conv_mrf(A.view(1, 2 * H, 2 * W, 1), Bm.view(3, H, W, 1))
+            sc = signal.convolve2d(A.numpy(), Bm[1].numpy(), 'valid')
+            print('CONV_MRF %dx%d err vs oracle %.2e ; oracle-vs-scipy(valid conv, pre-resize row0) %.2e' % (
+                H, W, relerr(got, refc), float(np.abs(sc[0, 0] - refc[1, 0, 0, 0].item()))))
+        except Exception as e:
+            print('SM case', (B, K, H, W), 'FAILED', repr(e))
+            traceback.print_exc()
+
+
+def sec_model():
+    for (B, H, W, K, debug, precision) in [(1, 96, 160, 7, True, 'fp32'), (1, 96, 160, 7, True, 'bf16'), (1, 480, 720, 7, False, 'fp32'),
+                                           (2, 480, 720, 7, False, 'bf16')]:
+        try:
+            gen = torch.Generator().manual_seed(3)
+            p64 = orc.init_part_detector(K, gen, debug=debug)
+            for k, v in p64.items():   # non-trivial BN parameters / moving stats
+                if 'gamma' in k or 'moving_variance' in k:
+                    v.add_(torch.rand(v.shape, generator=gen).double() * 0.5)
+                if 'beta' in k or 'moving_mean' in k or 'biases' in k:
+                    v.add_(torch.randn(v.shape, generator=gen).double() * 0.1)
+            x = torch.rand(B, H, W, 3, generator=gen)
+            for train in (False, True):
+                if train and H == 480 and B == 1 and precision == 'fp32':
+                    pass
+                tap_ref, tap = {}, {}
+                t0 = time.time()
+                ref = orc.model(x.double(), {k: v.clone() for k, v in p64.items()}, K, train, tap=tap_ref)
+                t_or = time.time() - t0
+                p = jcm.load_params(p64)
+                ctx = jcm.Context(n_joints=K, flag_train=train, precision=precision, debug=debug)
+                out = jcm.model(x.to(dev), K, p, ctx, tap=tap)
+                torch.cuda.synchronize()
+                print('MODEL B%d %dx%d debug=%d %s train=%d: logits err %.2e (oracle %.1fs)' % (B, H, W, debug, precision, train, relerr(out, ref), t_or))
+                for name in sorted(tap_ref):
+                    if name in tap:
+                        print('    %-24s err %.2e' % (name, relerr(tap[name], tap_ref[name])))
+                am_ref = orc.get_joints_coords(orc.spatial_softmax(ref))
+                am = jcm.get_joints_coords(jcm.spatial_softmax(out)).cpu()
+                print('    argmax equal: %s' % bool((am == am_ref).all()))
+        except Exception as e:
+            print('MODEL case FAILED', repr(e))
+            traceback.print_exc()
+
+
+def sec_time():
+    K = 7
+    gen = torch.Generator().manual_seed(5)
+    p = jcm.init_part_detector(K, gen)
+    distr = jcm.get_pairwise_distr()
+    names = jcm.JOINT_NAMES[:K] + ['torso']
+    smp = jcm.PairwiseParams.from_distribution(distr, names, K, 60, 90)
+    for precision in ('bf16', 'fp32'):
+        for B in (4, 16):
+            ctx = jcm.Context(n_joints=K, flag_train=False, precision=precision)
+            x = torch.rand(B, 480, 720, 3, generator=gen).to(dev)
+            y = torch.from_numpy(orc.synthetic_labels(B, 60, 90, K + 1, np.random.default_rng(0))).to(dev)
+            best, med = timeit(lambda: jcm.model(x, K, p, ctx), n=3, warm=1)
+            fl = 2 * 203.718e9 * B
+            print('TIME model fwd %s B=%d: %.2f ms  %.1f img/s  %.1f TFLOP/s (algorithmic)' % (precision, B, best, B / best * 1e3, fl / best / 1e9))
+            logit = jcm.model(x, K, p, ctx)
+            hm = jcm.spatial_softmax(logit)
+            cat = torch.cat([hm, y[..., K:]], dim=3).contiguous()
+            best, med = timeit(lambda: jcm.spatial_model(cat, smp, ctx), n=5, warm=2)
+            fl = 2 * 1.469e9 * B
+            print('TIME spatial model fwd B=%d: %.3f ms  %.1f TFLOP/s (algorithmic)' % (B, best, fl / best / 1e9))
+            # single layers
+            h = ops.split_planes(torch.randn(B, 60, 90, 512, generator=gen).to(dev), ctx.split)
+            w5 = ctx.packed('conv5', p['conv5/weights'])
+            best, med = timeit(lambda: ops.conv2d_planes(h, w5, p['conv5/biases'], 512, 9, True), n=3, warm=1)
+            fl = 2 * 114.6618e9 * B
+            print('TIME conv5 %s B=%d: %.2f ms  %.1f TFLOP/s' % (precision, B, best, fl / best / 1e9))
+
+
+if __name__ == '__main__':
+    secs = sys.argv[1:] or ['peak', 'conv', 'glue', 'sm', 'model', 'time']
+    print('device:', torch.cuda.get_device_name(0), 'SMs', jcm.lib().jcm_sm_count())
+    for s in secs:
+        print('=' * 30, s)
+        try:
+            globals()['sec_' + s]()
+        except Exception as e:
+            print('SECTION', s, 'FAILED', repr(e))
+            traceback.print_exc()
+        sys.stdout.flush()
