@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Headline benchmark of the joint-cnn-mrf hot path on B200 (see BASELINE.json / SURVEY.md section 8d).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload fwd16|train64] [--impl ours|reference]
+
+One process per GPU (torchrun for N>1).  A step is one pass of the hot path over one synthetic batch:
+  * fwd16   (BASELINE configs[1]): part detector + spatial model forward (+ both softmax-CE heads), batch 16 per GPU,
+            K=7, 720x480, fp32-equivalent arithmetic (bf16x3 split products on the tensor cores), inference-mode BN.
+  * train64 (BASELINE configs[2]/[3]): joint training step fwd+bwd + gradient all-reduce + clip + Adam, batch 64 per GPU,
+            bf16 tensor-core operands with fp32 accumulation.
+Rank 0 prints ONE JSON line (contract in the task statement): value = images/s with inputs resident in HBM,
+e2e = the same through the public API with pinned-host inputs copied in and results copied out every step,
+roofline = the conv implicit-GEMM kernel's achieved algorithmic TFLOP/s against the measured bf16 peak,
+cpu_baseline = the CPU restatement of the reference graph (oracle) timed on this box's host cores.
+`--impl reference` times that CPU restatement alone (TensorFlow 1.x cannot be installed: see DESIGN.md).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, 'joint-cnn-mrf_b200'))
+
+import numpy as np
+import torch
+
+K_JOINTS = 7
+IMG_H, IMG_W = 480, 720
+HM_H, HM_W = 60, 90
+PD_FWD_FLOP = 2 * 203.718e9      # per image, SURVEY Appendix A (K=7)
+SM_FWD_FLOP = 2 * 1.469e9        # per image, K^2 (H+1)(W+1)HW MACs
+
+
+def synthetic_labels(B, H, W, n_ch, rng):
+    """3x3 binomial blob per channel at a random interior position (reference data.py:112-114,180-188)."""
+    k = np.outer([1, 2, 1], [1, 2, 1]).astype(np.float32) / 16
+    y = np.zeros([B, H, W, n_ch], dtype=np.float32)
+    for b in range(B):
+        for c in range(n_ch):
+            r, q = int(rng.integers(1, H - 1)), int(rng.integers(1, W - 1))
+            y[b, r - 1:r + 2, q - 1:q + 2, c] = k
+    return y
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return dict(bf16=float(p['bf16_tflops']), bf16_sustained=float(p.get('bf16_tflops_sustained', p['bf16_tflops'])),
+                    hbm=float(p['hbm_gbs']), source='MEASURED_PEAKS.json')
+    except Exception:
+        return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle (CPU restatement of the reference TF graph), all host threads
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_step_fn(workload, sample_b):
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import jcm_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    gen = torch.Generator().manual_seed(0)
+    train = workload == 'train64'
+    p = orc.init_part_detector(K_JOINTS, gen, dtype=torch.float32, requires_grad=train)
+    with np.load(os.path.join(ROOT, 'joint-cnn-mrf_b200', 'jcm', 'data', 'pairwise_distribution.npz')) as z:
+        distr = {k: z[k] for k in z.files}
+    sm = orc.init_spatial_model(distr, K_JOINTS, HM_H, HM_W, dtype=torch.float32, requires_grad=train)
+    x = torch.rand(sample_b, IMG_H, IMG_W, 3, generator=gen)
+    y = torch.from_numpy(synthetic_labels(sample_b, HM_H, HM_W, K_JOINTS + 1, np.random.default_rng(0)))
+
+    def step():
+        if train:
+            out = orc.tower_forward(x, y, p, sm, K_JOINTS, True)
+            params = [v for k, v in list(p.items()) + list(sm.items()) if v.requires_grad]
+            torch.autograd.grad(out['loss'], params, allow_unused=True)
+        else:
+            with torch.no_grad():
+                orc.tower_forward(x, y, p, sm, K_JOINTS, False)
+    return step
+
+
+def time_cpu(step, n, warm):
+    for _ in range(warm):
+        step()
+    ts = []
+    for _ in range(n):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    return ts
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    sample_b = 2
+    step = cpu_reference_step_fn(args.workload, sample_b)
+    ts = time_cpu(step, args.steps, args.warmup)
+    total = sum(ts)
+    val = sample_b * len(ts) / total
+    cores = os.cpu_count() or 1
+    line = {
+        'impl': 'reference', 'metric': 'images/sec', 'value': val, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(ts), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args.workload, args.gpus),
+        'cpu_baseline': {'value': val, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                         'sample': '%d images per step (%s), torch-CPU fp32 restatement of the reference TF graph '
+                                   '(TensorFlow 1.x not installable)' % (sample_b, args.workload)},
+        'e2e': {'value': val, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(workload, n_gpus):
+    if workload == 'fwd16':
+        return {'workload': 'BASELINE configs[1]: part-detector + spatial-model forward (+ softmax-CE heads), batch 16 per GPU, K=7, '
+                            '720x480x3 synthetic, fp32-equivalent (bf16x3 split) tensor-core convs, inference-mode BN',
+                'per_gpu_batch': 16, 'global_batch': 16 * n_gpus, 'K': K_JOINTS, 'image': [IMG_H, IMG_W], 'heat_map': [HM_H, HM_W],
+                'l2': 'inputs + activations per step (> 1 GB) exceed the 126 MB L2', 'parallelism': 'dp%d' % n_gpus}
+    return {'workload': 'BASELINE configs[2]: joint training fwd+bwd + grad all-reduce + clip + Adam, batch 64 per GPU, K=7, 720x480x3 '
+                        'synthetic, bf16 tensor-core operands / fp32 accumulation',
+            'per_gpu_batch': 64, 'global_batch': 64 * n_gpus, 'K': K_JOINTS, 'image': [IMG_H, IMG_W], 'heat_map': [HM_H, HM_W],
+            'l2': 'inputs + activations per step (> 4 GB) exceed the 126 MB L2', 'parallelism': 'dp%d' % n_gpus}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import jcm
+    from jcm import ops
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device - the jcm kernels have no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    jcm.lib()  # fail loudly if libjcm.so is missing
+
+    train = args.workload == 'train64'
+    B = 64 if train else 16
+    precision = 'bf16' if train else 'fp32'
+    gen = torch.Generator().manual_seed(1234 + rank)
+    wgen = torch.Generator().manual_seed(0)          # identical parameters on every replica
+    p = jcm.init_part_detector(K_JOINTS, wgen, device=dev)
+    names = jcm.JOINT_NAMES[:K_JOINTS] + ['torso']
+    sm = jcm.PairwiseParams.from_distribution(jcm.get_pairwise_distr(), names, K_JOINTS, HM_H, HM_W, device=dev)
+    ctx = jcm.Context(n_joints=K_JOINTS, joint_names=names, flag_train=train, precision=precision)
+
+    x_host = torch.rand(B, IMG_H, IMG_W, 3, generator=gen).pin_memory()
+    y_host = torch.from_numpy(synthetic_labels(B, HM_H, HM_W, K_JOINTS + 1, np.random.default_rng(rank))).pin_memory()
+    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+
+    if train:
+        from jcm import train as jtrain
+        trainer = jtrain.Trainer(p, sm, ctx, world_size=world)
+
+        def step(x, y):
+            return trainer.step(x, y)['loss']
+    else:
+        def step(x, y):
+            out = jcm.tower_forward(x, y, p, sm, ctx)
+            return out['loss_pd'] + out['loss_sm']
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing
+    for _ in range(args.warmup):
+        step(x_dev, y_dev)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = jcm.lib().jcm_launch_count()
+    ops.PROFILE.clear()
+    ops.PROFILE.enabled = rank == 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(x_dev, y_dev)
+    e1.record()
+    barrier()
+    ops.PROFILE.enabled = False
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = (jcm.lib().jcm_launch_count() - launches0) // max(args.steps, 1)
+    clocks = sampler.stop() if rank == 0 else None
+    conv_prof = ops.PROFILE.summary(args.steps) if rank == 0 else None
+
+    # ---- end to end: pinned host -> device every step, result back to the host
+    res_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    for _ in range(min(args.warmup, 2)):
+        step(x_host.to(dev, non_blocking=True), y_host.to(dev, non_blocking=True))
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        xd = x_host.to(dev, non_blocking=True)
+        yd = y_host.to(dev, non_blocking=True)
+        loss = step(xd, yd)
+        res_host.copy_(loss.reshape(1), non_blocking=True)
+    e3.record()
+    barrier()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    imgs = B * world * args.steps
+    value = imgs / (ms_total / 1e3)
+    e2e_value = imgs / (ms_e2e / 1e3)
+
+    # CPU baseline on a bounded sample (rank 0, N = 1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sample_b = 2
+        st = cpu_reference_step_fn(args.workload, sample_b)
+        ts = time_cpu(st, 3, 1)
+        cpu = {'value': sample_b / min(ts), 'unit': 'images/s', 'cores': os.cpu_count() or 1, 'kind': 'port',
+               'sample': 'best of 3 steps of %d images (%s) after 1 warm-up; torch-CPU fp32 restatement of the reference TF graph '
+                         '(TensorFlow 1.x not installable here)' % (sample_b, args.workload)}
+
+    peak = peaks['bf16_sustained']
+    line = {
+        'metric': 'images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'bf16 operands, fp32 accumulate' if train else 'bf16x3 split products (fp32-equivalent), fp32 accumulate',
+        'data': 'synthetic', 'config': workload_config(args.workload, world),
+        'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': int(x_host.numel() * 4 + y_host.numel() * 4),
+                'd2h_bytes_per_step': 4},
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+        'roofline': {'bound': 'tensor', 'kernel': 'conv_igemm_kernel (tcgen05 implicit GEMM, %d launches/step)' % conv_prof['launches_per_step'],
+                     'achieved': conv_prof['tflops'], 'peak': peak, 'unit': 'TFLOP/s', 'frac': conv_prof['tflops'] / peak,
+                     'traffic': None,
+                     'note': 'achieved = algorithmic conv FLOPs (2*MACs, SURVEY App. A) of all conv launches / their summed CUDA-event time; '
+                             'peak = bf16_tflops_sustained of %s; in the fp32 config every algorithmic MAC is 3 bf16 MMAs, so the '
+                             'ceiling of frac is 1/3 there' % peaks['source'],
+                     'share_of_step': conv_prof['ms_per_step'] / (ms_total / args.steps)},
+        'loss': float(loss.item()) if torch.is_tensor(loss) else float(loss),
+    }
+    if cpu is not None:
+        line['cpu_baseline'] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--workload', default=None, choices=['fwd16', 'train64'])
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.workload is None:
+        args.workload = default_workload()
+    if args.warmup < 3 and args.impl == 'ours':
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+def default_workload():
+    """train64 (the configuration the metric is quoted on) once the training step is built; fwd16 otherwise."""
+    return 'train64' if os.path.exists(os.path.join(ROOT, 'joint-cnn-mrf_b200', 'jcm', 'train.py')) else 'fwd16'
+
+
+if __name__ == '__main__':
+    main()

@@ -29,6 +29,7 @@ extern "C" {
 const char* jcm_last_error(void);
 int jcm_version(void);
 int jcm_sm_count(void);
+long jcm_launch_count(void); /* kernels launched by this library since load */
 
 /* ---- operand preparation --------------------------------------------------------------------------------------- */
 

@@ -17,6 +17,7 @@ SIGNATURES = {
     'jcm_last_error': (_c.c_char_p, []),
     'jcm_version': (_I, []),
     'jcm_sm_count': (_I, []),
+    'jcm_launch_count': (_L, []),
     'jcm_prep_input': (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     'jcm_pack_weights': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     'jcm_pack_weights_s2d': (_I, [_P, _I, _P, _P, _P]),

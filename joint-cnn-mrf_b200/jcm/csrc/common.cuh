@@ -30,8 +30,11 @@ void jcm_set_error(const char* fmt, ...);
     }                                                                               \
   } while (0)
 
+void jcm_count_launch();
+
 #define JCM_LAUNCH_CHECK()                                                          \
   do {                                                                              \
+    jcm_count_launch();                                                             \
     cudaError_t e__ = cudaGetLastError();                                           \
     if (e__ != cudaSuccess) {                                                       \
       jcm_set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \

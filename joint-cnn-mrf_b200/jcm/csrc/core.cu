@@ -13,6 +13,11 @@ void jcm_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static long g_launches = 0;
+void jcm_count_launch() { __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); }
+// number of kernels this library has launched since it was loaded (bench.py reports the per-step delta)
+extern "C" long jcm_launch_count() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 int jcm_num_sms() {
   static int sms = 0;
   if (!sms) {

@@ -217,7 +217,8 @@ def model(x, n_joints, p, ctx, tap=None):
 
     def layer(xp, name, ksize, kind='fwd'):
         w, b = p[name + '/weights'], p[name + '/biases']
-        a = ops.conv2d_planes(xp, ctx.packed(name, w, kind), b, w.shape[3], ksize, relu=True)
+        a = ops.conv2d_planes(xp, ctx.packed(name, w, kind), b, w.shape[3], ksize, relu=True,
+                              alg_kdim=w.shape[0] * w.shape[1] * w.shape[2])
         if tap is not None:
             tap[name + '/relu'] = a
         ss = ops.bn_scale_shift(a, *_bn_vars(p, name), train=train)

@@ -33,6 +33,29 @@ def _req(t, dtype, name):
     return t
 
 
+class _ConvProfile:
+    """Optional CUDA-event timing of every conv launch (bench.py's roofline leg): algorithmic FLOPs and device time."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []
+
+    def clear(self):
+        self.records = []
+
+    def summary(self, steps=None):
+        torch.cuda.synchronize()
+        ms = sum(e0.elapsed_time(e1) for _, e0, e1 in self.records)
+        fl = sum(f for f, _, _ in self.records)
+        n = len(self.records)
+        steps = steps or 1
+        return {'launches': n, 'launches_per_step': n // steps if steps else n, 'ms_total': ms, 'ms_per_step': ms / steps,
+                'tflops': (fl / (ms * 1e-3) / 1e12) if ms > 0 else 0.0, 'flops_per_step': fl / steps}
+
+
+PROFILE = _ConvProfile()
+
+
 class Planes:
     """bf16 operand planes (hi, lo) of an NHWC activation or packed weight; lo is None in bf16 mode."""
     __slots__ = ('hi', 'lo', 'shape')
@@ -99,8 +122,9 @@ def split_planes(x, split):
 
 
 # ------------------------------------------------------------------------------------------------ part detector
-def conv2d_planes(xp, wp, bias, cout, ksize, relu, naive=False):
-    """xp activation planes [B,H,W,Cin], wp packed weight planes [k*k,Cout_pad,Cin] -> fp32 [B,H,W,cout]."""
+def conv2d_planes(xp, wp, bias, cout, ksize, relu, naive=False, alg_kdim=None):
+    """xp activation planes [B,H,W,Cin], wp packed weight planes [k*k,Cout_pad,Cin] -> fp32 [B,H,W,cout].
+    alg_kdim: contraction length of the ALGORITHMIC convolution (default k*k*Cin; 75 for the s2d conv1)."""
     B, H, W, cin = xp.shape
     taps, cout_pad, cin_w = wp.shape
     if cin_w != cin or taps != ksize * ksize:
@@ -111,8 +135,15 @@ def conv2d_planes(xp, wp, bias, cout, ksize, relu, naive=False):
         _req(bias, F32, 'bias')
     y = torch.empty((B, H, W, cout), dtype=F32, device=xp.hi.device)
     fn = lib().jcm_debug_conv2d_naive if naive else lib().jcm_conv2d_fwd
+    prof = PROFILE.enabled and not naive
+    if prof:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(fn(_ptr(xp.hi), _ptr(xp.lo), _ptr(wp.hi), _ptr(wp.lo), _ptr(bias), _ptr(y), B, H, W, cin, cout, cout_pad, ksize,
              int(relu), _stream()), 'jcm_conv2d_fwd')
+    if prof:
+        e1.record()
+        PROFILE.records.append((2.0 * B * H * W * (alg_kdim or ksize * ksize * cin) * cout, e0, e1))
     return y
 
 

@@ -1,0 +1,132 @@
+"""CPU-only checks (-m "not gpu"): golden vectors vs the oracle, the pairwise-prior table, the C ABI surface and the
+host-side argument validation (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import jcm_oracle as orc
+import pairwise_prior as pp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+NPZ = os.path.join(ROOT, 'joint-cnn-mrf_b200', 'jcm', 'data', 'pairwise_distribution.npz')
+REF = '/root/reference'
+
+
+# ------------------------------------------------------------------------------------------------ golden vectors
+@pytest.mark.parametrize('name', ['sm_small', 'sm_tiny_ragged'])
+def test_oracle_reproduces_sm_golden(name):
+    z = np.load(os.path.join(GOLD, name + '.npz'))
+    names = [str(s) for s in z['names']]
+    K = len(names) - 1
+    sm = {k[3:]: torch.from_numpy(z[k]).double() for k in z.files if k.startswith('sm/')}
+    cat = torch.from_numpy(z['heat_map']).double()
+    for train in (0, 1):
+        out = orc.spatial_model(cat, {k: v.clone() for k, v in sm.items()}, K, bool(train), joint_names=names)
+        np.testing.assert_allclose(out.numpy(), z['out_train%d' % train], rtol=1e-12, atol=1e-12)
+        assert np.array_equal(orc.get_joints_coords(orc.spatial_softmax(out)).numpy(), z['argmax_train%d' % train])
+
+
+def test_oracle_reproduces_model_golden():
+    sys.path.insert(0, GOLD)
+    import make_golden as mg
+    z = np.load(os.path.join(GOLD, 'model_debug_small.npz'))
+    p, _ = mg.model_params(int(z['K']), int(z['seed']))
+    assert abs(mg.params_checksum(p) - float(z['params_checksum'])) < 1e-6 * float(z['params_checksum'])
+    p64 = {k: v.double() for k, v in p.items()}
+    x = torch.from_numpy(z['x']).double()
+    for train in (0, 1):
+        logits = orc.model(x, {k: v.clone() for k, v in p64.items()}, int(z['K']), bool(train))
+        np.testing.assert_allclose(logits.numpy(), z['logits_train%d' % train], rtol=1e-9, atol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------------ pairwise prior
+def test_shipped_prior_table_structure():
+    """90 keys '<joint>_<cond>' in joint_ids x joint_ids order, float64 (120,180), sum 1 (prepare_pairwise_distribution.py:46-56)."""
+    with np.load(NPZ) as z:
+        keys = list(z.files)
+        want = [a + '_' + b for a in pp.JOINT_IDS for b in pp.JOINT_IDS if a != b]
+        assert keys == want
+        for k in keys:
+            a = z[k]
+            assert a.shape == (120, 180) and a.dtype == np.float64
+            assert abs(a.sum() - 1.0) < 1e-9 and a.min() >= 0
+        a = z['nose_torso']   # SURVEY Appendix C sanity values for the 'shipped' recipe
+        assert np.unravel_index(a.argmax(), a.shape) == (49, 89)
+        assert abs(a.max() - 0.013686) < 1e-5 and int((a != 0).sum()) == 800
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, 'data_FLIC.mat')), reason='reference mount not present')
+def test_prior_regenerates_from_flic_and_matches_corrupt_pickle_structure():
+    """The regenerated table equals the committed one, and its zero-run structure equals what survives in the
+    (corrupt) pickle shipped with the reference - the only pin on the reference's actual initialisation."""
+    keys = ['nose_torso', 'lwri_lelb', 'lsho_rsho', 'rhip_torso']
+    regen = pp.regenerate(os.path.join(REF, 'data_FLIC.mat'), 'shipped', keys=set(keys))
+    runs = pp.zero_runs_from_corrupt_pickle(os.path.join(REF, 'pairwise_distribution.pickle'))
+    with np.load(NPZ) as z:
+        for k in keys:
+            np.testing.assert_allclose(regen[k], z[k], rtol=0, atol=1e-15)
+            assert pp.zero_runs_of_array(regen[k]) == runs[k], k
+
+
+def test_labels_follow_data_py():
+    """data.py:106-114,180-189: a 3x3 binomial blob at int(row), int(col), clipped at the border."""
+    pos = np.array([[[10.6, 20.2]] * 10, [[0.0, 0.0]] * 10, [[59.9, 89.9]] * 10])
+    y = pp.target_heat_maps(pos)
+    assert y.shape == (3, 60, 90, 10)
+    assert abs(y[0, :, :, 0].sum() - 1) < 1e-6 and y[0, 10, 20, 0] == 0.25
+    assert abs(y[1, :, :, 0].sum() - 9 / 16) < 1e-6      # corner blob is clipped
+    assert y[2, 59, 89, 3] == 0.25
+
+
+# ------------------------------------------------------------------------------------------------ C ABI
+def test_library_exports_every_declared_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, 'include', 'jcm.h')).read()
+    declared = set(re.findall(r'\b(jcm_\w+)\s*\(', hdr))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(built_lib)
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+    from jcm._lib import SIGNATURES
+    assert declared == set(SIGNATURES), (declared ^ set(SIGNATURES))
+    lib.jcm_version.restype = ctypes.c_int
+    assert lib.jcm_version() >= 100
+    lib.jcm_spatial_model_workspace.restype = ctypes.c_long
+    assert lib.jcm_spatial_model_workspace(16, 60, 90, 7, 49) > 0
+
+
+def test_sass_contains_blackwell_instructions(built_lib):
+    """tcgen05.mma -> UTC*MMA, TMA -> UTMALDG, tcgen05.ld -> LDTM, packed fp32 FMA -> FFMA2 (B200_PROFILING.md)."""
+    import subprocess
+    sass = subprocess.run(['cuobjdump', '-sass', built_lib], capture_output=True, text=True).stdout
+    for mnemonic in ('UTCHMMA', 'UTMALDG', 'LDTM', 'FFMA2'):
+        assert mnemonic in sass, mnemonic
+
+
+def test_argument_errors_do_not_need_a_gpu(built_lib):
+    """Bad arguments are rejected on the host with a negative code and a message (ValueError in the Python layer)."""
+    import jcm
+    l = jcm.lib()
+    rc = l.jcm_conv2d_fwd(None, None, None, None, None, None, 1, 8, 8, 64, 64, 64, 3, 1, None)
+    assert rc == -1 and b'null pointer' in l.jcm_last_error()
+    rc = l.jcm_spatial_softmax(None, 1, 10, 7, None, None)
+    assert rc == -1
+    with pytest.raises(ValueError):
+        jcm.ops.spatial_softmax(torch.zeros(1, 4, 4, 2))          # CPU tensor: there is no CPU path
+    with pytest.raises(ValueError):
+        jcm.Context(n_joints=7, joint_names=['a', 'b'])
+    with pytest.raises(ValueError):
+        jcm.Context(precision='fp16')
+
+
+def test_product_path_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, 'joint-cnn-mrf_b200', 'jcm')
+    for f in os.listdir(pkg):
+        if f.endswith('.py'):
+            src = open(os.path.join(pkg, f)).read()
+            assert 'jcm_oracle' not in src and 'import oracle' not in src and 'pairwise_prior' not in src.replace('oracle/pairwise_prior.py', ''), f

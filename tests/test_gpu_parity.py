@@ -1,0 +1,296 @@
+"""GPU parity tests (-m gpu): every CUDA kernel, called through the C ABI (ctypes) via the jcm Python surface, against
+the CPU oracle / the committed golden vectors on identical seeded inputs.
+
+Tolerances (north_star: <= 1e-3 relative fp32, arg-max joint coordinates bit-exact):
+  * fp32 config (bf16x3 split products, fp32 accumulation): max|gpu - oracle| / max|oracle| <= 1e-3 end to end
+    (single kernels are checked much tighter), arg-max coordinates identical.
+  * bf16 config (training arithmetic): <= 5e-2 relative on logits (stated, not a parity claim at 1e-3).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import jcm_oracle as orc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+TOL_FP32 = 1e-3
+TOL_BF16 = 5e-2
+
+
+@pytest.fixture(scope='module')
+def jcm(built_lib):
+    if not torch.cuda.is_available():
+        pytest.fail('GPU tests need a CUDA device (no CPU fallback exists)')
+    import jcm as _jcm
+    _jcm.lib()
+    return _jcm
+
+
+def rel(a, b):
+    a = a.detach().double().cpu()
+    b = torch.as_tensor(np.asarray(b)).double() if not torch.is_tensor(b) else b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+# ------------------------------------------------------------------------------------------------ convolution
+CONV_CASES = [  # B, H, W, Cin, Cout, k   (edge cases: ragged patches, Cout not a multiple of 16, every swizzle mode, 2 N tiles)
+    (1, 16, 24, 64, 64, 5), (2, 20, 33, 16, 64, 3), (1, 16, 24, 32, 32, 5), (1, 15, 23, 128, 256, 9), (1, 30, 45, 256, 512, 9),
+    (1, 60, 90, 128, 7, 9), (1, 9, 200, 64, 16, 3), (3, 1, 1, 64, 48, 3), (1, 7, 129, 16, 9, 5)]
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+@pytest.mark.parametrize('split', [False, True])
+def test_conv2d_tcgen05_matches_oracle(jcm, case, split):
+    B, H, W, Cin, Cout, k = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x = torch.randn(B, H, W, Cin, generator=g)
+    w = torch.randn(k, k, Cin, Cout, generator=g) / np.sqrt(k * k * Cin)
+    b = torch.randn(Cout, generator=g)
+    xp = jcm.ops.split_planes(x.cuda(), split)
+    wp = jcm.ops.pack_weights(w.cuda(), split)
+    y = jcm.ops.conv2d_planes(xp, wp, b.cuda(), Cout, k, relu=True)
+    yn = jcm.ops.conv2d_planes(xp, wp, b.cuda(), Cout, k, relu=True, naive=True)
+    xr, wr = (x, w) if split else (bf16r(x), bf16r(w))   # plain bf16 mode is exact arithmetic on the rounded operands
+    ref = torch.relu(orc.conv2d(xr.double(), wr.double(), 1) + b.double())
+    assert rel(y, ref) < 2e-4
+    assert rel(y, yn) < 2e-4
+
+
+@pytest.mark.parametrize('split', [False, True])
+def test_conv1_stride2_via_space_to_depth(jcm, split):
+    """5x5 stride-2 SAME (TF pads 1 before / 2 after) over the full, 1/2 and 1/4 resolution images (main.py:44,51-52,60-61)."""
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand(2, 48, 80, 3, generator=g)
+    w = torch.randn(5, 5, 3, 64, generator=g) / np.sqrt(75)
+    b = torch.randn(64, generator=g)
+    banks = jcm.ops.prep_input(x.cuda(), split)
+    wp = jcm.ops.pack_weights_s2d(w.cuda(), split)
+    xr, wr = (x, w) if split else (bf16r(x), bf16r(w))
+    for bi, step in enumerate((1, 2, 4)):
+        y = jcm.ops.conv2d_planes(banks[bi], wp, b.cuda(), 64, 3, relu=True)
+        ref = torch.relu(orc.conv2d(xr.double()[:, ::step, ::step], wr.double(), 2) + b.double())
+        assert tuple(y.shape) == tuple(ref.shape)
+        assert rel(y, ref) < 5e-5
+
+
+def test_conv_rejects_bad_arguments(jcm):
+    x = jcm.ops.split_planes(torch.randn(1, 8, 8, 24).cuda(), False)     # 24 channels: not a multiple of 16
+    w = jcm.ops.Planes(torch.zeros(9, 16, 24, dtype=torch.bfloat16).cuda(), None)
+    with pytest.raises(ValueError):
+        jcm.ops.conv2d_planes(x, w, None, 16, 3, relu=False)
+    with pytest.raises(ValueError):
+        jcm.ops.conv2d_planes(x, w, None, 16, 5, relu=False)              # tap count mismatch
+
+
+# ------------------------------------------------------------------------------------------------ BN / pool / upsample
+@pytest.mark.parametrize('shape', [(2, 45, 31, 64), (1, 15, 23, 512), (3, 10, 12, 8), (2, 9, 7, 10)])
+@pytest.mark.parametrize('train', [True, False])
+def test_batch_norm_and_pool(jcm, shape, train):
+    g = torch.Generator().manual_seed(1)
+    B, H, W, C = shape
+    a = torch.relu(torch.randn(*shape, generator=g))
+    bn = {'gamma': torch.rand(C, generator=g) + 0.5, 'beta': torch.randn(C, generator=g), 'moving_mean': torch.randn(C, generator=g) * 0.1,
+          'moving_variance': torch.rand(C, generator=g) + 0.5}
+    bn64 = {k: v.double().clone() for k, v in bn.items()}
+    ref = orc.batch_norm(a.double(), bn64, train)
+    d = {k: v.cuda() for k, v in bn.items()}
+    ss = jcm.ops.bn_scale_shift(a.cuda(), d['gamma'], d['beta'], d['moving_mean'], d['moving_variance'], train=train)
+    if C % 4 == 0:
+        planes, f32 = jcm.ops.bn_apply_pool(a.cuda(), ss, False, True, want_planes=True, want_f32=True)
+        assert rel(f32, ref) < 1e-5
+        assert rel(planes.hi.float() + planes.lo.float(), ref) < 2e-5
+        pooled = jcm.ops.bn_apply_pool(a.cuda(), ss, True, False, want_planes=False, want_f32=True)
+        assert rel(pooled, orc.max_pool_layer(ref)) < 1e-5
+    assert rel(d['moving_mean'], bn64['moving_mean']) < 1e-5          # updated in place iff train
+    assert rel(d['moving_variance'], bn64['moving_variance']) < 1e-5
+
+
+def test_upsample_avg3(jcm):
+    g = torch.Generator().manual_seed(2)
+    a1, a2, a3 = (torch.randn(2, h, w, 64, generator=g) for h, w in ((60, 90), (30, 45), (15, 23)))
+    ss6 = torch.randn(6, 64, generator=g)
+    d = lambda t: t.double()
+    ref = (d(a1) * d(ss6[0]) + d(ss6[1]) + orc.resize_images(d(a2) * d(ss6[2]) + d(ss6[3]), 60, 90)
+           + orc.resize_images(d(a3) * d(ss6[4]) + d(ss6[5]), 60, 90)) / 3
+    out = jcm.ops.upsample_avg3(a1.cuda(), a2.cuda(), a3.cuda(), ss6.cuda(), False, want_planes=False, want_f32=True)
+    assert rel(out, ref) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ heads
+def test_softmax_ce_argmax(jcm):
+    g = torch.Generator().manual_seed(3)
+    B, H, W, K = 3, 60, 90, 7
+    logits = torch.randn(B, H, W, K, generator=g) * 3
+    labels = torch.from_numpy(orc.synthetic_labels(B, H, W, K + 1, np.random.default_rng(0)))
+    sm = jcm.spatial_softmax(logits.cuda())
+    assert rel(sm, orc.spatial_softmax(logits.double())) < 1e-5
+    loss = jcm.softmax_cross_entropy(logits.cuda(), labels.cuda())
+    assert abs(float(loss) - float(orc.softmax_cross_entropy(logits.double(), labels.double()[..., :K]))) < 1e-4
+    assert torch.equal(jcm.get_joints_coords(sm).cpu(), orc.get_joints_coords(orc.spatial_softmax(logits.double())))
+
+
+def test_argmax_first_max_tie_rule(jcm):
+    hm = torch.zeros(1, 6, 9, 2)
+    hm[0, 2, 3, 0] = 1.0
+    hm[0, 4, 1, 0] = 1.0          # tie: the first in row-major order wins (evaluation.py:15-24)
+    got = jcm.get_joints_coords(hm.cuda()).cpu()
+    assert got[0, :, 0].tolist() == [2, 3] and got[0, :, 1].tolist() == [0, 0]
+
+
+# ------------------------------------------------------------------------------------------------ spatial model
+def _sm_inputs(B, K, H, W, seed):
+    rng = np.random.default_rng(seed)
+    names = orc.JOINT_NAMES[:K] + ['torso']
+    g = torch.Generator().manual_seed(seed)
+    hm = torch.softmax(3 * torch.randn(B, H * W, K, generator=g), dim=1).reshape(B, H, W, K)
+    cat = torch.cat([hm, torch.from_numpy(orc.synthetic_labels(B, H, W, 1, rng))], dim=3).contiguous()
+    return names, cat, rng, g
+
+
+@pytest.mark.parametrize('B,K', [(1, 7), (2, 7), (5, 7), (2, 9)])
+@pytest.mark.parametrize('train', [False, True])
+def test_spatial_model_60x90_matches_oracle(jcm, B, K, train):
+    names, cat, rng, g = _sm_inputs(B, K, 60, 90, 5)
+    sm64 = orc.init_spatial_model(jcm.get_pairwise_distr(), K, 60, 90, joint_names=names)
+    for k, v in sm64.items():
+        if k.startswith('bias_'):
+            v.add_(torch.rand(v.shape, generator=g).double() * 0.01)
+        if 'gamma' in k or 'beta' in k:
+            v.add_(torch.randn(v.shape, generator=g).double() * 0.1)
+    sm32 = {k: v.float() for k, v in sm64.items()}
+    ref = orc.spatial_model(cat.double(), {k: v.double().clone() for k, v in sm32.items()}, K, train, joint_names=names)
+    smp = jcm.PairwiseParams.from_dict(sm32, names, K)
+    ctx = jcm.Context(n_joints=K, joint_names=names, flag_train=train)
+    out = jcm.spatial_model(cat.cuda(), smp, ctx)
+    assert rel(out, ref) < 1e-4
+    assert torch.equal(jcm.get_joints_coords(jcm.spatial_softmax(out)).cpu(), orc.get_joints_coords(orc.spatial_softmax(ref)))
+
+
+@pytest.mark.parametrize('name', ['sm_small', 'sm_tiny_ragged'])
+def test_spatial_model_golden(jcm, name):
+    z = np.load(os.path.join(GOLD, name + '.npz'))
+    names = [str(s) for s in z['names']]
+    K = len(names) - 1
+    sm = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('sm/')}
+    smp = jcm.PairwiseParams.from_dict(sm, names, K)
+    for train in (0, 1):
+        ctx = jcm.Context(n_joints=K, joint_names=names, flag_train=bool(train))
+        out = jcm.spatial_model(torch.from_numpy(z['heat_map']).cuda(), smp, ctx)
+        assert rel(out, z['out_train%d' % train]) < 1e-4
+        assert np.array_equal(jcm.get_joints_coords(jcm.spatial_softmax(out)).cpu().numpy(), z['argmax_train%d' % train])
+
+
+@pytest.mark.parametrize('H,W,b', [(60, 90, 3), (12, 20, 5), (7, 9, 1)])
+def test_conv_mrf_matches_scipy(jcm, H, W, b):
+    """conv_mrf == scipy 'valid' convolution + legacy bilinear resize (main.py:77-91)."""
+    from scipy import signal
+    rng = np.random.default_rng(4)
+    A = rng.random((2 * H, 2 * W)).astype(np.float32)
+    Bm = rng.random((b, H, W)).astype(np.float32)
+    got = jcm.conv_mrf(torch.from_numpy(A).view(1, 2 * H, 2 * W, 1).cuda(), torch.from_numpy(Bm).view(b, H, W, 1).cuda()).cpu()
+    for n in range(b):
+        c = signal.convolve2d(A.astype(np.float64), Bm[n].astype(np.float64), mode='valid')
+        ref = orc.resize_images(torch.from_numpy(c).view(1, H + 1, W + 1, 1), H, W)[0, :, :, 0]
+        assert rel(got[n, :, :, 0], ref) < 2e-5
+
+
+def test_spatial_model_linearity_in_likelihood_at_full_batch(jcm):
+    """Size-independent property at the BASELINE batch (16): conv_mrf is linear in the likelihood maps."""
+    rng = np.random.default_rng(6)
+    H, W, b = 60, 90, 16
+    A = torch.from_numpy(rng.random((1, 2 * H, 2 * W, 1)).astype(np.float32)).cuda()
+    B1 = torch.from_numpy(rng.random((b, H, W, 1)).astype(np.float32)).cuda()
+    B2 = torch.from_numpy(rng.random((b, H, W, 1)).astype(np.float32)).cuda()
+    lhs = jcm.conv_mrf(A, (B1 + 2 * B2).contiguous())
+    rhs = jcm.conv_mrf(A, B1) + 2 * jcm.conv_mrf(A, B2)
+    assert rel(lhs, rhs) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ part detector
+def _pd_params(K, debug, seed):
+    gen = torch.Generator().manual_seed(seed)
+    p = orc.init_part_detector(K, gen, debug=debug)
+    for k, v in p.items():
+        if 'gamma' in k or 'moving_variance' in k:
+            v.add_(torch.rand(v.shape, generator=gen).double() * 0.5)
+        if 'beta' in k or 'moving_mean' in k or 'biases' in k:
+            v.add_(torch.randn(v.shape, generator=gen).double() * 0.1)
+    return {k: v.float() for k, v in p.items()}, gen
+
+
+@pytest.mark.parametrize('train', [False, True])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_model_debug_width_matches_oracle_layer_by_layer(jcm, train, precision):
+    K = 7
+    p, gen = _pd_params(K, True, 3)
+    x = torch.rand(2, 96, 160, 3, generator=gen)
+    tap_ref, tap = {}, {}
+    ref = orc.model(x.double(), {k: v.double().clone() for k, v in p.items()}, K, train, tap=tap_ref)
+    ctx = jcm.Context(n_joints=K, flag_train=train, precision=precision, debug=True)
+    out = jcm.model(x.cuda(), K, jcm.load_params(p), ctx, tap=tap)
+    tol = TOL_FP32 if precision == 'fp32' else TOL_BF16
+    for name, r in tap_ref.items():
+        assert rel(tap[name], r) < tol, name
+    assert rel(out, ref) < tol
+    if precision == 'fp32':
+        assert torch.equal(jcm.get_joints_coords(jcm.spatial_softmax(out)).cpu(), orc.get_joints_coords(orc.spatial_softmax(ref)))
+
+
+def test_model_golden(jcm):
+    sys.path.insert(0, GOLD)
+    import make_golden as mg
+    z = np.load(os.path.join(GOLD, 'model_debug_small.npz'))
+    K = int(z['K'])
+    p, _ = mg.model_params(K, int(z['seed']))
+    assert abs(mg.params_checksum(p) - float(z['params_checksum'])) < 1e-6 * float(z['params_checksum'])
+    x = torch.from_numpy(z['x']).cuda()
+    y = torch.from_numpy(z['labels']).cuda()
+    for train in (0, 1):
+        ctx = jcm.Context(n_joints=K, flag_train=bool(train), precision='fp32', debug=True)
+        out = jcm.model(x, K, jcm.load_params(p), ctx)
+        assert rel(out, z['logits_train%d' % train]) < TOL_FP32
+        assert rel(jcm.spatial_softmax(out), z['softmax_train%d' % train]) < 2 * TOL_FP32
+        assert abs(float(jcm.softmax_cross_entropy(out, y)) - float(z['ce_train%d' % train])) < 1e-3 * float(z['ce_train%d' % train])
+        assert np.array_equal(jcm.get_joints_coords(jcm.spatial_softmax(out)).cpu().numpy(), z['argmax_train%d' % train])
+
+
+def test_full_size_tower_forward_fp32(jcm):
+    """BASELINE shapes (720x480, K=7, full width) on one image: part detector + spatial model + both heads vs the oracle."""
+    K = 7
+    p, gen = _pd_params(K, False, 9)
+    names = orc.JOINT_NAMES[:K] + ['torso']
+    x = torch.rand(1, 480, 720, 3, generator=gen)
+    y = torch.from_numpy(orc.synthetic_labels(1, 60, 90, K + 1, np.random.default_rng(1)))
+    sm32 = {k: v.float() for k, v in orc.init_spatial_model(jcm.get_pairwise_distr(), K, 60, 90, joint_names=names).items()}
+    ref = orc.tower_forward(x.double(), y.double(), {k: v.double() for k, v in p.items()}, {k: v.double() for k, v in sm32.items()}, K, False)
+    ctx = jcm.Context(n_joints=K, joint_names=names, flag_train=False, precision='fp32')
+    out = jcm.tower_forward(x.cuda(), y.cuda(), jcm.load_params(p), jcm.PairwiseParams.from_dict(sm32, names, K), ctx)
+    assert rel(out['logit_pd'], ref['logit_pd']) < TOL_FP32
+    assert rel(out['logit_sm'], ref['logit_sm']) < TOL_FP32
+    assert abs(float(out['loss_pd']) - float(ref['loss_pd'])) < 1e-3 * float(ref['loss_pd'])
+    assert abs(float(out['loss_sm']) - float(ref['loss_sm'])) < 1e-3 * float(ref['loss_sm'])
+    for key in ('hm_pd', 'hm_sm'):
+        assert torch.equal(jcm.get_joints_coords(out[key]).cpu(), orc.get_joints_coords(ref[key])), key
+
+
+def test_batch_16_forward_is_batch_independent(jcm):
+    """Property at the BASELINE batch size: in inference mode every image is processed independently, so a batch of 16
+    (two distinct images repeated) must give exactly the per-image results - exercises all tile/patch index paths."""
+    K = 7
+    gen = torch.Generator().manual_seed(21)
+    p = jcm.init_part_detector(K, gen)
+    ctx = jcm.Context(n_joints=K, flag_train=False, precision='bf16')
+    x2 = torch.rand(2, 480, 720, 3, generator=gen).cuda()
+    x16 = x2.repeat(8, 1, 1, 1).contiguous()
+    o2 = jcm.model(x2, K, p, ctx)
+    o16 = jcm.model(x16, K, p, ctx)
+    assert torch.equal(o16[:2], o2) and torch.equal(o16[14:], o2)
