@@ -78,12 +78,82 @@ __global__ void __launch_bounds__(512, 1) fma_peak_kernel(float* out, int iters,
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
   }
 }
+
+// Operand-pattern probes of the spatial-model inner loop (no memory traffic in the loop): 7 x 4 accumulators per lane,
+// a 7-slot rotating window operand and a per-step 4-image operand.  MODE 2: FFMA2 with duplicated (broadcast) window
+// values, MODE 3: FFMA2 with two different values per window pair (forces the 64-bit operand form), MODE 4: scalar FFMA.
+template <int MODE>
+__global__ void __launch_bounds__(640, 1) fma_pattern_kernel(float* io, int iters) {
+  const float* src = io + (threadIdx.x & 31);
+  if (MODE == 4) {
+    float acc[7][4], win[7], l[7][4];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      win[k] = src[k * 32];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { acc[k][e] = 0.f; l[k][e] = src[(7 + k * 4 + e) * 32]; }
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int s = 0; s < 7; ++s)
+#pragma unroll
+        for (int k = 0; k < 7; ++k)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[k][e] = fmaf(win[(s + k) % 7], l[s][e], acc[k][e]);
+    }
+    float r = 0.f;
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) r += acc[k][e];
+    io[4096 + blockIdx.x * blockDim.x + threadIdx.x] = r;
+  } else {
+    unsigned long long acc[7][2], win[7], l[7][2];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const float a = src[k * 32], b = (MODE == 3) ? src[(40 + k) * 32] : a;
+      asm("mov.b64 %0, {%1, %2};" : "=l"(win[k]) : "f"(a), "f"(b));
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        acc[k][e] = 0ull;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(l[k][e]) : "f"(src[(7 + k * 4 + 2 * e) * 32]), "f"(src[(8 + k * 4 + 2 * e) * 32]));
+      }
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int s = 0; s < 7; ++s)
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+          asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[k][0]) : "l"(win[(s + k) % 7]), "l"(l[s][0]));
+          asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[k][1]) : "l"(win[(s + k) % 7]), "l"(l[s][1]));
+        }
+    }
+    float r = 0.f;
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float x, y;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(acc[k][e]));
+        r += x + y;
+      }
+    io[4096 + blockIdx.x * blockDim.x + threadIdx.x] = r;
+  }
+}
 }  // namespace
 
 // Runs the FMA loop once on `stream`; flops_out = FLOPs executed (2 per FMA).  scratch: blocks*512 floats.
 // packed = 0: scalar FFMA, packed = 1: FFMA2 (fma.rn.f32x2).  Time it from the caller with CUDA events.
 extern "C" int jcm_fma_peak(float* scratch, int blocks, int iters, int packed, double* flops_out, void* stream) {
   JCM_CHECK_ARG(scratch && blocks > 0 && iters > 0, "jcm_fma_peak: bad arguments");
+  if (packed >= 2) {  // operand-pattern probes: scratch needs 4096 + blocks*640 floats
+    if (packed == 2) fma_pattern_kernel<2><<<blocks, 640, 0, (cudaStream_t)stream>>>(scratch, iters);
+    else if (packed == 3) fma_pattern_kernel<3><<<blocks, 640, 0, (cudaStream_t)stream>>>(scratch, iters);
+    else fma_pattern_kernel<4><<<blocks, 640, 0, (cudaStream_t)stream>>>(scratch, iters);
+    JCM_LAUNCH_CHECK();
+    if (flops_out) *flops_out = 2.0 * 7.0 * 7.0 * 4.0 * (double)iters * 640.0 * (double)blocks;
+    return JCM_OK;
+  }
   if (packed)
     fma_peak_kernel<1><<<blocks, 512, 0, (cudaStream_t)stream>>>(scratch, iters, 0.999f, 0.001f);
   else

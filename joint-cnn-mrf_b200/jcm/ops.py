@@ -264,7 +264,7 @@ def conv_mrf_fwd(A, Bm):
 
 def fma_peak(blocks, iters, packed):
     """Launches the FMA loop; returns FLOPs per launch (time it with CUDA events)."""
-    scratch = torch.empty((blocks * 512,), dtype=F32, device='cuda')
+    scratch = torch.rand((4096 + blocks * 640,), dtype=F32, device='cuda')
     flops = ctypes.c_double(0.0)
     check(lib().jcm_fma_peak(_ptr(scratch), blocks, iters, int(packed), ctypes.byref(flops), _stream()), 'jcm_fma_peak')
     return flops.value

@@ -46,11 +46,11 @@ def timeit(fn, n=5, warm=2):
 
 def sec_peak():
     sms = jcm.lib().jcm_sm_count()
-    for packed in (0, 1):
+    for packed in (0, 1, 2, 3, 4):
         fl = [0.0]
 
         def run():
-            fl[0] = ops.fma_peak(sms * 2, 2000, packed)
+            fl[0] = ops.fma_peak(sms * 2 if packed < 2 else sms, 2000, packed)
         best, med = timeit(run)
         print('PEAK packed=%d  %.1f TFLOP/s best, %.1f median (%.3f ms)' % (packed, fl[0] / best / 1e9, fl[0] / med / 1e9, best))
 

@@ -41,6 +41,24 @@ def bf16r(t):
     return t.to(torch.bfloat16).to(torch.float32)
 
 
+def assert_argmax_matches(gpu_hm, ref_hm, tol=1e-3):
+    """Arg-max joint coordinates must equal the oracle's.  Where they differ, the oracle itself must have a near tie
+    (the value at the GPU's arg-max is within `tol` relative of the oracle's maximum, i.e. inside the stated fp32
+    tolerance - this only happens on the nearly flat maps of a randomly initialised network)."""
+    import jcm as _jcm
+    got = _jcm.get_joints_coords(gpu_hm).cpu()
+    want = orc.get_joints_coords(ref_hm)
+    if torch.equal(got, want):
+        return
+    B, _, K = want.shape
+    for n in range(B):
+        for k in range(K):
+            if not torch.equal(got[n, :, k], want[n, :, k]):
+                m = ref_hm[n, :, :, k]
+                v = float(m[got[n, 0, k], got[n, 1, k]])
+                assert v >= float(m.max()) * (1 - tol), 'arg-max of joint %d differs and is not a near tie (%g vs max %g)' % (k, v, float(m.max()))
+
+
 # ------------------------------------------------------------------------------------------------ convolution
 CONV_CASES = [  # B, H, W, Cin, Cout, k   (edge cases: ragged patches, Cout not a multiple of 16, every swizzle mode, 2 N tiles)
     (1, 16, 24, 64, 64, 5), (2, 20, 33, 16, 64, 3), (1, 16, 24, 32, 32, 5), (1, 15, 23, 128, 256, 9), (1, 30, 45, 256, 512, 9),
@@ -279,7 +297,25 @@ def test_full_size_tower_forward_fp32(jcm):
     assert abs(float(out['loss_pd']) - float(ref['loss_pd'])) < 1e-3 * float(ref['loss_pd'])
     assert abs(float(out['loss_sm']) - float(ref['loss_sm'])) < 1e-3 * float(ref['loss_sm'])
     for key in ('hm_pd', 'hm_sm'):
-        assert torch.equal(jcm.get_joints_coords(out[key]).cpu(), orc.get_joints_coords(ref[key])), key
+        assert_argmax_matches(out[key], ref[key])
+
+
+def test_argmax_bit_exact_on_peaked_maps(jcm):
+    """With trained-like (peaked) part-detector maps the spatial model's arg-max coordinates are bit-exact."""
+    K, B = 7, 4
+    names = orc.JOINT_NAMES[:K] + ['torso']
+    rng = np.random.default_rng(8)
+    blobs = torch.from_numpy(orc.synthetic_labels(B, 60, 90, K + 1, rng))
+    g = torch.Generator().manual_seed(8)
+    logits = 12.0 * blobs[..., :K] / blobs.max() + torch.randn(B, 60, 90, K, generator=g)
+    hm = orc.spatial_softmax(logits.double()).float()
+    cat = torch.cat([hm, blobs[..., K:]], dim=3).contiguous()
+    sm32 = {k: v.float() for k, v in orc.init_spatial_model(jcm.get_pairwise_distr(), K, 60, 90, joint_names=names).items()}
+    ref = orc.spatial_model(cat.double(), {k: v.double() for k, v in sm32.items()}, K, False, joint_names=names)
+    ctx = jcm.Context(n_joints=K, joint_names=names, flag_train=False)
+    out = jcm.spatial_model(cat.cuda(), jcm.PairwiseParams.from_dict(sm32, names, K), ctx)
+    assert rel(out, ref) < 1e-4
+    assert torch.equal(jcm.get_joints_coords(jcm.spatial_softmax(out)).cpu(), orc.get_joints_coords(orc.spatial_softmax(ref)))
 
 
 def test_batch_16_forward_is_batch_independent(jcm):
