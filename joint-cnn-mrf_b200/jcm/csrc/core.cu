@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(512, 1) fma_peak_kernel(float* out, int iters,
 template <int MODE>
 __global__ void __launch_bounds__(640, 1) fma_pattern_kernel(float* io, int iters) {
   const float* src = io + (threadIdx.x & 31);
-  if (MODE == 4) {
+  if (MODE == 4 || MODE == 7) {
     float acc[7][4], win[7], l[7][4];
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
@@ -95,11 +95,19 @@ __global__ void __launch_bounds__(640, 1) fma_pattern_kernel(float* io, int iter
     }
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-      for (int s = 0; s < 7; ++s)
+      for (int s = 0; s < 7; ++s) {
+        if (MODE == 4) {
 #pragma unroll
-        for (int k = 0; k < 7; ++k)
+          for (int k = 0; k < 7; ++k)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) acc[k][e] = fmaf(win[(s + k) % 7], l[s][e], acc[k][e]);
+            for (int e = 0; e < 4; ++e) asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(acc[k][e]) : "f"(win[(s + k) % 7]), "f"(l[s][e]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int k = 0; k < 7; ++k) asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(acc[k][e]) : "f"(win[(s + k) % 7]), "f"(l[s][e]));
+        }
+      }
     }
     float r = 0.f;
 #pragma unroll
@@ -121,12 +129,27 @@ __global__ void __launch_bounds__(640, 1) fma_pattern_kernel(float* io, int iter
     }
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-      for (int s = 0; s < 7; ++s)
+      for (int s = 0; s < 7; ++s) {
+        if (MODE == 5) {          // likelihood-major: 7 window values per likelihood pair
 #pragma unroll
-        for (int k = 0; k < 7; ++k) {
-          asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[k][0]) : "l"(win[(s + k) % 7]), "l"(l[s][0]));
-          asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[k][1]) : "l"(win[(s + k) % 7]), "l"(l[s][1]));
+          for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int k = 0; k < 7; ++k) asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[k][e]) : "l"(win[(s + k) % 7]), "l"(l[s][e]));
+        } else if (MODE == 6) {   // snake: every instruction changes exactly one of the two shared operands
+#pragma unroll
+          for (int k = 0; k < 7; ++k) {
+            const int e0 = (k & 1), e1 = e0 ^ 1;
+            asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[k][e0]) : "l"(win[(s + k) % 7]), "l"(l[s][e0]));
+            asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[k][e1]) : "l"(win[(s + k) % 7]), "l"(l[s][e1]));
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 7; ++k) {
+            asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[k][0]) : "l"(win[(s + k) % 7]), "l"(l[s][0]));
+            asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[k][1]) : "l"(win[(s + k) % 7]), "l"(l[s][1]));
+          }
         }
+      }
     }
     float r = 0.f;
 #pragma unroll
@@ -149,7 +172,10 @@ extern "C" int jcm_fma_peak(float* scratch, int blocks, int iters, int packed, d
   if (packed >= 2) {  // operand-pattern probes: scratch needs 4096 + blocks*640 floats
     if (packed == 2) fma_pattern_kernel<2><<<blocks, 640, 0, (cudaStream_t)stream>>>(scratch, iters);
     else if (packed == 3) fma_pattern_kernel<3><<<blocks, 640, 0, (cudaStream_t)stream>>>(scratch, iters);
-    else fma_pattern_kernel<4><<<blocks, 640, 0, (cudaStream_t)stream>>>(scratch, iters);
+    else if (packed == 4) fma_pattern_kernel<4><<<blocks, 640, 0, (cudaStream_t)stream>>>(scratch, iters);
+    else if (packed == 5) fma_pattern_kernel<5><<<blocks, 640, 0, (cudaStream_t)stream>>>(scratch, iters);
+    else if (packed == 6) fma_pattern_kernel<6><<<blocks, 640, 0, (cudaStream_t)stream>>>(scratch, iters);
+    else fma_pattern_kernel<7><<<blocks, 640, 0, (cudaStream_t)stream>>>(scratch, iters);
     JCM_LAUNCH_CHECK();
     if (flops_out) *flops_out = 2.0 * 7.0 * 7.0 * 4.0 * (double)iters * 640.0 * (double)blocks;
     return JCM_OK;

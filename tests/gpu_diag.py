@@ -46,7 +46,7 @@ def timeit(fn, n=5, warm=2):
 
 def sec_peak():
     sms = jcm.lib().jcm_sm_count()
-    for packed in (0, 1, 2, 3, 4):
+    for packed in (0, 1, 2, 3, 4, 5, 6, 7):
         fl = [0.0]
 
         def run():
@@ -261,6 +261,20 @@ def sec_time():
             best, med = timeit(lambda: ops.conv2d_planes(h, w5, p['conv5/biases'], 512, 9, True), n=3, warm=1)
             fl = 2 * 114.6618e9 * B
             print('TIME conv5 %s B=%d: %.2f ms  %.1f TFLOP/s' % (precision, B, best, fl / best / 1e9))
+
+
+def sec_smtime():
+    K = 7
+    names = jcm.JOINT_NAMES[:K] + ['torso']
+    smp = jcm.PairwiseParams.from_distribution(jcm.get_pairwise_distr(), names, K, 60, 90)
+    ctx = jcm.Context(n_joints=K, flag_train=False)
+    for B in (16, 64):
+        _, cat, _ = make_sm_inputs(B, K, 60, 90)
+        cat = cat.to(dev)
+        best, med = timeit(lambda: jcm.spatial_model(cat, smp, ctx), n=10, warm=3)
+        fl = 2 * 1.469e9 * B
+        print('SMTIME spatial model fwd (bn + prep + conv + finish) B=%d: %.3f ms best %.3f median -> %.1f TFLOP/s algorithmic' % (
+            B, best, med, fl / best / 1e9))
 
 
 if __name__ == '__main__':
