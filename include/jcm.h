@@ -105,6 +105,62 @@ int jcm_spatial_model_fwd(const float* heat_map, const float* bn_scale, const fl
 int jcm_conv_mrf_fwd(const float* A, const float* Bmaps, float* out, void* workspace, long workspace_bytes, int b, int H,
                      int W, void* stream);
 
+/* ---- backward pass (the reference: TensorFlow autodiff via opt.compute_gradients(loss_tower), main.py:557-560) ------- */
+
+/* d(mean softmax-CE)/d logits * scale = scale * (softmax * sum(labels) - labels); lse from jcm_softmax_ce (main.py:239). */
+int jcm_softmax_ce_bwd(const float* logits, const float* labels, const float* lse, int B, int S, int K, int KL, float scale,
+                       float* dlogits, void* stream);
+
+/* backward of spatial_softmax (main.py:212-217): dx (+)= y * (dy - sum_s dy*y); dy has KD >= K channels. */
+int jcm_spatial_softmax_bwd(const float* y, const float* dy, int B, int S, int K, int KD, int accumulate, float* dx, void* stream);
+
+/* [2x2 SAME max-pool bwd] + training-mode batch-norm bwd + ReLU bwd of one conv_layer (main.py:156-169).
+ * a = ReLU output [B,H,W,C]; dout = gradient w.r.t. the layer output ([B,ceil(H/2),ceil(W/2),C] when pool), times dy_scale.
+ * Outputs: d_pre planes [B,H,W,C] (gradient w.r.t. the conv output), dgamma, dbeta, dbias [C].
+ * workspace: (4 * jcm_bn_relu_bwd_blocks(M_out, C) + 2) * C floats. */
+int jcm_bn_relu_bwd_blocks(long M_out, int C);
+int jcm_bn_relu_bwd(const float* a, const float* dout, const float* scale, const float* shift, const float* mean, const float* rstd,
+                    float dy_scale, int B, int H, int W, int C, int pool, void* d_hi, void* d_lo, float* d_f32, float* dgamma,
+                    float* dbeta, float* dbias, float* workspace, void* stream);
+
+/* column sums of x [M,C] (bias gradient of the last layer); partial: jcm_bn_stats_blocks(M,C)*2*C floats. */
+int jcm_colsum(const float* x, long M, int C, float* partial, float* out, void* stream);
+
+/* transpose of the up-sampling + 3-way average (main.py:58,67,69-70): d2 [B,H2,W2,C], d3 [B,H3,W3,C] (the full-resolution
+ * bank's gradient is dmerged / 3, folded into jcm_bn_relu_bwd's dy_scale). */
+int jcm_upsample_avg3_bwd(const float* dmerged, int B, int H, int W, int H2, int W2, int H3, int W3, int C, float* d2, float* d3,
+                          void* stream);
+
+/* fp32 [M,C] -> bf16 planes [M,Cpad] with zero-padded channels. */
+int jcm_pad_planes(const float* x, long M, int C, int Cpad, void* hi, void* lo, void* stream);
+
+/* weight gradient of tf.nn.conv2d (main.py:135): dw [k*k][Cin][dw_cout_stride] from input planes x [B,H,W,Cin] and output-gradient
+ * planes g [B,H,W,Gc].  tcgen05 GEMM per tap with the contraction over pixels (MN-major operands), split-K partial sums in
+ * `workspace` (jcm_conv2d_wgrad_workspace bytes), deterministic reduction.  The data gradient is jcm_conv2d_fwd on
+ * jcm_pack_weights(..., transpose = 1). */
+long jcm_conv2d_wgrad_workspace(int B, int H, int W, int Cin, int Gc, int ksize);
+int jcm_conv2d_wgrad(const void* x_hi, const void* x_lo, const void* g_hi, const void* g_lo, float* dw, void* workspace,
+                     long workspace_bytes, int B, int H, int W, int Cin, int Gc, int Cout, int dw_cout_stride, int ksize, void* stream);
+
+/* conv1 weight gradient in space-to-depth form [9][16][Cout] (as jcm_conv2d_wgrad writes it) -> [5,5,3,Cout]. */
+int jcm_unpack_s2d_grad(const float* g9, int Cout, float* dw, void* stream);
+
+/* backward of jcm_spatial_model_fwd.  fwd_workspace: the forward workspace of the same inputs. */
+long jcm_spatial_model_bwd_workspace(int B, int H, int W, int K, int P);
+int jcm_spatial_model_bwd(const float* g, const float* heat_map, const float* bn_scale, const float* bn_shift, const float* bn_mean,
+                          const float* bn_rstd, int train, const float* energies, const float* biases, const int* pair_target,
+                          const int* pair_cond, const void* fwd_workspace, void* workspace, long workspace_bytes, float* d_heat_map,
+                          float* dE, float* db, float* dgamma, float* dbeta, int B, int H, int W, int K, int P, void* stream);
+
+/* ---- optimizer on flat buffers (main.py:243-267 gradient mean, :195-205 weight decay, :302-309 clip, :501-506,577 Adam) --- */
+int jcm_optim_blocks(long n);
+/* g <- g * inv_world + lmbd * w (first n_decay elements); stats[0] = ||g||, stats[1] = sum w^2/2.  partial: 2*jcm_optim_blocks(n). */
+int jcm_grad_prepare(float* g, const float* w, long n, long n_decay, float inv_world, float lmbd, float* partial, float* stats,
+                     void* stream);
+/* w <- Adam_TF1(w, g * clip / max(stats[0], clip)) (momentum != 0: MomentumOptimizer with b1 as the momentum). */
+int jcm_clip_adam(float* w, const float* g, float* m, float* v, long n, const float* stats, float clip, float lr_t, float b1,
+                  float b2, float eps, int momentum, void* stream);
+
 /* ---- measurement / test support --------------------------------------------------------------------------------- */
 
 /* FP32 FMA peak loop (packed = 1: FFMA2); flops_out = FLOPs of one launch. scratch: blocks*512 floats. */

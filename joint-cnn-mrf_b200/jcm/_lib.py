@@ -34,6 +34,21 @@ SIGNATURES = {
     'jcm_spatial_model_workspace': (_L, [_I, _I, _I, _I, _I]),
     'jcm_spatial_model_fwd': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
     'jcm_conv_mrf_fwd': (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _P]),
+    'jcm_softmax_ce_bwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P]),
+    'jcm_spatial_softmax_bwd': (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    'jcm_bn_relu_bwd_blocks': (_I, [_L, _I]),
+    'jcm_bn_relu_bwd': (_I, [_P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'jcm_colsum': (_I, [_P, _L, _I, _P, _P, _P]),
+    'jcm_upsample_avg3_bwd': (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    'jcm_pad_planes': (_I, [_P, _L, _I, _I, _P, _P, _P]),
+    'jcm_conv2d_wgrad_workspace': (_L, [_I, _I, _I, _I, _I, _I]),
+    'jcm_conv2d_wgrad': (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'jcm_unpack_s2d_grad': (_I, [_P, _I, _P, _P]),
+    'jcm_spatial_model_bwd_workspace': (_L, [_I, _I, _I, _I, _I]),
+    'jcm_spatial_model_bwd': (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    'jcm_optim_blocks': (_I, [_L]),
+    'jcm_grad_prepare': (_I, [_P, _P, _L, _L, _F, _F, _P, _P, _P]),
+    'jcm_clip_adam': (_I, [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _I, _P]),
     'jcm_fma_peak': (_I, [_P, _I, _I, _I, _P, _P]),
     'jcm_debug_conv2d_naive': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
 }

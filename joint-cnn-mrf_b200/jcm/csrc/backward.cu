@@ -1,0 +1,387 @@
+// Backward (HBM-bound) kernels of the part detector and the loss heads.  The reference gets these from TensorFlow's
+// autodiff of main.py:29-74,212-240 (`opt.compute_gradients(loss_tower)`, main.py:557-560); here they are written out:
+//   jcm_softmax_ce_bwd        d(mean CE)/d logits = (softmax * sum(y) - y) / (B*K)                         (main.py:239)
+//   jcm_spatial_softmax_bwd   dx = y * (dy - sum_s dy*y)   (joint training: spatial model input -> PD logits, main.py:523-530)
+//   jcm_bn_relu_bwd           [2x2 SAME max-pool bwd] + training-mode batch-norm bwd + ReLU bwd in two passes
+//                             (reduce: sum dy, sum dy*xhat per channel; apply: d_pre planes + per-block bias-grad partials)
+//   jcm_colsum_finalize       deterministic reduction of per-block column partials (bias / gamma / beta gradients)
+//   jcm_upsample_avg3_bwd     transpose of the legacy-bilinear up-sampling + 3-way average (gather form, no atomics)
+//   jcm_pad_planes            fp32 [M,C] -> bf16 planes [M,Cpad] (zero padded channels; conv6's K-channel gradient)
+//   jcm_unpack_s2d_grad       conv1 weight gradient [9][16][Cout] (space-to-depth form) -> [5,5,3,Cout]
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ float blk_sum(float v, float* sh) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += sh[i];
+  return r;
+}
+
+// one block per (image, joint)
+__global__ void softmax_ce_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ labels, const float* __restrict__ lse,
+                                      int S, int K, int KL, float scale, float* __restrict__ dlogits) {
+  __shared__ float sh[32];
+  const int n = blockIdx.x / K, k = blockIdx.x % K;
+  const float* src = logits + (long)n * S * K + k;
+  const float* lab = labels + (long)n * S * KL + k;
+  float* dst = dlogits + (long)n * S * K + k;
+  float sy = 0.f;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) sy += lab[(long)s * KL];
+  sy = blk_sum(sy, sh);
+  const float l = lse[blockIdx.x];
+  for (int s = threadIdx.x; s < S; s += blockDim.x)
+    dst[(long)s * K] = scale * (expf(src[(long)s * K] - l) * sy - lab[(long)s * KL]);
+}
+
+// y [B,S,K] softmax output, dy [B,S,KD] (first K channels), dx [B,S,K] (+= if accumulate)
+__global__ void spatial_softmax_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, int S, int K, int KD, int accumulate,
+                                           float* __restrict__ dx) {
+  __shared__ float sh[32];
+  const int n = blockIdx.x / K, k = blockIdx.x % K;
+  const float* yy = y + (long)n * S * K + k;
+  const float* dd = dy + (long)n * S * KD + k;
+  float* out = dx + (long)n * S * K + k;
+  float dot = 0.f;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) dot += yy[(long)s * K] * dd[(long)s * KD];
+  dot = blk_sum(dot, sh);
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const float v = yy[(long)s * K] * (dd[(long)s * KD] - dot);
+    if (accumulate) out[(long)s * K] += v; else out[(long)s * K] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ BN + ReLU (+pool) backward
+// a [B,H,W,C] = ReLU output (BN input); dout = gradient w.r.t. the BN output ([B,H,W,C], or the pooled [B,Ho,Wo,C] when pool).
+// Work item = one output position of `dout` x 4 channels.  Row slabs per block as in bn_stats_kernel, so all per-channel
+// partial sums are deterministic.  PASS 0: partial[blk][0][c] = sum dy, partial[blk][1][c] = sum dy*xhat.
+// PASS 1: writes d_pre (gradient w.r.t. the conv output before ReLU) as bf16 planes (+fp32) and partial[blk][0][c] = sum d_pre.
+struct BnBwdArgs {
+  const float* a;
+  const float* dout;
+  const float* scale;      // gamma * rstd
+  const float* shift;      // beta - mean * scale
+  const float* mean;
+  const float* rstd;
+  const float* sums;       // [2][C]: sum dy, sum dy*xhat (PASS 1)
+  float dy_scale;          // constant factor folded into dout (1/3 of the bank average)
+  int B, H, W, C, pool;
+  float inv_count;         // 1 / (B*H*W)
+  __nv_bfloat16* hi;
+  __nv_bfloat16* lo;
+  float* d_f32;
+  float* partial;          // [grid][2][C]
+};
+
+template <int PASS>
+__global__ void bn_relu_bwd_kernel(BnBwdArgs p) {
+  extern __shared__ float sh[];  // [kThreads][8]
+  const int C4 = p.C / 4;
+  const int lanes = kThreads / C4;
+  const int g = threadIdx.x % C4, rl = threadIdx.x / C4;
+  const int Ho = p.pool ? (p.H + 1) / 2 : p.H, Wo = p.pool ? (p.W + 1) / 2 : p.W;
+  const long M = (long)p.B * Ho * Wo;
+  const long per_blk = (M + gridDim.x - 1) / gridDim.x;
+  const long r0 = blockIdx.x * per_blk;
+  long r1 = r0 + per_blk;
+  if (r1 > M) r1 = M;
+  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+  if (rl < lanes) {
+    const float4 sc = reinterpret_cast<const float4*>(p.scale)[g];
+    const float4 sf = reinterpret_cast<const float4*>(p.shift)[g];
+    const float4 mu = reinterpret_cast<const float4*>(p.mean)[g];
+    const float4 rs = reinterpret_cast<const float4*>(p.rstd)[g];
+    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, sfv[4] = {sf.x, sf.y, sf.z, sf.w};
+    const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, rsv[4] = {rs.x, rs.y, rs.z, rs.w};
+    float m_dy[4] = {0.f, 0.f, 0.f, 0.f}, m_dyx[4] = {0.f, 0.f, 0.f, 0.f};
+    if (PASS == 1) {
+      const float4 a0 = reinterpret_cast<const float4*>(p.sums)[g];
+      const float4 a1 = reinterpret_cast<const float4*>(p.sums + p.C)[g];
+      m_dy[0] = a0.x * p.inv_count; m_dy[1] = a0.y * p.inv_count; m_dy[2] = a0.z * p.inv_count; m_dy[3] = a0.w * p.inv_count;
+      m_dyx[0] = a1.x * p.inv_count; m_dyx[1] = a1.y * p.inv_count; m_dyx[2] = a1.z * p.inv_count; m_dyx[3] = a1.w * p.inv_count;
+    }
+    for (long r = r0 + rl; r < r1; r += lanes) {
+      const float4 d4 = *reinterpret_cast<const float4*>(p.dout + r * p.C + g * 4);
+      const float dv[4] = {d4.x * p.dy_scale, d4.y * p.dy_scale, d4.z * p.dy_scale, d4.w * p.dy_scale};
+      if (!p.pool) {
+        const float4 a4 = *reinterpret_cast<const float4*>(p.a + r * p.C + g * 4);
+        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+        float o[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float xh = (av[c] - muv[c]) * rsv[c];
+          if (PASS == 0) {
+            s0[c] += dv[c];
+            s1[c] += dv[c] * xh;
+          } else {
+            const float da = scv[c] * (dv[c] - m_dy[c] - xh * m_dyx[c]);
+            o[c] = av[c] > 0.f ? da : 0.f;
+            s0[c] += o[c];
+          }
+        }
+        if (PASS == 1) {
+          const long i4 = r * C4 + g;
+          __align__(8) __nv_bfloat16 h[4];
+          __align__(8) __nv_bfloat16 l[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) split_bf16(o[c], h[c], l[c]);
+          reinterpret_cast<uint2*>(p.hi)[i4] = *reinterpret_cast<uint2*>(h);
+          if (p.lo) reinterpret_cast<uint2*>(p.lo)[i4] = *reinterpret_cast<uint2*>(l);
+          if (p.d_f32) reinterpret_cast<float4*>(p.d_f32)[i4] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      } else {
+        const int xo = (int)(r % Wo);
+        const long t = r / Wo;
+        const int yo = (int)(t % Ho);
+        const int n = (int)(t / Ho);
+        const int y0 = 2 * yo, x0 = 2 * xo;
+        float av[4][4];   // [window element][channel]
+        bool ok[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int yy = y0 + (e >> 1), xx = x0 + (e & 1);
+          ok[e] = yy < p.H && xx < p.W;
+          float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok[e]) a4 = *reinterpret_cast<const float4*>(p.a + (((long)n * p.H + yy) * p.W + xx) * p.C + g * 4);
+          av[e][0] = a4.x; av[e][1] = a4.y; av[e][2] = a4.z; av[e][3] = a4.w;
+        }
+        float o[4][4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          int best = 0;
+          float bv = fmaf(av[0][c], scv[c], sfv[c]);
+#pragma unroll
+          for (int e = 1; e < 4; ++e) {
+            const float v = fmaf(av[e][c], scv[c], sfv[c]);
+            if (ok[e] && v > bv) { bv = v; best = e; }
+          }
+          if (PASS == 0) {
+            const float xh = (av[best][c] - muv[c]) * rsv[c];
+            s0[c] += dv[c];
+            s1[c] += dv[c] * xh;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float xh = (av[e][c] - muv[c]) * rsv[c];
+              const float dy = (e == best) ? dv[c] : 0.f;
+              const float da = scv[c] * (dy - m_dy[c] - xh * m_dyx[c]);
+              o[e][c] = (ok[e] && av[e][c] > 0.f) ? da : 0.f;
+              s0[c] += o[e][c];
+            }
+          }
+        }
+        if (PASS == 1) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (!ok[e]) continue;
+            const int yy = y0 + (e >> 1), xx = x0 + (e & 1);
+            const long i4 = (((long)n * p.H + yy) * p.W + xx) * C4 + g;
+            __align__(8) __nv_bfloat16 h[4];
+            __align__(8) __nv_bfloat16 l[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) split_bf16(o[e][c], h[c], l[c]);
+            reinterpret_cast<uint2*>(p.hi)[i4] = *reinterpret_cast<uint2*>(h);
+            if (p.lo) reinterpret_cast<uint2*>(p.lo)[i4] = *reinterpret_cast<uint2*>(l);
+            if (p.d_f32) reinterpret_cast<float4*>(p.d_f32)[i4] = make_float4(o[e][0], o[e][1], o[e][2], o[e][3]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    sh[threadIdx.x * 8 + c] = s0[c];
+    sh[threadIdx.x * 8 + 4 + c] = s1[c];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    const int gg = c / 4, v = c % 4;
+    float t0 = 0.f, t1 = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      t0 += sh[(l * C4 + gg) * 8 + v];
+      t1 += sh[(l * C4 + gg) * 8 + 4 + v];
+    }
+    p.partial[((long)blockIdx.x * 2 + 0) * p.C + c] = t0;
+    p.partial[((long)blockIdx.x * 2 + 1) * p.C + c] = t1;
+  }
+}
+
+// sums[j][c] = sum over blocks of partial[blk][j][c] (double accumulation); optionally scaled by mul[c]
+__global__ void colsum_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, int rows, float* __restrict__ sums) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * C) return;
+  const int j = idx / C, c = idx % C;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += (double)partial[((long)b * 2 + j) * C + c];
+  sums[idx] = (float)s;
+}
+
+// ------------------------------------------------------------------------------------------------ upsample/average backward
+__device__ __forceinline__ void legacy_tap(int dst, int n_in, int n_out, int& lo, int& hi, float& w) {
+  const float scale = (float)n_in / (float)n_out;
+  const float src = (float)dst * scale;
+  lo = (int)floorf(src);
+  hi = min(lo + 1, n_in - 1);
+  w = src - (float)lo;
+}
+
+// dlow[n,p,q,c] = mul * sum over (y,x) of dm[n,y,x,c] * wy(y->p) * wx(x->q)   (transpose of resize_images [Hi,Wi] -> [H,W])
+__global__ void upsample_bwd_kernel(const float* __restrict__ dm, int B, int H, int W, int Hi, int Wi, int C, float mul,
+                                    float* __restrict__ dlow) {
+  const int C4 = C / 4;
+  const long total = (long)B * Hi * Wi * C4;
+  const int ry = (H + Hi - 1) / Hi + 1, rx = (W + Wi - 1) / Wi + 1;   // how far a low-res pixel's footprint can reach
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    long t = i / C4;
+    const int q = (int)(t % Wi);
+    t /= Wi;
+    const int pp = (int)(t % Hi);
+    const int n = (int)(t / Hi);
+    const int ylo0 = max(0, (int)(((long)(pp - 1) * H) / Hi) - 1), yhi0 = min(H - 1, (int)(((long)(pp + 1) * H) / Hi) + ry);
+    const int xlo0 = max(0, (int)(((long)(q - 1) * W) / Wi) - 1), xhi0 = min(W - 1, (int)(((long)(q + 1) * W) / Wi) + rx);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int y = ylo0; y <= yhi0; ++y) {
+      int lo, hi;
+      float w;
+      legacy_tap(y, Hi, H, lo, hi, w);
+      const float wyv = (lo == pp ? 1.f - w : 0.f) + (hi == pp ? w : 0.f);
+      if (wyv == 0.f) continue;
+      for (int x = xlo0; x <= xhi0; ++x) {
+        int lo2, hi2;
+        float w2;
+        legacy_tap(x, Wi, W, lo2, hi2, w2);
+        const float wxv = (lo2 == q ? 1.f - w2 : 0.f) + (hi2 == q ? w2 : 0.f);
+        if (wxv == 0.f) continue;
+        const float4 d = *reinterpret_cast<const float4*>(dm + (((long)n * H + y) * W + x) * C + c4 * 4);
+        const float ww = wyv * wxv;
+        acc.x += d.x * ww; acc.y += d.y * ww; acc.z += d.z * ww; acc.w += d.w * ww;
+      }
+    }
+    reinterpret_cast<float4*>(dlow)[i] = make_float4(acc.x * mul, acc.y * mul, acc.z * mul, acc.w * mul);
+  }
+}
+
+__global__ void pad_planes_kernel(const float* __restrict__ x, long M, int C, int Cpad, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo) {
+  const long total = M * Cpad;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cpad);
+    const long r = i / Cpad;
+    const float v = c < C ? x[r * C + c] : 0.f;
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+// g9 [9][16][Cout] (fp32, s2d form as jcm_conv2d_wgrad writes it: tap, channel, cout) -> dw [5][5][3][Cout]
+__global__ void unpack_s2d_grad_kernel(const float* __restrict__ g9, int Cout, float* __restrict__ dw) {
+  const int total = 75 * Cout;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int co = idx % Cout;
+    const int r = idx / Cout;
+    const int ci = r % 3, tx = (r / 3) % 5, ty = r / 15;
+    const int by = (ty + 1) >> 1, sy = (ty + 1) & 1, bx = (tx + 1) >> 1, sx = (tx + 1) & 1;
+    dw[idx] = g9[((by * 3 + bx) * 16 + (sy * 2 + sx) * 3 + ci) * Cout + co];
+  }
+}
+
+inline int grid_for(long total, int threads) {
+  long g = (total + threads - 1) / threads;
+  long cap = (long)jcm_num_sms() * 16;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" int jcm_softmax_ce_bwd(const float* logits, const float* labels, const float* lse, int B, int S, int K, int KL, float scale,
+                                  float* dlogits, void* stream) {
+  JCM_CHECK_ARG(logits && labels && lse && dlogits && KL >= K, "jcm_softmax_ce_bwd: bad arguments");
+  softmax_ce_bwd_kernel<<<B * K, 256, 0, (cudaStream_t)stream>>>(logits, labels, lse, S, K, KL, scale, dlogits);
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}
+
+extern "C" int jcm_spatial_softmax_bwd(const float* y, const float* dy, int B, int S, int K, int KD, int accumulate, float* dx,
+                                       void* stream) {
+  JCM_CHECK_ARG(y && dy && dx && KD >= K, "jcm_spatial_softmax_bwd: bad arguments");
+  spatial_softmax_bwd_kernel<<<B * K, 256, 0, (cudaStream_t)stream>>>(y, dy, S, K, KD, accumulate, dx);
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}
+
+extern "C" int jcm_bn_relu_bwd_blocks(long M_out, int C) {
+  (void)C;
+  long b = M_out / 32;
+  if (b < 1) b = 1;
+  long cap = (long)jcm_num_sms() * 8;
+  return (int)(b < cap ? b : cap);
+}
+
+// Two passes.  workspace: 2 * blocks * 2 * C + 2 * C floats (partials of both passes + the reduced sums).
+// Outputs: d_pre planes [B,H,W,C] (hi[, lo]) and optionally fp32; dgamma[C], dbeta[C], dbias[C] (= column sums of d_pre).
+extern "C" int jcm_bn_relu_bwd(const float* a, const float* dout, const float* scale, const float* shift, const float* mean,
+                               const float* rstd, float dy_scale, int B, int H, int W, int C, int pool, void* d_hi, void* d_lo,
+                               float* d_f32, float* dgamma, float* dbeta, float* dbias, float* workspace, void* stream) {
+  JCM_CHECK_ARG(a && dout && scale && shift && mean && rstd && d_hi && dgamma && dbeta && dbias && workspace, "jcm_bn_relu_bwd: null pointer");
+  JCM_CHECK_ARG((C % 4) == 0 && C / 4 <= kThreads, "jcm_bn_relu_bwd: C must be a multiple of 4 and <= 1024 (got %d)", C);
+  const int Ho = pool ? (H + 1) / 2 : H, Wo = pool ? (W + 1) / 2 : W;
+  const long M_out = (long)B * Ho * Wo;
+  const int blocks = jcm_bn_relu_bwd_blocks(M_out, C);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* part0 = workspace;
+  float* part1 = workspace + (long)blocks * 2 * C;
+  float* sums = part1 + (long)blocks * 2 * C;
+  BnBwdArgs p;
+  p.a = a; p.dout = dout; p.scale = scale; p.shift = shift; p.mean = mean; p.rstd = rstd; p.sums = sums; p.dy_scale = dy_scale;
+  p.B = B; p.H = H; p.W = W; p.C = C; p.pool = pool; p.inv_count = 1.0f / (float)((long)B * H * W);
+  p.hi = (__nv_bfloat16*)d_hi; p.lo = (__nv_bfloat16*)d_lo; p.d_f32 = d_f32; p.partial = part0;
+  const size_t shb = kThreads * 8 * sizeof(float);
+  bn_relu_bwd_kernel<0><<<blocks, kThreads, shb, st>>>(p);
+  JCM_LAUNCH_CHECK();
+  colsum_finalize_kernel<<<jcm_cdiv(2 * C, 128), 128, 0, st>>>(part0, blocks, C, 2, sums);
+  JCM_LAUNCH_CHECK();
+  p.partial = part1;
+  bn_relu_bwd_kernel<1><<<blocks, kThreads, shb, st>>>(p);
+  JCM_LAUNCH_CHECK();
+  colsum_finalize_kernel<<<jcm_cdiv(C, 128), 128, 0, st>>>(part1, blocks, C, 1, dbias);
+  JCM_LAUNCH_CHECK();
+  // dbeta = sum dy, dgamma = sum dy * xhat
+  JCM_CUDA(cudaMemcpyAsync(dbeta, sums, C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  JCM_CUDA(cudaMemcpyAsync(dgamma, sums + C, C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return JCM_OK;
+}
+
+// column sums of x [M,C] (bias gradient of the last layer): partial workspace as jcm_bn_stats
+extern "C" int jcm_upsample_avg3_bwd(const float* dmerged, int B, int H, int W, int H2, int W2, int H3, int W3, int C, float* d2,
+                                     float* d3, void* stream) {
+  JCM_CHECK_ARG(dmerged && d2 && d3 && (C % 4) == 0, "jcm_upsample_avg3_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  upsample_bwd_kernel<<<grid_for((long)B * H2 * W2 * (C / 4), 256), 256, 0, st>>>(dmerged, B, H, W, H2, W2, C, 1.0f / 3.0f, d2);
+  JCM_LAUNCH_CHECK();
+  upsample_bwd_kernel<<<grid_for((long)B * H3 * W3 * (C / 4), 256), 256, 0, st>>>(dmerged, B, H, W, H3, W3, C, 1.0f / 3.0f, d3);
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}
+
+extern "C" int jcm_pad_planes(const float* x, long M, int C, int Cpad, void* hi, void* lo, void* stream) {
+  JCM_CHECK_ARG(x && hi && Cpad >= C && M > 0, "jcm_pad_planes: bad arguments");
+  pad_planes_kernel<<<grid_for(M * Cpad, 256), 256, 0, (cudaStream_t)stream>>>(x, M, C, Cpad, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}
+
+extern "C" int jcm_unpack_s2d_grad(const float* g9, int Cout, float* dw, void* stream) {
+  JCM_CHECK_ARG(g9 && dw && Cout > 0, "jcm_unpack_s2d_grad: bad arguments");
+  unpack_s2d_grad_kernel<<<grid_for(75L * Cout, 256), 256, 0, (cudaStream_t)stream>>>(g9, Cout, dw);
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}

@@ -398,3 +398,338 @@ extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_
   JCM_LAUNCH_CHECK();
   return JCM_OK;
 }
+
+// =====================================================================================================================
+// Weight gradient:  dW[tap, ci, co] = sum_{n,y,x} X[n, y+dy-pad, x+dx-pad, ci] * G[n, y, x, co]      (G = d loss / d conv output)
+//
+// Per tap this is a GEMM whose contraction runs over PIXELS, so both operands are "MN-major" for the tensor core: a TMA box
+// {64 channels, TW, TH, 1} lands in shared memory as [64 pixels][128 B of channels] (SWIZZLE_128B) and is consumed directly
+// as a UMMA operand with a_major = b_major = MN (16 pixels = one K=16 MMA step, channel blocks of 64 are LBO apart).
+// The tensor with more channels provides M (tile 128, zero-filled by TMA out-of-bounds when it has fewer), the other one N.
+// Work item = (k-split, tap, M tile, N tile): loops over its share of the 64-pixel patches; partial sums go to
+// partial[split][tap][M][N] and are reduced deterministically by wgrad_reduce_kernel (no atomics).
+// =====================================================================================================================
+namespace {
+
+constexpr int kWgPix = 64;   // pixels per k-block
+
+struct WgradParams {
+  int B, H, W;
+  int TW, TH, tiles_x, tiles_y;
+  int ksize, pad, taps;
+  int m_tiles, n_tiles, block_n, m_pad, n_pad;
+  int shift_m, shift_n;            // 1 when that operand is the (shifted) layer input X, 0 when it is the gradient G
+  int kc_n, kc_m;                  // channels per N-side / M-side box: 64, 32 or 16
+  int splits, total_patches;
+  int terms, stages, a_bytes, b_bytes, stage_bytes;
+  float* partial;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_m_hi, const __grid_constant__ CUtensorMap map_m_lo,
+                  const __grid_constant__ CUtensorMap map_n_hi, const __grid_constant__ CUtensorMap map_n_lo,
+                  const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[kMaxStages]);
+  const uint32_t bar_tfull = smem_u32(&bars[2 * kMaxStages]);
+  const uint32_t bar_tempty = smem_u32(&bars[2 * kMaxStages + 2]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_tfull + 8 * s, 1);
+      mbar_init(bar_tempty + 8 * s, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int tasks_per_split = p.taps * p.m_tiles * p.n_tiles;
+  const int total_tasks = p.splits * tasks_per_split;
+  const int patches_per_img = p.tiles_x * p.tiles_y;
+  const int m_boxes = kTileM / p.kc_m;
+  const int n_boxes = p.block_n / p.kc_n;
+  const int m_box_bytes = kWgPix * p.kc_m * 2;
+  const int n_box_bytes = kWgPix * p.kc_n * 2;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int task = blockIdx.x; task < total_tasks; task += gridDim.x) {
+        const int split = task / tasks_per_split;
+        int r = task - split * tasks_per_split;
+        const int tap = r / (p.m_tiles * p.n_tiles);
+        r -= tap * (p.m_tiles * p.n_tiles);
+        const int mt = r / p.n_tiles, nt = r - mt * p.n_tiles;
+        const int dy = tap / p.ksize - p.pad, dx = tap % p.ksize - p.pad;
+        const int p0 = (int)((long)split * p.total_patches / p.splits);
+        const int p1 = (int)((long)(split + 1) * p.total_patches / p.splits);
+        for (int patch = p0; patch < p1; ++patch) {
+          const int img = patch / patches_per_img;
+          const int q = patch - img * patches_per_img;
+          const int ty = q / p.tiles_x, tx = q - ty * p.tiles_x;
+          const int x0 = tx * p.TW, y0 = ty * p.TH;
+          for (int term = 0; term < p.terms; ++term) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            const uint32_t sa = smem_base + stage * p.stage_bytes;
+            const uint32_t sb = sa + p.a_bytes;
+            const uint32_t fb = bar_full + 8 * stage;
+            mbar_expect_tx(fb, p.a_bytes + p.b_bytes);
+            const void* mm = (term == 1) ? (const void*)&map_m_lo : (const void*)&map_m_hi;
+            const void* mn = (term == 2) ? (const void*)&map_n_lo : (const void*)&map_n_hi;
+            for (int b = 0; b < m_boxes; ++b)
+              tma_load_4d(sa + b * m_box_bytes, mm, fb, mt * kTileM + b * p.kc_m, x0 + p.shift_m * dx, y0 + p.shift_m * dy, img);
+            for (int b = 0; b < n_boxes; ++b)
+              tma_load_4d(sb + b * n_box_bytes, mn, fb, nt * p.block_n + b * p.kc_n, x0 + p.shift_n * dx, y0 + p.shift_n * dy, img);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // D=f32, A=B=bf16, both MN-major (bits 15, 16), N = block_n, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.block_n >> 3) << 17) |
+                             ((uint32_t)(kTileM >> 4) << 24);
+      const uint32_t n_row_bytes = p.kc_n * 2, m_row_bytes = p.kc_m * 2;
+      const uint32_t n_layout = (p.kc_n == 64) ? 2u : (p.kc_n == 32 ? 4u : 6u);
+      const uint32_t m_layout = (p.kc_m == 64) ? 2u : (p.kc_m == 32 ? 4u : 6u);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int task = blockIdx.x; task < total_tasks; task += gridDim.x) {
+        const int split = task / tasks_per_split;
+        const int p0 = (int)((long)split * p.total_patches / p.splits);
+        const int p1 = (int)((long)(split + 1) * p.total_patches / p.splits);
+        const int num_kb = (p1 - p0) * p.terms;
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * p.stage_bytes;
+          const uint32_t sb = sa + p.a_bytes;
+#pragma unroll
+          for (int k = 0; k < kWgPix / 16; ++k) {
+            // MN-major: leading byte offset = distance between channel blocks (one TMA box), stride byte offset = 8 pixel rows
+            uint64_t adesc = make_smem_desc(sa + k * 16 * m_row_bytes, 8 * m_row_bytes, m_layout);
+            adesc = (adesc & ~((uint64_t)0x3FFF << 16)) | ((uint64_t)((m_box_bytes >> 4) & 0x3FFF) << 16);
+            uint64_t bdesc = make_smem_desc(sb + k * 16 * n_row_bytes, 8 * n_row_bytes, n_layout);
+            bdesc = (bdesc & ~((uint64_t)0x3FFF << 16)) | ((uint64_t)((n_box_bytes >> 4) & 0x3FFF) << 16);
+            tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+          }
+          tc_commit(bar_empty + 8 * stage);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(bar_tfull + 8 * acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: accumulator -> partial[split][tap][m][n] =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int task = blockIdx.x; task < total_tasks; task += gridDim.x) {
+      const int split = task / tasks_per_split;
+      int r = task - split * tasks_per_split;
+      const int tap = r / (p.m_tiles * p.n_tiles);
+      r -= tap * (p.m_tiles * p.n_tiles);
+      const int mt = r / p.n_tiles, nt = r - mt * p.n_tiles;
+      float* orow = p.partial + (((long)split * p.taps + tap) * p.m_pad + mt * kTileM + row) * p.n_pad + nt * p.block_n;
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t v[32];
+        tc_ld32(taddr0 + c0, v);
+        tc_ld_wait();
+        if (c0 + 32 <= p.block_n) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(orow + c0 + j) =
+                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < p.block_n) orow[c0 + j] = __uint_as_float(v[j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// dw[tap][ci][co] (+)= sum_split partial[split][tap][m][n],  (m, n) = (ci, co) when the input provided M, else (co, ci)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int m_pad, int n_pad, int Cin, int Cout,
+                                    int dw_cout_stride, int x_is_m, float* __restrict__ dw) {
+  const long total = (long)taps * Cin * Cout;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int co = (int)(idx % Cout);
+    const long t = idx / Cout;
+    const int ci = (int)(t % Cin);
+    const int tap = (int)(t / Cin);
+    const int m = x_is_m ? ci : co, n = x_is_m ? co : ci;
+    float s = 0.f;
+    for (int sp = 0; sp < splits; ++sp) s += partial[(((long)sp * taps + tap) * m_pad + m) * n_pad + n];
+    dw[((long)tap * Cin + ci) * dw_cout_stride + co] = s;
+  }
+}
+
+void pick_patch64(int H, int W, int* TW, int* TH) {
+  int best = 1 << 30, bw = 16, bh = 4;
+  const int cand[5][2] = {{16, 4}, {8, 8}, {32, 2}, {64, 1}, {4, 16}};
+  for (int i = 0; i < 5; ++i) {
+    int t = jcm_cdiv(W, cand[i][0]) * jcm_cdiv(H, cand[i][1]);
+    if (t < best) { best = t; bw = cand[i][0]; bh = cand[i][1]; }
+  }
+  *TW = bw;
+  *TH = bh;
+}
+
+struct WgradPlan {
+  int x_is_m, m_ch, n_ch, m_tiles, n_tiles, block_n, kc_n, kc_m, m_pad, n_pad, splits, TW, TH, tiles_x, tiles_y, total_patches;
+};
+
+void plan_wgrad(int B, int H, int W, int Cin, int Gc, int ksize, WgradPlan* pl) {
+  pl->x_is_m = Cin >= Gc;
+  pl->m_ch = pl->x_is_m ? Cin : Gc;
+  pl->n_ch = pl->x_is_m ? Gc : Cin;
+  pl->m_tiles = jcm_cdiv(pl->m_ch, kTileM);
+  pl->block_n = pl->n_ch <= 256 ? pl->n_ch : 256;
+  pl->n_tiles = jcm_cdiv(pl->n_ch, pl->block_n);
+  pl->kc_n = (pl->block_n % 64) == 0 ? 64 : ((pl->block_n % 32) == 0 ? 32 : 16);
+  pl->kc_m = (pl->m_ch % 64) == 0 ? 64 : ((pl->m_ch % 32) == 0 ? 32 : 16);
+  pl->m_pad = pl->m_tiles * kTileM;
+  pl->n_pad = pl->n_tiles * pl->block_n;
+  pick_patch64(H, W, &pl->TW, &pl->TH);
+  pl->tiles_x = jcm_cdiv(W, pl->TW);
+  pl->tiles_y = jcm_cdiv(H, pl->TH);
+  pl->total_patches = B * pl->tiles_x * pl->tiles_y;
+  // enough independent work items for ~4 waves of the persistent grid, each with at least 8 patches to amortise the epilogue
+  const int base = ksize * ksize * pl->m_tiles * pl->n_tiles;
+  int s = jcm_cdiv(4 * jcm_num_sms(), base);
+  if (s > pl->total_patches / 8) s = pl->total_patches / 8;
+  if (s < 1) s = 1;
+  if (s > 64) s = 64;
+  pl->splits = s;
+}
+
+}  // namespace
+
+// bytes of fp32 partial sums jcm_conv2d_wgrad needs in `workspace`
+extern "C" long jcm_conv2d_wgrad_workspace(int B, int H, int W, int Cin, int Gc, int ksize) {
+  WgradPlan pl;
+  plan_wgrad(B, H, W, Cin, Gc, ksize, &pl);
+  return (long)pl.splits * ksize * ksize * pl.m_pad * pl.n_pad * (long)sizeof(float);
+}
+
+// x planes [B,H,W,Cin] (layer input, Cin multiple of 16), g planes [B,H,W,Gc] (gradient w.r.t. the conv output, Gc = Cout padded
+// to a multiple of 16) -> dw fp32 [k*k][Cin][dw_cout_stride] (first Cout columns written).  Gradient of tf.nn.conv2d w.r.t. its
+// filter (TF autodiff of main.py:135).
+extern "C" int jcm_conv2d_wgrad(const void* x_hi, const void* x_lo, const void* g_hi, const void* g_lo, float* dw, void* workspace,
+                                long workspace_bytes, int B, int H, int W, int Cin, int Gc, int Cout, int dw_cout_stride, int ksize,
+                                void* stream) {
+  JCM_CHECK_ARG(x_hi && g_hi && dw && workspace, "jcm_conv2d_wgrad: null pointer");
+  JCM_CHECK_ARG((x_lo == nullptr) == (g_lo == nullptr), "jcm_conv2d_wgrad: x_lo and g_lo must both be given or both NULL");
+  JCM_CHECK_ARG(B > 0 && H > 0 && W > 0 && (ksize & 1), "jcm_conv2d_wgrad: bad shape");
+  JCM_CHECK_ARG((Cin % 16) == 0 && (Gc % 16) == 0 && Cout <= Gc && Cout <= dw_cout_stride, "jcm_conv2d_wgrad: channel counts must be multiples of 16 (Cin=%d Gc=%d)", Cin, Gc);
+  WgradPlan pl;
+  plan_wgrad(B, H, W, Cin, Gc, ksize, &pl);
+  JCM_CHECK_ARG(pl.n_ch % pl.block_n == 0, "jcm_conv2d_wgrad: N-side channel count %d must be <= 256 or a multiple of 256", pl.n_ch);
+  if (workspace_bytes < jcm_conv2d_wgrad_workspace(B, H, W, Cin, Gc, ksize)) {
+    jcm_set_error("jcm_conv2d_wgrad: workspace too small");
+    return JCM_EWORKSPACE;
+  }
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.H = H; p.W = W;
+  p.TW = pl.TW; p.TH = pl.TH; p.tiles_x = pl.tiles_x; p.tiles_y = pl.tiles_y;
+  p.ksize = ksize; p.pad = (ksize - 1) / 2; p.taps = ksize * ksize;
+  p.m_tiles = pl.m_tiles; p.n_tiles = pl.n_tiles; p.block_n = pl.block_n; p.m_pad = pl.m_pad; p.n_pad = pl.n_pad;
+  p.shift_m = pl.x_is_m ? 1 : 0; p.shift_n = pl.x_is_m ? 0 : 1;
+  p.kc_n = pl.kc_n; p.kc_m = pl.kc_m;
+  p.splits = pl.splits; p.total_patches = pl.total_patches;
+  p.terms = x_lo ? 3 : 1;
+  p.a_bytes = kTileM * kWgPix * 2;
+  p.b_bytes = pl.block_n * kWgPix * 2;
+  p.stage_bytes = ((p.a_bytes + p.b_bytes + 1023) / 1024) * 1024;
+  p.stages = (200 * 1024) / p.stage_bytes;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  p.partial = (float*)workspace;
+
+  const void* m_hi = pl.x_is_m ? x_hi : g_hi;
+  const void* m_lo = pl.x_is_m ? x_lo : g_lo;
+  const void* n_hi = pl.x_is_m ? g_hi : x_hi;
+  const void* n_lo = pl.x_is_m ? g_lo : x_lo;
+  const int m_c = pl.x_is_m ? Cin : Gc, n_c = pl.x_is_m ? Gc : Cin;
+  CUtensorMap mm_hi, mm_lo, mn_hi, mn_lo;
+  {
+    uint64_t dims[4] = {(uint64_t)m_c, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)m_c * 2, (uint64_t)W * m_c * 2, (uint64_t)H * W * m_c * 2};
+    // channels per box: 64 (SWIZZLE_128B) when the count allows, else 32 / 16 with the narrower swizzle; boxes past the
+    // tensor's channel extent are zero-filled by TMA, which pads M to 128
+    uint32_t box[4] = {(uint32_t)pl.kc_m, (uint32_t)pl.TW, (uint32_t)pl.TH, 1};
+    const CUtensorMapSwizzle swz = pl.kc_m == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (pl.kc_m == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    int rc = make_map(&mm_hi, m_hi, 4, dims, str, box, swz);
+    if (rc) return rc;
+    rc = make_map(&mm_lo, m_lo ? m_lo : m_hi, 4, dims, str, box, swz);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)n_c, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)n_c * 2, (uint64_t)W * n_c * 2, (uint64_t)H * W * n_c * 2};
+    uint32_t box[4] = {(uint32_t)pl.kc_n, (uint32_t)pl.TW, (uint32_t)pl.TH, 1};
+    const CUtensorMapSwizzle swz = pl.kc_n == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (pl.kc_n == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    int rc = make_map(&mn_hi, n_hi, 4, dims, str, box, swz);
+    if (rc) return rc;
+    rc = make_map(&mn_lo, n_lo ? n_lo : n_hi, 4, dims, str, box, swz);
+    if (rc) return rc;
+  }
+  const int total_tasks = p.splits * p.taps * p.m_tiles * p.n_tiles;
+  int grid = jcm_num_sms();
+  if (grid > total_tasks) grid = total_tasks;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  JCM_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512));
+  conv_wgrad_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(mm_hi, mm_lo, mn_hi, mn_lo, p);
+  JCM_LAUNCH_CHECK();
+  const long total = (long)p.taps * Cin * Cout;
+  long rg = (total + 255) / 256;
+  if (rg > (long)jcm_num_sms() * 16) rg = (long)jcm_num_sms() * 16;
+  wgrad_reduce_kernel<<<(int)rg, 256, 0, (cudaStream_t)stream>>>(p.partial, p.splits, p.taps, p.m_pad, p.n_pad, Cin, Cout, dw_cout_stride,
+                                                                 pl.x_is_m, dw);
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}

@@ -331,6 +331,25 @@ extern "C" int jcm_bn_stats(const float* x, long M, int C, float* partial, void*
   return JCM_OK;
 }
 
+namespace {
+__global__ void colsum_from_partial_kernel(const float* __restrict__ partial, int nblocks, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += (double)partial[((long)b * 2 + 0) * C + c];
+  out[c] = (float)s;
+}
+}  // namespace
+
+// out[c] = sum over rows of x [M,C] (bias gradient of the last conv layer); partial as for jcm_bn_stats
+extern "C" int jcm_colsum(const float* x, long M, int C, float* partial, float* out, void* stream) {
+  int rc = jcm_bn_stats(x, M, C, partial, stream);
+  if (rc) return rc;
+  colsum_from_partial_kernel<<<jcm_cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(partial, jcm_bn_stats_blocks(M, C), C, out);
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}
+
 extern "C" int jcm_bn_finalize(const float* partial, long M, int C, const float* gamma, const float* beta, float* moving_mean,
                                float* moving_var, float eps, float decay, int train, int update_moving, float* scale,
                                float* shift, float* save_mean, float* save_rstd, void* stream) {

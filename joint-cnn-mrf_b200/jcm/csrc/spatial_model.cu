@@ -34,7 +34,8 @@ struct SmDims {
   int B, H, W, K;      // K predicted joints, K+1 heat-map channels
   int P;               // number of (target, cond) pairs
   int G;               // image groups = ceil(B / 4)
-  int Hp, Wp;          // H padded to URC, W padded to TX
+  int OH, OW;          // output extent of the sliding-window kernel ((H+1)x(W+1) forward, HxW for d/d likelihood)
+  int Hp, Wp;          // kernel (streamed operand) extent padded to URC rows / TX columns
   int XG, tiles, NS;   // strips per output row, strips per image, slices (32 strips) per image
   int pstride, prows;  // shared-memory layout of the prior
   int raw;             // 1: operands are used as given (conv_mrf entry point), 0: BN + softplus applied while staging
@@ -118,7 +119,7 @@ sm_conv_kernel(const float* __restrict__ energies /*[P][2H][2W]*/, const float* 
     const int pair = (int)(t / tasks_per_pair);
     const long pair_base = (long)pair * tasks_per_pair;
     const long seg_end = min(t_end, pair_base + tasks_per_pair);
-    const int j = pair_cond[pair];
+    const int j = pair_cond ? pair_cond[pair] : pair;   // which streamed operand this pair reads
 
     // ---- stage the prior: Ps = softplus(E_pair), zero padding (rows >= 2H, columns >= 2W)
     __syncthreads();
@@ -213,7 +214,7 @@ sm_conv_kernel(const float* __restrict__ energies /*[P][2H][2W]*/, const float* 
       }
 
       if (lane_valid) {
-        const int OW = d.W + 1, OH = d.H + 1;
+        const int OW = d.OW, OH = d.OH;
 #pragma unroll
         for (int k = 0; k < TX; ++k) {
           const int x = x0 + k;
@@ -308,17 +309,21 @@ __global__ void sm_resize_kernel(const float* __restrict__ Cb, SmDims d, float* 
   }
 }
 
-int fill_dims(SmDims& d, int B, int H, int W, int K, int P) {
+// mode 0: forward  (output (H+1)x(W+1), streamed kernel HxW);  mode 1: d/d likelihood (output HxW, streamed kernel (H+1)x(W+1))
+int fill_dims(SmDims& d, int B, int H, int W, int K, int P, int mode = 0) {
   d.raw = 0;
   d.B = B; d.H = H; d.W = W; d.K = K; d.P = P;
   d.G = jcm_cdiv(B, NI);
-  d.Hp = jcm_cdiv(H, URC) * URC;
-  d.Wp = jcm_cdiv(W, TX) * TX;
-  d.XG = jcm_cdiv(W + 1, TX);
-  d.tiles = (H + 1) * d.XG;
+  const int KH = mode ? H + 1 : H, KW = mode ? W + 1 : W;
+  d.OH = mode ? H : H + 1;
+  d.OW = mode ? W : W + 1;
+  d.Hp = jcm_cdiv(KH, URC) * URC;
+  d.Wp = jcm_cdiv(KW, TX) * TX;
+  d.XG = jcm_cdiv(d.OW, TX);
+  d.tiles = d.OH * d.XG;
   d.NS = jcm_cdiv(d.tiles, 32);
-  // prior rows read: y + u <= H + Hp - 1;   columns read: x0 + (TX-1) + v <= XG*TX - 1 + Wp - 1
-  d.prows = H + d.Hp;
+  // prior rows read: y + u <= OH - 1 + Hp - 1;   columns read: x0 + (TX-1) + v <= XG*TX - 1 + Wp - 1
+  d.prows = d.OH - 1 + d.Hp;
   if (d.prows < 2 * H) d.prows = 2 * H;
   int need = d.XG * TX + d.Wp - 1;
   if (need < 2 * W) need = 2 * W;
@@ -429,5 +434,342 @@ extern "C" int jcm_conv_mrf_fwd(const float* A, const float* Bmaps, float* out, 
   const long tot2 = (long)b * H * W;
   sm_resize_kernel<<<(int)((tot2 + 255) / 256), 256, 0, st>>>(Cb, d, out);
   JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}
+
+// =====================================================================================================================
+// Backward of the spatial model (the reference gets it from TensorFlow autodiff of main.py:94-125).
+//   T_p = resize(C_p) + sp(b_p) + d,  dT = g_i / T,  db_p = sigmoid(5 b_p) * sum_n dT,  dC = R_y^T dT R_x
+//   dL_j[n] = sum_{p: cond(p)=j} corr(dC_p[n], P_p)       -> the forward kernel again (mode 1: output HxW, streamed (H+1)x(W+1))
+//   dP_p    = sum_n  dC_p[n] (*) flip(L_j[n])  (full convolution)                     -> sm_bwd_dp_kernel
+//   dE_p = dP_p * sigmoid(5 E_p);  dh = (dL * sigmoid(5 h) + unary term) -> batch-norm backward over the K+1 channels
+// =====================================================================================================================
+namespace {
+
+// thread per (pair, y, x): dT for every image (zero for the padding images) and the bias gradient
+__global__ void sm_bwd_dt_kernel(const float* __restrict__ g, const float* __restrict__ Cb, const float* __restrict__ biases,
+                                 const int* __restrict__ pair_target, SmDims d, float* __restrict__ dT, float* __restrict__ db) {
+  const int OH = d.H + 1, OW = d.W + 1;
+  const long total = (long)d.P * d.H * d.W;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % d.W);
+    long t = idx / d.W;
+    const int y = (int)(t % d.H);
+    const int p = (int)(t / d.H);
+    const int i = pair_target[p];
+    int ylo, yhi, xlo, xhi;
+    float wy, wx;
+    legacy_tap(y, OH, d.H, ylo, yhi, wy);
+    legacy_tap(x, OW, d.W, xlo, xhi, wx);
+    const float bv = biases[idx];
+    const float sb = softplus5(bv) + kDelta;
+    float acc = 0.f;
+    for (int n = 0; n < 4 * d.G; ++n) {
+      float tv = 0.f;
+      if (n < d.B) {
+        const float* C = Cb + ((long)p * (4 * d.G) + n) * OH * OW;
+        const float tl = C[ylo * OW + xlo], tr = C[ylo * OW + xhi];
+        const float bl = C[yhi * OW + xlo], br = C[yhi * OW + xhi];
+        const float top = tl + (tr - tl) * wx;
+        const float bot = bl + (br - bl) * wx;
+        tv = g[(((long)n * d.H + y) * d.W + x) * d.K + i] / (top + (bot - top) * wy + sb);
+        acc += tv;
+      }
+      dT[(((long)p * (4 * d.G) + n) * d.H + y) * d.W + x] = tv;
+    }
+    db[idx] = acc * sigmoid5(bv);
+  }
+}
+
+// dCs[p][g][u][v][e] = (R_y^T dT R_x)[4g+e][u][v] on the (H+1)x(W+1) grid, zero in the padding.  The legacy resize
+// (H+1 -> H) has lo(y') = y', hi(y') = y'+1 (checked on the host), so row u receives (1-w(u)) from y'=u and w(u-1) from y'=u-1.
+__global__ void sm_bwd_dc_kernel(const float* __restrict__ dT, SmDims dm, float* __restrict__ dCs) {
+  const long total = (long)dm.P * dm.G * dm.Hp * dm.Wp;
+  const int H = dm.H, W = dm.W;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % dm.Wp);
+    long t = idx / dm.Wp;
+    const int u = (int)(t % dm.Hp);
+    t /= dm.Hp;
+    const int gi = (int)(t % dm.G);
+    const int p = (int)(t / dm.G);
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    if (u <= H && v <= W) {
+      float wyv[2], wxv[2];
+      int ys[2], xs[2];
+      int lo, hi;
+      float w;
+      ys[0] = u; wyv[0] = 0.f;
+      if (u < H) { legacy_tap(u, H + 1, H, lo, hi, w); wyv[0] = 1.f - w; }
+      ys[1] = u - 1; wyv[1] = 0.f;
+      if (u >= 1) { legacy_tap(u - 1, H + 1, H, lo, hi, w); wyv[1] = w; }
+      xs[0] = v; wxv[0] = 0.f;
+      if (v < W) { legacy_tap(v, W + 1, W, lo, hi, w); wxv[0] = 1.f - w; }
+      xs[1] = v - 1; wxv[1] = 0.f;
+      if (v >= 1) { legacy_tap(v - 1, W + 1, W, lo, hi, w); wxv[1] = w; }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float* src = dT + ((long)p * (4 * dm.G) + 4 * gi + e) * H * W;
+        float s = 0.f;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 2; ++b)
+            if (wyv[a] != 0.f && wxv[b] != 0.f) s += wyv[a] * wxv[b] * src[ys[a] * W + xs[b]];
+        o[e] = s;
+      }
+    }
+    reinterpret_cast<float4*>(dCs)[idx] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- dP (prior gradient)
+// dP[a][b] = sum_n sum_{y,x} dC[n][y][x] * Ltf[n][a-y][b-x]   (Ltf = the flipped, image-interleaved likelihood of the forward pass)
+// One warp owns output rows a and a+H (their y ranges [0,a] and [a+1,H] are complementary, so every warp does exactly H+1
+// row passes), each lane a strip of 6 columns; the two images of a pair ride in the two halves of an FFMA2.
+constexpr int DPW = 20;   // warps per CTA = output row pairs per CTA
+constexpr int TXP = 6;    // strip width
+
+struct DpDims {
+  int B, H, W, P, G, Hp_l, Wp_l, Hp_c, Wp_c;   // padded extents of Lt ([Hp_l][Wp_l]) and dCs ([Hp_c][Wp_c])
+  int lunits;                                   // float2 units per skewed likelihood row
+  int chunks;                                   // ceil(H / DPW)
+};
+
+__device__ __forceinline__ void ffma2p(unsigned long long& d, unsigned long long a, unsigned long long b) {
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+
+// accumulates rows y in [y_begin, y_end) of dC against likelihood rows u = a_row - y
+__device__ __forceinline__ void dp_rows(unsigned long long (&acc)[TXP], const unsigned long long* __restrict__ Lsk,
+                                        const unsigned long long* __restrict__ Cs, int a_row, int y_begin, int y_end, int lane,
+                                        const DpDims& d, int h) {
+  const int W = d.W;
+#pragma unroll 1
+  for (int y = y_begin; y < y_end; ++y) {
+    const int u = a_row - y;
+    const unsigned long long* lrow = Lsk + ((long)h * d.Hp_l + u) * d.lunits;
+    const unsigned long long* crow = Cs + ((long)y * d.Wp_c) * 2 + h;
+    unsigned long long win[TXP];
+    // initial window: columns b0 + k, k = 1..5, at x = 0 (slot k)
+#pragma unroll
+    for (int k = 1; k < TXP; ++k) {
+      const int c = TXP * lane + k;
+      win[k] = (c < W) ? lrow[7 * lane + k] : 0ull;
+    }
+#pragma unroll 1
+    for (int xb = 0; xb * TXP <= W; ++xb) {
+      const int q = lane - xb;
+#pragma unroll
+      for (int s = 0; s < TXP; ++s) {
+        const int x = xb * TXP + s;
+        if (x <= W) {   // warp-uniform
+          const int c = TXP * q - s;
+          const int unit = 7 * q - (s == 0 ? 0 : s + 1);
+          win[(TXP - s) % TXP] = (c >= 0 && c < W) ? lrow[unit] : 0ull;
+          const unsigned long long cv = crow[(long)x * 2];
+#pragma unroll
+          for (int k = 0; k < TXP; ++k) ffma2p(acc[k], win[(k - s + TXP) % TXP], cv);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(DPW * 32, 1)
+sm_bwd_dp_kernel(const float* __restrict__ Lt, const float* __restrict__ dCs, const float* __restrict__ energies,
+                 const int* __restrict__ pair_cond, DpDims d, float* __restrict__ dE) {
+  extern __shared__ __align__(16) unsigned long long dsm[];
+  unsigned long long* Lsk = dsm;                                       // [2 pairs][Hp_l][lunits] skewed float2
+  unsigned long long* Cs = dsm + (size_t)2 * d.Hp_l * d.lunits;         // [H+1][Wp_c][2 pairs] float2
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = blockIdx.x / d.chunks, chunk = blockIdx.x % d.chunks;
+  const int j = pair_cond[p];
+  const int a = chunk * DPW + warp;
+  const bool active = a < d.H;
+  unsigned long long accA[TXP], accB[TXP];
+#pragma unroll
+  for (int k = 0; k < TXP; ++k) { accA[k] = 0ull; accB[k] = 0ull; }
+
+  for (int gi = 0; gi < d.G; ++gi) {
+    __syncthreads();
+    // stage the likelihood (skewed: unit(v) = v + v/6 so that a warp's strips hit distinct banks) and dC of this image group
+    const float4* lsrc = reinterpret_cast<const float4*>(Lt) + ((long)j * d.G + gi) * d.Hp_l * d.Wp_l;
+    for (int idx = threadIdx.x; idx < d.Hp_l * d.Wp_l; idx += blockDim.x) {
+      const int u = idx / d.Wp_l, v = idx - u * d.Wp_l;
+      const float4 q4 = lsrc[idx];
+      const int unit = v + v / TXP;
+      Lsk[((long)0 * d.Hp_l + u) * d.lunits + unit] = pack2(q4.x, q4.y);
+      Lsk[((long)1 * d.Hp_l + u) * d.lunits + unit] = pack2(q4.z, q4.w);
+    }
+    const float4* csrc = reinterpret_cast<const float4*>(dCs) + ((long)p * d.G + gi) * d.Hp_c * d.Wp_c;
+    float4* cdst = reinterpret_cast<float4*>(Cs);
+    for (int idx = threadIdx.x; idx < (d.H + 1) * d.Wp_c; idx += blockDim.x) cdst[idx] = csrc[idx];
+    __syncthreads();
+    if (active) {
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        dp_rows(accA, Lsk, Cs, a, 0, a + 1, lane, d, h);               // output row a:     y in [0, a]
+        dp_rows(accB, Lsk, Cs, a + d.H, a + 1, d.H + 1, lane, d, h);   // output row a + H: y in [a+1, H]
+      }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < TXP; ++k) {
+      const int b = TXP * lane + k;
+      if (b < 2 * d.W) {
+        float s0, s1;
+        const long ia = ((long)p * 2 * d.H + a) * 2 * d.W + b;
+        const long ib = ((long)p * 2 * d.H + a + d.H) * 2 * d.W + b;
+        unpack2(accA[k], s0, s1);
+        dE[ia] = (s0 + s1) * sigmoid5(energies[ia]);
+        unpack2(accB[k], s0, s1);
+        dE[ib] = (s0 + s1) * sigmoid5(energies[ib]);
+      }
+    }
+  }
+}
+
+// dhbn[n,y,x,j] = sigmoid(5 hbn) * ( sum_{p: cond(p)=j} dLf[p][n][H-1-y][W-1-x]  +  [j<K] g[n,y,x,j] / (sp(hbn) + d) )
+__global__ void sm_bwd_dh_kernel(const float* __restrict__ hm, const float* __restrict__ scale, const float* __restrict__ shift,
+                                 const float* __restrict__ g, const float* __restrict__ dLf, const int* __restrict__ pair_cond, SmDims d,
+                                 float* __restrict__ dhbn) {
+  const int KC = d.K + 1;
+  const long total = (long)d.B * d.H * d.W * KC;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % KC);
+    long t = idx / KC;
+    const int x = (int)(t % d.W);
+    t /= d.W;
+    const int y = (int)(t % d.H);
+    const int n = (int)(t / d.H);
+    const float hb = fmaf(hm[idx], scale[j], shift[j]);
+    float s = 0.f;
+    for (int p = 0; p < d.P; ++p)
+      if (pair_cond[p] == j) s += dLf[(((long)p * (4 * d.G) + n) * d.H + (d.H - 1 - y)) * d.W + (d.W - 1 - x)];
+    if (j < d.K) s += g[(((long)n * d.H + y) * d.W + x) * d.K + j] / (softplus5(hb) + kDelta);
+    dhbn[idx] = s * sigmoid5(hb);
+  }
+}
+
+// batch-norm backward over [M, KC], one CTA per channel (tiny tensor).  train: batch statistics; else d_in = scale * dy.
+__global__ void sm_bn_bwd_kernel(const float* __restrict__ hm, const float* __restrict__ dy, const float* __restrict__ scale,
+                                 const float* __restrict__ mean, const float* __restrict__ rstd, long M, int KC, int train,
+                                 float* __restrict__ d_in, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float sh[2][32];
+  const int j = blockIdx.x;
+  const float mu = mean ? mean[j] : 0.f, rs = rstd ? rstd[j] : 1.f;
+  double s0 = 0.0, s1 = 0.0;
+  for (long r = threadIdx.x; r < M; r += blockDim.x) {
+    const float dv = dy[r * KC + j];
+    s0 += dv;
+    s1 += dv * ((hm[r * KC + j] - mu) * rs);
+  }
+  float a = warp_sum((float)s0), b = warp_sum((float)s1);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a; sh[1][threadIdx.x >> 5] = b; }
+  __syncthreads();
+  float ta = 0.f, tb = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { ta += sh[0][i]; tb += sh[1][i]; }
+  if (threadIdx.x == 0) { dbeta[j] = ta; dgamma[j] = tb; }
+  const float sc = scale[j];
+  const float m0 = train ? ta / (float)M : 0.f, m1 = train ? tb / (float)M : 0.f;
+  for (long r = threadIdx.x; r < M; r += blockDim.x) {
+    const float xh = (hm[r * KC + j] - mu) * rs;
+    d_in[r * KC + j] = sc * (dy[r * KC + j] - m0 - xh * m1);
+  }
+}
+
+}  // namespace
+
+// extra workspace (bytes) the backward pass needs on top of the forward workspace (which must be kept: it holds Lt and C)
+extern "C" long jcm_spatial_model_bwd_workspace(int B, int H, int W, int K, int P) {
+  SmDims df, dm;
+  fill_dims(df, B, H, W, K, P, 0);
+  fill_dims(dm, B, H, W, K, P, 1);
+  const long dT = (long)P * 4 * df.G * H * W;
+  const long dCs = (long)P * dm.G * dm.Hp * dm.Wp * 4;
+  const long dLf = (long)P * 4 * dm.G * H * W;
+  const long dh = (long)B * H * W * (K + 1);
+  return (dT + dCs + dLf + dh) * (long)sizeof(float) + 64;
+}
+
+// g = d loss / d out [B,H,W,K].  fwd_workspace = the workspace jcm_spatial_model_fwd filled for the SAME inputs.
+// bn_mean / bn_rstd: saved batch statistics of bn_sm (train != 0) or NULL.  Outputs: d_heat_map [B,H,W,K+1], dE [P][2H][2W],
+// db [P][H][W], dgamma / dbeta [K+1].
+extern "C" int jcm_spatial_model_bwd(const float* g, const float* heat_map, const float* bn_scale, const float* bn_shift,
+                                     const float* bn_mean, const float* bn_rstd, int train, const float* energies, const float* biases,
+                                     const int* pair_target, const int* pair_cond, const void* fwd_workspace, void* workspace,
+                                     long workspace_bytes, float* d_heat_map, float* dE, float* db, float* dgamma, float* dbeta, int B,
+                                     int H, int W, int K, int P, void* stream) {
+  JCM_CHECK_ARG(g && heat_map && bn_scale && bn_shift && energies && biases && pair_target && pair_cond && fwd_workspace && workspace &&
+                    d_heat_map && dE && db && dgamma && dbeta, "jcm_spatial_model_bwd: null pointer");
+  JCM_CHECK_ARG(!train || (bn_mean && bn_rstd), "jcm_spatial_model_bwd: training mode needs the saved batch statistics");
+  if (workspace_bytes < jcm_spatial_model_bwd_workspace(B, H, W, K, P)) {
+    jcm_set_error("jcm_spatial_model_bwd: workspace too small");
+    return JCM_EWORKSPACE;
+  }
+  // the gather form of the resize transpose assumes lo(y') = y' for the (H+1) -> H legacy resize
+  for (int yy = 0; yy < H; ++yy) {
+    const float src = (float)yy * ((float)(H + 1) / (float)H);
+    JCM_CHECK_ARG((int)floorf(src) == yy, "jcm_spatial_model_bwd: unsupported heat-map height %d", H);
+  }
+  for (int xx = 0; xx < W; ++xx) {
+    const float src = (float)xx * ((float)(W + 1) / (float)W);
+    JCM_CHECK_ARG((int)floorf(src) == xx, "jcm_spatial_model_bwd: unsupported heat-map width %d", W);
+  }
+  SmDims df, dm;
+  fill_dims(df, B, H, W, K, P, 0);
+  fill_dims(dm, B, H, W, K, P, 1);
+  const size_t smem_conv = sm_smem_bytes(dm);
+  DpDims dp;
+  dp.B = B; dp.H = H; dp.W = W; dp.P = P; dp.G = df.G;
+  dp.Hp_l = df.Hp; dp.Wp_l = df.Wp; dp.Hp_c = dm.Hp; dp.Wp_c = dm.Wp;
+  dp.lunits = df.Wp + df.Wp / TXP + 2;
+  dp.chunks = jcm_cdiv(H, DPW);
+  const size_t smem_dp = ((size_t)2 * dp.Hp_l * dp.lunits + (size_t)(H + 1) * dp.Wp_c * 2) * sizeof(unsigned long long);
+  if (smem_conv > 227 * 1024 || smem_dp > 227 * 1024) {
+    jcm_set_error("jcm_spatial_model_bwd: heat-map size %dx%d not supported by this build (shared memory %zu / %zu B)", H, W, smem_conv, smem_dp);
+    return JCM_ENOTSUP;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* Lt = (const float*)fwd_workspace;
+  const float* Cb = Lt + (long)(K + 1) * df.G * df.Hp * df.Wp * 4;
+  float* dT = (float*)workspace;
+  float* dCs = dT + (long)P * 4 * df.G * H * W;
+  float* dLf = dCs + (long)P * dm.G * dm.Hp * dm.Wp * 4;
+  float* dh = dLf + (long)P * 4 * dm.G * H * W;
+
+  {
+    const long total = (long)P * H * W;
+    sm_bwd_dt_kernel<<<(int)((total + 127) / 128), 128, 0, st>>>(g, Cb, biases, pair_target, df, dT, db);
+    JCM_LAUNCH_CHECK();
+  }
+  {
+    const long total = (long)P * dm.G * dm.Hp * dm.Wp;
+    sm_bwd_dc_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(dT, dm, dCs);
+    JCM_LAUNCH_CHECK();
+  }
+  {
+    JCM_CUDA(cudaFuncSetAttribute(sm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
+    const long T = (long)P * dm.G * dm.NS;
+    long grid = jcm_num_sms();
+    if (grid > (T + NW - 1) / NW) grid = (T + NW - 1) / NW;
+    sm_conv_kernel<<<(int)grid, NW * 32, smem_conv, st>>>(energies, dCs, nullptr, dm, dLf);
+    JCM_LAUNCH_CHECK();
+  }
+  {
+    JCM_CUDA(cudaFuncSetAttribute(sm_bwd_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
+    sm_bwd_dp_kernel<<<P * dp.chunks, DPW * 32, smem_dp, st>>>(Lt, dCs, energies, pair_cond, dp, dE);
+    JCM_LAUNCH_CHECK();
+  }
+  {
+    const long total = (long)B * H * W * (K + 1);
+    sm_bwd_dh_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(heat_map, bn_scale, bn_shift, g, dLf, pair_cond, df, dh);
+    JCM_LAUNCH_CHECK();
+    sm_bn_bwd_kernel<<<K + 1, 1024, 0, st>>>(heat_map, dh, bn_scale, bn_mean, bn_rstd, (long)B * H * W, K + 1, train, d_heat_map, dgamma,
+                                             dbeta);
+    JCM_LAUNCH_CHECK();
+  }
   return JCM_OK;
 }

@@ -1,0 +1,285 @@
+"""Joint training step of the part detector + spatial model (reference main.py:474-577) on the sm_100a kernels.
+
+One process per GPU.  Per step: forward in training mode (batch-norm batch statistics, activations kept), hand-written
+backward (tcgen05 data- and weight-gradient GEMMs, fused BN/ReLU/pool backward, spatial-model backward), ONE NCCL
+all-reduce of the flat gradient buffer (the reference averages tower gradients on the CPU, main.py:243-267), then global-norm
+clipping (main.py:302-309) and TF1-style Adam / Momentum (main.py:501-506,577) as two fused kernels over the flat buffers.
+
+All trainable variables are views into one flat fp32 buffer laid out as
+    [conv kernels ('weights': weight-decayed, main.py:195-205)] [conv biases] [BN gamma/beta] [energies] [pairwise biases] [bn_sm gamma/beta]
+so weight decay is a prefix, the all-reduce is one call and the optimizer is shape-agnostic.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import ops
+from ._lib import lib, check
+from .ops import _ptr, _stream, F32, Planes
+
+ADAM_B1, ADAM_B2, ADAM_EPS = 0.9, 0.999, 1e-8   # tf.train.AdamOptimizer defaults (main.py:502)
+CLIP_NORM = 4.0                                  # main.py:576
+
+
+# ------------------------------------------------------------------------------------------------ backward op wrappers
+def softmax_ce_bwd(logits, labels, lse, scale):
+    B, H, W, K = logits.shape
+    d = torch.empty_like(logits)
+    check(lib().jcm_softmax_ce_bwd(_ptr(logits), _ptr(labels), _ptr(lse), B, H * W, K, labels.shape[3], float(scale), _ptr(d), _stream()),
+          'jcm_softmax_ce_bwd')
+    return d
+
+
+def spatial_softmax_bwd(y, dy, dx, accumulate):
+    B, H, W, K = y.shape
+    check(lib().jcm_spatial_softmax_bwd(_ptr(y), _ptr(dy), B, H * W, K, dy.shape[3], int(accumulate), _ptr(dx), _stream()),
+          'jcm_spatial_softmax_bwd')
+    return dx
+
+
+def bn_relu_bwd(a, dout, ss, saved, dy_scale, pool, split, dgamma, dbeta, dbias, want_f32=False):
+    B, H, W, C = a.shape
+    Ho, Wo = ((H + 1) // 2, (W + 1) // 2) if pool else (H, W)
+    if tuple(dout.shape) != (B, Ho, Wo, C):
+        raise ValueError('dout %s does not match layer output %s' % (tuple(dout.shape), (B, Ho, Wo, C)))
+    planes = ops._new_planes((B, H, W, C), a.device, split)
+    f32 = torch.empty((B, H, W, C), dtype=F32, device=a.device) if want_f32 else None
+    nb = lib().jcm_bn_relu_bwd_blocks(B * Ho * Wo, C)
+    ws = torch.empty(((4 * nb + 2) * C,), dtype=F32, device=a.device)
+    check(lib().jcm_bn_relu_bwd(_ptr(a), _ptr(dout), _ptr(ss[0]), _ptr(ss[1]), _ptr(saved[0]), _ptr(saved[1]), float(dy_scale), B, H, W, C,
+                                int(pool), _ptr(planes.hi), _ptr(planes.lo), _ptr(f32), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), _ptr(ws),
+                                _stream()), 'jcm_bn_relu_bwd')
+    return (planes, f32) if want_f32 else planes
+
+
+def colsum(x, out):
+    C = x.shape[-1]
+    M = x.numel() // C
+    nb = lib().jcm_bn_stats_blocks(M, C)
+    partial = torch.empty((nb, 2, C), dtype=F32, device=x.device)
+    check(lib().jcm_colsum(_ptr(x), M, C, _ptr(partial), _ptr(out), _stream()), 'jcm_colsum')
+    return out
+
+
+def upsample_avg3_bwd(dm, shape2, shape3):
+    B, H, W, C = dm.shape
+    d2 = torch.empty((B, shape2[0], shape2[1], C), dtype=F32, device=dm.device)
+    d3 = torch.empty((B, shape3[0], shape3[1], C), dtype=F32, device=dm.device)
+    check(lib().jcm_upsample_avg3_bwd(_ptr(dm), B, H, W, shape2[0], shape2[1], shape3[0], shape3[1], C, _ptr(d2), _ptr(d3), _stream()),
+          'jcm_upsample_avg3_bwd')
+    return d2, d3
+
+
+def pad_planes(x, cpad, split):
+    C = x.shape[-1]
+    M = x.numel() // C
+    out = ops._new_planes(tuple(x.shape[:-1]) + (cpad,), x.device, split)
+    check(lib().jcm_pad_planes(_ptr(x), M, C, cpad, _ptr(out.hi), _ptr(out.lo), _stream()), 'jcm_pad_planes')
+    return out
+
+
+def conv2d_wgrad(xp, gp, dw, cout, ksize):
+    """xp input planes [B,H,W,Cin], gp output-gradient planes [B,H,W,Gc] -> dw (contiguous fp32 [k*k, Cin, cout]) in place."""
+    B, H, W, cin = xp.shape
+    gc = gp.shape[3]
+    if tuple(gp.shape[:3]) != (B, H, W):
+        raise ValueError('gradient planes %s do not match input planes %s' % (gp.shape, xp.shape))
+    if dw.numel() != ksize * ksize * cin * cout or not dw.is_contiguous():
+        raise ValueError('dw must be a contiguous [%d,%d,%d] tensor' % (ksize * ksize, cin, cout))
+    nbytes = lib().jcm_conv2d_wgrad_workspace(B, H, W, cin, gc, ksize)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dw.device)
+    check(lib().jcm_conv2d_wgrad(_ptr(xp.hi), _ptr(xp.lo), _ptr(gp.hi), _ptr(gp.lo), _ptr(dw), _ptr(ws), nbytes, B, H, W, cin, gc, cout, cout,
+                                 ksize, _stream()), 'jcm_conv2d_wgrad')
+    return dw
+
+
+def unpack_s2d_grad(g9, dw):
+    check(lib().jcm_unpack_s2d_grad(_ptr(g9), dw.shape[3], _ptr(dw), _stream()), 'jcm_unpack_s2d_grad')
+    return dw
+
+
+def spatial_model_bwd(g, heat_map, ss, saved, train, sm, fwd_ws, d_energies, d_biases, dgamma, dbeta):
+    B, H, W, KC = heat_map.shape
+    K, P = KC - 1, sm.energies.shape[0]
+    nbytes = lib().jcm_spatial_model_bwd_workspace(B, H, W, K, P)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=g.device)
+    d_hm = torch.empty_like(heat_map)
+    check(lib().jcm_spatial_model_bwd(_ptr(g), _ptr(heat_map), _ptr(ss[0]), _ptr(ss[1]), _ptr(saved[0] if saved is not None else None),
+                                      _ptr(saved[1] if saved is not None else None), int(train), _ptr(sm.energies), _ptr(sm.biases),
+                                      _ptr(sm.pair_target), _ptr(sm.pair_cond), _ptr(fwd_ws), _ptr(ws), nbytes, _ptr(d_hm), _ptr(d_energies),
+                                      _ptr(d_biases), _ptr(dgamma), _ptr(dbeta), B, H, W, K, P, _stream()), 'jcm_spatial_model_bwd')
+    return d_hm
+
+
+# ------------------------------------------------------------------------------------------------ trainer
+class Trainer:
+    """Owns the flat parameter / gradient / optimizer-state buffers and runs the training step."""
+
+    def __init__(self, p, sm, ctx, world_size=1, lr=0.001, optimizer='adam', n_updates_total=None):
+        if not ctx.train_pd:
+            raise ValueError('train_pd=False (frozen part detector) is not implemented in the training step')
+        if optimizer not in ('adam', 'momentum'):
+            raise Exception('wrong optimizer')            # same message as main.py:506
+        self.p, self.sm, self.ctx = p, sm, ctx
+        self.world_size, self.lr, self.optimizer = world_size, lr, optimizer
+        self.t = 0
+        self.n_updates_total = n_updates_total
+        dev = sm.energies.device
+        names_w = [k for k in p if k.endswith('/weights')]
+        names_rest = [k for k in p if not k.endswith('/weights') and 'moving_' not in k]
+        entries = [(k, p[k]) for k in names_w]
+        self.n_decay = sum(t.numel() for _, t in entries)
+        entries += [(k, p[k]) for k in names_rest]
+        entries += [('sm/energies', sm.energies), ('sm/biases', sm.biases), ('sm/gamma', sm.bn['gamma']), ('sm/beta', sm.bn['beta'])]
+        # 16-byte aligned offsets so that every view can be a TMA / float4 base
+        offs, n = {}, 0
+        for k, t in entries:
+            offs[k] = n
+            n += (t.numel() + 3) // 4 * 4
+        if self.n_decay % 4:
+            raise ValueError('conv kernel sizes must be multiples of 4 elements')
+        self.n = n
+        self.flat = torch.zeros(n, dtype=F32, device=dev)
+        self.grads = torch.zeros(n, dtype=F32, device=dev)
+        self.m = torch.zeros(n, dtype=F32, device=dev)
+        self.v = torch.zeros(n, dtype=F32, device=dev)
+        self.g = {}
+        for k, t in entries:
+            view = self.flat[offs[k]:offs[k] + t.numel()].view(t.shape)
+            view.copy_(t)
+            self.g[k] = self.grads[offs[k]:offs[k] + t.numel()].view(t.shape)
+            if k.startswith('sm/'):
+                if k == 'sm/energies':
+                    sm.energies = view
+                elif k == 'sm/biases':
+                    sm.biases = view
+                else:
+                    sm.bn[k[3:]] = view
+            else:
+                p[k] = view
+        nb = lib().jcm_optim_blocks(n)
+        self.partial = torch.empty(2 * nb, dtype=F32, device=dev)
+        self.stats = torch.zeros(2, dtype=F32, device=dev)
+
+    # ---------------------------------------------------------------------------------------- learning-rate schedule
+    def current_lr(self):
+        """main.py:468-470,492: piecewise constant, lr/2, lr/5, lr/10 after 70/80/90 % of the updates."""
+        if not self.n_updates_total:
+            return self.lr
+        b = [round(f * self.n_updates_total) for f in (0.7, 0.8, 0.9)]
+        vals = [self.lr, self.lr / 2, self.lr / 5, self.lr / 10]
+        for bound, v in zip(b, vals):
+            if self.t <= bound:
+                return v
+        return vals[-1]
+
+    # ---------------------------------------------------------------------------------------- forward + backward
+    def forward_backward(self, x, y):
+        """Fills self.grads with d(loss_pd + loss_sm)/d(variables) of THIS replica (weight decay is added in apply())."""
+        p, sm, ctx, g = self.p, self.sm, self.ctx, self.g
+        K, split = ctx.n_joints, ctx.split
+        B = x.shape[0]
+        dev = x.device
+        banks = ops.prep_input(x, split)
+        saved = {}
+
+        def fwd_layer(xp, name, ksize, kind='fwd'):
+            w, b = p[name + '/weights'], p[name + '/biases']
+            a = ops.conv2d_planes(xp, ctx.packed(name, w, kind), b, w.shape[3], ksize, relu=True,
+                                  alg_kdim=w.shape[0] * w.shape[1] * w.shape[2])
+            ss, st = ops.bn_scale_shift(a, p[name + '/BatchNorm/gamma'], p[name + '/BatchNorm/beta'], p[name + '/BatchNorm/moving_mean'],
+                                        p[name + '/BatchNorm/moving_variance'], train=True, save=True)
+            saved[name] = (xp, a, ss, st)
+            return a, ss
+
+        outs = []
+        sfxs = ('fullres', 'halfres', 'quarterres')
+        for xp, sfx in zip(banks, sfxs):
+            a, ss = fwd_layer(xp, 'conv1_' + sfx, 3, 's2d')
+            h = ops.bn_apply_pool(a, ss, True, split)
+            a, ss = fwd_layer(h, 'conv2_' + sfx, 5)
+            h = ops.bn_apply_pool(a, ss, True, split)
+            a, ss = fwd_layer(h, 'conv3_' + sfx, 5)
+            h = ops.bn_apply_pool(a, ss, False, split)
+            a, ss = fwd_layer(h, 'conv4_' + sfx, 9)
+            outs.append((a, ss))
+        ss6 = torch.cat([o[1] for o in outs], dim=0).contiguous()
+        merged = ops.upsample_avg3(outs[0][0], outs[1][0], outs[2][0], ss6, split)
+        a5, ss5 = fwd_layer(merged, 'conv5', 9)
+        h5 = ops.bn_apply_pool(a5, ss5, False, split)
+        w6 = p['conv6/weights']
+        logit_pd = ops.conv2d_planes(h5, ctx.packed('conv6', w6), p['conv6/biases'], K, 9, relu=False, alg_kdim=81 * w6.shape[2])
+        hm_pd = ops.spatial_softmax(logit_pd)
+        loss_pd, _, lse_pd = ops.softmax_ce(logit_pd, y, want_lse=True)
+        inv_bk = 1.0 / (B * K)
+        d_logit = softmax_ce_bwd(logit_pd, y, lse_pd, inv_bk)
+        loss_sm = loss_pd
+        if ctx.use_sm:
+            cat = torch.cat([hm_pd, y[:, :, :, K:]], dim=3).contiguous()       # main.py:528
+            ss_sm, st_sm = ops.bn_scale_shift(cat, sm.bn['gamma'], sm.bn['beta'], sm.bn['moving_mean'], sm.bn['moving_variance'],
+                                              train=True, save=True)
+            logit_sm, ws_sm = ops.spatial_model_fwd(cat, ss_sm, sm.energies, sm.biases, sm.pair_target, sm.pair_cond, K, keep_workspace=True)
+            loss_sm, _, lse_sm = ops.softmax_ce(logit_sm, y, want_lse=True)
+            g_sm = softmax_ce_bwd(logit_sm, y, lse_sm, inv_bk)
+            d_cat = spatial_model_bwd(g_sm, cat, ss_sm, st_sm, True, sm, ws_sm, g['sm/energies'], g['sm/biases'], g['sm/gamma'], g['sm/beta'])
+            spatial_softmax_bwd(hm_pd, d_cat, d_logit, accumulate=True)
+        else:
+            d_logit.mul_(2.0)   # loss_sm == loss_pd when the spatial model is off (main.py:533-536)
+
+        # ---- part-detector backward
+        gp6 = pad_planes(d_logit, ops.pad16(K), split)
+        conv2d_wgrad(h5, gp6, g['conv6/weights'].view(81, w6.shape[2], K), K, 9)
+        colsum(d_logit, g['conv6/biases'])
+        dh = ops.conv2d_planes(gp6, ctx.packed('conv6', w6, 'dgrad'), None, w6.shape[2], 9, relu=False)
+
+        def bwd_layer(name, dout, dy_scale, pool, ksize, need_dx):
+            xp, a, ss, st = saved.pop(name)
+            w = p[name + '/weights']
+            cin, cout = w.shape[2], w.shape[3]
+            d_pre = bn_relu_bwd(a, dout, ss, st, dy_scale, pool, split, g[name + '/BatchNorm/gamma'], g[name + '/BatchNorm/beta'],
+                                g[name + '/biases'])
+            if name.startswith('conv1_'):
+                g9 = torch.empty((9, 16, cout), dtype=F32, device=dev)
+                conv2d_wgrad(xp, d_pre, g9, cout, 3)
+                unpack_s2d_grad(g9, g[name + '/weights'])
+            else:
+                conv2d_wgrad(xp, d_pre, g[name + '/weights'].view(ksize * ksize, cin, cout), cout, ksize)
+            if need_dx:
+                return ops.conv2d_planes(d_pre, ctx.packed(name, w, 'dgrad'), None, cin, ksize, relu=False)
+            return None
+
+        dmerged = bwd_layer('conv5', dh, 1.0, False, 9, True)
+        a4_2, a4_3 = outs[1][0], outs[2][0]
+        d2, d3 = upsample_avg3_bwd(dmerged, a4_2.shape[1:3], a4_3.shape[1:3])
+        for sfx, dout, sc in zip(sfxs, (dmerged, d2, d3), (1.0 / 3.0, 1.0, 1.0)):
+            d = bwd_layer('conv4_' + sfx, dout, sc, False, 9, True)
+            d = bwd_layer('conv3_' + sfx, d, 1.0, False, 5, True)
+            d = bwd_layer('conv2_' + sfx, d, 1.0, True, 5, True)
+            bwd_layer('conv1_' + sfx, d, 1.0, True, 5, False)
+        return {'loss_pd': loss_pd, 'loss_sm': loss_sm, 'logit_pd': logit_pd}
+
+    # ---------------------------------------------------------------------------------------- optimizer
+    def apply(self):
+        """Gradient mean over replicas (one NCCL all-reduce), weight decay, global-norm clip, Adam / Momentum."""
+        if self.world_size > 1:
+            torch.distributed.all_reduce(self.grads, op=torch.distributed.ReduceOp.SUM)
+        self.t += 1
+        check(lib().jcm_grad_prepare(_ptr(self.grads), _ptr(self.flat), self.n, self.n_decay, 1.0 / self.world_size, float(self.ctx.lmbd),
+                                     _ptr(self.partial), _ptr(self.stats), _stream()), 'jcm_grad_prepare')
+        lr = self.current_lr()
+        if self.optimizer == 'adam':
+            lr_t = lr * math.sqrt(1.0 - ADAM_B2 ** self.t) / (1.0 - ADAM_B1 ** self.t)
+            check(lib().jcm_clip_adam(_ptr(self.flat), _ptr(self.grads), _ptr(self.m), _ptr(self.v), self.n, _ptr(self.stats), CLIP_NORM,
+                                      lr_t, ADAM_B1, ADAM_B2, ADAM_EPS, 0, _stream()), 'jcm_clip_adam')
+        else:
+            check(lib().jcm_clip_adam(_ptr(self.flat), _ptr(self.grads), _ptr(self.m), _ptr(self.v), self.n, _ptr(self.stats), CLIP_NORM,
+                                      lr, 0.9, 0.0, 0.0, 1, _stream()), 'jcm_clip_adam')
+        self.ctx._wcache.clear()   # the kernels changed the weights in place: packed operand planes are stale
+
+    def step(self, x, y):
+        out = self.forward_backward(x, y)
+        self.apply()
+        # loss_tower = loss_pd + loss_sm + lmbd * weight_decay (main.py:541); stats[1] holds sum w^2/2 of this step's weights
+        out['loss'] = out['loss_pd'] + out['loss_sm'] + self.ctx.lmbd * self.stats[1:2]
+        return out

@@ -263,6 +263,87 @@ def sec_time():
             print('TIME conv5 %s B=%d: %.2f ms  %.1f TFLOP/s' % (precision, B, best, fl / best / 1e9))
 
 
+def grad_case(B, H, W, K, debug, precision, use_sm=True, seed=4):
+    """Returns (oracle grads dict, gpu grads dict, oracle losses, gpu losses) for one training-mode forward+backward."""
+    from jcm import train as jtrain
+    gen = torch.Generator().manual_seed(seed)
+    hm_h, hm_w = H // 8, W // 8
+    names = orc.JOINT_NAMES[:K] + ['torso']
+    p64 = orc.init_part_detector(K, gen, debug=debug)
+    for k, v in p64.items():
+        if 'gamma' in k:
+            v.add_(torch.rand(v.shape, generator=gen).double() * 0.5)
+        if 'beta' in k or 'biases' in k:
+            v.add_(torch.randn(v.shape, generator=gen).double() * 0.1)
+    rng = np.random.default_rng(seed)
+    distr = jcm.get_pairwise_distr() if (hm_h, hm_w) == (60, 90) else orc.synthetic_pairwise(names, K, hm_h, hm_w, rng)
+    sm64 = orc.init_spatial_model(distr, K, hm_h, hm_w, joint_names=names)
+    for k, v in sm64.items():
+        if k.startswith('bias_'):
+            v.add_(torch.rand(v.shape, generator=gen).double() * 0.01)
+        if 'gamma' in k or 'beta' in k:
+            v.add_(torch.randn(v.shape, generator=gen).double() * 0.1)
+    p32 = {k: v.float() for k, v in p64.items()}
+    sm32 = {k: v.float() for k, v in sm64.items()}
+    x = torch.rand(B, H, W, 3, generator=gen)
+    y = torch.from_numpy(orc.synthetic_labels(B, hm_h, hm_w, K + 1, rng))
+    # oracle
+    po = {k: v.double().clone().requires_grad_('moving_' not in k) for k, v in p32.items()}
+    so = {k: v.double().clone().requires_grad_('moving_' not in k) for k, v in sm32.items()}
+    out = orc.tower_forward(x.double(), y.double(), po, so, K, True, use_sm=use_sm, lmbd=0.0)
+    (out['loss_pd'] + out['loss_sm']).backward()
+    ref = {k: v.grad for k, v in po.items() if v.requires_grad}
+    ref.update({k: v.grad for k, v in so.items() if v.requires_grad})
+    # gpu
+    p = jcm.load_params(p32)
+    smp = jcm.PairwiseParams.from_dict(sm32, names, K)
+    ctx = jcm.Context(n_joints=K, joint_names=names, flag_train=True, precision=precision, debug=debug, use_sm=use_sm)
+    tr = jtrain.Trainer(p, smp, ctx)
+    res = tr.forward_backward(x.to(dev), y.to(dev))
+    torch.cuda.synchronize()
+    got = {}
+    for k in p32:
+        if 'moving_' not in k:
+            got[k] = tr.g[k]
+    if use_sm:
+        P, H2, W2 = smp.energies.shape
+        for i, key in enumerate(smp.keys):
+            got['energy_' + key] = tr.g['sm/energies'][i].view(1, H2, W2, 1)
+            got['bias_' + key] = tr.g['sm/biases'][i].view(1, H2 // 2, W2 // 2, 1)
+        got['bn_sm/BatchNorm/gamma'] = tr.g['sm/gamma']
+        got['bn_sm/BatchNorm/beta'] = tr.g['sm/beta']
+    return ref, got, (float(out['loss_pd']), float(out['loss_sm'])), (float(res['loss_pd']), float(res['loss_sm']))
+
+
+def sec_grad():
+    for (B, H, W, K, debug, precision, use_sm) in [(2, 96, 160, 4, True, 'fp32', True), (2, 96, 160, 4, True, 'bf16', True),
+                                                   (1, 64, 96, 7, False, 'fp32', False)]:
+        try:
+            ref, got, lo, lg = grad_case(B, H, W, K, debug, precision, use_sm)
+            print('GRAD B%d %dx%d K%d debug=%d %s use_sm=%d: losses oracle %.5f %.5f gpu %.5f %.5f' % ((B, H, W, K, debug, precision, use_sm) + lo + lg))
+            worst = 0.0
+            agg = {}
+            for k in sorted(ref):
+                if ref[k] is None:
+                    continue
+                if k not in got:
+                    print('    missing', k)
+                    continue
+                e = relerr(got[k], ref[k])
+                worst = max(worst, e)
+                if k.startswith('energy_') or k.startswith('bias_'):
+                    kk = k.split('_')[0] + '_*'
+                    agg[kk] = max(agg.get(kk, 0.0), e)
+                else:
+                    print('    %-40s err %.2e  |ref|max %.2e' % (k, e, float(ref[k].abs().max())))
+            for kk, e in agg.items():
+                print('    %-40s err %.2e (max over pairs)' % (kk, e))
+            print('    WORST %.2e' % worst)
+        except Exception as e:
+            print('GRAD case FAILED', repr(e))
+            traceback.print_exc()
+
+
 def sec_smtime():
     K = 7
     names = jcm.JOINT_NAMES[:K] + ['torso']
