@@ -175,8 +175,9 @@ class Trainer:
         return vals[-1]
 
     # ---------------------------------------------------------------------------------------- forward + backward
-    def forward_backward(self, x, y):
-        """Fills self.grads with d(loss_pd + loss_sm)/d(variables) of THIS replica (weight decay is added in apply())."""
+    def forward_backward(self, x, y, tap=None):
+        """Fills self.grads with d(loss_pd + loss_sm)/d(variables) of THIS replica (weight decay is added in apply()).
+        tap (optional dict) receives the ReLU output of every layer ('<name>/relu'), as graph.model does."""
         p, sm, ctx, g = self.p, self.sm, self.ctx, self.g
         K, split = ctx.n_joints, ctx.split
         B = x.shape[0]
@@ -191,6 +192,8 @@ class Trainer:
             ss, st = ops.bn_scale_shift(a, p[name + '/BatchNorm/gamma'], p[name + '/BatchNorm/beta'], p[name + '/BatchNorm/moving_mean'],
                                         p[name + '/BatchNorm/moving_variance'], train=True, save=True)
             saved[name] = (xp, a, ss, st)
+            if tap is not None:
+                tap[name + '/relu'] = a
             return a, ss
 
         outs = []

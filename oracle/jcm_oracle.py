@@ -79,12 +79,19 @@ def batch_norm(x, bn, flag_train, update=True):
     return (x - mean) * torch.rsqrt(var + BN_EPS) * bn['gamma'] + bn['beta']
 
 
-def max_pool_layer(x, size=2, stride=2):
-    """main.py:172-174  2x2 s2 SAME max-pool (45 -> 23, the padded column never wins)   [TF1]."""
+def max_pool_layer(x, size=2, stride=2, select=None):
+    """main.py:172-174  2x2 s2 SAME max-pool (45 -> 23, the padded column never wins)   [TF1].
+    select (tests only): int64 [B,Ho,Wo,C] with the window element (2*dy + dx) to take instead of the arg-max, so that a
+    gradient comparison does not depend on how a near-tie between two window elements was rounded (see conv_layer)."""
     pt, pb, _ = same_pad(x.shape[1], size, stride)
     pl, pr, _ = same_pad(x.shape[2], size, stride)
     xc = F.pad(x.permute(0, 3, 1, 2), (pl, pr, pt, pb), value=float('-inf'))
-    return F.max_pool2d(xc, size, stride).permute(0, 2, 3, 1)
+    if select is None:
+        return F.max_pool2d(xc, size, stride).permute(0, 2, 3, 1)
+    assert size == 2 and stride == 2
+    B, C, Hp, Wp = xc.shape
+    win = xc.reshape(B, C, Hp // 2, 2, Wp // 2, 2).permute(0, 2, 4, 3, 5, 1).reshape(B, Hp // 2, Wp // 2, 4, C)
+    return torch.gather(win, 3, select.unsqueeze(3)).squeeze(3)
 
 
 def resize_images(x, out_h, out_w):
@@ -121,12 +128,19 @@ def weight_variable(shape, gen, dtype=torch.float64):
     return (w * std).to(dtype)
 
 
-def conv_layer(x, p, size, stride, name, flag_train, last_layer=False, tap=None):
-    """main.py:156-169  relu(conv_SAME(x,w)+b) then BN (BN after ReLU); last layer: bias only."""
+def conv_layer(x, p, size, stride, name, flag_train, last_layer=False, tap=None, relu_masks=None):
+    """main.py:156-169  relu(conv_SAME(x,w)+b) then BN (BN after ReLU); last layer: bias only.
+    relu_masks (tests only): dict name -> bool tensor; the ReLU is then evaluated as pre * mask, i.e. with the on/off
+    pattern decided elsewhere (the fp32 GPU forward).  The two agree except where |pre| is below the fp32 forward error,
+    so the forward value is unchanged to ~1e-6 while the GRADIENT comparison no longer depends on which side of zero
+    such elements were rounded to (one flipped element moves a bias gradient by several per cent)."""
     pre = conv2d(x, p[name + '/weights'], stride) + p[name + '/biases']
     if last_layer:
         return pre
-    act = torch.relu(pre)
+    if relu_masks is not None and name in relu_masks:
+        act = pre * relu_masks[name].to(pre.dtype)
+    else:
+        act = torch.relu(pre)
     if tap is not None:
         tap[name + '/relu'] = act
     bn = {k: p[name + '/BatchNorm/' + k] for k in ('gamma', 'beta', 'moving_mean', 'moving_variance')}
@@ -141,15 +155,18 @@ def n_filters(debug=False):
     return f // 4 if debug else f           # main.py:40-41
 
 
-def model(x, p, n_joints, flag_train, tap=None):
+def model(x, p, n_joints, flag_train, tap=None, relu_masks=None, pool_select=None):
     """main.py:29-74. x [B,H,W,3] -> logits [B,H/8,W/8,n_joints]."""
+    kw = dict(tap=tap, relu_masks=relu_masks)
+    ps = pool_select or {}
+
     def bank(xin, sfx):
-        h = conv_layer(xin, p, 5, 2, 'conv1_' + sfx, flag_train, tap=tap)
-        h = max_pool_layer(h)
-        h = conv_layer(h, p, 5, 1, 'conv2_' + sfx, flag_train, tap=tap)
-        h = max_pool_layer(h)
-        h = conv_layer(h, p, 5, 1, 'conv3_' + sfx, flag_train, tap=tap)
-        h = conv_layer(h, p, 9, 1, 'conv4_' + sfx, flag_train, tap=tap)
+        h = conv_layer(xin, p, 5, 2, 'conv1_' + sfx, flag_train, **kw)
+        h = max_pool_layer(h, select=ps.get('conv1_' + sfx))
+        h = conv_layer(h, p, 5, 1, 'conv2_' + sfx, flag_train, **kw)
+        h = max_pool_layer(h, select=ps.get('conv2_' + sfx))
+        h = conv_layer(h, p, 5, 1, 'conv3_' + sfx, flag_train, **kw)
+        h = conv_layer(h, p, 9, 1, 'conv4_' + sfx, flag_train, **kw)
         return h
 
     H, W = x.shape[1], x.shape[2]
@@ -161,7 +178,7 @@ def model(x, p, n_joints, flag_train, tap=None):
     h = (x1 + x2 + x3) / 3
     if tap is not None:
         tap['merge'] = h
-    h = conv_layer(h, p, 9, 1, 'conv5', flag_train, tap=tap)
+    h = conv_layer(h, p, 9, 1, 'conv5', flag_train, **kw)
     return conv_layer(h, p, 9, 1, 'conv6', flag_train, last_layer=True)
 
 
@@ -297,13 +314,14 @@ def det_rate(heat_map_pred, heat_map_target, normalized_radius=10, joints='all')
 # ----------------------------------------------------------------------------------------------------------
 # tower loss + DP step (main.py:243-267, 302-309, 491-577)
 # ----------------------------------------------------------------------------------------------------------
-def tower_forward(x, hm_target, p, sm, n_joints, flag_train, use_sm=True, lmbd=0.001, tap=None):
+def tower_forward(x, hm_target, p, sm, n_joints, flag_train, use_sm=True, lmbd=0.001, tap=None, relu_masks=None,
+                  joint_names=None, pool_select=None):
     """main.py:522-541 for one tower. Returns dict(loss, loss_pd, loss_sm, logits..)."""
-    logit_pd = model(x, p, n_joints, flag_train, tap=tap)
+    logit_pd = model(x, p, n_joints, flag_train, tap=tap, relu_masks=relu_masks, pool_select=pool_select)
     hm_pd = spatial_softmax(logit_pd)
     if use_sm:
         cat = torch.cat([hm_pd, hm_target[:, :, :, n_joints:]], dim=3)          # main.py:528
-        logit_sm = spatial_model(cat, sm, n_joints, flag_train)
+        logit_sm = spatial_model(cat, sm, n_joints, flag_train, joint_names=joint_names)
         hm_sm = spatial_softmax(logit_sm)
     else:
         logit_sm, hm_sm = logit_pd, hm_pd

@@ -19,6 +19,8 @@ import torch
 import jcm
 from jcm import ops
 import jcm_oracle as orc
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import pins
 
 dev = 'cuda'
 
@@ -263,7 +265,7 @@ def sec_time():
             print('TIME conv5 %s B=%d: %.2f ms  %.1f TFLOP/s' % (precision, B, best, fl / best / 1e9))
 
 
-def grad_case(B, H, W, K, debug, precision, use_sm=True, seed=4):
+def grad_case(B, H, W, K, debug, precision, use_sm=True, seed=4, perturb=True, pin_relu=True):
     """Returns (oracle grads dict, gpu grads dict, oracle losses, gpu losses) for one training-mode forward+backward."""
     from jcm import train as jtrain
     gen = torch.Generator().manual_seed(seed)
@@ -271,9 +273,9 @@ def grad_case(B, H, W, K, debug, precision, use_sm=True, seed=4):
     names = orc.JOINT_NAMES[:K] + ['torso']
     p64 = orc.init_part_detector(K, gen, debug=debug)
     for k, v in p64.items():
-        if 'gamma' in k:
+        if perturb and 'gamma' in k:
             v.add_(torch.rand(v.shape, generator=gen).double() * 0.5)
-        if 'beta' in k or 'biases' in k:
+        if perturb and ('beta' in k or 'biases' in k):
             v.add_(torch.randn(v.shape, generator=gen).double() * 0.1)
     rng = np.random.default_rng(seed)
     distr = jcm.get_pairwise_distr() if (hm_h, hm_w) == (60, 90) else orc.synthetic_pairwise(names, K, hm_h, hm_w, rng)
@@ -287,20 +289,24 @@ def grad_case(B, H, W, K, debug, precision, use_sm=True, seed=4):
     sm32 = {k: v.float() for k, v in sm64.items()}
     x = torch.rand(B, H, W, 3, generator=gen)
     y = torch.from_numpy(orc.synthetic_labels(B, hm_h, hm_w, K + 1, rng))
-    # oracle
-    po = {k: v.double().clone().requires_grad_('moving_' not in k) for k, v in p32.items()}
-    so = {k: v.double().clone().requires_grad_('moving_' not in k) for k, v in sm32.items()}
-    out = orc.tower_forward(x.double(), y.double(), po, so, K, True, use_sm=use_sm, lmbd=0.0)
-    (out['loss_pd'] + out['loss_sm']).backward()
-    ref = {k: v.grad for k, v in po.items() if v.requires_grad}
-    ref.update({k: v.grad for k, v in so.items() if v.requires_grad})
     # gpu
     p = jcm.load_params(p32)
     smp = jcm.PairwiseParams.from_dict(sm32, names, K)
     ctx = jcm.Context(n_joints=K, joint_names=names, flag_train=True, precision=precision, debug=debug, use_sm=use_sm)
     tr = jtrain.Trainer(p, smp, ctx)
-    res = tr.forward_backward(x.to(dev), y.to(dev))
+    tap = {}
+    res = tr.forward_backward(x.to(dev), y.to(dev), tap=tap)
     torch.cuda.synchronize()
+    # oracle (ReLU on/off pattern pinned to the GPU forward's unless pin_relu=False)
+    masks = pins.relu_masks(tap) if pin_relu else None
+    psel = pins.pool_select(jcm, tap, tr.p) if pin_relu else None
+    po = {k: v.double().clone().requires_grad_('moving_' not in k) for k, v in p32.items()}
+    so = {k: v.double().clone().requires_grad_('moving_' not in k) for k, v in sm32.items()}
+    out = orc.tower_forward(x.double(), y.double(), po, so, K, True, use_sm=use_sm, lmbd=0.0, relu_masks=masks, joint_names=names,
+                            pool_select=psel)
+    (out['loss_pd'] + out['loss_sm']).backward()
+    ref = {k: v.grad for k, v in po.items() if v.requires_grad}
+    ref.update({k: v.grad for k, v in so.items() if v.requires_grad})
     got = {}
     for k in p32:
         if 'moving_' not in k:
@@ -316,11 +322,13 @@ def grad_case(B, H, W, K, debug, precision, use_sm=True, seed=4):
 
 
 def sec_grad():
-    for (B, H, W, K, debug, precision, use_sm) in [(2, 96, 160, 4, True, 'fp32', True), (2, 96, 160, 4, True, 'bf16', True),
-                                                   (1, 64, 96, 7, False, 'fp32', False)]:
+    cases = [(2, 96, 160, 4, True, 'fp32', True, 4, True), (2, 96, 160, 4, True, 'bf16', True, 4, True),
+             (1, 128, 192, 7, False, 'fp32', False, 4, True), (2, 64, 96, 3, True, 'fp32', True, 5, False)]
+    for (B, H, W, K, debug, precision, use_sm, seed, perturb) in cases:
         try:
-            ref, got, lo, lg = grad_case(B, H, W, K, debug, precision, use_sm)
-            print('GRAD B%d %dx%d K%d debug=%d %s use_sm=%d: losses oracle %.5f %.5f gpu %.5f %.5f' % ((B, H, W, K, debug, precision, use_sm) + lo + lg))
+            ref, got, lo, lg = grad_case(B, H, W, K, debug, precision, use_sm, seed=seed, perturb=perturb)
+            print('GRAD B%d %dx%d K%d debug=%d %s use_sm=%d seed=%d perturb=%d: losses oracle %.5f %.5f gpu %.5f %.5f' % (
+                (B, H, W, K, debug, precision, use_sm, seed, perturb) + lo + lg))
             worst = 0.0
             agg = {}
             for k in sorted(ref):
@@ -342,6 +350,64 @@ def sec_grad():
         except Exception as e:
             print('GRAD case FAILED', repr(e))
             traceback.print_exc()
+
+
+def sec_step():
+    """One optimizer step at debug width: gradient, clip norm and updated parameters vs the oracle, per variable."""
+    from jcm import train as jtrain
+    B, H, W, K = 2, 64, 96, 3
+    gen = torch.Generator().manual_seed(5)
+    names = orc.JOINT_NAMES[:K] + ['torso']
+    rng = np.random.default_rng(5)
+    p32 = {k: v.float() for k, v in orc.init_part_detector(K, gen, debug=True).items()}
+    sm32 = {k: v.float() for k, v in orc.init_spatial_model(orc.synthetic_pairwise(names, K, H // 8, W // 8, rng), K, H // 8, W // 8,
+                                                           joint_names=names).items()}
+    x = torch.rand(B, H, W, 3, generator=gen)
+    y = torch.from_numpy(orc.synthetic_labels(B, H // 8, W // 8, K + 1, rng))
+    lmbd, lr = 0.01, 2e-2
+    p = jcm.load_params(p32)
+    smp = jcm.PairwiseParams.from_dict(sm32, names, K)
+    ctx = jcm.Context(n_joints=K, joint_names=names, flag_train=True, precision='fp32', debug=True, lmbd=lmbd)
+    tr = jtrain.Trainer(p, smp, ctx, lr=lr, optimizer='momentum')
+    po = {k: v.double().clone().requires_grad_('moving_' not in k) for k, v in p32.items()}
+    so = {k: v.double().clone().requires_grad_('moving_' not in k) for k, v in sm32.items()}
+    tap = {}
+    res = tr.forward_backward(x.to(dev), y.to(dev), tap=tap)
+    graw = {k: tr.g[k].clone() for k in p32 if 'moving_' not in k}
+    masks, psel = pins.relu_masks(tap), pins.pool_select(jcm, tap, tr.p)
+    tr.apply()
+    out = orc.tower_forward(x.double(), y.double(), po, so, K, True, lmbd=lmbd, relu_masks=masks, joint_names=names, pool_select=psel)
+    keys = [k for k, v in po.items() if v.requires_grad]
+    g_nowd = torch.autograd.grad(out['loss_pd'] + out['loss_sm'], [po[k] for k in keys], retain_graph=True)
+    allv = [v for v in list(po.values()) + list(so.values()) if v.requires_grad]
+    g_all = torch.autograd.grad(out['loss'], allv)
+    _, gn = orc.grad_renorm(list(g_all), 4.0)
+    print('STEP norm oracle %.6f gpu %.6f ; wd term oracle %.6f gpu %.6f' % (gn, float(tr.stats[0]), float(orc.weight_decay(po)), float(tr.stats[1])))
+    scale = 4.0 / max(gn, 4.0)
+    for k, g0 in zip(keys, g_nowd):
+        if k in ('conv2_fullres/weights', 'conv1_fullres/weights'):
+            d = (graw[k].double().cpu() - g0).abs()
+            print('   ', k, 'max err per cin', [float('%.1e' % v) for v in d.amax((0, 1, 3))])
+            print('   ', k, 'max err per cout', [float('%.1e' % v) for v in d.amax((0, 1, 2))])
+            print('   ', k, 'max err per tap', [float('%.1e' % v) for v in d.amax((2, 3)).flatten()])
+    a1 = tap['conv1_fullres/relu']
+    a64 = a1.double().cpu()
+    print('    conv1_fullres relu: per-channel fraction > 0', [float('%.3f' % v) for v in (a64 > 0).double().mean((0, 1, 2))])
+    bn1 = {'gamma': torch.ones(16, dtype=torch.float64), 'beta': torch.zeros(16, dtype=torch.float64)}
+    hb = orc.batch_norm(a64, bn1, True, update=False)
+    # ties inside 2x2 pooling windows among positive values
+    hp = hb.permute(0, 3, 1, 2)
+    win = torch.nn.functional.unfold(hp.reshape(-1, 1, hp.shape[2], hp.shape[3]), 2, stride=2)   # [B*C, 4, L]
+    srt = win.sort(dim=1, descending=True).values
+    gap = (srt[:, 0] - srt[:, 1])
+    apos = torch.nn.functional.unfold(a64.permute(0, 3, 1, 2).reshape(-1, 1, hp.shape[2], hp.shape[3]), 2, stride=2).amax(1) > 0
+    print('    pooling windows with top-2 gap < 1e-6 and a positive max: %d of %d; exact ties: %d' % (
+        int(((gap < 1e-6) & apos).sum()), gap.numel(), int(((gap == 0) & apos).sum())))
+    for k, g0 in zip(keys, g_nowd):
+        gfull = g0 + (lmbd * po[k].detach() if 'weights' in k else 0)
+        new = po[k].detach() - lr * scale * gfull
+        print('    %-36s grad err %.2e  param err %.2e  (|update|max %.2e, |param| max %.2e)' % (
+            k, relerr(graw[k], g0), relerr(tr.p[k], new), float((lr * scale * gfull).abs().max()), float(new.abs().max())))
 
 
 def sec_smtime():

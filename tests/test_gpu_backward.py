@@ -1,0 +1,395 @@
+"""GPU parity tests (-m gpu) of the BACKWARD pass and the optimizer: every kernel, called through the C ABI via the jcm
+Python surface, against torch-autograd gradients of the CPU oracle (fp64) on identical seeded inputs.
+
+The reference obtains these gradients from TensorFlow's autodiff (`opt.compute_gradients(loss_tower)`, main.py:557-560),
+so the oracle for them is autograd of the restated graph.  Tolerances:
+  * single kernels, fp32 config (bf16x3 split products):  max|gpu - oracle| / max|oracle| <= 1e-4 .. 5e-4
+  * whole training step, fp32 config:                     <= 2e-3 per variable with the ReLU on/off pattern and the max-pool
+                                                          arg-max pinned to the GPU forward's (tests/pins.py explains why)
+  * bf16 config (training arithmetic of BASELINE config 3): cosine similarity of every weight gradient >= 0.98
+    (stated; not a 1e-3 parity claim - bf16 operands carry 2^-9 relative rounding)
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import jcm_oracle as orc
+import pins
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def jcm(built_lib):
+    if not torch.cuda.is_available():
+        pytest.fail('GPU tests need a CUDA device (no CPU fallback exists)')
+    import jcm as _jcm
+    _jcm.lib()
+    return _jcm
+
+
+@pytest.fixture(scope='module')
+def jtrain(jcm):
+    from jcm import train
+    return train
+
+
+def rel(a, b, floor=0.0):
+    a = a.detach().double().cpu()
+    b = torch.as_tensor(np.asarray(b)).double() if not torch.is_tensor(b) else b.detach().double().cpu()
+    return float((a - b).abs().max() / max(float(b.abs().max()), floor, 1e-30))
+
+
+def cosine(a, b):
+    a = a.detach().double().cpu().flatten()
+    b = b.detach().double().cpu().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-300))
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+# ------------------------------------------------------------------------------------------------ loss heads
+def test_softmax_ce_bwd(jcm, jtrain):
+    g = torch.Generator().manual_seed(11)
+    B, H, W, K = 3, 12, 20, 5
+    logits = (torch.randn(B, H, W, K, generator=g) * 2).double().requires_grad_(True)
+    labels = torch.from_numpy(orc.synthetic_labels(B, H, W, K + 1, np.random.default_rng(2)))
+    loss = orc.softmax_cross_entropy(logits, labels.double()[..., :K])
+    loss.backward()
+    lg = logits.detach().float().cuda()
+    l, per, lse = jcm.ops.softmax_ce(lg, labels.cuda(), want_lse=True)
+    d = jtrain.softmax_ce_bwd(lg, labels.cuda(), lse, 1.0 / (B * K))
+    assert abs(float(l) - float(loss)) < 1e-5 * abs(float(loss))
+    assert rel(d, logits.grad) < 1e-5
+
+
+@pytest.mark.parametrize('accumulate', [False, True])
+def test_spatial_softmax_bwd(jcm, jtrain, accumulate):
+    g = torch.Generator().manual_seed(12)
+    B, H, W, K = 2, 10, 14, 4
+    x = torch.randn(B, H, W, K, generator=g).double().requires_grad_(True)
+    dy = torch.randn(B, H, W, K + 1, generator=g)       # the spatial model's input gradient has K+1 channels
+    y = orc.spatial_softmax(x)
+    (y * dy[..., :K].double()).sum().backward()
+    yg = jcm.spatial_softmax(x.detach().float().cuda())
+    base = torch.randn(B, H, W, K, generator=g)
+    dx = base.clone().cuda() if accumulate else torch.empty(B, H, W, K, device='cuda')
+    jtrain.spatial_softmax_bwd(yg, dy.cuda(), dx, accumulate)
+    want = x.grad + (base.double() if accumulate else 0)
+    assert rel(dx, want) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ BN / ReLU / pool / upsample
+@pytest.mark.parametrize('shape,pool', [((2, 12, 20, 64), False), ((2, 12, 20, 64), True), ((1, 15, 23, 128), True),
+                                        ((3, 9, 7, 16), True), ((1, 30, 45, 512), False)])
+@pytest.mark.parametrize('split', [False, True])
+def test_bn_relu_pool_bwd(jcm, jtrain, shape, pool, split):
+    """conv output -> ReLU -> batch norm (batch statistics) [-> 2x2 SAME max-pool]: gradients w.r.t. the conv output, gamma, beta
+    and the conv bias, as TF autodiff of main.py:156-174 gives them."""
+    g = torch.Generator().manual_seed(13)
+    B, H, W, C = shape
+    pre = torch.randn(B, H, W, C, generator=g)
+    gamma = torch.rand(C, generator=g) + 0.5
+    beta = torch.randn(C, generator=g) * 0.2
+    pre64 = pre.double().requires_grad_(True)
+    bn = {'gamma': gamma.double().requires_grad_(True), 'beta': beta.double().requires_grad_(True),
+          'moving_mean': torch.zeros(C, dtype=torch.float64), 'moving_variance': torch.ones(C, dtype=torch.float64)}
+    out = orc.batch_norm(torch.relu(pre64), bn, True)
+    if pool:
+        out = orc.max_pool_layer(out)
+    dout = torch.randn(out.shape, generator=g)
+    dy_scale = 1.0 / 3.0
+    (out * dout.double() * dy_scale).sum().backward()
+
+    a = torch.relu(pre).cuda()
+    mm, mv = torch.zeros(C, device='cuda'), torch.ones(C, device='cuda')
+    ss, st = jcm.ops.bn_scale_shift(a, gamma.cuda(), beta.cuda(), mm, mv, train=True, save=True)
+    dgamma, dbeta, dbias = (torch.empty(C, device='cuda') for _ in range(3))
+    planes, f32 = jtrain.bn_relu_bwd(a, dout.cuda(), ss, st, dy_scale, pool, split, dgamma, dbeta, dbias, want_f32=True)
+    assert rel(f32, pre64.grad) < 2e-5
+    rec = planes.hi.float() + (planes.lo.float() if split else 0)
+    assert rel(rec, pre64.grad) < (2e-5 if split else 5e-3)
+    assert rel(dgamma, bn['gamma'].grad) < 5e-5
+    assert rel(dbeta, bn['beta'].grad) < 5e-5
+    assert rel(dbias, pre64.grad.sum((0, 1, 2))) < 5e-5
+
+
+def test_upsample_avg3_bwd(jcm, jtrain):
+    g = torch.Generator().manual_seed(14)
+    B, C = 2, 32
+    a2 = torch.randn(B, 30, 45, C, generator=g).double().requires_grad_(True)
+    a3 = torch.randn(B, 15, 23, C, generator=g).double().requires_grad_(True)
+    dm = torch.randn(B, 60, 90, C, generator=g)
+    out = (orc.resize_images(a2, 60, 90) + orc.resize_images(a3, 60, 90)) / 3
+    (out * dm.double()).sum().backward()
+    d2, d3 = jtrain.upsample_avg3_bwd(dm.cuda(), (30, 45), (15, 23))
+    assert rel(d2, a2.grad) < 1e-5
+    assert rel(d3, a3.grad) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ conv gradients
+WGRAD_CASES = [  # B, H, W, Cin, Cout, k : M side = the wider tensor, every swizzle mode, ragged patches, 2 M tiles, 2 N tiles
+    (2, 12, 20, 64, 64, 5), (1, 15, 23, 128, 256, 9), (2, 16, 24, 32, 64, 5), (1, 9, 33, 16, 64, 3), (2, 8, 12, 256, 512, 9),
+    (1, 12, 20, 128, 7, 9), (3, 7, 5, 64, 16, 3), (1, 30, 45, 512, 512, 9), (2, 60, 90, 16, 32, 5)]
+
+
+@pytest.mark.parametrize('case', WGRAD_CASES)
+@pytest.mark.parametrize('split', [False, True])
+def test_conv2d_wgrad_and_dgrad(jcm, jtrain, case, split):
+    B, H, W, Cin, Cout, k = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x = torch.randn(B, H, W, Cin, generator=g)
+    w = torch.randn(k, k, Cin, Cout, generator=g) / math.sqrt(k * k * Cin)
+    dy = torch.randn(B, H, W, Cout, generator=g)
+    xr, wr, dyr = (x, w, dy) if split else (bf16r(x), bf16r(w), bf16r(dy))
+    x64 = xr.double().requires_grad_(True)
+    w64 = wr.double().requires_grad_(True)
+    (orc.conv2d(x64, w64, 1) * dyr.double()).sum().backward()
+
+    xp = jcm.ops.split_planes(x.cuda(), split)
+    gp = jtrain.pad_planes(dy.cuda(), jcm.ops.pad16(Cout), split)
+    dw = torch.empty(k * k, Cin, Cout, device='cuda')
+    jtrain.conv2d_wgrad(xp, gp, dw, Cout, k)
+    assert rel(dw.view(k, k, Cin, Cout), w64.grad) < 2e-4
+    if Cin % 16 == 0:
+        wp_t = jcm.ops.pack_weights(w.cuda(), split, transpose=True)
+        dx = jcm.ops.conv2d_planes(gp, wp_t, None, Cin, k, relu=False)
+        assert rel(dx, x64.grad) < 2e-4
+
+
+@pytest.mark.parametrize('split', [False, True])
+def test_conv1_stride2_wgrad_via_space_to_depth(jcm, jtrain, split):
+    g = torch.Generator().manual_seed(15)
+    x = torch.rand(2, 48, 80, 3, generator=g)
+    w = torch.randn(5, 5, 3, 64, generator=g) / math.sqrt(75)
+    banks = jcm.ops.prep_input(x.cuda(), split)
+    for bi, step in enumerate((1, 2, 4)):
+        xs = x[:, ::step, ::step]
+        Ho, Wo = xs.shape[1] // 2, xs.shape[2] // 2
+        dy = torch.randn(2, Ho, Wo, 64, generator=g)
+        xr, dyr = (xs, dy) if split else (bf16r(xs), bf16r(dy))
+        w64 = w.double().requires_grad_(True)
+        (orc.conv2d(xr.double(), w64, 2) * dyr.double()).sum().backward()
+        gp = jcm.ops.split_planes(dy.cuda(), split)
+        g9 = torch.empty(9, 16, 64, device='cuda')
+        jtrain.conv2d_wgrad(banks[bi], gp, g9, 64, 3)
+        dw = torch.empty(5, 5, 3, 64, device='cuda')
+        jtrain.unpack_s2d_grad(g9, dw)
+        assert rel(dw, w64.grad) < 2e-4
+
+
+# ------------------------------------------------------------------------------------------------ spatial model
+@pytest.mark.parametrize('B,K,H,W', [(2, 4, 12, 20), (5, 3, 9, 13), (2, 7, 60, 90), (6, 7, 60, 90)])
+@pytest.mark.parametrize('train', [True, False])
+def test_spatial_model_bwd(jcm, jtrain, B, K, H, W, train):
+    """dE, db, d(bn gamma/beta), d(heat map) of SURVEY Appendix D vs autograd of the oracle."""
+    seed = 16
+    rng = np.random.default_rng(seed)
+    g = torch.Generator().manual_seed(seed)
+    names = orc.JOINT_NAMES[:K] + ['torso']
+    distr = jcm.get_pairwise_distr() if (H, W) == (60, 90) else orc.synthetic_pairwise(names, K, H, W, rng)
+    sm64 = orc.init_spatial_model(distr, K, H, W, joint_names=names)
+    for k, v in sm64.items():
+        if k.startswith('bias_'):
+            v.add_(torch.rand(v.shape, generator=g).double() * 0.01)
+        if 'gamma' in k or 'beta' in k:
+            v.add_(torch.randn(v.shape, generator=g).double() * 0.1)
+        if 'moving_variance' in k:
+            v.add_(torch.rand(v.shape, generator=g).double())
+    sm32 = {k: v.float() for k, v in sm64.items()}
+    hm = torch.softmax(3 * torch.randn(B, H * W, K, generator=g), dim=1).reshape(B, H, W, K)
+    cat = torch.cat([hm, torch.from_numpy(orc.synthetic_labels(B, H, W, 1, rng))], dim=3).contiguous()
+    gout = torch.randn(B, H, W, K, generator=g) / (B * K)
+
+    so = {k: v.double().clone().requires_grad_('moving_' not in k) for k, v in sm32.items()}
+    cat64 = cat.double().requires_grad_(True)
+    out = orc.spatial_model(cat64, so, K, train, joint_names=names)
+    (out * gout.double()).sum().backward()
+
+    smp = jcm.PairwiseParams.from_dict(sm32, names, K)
+    bn = smp.bn
+    catg = cat.cuda()
+    ss, st = jcm.ops.bn_scale_shift(catg, bn['gamma'], bn['beta'], bn['moving_mean'], bn['moving_variance'], train=train, save=True)
+    o, ws = jcm.ops.spatial_model_fwd(catg, ss, smp.energies, smp.biases, smp.pair_target, smp.pair_cond, K, keep_workspace=True)
+    assert rel(o, out) < 1e-4
+    dE, db = torch.empty_like(smp.energies), torch.empty_like(smp.biases)
+    dgamma, dbeta = torch.empty(K + 1, device='cuda'), torch.empty(K + 1, device='cuda')
+    d_hm = jtrain.spatial_model_bwd(gout.cuda(), catg, ss, st, train, smp, ws, dE, db, dgamma, dbeta)
+    refE = torch.stack([so['energy_' + k].grad[0, :, :, 0] for k in smp.keys])
+    refb = torch.stack([so['bias_' + k].grad[0, :, :, 0] for k in smp.keys])
+    assert rel(dE, refE) < 3e-4
+    assert rel(db, refb) < 3e-4
+    assert rel(d_hm, cat64.grad) < 3e-4
+    assert rel(dgamma, so['bn_sm/BatchNorm/gamma'].grad) < 3e-4
+    assert rel(dbeta, so['bn_sm/BatchNorm/beta'].grad) < 3e-4
+
+
+# ------------------------------------------------------------------------------------------------ optimizer
+@pytest.mark.parametrize('optimizer', ['adam', 'momentum'])
+def test_grad_prepare_clip_and_optimizer_steps(jcm, optimizer):
+    """mean over replicas + weight decay (main.py:195-205,541) + clip_by_global_norm(4) (main.py:302-309) + TF1 Adam /
+    Momentum (main.py:501-506,577) on flat buffers, three steps, vs the oracle's restatement."""
+    import ctypes
+    from jcm._lib import lib, check
+    from jcm.ops import _ptr, _stream
+    g = torch.Generator().manual_seed(17)
+    n, n_decay, world, lmbd, lr, clip = 10000, 6000, 4, 0.01, 1e-3, 4.0
+    w0 = torch.randn(n, generator=g)
+    w = w0.clone().cuda()
+    m, v = torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
+    nb = lib().jcm_optim_blocks(n)
+    partial = torch.empty(2 * nb, device='cuda')
+    stats = torch.zeros(2, device='cuda')
+    wr = w0.double().clone()
+    mr, vr = torch.zeros(n, dtype=torch.float64), torch.zeros(n, dtype=torch.float64)
+    for t in range(1, 4):
+        gsum = torch.randn(n, generator=g) * (3.0 if t == 1 else 0.01)      # step 1 clips, later steps do not
+        gd = gsum.clone().cuda()
+        check(lib().jcm_grad_prepare(_ptr(gd), _ptr(w), n, n_decay, 1.0 / world, lmbd, _ptr(partial), _ptr(stats), _stream()), 'prep')
+        gr = gsum.double() / world
+        wd = 0.5 * float((wr[:n_decay] ** 2).sum())
+        gr[:n_decay] += lmbd * wr[:n_decay]
+        (gc,), gn = orc.grad_renorm([gr], clip)
+        assert abs(float(stats[0]) - gn) < 1e-5 * gn
+        assert abs(float(stats[1]) - wd) < 1e-5 * wd
+        if optimizer == 'adam':
+            lr_t = lr * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
+            check(lib().jcm_clip_adam(_ptr(w), _ptr(gd), _ptr(m), _ptr(v), n, _ptr(stats), clip, lr_t, 0.9, 0.999, 1e-8, 0, _stream()), 'adam')
+            orc.adam_tf1_step([wr], [gc], [mr], [vr], t, lr)
+        else:
+            check(lib().jcm_clip_adam(_ptr(w), _ptr(gd), _ptr(m), _ptr(v), n, _ptr(stats), clip, lr, 0.9, 0.0, 0.0, 1, _stream()), 'mom')
+            mr.mul_(0.9).add_(gc)                      # [TF1] MomentumOptimizer: accum = momentum*accum + g; w -= lr*accum
+            wr.sub_(lr * mr)
+        assert rel(w, wr) < 1e-6
+    assert float((w.cpu().double() - w0.double()).abs().max()) > 1e-4      # the parameters did move
+
+
+# ------------------------------------------------------------------------------------------------ whole training step
+def _train_case(jcm, jtrain, B, H, W, K, debug, precision, use_sm, seed=4, pin_relu=True):
+    gen = torch.Generator().manual_seed(seed)
+    hm_h, hm_w = H // 8, W // 8
+    names = orc.JOINT_NAMES[:K] + ['torso']
+    p64 = orc.init_part_detector(K, gen, debug=debug)
+    for k, v in p64.items():
+        if 'gamma' in k:
+            v.add_(torch.rand(v.shape, generator=gen).double() * 0.5)
+        if 'beta' in k or 'biases' in k:
+            v.add_(torch.randn(v.shape, generator=gen).double() * 0.1)
+    rng = np.random.default_rng(seed)
+    distr = jcm.get_pairwise_distr() if (hm_h, hm_w) == (60, 90) else orc.synthetic_pairwise(names, K, hm_h, hm_w, rng)
+    sm64 = orc.init_spatial_model(distr, K, hm_h, hm_w, joint_names=names)
+    for k, v in sm64.items():
+        if k.startswith('bias_'):
+            v.add_(torch.rand(v.shape, generator=gen).double() * 0.01)
+        if 'gamma' in k or 'beta' in k:
+            v.add_(torch.randn(v.shape, generator=gen).double() * 0.1)
+    p32 = {k: v.float() for k, v in p64.items()}
+    sm32 = {k: v.float() for k, v in sm64.items()}
+    x = torch.rand(B, H, W, 3, generator=gen)
+    y = torch.from_numpy(orc.synthetic_labels(B, hm_h, hm_w, K + 1, rng))
+
+    p = jcm.load_params(p32)
+    smp = jcm.PairwiseParams.from_dict(sm32, names, K)
+    ctx = jcm.Context(n_joints=K, joint_names=names, flag_train=True, precision=precision, debug=debug, use_sm=use_sm)
+    tr = jtrain.Trainer(p, smp, ctx)
+    tap = {}
+    res = tr.forward_backward(x.cuda(), y.cuda(), tap=tap)
+    torch.cuda.synchronize()
+    got = {k: tr.g[k] for k in p32 if 'moving_' not in k}
+    if use_sm:
+        P, H2, W2 = smp.energies.shape
+        for i, key in enumerate(smp.keys):
+            got['energy_' + key] = tr.g['sm/energies'][i].view(1, H2, W2, 1)
+            got['bias_' + key] = tr.g['sm/biases'][i].view(1, H2 // 2, W2 // 2, 1)
+        got['bn_sm/BatchNorm/gamma'] = tr.g['sm/gamma']
+        got['bn_sm/BatchNorm/beta'] = tr.g['sm/beta']
+
+    masks = pins.relu_masks(tap) if pin_relu else None
+    psel = pins.pool_select(jcm, tap, tr.p) if pin_relu else None
+    po = {k: v.double().clone().requires_grad_('moving_' not in k) for k, v in p32.items()}
+    so = {k: v.double().clone().requires_grad_('moving_' not in k) for k, v in sm32.items()}
+    out = orc.tower_forward(x.double(), y.double(), po, so, K, True, use_sm=use_sm, lmbd=0.0, relu_masks=masks, joint_names=names,
+                            pool_select=psel)
+    (out['loss_pd'] + out['loss_sm']).backward()
+    ref = {k: v.grad for k, v in list(po.items()) + (list(so.items()) if use_sm else []) if v.requires_grad}
+    return ref, got, out, res
+
+
+@pytest.mark.parametrize('cfg', [(2, 96, 160, 4, True, True), (1, 128, 192, 7, False, False), (2, 64, 96, 3, True, True)])
+def test_training_step_gradients_fp32(jcm, jtrain, cfg):
+    B, H, W, K, debug, use_sm = cfg
+    ref, got, out, res = _train_case(jcm, jtrain, B, H, W, K, debug, 'fp32', use_sm)
+    assert abs(float(res['loss_pd']) - float(out['loss_pd'])) < 1e-3 * float(out['loss_pd'])
+    assert abs(float(res['loss_sm']) - float(out['loss_sm'])) < 1e-3 * float(out['loss_sm'])
+    gmax = max(float(v.abs().max()) for v in ref.values())
+    # conv6/biases: softmax gradients sum to zero over H*W, so the reference value is exactly 0 up to rounding noise and the
+    # GPU's is fp32 summation noise (~1e-8): compared against an absolute floor
+    errs = {k: rel(got[k], r, floor=(1e-4 if k == 'conv6/biases' else 1e-5) * gmax) for k, r in ref.items()}
+    bad = {k: e for k, e in errs.items() if e >= 2e-3}
+    assert not bad, bad
+
+
+def test_training_step_gradients_bf16(jcm, jtrain):
+    ref, got, out, res = _train_case(jcm, jtrain, 2, 96, 160, 4, True, 'bf16', True)
+    assert abs(float(res['loss_pd']) - float(out['loss_pd'])) < 1e-2 * float(out['loss_pd'])
+    for k, r in ref.items():
+        if k.endswith('/weights') or k.startswith('energy_'):
+            assert cosine(got[k], r) > 0.98, k
+
+
+def test_trainer_steps_follow_the_oracle(jcm, jtrain):
+    """Three full steps (forward, backward, weight decay, clip, Momentum) at debug width: the parameters after each step match
+    the oracle's update computed from ITS OWN gradients (ReLU pattern pinned), and the loss goes down.  Momentum rather than
+    Adam here because Adam's first steps are +-lr * sign(g): wherever g is rounding noise the comparison would be a coin flip
+    (the Adam arithmetic itself is pinned by test_grad_prepare_clip_and_optimizer_steps)."""
+    B, H, W, K = 2, 64, 96, 3
+    gen = torch.Generator().manual_seed(5)
+    names = orc.JOINT_NAMES[:K] + ['torso']
+    rng = np.random.default_rng(5)
+    p32 = {k: v.float() for k, v in orc.init_part_detector(K, gen, debug=True).items()}
+    sm32 = {k: v.float() for k, v in orc.init_spatial_model(orc.synthetic_pairwise(names, K, H // 8, W // 8, rng), K, H // 8, W // 8,
+                                                           joint_names=names).items()}
+    x = torch.rand(B, H, W, 3, generator=gen)
+    y = torch.from_numpy(orc.synthetic_labels(B, H // 8, W // 8, K + 1, rng))
+    lmbd, lr = 0.01, 2e-2
+    p = jcm.load_params(p32)
+    smp = jcm.PairwiseParams.from_dict(sm32, names, K)
+    ctx = jcm.Context(n_joints=K, joint_names=names, flag_train=True, precision='fp32', debug=True, lmbd=lmbd)
+    tr = jtrain.Trainer(p, smp, ctx, lr=lr, optimizer='momentum')
+    po = {k: v.double().clone().requires_grad_('moving_' not in k) for k, v in p32.items()}
+    so = {k: v.double().clone().requires_grad_('moving_' not in k) for k, v in sm32.items()}
+    train_o = [(k, v) for k, v in list(po.items()) + list(so.items()) if v.requires_grad]
+    m = [torch.zeros_like(v) for _, v in train_o]
+    losses = []
+    for t in (1, 2, 3):
+        tap = {}
+        res = tr.forward_backward(x.cuda(), y.cuda(), tap=tap)
+        masks, psel = pins.relu_masks(tap), pins.pool_select(jcm, tap, tr.p)
+        tr.apply()
+        out = orc.tower_forward(x.double(), y.double(), po, so, K, True, lmbd=lmbd, relu_masks=masks, joint_names=names,
+                                pool_select=psel)
+        losses.append(float(res['loss_pd']) + float(res['loss_sm']))
+        assert abs(losses[-1] - float(out['loss_pd'] + out['loss_sm'])) < 2e-3 * losses[-1]
+        grads = torch.autograd.grad(out['loss'], [v for _, v in train_o])
+        grads, _ = orc.grad_renorm(list(grads), 4.0)
+        with torch.no_grad():
+            for (_, v), g_, m_ in zip(train_o, grads, m):     # [TF1] MomentumOptimizer(momentum=0.9), main.py:503-504
+                m_.mul_(0.9).add_(g_)
+                v.sub_(lr * m_)
+        for k, v in train_o:
+            if k.startswith('energy_') or k.startswith('bias_'):
+                i = smp.keys.index(k.split('_', 1)[1])
+                gv = (tr.sm.energies if k.startswith('energy_') else tr.sm.biases)[i]
+                assert rel(gv, v.detach()[0, :, :, 0]) < 2e-3, (t, k)
+            elif k.startswith('bn_sm'):
+                assert rel(tr.sm.bn[k.split('/')[-1]], v.detach()) < 2e-3, (t, k)
+            elif k == 'conv6/biases':    # its gradient is identically zero (softmax gradients sum to 0): stays at its init
+                assert float(tr.p[k].abs().max()) < 1e-6 and float(v.detach().abs().max()) < 1e-6
+            else:
+                assert rel(tr.p[k], v.detach()) < 2e-3, (t, k)
+    assert losses[-1] < losses[0]
