@@ -152,6 +152,18 @@ int jcm_spatial_model_bwd(const float* g, const float* heat_map, const float* bn
                           const int* pair_cond, const void* fwd_workspace, void* workspace, long workspace_bytes, float* d_heat_map,
                           float* dE, float* db, float* dgamma, float* dbeta, int B, int H, int W, int K, int P, void* stream);
 
+/* ---- tap-expanded form of a convolution with very few output channels (conv6: 9x9, 512 -> K, main.py:72) ------------------
+ * y[p,co] = b[co] + sum_tap Z[p+tap-pad, tap*KP+co] with Z = 1x1 conv (jcm_conv2d_fwd, ksize 1) of the input with the weights packed
+ * by jcm_pack_weights_taps (rows n = tap*KP+co; KP = Cout padded to a multiple of 4; Npad >= k*k*KP rows, zero filled).
+ * Backward: jcm_tap_scatter_planes builds Gt[q, tap*KP+co] = G[q-(tap-pad), co] as bf16 operand planes; the weight gradient is
+ * jcm_conv2d_wgrad(x, Gt, ksize 1) -> dwz [Cin][ZC] -> jcm_unpack_tap_grad -> [k,k,Cin,Cout]; the data gradient is jcm_conv2d_fwd
+ * (ksize 1) of Gt with jcm_pack_weights_taps(transpose = 1). */
+int jcm_pack_weights_taps(const float* w, int ksize, int Cin, int Cout, int KP, int Npad, int transpose, void* out_hi, void* out_lo,
+                          void* stream);
+int jcm_tap_gather(const float* z, const float* bias, int B, int H, int W, int ksize, int KP, int ZC, int Cout, float* y, void* stream);
+int jcm_tap_scatter_planes(const float* g, int B, int H, int W, int ksize, int Cout, int KP, int Npad, void* hi, void* lo, void* stream);
+int jcm_unpack_tap_grad(const float* dwz, int ksize, int Cin, int Cout, int KP, int ZC, float* dw, void* stream);
+
 /* ---- optimizer on flat buffers (main.py:243-267 gradient mean, :195-205 weight decay, :302-309 clip, :501-506,577 Adam) --- */
 int jcm_optim_blocks(long n);
 /* g <- g * inv_world + lmbd * w (first n_decay elements); stats[0] = ||g||, stats[1] = sum w^2/2.  partial: 2*jcm_optim_blocks(n). */

@@ -46,6 +46,10 @@ SIGNATURES = {
     'jcm_unpack_s2d_grad': (_I, [_P, _I, _P, _P]),
     'jcm_spatial_model_bwd_workspace': (_L, [_I, _I, _I, _I, _I]),
     'jcm_spatial_model_bwd': (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    'jcm_pack_weights_taps': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    'jcm_tap_gather': (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    'jcm_tap_scatter_planes': (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    'jcm_unpack_tap_grad': (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     'jcm_optim_blocks': (_I, [_L]),
     'jcm_grad_prepare': (_I, [_P, _P, _L, _L, _F, _F, _P, _P, _P]),
     'jcm_clip_adam': (_I, [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _I, _P]),

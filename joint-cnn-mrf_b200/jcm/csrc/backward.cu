@@ -213,13 +213,18 @@ __global__ void bn_relu_bwd_kernel(BnBwdArgs p) {
 }
 
 // sums[j][c] = sum over blocks of partial[blk][j][c] (double accumulation); optionally scaled by mul[c]
-__global__ void colsum_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, int rows, float* __restrict__ sums) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * C) return;
-  const int j = idx / C, c = idx % C;
-  double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += (double)partial[((long)b * 2 + j) * C + c];
-  sums[idx] = (float)s;
+__global__ void colsum_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, int rows, float* __restrict__ sums,
+                                       float* __restrict__ copy0, float* __restrict__ copy1) {
+  __shared__ double sh[kPartY][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  for (int j = 0; j < rows; ++j) {
+    const double s = partial_colsum(partial, nblocks, C, j, c, sh);
+    if (threadIdx.y == 0 && c < C) {
+      sums[j * C + c] = (float)s;
+      float* cp = j == 0 ? copy0 : copy1;
+      if (cp) cp[c] = (float)s;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ upsample/average backward
@@ -347,16 +352,13 @@ extern "C" int jcm_bn_relu_bwd(const float* a, const float* dout, const float* s
   const size_t shb = kThreads * 8 * sizeof(float);
   bn_relu_bwd_kernel<0><<<blocks, kThreads, shb, st>>>(p);
   JCM_LAUNCH_CHECK();
-  colsum_finalize_kernel<<<jcm_cdiv(2 * C, 128), 128, 0, st>>>(part0, blocks, C, 2, sums);
+  colsum_finalize_kernel<<<jcm_cdiv(C, 32), dim3(32, kPartY), 0, st>>>(part0, blocks, C, 2, sums, dbeta, dgamma);   // dbeta = sum dy, dgamma = sum dy * xhat
   JCM_LAUNCH_CHECK();
   p.partial = part1;
   bn_relu_bwd_kernel<1><<<blocks, kThreads, shb, st>>>(p);
   JCM_LAUNCH_CHECK();
-  colsum_finalize_kernel<<<jcm_cdiv(C, 128), 128, 0, st>>>(part1, blocks, C, 1, dbias);
+  colsum_finalize_kernel<<<jcm_cdiv(C, 32), dim3(32, kPartY), 0, st>>>(part1, blocks, C, 1, dbias, nullptr, nullptr);
   JCM_LAUNCH_CHECK();
-  // dbeta = sum dy, dgamma = sum dy * xhat
-  JCM_CUDA(cudaMemcpyAsync(dbeta, sums, C * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  JCM_CUDA(cudaMemcpyAsync(dgamma, sums + C, C * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return JCM_OK;
 }
 

@@ -75,3 +75,20 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
+
+// Deterministic column sum of per-block partials laid out [nblocks][2][C]: call from a (32, kPartY) thread block; thread
+// (tx, ty) adds blocks ty, ty + kPartY, ... of column c, the kPartY lanes are then added in order.  Valid in ty == 0.
+constexpr int kPartY = 16;
+__device__ __forceinline__ double partial_colsum(const float* __restrict__ partial, int nblocks, int C, int j, int c,
+                                                 double (*sh)[33]) {
+  double s = 0.0;
+  if (c < C)
+    for (int b = threadIdx.y; b < nblocks; b += kPartY) s += (double)partial[((long)b * 2 + j) * C + c];
+  __syncthreads();
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.y == 0)
+    for (int l = 0; l < kPartY; ++l) t += sh[l][threadIdx.x];
+  return t;
+}

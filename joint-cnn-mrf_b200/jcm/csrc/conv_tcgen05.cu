@@ -638,13 +638,22 @@ void plan_wgrad(int B, int H, int W, int Cin, int Gc, int ksize, WgradPlan* pl) 
   pl->tiles_x = jcm_cdiv(W, pl->TW);
   pl->tiles_y = jcm_cdiv(H, pl->TH);
   pl->total_patches = B * pl->tiles_x * pl->tiles_y;
-  // enough independent work items for ~4 waves of the persistent grid, each with at least 8 patches to amortise the epilogue
+  // k-split: the persistent grid runs ceil(tasks / SMs) waves of tasks that each stream total_patches / splits k-blocks (+ an
+  // epilogue worth ~6 k-blocks).  Pick the split count that minimises waves x task length: e.g. conv5 (648 tasks = 4.4 waves)
+  // wastes 12 % of the last wave unsplit, 0.5 % with 5 splits; the partial sums cost one extra read in wgrad_reduce_kernel.
   const int base = ksize * ksize * pl->m_tiles * pl->n_tiles;
-  int s = jcm_cdiv(4 * jcm_num_sms(), base);
-  if (s > pl->total_patches / 8) s = pl->total_patches / 8;
-  if (s < 1) s = 1;
-  if (s > 64) s = 64;
-  pl->splits = s;
+  const int sms = jcm_num_sms();
+  int best_s = 1;
+  double best_cost = 1e300;
+  for (int s = 1; s <= 64; ++s) {
+    if (s > 1 && s > pl->total_patches / 8) break;
+    const double waves = (double)jcm_cdiv(base * s, sms);
+    // + the reduction pass over s partial copies (HBM-bound), in units of one k-block (~0.5 us)
+    const double reduce = (double)s * ksize * ksize * pl->m_pad * pl->n_pad * 4.0 / 6.4e12 / 0.5e-6;
+    const double cost = waves * (jcm_cdiv(pl->total_patches, s) + 6.0) + reduce;
+    if (cost < best_cost * 0.999) { best_cost = cost; best_s = s; }
+  }
+  pl->splits = best_s;
 }
 
 }  // namespace

@@ -67,15 +67,16 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblock
                                    const float* __restrict__ beta, float* __restrict__ moving_mean, float* __restrict__ moving_var,
                                    float eps, float decay, int train, int update_moving, float* __restrict__ scale,
                                    float* __restrict__ shift, float* __restrict__ save_mean, float* __restrict__ save_rstd) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  __shared__ double sh[kPartY][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s = 0.0, q = 0.0;
+  if (train) {
+    s = partial_colsum(partial, nblocks, C, 0, c, sh);
+    q = partial_colsum(partial, nblocks, C, 1, c, sh);
+  }
+  if (threadIdx.y != 0 || c >= C) return;
   double mean, var;
   if (train) {
-    double s = 0.0, q = 0.0;
-    for (int b = 0; b < nblocks; ++b) {
-      s += (double)partial[((long)b * 2 + 0) * C + c];
-      q += (double)partial[((long)b * 2 + 1) * C + c];
-    }
     mean = s / (double)M;
     var = q / (double)M - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -333,11 +334,10 @@ extern "C" int jcm_bn_stats(const float* x, long M, int C, float* partial, void*
 
 namespace {
 __global__ void colsum_from_partial_kernel(const float* __restrict__ partial, int nblocks, int C, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += (double)partial[((long)b * 2 + 0) * C + c];
-  out[c] = (float)s;
+  __shared__ double sh[kPartY][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const double s = partial_colsum(partial, nblocks, C, 0, c, sh);
+  if (threadIdx.y == 0 && c < C) out[c] = (float)s;
 }
 }  // namespace
 
@@ -345,7 +345,7 @@ __global__ void colsum_from_partial_kernel(const float* __restrict__ partial, in
 extern "C" int jcm_colsum(const float* x, long M, int C, float* partial, float* out, void* stream) {
   int rc = jcm_bn_stats(x, M, C, partial, stream);
   if (rc) return rc;
-  colsum_from_partial_kernel<<<jcm_cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(partial, jcm_bn_stats_blocks(M, C), C, out);
+  colsum_from_partial_kernel<<<jcm_cdiv(C, 32), dim3(32, kPartY), 0, (cudaStream_t)stream>>>(partial, jcm_bn_stats_blocks(M, C), C, out);
   JCM_LAUNCH_CHECK();
   return JCM_OK;
 }
@@ -356,7 +356,7 @@ extern "C" int jcm_bn_finalize(const float* partial, long M, int C, const float*
   JCM_CHECK_ARG(gamma && beta && moving_mean && moving_var && scale && shift, "jcm_bn_finalize: null pointer");
   JCM_CHECK_ARG(!train || partial, "jcm_bn_finalize: training mode needs the partial sums");
   const int nblocks = train ? jcm_bn_stats_blocks(M, C) : 0;
-  bn_finalize_kernel<<<jcm_cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(partial, nblocks, M, C, gamma, beta, moving_mean, moving_var, eps,
+  bn_finalize_kernel<<<jcm_cdiv(C, 32), dim3(32, kPartY), 0, (cudaStream_t)stream>>>(partial, nblocks, M, C, gamma, beta, moving_mean, moving_var, eps,
                                                                          decay, train, update_moving, scale, shift, save_mean, save_rstd);
   JCM_LAUNCH_CHECK();
   return JCM_OK;

@@ -47,6 +47,8 @@ class Context:
             return ent[2]
         if kind == 's2d':
             p = ops.pack_weights_s2d(w, self.split)
+        elif kind in ('taps', 'taps_dgrad'):
+            p = ops.pack_weights_taps(w, self.split, transpose=(kind == 'taps_dgrad'))
         else:
             p = ops.pack_weights(w, self.split, transpose=(kind == 'dgrad'))
         self._wcache[key] = (w.data_ptr(), w._version, p)
@@ -243,7 +245,7 @@ def model(x, n_joints, p, ctx, tap=None):
     a, ss = layer(merged, 'conv5', 9)
     h = ops.bn_apply_pool(a, ss, False, split)
     w6 = p['conv6/weights']
-    return ops.conv2d_planes(h, ctx.packed('conv6', w6), p['conv6/biases'], w6.shape[3], 9, relu=False)
+    return ops.conv2d_taps(h, ctx.packed('conv6', w6, 'taps'), p['conv6/biases'], w6.shape[3], 9)
 
 
 # ----------------------------------------------------------------------------------------------------------

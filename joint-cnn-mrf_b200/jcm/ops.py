@@ -147,6 +147,60 @@ def conv2d_planes(xp, wp, bias, cout, ksize, relu, naive=False, alg_kdim=None):
     return y
 
 
+# ---- tap-expanded path for convolutions with very few output channels (conv6; csrc/taps.cu explains the re-association)
+def tap_layout(ksize, cout):
+    """(KP, ZC, Npad): channels per tap (cout padded to 4), used Z channels k*k*KP, and the GEMM N extent (16-/256-padded)."""
+    kp = (cout + 3) // 4 * 4
+    zc = ksize * ksize * kp
+    npad = pad16(zc) if zc <= 256 else (zc + 255) // 256 * 256
+    return kp, zc, npad
+
+
+def pack_weights_taps(w, split, transpose=False):
+    """HWIO fp32 [k,k,Cin,Cout] -> planes [1, Npad, Cin] (forward) or [1, Cin, Npad] (data gradient), rows n = tap*KP + co."""
+    _req(w, F32, 'w')
+    k, k2, cin, cout = w.shape
+    if k != k2 or cin % 16:
+        raise ValueError('pack_weights_taps expects square kernels and Cin a multiple of 16')
+    kp, zc, npad = tap_layout(k, cout)
+    out = _new_planes((1, cin, npad) if transpose else (1, npad, cin), w.device, split)
+    check(lib().jcm_pack_weights_taps(_ptr(w), k, cin, cout, kp, npad, int(transpose), _ptr(out.hi), _ptr(out.lo), _stream()),
+          'jcm_pack_weights_taps')
+    return out
+
+
+def conv2d_taps(xp, wz, bias, cout, ksize):
+    """[B,H,W,Cin] planes (*) [k,k,Cin,cout] (+ bias), SAME, stride 1, for small cout: 1x1 tcgen05 GEMM to Z [B,H,W,k*k*KP], then
+    the tap gather.  Same result as conv2d_planes(..., relu=False) on the directly packed weights."""
+    B, H, W, cin = xp.shape
+    kp, zc, npad = tap_layout(ksize, cout)
+    if tuple(wz.shape) != (1, npad, cin):
+        raise ValueError('tap-packed weight planes %s do not match (1, %d, %d)' % (wz.shape, npad, cin))
+    z = conv2d_planes(xp, wz, None, zc, 1, relu=False, alg_kdim=ksize * ksize * cin * cout / zc)
+    if bias is not None:
+        _req(bias, F32, 'bias')
+    y = torch.empty((B, H, W, cout), dtype=F32, device=z.device)
+    check(lib().jcm_tap_gather(_ptr(z), _ptr(bias), B, H, W, ksize, kp, zc, cout, _ptr(y), _stream()), 'jcm_tap_gather')
+    return y
+
+
+def tap_scatter_planes(g, ksize, split):
+    """g fp32 [B,H,W,cout] (gradient w.r.t. the conv output) -> planes Gt [B,H,W,Npad], Gt[q, tap*KP+co] = g[q-(tap-pad), co]."""
+    _req(g, F32, 'g')
+    B, H, W, cout = g.shape
+    kp, zc, npad = tap_layout(ksize, cout)
+    out = _new_planes((B, H, W, npad), g.device, split)
+    check(lib().jcm_tap_scatter_planes(_ptr(g), B, H, W, ksize, cout, kp, npad, _ptr(out.hi), _ptr(out.lo), _stream()),
+          'jcm_tap_scatter_planes')
+    return out
+
+
+def unpack_tap_grad(dwz, ksize, cin, cout, dw):
+    kp, zc, npad = tap_layout(ksize, cout)
+    check(lib().jcm_unpack_tap_grad(_ptr(dwz), ksize, cin, cout, kp, zc, _ptr(dw), _stream()), 'jcm_unpack_tap_grad')
+    return dw
+
+
 def bn_scale_shift(a, gamma, beta, moving_mean, moving_var, train, update_moving=True, save=False):
     """Per-channel (scale, shift) of tf.contrib.layers.batch_norm for a [.., C] fp32 tensor (batch stats if train)."""
     _req(a, F32, 'a')

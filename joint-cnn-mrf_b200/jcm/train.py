@@ -212,7 +212,7 @@ class Trainer:
         a5, ss5 = fwd_layer(merged, 'conv5', 9)
         h5 = ops.bn_apply_pool(a5, ss5, False, split)
         w6 = p['conv6/weights']
-        logit_pd = ops.conv2d_planes(h5, ctx.packed('conv6', w6), p['conv6/biases'], K, 9, relu=False, alg_kdim=81 * w6.shape[2])
+        logit_pd = ops.conv2d_taps(h5, ctx.packed('conv6', w6, 'taps'), p['conv6/biases'], K, 9)
         hm_pd = ops.spatial_softmax(logit_pd)
         loss_pd, _, lse_pd = ops.softmax_ce(logit_pd, y, want_lse=True)
         inv_bk = 1.0 / (B * K)
@@ -231,10 +231,15 @@ class Trainer:
             d_logit.mul_(2.0)   # loss_sm == loss_pd when the spatial model is off (main.py:533-536)
 
         # ---- part-detector backward
-        gp6 = pad_planes(d_logit, ops.pad16(K), split)
-        conv2d_wgrad(h5, gp6, g['conv6/weights'].view(81, w6.shape[2], K), K, 9)
+        # conv6 in its tap-expanded form (csrc/taps.cu): one scatter of the K-channel gradient, then two 1x1 GEMMs
+        c5 = w6.shape[2]
+        kp, zc, npad = ops.tap_layout(9, K)
+        gt6 = ops.tap_scatter_planes(d_logit, 9, split)
+        dwz = torch.empty((1, c5, zc), dtype=F32, device=dev)
+        conv2d_wgrad(h5, gt6, dwz, zc, 1)
+        ops.unpack_tap_grad(dwz, 9, c5, K, g['conv6/weights'])
         colsum(d_logit, g['conv6/biases'])
-        dh = ops.conv2d_planes(gp6, ctx.packed('conv6', w6, 'dgrad'), None, w6.shape[2], 9, relu=False)
+        dh = ops.conv2d_planes(gt6, ctx.packed('conv6', w6, 'taps_dgrad'), None, c5, 1, relu=False, alg_kdim=81 * K)
 
         def bwd_layer(name, dout, dy_scale, pool, ksize, need_dx):
             xp, a, ss, st = saved.pop(name)

@@ -162,6 +162,36 @@ def test_conv2d_wgrad_and_dgrad(jcm, jtrain, case, split):
         assert rel(dx, x64.grad) < 2e-4
 
 
+@pytest.mark.parametrize('case', [(2, 12, 20, 64, 7, 9), (1, 60, 90, 128, 7, 9), (3, 9, 7, 32, 14, 5), (1, 15, 23, 512, 9, 9)])
+@pytest.mark.parametrize('split', [False, True])
+def test_conv_taps_forward_wgrad_dgrad(jcm, jtrain, case, split):
+    """The tap-expanded form used for conv6 (few output channels): forward, weight gradient and data gradient vs the oracle."""
+    B, H, W, Cin, Cout, k = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x = torch.randn(B, H, W, Cin, generator=g)
+    w = torch.randn(k, k, Cin, Cout, generator=g) / math.sqrt(k * k * Cin)
+    b = torch.randn(Cout, generator=g)
+    dy = torch.randn(B, H, W, Cout, generator=g)
+    xr, wr, dyr = (x, w, dy) if split else (bf16r(x), bf16r(w), bf16r(dy))
+    x64 = xr.double().requires_grad_(True)
+    w64 = wr.double().requires_grad_(True)
+    y64 = orc.conv2d(x64, w64, 1) + b.double()
+    (y64 * dyr.double()).sum().backward()
+
+    xp = jcm.ops.split_planes(x.cuda(), split)
+    y = jcm.ops.conv2d_taps(xp, jcm.ops.pack_weights_taps(w.cuda(), split), b.cuda(), Cout, k)
+    assert rel(y, y64) < 2e-4
+    kp, zc, npad = jcm.ops.tap_layout(k, Cout)
+    gt = jcm.ops.tap_scatter_planes(dy.cuda(), k, split)
+    dwz = torch.empty(1, Cin, zc, device='cuda')
+    jtrain.conv2d_wgrad(xp, gt, dwz, zc, 1)
+    dw = torch.empty(k, k, Cin, Cout, device='cuda')
+    jcm.ops.unpack_tap_grad(dwz, k, Cin, Cout, dw)
+    assert rel(dw, w64.grad) < 2e-4
+    dx = jcm.ops.conv2d_planes(gt, jcm.ops.pack_weights_taps(w.cuda(), split, transpose=True), None, Cin, 1, relu=False)
+    assert rel(dx, x64.grad) < 2e-4
+
+
 @pytest.mark.parametrize('split', [False, True])
 def test_conv1_stride2_wgrad_via_space_to_depth(jcm, jtrain, split):
     g = torch.Generator().manual_seed(15)
