@@ -64,6 +64,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* map, uint3
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -482,10 +488,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_m_hi, const __grid_con
         const int dy = tap / p.ksize - p.pad, dx = tap % p.ksize - p.pad;
         const int p0 = (int)((long)split * p.total_patches / p.splits);
         const int p1 = (int)((long)(split + 1) * p.total_patches / p.splits);
+        int img = p0 / patches_per_img;
+        int q = p0 - img * patches_per_img;
+        int ty = q / p.tiles_x, tx = q - ty * p.tiles_x;
+        const int mblk0 = mt * m_boxes, nblk0 = nt * n_boxes;   // first channel block (of kc_m / kc_n channels) of this tile
+        const int sdx_m = p.shift_m * dx, sdy_m = p.shift_m * dy, sdx_n = p.shift_n * dx, sdy_n = p.shift_n * dy;
         for (int patch = p0; patch < p1; ++patch) {
-          const int img = patch / patches_per_img;
-          const int q = patch - img * patches_per_img;
-          const int ty = q / p.tiles_x, tx = q - ty * p.tiles_x;
           const int x0 = tx * p.TW, y0 = ty * p.TH;
           for (int term = 0; term < p.terms; ++term) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -495,11 +503,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_m_hi, const __grid_con
             mbar_expect_tx(fb, p.a_bytes + p.b_bytes);
             const void* mm = (term == 1) ? (const void*)&map_m_lo : (const void*)&map_m_hi;
             const void* mn = (term == 2) ? (const void*)&map_n_lo : (const void*)&map_n_hi;
-            for (int b = 0; b < m_boxes; ++b)
-              tma_load_4d(sa + b * m_box_bytes, mm, fb, mt * kTileM + b * p.kc_m, x0 + p.shift_m * dx, y0 + p.shift_m * dy, img);
-            for (int b = 0; b < n_boxes; ++b)
-              tma_load_4d(sb + b * n_box_bytes, mn, fb, nt * p.block_n + b * p.kc_n, x0 + p.shift_n * dx, y0 + p.shift_n * dy, img);
+            // one 5-D box per operand: {kc channels, TW, TH, 1 image, all channel blocks of the tile}
+            tma_load_5d(sa, mm, fb, 0, x0 + sdx_m, y0 + sdy_m, img, mblk0);
+            tma_load_5d(sb, mn, fb, 0, x0 + sdx_n, y0 + sdy_n, img, nblk0);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          if (++tx == p.tiles_x) {
+            tx = 0;
+            if (++ty == p.tiles_y) { ty = 0; ++img; }
           }
         }
       }
@@ -704,27 +715,28 @@ extern "C" int jcm_conv2d_wgrad(const void* x_hi, const void* x_lo, const void* 
   const void* n_hi = pl.x_is_m ? g_hi : x_hi;
   const void* n_lo = pl.x_is_m ? g_lo : x_lo;
   const int m_c = pl.x_is_m ? Cin : Gc, n_c = pl.x_is_m ? Gc : Cin;
+  // 5-D views {kc channels, W, H, B, C / kc channel blocks}: one TMA box {kc, TW, TH, 1, blocks per tile} lands in shared memory as
+  // [block][TH][TW][kc] = per channel block a [64 pixels][kc] MN-major UMMA operand.  Blocks past the tensor's channel extent
+  // (M tile of 128 over a 64-channel tensor) are zero-filled by TMA, which pads M.
   CUtensorMap mm_hi, mm_lo, mn_hi, mn_lo;
   {
-    uint64_t dims[4] = {(uint64_t)m_c, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    uint64_t str[3] = {(uint64_t)m_c * 2, (uint64_t)W * m_c * 2, (uint64_t)H * W * m_c * 2};
-    // channels per box: 64 (SWIZZLE_128B) when the count allows, else 32 / 16 with the narrower swizzle; boxes past the
-    // tensor's channel extent are zero-filled by TMA, which pads M to 128
-    uint32_t box[4] = {(uint32_t)pl.kc_m, (uint32_t)pl.TW, (uint32_t)pl.TH, 1};
+    uint64_t dims[5] = {(uint64_t)pl.kc_m, (uint64_t)W, (uint64_t)H, (uint64_t)B, (uint64_t)(m_c / pl.kc_m)};
+    uint64_t str[4] = {(uint64_t)m_c * 2, (uint64_t)W * m_c * 2, (uint64_t)H * W * m_c * 2, (uint64_t)pl.kc_m * 2};
+    uint32_t box[5] = {(uint32_t)pl.kc_m, (uint32_t)pl.TW, (uint32_t)pl.TH, 1, (uint32_t)(kTileM / pl.kc_m)};
     const CUtensorMapSwizzle swz = pl.kc_m == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (pl.kc_m == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-    int rc = make_map(&mm_hi, m_hi, 4, dims, str, box, swz);
+    int rc = make_map(&mm_hi, m_hi, 5, dims, str, box, swz);
     if (rc) return rc;
-    rc = make_map(&mm_lo, m_lo ? m_lo : m_hi, 4, dims, str, box, swz);
+    rc = make_map(&mm_lo, m_lo ? m_lo : m_hi, 5, dims, str, box, swz);
     if (rc) return rc;
   }
   {
-    uint64_t dims[4] = {(uint64_t)n_c, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    uint64_t str[3] = {(uint64_t)n_c * 2, (uint64_t)W * n_c * 2, (uint64_t)H * W * n_c * 2};
-    uint32_t box[4] = {(uint32_t)pl.kc_n, (uint32_t)pl.TW, (uint32_t)pl.TH, 1};
+    uint64_t dims[5] = {(uint64_t)pl.kc_n, (uint64_t)W, (uint64_t)H, (uint64_t)B, (uint64_t)(n_c / pl.kc_n)};
+    uint64_t str[4] = {(uint64_t)n_c * 2, (uint64_t)W * n_c * 2, (uint64_t)H * W * n_c * 2, (uint64_t)pl.kc_n * 2};
+    uint32_t box[5] = {(uint32_t)pl.kc_n, (uint32_t)pl.TW, (uint32_t)pl.TH, 1, (uint32_t)(pl.block_n / pl.kc_n)};
     const CUtensorMapSwizzle swz = pl.kc_n == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (pl.kc_n == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-    int rc = make_map(&mn_hi, n_hi, 4, dims, str, box, swz);
+    int rc = make_map(&mn_hi, n_hi, 5, dims, str, box, swz);
     if (rc) return rc;
-    rc = make_map(&mn_lo, n_lo ? n_lo : n_hi, 4, dims, str, box, swz);
+    rc = make_map(&mn_lo, n_lo ? n_lo : n_hi, 5, dims, str, box, swz);
     if (rc) return rc;
   }
   const int total_tasks = p.splits * p.taps * p.m_tiles * p.n_tiles;

@@ -410,6 +410,23 @@ def sec_step():
             k, relerr(graw[k], g0), relerr(tr.p[k], new), float((lr * scale * gfull).abs().max()), float(new.abs().max())))
 
 
+def sec_wgtime():
+    """Weight-gradient / forward kernel timings on the dominant layers (bf16 operands)."""
+    from jcm import train as jtrain
+    gen = torch.Generator().manual_seed(6)
+    for (B, H, W, Cin, Cout, k, name) in [(32, 60, 90, 512, 512, 9, 'conv5'), (32, 60, 90, 256, 512, 9, 'conv4_fullres'),
+                                          (32, 120, 180, 64, 128, 5, 'conv2_fullres'), (32, 240, 360, 16, 64, 3, 'conv1_fullres(s2d)'),
+                                          (32, 30, 45, 256, 512, 9, 'conv4_halfres')]:
+        x = ops.split_planes(torch.randn(B, H, W, Cin, generator=gen).to(dev), False)
+        g = ops.split_planes(torch.randn(B, H, W, Cout, generator=gen).to(dev), False)
+        w = ops.pack_weights((torch.randn(k, k, Cin, Cout, generator=gen) / 30).to(dev), False)
+        dw = torch.empty(k * k, Cin, Cout, device=dev)
+        fl = 2.0 * B * H * W * k * k * Cin * Cout
+        bw, _ = timeit(lambda: jtrain.conv2d_wgrad(x, g, dw, Cout, k), n=3, warm=1)
+        bf, _ = timeit(lambda: ops.conv2d_planes(x, w, None, Cout, k, False), n=3, warm=1)
+        print('WGTIME %-20s B=%d: wgrad %.3f ms %.0f TFLOP/s | fwd %.3f ms %.0f TFLOP/s' % (name, B, bw, fl / bw / 1e9, bf, fl / bf / 1e9))
+
+
 def sec_smtime():
     K = 7
     names = jcm.JOINT_NAMES[:K] + ['torso']
