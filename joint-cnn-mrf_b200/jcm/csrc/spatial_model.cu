@@ -524,111 +524,178 @@ __global__ void sm_bwd_dc_kernel(const float* __restrict__ dT, SmDims dm, float*
 }
 
 // ---------------------------------------------------------------------------------------------- dP (prior gradient)
-// dP[a][b] = sum_n sum_{y,x} dC[n][y][x] * Ltf[n][a-y][b-x]   (Ltf = the flipped, image-interleaved likelihood of the forward pass)
-// One warp owns output rows a and a+H (their y ranges [0,a] and [a+1,H] are complementary, so every warp does exactly H+1
-// row passes), each lane a strip of 6 columns; the two images of a pair ride in the two halves of an FFMA2.
-constexpr int DPW = 20;   // warps per CTA = output row pairs per CTA
-constexpr int TXP = 6;    // strip width
+// dP[a][b] = sum_n sum_{y<=H, x<=W} dC[n][y][x] * Ltf[n][a-y][b-x]      a in [0,2H), b in [0,2W)      (full correlation, reduced over n)
+// with Ltf = the flipped likelihood of the forward pass.  Every one of the (H+1)(W+1)HW products per image is needed exactly
+// once; a gather over zero-padded operands would do 4x that.  The mapping below does the exact work (+ padding to 32 / 12):
+//
+//   * rows:    lane <-> output rows (a, a + Hm), Hm = 32*ceil(H/32).  For a fixed dC row y (warp-uniform, broadcast loads) the lane
+//              reads likelihood row u = (a - y) mod Hm: y <= a contributes to row a, y > a to row a + Hm - so ONE accumulator set
+//              serves both rows; it is flushed to the partial output once when y passes a (and once at the end).
+//   * columns: warp <-> strip pair (b0 .. b0+11, b0+Wm .. b0+Wm+11), Wm = 12*ceil((W+1)/12), b0 = 12*strip.  x runs over Wm/12
+//              blocks of 12; column b0+k at step x reads likelihood column (b0+k-x) mod Wm: x <= b0+k goes to the low strip, else to
+//              the high one.  Because b0 is a multiple of the block size this is decided per BLOCK (all-low / mixed / all-high),
+//              so the inner loop is branch free: one per-lane LDS.64 (new window element) + one broadcast LDS.64 (dC) per 12 FFMA2.
+//   * the two halves of every FFMA2 are two images (their sum is taken at the flush); a CTA = (pair, chunk of image pairs) runs all
+//     strips x row groups as warps, streams its image pairs through a cp.async double buffer and adds into its own partial
+//     output [2Hm][2Wm] (each element is owned by exactly one lane: plain read-modify-write, deterministic).
+//   * sm_bwd_dp_finish_kernel: dE = sigmoid(5E) * sum over chunks.
+constexpr int TXD = 12;        // strip width
+constexpr int DP_MAXW = 16;    // warps per CTA (strips x row groups are looped over when there are more)
 
 struct DpDims {
-  int B, H, W, P, G, Hp_l, Wp_l, Hp_c, Wp_c;   // padded extents of Lt ([Hp_l][Wp_l]) and dCs ([Hp_c][Wp_c])
-  int lunits;                                   // float2 units per skewed likelihood row
-  int chunks;                                   // ceil(H / DPW)
+  int B, H, W, P, G;
+  int Hp_l, Wp_l, Hp_c, Wp_c;     // padded extents of Lt ([Hp_l][Wp_l][4]) and dCs ([Hp_c][Wp_c][4])
+  int Hm, Wm, NB, RG;             // row / column moduli, column blocks (= strips), row groups
+  int LS;                         // likelihood row stride in float2 units (odd; TXD-1 wrap-around halo in front)
+  int npairs, nchunks, nbuf;      // image pairs (2 images each), chunks of image pairs (grid.y), shared-memory buffers (1 or 2)
+  int lbuf, cbuf;                 // float2 units per likelihood / dC buffer
 };
 
 __device__ __forceinline__ void ffma2p(unsigned long long& d, unsigned long long a, unsigned long long b) {
   asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
 }
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
 
-// accumulates rows y in [y_begin, y_end) of dC against likelihood rows u = a_row - y
-__device__ __forceinline__ void dp_rows(unsigned long long (&acc)[TXP], const unsigned long long* __restrict__ Lsk,
-                                        const unsigned long long* __restrict__ Cs, int a_row, int y_begin, int y_end, int lane,
-                                        const DpDims& d, int h) {
-  const int W = d.W;
-#pragma unroll 1
-  for (int y = y_begin; y < y_end; ++y) {
-    const int u = a_row - y;
-    const unsigned long long* lrow = Lsk + ((long)h * d.Hp_l + u) * d.lunits;
-    const unsigned long long* crow = Cs + ((long)y * d.Wp_c) * 2 + h;
-    unsigned long long win[TXP];
-    // initial window: columns b0 + k, k = 1..5, at x = 0 (slot k)
+// one block of TXD x-steps.  MODE 0: every column accumulates into lo; 2: into hi; 1: column k into lo iff step <= k.
+// lcol points at likelihood column cbase of the lane's row (physical index, halo included); crow at dC[y][xb*TXD].
+template <int MODE>
+__device__ __forceinline__ void dp_block(unsigned long long (&lo)[TXD], unsigned long long (&hi)[TXD], unsigned long long (&win)[TXD],
+                                         const unsigned long long* __restrict__ lcol, const unsigned long long* __restrict__ crow) {
 #pragma unroll
-    for (int k = 1; k < TXP; ++k) {
-      const int c = TXP * lane + k;
-      win[k] = (c < W) ? lrow[7 * lane + k] : 0ull;
-    }
-#pragma unroll 1
-    for (int xb = 0; xb * TXP <= W; ++xb) {
-      const int q = lane - xb;
+  for (int s = 0; s < TXD; ++s) {
+    win[(TXD - s) % TXD] = lcol[-s];
+    const unsigned long long cv = crow[s];
 #pragma unroll
-      for (int s = 0; s < TXP; ++s) {
-        const int x = xb * TXP + s;
-        if (x <= W) {   // warp-uniform
-          const int c = TXP * q - s;
-          const int unit = 7 * q - (s == 0 ? 0 : s + 1);
-          win[(TXP - s) % TXP] = (c >= 0 && c < W) ? lrow[unit] : 0ull;
-          const unsigned long long cv = crow[(long)x * 2];
-#pragma unroll
-          for (int k = 0; k < TXP; ++k) ffma2p(acc[k], win[(k - s + TXP) % TXP], cv);
-        }
-      }
+    for (int k = 0; k < TXD; ++k) {
+      const bool to_lo = MODE == 0 || (MODE == 1 && s <= k);
+      if (to_lo) ffma2p(lo[k], win[(k - s + TXD) % TXD], cv);
+      else ffma2p(hi[k], win[(k - s + TXD) % TXD], cv);
     }
   }
 }
 
-__global__ void __launch_bounds__(DPW * 32, 1)
-sm_bwd_dp_kernel(const float* __restrict__ Lt, const float* __restrict__ dCs, const float* __restrict__ energies,
-                 const int* __restrict__ pair_cond, DpDims d, float* __restrict__ dE) {
+__global__ void __launch_bounds__(DP_MAXW * 32, 1)
+sm_bwd_dp_kernel(const float* __restrict__ Lt, const float* __restrict__ dCs, const int* __restrict__ pair_cond, DpDims d,
+                 float* __restrict__ partial /*[P][nchunks][2Hm][2Wm]*/) {
   extern __shared__ __align__(16) unsigned long long dsm[];
-  unsigned long long* Lsk = dsm;                                       // [2 pairs][Hp_l][lunits] skewed float2
-  unsigned long long* Cs = dsm + (size_t)2 * d.Hp_l * d.lunits;         // [H+1][Wp_c][2 pairs] float2
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int p = blockIdx.x / d.chunks, chunk = blockIdx.x % d.chunks;
+  unsigned long long* Lsm = dsm;                               // [nbuf][Hm][LS]
+  unsigned long long* Csm = dsm + (size_t)d.nbuf * d.lbuf;      // [nbuf][H+1][Wm]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int p = blockIdx.x, chunk = blockIdx.y;
   const int j = pair_cond[p];
-  const int a = chunk * DPW + warp;
-  const bool active = a < d.H;
-  unsigned long long accA[TXP], accB[TXP];
-#pragma unroll
-  for (int k = 0; k < TXP; ++k) { accA[k] = 0ull; accB[k] = 0ull; }
+  const int ip0 = (int)((long)chunk * d.npairs / d.nchunks), ip1 = (int)((long)(chunk + 1) * d.npairs / d.nchunks);
+  float* out = partial + ((long)p * d.nchunks + chunk) * (2 * d.Hm) * (2 * d.Wm);
+  const int HALO = TXD - 1;
 
-  for (int gi = 0; gi < d.G; ++gi) {
-    __syncthreads();
-    // stage the likelihood (skewed: unit(v) = v + v/6 so that a warp's strips hit distinct banks) and dC of this image group
-    const float4* lsrc = reinterpret_cast<const float4*>(Lt) + ((long)j * d.G + gi) * d.Hp_l * d.Wp_l;
-    for (int idx = threadIdx.x; idx < d.Hp_l * d.Wp_l; idx += blockDim.x) {
-      const int u = idx / d.Wp_l, v = idx - u * d.Wp_l;
-      const float4 q4 = lsrc[idx];
-      const int unit = v + v / TXP;
-      Lsk[((long)0 * d.Hp_l + u) * d.lunits + unit] = pack2(q4.x, q4.y);
-      Lsk[((long)1 * d.Hp_l + u) * d.lunits + unit] = pack2(q4.z, q4.w);
+  // zero everything once: the padding (rows >= H, columns >= W of the likelihood, columns > W of dC) is never written again
+  for (int i = threadIdx.x; i < d.nbuf * (d.lbuf + d.cbuf); i += blockDim.x) dsm[i] = 0ull;
+  __syncthreads();
+
+  auto stage = [&](int ip, int buf) {
+    const int g = ip >> 1, h = ip & 1;
+    const float* lsrc = Lt + (((long)j * d.G + g) * d.Hp_l * d.Wp_l) * 4 + 2 * h;
+    unsigned long long* ldst = Lsm + (size_t)buf * d.lbuf;
+    for (int i = threadIdx.x; i < d.H * d.W; i += blockDim.x) {
+      const int u = i / d.W, v = i - u * d.W;
+      cp_async8(smem_u32(ldst + u * d.LS + HALO + v), lsrc + ((long)u * d.Wp_l + v) * 4);
+      if (v >= d.Wm - HALO) cp_async8(smem_u32(ldst + u * d.LS + v - (d.Wm - HALO)), lsrc + ((long)u * d.Wp_l + v) * 4);   // wrap-around halo
     }
-    const float4* csrc = reinterpret_cast<const float4*>(dCs) + ((long)p * d.G + gi) * d.Hp_c * d.Wp_c;
-    float4* cdst = reinterpret_cast<float4*>(Cs);
-    for (int idx = threadIdx.x; idx < (d.H + 1) * d.Wp_c; idx += blockDim.x) cdst[idx] = csrc[idx];
-    __syncthreads();
-    if (active) {
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        dp_rows(accA, Lsk, Cs, a, 0, a + 1, lane, d, h);               // output row a:     y in [0, a]
-        dp_rows(accB, Lsk, Cs, a + d.H, a + 1, d.H + 1, lane, d, h);   // output row a + H: y in [a+1, H]
-      }
+    const float* csrc = dCs + (((long)p * d.G + g) * d.Hp_c * d.Wp_c) * 4 + 2 * h;
+    unsigned long long* cdst = Csm + (size_t)buf * d.cbuf;
+    for (int i = threadIdx.x; i < (d.H + 1) * (d.W + 1); i += blockDim.x) {
+      const int y = i / (d.W + 1), x = i - y * (d.W + 1);
+      cp_async8(smem_u32(cdst + y * d.Wm + x), csrc + ((long)y * d.Wp_c + x) * 4);
     }
-  }
-  if (active) {
+    cp_async_commit();
+  };
+
+  if (ip0 < ip1) stage(ip0, 0);
+  for (int ip = ip0; ip < ip1; ++ip) {
+    const int buf = d.nbuf == 2 ? ((ip - ip0) & 1) : 0;
+    if (d.nbuf == 2 && ip + 1 < ip1) {
+      stage(ip + 1, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const unsigned long long* Lb = Lsm + (size_t)buf * d.lbuf + HALO;
+    const unsigned long long* Cb = Csm + (size_t)buf * d.cbuf;
+    for (int wt = warp; wt < d.NB * d.RG; wt += nwarps) {
+      const int strip = wt % d.NB, rg = wt / d.NB;
+      const int a = rg * 32 + lane;               // low output row; high = a + Hm
+      const int b0 = strip * TXD;
+      unsigned long long lo[TXD], hi[TXD], win[TXD];
 #pragma unroll
-    for (int k = 0; k < TXP; ++k) {
-      const int b = TXP * lane + k;
-      if (b < 2 * d.W) {
-        float s0, s1;
-        const long ia = ((long)p * 2 * d.H + a) * 2 * d.W + b;
-        const long ib = ((long)p * 2 * d.H + a + d.H) * 2 * d.W + b;
-        unpack2(accA[k], s0, s1);
-        dE[ia] = (s0 + s1) * sigmoid5(energies[ia]);
-        unpack2(accB[k], s0, s1);
-        dE[ib] = (s0 + s1) * sigmoid5(energies[ib]);
+      for (int k = 0; k < TXD; ++k) { lo[k] = 0ull; hi[k] = 0ull; }
+      auto flush = [&](int row) {
+        float* orow = out + (long)row * (2 * d.Wm) + b0;
+#pragma unroll
+        for (int k = 0; k < TXD; ++k) {
+          float s0, s1;
+          unpack2(lo[k], s0, s1);
+          orow[k] += s0 + s1;
+          unpack2(hi[k], s0, s1);
+          orow[d.Wm + k] += s0 + s1;
+          lo[k] = 0ull;
+          hi[k] = 0ull;
+        }
+      };
+#pragma unroll 1
+      for (int y = 0; y <= d.H; ++y) {
+        if (y == a + 1) flush(a);                 // rows y <= a went to output row a; from here on to row a + Hm
+        int u = a - y;
+        if (u < 0) u += d.Hm;
+        const unsigned long long* lrow = Lb + u * d.LS;
+        const unsigned long long* crow = Cb + y * d.Wm;
+#pragma unroll
+        for (int k = 1; k < TXD; ++k) win[k] = lrow[b0 + k];
+#pragma unroll 1
+        for (int xb = 0; xb < strip; ++xb) dp_block<0>(lo, hi, win, lrow + TXD * (strip - xb), crow + xb * TXD);
+        dp_block<1>(lo, hi, win, lrow, crow + strip * TXD);
+#pragma unroll 1
+        for (int xb = strip + 1; xb < d.NB; ++xb) dp_block<2>(lo, hi, win, lrow + TXD * (strip - xb + d.NB), crow + xb * TXD);
       }
+      flush(a < d.H ? a + d.Hm : a);              // a >= H never switched rows: everything it summed belongs to its low row
     }
+    __syncthreads();                              // everyone is done with `buf` before it is refilled
+    if (d.nbuf == 1 && ip + 1 < ip1) stage(ip + 1, 0);
   }
+}
+
+// dE[p][a][b] = sigmoid(5 E[p][a][b]) * sum_chunks partial[p][chunk][a][b]
+__global__ void sm_bwd_dp_finish_kernel(const float* __restrict__ partial, const float* __restrict__ energies, DpDims d, float* __restrict__ dE) {
+  const long total = (long)d.P * 2 * d.H * 2 * d.W;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int b = (int)(idx % (2 * d.W));
+    long t = idx / (2 * d.W);
+    const int a = (int)(t % (2 * d.H));
+    const int p = (int)(t / (2 * d.H));
+    float s = 0.f;
+    for (int c = 0; c < d.nchunks; ++c) s += partial[(((long)p * d.nchunks + c) * (2 * d.Hm) + a) * (2 * d.Wm) + b];
+    dE[idx] = s * sigmoid5(energies[idx]);
+  }
+}
+
+void fill_dp_dims(DpDims& dp, const SmDims& df, const SmDims& dm, int B, int H, int W, int P) {
+  dp.B = B; dp.H = H; dp.W = W; dp.P = P; dp.G = df.G;
+  dp.Hp_l = df.Hp; dp.Wp_l = df.Wp; dp.Hp_c = dm.Hp; dp.Wp_c = dm.Wp;
+  dp.Hm = jcm_cdiv(H, 32) * 32;
+  dp.RG = dp.Hm / 32;
+  dp.NB = jcm_cdiv(W + 1, TXD);
+  dp.Wm = dp.NB * TXD;
+  dp.LS = dp.Wm + TXD - 1;
+  if ((dp.LS & 1) == 0) ++dp.LS;
+  dp.npairs = 2 * df.G;
+  int nch = jcm_num_sms() / P;
+  if (nch < 1) nch = 1;
+  if (nch > dp.npairs) nch = dp.npairs;
+  dp.nchunks = nch;
+  dp.lbuf = dp.Hm * dp.LS;
+  dp.cbuf = (H + 1) * dp.Wm;
+  dp.nbuf = ((size_t)2 * (dp.lbuf + dp.cbuf) * 8 <= (size_t)227 * 1024 - 256) ? 2 : 1;
 }
 
 // dhbn[n,y,x,j] = sigmoid(5 hbn) * ( sum_{p: cond(p)=j} dLf[p][n][H-1-y][W-1-x]  +  [j<K] g[n,y,x,j] / (sp(hbn) + d) )
@@ -691,7 +758,10 @@ extern "C" long jcm_spatial_model_bwd_workspace(int B, int H, int W, int K, int 
   const long dCs = (long)P * dm.G * dm.Hp * dm.Wp * 4;
   const long dLf = (long)P * 4 * dm.G * H * W;
   const long dh = (long)B * H * W * (K + 1);
-  return (dT + dCs + dLf + dh) * (long)sizeof(float) + 64;
+  DpDims dp;
+  fill_dp_dims(dp, df, dm, B, H, W, P);
+  const long part = (long)P * dp.nchunks * (2 * dp.Hm) * (2 * dp.Wm);
+  return (dT + dCs + dLf + dh + part) * (long)sizeof(float) + 64;
 }
 
 // g = d loss / d out [B,H,W,K].  fwd_workspace = the workspace jcm_spatial_model_fwd filled for the SAME inputs.
@@ -723,12 +793,9 @@ extern "C" int jcm_spatial_model_bwd(const float* g, const float* heat_map, cons
   fill_dims(dm, B, H, W, K, P, 1);
   const size_t smem_conv = sm_smem_bytes(dm);
   DpDims dp;
-  dp.B = B; dp.H = H; dp.W = W; dp.P = P; dp.G = df.G;
-  dp.Hp_l = df.Hp; dp.Wp_l = df.Wp; dp.Hp_c = dm.Hp; dp.Wp_c = dm.Wp;
-  dp.lunits = df.Wp + df.Wp / TXP + 2;
-  dp.chunks = jcm_cdiv(H, DPW);
-  const size_t smem_dp = ((size_t)2 * dp.Hp_l * dp.lunits + (size_t)(H + 1) * dp.Wp_c * 2) * sizeof(unsigned long long);
-  if (smem_conv > 227 * 1024 || smem_dp > 227 * 1024) {
+  fill_dp_dims(dp, df, dm, B, H, W, P);
+  const size_t smem_dp = (size_t)dp.nbuf * (dp.lbuf + dp.cbuf) * sizeof(unsigned long long);
+  if (smem_conv > 227 * 1024 || smem_dp > 227 * 1024 - 256) {
     jcm_set_error("jcm_spatial_model_bwd: heat-map size %dx%d not supported by this build (shared memory %zu / %zu B)", H, W, smem_conv, smem_dp);
     return JCM_ENOTSUP;
   }
@@ -739,6 +806,7 @@ extern "C" int jcm_spatial_model_bwd(const float* g, const float* heat_map, cons
   float* dCs = dT + (long)P * 4 * df.G * H * W;
   float* dLf = dCs + (long)P * dm.G * dm.Hp * dm.Wp * 4;
   float* dh = dLf + (long)P * 4 * dm.G * H * W;
+  float* part = dh + (long)B * H * W * (K + 1);
 
   {
     const long total = (long)P * H * W;
@@ -760,7 +828,13 @@ extern "C" int jcm_spatial_model_bwd(const float* g, const float* heat_map, cons
   }
   {
     JCM_CUDA(cudaFuncSetAttribute(sm_bwd_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
-    sm_bwd_dp_kernel<<<P * dp.chunks, DPW * 32, smem_dp, st>>>(Lt, dCs, energies, pair_cond, dp, dE);
+    JCM_CUDA(cudaMemsetAsync(part, 0, (size_t)P * dp.nchunks * (2 * dp.Hm) * (2 * dp.Wm) * sizeof(float), st));
+    int nw = dp.NB * dp.RG;
+    if (nw > DP_MAXW) nw = DP_MAXW;
+    sm_bwd_dp_kernel<<<dim3(P, dp.nchunks), nw * 32, smem_dp, st>>>(Lt, dCs, pair_cond, dp, part);
+    JCM_LAUNCH_CHECK();
+    const long tot = (long)P * 4 * H * W;
+    sm_bwd_dp_finish_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(part, energies, dp, dE);
     JCM_LAUNCH_CHECK();
   }
   {
