@@ -6,3 +6,4 @@ from .graph import (Context, PairwiseParams, JOINT_NAMES, model, spatial_model, 
                     max_pool_layer, weight_variable, bias_variable, spatial_softmax, softmax_cross_entropy,
                     get_joints_coords, det_rate, get_pairwise_distr, init_part_detector, load_params, tower_forward,
                     n_filters, conv_specs)
+from . import train  # noqa: F401,E402  (Trainer: the data-parallel training step, main.py:474-577)

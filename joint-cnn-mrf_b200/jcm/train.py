@@ -268,10 +268,15 @@ class Trainer:
         return {'loss_pd': loss_pd, 'loss_sm': loss_sm, 'logit_pd': logit_pd}
 
     # ---------------------------------------------------------------------------------------- optimizer
-    def apply(self):
-        """Gradient mean over replicas (one NCCL all-reduce), weight decay, global-norm clip, Adam / Momentum."""
+    def reduce_gradients(self):
+        """The one exchange step of the path (main.py:243-267 averages tower gradients on the CPU): a single all-reduce (sum) of
+        the flat gradient buffer over NCCL / NVLink; the division by the replica count is folded into jcm_grad_prepare."""
         if self.world_size > 1:
             torch.distributed.all_reduce(self.grads, op=torch.distributed.ReduceOp.SUM)
+
+    def apply(self):
+        """Gradient mean over replicas (one NCCL all-reduce), weight decay, global-norm clip, Adam / Momentum."""
+        self.reduce_gradients()
         self.t += 1
         check(lib().jcm_grad_prepare(_ptr(self.grads), _ptr(self.flat), self.n, self.n_decay, 1.0 / self.world_size, float(self.ctx.lmbd),
                                      _ptr(self.partial), _ptr(self.stats), _stream()), 'jcm_grad_prepare')
