@@ -36,7 +36,8 @@ struct SmDims {
   int G;               // image groups = ceil(B / 4)
   int OH, OW;          // output extent of the sliding-window kernel ((H+1)x(W+1) forward, HxW for d/d likelihood)
   int Hp, Wp;          // kernel (streamed operand) extent padded to URC rows / TX columns
-  int XG, tiles, NS;   // strips per output row, strips per image, slices (32 strips) per image
+  int XG, tiles, NS;   // strips per output row, strips per (image, band), slices (32 strips) per (image, band)
+  int NBD, TB;         // output-row bands per image and rows per band: only TB - 1 + Hp prior rows are resident at a time
   int pstride, prows;  // shared-memory layout of the prior
   int raw;             // 1: operands are used as given (conv_mrf entry point), 0: BN + softplus applied while staging
 };
@@ -110,24 +111,28 @@ sm_conv_kernel(const float* __restrict__ energies /*[P][2H][2W]*/, const float* 
   const int lgroup = URC * d.Wp * 4;                  // floats per (group, chunk)
   const int lbuf = 2 * lgroup;
 
-  const long tasks_per_pair = (long)d.G * d.NS;
-  const long T = (long)d.P * tasks_per_pair;
+  // segment = (pair, band of output rows): the tasks of a segment share the staged prior rows [band*TB, band*TB + prows)
+  const long tasks_per_seg = (long)d.G * d.NS;
+  const long T = (long)d.P * d.NBD * tasks_per_seg;
   long t = (long)blockIdx.x * T / gridDim.x;
   const long t_end = (long)(blockIdx.x + 1) * T / gridDim.x;
 
   while (t < t_end) {
-    const int pair = (int)(t / tasks_per_pair);
-    const long pair_base = (long)pair * tasks_per_pair;
-    const long seg_end = min(t_end, pair_base + tasks_per_pair);
+    const int seg = (int)(t / tasks_per_seg);
+    const int pair = seg / d.NBD, band = seg - pair * d.NBD;
+    const int yb = band * d.TB;
+    const long pair_base = (long)seg * tasks_per_seg;
+    const long seg_end = min(t_end, pair_base + tasks_per_seg);
     const int j = pair_cond ? pair_cond[pair] : pair;   // which streamed operand this pair reads
 
-    // ---- stage the prior: Ps = softplus(E_pair), zero padding (rows >= 2H, columns >= 2W)
+    // ---- stage the prior: Ps = softplus(E_pair) rows yb .. yb+prows-1, zero padding (rows >= 2H, columns >= 2W)
     __syncthreads();
     {
       const float* E = energies + (long)pair * (2 * d.H) * (2 * d.W);
       const int n = d.prows * d.pstride;
       for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-        const int r = idx / d.pstride, c = idx - r * d.pstride;
+        const int rl = idx / d.pstride, c = idx - rl * d.pstride;
+        const int r = rl + yb;
         float pv = 0.f;
         if (r < 2 * d.H && c < 2 * d.W) {
           pv = E[(long)r * (2 * d.W) + c];
@@ -150,9 +155,10 @@ sm_conv_kernel(const float* __restrict__ energies /*[P][2H][2W]*/, const float* 
       const int g = (int)(rel / d.NS);
       const int slice = (int)(rel - (long)g * d.NS);
       int tile = slice * 32 + lane;
-      const bool lane_valid = active && tile < d.tiles;
+      bool lane_valid = active && tile < d.tiles;
       if (tile >= d.tiles) tile = 0;
-      const int y = tile / d.XG, x0 = (tile - y * d.XG) * TX;
+      const int y = tile / d.XG, x0 = (tile - y * d.XG) * TX;   // y: row inside the band
+      lane_valid = lane_valid && (yb + y) < d.OH;
       const int gsel = g - g_lo;
 
       unsigned long long acc[TX][2];
@@ -222,7 +228,7 @@ sm_conv_kernel(const float* __restrict__ energies /*[P][2H][2W]*/, const float* 
             float a0, a1, a2, a3;
             unpack2(acc[k][0], a0, a1);
             unpack2(acc[k][1], a2, a3);
-            float* o = Cb + (((long)pair * (4 * d.G) + 4 * g) * OH + y) * OW + x;
+            float* o = Cb + (((long)pair * (4 * d.G) + 4 * g) * OH + yb + y) * OW + x;
             const long istr = (long)OH * OW;
             o[0] = a0;
             o[istr] = a1;
@@ -309,6 +315,10 @@ __global__ void sm_resize_kernel(const float* __restrict__ Cb, SmDims d, float* 
   }
 }
 
+size_t sm_smem_bytes(const SmDims& d) {
+  return ((((size_t)d.prows * d.pstride + 3) & ~(size_t)3) + (size_t)2 * 2 * URC * d.Wp * 4) * sizeof(float);
+}
+
 // mode 0: forward  (output (H+1)x(W+1), streamed kernel HxW);  mode 1: d/d likelihood (output HxW, streamed kernel (H+1)x(W+1))
 int fill_dims(SmDims& d, int B, int H, int W, int K, int P, int mode = 0) {
   d.raw = 0;
@@ -320,11 +330,6 @@ int fill_dims(SmDims& d, int B, int H, int W, int K, int P, int mode = 0) {
   d.Hp = jcm_cdiv(KH, URC) * URC;
   d.Wp = jcm_cdiv(KW, TX) * TX;
   d.XG = jcm_cdiv(d.OW, TX);
-  d.tiles = d.OH * d.XG;
-  d.NS = jcm_cdiv(d.tiles, 32);
-  // prior rows read: y + u <= OH - 1 + Hp - 1;   columns read: x0 + (TX-1) + v <= XG*TX - 1 + Wp - 1
-  d.prows = d.OH - 1 + d.Hp;
-  if (d.prows < 2 * H) d.prows = 2 * H;
   int need = d.XG * TX + d.Wp - 1;
   if (need < 2 * W) need = 2 * W;
   // bank-conflict-free: a warp's 32 consecutive strips (y*XG + xg) must map to addresses == 7*strip (mod 32)
@@ -332,11 +337,16 @@ int fill_dims(SmDims& d, int B, int H, int W, int K, int P, int mode = 0) {
   int ps = need;
   while (ps % 32 != want) ++ps;
   d.pstride = ps;
+  // output-row bands: the fewest such that the resident prior rows (TB - 1 + Hp) + the likelihood buffers fit in shared memory
+  // (one band for 60x90 maps; two for the 96x128 maps of the K=14 configuration)
+  for (d.NBD = 1;; ++d.NBD) {
+    d.TB = jcm_cdiv(d.OH, d.NBD);
+    d.prows = d.TB - 1 + d.Hp;     // prior rows read by a band: y_local + u <= TB - 1 + Hp - 1
+    d.tiles = d.TB * d.XG;
+    d.NS = jcm_cdiv(d.tiles, 32);
+    if (sm_smem_bytes(d) <= (size_t)227 * 1024 - 256 || d.TB <= 1) break;
+  }
   return 0;
-}
-
-size_t sm_smem_bytes(const SmDims& d) {
-  return ((((size_t)d.prows * d.pstride + 3) & ~(size_t)3) + (size_t)2 * 2 * URC * d.Wp * 4) * sizeof(float);
 }
 
 }  // namespace
@@ -384,7 +394,7 @@ extern "C" int jcm_spatial_model_fwd(const float* heat_map, const float* bn_scal
   }
   {
     JCM_CUDA(cudaFuncSetAttribute(sm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
-    const long T = (long)P * d.G * d.NS;
+    const long T = (long)P * d.NBD * d.G * d.NS;
     long grid = jcm_num_sms();
     if (grid > (T + NW - 1) / NW) grid = (T + NW - 1) / NW;
     sm_conv_kernel<<<(int)grid, NW * 32, smem, st>>>(energies, Lt, pair_cond, d, Cb);
@@ -426,7 +436,7 @@ extern "C" int jcm_conv_mrf_fwd(const float* A, const float* Bmaps, float* out, 
   sm_prep_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(Bmaps, nullptr, nullptr, d, Lt);
   JCM_LAUNCH_CHECK();
   JCM_CUDA(cudaFuncSetAttribute(sm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
-  const long T = (long)d.G * d.NS;
+  const long T = (long)d.NBD * d.G * d.NS;
   long grid = jcm_num_sms();
   if (grid > (T + NW - 1) / NW) grid = (T + NW - 1) / NW;
   sm_conv_kernel<<<(int)grid, NW * 32, smem, st>>>(A, Lt, zero, d, Cb);
@@ -820,7 +830,7 @@ extern "C" int jcm_spatial_model_bwd(const float* g, const float* heat_map, cons
   }
   {
     JCM_CUDA(cudaFuncSetAttribute(sm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
-    const long T = (long)P * dm.G * dm.NS;
+    const long T = (long)P * dm.NBD * dm.G * dm.NS;
     long grid = jcm_num_sms();
     if (grid > (T + NW - 1) / NW) grid = (T + NW - 1) / NW;
     sm_conv_kernel<<<(int)grid, NW * 32, smem_conv, st>>>(energies, dCs, nullptr, dm, dLf);

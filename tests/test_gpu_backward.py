@@ -214,7 +214,7 @@ def test_conv1_stride2_wgrad_via_space_to_depth(jcm, jtrain, split):
 
 
 # ------------------------------------------------------------------------------------------------ spatial model
-@pytest.mark.parametrize('B,K,H,W', [(2, 4, 12, 20), (5, 3, 9, 13), (2, 7, 60, 90), (6, 7, 60, 90)])
+@pytest.mark.parametrize('B,K,H,W', [(2, 4, 12, 20), (5, 3, 9, 13), (2, 7, 60, 90), (6, 7, 60, 90), (3, 2, 96, 128)])
 @pytest.mark.parametrize('train', [True, False])
 def test_spatial_model_bwd(jcm, jtrain, B, K, H, W, train):
     """dE, db, d(bn gamma/beta), d(heat map) of SURVEY Appendix D vs autograd of the oracle."""

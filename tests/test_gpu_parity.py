@@ -193,6 +193,44 @@ def test_spatial_model_60x90_matches_oracle(jcm, B, K, train):
     assert torch.equal(jcm.get_joints_coords(jcm.spatial_softmax(out)).cpu(), orc.get_joints_coords(orc.spatial_softmax(ref)))
 
 
+def test_spatial_model_k14_96x128_config5(jcm):
+    """BASELINE config 5 shapes (K=14 joints, 96x128 maps: the prior no longer fits shared memory whole, the kernel runs two
+    output-row bands).  The oracle takes minutes at this size, so: (a) three of the 196 pairs against the oracle's conv_mrf,
+    (b) the full K=14 model against its own per-pair composition (size-independent identity of main.py:114-123)."""
+    K, H, W, B = 14, 96, 128, 5
+    rng = np.random.default_rng(14)
+    g = torch.Generator().manual_seed(14)
+    names = ['j%02d' % i for i in range(K)] + ['torso']
+    distr = orc.synthetic_pairwise(names, K, H, W, rng)
+    hm = torch.softmax(3 * torch.randn(B, H * W, K, generator=g), dim=1).reshape(B, H, W, K)
+    cat = torch.cat([hm, torch.from_numpy(orc.synthetic_labels(B, H, W, 1, rng))], dim=3).contiguous()
+    smp = jcm.PairwiseParams.from_distribution(distr, names, K, H, W)
+    ctx = jcm.Context(n_joints=K, joint_names=names, flag_train=False)
+    out = jcm.spatial_model(cat.cuda(), smp, ctx)
+    assert bool(torch.isfinite(out).all())
+    # inference-mode bn_sm with the initial moving statistics: h = x / sqrt(1 + eps)
+    h = cat.double() / np.sqrt(1.0 + orc.BN_EPS)
+    sp = orc.softplus
+    for i in (0, 7, 13):
+        m = torch.log(sp(h[..., i:i + 1]) + orc.DELTA)
+        for jn, cn in enumerate(names):
+            if jn == i:
+                continue
+            key = names[i] + '_' + cn
+            A = sp(torch.from_numpy(distr[key].astype(np.float32)).double()).float().view(1, 2 * H, 2 * W, 1)
+            lik = sp(h[..., jn:jn + 1]).float()
+            conv = jcm.conv_mrf(A.cuda(), lik.contiguous().cuda()).double().cpu()      # the GPU primitive, one pair at a time
+            m = m + torch.log(conv + sp(torch.tensor(1e-5, dtype=torch.float64)) + orc.DELTA)
+        assert rel(out[..., i], m[..., 0]) < 1e-4
+    # (a) the primitive itself vs the oracle on three pairs
+    for key in (names[0] + '_' + names[1], names[7] + '_torso', names[13] + '_' + names[2]):
+        A = torch.from_numpy(distr[key]).double().view(1, 2 * H, 2 * W, 1)
+        lik = sp(h[:2, :, :, 3:4])
+        ref = orc.conv_mrf(A, lik)
+        got = jcm.conv_mrf(A.float().cuda(), lik.float().contiguous().cuda())
+        assert rel(got, ref) < 2e-5
+
+
 @pytest.mark.parametrize('name', ['sm_small', 'sm_tiny_ragged'])
 def test_spatial_model_golden(jcm, name):
     z = np.load(os.path.join(GOLD, name + '.npz'))
