@@ -32,6 +32,7 @@ struct ConvParams {
   int kc, cblocks, ksize, pad, terms;
   int stages, a_bytes, b_bytes, stage_bytes;
   int relu;
+  int tma_store;        // 1: epilogue stages 32-column chunks in swizzled shared memory and writes them with TMA stores
   const float* bias;
   float* y;
 };
@@ -76,6 +77,17 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* map, uint3
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const void* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -120,7 +132,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                  const ConvParams p) {
+                  const __grid_constant__ CUtensorMap map_y, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
   __shared__ uint32_t tmem_base_slot;
@@ -226,6 +238,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     const int ly = row / p.TW, lx = row - ly * p.TW;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int epi_chunk = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile / m_tiles, mt = tile - nt * m_tiles;
       const int img = mt / (p.tiles_y * p.tiles_x);
@@ -237,32 +250,68 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-        uint32_t v[32];
-        tc_ld32(taddr0 + c0, v);
-        tc_ld_wait();
-        const int co0 = nt * p.block_n + c0;
-        if (valid) {
-          if (((p.Cout & 3) == 0) && (co0 + 32 <= p.Cout)) {
+      if (p.tma_store) {
+        // coalesced epilogue: 32-column chunks go through two 16 KB swizzled staging buffers and out with TMA stores (the box
+        // {32 ch, TW, TH, 1} has the A operand's pixel order, so accumulator row == staging row; ragged edges are clipped by TMA)
+        const uint32_t stage0 = smem_base + p.stages * p.stage_bytes;
+        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+          const uint32_t buf = stage0 + (uint32_t)(epi_chunk & 1) * (kTileM * 128);
+          if (threadIdx.x == 128) bulk_wait_read<1>();     // the store that last read this buffer is done with it
+          epi_bar();
+          uint32_t v[32];
+          tc_ld32(taddr0 + c0, v);
+          tc_ld_wait();
+          const int co0 = nt * p.block_n + c0;
+          const uint32_t rowaddr = buf + (uint32_t)row * 128;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o;
-              float4 b = p.bias ? *reinterpret_cast<const float4*>(p.bias + co0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-              o.x = __uint_as_float(v[j + 0]) + b.x;
-              o.y = __uint_as_float(v[j + 1]) + b.y;
-              o.z = __uint_as_float(v[j + 2]) + b.z;
-              o.w = __uint_as_float(v[j + 3]) + b.w;
-              if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-              *reinterpret_cast<float4*>(yrow + co0 + j) = o;
+          for (int j = 0; j < 8; ++j) {
+            float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                   __uint_as_float(v[4 * j + 3]));
+            if (p.bias && co0 + 4 * j < p.Cout) {
+              const float4 b = *reinterpret_cast<const float4*>(p.bias + co0 + 4 * j);
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int co = co0 + j;
-              if (co < p.Cout && (c0 + j) < p.block_n) {
-                float o = __uint_as_float(v[j]) + (p.bias ? p.bias[co] : 0.f);
-                if (p.relu) o = fmaxf(o, 0.f);
-                yrow[co] = o;
+            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (uint32_t)((j ^ (row & 7)) << 4)), "f"(o.x), "f"(o.y),
+                         "f"(o.z), "f"(o.w)
+                         : "memory");
+          }
+          fence_proxy_async();
+          epi_bar();
+          if (threadIdx.x == 128 && co0 < p.Cout) {
+            tma_store_4d(&map_y, buf, co0, tx * p.TW, ty * p.TH, img);
+            bulk_commit();
+          }
+          ++epi_chunk;
+        }
+      } else {
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+          uint32_t v[32];
+          tc_ld32(taddr0 + c0, v);
+          tc_ld_wait();
+          const int co0 = nt * p.block_n + c0;
+          if (valid) {
+            if (((p.Cout & 3) == 0) && (co0 + 32 <= p.Cout)) {
+  #pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 o;
+                float4 b = p.bias ? *reinterpret_cast<const float4*>(p.bias + co0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                o.x = __uint_as_float(v[j + 0]) + b.x;
+                o.y = __uint_as_float(v[j + 1]) + b.y;
+                o.z = __uint_as_float(v[j + 2]) + b.z;
+                o.w = __uint_as_float(v[j + 3]) + b.w;
+                if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                *reinterpret_cast<float4*>(yrow + co0 + j) = o;
+              }
+            } else {
+  #pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int co = co0 + j;
+                if (co < p.Cout && (c0 + j) < p.block_n) {
+                  float o = __uint_as_float(v[j]) + (p.bias ? p.bias[co] : 0.f);
+                  if (p.relu) o = fmaxf(o, 0.f);
+                  yrow[co] = o;
+                }
               }
             }
           }
@@ -273,6 +322,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.tma_store && threadIdx.x == 128) bulk_wait_all();   // shared memory must outlive the last TMA store
   }
 
   tc_fence_before();
@@ -301,14 +351,14 @@ PFN_tmapEncodeTiled get_encode() {
 }
 
 int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-             const uint32_t* box, CUtensorMapSwizzle swz) {
+             const uint32_t* box, CUtensorMapSwizzle swz, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
   PFN_tmapEncodeTiled enc = get_encode();
   if (!enc) {
     jcm_set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
     return JCM_ENOTSUP;
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+  CUresult r = enc(m, dtype, (cuuint32_t)rank, const_cast<void*>(base),
                    (const cuuint64_t*)dims, (const cuuint64_t*)strides_bytes, (const cuuint32_t*)box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -364,7 +414,9 @@ extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_
   p.a_bytes = kTileM * p.kc * 2;
   p.b_bytes = p.block_n * p.kc * 2;
   p.stage_bytes = ((p.a_bytes + p.b_bytes + 1023) / 1024) * 1024;
-  p.stages = (200 * 1024) / p.stage_bytes;
+  p.tma_store = (Cout % 4) == 0 && Cout >= 32 && (p.block_n % 32) == 0;
+  const int epi_bytes = p.tma_store ? 2 * kTileM * 128 : 0;     // two staging buffers of 128 rows x 32 fp32
+  p.stages = (225 * 1024 - epi_bytes) / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   p.relu = relu;
   p.bias = bias;
@@ -391,16 +443,26 @@ extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_
     if (rc) return rc;
   }
 
+  CUtensorMap my;
+  memset(&my, 0, sizeof(my));
+  if (p.tma_store) {
+    uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)Cout * 4, (uint64_t)W * Cout * 4, (uint64_t)H * W * Cout * 4};
+    uint32_t box[4] = {32, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+    int rc = make_map(&my, y, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+    if (rc) return rc;
+  }
+
   const int total_tiles = B * p.tiles_x * p.tiles_y * p.n_tiles;
   int grid = jcm_num_sms();
   if (grid > total_tiles) grid = total_tiles;
-  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + epi_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     JCM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512));
     attr_set = true;
   }
-  conv_igemm_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  conv_igemm_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, my, p);
   JCM_LAUNCH_CHECK();
   return JCM_OK;
 }
