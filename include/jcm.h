@@ -33,8 +33,10 @@ long jcm_launch_count(void); /* kernels launched by this library since load */
 
 /* ---- operand preparation --------------------------------------------------------------------------------------- */
 
-/* x fp32 [B,H,W,3] -> space-to-depth bf16 planes [B,H/2,W/2,16], [B,H/4,W/4,16], [B,H/8,W/8,16] for the three banks.
- * Replaces tf.image.resize_images(x,[H/2,W/2]) / [H/4,W/4] (main.py:51,60) and prepares the stride-2 conv1_* (main.py:44,52,61). */
+/* x fp32 [B,H,W,3] -> space-to-depth bf16 planes [B,H/2,W/2,64], [B,H/4,W/4,64], [B,H/8,W/8,64] for the three banks: channel
+ * dx*16 + (sy*2+sx)*3 + c holds x[2Y+sy, 2(X+dx-1)+sx, c] (the three horizontal taps of the 3x3 s2d kernel folded into channels).
+ * Replaces tf.image.resize_images(x,[H/2,W/2]) / [H/4,W/4] (main.py:51,60) and prepares the stride-2 conv1_* (main.py:44,52,61),
+ * which becomes a 3x1 stride-1 convolution (ksize 3, kw 1) over these planes. */
 int jcm_prep_input(const float* x, int B, int H, int W, void* full_hi, void* full_lo, void* half_hi, void* half_lo,
                    void* quarter_hi, void* quarter_lo, void* stream);
 
@@ -43,7 +45,7 @@ int jcm_prep_input(const float* x, int B, int H, int W, void* full_hi, void* ful
 int jcm_pack_weights(const float* w, int ksize, int Cin, int Cout, int Opad, int Ipad, int transpose, void* out_hi,
                      void* out_lo, void* stream);
 
-/* conv1_* kernels [5,5,3,Cout] -> [9][Cout][16] matching jcm_prep_input's channel order (5x5 s2 SAME == 3x3 s1 over s2d). */
+/* conv1_* kernels [5,5,3,Cout] -> [3][Cout][64] matching jcm_prep_input's channel order (5x5 s2 SAME == 3x1 s1 over x-folded s2d). */
 int jcm_pack_weights_s2d(const float* w, int Cout, void* out_hi, void* out_lo, void* stream);
 
 /* fp32 -> bf16 hi (+ lo) element-wise; n multiple of 4. */
@@ -52,10 +54,11 @@ int jcm_split_planes(const float* x, long n, void* hi, void* lo, void* stream);
 /* ---- part detector --------------------------------------------------------------------------------------------- */
 
 /* y = [relu](conv_SAME_stride1(x, w) + bias): tf.nn.conv2d + bias + tf.nn.relu, main.py:133-135,160-162.
- * x planes [B,H,W,Cin] (Cin a multiple of 16), w planes [k*k][Cout_pad][Cin], y fp32 [B,H,W,Cout].
+ * x planes [B,H,W,Cin] (Cin a multiple of 16), w planes [ksize*kw][Cout_pad][Cin], y fp32 [B,H,W,Cout].
+ * ksize = kernel height, kw = kernel width (0: square, kw = ksize).
  * TMA-fed implicit GEMM on tcgen05 tensor cores, fp32 accumulation in TMEM. */
 int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, float* y,
-                   int B, int H, int W, int Cin, int Cout, int Cout_pad, int ksize, int relu, void* stream);
+                   int B, int H, int W, int Cin, int Cout, int Cout_pad, int ksize, int kw, int relu, void* stream);
 
 /* tf.contrib.layers.batch_norm(decay=0.9, eps=1e-3, center, scale), main.py:128-130 and :112-113.
  * jcm_bn_stats: per-channel partial sums of x [M,C] into `partial` (jcm_bn_stats_blocks(M,C)*2*C floats).
@@ -134,15 +137,16 @@ int jcm_upsample_avg3_bwd(const float* dmerged, int B, int H, int W, int H2, int
 /* fp32 [M,C] -> bf16 planes [M,Cpad] with zero-padded channels. */
 int jcm_pad_planes(const float* x, long M, int C, int Cpad, void* hi, void* lo, void* stream);
 
-/* weight gradient of tf.nn.conv2d (main.py:135): dw [k*k][Cin][dw_cout_stride] from input planes x [B,H,W,Cin] and output-gradient
+/* weight gradient of tf.nn.conv2d (main.py:135): dw [ksize*kw][Cin][dw_cout_stride] from input planes x [B,H,W,Cin] and output-gradient
  * planes g [B,H,W,Gc].  tcgen05 GEMM per tap with the contraction over pixels (MN-major operands), split-K partial sums in
  * `workspace` (jcm_conv2d_wgrad_workspace bytes), deterministic reduction.  The data gradient is jcm_conv2d_fwd on
  * jcm_pack_weights(..., transpose = 1). */
-long jcm_conv2d_wgrad_workspace(int B, int H, int W, int Cin, int Gc, int ksize);
+long jcm_conv2d_wgrad_workspace(int B, int H, int W, int Cin, int Gc, int ksize, int kw);
 int jcm_conv2d_wgrad(const void* x_hi, const void* x_lo, const void* g_hi, const void* g_lo, float* dw, void* workspace,
-                     long workspace_bytes, int B, int H, int W, int Cin, int Gc, int Cout, int dw_cout_stride, int ksize, void* stream);
+                     long workspace_bytes, int B, int H, int W, int Cin, int Gc, int Cout, int dw_cout_stride, int ksize, int kw,
+                     void* stream);
 
-/* conv1 weight gradient in space-to-depth form [9][16][Cout] (as jcm_conv2d_wgrad writes it) -> [5,5,3,Cout]. */
+/* conv1 weight gradient in x-folded space-to-depth form [3][64][Cout] (as jcm_conv2d_wgrad writes it) -> [5,5,3,Cout]. */
 int jcm_unpack_s2d_grad(const float* g9, int Cout, float* dw, void* stream);
 
 /* backward of jcm_spatial_model_fwd.  fwd_workspace: the forward workspace of the same inputs. */
@@ -180,7 +184,7 @@ int jcm_fma_peak(float* scratch, int blocks, int iters, int packed, double* flop
 
 /* Naive direct convolution on the same operand planes - used only by tests to cross-check the tcgen05 kernel. */
 int jcm_debug_conv2d_naive(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
-                           float* y, int B, int H, int W, int Cin, int Cout, int Cout_pad, int ksize, int relu, void* stream);
+                           float* y, int B, int H, int W, int Cin, int Cout, int Cout_pad, int ksize, int kw, int relu, void* stream);
 
 #ifdef __cplusplus
 }

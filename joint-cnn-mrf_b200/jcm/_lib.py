@@ -22,7 +22,7 @@ SIGNATURES = {
     'jcm_pack_weights': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     'jcm_pack_weights_s2d': (_I, [_P, _I, _P, _P, _P]),
     'jcm_split_planes': (_I, [_P, _L, _P, _P, _P]),
-    'jcm_conv2d_fwd': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'jcm_conv2d_fwd': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'jcm_bn_stats_blocks': (_I, [_L, _I]),
     'jcm_bn_stats': (_I, [_P, _L, _I, _P, _P]),
     'jcm_bn_finalize': (_I, [_P, _L, _I, _P, _P, _P, _P, _F, _F, _I, _I, _P, _P, _P, _P, _P]),
@@ -41,8 +41,8 @@ SIGNATURES = {
     'jcm_colsum': (_I, [_P, _L, _I, _P, _P, _P]),
     'jcm_upsample_avg3_bwd': (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     'jcm_pad_planes': (_I, [_P, _L, _I, _I, _P, _P, _P]),
-    'jcm_conv2d_wgrad_workspace': (_L, [_I, _I, _I, _I, _I, _I]),
-    'jcm_conv2d_wgrad': (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'jcm_conv2d_wgrad_workspace': (_L, [_I, _I, _I, _I, _I, _I, _I]),
+    'jcm_conv2d_wgrad': (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'jcm_unpack_s2d_grad': (_I, [_P, _I, _P, _P]),
     'jcm_spatial_model_bwd_workspace': (_L, [_I, _I, _I, _I, _I]),
     'jcm_spatial_model_bwd': (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
@@ -54,7 +54,7 @@ SIGNATURES = {
     'jcm_grad_prepare': (_I, [_P, _P, _L, _L, _F, _F, _P, _P, _P]),
     'jcm_clip_adam': (_I, [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _I, _P]),
     'jcm_fma_peak': (_I, [_P, _I, _I, _I, _P, _P]),
-    'jcm_debug_conv2d_naive': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'jcm_debug_conv2d_naive': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
 }
 
 _lib = None

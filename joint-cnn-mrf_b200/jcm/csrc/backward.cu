@@ -7,7 +7,7 @@
 //   jcm_colsum_finalize       deterministic reduction of per-block column partials (bias / gamma / beta gradients)
 //   jcm_upsample_avg3_bwd     transpose of the legacy-bilinear up-sampling + 3-way average (gather form, no atomics)
 //   jcm_pad_planes            fp32 [M,C] -> bf16 planes [M,Cpad] (zero padded channels; conv6's K-channel gradient)
-//   jcm_unpack_s2d_grad       conv1 weight gradient [9][16][Cout] (space-to-depth form) -> [5,5,3,Cout]
+//   jcm_unpack_s2d_grad       conv1 weight gradient [3][64][Cout] (x-folded space-to-depth form) -> [5,5,3,Cout]
 #include "common.cuh"
 
 namespace {
@@ -287,7 +287,7 @@ __global__ void pad_planes_kernel(const float* __restrict__ x, long M, int C, in
   }
 }
 
-// g9 [9][16][Cout] (fp32, s2d form as jcm_conv2d_wgrad writes it: tap, channel, cout) -> dw [5][5][3][Cout]
+// g9 [3][64][Cout] (fp32, x-folded s2d form as jcm_conv2d_wgrad writes it: vertical tap, channel, cout) -> dw [5][5][3][Cout]
 __global__ void unpack_s2d_grad_kernel(const float* __restrict__ g9, int Cout, float* __restrict__ dw) {
   const int total = 75 * Cout;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -295,7 +295,7 @@ __global__ void unpack_s2d_grad_kernel(const float* __restrict__ g9, int Cout, f
     const int r = idx / Cout;
     const int ci = r % 3, tx = (r / 3) % 5, ty = r / 15;
     const int by = (ty + 1) >> 1, sy = (ty + 1) & 1, bx = (tx + 1) >> 1, sx = (tx + 1) & 1;
-    dw[idx] = g9[((by * 3 + bx) * 16 + (sy * 2 + sx) * 3 + ci) * Cout + co];
+    dw[idx] = g9[((by * 64 + bx * 16) + (sy * 2 + sx) * 3 + ci) * Cout + co];
   }
 }
 

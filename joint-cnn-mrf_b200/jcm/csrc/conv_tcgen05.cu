@@ -29,7 +29,7 @@ struct ConvParams {
   int B, H, W, Cout;
   int TW, TH, tiles_x, tiles_y;
   int n_tiles, block_n;
-  int kc, cblocks, ksize, pad, terms;
+  int kc, cblocks, ksize, kw, pad, pad_x, terms;   // ksize x kw taps (kernel height x width), SAME padding pad / pad_x
   int stages, a_bytes, b_bytes, stage_bytes;
   int relu;
   int tma_store;        // 1: epilogue stages 32-column chunks in swizzled shared memory and writes them with TMA stores
@@ -166,7 +166,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 
   const int m_tiles = p.B * p.tiles_y * p.tiles_x;
   const int total_tiles = m_tiles * p.n_tiles;
-  const int taps = p.ksize * p.ksize;
+  const int taps = p.ksize * p.kw;
   const int num_kb = taps * p.cblocks * p.terms;
 
   if (warp == 0) {
@@ -179,9 +179,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         const int img = mt / (p.tiles_y * p.tiles_x);
         const int r = mt - img * (p.tiles_y * p.tiles_x);
         const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-        const int x0 = tx * p.TW - p.pad, y0 = ty * p.TH - p.pad;
+        const int x0 = tx * p.TW - p.pad_x, y0 = ty * p.TH - p.pad;
         for (int tap = 0; tap < taps; ++tap) {
-          const int dy = tap / p.ksize, dx = tap - dy * p.ksize;
+          const int dy = tap / p.kw, dx = tap - dy * p.kw;
           for (int cb = 0; cb < p.cblocks; ++cb) {
             for (int term = 0; term < p.terms; ++term) {
               mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -278,9 +278,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
           }
           fence_proxy_async();
           epi_bar();
-          if (threadIdx.x == 128 && co0 < p.Cout) {
-            tma_store_4d(&map_y, buf, co0, tx * p.TW, ty * p.TH, img);
-            bulk_commit();
+          if (threadIdx.x == 128) {
+            if (co0 < p.Cout) tma_store_4d(&map_y, buf, co0, tx * p.TW, ty * p.TH, img);
+            bulk_commit();   // one group per chunk even when nothing is stored (padded columns), so wait_group.read 1 == "chunk - 2 done"
           }
           ++epi_chunk;
         }
@@ -386,12 +386,13 @@ static void pick_patch(int H, int W, int* TW, int* TH) {
 }
 
 extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
-                              float* y, int B, int H, int W, int Cin, int Cout, int Cout_pad, int ksize, int relu,
+                              float* y, int B, int H, int W, int Cin, int Cout, int Cout_pad, int ksize, int kw, int relu,
                               void* stream) {
+  if (kw <= 0) kw = ksize;
   JCM_CHECK_ARG(x_hi && w_hi && y, "jcm_conv2d_fwd: null pointer");
   JCM_CHECK_ARG((x_lo == nullptr) == (w_lo == nullptr), "jcm_conv2d_fwd: x_lo and w_lo must both be given (bf16x3) or both NULL (bf16)");
   JCM_CHECK_ARG(B > 0 && H > 0 && W > 0, "jcm_conv2d_fwd: bad shape B=%d H=%d W=%d", B, H, W);
-  JCM_CHECK_ARG(ksize > 0 && (ksize & 1), "jcm_conv2d_fwd: ksize must be odd (SAME, stride 1), got %d", ksize);
+  JCM_CHECK_ARG(ksize > 0 && (ksize & 1) && (kw & 1), "jcm_conv2d_fwd: kernel extents must be odd (SAME, stride 1), got %d x %d", ksize, kw);
   JCM_CHECK_ARG(Cin >= 16 && (Cin % 16) == 0, "jcm_conv2d_fwd: Cin must be a multiple of 16, got %d", Cin);
   JCM_CHECK_ARG(Cout > 0 && Cout_pad >= Cout && (Cout_pad % 16) == 0, "jcm_conv2d_fwd: Cout_pad=%d must be >= Cout=%d and a multiple of 16", Cout_pad, Cout);
   JCM_CHECK_ARG((((uintptr_t)x_hi | (uintptr_t)w_hi | (uintptr_t)x_lo | (uintptr_t)w_lo | (uintptr_t)y) & 15) == 0,
@@ -409,7 +410,9 @@ extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_
   p.kc = (Cin % 64) == 0 ? 64 : ((Cin % 32) == 0 ? 32 : 16);
   p.cblocks = Cin / p.kc;
   p.ksize = ksize;
+  p.kw = kw;
   p.pad = (ksize - 1) / 2;
+  p.pad_x = (kw - 1) / 2;
   p.terms = x_lo ? 3 : 1;
   p.a_bytes = kTileM * p.kc * 2;
   p.b_bytes = p.block_n * p.kc * 2;
@@ -434,7 +437,7 @@ extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_
     if (rc) return rc;
   }
   {
-    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout_pad, (uint64_t)(ksize * ksize)};
+    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout_pad, (uint64_t)(ksize * kw)};
     uint64_t str[2] = {(uint64_t)Cin * 2, (uint64_t)Cout_pad * Cin * 2};
     uint32_t box[3] = {(uint32_t)p.kc, (uint32_t)p.block_n, 1};
     int rc = make_map(&mb_hi, w_hi, 3, dims, str, box, swz);
@@ -484,7 +487,7 @@ constexpr int kWgPix = 64;   // pixels per k-block
 struct WgradParams {
   int B, H, W;
   int TW, TH, tiles_x, tiles_y;
-  int ksize, pad, taps;
+  int ksize, kw, pad, pad_x, taps;
   int m_tiles, n_tiles, block_n, m_pad, n_pad;
   int shift_m, shift_n;            // 1 when that operand is the (shifted) layer input X, 0 when it is the gradient G
   int kc_n, kc_m;                  // channels per N-side / M-side box: 64, 32 or 16
@@ -547,7 +550,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_m_hi, const __grid_con
         const int tap = r / (p.m_tiles * p.n_tiles);
         r -= tap * (p.m_tiles * p.n_tiles);
         const int mt = r / p.n_tiles, nt = r - mt * p.n_tiles;
-        const int dy = tap / p.ksize - p.pad, dx = tap % p.ksize - p.pad;
+        const int dy = tap / p.kw - p.pad, dx = tap % p.kw - p.pad_x;
         const int p0 = (int)((long)split * p.total_patches / p.splits);
         const int p1 = (int)((long)(split + 1) * p.total_patches / p.splits);
         int img = p0 / patches_per_img;
@@ -696,7 +699,7 @@ struct WgradPlan {
   int x_is_m, m_ch, n_ch, m_tiles, n_tiles, block_n, kc_n, kc_m, m_pad, n_pad, splits, TW, TH, tiles_x, tiles_y, total_patches;
 };
 
-void plan_wgrad(int B, int H, int W, int Cin, int Gc, int ksize, WgradPlan* pl) {
+void plan_wgrad(int B, int H, int W, int Cin, int Gc, int ksize, int kw, WgradPlan* pl) {
   pl->x_is_m = Cin >= Gc;
   pl->m_ch = pl->x_is_m ? Cin : Gc;
   pl->n_ch = pl->x_is_m ? Gc : Cin;
@@ -714,7 +717,7 @@ void plan_wgrad(int B, int H, int W, int Cin, int Gc, int ksize, WgradPlan* pl) 
   // k-split: the persistent grid runs ceil(tasks / SMs) waves of tasks that each stream total_patches / splits k-blocks (+ an
   // epilogue worth ~6 k-blocks).  Pick the split count that minimises waves x task length: e.g. conv5 (648 tasks = 4.4 waves)
   // wastes 12 % of the last wave unsplit, 0.5 % with 5 splits; the partial sums cost one extra read in wgrad_reduce_kernel.
-  const int base = ksize * ksize * pl->m_tiles * pl->n_tiles;
+  const int base = ksize * kw * pl->m_tiles * pl->n_tiles;
   const int sms = jcm_num_sms();
   int best_s = 1;
   double best_cost = 1e300;
@@ -722,7 +725,7 @@ void plan_wgrad(int B, int H, int W, int Cin, int Gc, int ksize, WgradPlan* pl) 
     if (s > 1 && s > pl->total_patches / 8) break;
     const double waves = (double)jcm_cdiv(base * s, sms);
     // + the reduction pass over s partial copies (HBM-bound), in units of one k-block (~0.5 us)
-    const double reduce = (double)s * ksize * ksize * pl->m_pad * pl->n_pad * 4.0 / 6.4e12 / 0.5e-6;
+    const double reduce = (double)s * ksize * kw * pl->m_pad * pl->n_pad * 4.0 / 6.4e12 / 0.5e-6;
     const double cost = waves * (jcm_cdiv(pl->total_patches, s) + 6.0) + reduce;
     if (cost < best_cost * 0.999) { best_cost = cost; best_s = s; }
   }
@@ -732,10 +735,11 @@ void plan_wgrad(int B, int H, int W, int Cin, int Gc, int ksize, WgradPlan* pl) 
 }  // namespace
 
 // bytes of fp32 partial sums jcm_conv2d_wgrad needs in `workspace`
-extern "C" long jcm_conv2d_wgrad_workspace(int B, int H, int W, int Cin, int Gc, int ksize) {
+extern "C" long jcm_conv2d_wgrad_workspace(int B, int H, int W, int Cin, int Gc, int ksize, int kw) {
+  if (kw <= 0) kw = ksize;
   WgradPlan pl;
-  plan_wgrad(B, H, W, Cin, Gc, ksize, &pl);
-  return (long)pl.splits * ksize * ksize * pl.m_pad * pl.n_pad * (long)sizeof(float);
+  plan_wgrad(B, H, W, Cin, Gc, ksize, kw, &pl);
+  return (long)pl.splits * ksize * kw * pl.m_pad * pl.n_pad * (long)sizeof(float);
 }
 
 // x planes [B,H,W,Cin] (layer input, Cin multiple of 16), g planes [B,H,W,Gc] (gradient w.r.t. the conv output, Gc = Cout padded
@@ -743,15 +747,16 @@ extern "C" long jcm_conv2d_wgrad_workspace(int B, int H, int W, int Cin, int Gc,
 // filter (TF autodiff of main.py:135).
 extern "C" int jcm_conv2d_wgrad(const void* x_hi, const void* x_lo, const void* g_hi, const void* g_lo, float* dw, void* workspace,
                                 long workspace_bytes, int B, int H, int W, int Cin, int Gc, int Cout, int dw_cout_stride, int ksize,
-                                void* stream) {
+                                int kw, void* stream) {
+  if (kw <= 0) kw = ksize;
   JCM_CHECK_ARG(x_hi && g_hi && dw && workspace, "jcm_conv2d_wgrad: null pointer");
   JCM_CHECK_ARG((x_lo == nullptr) == (g_lo == nullptr), "jcm_conv2d_wgrad: x_lo and g_lo must both be given or both NULL");
-  JCM_CHECK_ARG(B > 0 && H > 0 && W > 0 && (ksize & 1), "jcm_conv2d_wgrad: bad shape");
+  JCM_CHECK_ARG(B > 0 && H > 0 && W > 0 && (ksize & 1) && (kw & 1), "jcm_conv2d_wgrad: bad shape");
   JCM_CHECK_ARG((Cin % 16) == 0 && (Gc % 16) == 0 && Cout <= Gc && Cout <= dw_cout_stride, "jcm_conv2d_wgrad: channel counts must be multiples of 16 (Cin=%d Gc=%d)", Cin, Gc);
   WgradPlan pl;
-  plan_wgrad(B, H, W, Cin, Gc, ksize, &pl);
+  plan_wgrad(B, H, W, Cin, Gc, ksize, kw, &pl);
   JCM_CHECK_ARG(pl.n_ch % pl.block_n == 0, "jcm_conv2d_wgrad: N-side channel count %d must be <= 256 or a multiple of 256", pl.n_ch);
-  if (workspace_bytes < jcm_conv2d_wgrad_workspace(B, H, W, Cin, Gc, ksize)) {
+  if (workspace_bytes < jcm_conv2d_wgrad_workspace(B, H, W, Cin, Gc, ksize, kw)) {
     jcm_set_error("jcm_conv2d_wgrad: workspace too small");
     return JCM_EWORKSPACE;
   }
@@ -759,7 +764,7 @@ extern "C" int jcm_conv2d_wgrad(const void* x_hi, const void* x_lo, const void* 
   memset(&p, 0, sizeof(p));
   p.B = B; p.H = H; p.W = W;
   p.TW = pl.TW; p.TH = pl.TH; p.tiles_x = pl.tiles_x; p.tiles_y = pl.tiles_y;
-  p.ksize = ksize; p.pad = (ksize - 1) / 2; p.taps = ksize * ksize;
+  p.ksize = ksize; p.kw = kw; p.pad = (ksize - 1) / 2; p.pad_x = (kw - 1) / 2; p.taps = ksize * kw;
   p.m_tiles = pl.m_tiles; p.n_tiles = pl.n_tiles; p.block_n = pl.block_n; p.m_pad = pl.m_pad; p.n_pad = pl.n_pad;
   p.shift_m = pl.x_is_m ? 1 : 0; p.shift_n = pl.x_is_m ? 0 : 1;
   p.kc_n = pl.kc_n; p.kc_m = pl.kc_m;

@@ -194,9 +194,9 @@ namespace {
 __global__ void conv_naive_kernel(const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __restrict__ x_lo,
                                   const __nv_bfloat16* __restrict__ w_hi, const __nv_bfloat16* __restrict__ w_lo,
                                   const float* __restrict__ bias, float* __restrict__ y, int B, int H, int W, int Cin, int Cout,
-                                  int Cout_pad, int ksize, int relu) {
+                                  int Cout_pad, int ksize, int kw, int relu) {
   const long total = (long)B * H * W * Cout;
-  const int pad = (ksize - 1) / 2;
+  const int pad = (ksize - 1) / 2, pad_x = (kw - 1) / 2;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     const int co = (int)(idx % Cout);
     long t = idx / Cout;
@@ -208,11 +208,11 @@ __global__ void conv_naive_kernel(const __nv_bfloat16* __restrict__ x_hi, const 
     for (int dy = 0; dy < ksize; ++dy) {
       const int iy = oy + dy - pad;
       if (iy < 0 || iy >= H) continue;
-      for (int dx = 0; dx < ksize; ++dx) {
-        const int ix = ox + dx - pad;
+      for (int dx = 0; dx < kw; ++dx) {
+        const int ix = ox + dx - pad_x;
         if (ix < 0 || ix >= W) continue;
         const long xo = (((long)n * H + iy) * W + ix) * Cin;
-        const long wo = ((long)(dy * ksize + dx) * Cout_pad + co) * Cin;
+        const long wo = ((long)(dy * kw + dx) * Cout_pad + co) * Cin;
         for (int ci = 0; ci < Cin; ++ci) {
           const float xh = __bfloat162float(x_hi[xo + ci]), wh = __bfloat162float(w_hi[wo + ci]);
           acc = fmaf(xh, wh, acc);
@@ -231,15 +231,16 @@ __global__ void conv_naive_kernel(const __nv_bfloat16* __restrict__ x_hi, const 
 }  // namespace
 
 extern "C" int jcm_debug_conv2d_naive(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
-                                      float* y, int B, int H, int W, int Cin, int Cout, int Cout_pad, int ksize, int relu,
+                                      float* y, int B, int H, int W, int Cin, int Cout, int Cout_pad, int ksize, int kw, int relu,
                                       void* stream) {
   JCM_CHECK_ARG(x_hi && w_hi && y, "jcm_debug_conv2d_naive: null pointer");
+  if (kw <= 0) kw = ksize;
   const long total = (long)B * H * W * Cout;
   long grid = (total + 127) / 128;
   if (grid > 148L * 32) grid = 148L * 32;
   conv_naive_kernel<<<(int)grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo,
                                                                  (const __nv_bfloat16*)w_hi, (const __nv_bfloat16*)w_lo, bias, y, B, H, W,
-                                                                 Cin, Cout, Cout_pad, ksize, relu);
+                                                                 Cin, Cout, Cout_pad, ksize, kw, relu);
   JCM_LAUNCH_CHECK();
   return JCM_OK;
 }

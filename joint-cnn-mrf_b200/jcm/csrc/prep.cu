@@ -3,35 +3,44 @@
 //                         Folds the reference's `tf.image.resize_images(x, [H/2,W/2])` / `[H/4,W/4]`
 //                         (main.py:51,60; legacy bilinear at integer factors == exact strided sub-sampling, SURVEY
 //                         Appendix B) into the gather, and turns the 5x5 stride-2 SAME conv1 (main.py:44,52,61;
-//                         TF pads 1 before / 2 after) into a 3x3 stride-1 conv over 16 channels (12 used).
+//                         TF pads 1 before / 2 after) into a 3x1 stride-1 conv over 64 channels (3 horizontal taps x 16, 36 used).
 //   * jcm_pack_weights    HWIO fp32 -> [tap][Cout_pad][Cin_pad] bf16 hi/lo (K-major B operand); optional
 //                         flip+transpose for the data-gradient convolution.
-//   * jcm_pack_weights_s2d  the conv1 weights [5,5,3,C] -> [9][C][16] matching jcm_prep_input's channel order.
+//   * jcm_pack_weights_s2d  the conv1 weights [5,5,3,C] -> [3][C][64] matching jcm_prep_input's channel order.
 //   * jcm_split_planes    fp32 -> bf16 hi (+ lo) element-wise.
 #include "common.cuh"
 
 namespace {
 
+// One thread per output pixel (n, Y, X) and x-tap dxi: writes the 16-channel group dxi of the 64-channel pixel,
+//   out[n,Y,X, dxi*16 + (sy*2+sx)*3 + c] = x[n, step*(2Y+sy), step*(2(X+dxi-1)+sx), c]     (0 outside the image, channels 12..15 of
+// each group and the whole group 3 are padding).  Folding the three horizontal taps of the 3x3 space-to-depth kernel into the
+// channel axis makes conv1 a 3x1 convolution with a 64-channel (128-byte) contraction per tap instead of 9 taps of 16 channels.
 __global__ void prep_input_kernel(const float* __restrict__ x, int B, int H, int W, int step,
                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   const int Ho = H / (2 * step), Wo = W / (2 * step);
-  const long total = (long)B * Ho * Wo;
+  const long total = (long)B * Ho * Wo * 4;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int X = (int)(i % Wo);
-    const long t = i / Wo;
+    const int dxi = (int)(i & 3);
+    const long pix = i >> 2;
+    const int X = (int)(pix % Wo);
+    const long t = pix / Wo;
     const int Y = (int)(t % Ho);
     const int n = (int)(t / Ho);
     __align__(16) __nv_bfloat16 vh[16];
     __align__(16) __nv_bfloat16 vl[16];
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      const int sy = s >> 1, sx = s & 1;
-      const float* px = x + (((long)n * H + (long)step * (2 * Y + sy)) * W + (long)step * (2 * X + sx)) * 3;
+    for (int c = 0; c < 16; ++c) { vh[c] = __float2bfloat16_rn(0.f); vl[c] = vh[c]; }
+    const int Xs = X + dxi - 1;
+    if (dxi < 3 && Xs >= 0 && Xs < Wo) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) split_bf16(px[c], vh[s * 3 + c], vl[s * 3 + c]);
+      for (int s = 0; s < 4; ++s) {
+        const int sy = s >> 1, sx = s & 1;
+        const float* px = x + (((long)n * H + (long)step * (2 * Y + sy)) * W + (long)step * (2 * Xs + sx)) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) split_bf16(px[c], vh[s * 3 + c], vl[s * 3 + c]);
+      }
     }
-#pragma unroll
-    for (int c = 12; c < 16; ++c) { vh[c] = __float2bfloat16_rn(0.f); vl[c] = vh[c]; }
     uint4* dh = reinterpret_cast<uint4*>(hi + i * 16);
     dh[0] = reinterpret_cast<uint4*>(vh)[0];
     dh[1] = reinterpret_cast<uint4*>(vh)[1];
@@ -67,18 +76,18 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int taps, int C
   }
 }
 
-// conv1: w [5][5][3][Cout] -> out [3x3][Cout][16];  tap t in 0..4 -> block tap (t+1)/2, sub position (t+1)&1
-// (input row = 2*o - 1 + t under TF SAME padding (1 before, 2 after), see prep_input_kernel's channel order).
+// conv1: w [5][5][3][Cout] -> out [3 vertical taps][Cout][64], channel = bx*16 + (sy*2+sx)*3 + ci as prep_input_kernel writes it;
+// original tap t in 0..4 -> block tap (t+1)/2, sub position (t+1)&1 (input row = 2*o - 1 + t under TF SAME padding (1 before, 2 after)).
 __global__ void pack_weights_s2d_kernel(const float* __restrict__ w, int Cout, __nv_bfloat16* __restrict__ hi,
                                         __nv_bfloat16* __restrict__ lo) {
-  const int total = 9 * Cout * 16;
+  const int total = 3 * Cout * 64;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int ch = idx & 15;
-    const int co = (idx >> 4) % Cout;
-    const int tap = (idx >> 4) / Cout;
-    const int by = tap / 3, bx = tap % 3;
+    const int ch64 = idx & 63;
+    const int co = (idx >> 6) % Cout;
+    const int by = (idx >> 6) / Cout;
+    const int bx = ch64 >> 4, ch = ch64 & 15;
     float v = 0.f;
-    if (ch < 12) {
+    if (bx < 3 && ch < 12) {
       const int s = ch / 3, ci = ch % 3;
       const int sy = s >> 1, sx = s & 1;
       const int ty = 2 * by + sy - 1, tx = 2 * bx + sx - 1;  // original 5x5 tap
@@ -122,7 +131,7 @@ extern "C" int jcm_prep_input(const float* x, int B, int H, int W, void* full_hi
   void* lo[3] = {full_lo, half_lo, quarter_lo};
   for (int b = 0; b < 3; ++b) {
     const int step = 1 << b;
-    const long total = (long)B * (H / (2 * step)) * (W / (2 * step));
+    const long total = (long)B * (H / (2 * step)) * (W / (2 * step)) * 4;
     prep_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, step, (__nv_bfloat16*)hi[b],
                                                                               (__nv_bfloat16*)lo[b]);
     JCM_LAUNCH_CHECK();
@@ -144,7 +153,7 @@ extern "C" int jcm_pack_weights(const float* w, int ksize, int Cin, int Cout, in
 
 extern "C" int jcm_pack_weights_s2d(const float* w, int Cout, void* out_hi, void* out_lo, void* stream) {
   JCM_CHECK_ARG(w && out_hi && Cout > 0, "jcm_pack_weights_s2d: bad arguments");
-  pack_weights_s2d_kernel<<<grid_for(9L * Cout * 16, 256), 256, 0, (cudaStream_t)stream>>>(w, Cout, (__nv_bfloat16*)out_hi,
+  pack_weights_s2d_kernel<<<grid_for(3L * Cout * 64, 256), 256, 0, (cudaStream_t)stream>>>(w, Cout, (__nv_bfloat16*)out_hi,
                                                                                             (__nv_bfloat16*)out_lo);
   JCM_LAUNCH_CHECK();
   return JCM_OK;

@@ -228,7 +228,7 @@ def model(x, n_joints, p, ctx, tap=None):
 
     outs = []
     for xp, sfx in zip(banks, ('fullres', 'halfres', 'quarterres')):
-        a, ss = layer(xp, 'conv1_' + sfx, 3, 's2d')
+        a, ss = layer(xp, 'conv1_' + sfx, ops.S2D_KSIZE, 's2d')
         h = ops.bn_apply_pool(a, ss, True, split)
         a, ss = layer(h, 'conv2_' + sfx, 5)
         h = ops.bn_apply_pool(a, ss, True, split)

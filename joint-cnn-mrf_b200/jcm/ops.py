@@ -71,13 +71,21 @@ def _new_planes(shape, device, split):
 
 
 # ------------------------------------------------------------------------------------------------ preparation
+def _khw(ksize):
+    """kernel extent: int k (square) or (kh, kw)."""
+    return (int(ksize), int(ksize)) if isinstance(ksize, int) else (int(ksize[0]), int(ksize[1]))
+
+
+S2D_KSIZE = (3, 1)   # conv1_* (5x5 stride 2) over the x-folded space-to-depth planes of prep_input: 3 vertical taps x 64 channels
+
+
 def prep_input(x, split):
-    """x [B,H,W,3] fp32 -> (full, half, quarter) s2d operand planes [B,H/2,W/2,16], [B,H/4,W/4,16], [B,H/8,W/8,16]."""
+    """x [B,H,W,3] fp32 -> (full, half, quarter) x-folded s2d operand planes [B,H/2,W/2,64], [B,H/4,W/4,64], [B,H/8,W/8,64]."""
     _req(x, F32, 'x')
     B, H, W, C = x.shape
     if C != 3:
         raise ValueError('x must have 3 channels')
-    outs = [_new_planes((B, H // (2 * s), W // (2 * s), 16), x.device, split) for s in (1, 2, 4)]
+    outs = [_new_planes((B, H // (2 * s), W // (2 * s), 64), x.device, split) for s in (1, 2, 4)]
     check(lib().jcm_prep_input(_ptr(x), B, H, W, _ptr(outs[0].hi), _ptr(outs[0].lo), _ptr(outs[1].hi), _ptr(outs[1].lo),
                                _ptr(outs[2].hi), _ptr(outs[2].lo), _stream()), 'jcm_prep_input')
     return outs
@@ -105,11 +113,11 @@ def pack_weights(w, split, transpose=False):
 
 
 def pack_weights_s2d(w, split):
-    """conv1 kernels [5,5,3,Cout] -> [9, Cout, 16]."""
+    """conv1 kernels [5,5,3,Cout] -> [3, Cout, 64] (use with ksize = S2D_KSIZE)."""
     _req(w, F32, 'w')
     if tuple(w.shape[:3]) != (5, 5, 3) or w.shape[3] % 16:
         raise ValueError('pack_weights_s2d expects [5,5,3,Cout] with Cout a multiple of 16')
-    out = _new_planes((9, w.shape[3], 16), w.device, split)
+    out = _new_planes((3, w.shape[3], 64), w.device, split)
     check(lib().jcm_pack_weights_s2d(_ptr(w), w.shape[3], _ptr(out.hi), _ptr(out.lo), _stream()), 'jcm_pack_weights_s2d')
     return out
 
@@ -123,11 +131,13 @@ def split_planes(x, split):
 
 # ------------------------------------------------------------------------------------------------ part detector
 def conv2d_planes(xp, wp, bias, cout, ksize, relu, naive=False, alg_kdim=None):
-    """xp activation planes [B,H,W,Cin], wp packed weight planes [k*k,Cout_pad,Cin] -> fp32 [B,H,W,cout].
-    alg_kdim: contraction length of the ALGORITHMIC convolution (default k*k*Cin; 75 for the s2d conv1)."""
+    """xp activation planes [B,H,W,Cin], wp packed weight planes [kh*kw,Cout_pad,Cin] -> fp32 [B,H,W,cout].
+    ksize: int (square) or (kh, kw).  alg_kdim: contraction length of the ALGORITHMIC convolution (default kh*kw*Cin; 75 for
+    the s2d conv1)."""
     B, H, W, cin = xp.shape
     taps, cout_pad, cin_w = wp.shape
-    if cin_w != cin or taps != ksize * ksize:
+    kh, kw = _khw(ksize)
+    if cin_w != cin or taps != kh * kw:
         raise ValueError('weight planes %s do not match activation planes %s (ksize %d)' % (wp.shape, xp.shape, ksize))
     if (xp.lo is None) != (wp.lo is None):
         raise ValueError('activation and weight planes must use the same precision mode')
@@ -139,11 +149,11 @@ def conv2d_planes(xp, wp, bias, cout, ksize, relu, naive=False, alg_kdim=None):
     if prof:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    check(fn(_ptr(xp.hi), _ptr(xp.lo), _ptr(wp.hi), _ptr(wp.lo), _ptr(bias), _ptr(y), B, H, W, cin, cout, cout_pad, ksize,
+    check(fn(_ptr(xp.hi), _ptr(xp.lo), _ptr(wp.hi), _ptr(wp.lo), _ptr(bias), _ptr(y), B, H, W, cin, cout, cout_pad, kh, kw,
              int(relu), _stream()), 'jcm_conv2d_fwd')
     if prof:
         e1.record()
-        PROFILE.records.append((2.0 * B * H * W * (alg_kdim or ksize * ksize * cin) * cout, e0, e1))
+        PROFILE.records.append((2.0 * B * H * W * (alg_kdim or kh * kw * cin) * cout, e0, e1))
     return y
 
 

@@ -80,17 +80,19 @@ def pad_planes(x, cpad, split):
 
 
 def conv2d_wgrad(xp, gp, dw, cout, ksize):
-    """xp input planes [B,H,W,Cin], gp output-gradient planes [B,H,W,Gc] -> dw (contiguous fp32 [k*k, Cin, cout]) in place."""
+    """xp input planes [B,H,W,Cin], gp output-gradient planes [B,H,W,Gc] -> dw (contiguous fp32 [kh*kw, Cin, cout]) in place.
+    ksize: int (square) or (kh, kw)."""
     B, H, W, cin = xp.shape
     gc = gp.shape[3]
+    kh, kw = ops._khw(ksize)
     if tuple(gp.shape[:3]) != (B, H, W):
         raise ValueError('gradient planes %s do not match input planes %s' % (gp.shape, xp.shape))
-    if dw.numel() != ksize * ksize * cin * cout or not dw.is_contiguous():
-        raise ValueError('dw must be a contiguous [%d,%d,%d] tensor' % (ksize * ksize, cin, cout))
-    nbytes = lib().jcm_conv2d_wgrad_workspace(B, H, W, cin, gc, ksize)
+    if dw.numel() != kh * kw * cin * cout or not dw.is_contiguous():
+        raise ValueError('dw must be a contiguous [%d,%d,%d] tensor' % (kh * kw, cin, cout))
+    nbytes = lib().jcm_conv2d_wgrad_workspace(B, H, W, cin, gc, kh, kw)
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=dw.device)
     check(lib().jcm_conv2d_wgrad(_ptr(xp.hi), _ptr(xp.lo), _ptr(gp.hi), _ptr(gp.lo), _ptr(dw), _ptr(ws), nbytes, B, H, W, cin, gc, cout, cout,
-                                 ksize, _stream()), 'jcm_conv2d_wgrad')
+                                 kh, kw, _stream()), 'jcm_conv2d_wgrad')
     return dw
 
 
@@ -199,7 +201,7 @@ class Trainer:
         outs = []
         sfxs = ('fullres', 'halfres', 'quarterres')
         for xp, sfx in zip(banks, sfxs):
-            a, ss = fwd_layer(xp, 'conv1_' + sfx, 3, 's2d')
+            a, ss = fwd_layer(xp, 'conv1_' + sfx, ops.S2D_KSIZE, 's2d')
             h = ops.bn_apply_pool(a, ss, True, split)
             a, ss = fwd_layer(h, 'conv2_' + sfx, 5)
             h = ops.bn_apply_pool(a, ss, True, split)
@@ -248,8 +250,8 @@ class Trainer:
             d_pre = bn_relu_bwd(a, dout, ss, st, dy_scale, pool, split, g[name + '/BatchNorm/gamma'], g[name + '/BatchNorm/beta'],
                                 g[name + '/biases'])
             if name.startswith('conv1_'):
-                g9 = torch.empty((9, 16, cout), dtype=F32, device=dev)
-                conv2d_wgrad(xp, d_pre, g9, cout, 3)
+                g9 = torch.empty((3, 64, cout), dtype=F32, device=dev)
+                conv2d_wgrad(xp, d_pre, g9, cout, ops.S2D_KSIZE)
                 unpack_s2d_grad(g9, g[name + '/weights'])
             else:
                 conv2d_wgrad(xp, d_pre, g[name + '/weights'].view(ksize * ksize, cin, cout), cout, ksize)

@@ -98,7 +98,7 @@ def sec_conv():
             xd = x.double().cpu() if split else bf16_round(x).double().cpu()
             wd = w.double().cpu() if split else bf16_round(w).double().cpu()
             for bi, step in enumerate((1, 2, 4)):
-                y = ops.conv2d_planes(banks[bi], wp, b, 64, 3, relu=True)
+                y = ops.conv2d_planes(banks[bi], wp, b, 64, ops.S2D_KSIZE, relu=True)
                 ref = torch.relu(orc.conv2d(xd[:, ::step, ::step], wd, 2) + b.double().cpu())
                 print('CONV1 s2d bank %d split=%d: err %.2e  shape %s' % (bi, split, relerr(y, ref), tuple(y.shape)))
     except Exception as e:

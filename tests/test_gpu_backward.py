@@ -162,7 +162,8 @@ def test_conv2d_wgrad_and_dgrad(jcm, jtrain, case, split):
         assert rel(dx, x64.grad) < 2e-4
 
 
-@pytest.mark.parametrize('case', [(2, 12, 20, 64, 7, 9), (1, 60, 90, 128, 7, 9), (3, 9, 7, 32, 14, 5), (1, 15, 23, 512, 9, 9)])
+@pytest.mark.parametrize('case', [(2, 12, 20, 64, 7, 9), (1, 60, 90, 128, 7, 9), (3, 9, 7, 32, 14, 5), (1, 15, 23, 512, 9, 9),
+                                  (12, 60, 90, 64, 7, 9)])   # the last: many tiles per CTA (staging-buffer reuse in the TMA-store epilogue)
 @pytest.mark.parametrize('split', [False, True])
 def test_conv_taps_forward_wgrad_dgrad(jcm, jtrain, case, split):
     """The tap-expanded form used for conv6 (few output channels): forward, weight gradient and data gradient vs the oracle."""
@@ -206,8 +207,8 @@ def test_conv1_stride2_wgrad_via_space_to_depth(jcm, jtrain, split):
         w64 = w.double().requires_grad_(True)
         (orc.conv2d(xr.double(), w64, 2) * dyr.double()).sum().backward()
         gp = jcm.ops.split_planes(dy.cuda(), split)
-        g9 = torch.empty(9, 16, 64, device='cuda')
-        jtrain.conv2d_wgrad(banks[bi], gp, g9, 64, 3)
+        g9 = torch.empty(3, 64, 64, device='cuda')
+        jtrain.conv2d_wgrad(banks[bi], gp, g9, 64, jcm.ops.S2D_KSIZE)
         dw = torch.empty(5, 5, 3, 64, device='cuda')
         jtrain.unpack_s2d_grad(g9, dw)
         assert rel(dw, w64.grad) < 2e-4

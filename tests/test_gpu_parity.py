@@ -94,7 +94,7 @@ def test_conv1_stride2_via_space_to_depth(jcm, split):
     wp = jcm.ops.pack_weights_s2d(w.cuda(), split)
     xr, wr = (x, w) if split else (bf16r(x), bf16r(w))
     for bi, step in enumerate((1, 2, 4)):
-        y = jcm.ops.conv2d_planes(banks[bi], wp, b.cuda(), 64, 3, relu=True)
+        y = jcm.ops.conv2d_planes(banks[bi], wp, b.cuda(), 64, jcm.ops.S2D_KSIZE, relu=True)
         ref = torch.relu(orc.conv2d(xr.double()[:, ::step, ::step], wr.double(), 2) + b.double())
         assert tuple(y.shape) == tuple(ref.shape)
         assert rel(y, ref) < 5e-5
