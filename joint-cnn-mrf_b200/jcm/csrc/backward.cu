@@ -241,7 +241,6 @@ __global__ void upsample_bwd_kernel(const float* __restrict__ dm, int B, int H, 
                                     float* __restrict__ dlow) {
   const int C4 = C / 4;
   const long total = (long)B * Hi * Wi * C4;
-  const int ry = (H + Hi - 1) / Hi + 1, rx = (W + Wi - 1) / Wi + 1;   // how far a low-res pixel's footprint can reach
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int c4 = (int)(i % C4);
     long t = i / C4;
@@ -249,8 +248,10 @@ __global__ void upsample_bwd_kernel(const float* __restrict__ dm, int B, int H, 
     t /= Wi;
     const int pp = (int)(t % Hi);
     const int n = (int)(t / Hi);
-    const int ylo0 = max(0, (int)(((long)(pp - 1) * H) / Hi) - 1), yhi0 = min(H - 1, (int)(((long)(pp + 1) * H) / Hi) + ry);
-    const int xlo0 = max(0, (int)(((long)(q - 1) * W) / Wi) - 1), xhi0 = min(W - 1, (int)(((long)(q + 1) * W) / Wi) + rx);
+    // destination rows whose lo or hi tap can be pp: lo(y) = floor(y*Hi/H) in {pp-1, pp}  <=>  y in [(pp-1)*H/Hi, (pp+1)*H/Hi);
+    // one row of slack on each side covers the fp32 rounding of the tap computation (the weights are re-checked below)
+    const int ylo0 = max(0, (int)(((long)(pp - 1) * H) / Hi) - 1), yhi0 = min(H - 1, (int)(((long)(pp + 1) * H + Hi - 1) / Hi));
+    const int xlo0 = max(0, (int)(((long)(q - 1) * W) / Wi) - 1), xhi0 = min(W - 1, (int)(((long)(q + 1) * W + Wi - 1) / Wi));
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int y = ylo0; y <= yhi0; ++y) {
       int lo, hi;

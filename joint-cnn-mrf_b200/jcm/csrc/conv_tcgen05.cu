@@ -668,19 +668,40 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_m_hi, const __grid_con
   }
 }
 
-// dw[tap][ci][co] (+)= sum_split partial[split][tap][m][n],  (m, n) = (ci, co) when the input provided M, else (co, ci)
+// dw[tap][ci][co] = sum_split partial[split][tap][m][n],  (m, n) = (ci, co) when the input provided M, else (co, ci).
+// 32 x 32 tiles through shared memory so that both the partial reads (n fastest) and the dw writes (co fastest) are coalesced
+// in either orientation.  grid = (ceil(Cout/32), ceil(Cin/32), taps), block = (32, 8).
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int m_pad, int n_pad, int Cin, int Cout,
                                     int dw_cout_stride, int x_is_m, float* __restrict__ dw) {
-  const long total = (long)taps * Cin * Cout;
-  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int co = (int)(idx % Cout);
-    const long t = idx / Cout;
-    const int ci = (int)(t % Cin);
-    const int tap = (int)(t / Cin);
-    const int m = x_is_m ? ci : co, n = x_is_m ? co : ci;
-    float s = 0.f;
-    for (int sp = 0; sp < splits; ++sp) s += partial[(((long)sp * taps + tap) * m_pad + m) * n_pad + n];
-    dw[((long)tap * Cin + ci) * dw_cout_stride + co] = s;
+  __shared__ float tile[32][33];
+  const int tap = blockIdx.z;
+  const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 32;
+  const long split_stride = (long)taps * m_pad * n_pad;
+  const float* base = partial + (long)tap * m_pad * n_pad;
+  if (x_is_m) {
+    // rows m = ci, columns n = co: already co-fastest, no transpose needed
+    for (int r = threadIdx.y; r < 32; r += 8) {
+      const int ci = ci0 + r, co = co0 + threadIdx.x;
+      if (ci < Cin && co < Cout) {
+        float s = 0.f;
+        for (int sp = 0; sp < splits; ++sp) s += base[sp * split_stride + (long)ci * n_pad + co];
+        dw[((long)tap * Cin + ci) * dw_cout_stride + co] = s;
+      }
+    }
+  } else {
+    // rows m = co, columns n = ci: read ci-fastest, transpose, write co-fastest
+    for (int r = threadIdx.y; r < 32; r += 8) {
+      const int co = co0 + r, ci = ci0 + threadIdx.x;
+      float s = 0.f;
+      if (ci < Cin && co < Cout)
+        for (int sp = 0; sp < splits; ++sp) s += base[sp * split_stride + (long)co * n_pad + ci];
+      tile[r][threadIdx.x] = s;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+      const int ci = ci0 + r, co = co0 + threadIdx.x;
+      if (ci < Cin && co < Cout) dw[((long)tap * Cin + ci) * dw_cout_stride + co] = tile[threadIdx.x][r];
+    }
   }
 }
 
@@ -813,11 +834,8 @@ extern "C" int jcm_conv2d_wgrad(const void* x_hi, const void* x_lo, const void* 
   JCM_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512));
   conv_wgrad_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(mm_hi, mm_lo, mn_hi, mn_lo, p);
   JCM_LAUNCH_CHECK();
-  const long total = (long)p.taps * Cin * Cout;
-  long rg = (total + 255) / 256;
-  if (rg > (long)jcm_num_sms() * 16) rg = (long)jcm_num_sms() * 16;
-  wgrad_reduce_kernel<<<(int)rg, 256, 0, (cudaStream_t)stream>>>(p.partial, p.splits, p.taps, p.m_pad, p.n_pad, Cin, Cout, dw_cout_stride,
-                                                                 pl.x_is_m, dw);
+  wgrad_reduce_kernel<<<dim3(jcm_cdiv(Cout, 32), jcm_cdiv(Cin, 32), p.taps), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      p.partial, p.splits, p.taps, p.m_pad, p.n_pad, Cin, Cout, dw_cout_stride, pl.x_is_m, dw);
   JCM_LAUNCH_CHECK();
   return JCM_OK;
 }

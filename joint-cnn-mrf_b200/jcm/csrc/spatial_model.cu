@@ -735,30 +735,58 @@ __global__ void sm_bwd_dh_kernel(const float* __restrict__ hm, const float* __re
   }
 }
 
-// batch-norm backward over [M, KC], one CTA per channel (tiny tensor).  train: batch statistics; else d_in = scale * dy.
-__global__ void sm_bn_bwd_kernel(const float* __restrict__ hm, const float* __restrict__ dy, const float* __restrict__ scale,
-                                 const float* __restrict__ mean, const float* __restrict__ rstd, long M, int KC, int train,
-                                 float* __restrict__ d_in, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  __shared__ float sh[2][32];
-  const int j = blockIdx.x;
-  const float mu = mean ? mean[j] : 0.f, rs = rstd ? rstd[j] : 1.f;
-  double s0 = 0.0, s1 = 0.0;
-  for (long r = threadIdx.x; r < M; r += blockDim.x) {
-    const float dv = dy[r * KC + j];
-    s0 += dv;
-    s1 += dv * ((hm[r * KC + j] - mu) * rs);
+// batch-norm backward over [M, KC] (KC = K+1 <= 32 channels).  Pass 1: per-block partial sums of dy and dy*xhat
+// (block = 32 rows x KC... threads (c, r)); pass 2: totals (fixed order) + d_in = scale * (dy - mean(dy) - xhat * mean(dy*xhat)).
+constexpr int BNB_THREADS = 256;
+__global__ void sm_bn_bwd_partial_kernel(const float* __restrict__ hm, const float* __restrict__ dy, const float* __restrict__ mean,
+                                         const float* __restrict__ rstd, long M, int KC, float* __restrict__ partial /*[grid][2][KC]*/) {
+  __shared__ float sh[2][BNB_THREADS];
+  const int lanes = BNB_THREADS / KC;            // rows handled in parallel
+  const int c = threadIdx.x % KC, rl = threadIdx.x / KC;
+  const long per_blk = (M + gridDim.x - 1) / gridDim.x;
+  const long r0 = blockIdx.x * per_blk;
+  long r1 = r0 + per_blk;
+  if (r1 > M) r1 = M;
+  float s0 = 0.f, s1 = 0.f;
+  if (rl < lanes) {
+    const float mu = mean ? mean[c] : 0.f, rs = rstd ? rstd[c] : 1.f;
+    for (long r = r0 + rl; r < r1; r += lanes) {
+      const float dv = dy[r * KC + c];
+      s0 += dv;
+      s1 += dv * ((hm[r * KC + c] - mu) * rs);
+    }
   }
-  float a = warp_sum((float)s0), b = warp_sum((float)s1);
-  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a; sh[1][threadIdx.x >> 5] = b; }
+  sh[0][threadIdx.x] = s0;
+  sh[1][threadIdx.x] = s1;
   __syncthreads();
-  float ta = 0.f, tb = 0.f;
-  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { ta += sh[0][i]; tb += sh[1][i]; }
-  if (threadIdx.x == 0) { dbeta[j] = ta; dgamma[j] = tb; }
-  const float sc = scale[j];
-  const float m0 = train ? ta / (float)M : 0.f, m1 = train ? tb / (float)M : 0.f;
-  for (long r = threadIdx.x; r < M; r += blockDim.x) {
-    const float xh = (hm[r * KC + j] - mu) * rs;
-    d_in[r * KC + j] = sc * (dy[r * KC + j] - m0 - xh * m1);
+  if (threadIdx.x < KC) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int l = 0; l < lanes; ++l) { t0 += sh[0][l * KC + threadIdx.x]; t1 += sh[1][l * KC + threadIdx.x]; }
+    partial[((long)blockIdx.x * 2 + 0) * KC + threadIdx.x] = t0;
+    partial[((long)blockIdx.x * 2 + 1) * KC + threadIdx.x] = t1;
+  }
+}
+
+__global__ void sm_bn_bwd_apply_kernel(const float* __restrict__ hm, const float* __restrict__ dy, const float* __restrict__ scale,
+                                       const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ partial,
+                                       int nblocks, long M, int KC, int train, float* __restrict__ d_in, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta) {
+  __shared__ float tot[2][32];
+  if (threadIdx.x < 2 * KC) {
+    const int j = threadIdx.x / KC, c = threadIdx.x % KC;
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += (double)partial[((long)b * 2 + j) * KC + c];
+    tot[j][c] = (float)s;
+    if (blockIdx.x == 0) { if (j == 0) dbeta[c] = (float)s; else dgamma[c] = (float)s; }
+  }
+  __syncthreads();
+  const long total = M * KC;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % KC);
+    const float mu = mean ? mean[c] : 0.f, rs = rstd ? rstd[c] : 1.f;
+    const float m0 = train ? tot[0][c] / (float)M : 0.f, m1 = train ? tot[1][c] / (float)M : 0.f;
+    const float xh = (hm[i] - mu) * rs;
+    d_in[i] = scale[c] * (dy[i] - m0 - xh * m1);
   }
 }
 
@@ -790,6 +818,7 @@ extern "C" int jcm_spatial_model_bwd(const float* g, const float* heat_map, cons
   JCM_CHECK_ARG(g && heat_map && bn_scale && bn_shift && energies && biases && pair_target && pair_cond && fwd_workspace && workspace &&
                     d_heat_map && dE && db && dgamma && dbeta, "jcm_spatial_model_bwd: null pointer");
   JCM_CHECK_ARG(!train || (bn_mean && bn_rstd), "jcm_spatial_model_bwd: training mode needs the saved batch statistics");
+  JCM_CHECK_ARG(K + 1 <= 32, "jcm_spatial_model_bwd: at most 31 joints are supported (got %d)", K);
   if (workspace_bytes < jcm_spatial_model_bwd_workspace(B, H, W, K, P)) {
     jcm_set_error("jcm_spatial_model_bwd: workspace too small");
     return JCM_EWORKSPACE;
@@ -856,8 +885,14 @@ extern "C" int jcm_spatial_model_bwd(const float* g, const float* heat_map, cons
     const long total = (long)B * H * W * (K + 1);
     sm_bwd_dh_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(heat_map, bn_scale, bn_shift, g, dLf, pair_cond, df, dh);
     JCM_LAUNCH_CHECK();
-    sm_bn_bwd_kernel<<<K + 1, 1024, 0, st>>>(heat_map, dh, bn_scale, bn_mean, bn_rstd, (long)B * H * W, K + 1, train, d_heat_map, dgamma,
-                                             dbeta);
+    const long Mr = (long)B * H * W;
+    int nb = (int)((Mr + 255) / 256);
+    if (nb > 2 * jcm_num_sms()) nb = 2 * jcm_num_sms();
+    float* bnpart = part;   // the dP partial buffer is free again (its finish kernel ran above): reuse its first 2*nb*(K+1) floats
+    sm_bn_bwd_partial_kernel<<<nb, BNB_THREADS, 0, st>>>(heat_map, dh, bn_mean, bn_rstd, Mr, K + 1, bnpart);
+    JCM_LAUNCH_CHECK();
+    sm_bn_bwd_apply_kernel<<<2 * jcm_num_sms(), 256, 0, st>>>(heat_map, dh, bn_scale, bn_mean, bn_rstd, bnpart, nb, Mr, K + 1, train,
+                                                             d_heat_map, dgamma, dbeta);
     JCM_LAUNCH_CHECK();
   }
   return JCM_OK;
