@@ -7,3 +7,4 @@ from .graph import (Context, PairwiseParams, JOINT_NAMES, model, spatial_model, 
                     get_joints_coords, det_rate, get_pairwise_distr, init_part_detector, load_params, tower_forward,
                     n_filters, conv_specs)
 from . import train  # noqa: F401,E402  (Trainer: the data-parallel training step, main.py:474-577)
+from .feed import DeviceFeed  # noqa: F401,E402

@@ -43,14 +43,30 @@ class _ConvProfile:
     def clear(self):
         self.records = []
 
-    def summary(self, steps=None):
+    def add(self, kernel, flops, e0, e1):
+        self.records.append((kernel, flops, e0, e1))
+
+    def summary(self, steps=None, kernel=None):
+        """Aggregate over the recorded launches of `kernel` (all if None): algorithmic FLOPs / summed CUDA-event time."""
         torch.cuda.synchronize()
-        ms = sum(e0.elapsed_time(e1) for _, e0, e1 in self.records)
-        fl = sum(f for f, _, _ in self.records)
-        n = len(self.records)
+        recs = [r for r in self.records if kernel is None or r[0] == kernel]
+        ms = sum(e0.elapsed_time(e1) for _, _, e0, e1 in recs)
+        fl = sum(f for _, f, _, _ in recs)
+        n = len(recs)
         steps = steps or 1
         return {'launches': n, 'launches_per_step': n // steps if steps else n, 'ms_total': ms, 'ms_per_step': ms / steps,
                 'tflops': (fl / (ms * 1e-3) / 1e12) if ms > 0 else 0.0, 'flops_per_step': fl / steps}
+
+    def largest(self, kernel):
+        """The launch shape with the most FLOPs: (flops per launch, mean ms per launch, launches)."""
+        torch.cuda.synchronize()
+        recs = [r for r in self.records if r[0] == kernel]
+        if not recs:
+            return None
+        fmax = max(r[1] for r in recs)
+        big = [r for r in recs if r[1] == fmax]
+        ms = sum(e0.elapsed_time(e1) for _, _, e0, e1 in big) / len(big)
+        return {'flops': fmax, 'ms': ms, 'launches': len(big), 'tflops': fmax / (ms * 1e-3) / 1e12}
 
 
 PROFILE = _ConvProfile()
@@ -153,7 +169,7 @@ def conv2d_planes(xp, wp, bias, cout, ksize, relu, naive=False, alg_kdim=None):
              int(relu), _stream()), 'jcm_conv2d_fwd')
     if prof:
         e1.record()
-        PROFILE.records.append((2.0 * B * H * W * (alg_kdim or kh * kw * cin) * cout, e0, e1))
+        PROFILE.add('conv_igemm_kernel', 2.0 * B * H * W * (alg_kdim or kh * kw * cin) * cout, e0, e1)
     return y
 
 

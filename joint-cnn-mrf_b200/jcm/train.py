@@ -79,7 +79,7 @@ def pad_planes(x, cpad, split):
     return out
 
 
-def conv2d_wgrad(xp, gp, dw, cout, ksize):
+def conv2d_wgrad(xp, gp, dw, cout, ksize, alg_flops=None):
     """xp input planes [B,H,W,Cin], gp output-gradient planes [B,H,W,Gc] -> dw (contiguous fp32 [kh*kw, Cin, cout]) in place.
     ksize: int (square) or (kh, kw)."""
     B, H, W, cin = xp.shape
@@ -91,8 +91,15 @@ def conv2d_wgrad(xp, gp, dw, cout, ksize):
         raise ValueError('dw must be a contiguous [%d,%d,%d] tensor' % (kh * kw, cin, cout))
     nbytes = lib().jcm_conv2d_wgrad_workspace(B, H, W, cin, gc, kh, kw)
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=dw.device)
+    prof = ops.PROFILE.enabled
+    if prof:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(lib().jcm_conv2d_wgrad(_ptr(xp.hi), _ptr(xp.lo), _ptr(gp.hi), _ptr(gp.lo), _ptr(dw), _ptr(ws), nbytes, B, H, W, cin, gc, cout, cout,
                                  kh, kw, _stream()), 'jcm_conv2d_wgrad')
+    if prof:
+        e1.record()   # includes the (small) deterministic split reduction kernel that follows the GEMM
+        ops.PROFILE.add('conv_wgrad_kernel', alg_flops if alg_flops is not None else 2.0 * B * H * W * kh * kw * cin * cout, e0, e1)
     return dw
 
 
@@ -238,7 +245,7 @@ class Trainer:
         kp, zc, npad = ops.tap_layout(9, K)
         gt6 = ops.tap_scatter_planes(d_logit, 9, split)
         dwz = torch.empty((1, c5, zc), dtype=F32, device=dev)
-        conv2d_wgrad(h5, gt6, dwz, zc, 1)
+        conv2d_wgrad(h5, gt6, dwz, zc, 1, alg_flops=2.0 * B * h5.shape[1] * h5.shape[2] * 81 * c5 * K)
         ops.unpack_tap_grad(dwz, 9, c5, K, g['conv6/weights'])
         colsum(d_logit, g['conv6/biases'])
         dh = ops.conv2d_planes(gt6, ctx.packed('conv6', w6, 'taps_dgrad'), None, c5, 1, relu=False, alg_kdim=81 * K)
@@ -251,7 +258,7 @@ class Trainer:
                                 g[name + '/biases'])
             if name.startswith('conv1_'):
                 g9 = torch.empty((3, 64, cout), dtype=F32, device=dev)
-                conv2d_wgrad(xp, d_pre, g9, cout, ops.S2D_KSIZE)
+                conv2d_wgrad(xp, d_pre, g9, cout, ops.S2D_KSIZE, alg_flops=2.0 * B * xp.shape[1] * xp.shape[2] * 75 * cout)
                 unpack_s2d_grad(g9, g[name + '/weights'])
             else:
                 conv2d_wgrad(xp, d_pre, g[name + '/weights'].view(ksize * ksize, cin, cout), cout, ksize)

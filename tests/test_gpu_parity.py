@@ -368,3 +368,19 @@ def test_batch_16_forward_is_batch_independent(jcm):
     o2 = jcm.model(x2, K, p, ctx)
     o16 = jcm.model(x16, K, p, ctx)
     assert torch.equal(o16[:2], o2) and torch.equal(o16[14:], o2)
+
+
+def test_device_feed_overlapped_copies(jcm):
+    """jcm.DeviceFeed (the replacement of the reference's feed_dict host->device copy, main.py:648): contents arrive intact."""
+    feed = jcm.DeviceFeed('cuda:0')
+    g = torch.Generator().manual_seed(3)
+    for i in range(3):
+        x = torch.rand(2, 48, 80, 3, generator=g).pin_memory()
+        y = torch.rand(2, 6, 10, 8, generator=g).pin_memory()
+        feed.submit(x, y)
+        xd, yd = feed.take()
+        assert torch.equal(xd.cpu(), x) and torch.equal(yd.cpu(), y)
+    with pytest.raises(ValueError):
+        feed.submit(torch.zeros(4))          # not pinned
+    with pytest.raises(RuntimeError):
+        feed.take()
