@@ -18,6 +18,7 @@
 //     (tcgen05.ld -> +bias -> ReLU -> fp32 NHWC store).  Persistent grid, one CTA per SM.
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -33,6 +34,16 @@ struct ConvParams {
   int stages, a_bytes, b_bytes, stage_bytes;
   int relu;
   int tma_store;        // 1: epilogue stages 32-column chunks in swizzled shared memory and writes them with TMA stores
+  // halo mode (layers whose A operand traffic is the limiter: N <= 128): the A tile is loaded ONCE per (dx, channel block) as a
+  // (TH + kh - 1)-row halo patch and the kh vertical taps address it at row offsets dy*TW (a multiple of the 8-row swizzle
+  // period, so the UMMA descriptor just moves its start address); weights stream through their own ring, one tap at a time.
+  int halo, a_stages, b_stages, a_halo_bytes, a_stride, b_stride;
+  int mma_split_n;      // measurement switch (JCM_MMA_SPLITN): issue every MMA as two independent half-N MMAs
+  int nacc;             // independent accumulators per tile (K steps are dealt round-robin to them and summed in the epilogue):
+                        // back-to-back tcgen05.mma into the SAME TMEM tile serialise at ~170 clk each whatever N is, so for
+                        // N <= 128 the tensor pipe idles unless consecutive MMAs target different accumulators
+  int dbg;              // measurement switches (JCM_CONV_DBG bit 0: epilogue releases TMEM without storing, bit 1: no MMAs issued,
+                        // bit 2: producer skips the B loads) - results are garbage, timing only
   const float* bias;
   float* y;
 };
@@ -88,6 +99,13 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// one lane of a converged warp (elect.sync): unlike `lane == 0` the compiler knows the region is executed by a single thread
+// and emits the uniform-datapath instructions (UTCHMMA / UTMALDG / UTCBAR) directly instead of wrapping each in an election loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -134,7 +152,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                   const __grid_constant__ CUtensorMap map_y, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
+  __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 4];
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -143,11 +161,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
   const uint32_t bar_empty = smem_u32(&bars[kMaxStages]);
   const uint32_t bar_tfull = smem_u32(&bars[2 * kMaxStages]);
   const uint32_t bar_tempty = smem_u32(&bars[2 * kMaxStages + 2]);
+  const uint32_t bar_afull = smem_u32(&bars[2 * kMaxStages + 4]);          // halo mode: ring of A halo tiles
+  const uint32_t bar_aempty = smem_u32(&bars[3 * kMaxStages + 4]);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) {
+    for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_afull + 8 * s, 1);
+      mbar_init(bar_aempty + 8 * s, 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
@@ -168,10 +190,85 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
   const int total_tiles = m_tiles * p.n_tiles;
   const int taps = p.ksize * p.kw;
   const int num_kb = taps * p.cblocks * p.terms;
+  const uint32_t smem_b0 = smem_base + p.a_stages * p.a_stride;     // halo mode: start of the weight ring
 
-  if (warp == 0) {
+  if (warp == 0 && p.halo) {
+    // ===================== TMA producer, halo mode (map_a_lo carries the halo-box tensor map) =====================
+    if (elect_one()) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile / m_tiles, mt = tile - nt * m_tiles;
+        const int img = mt / (p.tiles_y * p.tiles_x);
+        const int r = mt - img * (p.tiles_y * p.tiles_x);
+        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        const int x0 = tx * p.TW - p.pad_x, y0 = ty * p.TH - p.pad;
+        for (int dx = 0; dx < p.kw; ++dx) {
+          for (int cb = 0; cb < p.cblocks; ++cb) {
+            mbar_wait(bar_aempty + 8 * sa, pa ^ 1);
+            mbar_expect_tx(bar_afull + 8 * sa, p.a_halo_bytes);
+            tma_load_4d(smem_base + sa * p.a_stride, &map_a_lo, bar_afull + 8 * sa, cb * p.kc, x0 + dx, y0, img);
+            if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+            for (int dy = 0; dy < p.ksize; ++dy) {
+              mbar_wait(bar_empty + 8 * sb, pb ^ 1);
+              if (p.dbg & 4) {
+                mbar_arrive(bar_full + 8 * sb);
+              } else {
+                mbar_expect_tx(bar_full + 8 * sb, p.b_bytes);
+                tma_load_3d(smem_b0 + sb * p.b_stride, &map_b_hi, bar_full + 8 * sb, cb * p.kc, nt * p.block_n, dy * p.kw + dx);
+              }
+              if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && p.halo) {
+    // ===================== MMA issuer, halo mode =====================
+    if (elect_one()) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      const uint32_t row_bytes = p.kc * 2;
+      const uint32_t layout = (p.kc == 64) ? 2u : (p.kc == 32 ? 4u : 6u);
+      const uint32_t sbo = 8 * row_bytes;
+      const uint32_t dy_bytes = (uint32_t)p.TW * row_bytes;     // one patch row of the halo tile; TW % 8 == 0 keeps the swizzle phase
+      const int kk = p.kc / 16;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        uint32_t accumulate = 0, mcount = 0;
+        for (int it = 0; it < p.kw * p.cblocks; ++it) {
+          mbar_wait(bar_afull + 8 * sa, pa);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + sa * p.a_stride;
+          for (int dy = 0; dy < p.ksize; ++dy) {
+            mbar_wait(bar_full + 8 * sb, pb);
+            tc_fence_after();
+            const uint64_t adesc = make_smem_desc(a_addr + dy * dy_bytes, sbo, layout);
+            const uint64_t bdesc = make_smem_desc(smem_b0 + sb * p.b_stride, sbo, layout);
+            if (!(p.dbg & 2))
+            for (int k = 0; k < kk; ++k) {
+              const int j = (mcount++) & (p.nacc - 1);
+              tc_mma_bf16(d_tmem + j * p.block_n, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (accumulate >> j) & 1u);
+              accumulate |= 1u << j;
+            }
+            tc_commit(bar_empty + 8 * sb);
+            if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+          }
+          tc_commit(bar_aempty + 8 * sa);
+          if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+        }
+        tc_commit(bar_tfull + 8 * acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -188,9 +285,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
               const uint32_t sa = smem_base + stage * p.stage_bytes;
               const uint32_t sb = sa + p.a_bytes;
               const uint32_t fb = bar_full + 8 * stage;
-              mbar_expect_tx(fb, p.a_bytes + p.b_bytes);
+              mbar_expect_tx(fb, (p.dbg & 4) ? p.a_bytes : p.a_bytes + p.b_bytes);
               tma_load_4d(sa, term == 1 ? &map_a_lo : &map_a_hi, fb, cb * p.kc, x0 + dx, y0 + dy, img);
-              tma_load_3d(sb, term == 2 ? &map_b_lo : &map_b_hi, fb, cb * p.kc, nt * p.block_n, tap);
+              if (!(p.dbg & 4)) tma_load_3d(sb, term == 2 ? &map_b_lo : &map_b_hi, fb, cb * p.kc, nt * p.block_n, tap);
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -199,7 +296,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N = block_n, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
       const uint32_t row_bytes = p.kc * 2;                  // 128, 64 or 32 = the swizzle span
@@ -214,15 +311,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
+        uint32_t accumulate = 0, mcount = 0;     // bit j: accumulator j of this tile has been written; MMAs are dealt round-robin
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * p.stage_bytes;
           const uint64_t adesc = make_smem_desc(sa, sbo, layout);
           const uint64_t bdesc = make_smem_desc(sa + p.a_bytes, sbo, layout);
+          if (p.dbg & 2) {
+          } else if (p.mma_split_n) {
+            // experiment: two independent half-N MMAs per K step (different TMEM columns, B rows n/2.. of the same stage)
+            const uint32_t hn = p.block_n / 2;
+            const uint32_t idesc_h = (idesc & ~(0x3Fu << 17)) | ((hn >> 3) << 17);
+            const uint64_t bdesc2 = make_smem_desc(sa + p.a_bytes + hn * row_bytes, sbo, layout);
+            for (int k = 0; k < kk; ++k) {
+              tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_h, (kb | k) != 0);
+              tc_mma_bf16(d_tmem + hn, adesc + (uint64_t)(2 * k), bdesc2 + (uint64_t)(2 * k), idesc_h, (kb | k) != 0);
+            }
+          } else
           for (int k = 0; k < kk; ++k) {
             // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the 16-byte address field
-            tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            const int j = (mcount++) & (p.nacc - 1);
+            tc_mma_bf16(d_tmem + j * p.block_n, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (accumulate >> j) & 1u);
+            accumulate |= 1u << j;
           }
           tc_commit(bar_empty + 8 * stage);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -250,10 +361,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
-      if (p.tma_store) {
+      if (p.dbg & 1) {
+        // timing experiment: no stores
+      } else if (p.tma_store) {
         // coalesced epilogue: 32-column chunks go through two 16 KB swizzled staging buffers and out with TMA stores (the box
         // {32 ch, TW, TH, 1} has the A operand's pixel order, so accumulator row == staging row; ragged edges are clipped by TMA)
-        const uint32_t stage0 = smem_base + p.stages * p.stage_bytes;
+        const uint32_t stage0 = p.halo ? smem_b0 + p.b_stages * p.b_stride : smem_base + p.stages * p.stage_bytes;
         for (int c0 = 0; c0 < p.block_n; c0 += 32) {
           const uint32_t buf = stage0 + (uint32_t)(epi_chunk & 1) * (kTileM * 128);
           if (threadIdx.x == 128) bulk_wait_read<1>();     // the store that last read this buffer is done with it
@@ -261,6 +374,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
           uint32_t v[32];
           tc_ld32(taddr0 + c0, v);
           tc_ld_wait();
+          for (int j = 1; j < p.nacc; ++j) {
+            uint32_t u[32];
+            tc_ld32(taddr0 + j * p.block_n + c0, u);
+            tc_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(u[e]));
+          }
           const int co0 = nt * p.block_n + c0;
           const uint32_t rowaddr = buf + (uint32_t)row * 128;
 #pragma unroll
@@ -289,6 +409,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
           uint32_t v[32];
           tc_ld32(taddr0 + c0, v);
           tc_ld_wait();
+          for (int j = 1; j < p.nacc; ++j) {
+            uint32_t u[32];
+            tc_ld32(taddr0 + j * p.block_n + c0, u);
+            tc_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(u[e]));
+          }
           const int co0 = nt * p.block_n + c0;
           if (valid) {
             if (((p.Cout & 3) == 0) && (co0 + 32 <= p.Cout)) {
@@ -383,6 +510,8 @@ static void pick_patch(int H, int W, int* TW, int* TH) {
   }
   *TW = bw;
   *TH = bh;
+  static const int force = getenv("JCM_CONV_PATCH_TW") ? atoi(getenv("JCM_CONV_PATCH_TW")) : 0;   // measurement switch
+  if (force > 0 && 128 % force == 0) { *TW = force; *TH = 128 / force; }
 }
 
 extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
@@ -421,6 +550,35 @@ extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_
   const int epi_bytes = p.tma_store ? 2 * kTileM * 128 : 0;     // two staging buffers of 128 rows x 32 fp32
   p.stages = (225 * 1024 - epi_bytes) / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
+  // halo mode where the A operand's L2 traffic is the limiter (few output channels per A tile) and the taps have vertical extent
+  p.halo = 0;
+  static const int splitn_env = getenv("JCM_MMA_SPLITN") ? atoi(getenv("JCM_MMA_SPLITN")) : 0;
+  p.mma_split_n = splitn_env && (p.block_n % 32) == 0;
+  {
+    static const int nacc_env = getenv("JCM_CONV_NACC") ? atoi(getenv("JCM_CONV_NACC")) : 0;   // 2 enables (measurement)
+    const int mmas_per_tile = ksize * kw * p.cblocks * p.terms * (p.kc / 16);
+    // measured (profiles/r01/conv_sweep_r01.txt): once the MMA warp issues through elect.sync the round-robin accumulators no longer
+    // help (the serialisation seen before was the issuing thread, not the tensor pipe), so they stay off unless JCM_CONV_NACC=2
+    p.nacc = 1;
+    if (nacc_env >= 2) {
+      if (p.block_n <= 128 && mmas_per_tile >= 2) p.nacc = 2;
+      if (p.block_n <= 64 && mmas_per_tile >= 4) p.nacc = 4;
+    }
+    if (p.mma_split_n) p.nacc = 1;
+  }
+  static const int dbg_env = getenv("JCM_CONV_DBG") ? atoi(getenv("JCM_CONV_DBG")) : 0;
+  p.dbg = dbg_env;
+  p.a_stages = 0; p.b_stages = 0; p.a_stride = 0; p.b_stride = 0; p.a_halo_bytes = 0;
+  static const int halo_env = getenv("JCM_CONV_HALO") ? atoi(getenv("JCM_CONV_HALO")) : 1;   // 0 disables (for A/B measurements)
+  if (halo_env && p.terms == 1 && ksize >= 3 && p.block_n <= (halo_env > 1 ? 256 : 128) && (p.TW % 8) == 0) {
+    p.a_halo_bytes = (p.TH + ksize - 1) * p.TW * p.kc * 2;
+    p.a_stride = ((p.a_halo_bytes + 1023) / 1024) * 1024;
+    p.b_stride = ((p.b_bytes + 1023) / 1024) * 1024;
+    p.a_stages = 3;
+    p.b_stages = (225 * 1024 - epi_bytes - p.a_stages * p.a_stride) / p.b_stride;
+    if (p.b_stages > kMaxStages) p.b_stages = kMaxStages;
+    p.halo = p.b_stages >= 4;
+  }
   p.relu = relu;
   p.bias = bias;
   p.y = y;
@@ -433,6 +591,7 @@ extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_
     uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)p.TW, (uint32_t)p.TH, 1};
     int rc = make_map(&ma_hi, x_hi, 4, dims, str, box, swz);
     if (rc) return rc;
+    if (p.halo) box[2] = (uint32_t)(p.TH + ksize - 1);   // halo mode: the (unused) lo slot carries the halo-box map of x_hi
     rc = make_map(&ma_lo, x_lo ? x_lo : x_hi, 4, dims, str, box, swz);
     if (rc) return rc;
   }
@@ -459,7 +618,7 @@ extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_
   const int total_tiles = B * p.tiles_x * p.tiles_y * p.n_tiles;
   int grid = jcm_num_sms();
   if (grid > total_tiles) grid = total_tiles;
-  const size_t smem = (size_t)p.stages * p.stage_bytes + epi_bytes + 1024;
+  const size_t smem = (p.halo ? (size_t)p.a_stages * p.a_stride + (size_t)p.b_stages * p.b_stride : (size_t)p.stages * p.stage_bytes) + epi_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     JCM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512));
@@ -541,7 +700,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_m_hi, const __grid_con
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int task = blockIdx.x; task < total_tasks; task += gridDim.x) {
@@ -582,7 +741,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_m_hi, const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       // D=f32, A=B=bf16, both MN-major (bits 15, 16), N = block_n, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.block_n >> 3) << 17) |
                              ((uint32_t)(kTileM >> 4) << 24);

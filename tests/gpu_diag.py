@@ -427,6 +427,21 @@ def sec_wgtime():
         print('WGTIME %-20s B=%d: wgrad %.3f ms %.0f TFLOP/s | fwd %.3f ms %.0f TFLOP/s' % (name, B, bw, fl / bw / 1e9, bf, fl / bf / 1e9))
 
 
+def sec_convsweep():
+    """Forward conv time per k-block for small-N layers (what bounds them?)."""
+    gen = torch.Generator().manual_seed(7)
+    for (B, H, W, Cin, Cout, k) in [(32, 120, 180, 64, 64, 5), (32, 120, 180, 64, 128, 5), (32, 120, 180, 64, 256, 5), (32, 120, 180, 128, 64, 5),
+                                    (32, 60, 90, 256, 128, 5), (32, 60, 90, 128, 256, 5), (16, 60, 90, 512, 512, 9)]:
+        x = ops.split_planes(torch.randn(B, H, W, Cin, generator=gen).to(dev), False)
+        w = ops.pack_weights((torch.randn(k, k, Cin, Cout, generator=gen) / 30).to(dev), False)
+        fl = 2.0 * B * H * W * k * k * Cin * Cout
+        bf, _ = timeit(lambda: ops.conv2d_planes(x, w, None, Cout, k, False), n=3, warm=1)
+        tiles = B * ((H + 7) // 8) * ((W + 15) // 16) * max(1, Cout // 256)
+        kb = tiles * k * k * (Cin // 64)
+        print('CONVSWEEP B%d %dx%d Cin%d Cout%d k%d: %.3f ms %.0f TFLOP/s  ~%.0f clk/k-block (at 1.9 GHz, %d k-blocks/SM)' % (
+            B, H, W, Cin, Cout, k, bf, fl / bf / 1e9, bf * 1e-3 * 1.9e9 / (kb / 148.0), kb // 148))
+
+
 def sec_smtime():
     K = 7
     names = jcm.JOINT_NAMES[:K] + ['torso']
