@@ -748,6 +748,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_m_hi, const __grid_con
       const uint32_t n_row_bytes = p.kc_n * 2, m_row_bytes = p.kc_m * 2;
       const uint32_t n_layout = (p.kc_n == 64) ? 2u : (p.kc_n == 32 ? 4u : 6u);
       const uint32_t m_layout = (p.kc_m == 64) ? 2u : (p.kc_m == 32 ? 4u : 6u);
+      const uint64_t adesc_hi = (make_smem_desc(0, 8 * m_row_bytes, m_layout) & ~(((uint64_t)0x3FFF << 16) | 0x3FFF)) |
+                                ((uint64_t)((m_box_bytes >> 4) & 0x3FFF) << 16);
+      const uint64_t bdesc_hi = (make_smem_desc(0, 8 * n_row_bytes, n_layout) & ~(((uint64_t)0x3FFF << 16) | 0x3FFF)) |
+                                ((uint64_t)((n_box_bytes >> 4) & 0x3FFF) << 16);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -765,13 +769,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_m_hi, const __grid_con
           tc_fence_after();
           const uint32_t sa = smem_base + stage * p.stage_bytes;
           const uint32_t sb = sa + p.a_bytes;
+          // MN-major descriptors: leading byte offset = distance between channel blocks (one box), stride byte offset = 8 pixel rows;
+          // only the start address changes between stages / K steps, so the upper words are built once (adesc_hi / bdesc_hi)
 #pragma unroll
           for (int k = 0; k < kWgPix / 16; ++k) {
-            // MN-major: leading byte offset = distance between channel blocks (one TMA box), stride byte offset = 8 pixel rows
-            uint64_t adesc = make_smem_desc(sa + k * 16 * m_row_bytes, 8 * m_row_bytes, m_layout);
-            adesc = (adesc & ~((uint64_t)0x3FFF << 16)) | ((uint64_t)((m_box_bytes >> 4) & 0x3FFF) << 16);
-            uint64_t bdesc = make_smem_desc(sb + k * 16 * n_row_bytes, 8 * n_row_bytes, n_layout);
-            bdesc = (bdesc & ~((uint64_t)0x3FFF << 16)) | ((uint64_t)((n_box_bytes >> 4) & 0x3FFF) << 16);
+            const uint64_t adesc = adesc_hi | (uint64_t)(((sa + k * 16 * m_row_bytes) >> 4) & 0x3FFF);
+            const uint64_t bdesc = bdesc_hi | (uint64_t)(((sb + k * 16 * n_row_bytes) >> 4) & 0x3FFF);
             tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
           }
           tc_commit(bar_empty + 8 * stage);
