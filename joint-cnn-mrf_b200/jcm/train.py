@@ -135,7 +135,12 @@ class Trainer:
         self.t = 0
         self.n_updates_total = n_updates_total
         dev = sm.energies.device
-        names_w = [k for k in p if k.endswith('/weights')]
+        # conv kernels first (the weight-decayed prefix), ordered by when the backward pass finishes them - LAST finished first - so
+        # that the gradient all-reduce can start on the tail of the prefix while earlier layers are still being differentiated:
+        #   [quarter bank | half bank | full bank | conv5 conv6]  ->  buckets 3, 2, 1, 0 (bucket 3 also carries everything else)
+        def bank_of(k):
+            return 3 if 'quarterres' in k else 2 if 'halfres' in k else 1 if 'fullres' in k else 0
+        names_w = sorted([k for k in p if k.endswith('/weights')], key=lambda k: -bank_of(k))     # stable: spec order inside a bank
         names_rest = [k for k in p if not k.endswith('/weights') and 'moving_' not in k]
         entries = [(k, p[k]) for k in names_w]
         self.n_decay = sum(t.numel() for _, t in entries)
@@ -146,9 +151,16 @@ class Trainer:
         for k, t in entries:
             offs[k] = n
             n += (t.numel() + 3) // 4 * 4
-        if self.n_decay % 4:
+        if self.n_decay % 4 or any(p[k].numel() % 4 for k in names_w):
             raise ValueError('conv kernel sizes must be multiples of 4 elements')
         self.n = n
+        # gradient buckets (element ranges of the flat buffer): 0 = conv5+conv6 kernels, 1 = full bank, 2 = half bank,
+        # 3 = quarter bank kernels + every other variable (two ranges)
+        first = {b: min(offs[k] for k in names_w if bank_of(k) == b) for b in range(4)}
+        self.buckets = [[(first[0], self.n_decay)], [(first[1], first[0])], [(first[2], first[1])], [(0, first[2]), (self.n_decay, n)]]
+        self._pending = []          # async all-reduce handles of this step
+        self._started = set()       # buckets whose all-reduce has been issued this step
+        self._comm_stream = None
         self.flat = torch.zeros(n, dtype=F32, device=dev)
         self.grads = torch.zeros(n, dtype=F32, device=dev)
         self.m = torch.zeros(n, dtype=F32, device=dev)
@@ -188,6 +200,7 @@ class Trainer:
         """Fills self.grads with d(loss_pd + loss_sm)/d(variables) of THIS replica (weight decay is added in apply()).
         tap (optional dict) receives the ReLU output of every layer ('<name>/relu'), as graph.model does."""
         p, sm, ctx, g = self.p, self.sm, self.ctx, self.g
+        self._started = set()
         K, split = ctx.n_joints, ctx.split
         B = x.shape[0]
         dev = x.device
@@ -267,6 +280,7 @@ class Trainer:
             return None
 
         dmerged = bwd_layer('conv5', dh, 1.0, False, 9, True)
+        self.reduce_bucket(0)                                     # conv5 + conv6 kernels are final: overlap their all-reduce
         a4_2, a4_3 = outs[1][0], outs[2][0]
         d2, d3 = upsample_avg3_bwd(dmerged, a4_2.shape[1:3], a4_3.shape[1:3])
         for sfx, dout, sc in zip(sfxs, (dmerged, d2, d3), (1.0 / 3.0, 1.0, 1.0)):
@@ -274,14 +288,45 @@ class Trainer:
             d = bwd_layer('conv3_' + sfx, d, 1.0, False, 5, True)
             d = bwd_layer('conv2_' + sfx, d, 1.0, True, 5, True)
             bwd_layer('conv1_' + sfx, d, 1.0, True, 5, False)
+            if sfx != 'quarterres':
+                self.reduce_bucket(1 if sfx == 'fullres' else 2)  # this bank's kernels are final
         return {'loss_pd': loss_pd, 'loss_sm': loss_sm, 'logit_pd': logit_pd}
 
     # ---------------------------------------------------------------------------------------- optimizer
+    def reduce_bucket(self, b):
+        """Starts the all-reduce (sum) of gradient bucket b.  On CUDA it runs asynchronously on a side stream that first waits for
+        everything queued so far on the current stream (= the kernels that produced the bucket), so NCCL overlaps with the rest
+        of the backward pass; reduce_gradients() waits for all of them.  No-op for a single replica."""
+        if self.world_size == 1 or b in self._started:
+            return
+        self._started.add(b)
+        dist = torch.distributed
+        if self.grads.is_cuda:
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(device=self.grads.device)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.grads.device))
+            self._comm_stream.wait_event(ev)
+            with torch.cuda.stream(self._comm_stream):
+                for lo, hi in self.buckets[b]:
+                    if hi > lo:
+                        self._pending.append(dist.all_reduce(self.grads[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+        else:
+            for lo, hi in self.buckets[b]:
+                if hi > lo:
+                    dist.all_reduce(self.grads[lo:hi], op=dist.ReduceOp.SUM)
+
     def reduce_gradients(self):
-        """The one exchange step of the path (main.py:243-267 averages tower gradients on the CPU): a single all-reduce (sum) of
-        the flat gradient buffer over NCCL / NVLink; the division by the replica count is folded into jcm_grad_prepare."""
+        """The one exchange step of the path (main.py:243-267 averages tower gradients on the CPU): an all-reduce (sum) of the flat
+        gradient buffer over NCCL / NVLink, issued in four buckets as the backward pass completes them; the division by the
+        replica count is folded into jcm_grad_prepare.  Buckets not started yet are started here; then all are awaited."""
         if self.world_size > 1:
-            torch.distributed.all_reduce(self.grads, op=torch.distributed.ReduceOp.SUM)
+            for b in range(len(self.buckets)):
+                self.reduce_bucket(b)
+            for w in self._pending:
+                w.wait()                    # the current stream waits for the NCCL work
+            self._pending = []
+        self._started = set()
 
     def apply(self):
         """Gradient mean over replicas (one NCCL all-reduce), weight decay, global-norm clip, Adam / Momentum."""

@@ -35,7 +35,18 @@ def _worker(rank, world, port, out_dir):
     for k in tr.g:
         tr.g[k].fill_(float(rank + 1))                           # "this replica's gradient"
     tr.g['conv1_fullres/weights'].view(-1)[0] = 10.0 * (rank + 1)
-    tr.reduce_gradients()
+    # the buckets partition the flat buffer: every element is reduced exactly once, kernels of conv5/conv6 first
+    cover = torch.zeros(tr.n, dtype=torch.int32)
+    for ranges in tr.buckets:
+        for lo, hi in ranges:
+            cover[lo:hi] += 1
+    assert bool((cover == 1).all())
+    lo0, hi0 = tr.buckets[0][0]
+    assert hi0 == tr.n_decay and hi0 - lo0 == tr.g['conv5/weights'].numel() + tr.g['conv6/weights'].numel()
+    tr._started = set()
+    tr.reduce_bucket(0)              # as the backward pass does after conv5 ...
+    tr.reduce_bucket(1)
+    tr.reduce_gradients()            # ... the rest, and wait
     want = float(sum(range(1, world + 1)))
     ok = all(bool((v.view(-1)[1:] == want).all()) for v in tr.g.values())
     ok = ok and float(tr.g['conv1_fullres/weights'].view(-1)[0]) == 10.0 * want
