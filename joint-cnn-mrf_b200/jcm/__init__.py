@@ -8,3 +8,4 @@ from .graph import (Context, PairwiseParams, JOINT_NAMES, model, spatial_model, 
                     n_filters, conv_specs)
 from . import train  # noqa: F401,E402  (Trainer: the data-parallel training step, main.py:474-577)
 from .feed import DeviceFeed  # noqa: F401,E402
+from .checkpoint import save_checkpoint, load_checkpoint  # noqa: F401,E402

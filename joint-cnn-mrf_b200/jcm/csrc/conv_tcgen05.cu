@@ -574,10 +574,10 @@ extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_
     p.a_halo_bytes = (p.TH + ksize - 1) * p.TW * p.kc * 2;
     p.a_stride = ((p.a_halo_bytes + 1023) / 1024) * 1024;
     p.b_stride = ((p.b_bytes + 1023) / 1024) * 1024;
-    p.a_stages = 3;
+    p.a_stages = p.a_stride > 40 * 1024 ? 2 : 3;
     p.b_stages = (225 * 1024 - epi_bytes - p.a_stages * p.a_stride) / p.b_stride;
     if (p.b_stages > kMaxStages) p.b_stages = kMaxStages;
-    p.halo = p.b_stages >= 4;
+    p.halo = p.b_stages >= (halo_env > 1 ? 3 : 4);
   }
   p.relu = relu;
   p.bias = bias;

@@ -130,3 +130,50 @@ def test_product_path_does_not_import_the_oracle():
         if f.endswith('.py'):
             src = open(os.path.join(pkg, f)).read()
             assert 'jcm_oracle' not in src and 'import oracle' not in src and 'pairwise_prior' not in src.replace('oracle/pairwise_prior.py', ''), f
+
+
+def test_checkpoint_roundtrip_under_tf_variable_names(tmp_path, built_lib):
+    """save / restore of variables, BN moving statistics, optimizer slots and n_iters under the reference's
+    TensorFlow names (main.py:604-617,663-666).  Host-side only: the buffers live on the CPU here."""
+    import jcm
+    K = 3
+    names = jcm.JOINT_NAMES[:K] + ['torso']
+
+    def make(seed):
+        gen = torch.Generator().manual_seed(seed)
+        p = jcm.init_part_detector(K, gen, debug=True, device='cpu')
+        distr = {a + '_' + b: torch.rand(16, 24, generator=gen).numpy() for a in names[:K] for b in names if a != b}
+        sm = jcm.PairwiseParams.from_distribution(distr, names, K, 8, 12, device='cpu')
+        ctx = jcm.Context(n_joints=K, joint_names=names, flag_train=True, precision='bf16', debug=True)
+        return jcm.train.Trainer(p, sm, ctx, lr=1e-3)
+
+    a = make(1)
+    gen = torch.Generator().manual_seed(9)
+    a.m.copy_(torch.rand(a.n, generator=gen))
+    a.v.copy_(torch.rand(a.n, generator=gen))
+    a.p['conv3_halfres/BatchNorm/moving_mean'].copy_(torch.rand(64, generator=gen))
+    a.t = 1234
+    path = str(tmp_path / 'ckpt.npz')
+    jcm.save_checkpoint(path, a)
+    z = np.load(path)
+    for name in ('conv1_fullres/weights', 'conv5/BatchNorm/moving_variance', 'bn_sm/BatchNorm/gamma', 'energy_lsho_torso', 'bias_lelb_lsho',
+                 'conv6/biases/Adam', 'energy_lwri_lsho/Adam_1', 'n_iters'):
+        assert name in z.files, name
+    assert z['energy_lsho_torso'].shape == (1, 16, 24, 1) and z['conv1_fullres/weights'].shape == (5, 5, 3, 16)
+    b = make(2)
+    assert not torch.equal(a.flat, b.flat)
+    jcm.load_checkpoint(path, b)
+    from jcm.checkpoint import state_dict
+    sa, sb = state_dict(a), state_dict(b)
+    assert sorted(sa) == sorted(sb) and all(np.array_equal(sa[k], sb[k]) for k in sa) and b.t == 1234
+    assert torch.equal(a.p['conv3_halfres/BatchNorm/moving_mean'], b.p['conv3_halfres/BatchNorm/moving_mean'])
+    with pytest.raises(ValueError):
+        jcm.load_checkpoint(path, jcm.train.Trainer(*_mk_parts(jcm, names, K), optimizer='momentum'))
+
+
+def _mk_parts(jcm, names, K):
+    gen = torch.Generator().manual_seed(3)
+    p = jcm.init_part_detector(K, gen, debug=True, device='cpu')
+    distr = {a + '_' + b: torch.rand(16, 24, generator=gen).numpy() for a in names[:K] for b in names if a != b}
+    sm = jcm.PairwiseParams.from_distribution(distr, names, K, 8, 12, device='cpu')
+    return p, sm, jcm.Context(n_joints=K, joint_names=names, flag_train=True, precision='bf16', debug=True)
