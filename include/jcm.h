@@ -177,6 +177,16 @@ int jcm_grad_prepare(float* g, const float* w, long n, long n_decay, float inv_w
 int jcm_clip_adam(float* w, const float* g, float* m, float* v, long n, const float* stats, float clip, float lr_t, float b1,
                   float b2, float eps, int momentum, void* stream);
 
+/* ---- training augmentation (augmentation.py:12-77, applied at main.py:495-499 before the tower forward) -------
+ * NHWC fp32; prm [B][8] on the device = {flip 0/1, brightness delta, contrast factor, cos(angle), sin(angle), rh, rw, unused}:
+ * the caller makes the random draws (tf.random_uniform in the reference).  src != out for the resampling kernels. */
+int jcm_augment_color(const float* x, const float* prm, float* mean_ws /*[B*C]*/, int B, int H, int W, int C, float* out, void* stream);
+int jcm_augment_flip_channels(const float* hm, const float* prm, const int* perm /*[C] device*/, int B, int H, int W, int C, float* out,
+                              void* stream);
+int jcm_augment_rotate(const float* src, const float* prm, int B, int H, int W, int C, float* out, void* stream);
+int jcm_augment_crop_resize(const float* src, const float* prm, int B, int H, int W, int C, float crop_size, float* out, void* stream);
+int jcm_augment_hm_renorm(const float* hm, int B, int H, int W, int C, float power, float eps, float* out, void* stream);
+
 /* ---- measurement / test support --------------------------------------------------------------------------------- */
 
 /* FP32 FMA peak loop (packed = 1: FFMA2); flops_out = FLOPs of one launch. scratch: blocks*512 floats. */

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'jcm', 'csrc')
 OUT = os.path.join(HERE, 'jcm', 'libjcm.so')
 STAMP = os.path.join(HERE, 'jcm', '.libjcm.stamp')
-SOURCES = ['core.cu', 'prep.cu', 'glue.cu', 'conv_tcgen05.cu', 'spatial_model.cu', 'backward.cu', 'taps.cu', 'optim.cu']
+SOURCES = ['core.cu', 'prep.cu', 'glue.cu', 'conv_tcgen05.cu', 'spatial_model.cu', 'backward.cu', 'taps.cu', 'optim.cu', 'augment.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--expt-relaxed-constexpr',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-Wall', '-Xcompiler', '-Wno-unused-function']
 

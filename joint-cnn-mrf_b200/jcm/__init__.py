@@ -9,3 +9,4 @@ from .graph import (Context, PairwiseParams, JOINT_NAMES, model, spatial_model, 
 from . import train  # noqa: F401,E402  (Trainer: the data-parallel training step, main.py:474-577)
 from .feed import DeviceFeed  # noqa: F401,E402
 from .checkpoint import save_checkpoint, load_checkpoint  # noqa: F401,E402
+from . import augment  # noqa: F401,E402  (augmentation.py: augment_train / augment_test)

@@ -50,6 +50,11 @@ SIGNATURES = {
     'jcm_tap_gather': (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     'jcm_tap_scatter_planes': (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     'jcm_unpack_tap_grad': (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    'jcm_augment_color': (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    'jcm_augment_flip_channels': (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    'jcm_augment_rotate': (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
+    'jcm_augment_crop_resize': (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _P]),
+    'jcm_augment_hm_renorm': (_I, [_P, _I, _I, _I, _I, _F, _F, _P, _P]),
     'jcm_optim_blocks': (_I, [_L]),
     'jcm_grad_prepare': (_I, [_P, _P, _L, _L, _F, _F, _P, _P, _P]),
     'jcm_clip_adam': (_I, [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _I, _P]),
