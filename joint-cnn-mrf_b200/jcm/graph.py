@@ -316,3 +316,25 @@ def tower_forward(x, hm_target, p, sm, ctx, tap=None):
         out['loss_pd'] = softmax_cross_entropy(logit_pd, hm_target)
         out['loss_sm'] = softmax_cross_entropy(out['logit_sm'], hm_target)
     return out
+
+
+def eval_error(X, Y, p, sm, ctx, batch_size, det_radius=10, joints_to_eval=(2,)):
+    """main.py:275-283: loss_pd, loss_sm, det_rate_pd, det_rate_sm averaged over the full batches of a dataset in inference mode
+    (flag_train False).  X [n,H,W,3], Y [n,h,w,K+1]: CPU (pinned or not) or CUDA tensors; incomplete last batches are dropped as
+    `get_next_batch` does (main.py:184-192).  joints_to_eval / det_radius: main.py:455-456 (wrist, r = 10)."""
+    if ctx.flag_train:
+        raise ValueError('eval_error runs in inference mode: pass a Context with flag_train=False')
+    n_batches = len(X) // batch_size
+    if n_batches == 0:
+        raise ValueError('dataset smaller than one batch')
+    tot = torch.zeros(4, dtype=torch.float64)
+    dev = sm.energies.device
+    K = ctx.n_joints
+    for i in range(n_batches):
+        xb = X[i * batch_size:(i + 1) * batch_size].to(dev, non_blocking=True).contiguous()
+        yb = Y[i * batch_size:(i + 1) * batch_size].to(dev, non_blocking=True).contiguous()
+        out = tower_forward(xb, yb, p, sm, ctx)
+        dr_pd = det_rate(out['hm_pd'], yb[..., :K].contiguous(), normalized_radius=det_radius, joints=list(joints_to_eval))
+        dr_sm = det_rate(out['hm_sm'], yb[..., :K].contiguous(), normalized_radius=det_radius, joints=list(joints_to_eval))
+        tot += torch.stack([out['loss_pd'].double().cpu(), out['loss_sm'].double().cpu(), dr_pd.double().cpu(), dr_sm.double().cpu()])
+    return tuple(float(v) for v in tot / n_batches)

@@ -384,3 +384,26 @@ def test_device_feed_overlapped_copies(jcm):
         feed.submit(torch.zeros(4))          # not pinned
     with pytest.raises(RuntimeError):
         feed.take()
+
+
+def test_eval_error_matches_oracle(jcm):
+    """main.py:275-283: per-batch losses and wrist detection rates averaged over a small dataset, inference mode."""
+    K, n, bs = 9, 5, 2
+    p, gen = _pd_params(K, True, 13)
+    names = orc.JOINT_NAMES[:K] + ['torso']
+    rng = np.random.default_rng(13)
+    X = torch.rand(n, 64, 96, 3, generator=gen)
+    Y = torch.from_numpy(orc.synthetic_labels(n, 8, 12, K + 1, rng))
+    sm32 = {k: v.float() for k, v in orc.init_spatial_model(orc.synthetic_pairwise(names, K, 8, 12, rng), K, 8, 12, joint_names=names).items()}
+    ctx = jcm.Context(n_joints=K, joint_names=names, flag_train=False, precision='fp32', debug=True)
+    got = jcm.eval_error(X, Y, jcm.load_params(p), jcm.PairwiseParams.from_dict(sm32, names, K), ctx, bs)
+    want = np.zeros(4)
+    for i in range(n // bs):
+        xb, yb = X[i * bs:(i + 1) * bs].double(), Y[i * bs:(i + 1) * bs].double()
+        o = orc.tower_forward(xb, yb, {k: v.double() for k, v in p.items()}, {k: v.double() for k, v in sm32.items()}, K, False,
+                              joint_names=names)
+        want += [float(o['loss_pd']), float(o['loss_sm']), float(orc.det_rate(o['hm_pd'], yb[..., :K], 10, [2])),
+                 float(orc.det_rate(o['hm_sm'], yb[..., :K], 10, [2]))]
+    want /= n // bs
+    assert abs(got[0] - want[0]) < 1e-3 * want[0] and abs(got[1] - want[1]) < 1e-3 * want[1]
+    assert got[2] == pytest.approx(want[2], abs=1e-4) and got[3] == pytest.approx(want[3], abs=1e-4)
