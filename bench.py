@@ -303,11 +303,11 @@ def run_ours(args):
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this same command (per launch, like achieved)
     traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, 'profiles', 'r01', 'ncu_full_train64_v3_traffic.json')) as f:
+        with open(os.path.join(ROOT, 'profiles', 'r01', 'ncu_full_train64_v8_traffic.json')) as f:
             tj = json.load(f)
         if train:
             traffic = tj['kernels']['conv_igemm_kernel']['dram_bytes_per_launch']
-            traffic_src = 'profiles/r01/ncu_full_train64_v3_traffic.json (mean over the 25 launches of a step)'
+            traffic_src = 'profiles/r01/ncu_full_train64_v8_traffic.json (mean over the 25 launches of a step)'
     except Exception:
         pass
     mult = 1 if train else 3

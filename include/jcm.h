@@ -56,8 +56,9 @@ int jcm_split_planes(const float* x, long n, void* hi, void* lo, void* stream);
 /* y = [relu](conv_SAME_stride1(x, w) + bias): tf.nn.conv2d + bias + tf.nn.relu, main.py:133-135,160-162.
  * x planes [B,H,W,Cin] (Cin a multiple of 16), w planes [ksize*kw][Cout_pad][Cin], y fp32 [B,H,W,Cout].
  * ksize = kernel height, kw = kernel width (0: square, kw = ksize).
- * TMA-fed implicit GEMM on tcgen05 tensor cores, fp32 accumulation in TMEM. */
-int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, float* y,
+ * TMA-fed implicit GEMM on tcgen05 tensor cores, fp32 accumulation in TMEM.
+ * y: fp32 [B,H,W,Cout], or bf16 when y_bf16 != 0 (activations of the bf16 training configuration; Cout a multiple of 64). */
+int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, void* y, int y_bf16,
                    int B, int H, int W, int Cin, int Cout, int Cout_pad, int ksize, int kw, int relu, void* stream);
 
 /* tf.contrib.layers.batch_norm(decay=0.9, eps=1e-3, center, scale), main.py:128-130 and :112-113.
@@ -65,18 +66,18 @@ int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const v
  * jcm_bn_finalize: train != 0 -> batch statistics (biased variance), moving stats updated in place when update_moving
  * (unbiased variance); train == 0 -> moving statistics.  Emits scale = gamma*rstd, shift = beta - mean*scale. */
 int jcm_bn_stats_blocks(long M, int C);
-int jcm_bn_stats(const float* x, long M, int C, float* partial, void* stream);
+int jcm_bn_stats(const void* x, int x_bf16, long M, int C, float* partial, void* stream);   /* x: fp32, or bf16 when x_bf16 */
 int jcm_bn_finalize(const float* partial, long M, int C, const float* gamma, const float* beta, float* moving_mean,
                     float* moving_var, float eps, float decay, int train, int update_moving, float* scale, float* shift,
                     float* save_mean, float* save_rstd, void* stream);
 
 /* BN affine (+ tf.nn.max_pool 2x2 s2 SAME, main.py:172-174) -> operand planes and/or fp32. */
-int jcm_bn_apply_pool(const float* a, const float* scale, const float* shift, int B, int H, int W, int C, int pool,
+int jcm_bn_apply_pool(const void* a, int a_bf16, const float* scale, const float* shift, int B, int H, int W, int C, int pool,
                       void* out_hi, void* out_lo, float* out_f32, void* stream);
 
 /* (bn(a1) + resize(bn(a2)) + resize(bn(a3))) / 3 with tf.image.resize_images legacy bilinear, main.py:58,67,69-70.
  * scale_shift = [6][C] = scale1, shift1, scale2, shift2, scale3, shift3. */
-int jcm_upsample_avg3(const float* a1, const float* a2, const float* a3, const float* scale_shift, int B, int H, int W,
+int jcm_upsample_avg3(const void* a1, const void* a2, const void* a3, int a_bf16, const float* scale_shift, int B, int H, int W,
                       int H2, int W2, int H3, int W3, int C, void* out_hi, void* out_lo, float* out_f32, void* stream);
 
 /* ---- heads ----------------------------------------------------------------------------------------------------- */
@@ -122,7 +123,7 @@ int jcm_spatial_softmax_bwd(const float* y, const float* dy, int B, int S, int K
  * Outputs: d_pre planes [B,H,W,C] (gradient w.r.t. the conv output), dgamma, dbeta, dbias [C].
  * workspace: (4 * jcm_bn_relu_bwd_blocks(M_out, C) + 2) * C floats. */
 int jcm_bn_relu_bwd_blocks(long M_out, int C);
-int jcm_bn_relu_bwd(const float* a, const float* dout, const float* scale, const float* shift, const float* mean, const float* rstd,
+int jcm_bn_relu_bwd(const void* a, int a_bf16, const float* dout, const float* scale, const float* shift, const float* mean, const float* rstd,
                     float dy_scale, int B, int H, int W, int C, int pool, void* d_hi, void* d_lo, float* d_f32, float* dgamma,
                     float* dbeta, float* dbias, float* workspace, void* stream);
 

@@ -22,12 +22,12 @@ SIGNATURES = {
     'jcm_pack_weights': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     'jcm_pack_weights_s2d': (_I, [_P, _I, _P, _P, _P]),
     'jcm_split_planes': (_I, [_P, _L, _P, _P, _P]),
-    'jcm_conv2d_fwd': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'jcm_conv2d_fwd': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'jcm_bn_stats_blocks': (_I, [_L, _I]),
-    'jcm_bn_stats': (_I, [_P, _L, _I, _P, _P]),
+    'jcm_bn_stats': (_I, [_P, _I, _L, _I, _P, _P]),
     'jcm_bn_finalize': (_I, [_P, _L, _I, _P, _P, _P, _P, _F, _F, _I, _I, _P, _P, _P, _P, _P]),
-    'jcm_bn_apply_pool': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
-    'jcm_upsample_avg3': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    'jcm_bn_apply_pool': (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    'jcm_upsample_avg3': (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     'jcm_spatial_softmax': (_I, [_P, _I, _I, _I, _P, _P]),
     'jcm_softmax_ce': (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     'jcm_argmax_hw': (_I, [_P, _I, _I, _I, _I, _P, _P]),
@@ -37,7 +37,7 @@ SIGNATURES = {
     'jcm_softmax_ce_bwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P]),
     'jcm_spatial_softmax_bwd': (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     'jcm_bn_relu_bwd_blocks': (_I, [_L, _I]),
-    'jcm_bn_relu_bwd': (_I, [_P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'jcm_bn_relu_bwd': (_I, [_P, _I, _P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     'jcm_colsum': (_I, [_P, _L, _I, _P, _P, _P]),
     'jcm_upsample_avg3_bwd': (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     'jcm_pad_planes': (_I, [_P, _L, _I, _I, _P, _P, _P]),

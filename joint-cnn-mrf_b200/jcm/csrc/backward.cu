@@ -63,7 +63,8 @@ __global__ void spatial_softmax_bwd_kernel(const float* __restrict__ y, const fl
 // partial sums are deterministic.  PASS 0: partial[blk][0][c] = sum dy, partial[blk][1][c] = sum dy*xhat.
 // PASS 1: writes d_pre (gradient w.r.t. the conv output before ReLU) as bf16 planes (+fp32) and partial[blk][0][c] = sum d_pre.
 struct BnBwdArgs {
-  const float* a;
+  const void* a;           // ReLU output, fp32 or bf16 (a_bf16)
+  int a_bf16;
   const float* dout;
   const float* scale;      // gamma * rstd
   const float* shift;      // beta - mean * scale
@@ -110,7 +111,7 @@ __global__ void bn_relu_bwd_kernel(BnBwdArgs p) {
       const float4 d4 = *reinterpret_cast<const float4*>(p.dout + r * p.C + g * 4);
       const float dv[4] = {d4.x * p.dy_scale, d4.y * p.dy_scale, d4.z * p.dy_scale, d4.w * p.dy_scale};
       if (!p.pool) {
-        const float4 a4 = *reinterpret_cast<const float4*>(p.a + r * p.C + g * 4);
+        const float4 a4 = load_act4(p.a, (r * p.C + g * 4) >> 2, p.a_bf16);
         const float av[4] = {a4.x, a4.y, a4.z, a4.w};
         float o[4];
 #pragma unroll
@@ -148,7 +149,7 @@ __global__ void bn_relu_bwd_kernel(BnBwdArgs p) {
           const int yy = y0 + (e >> 1), xx = x0 + (e & 1);
           ok[e] = yy < p.H && xx < p.W;
           float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok[e]) a4 = *reinterpret_cast<const float4*>(p.a + (((long)n * p.H + yy) * p.W + xx) * p.C + g * 4);
+          if (ok[e]) a4 = load_act4(p.a, ((((long)n * p.H + yy) * p.W + xx) * p.C + g * 4) >> 2, p.a_bf16);
           av[e][0] = a4.x; av[e][1] = a4.y; av[e][2] = a4.z; av[e][3] = a4.w;
         }
         float o[4][4];
@@ -334,7 +335,7 @@ extern "C" int jcm_bn_relu_bwd_blocks(long M_out, int C) {
 
 // Two passes.  workspace: 2 * blocks * 2 * C + 2 * C floats (partials of both passes + the reduced sums).
 // Outputs: d_pre planes [B,H,W,C] (hi[, lo]) and optionally fp32; dgamma[C], dbeta[C], dbias[C] (= column sums of d_pre).
-extern "C" int jcm_bn_relu_bwd(const float* a, const float* dout, const float* scale, const float* shift, const float* mean,
+extern "C" int jcm_bn_relu_bwd(const void* a, int a_bf16, const float* dout, const float* scale, const float* shift, const float* mean,
                                const float* rstd, float dy_scale, int B, int H, int W, int C, int pool, void* d_hi, void* d_lo,
                                float* d_f32, float* dgamma, float* dbeta, float* dbias, float* workspace, void* stream) {
   JCM_CHECK_ARG(a && dout && scale && shift && mean && rstd && d_hi && dgamma && dbeta && dbias && workspace, "jcm_bn_relu_bwd: null pointer");
@@ -347,7 +348,7 @@ extern "C" int jcm_bn_relu_bwd(const float* a, const float* dout, const float* s
   float* part1 = workspace + (long)blocks * 2 * C;
   float* sums = part1 + (long)blocks * 2 * C;
   BnBwdArgs p;
-  p.a = a; p.dout = dout; p.scale = scale; p.shift = shift; p.mean = mean; p.rstd = rstd; p.sums = sums; p.dy_scale = dy_scale;
+  p.a = a; p.a_bf16 = a_bf16; p.dout = dout; p.scale = scale; p.shift = shift; p.mean = mean; p.rstd = rstd; p.sums = sums; p.dy_scale = dy_scale;
   p.B = B; p.H = H; p.W = W; p.C = C; p.pool = pool; p.inv_count = 1.0f / (float)((long)B * H * W);
   p.hi = (__nv_bfloat16*)d_hi; p.lo = (__nv_bfloat16*)d_lo; p.d_f32 = d_f32; p.partial = part0;
   const size_t shb = kThreads * 8 * sizeof(float);

@@ -92,3 +92,18 @@ __device__ __forceinline__ double partial_colsum(const float* __restrict__ parti
     for (int l = 0; l < kPartY; ++l) t += sh[l][threadIdx.x];
   return t;
 }
+
+// Activations (post-ReLU conv outputs kept for the BN / backward passes) are fp32, or bf16 in the bf16 training configuration.
+// 4 consecutive channels starting at element index i4*4 of `base`:
+__device__ __forceinline__ float4 load_act4(const void* __restrict__ base, long i4, int is_bf16) {
+  if (is_bf16) {
+    const uint2 r = reinterpret_cast<const uint2*>(base)[i4];
+    const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&r.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&r.y);
+    const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return reinterpret_cast<const float4*>(base)[i4];
+}
+__device__ __forceinline__ float load_act1(const void* __restrict__ base, long i, int is_bf16) {
+  return is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[i]) : reinterpret_cast<const float*>(base)[i];
+}

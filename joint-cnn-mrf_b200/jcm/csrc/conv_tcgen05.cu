@@ -33,6 +33,7 @@ struct ConvParams {
   int kc, cblocks, ksize, kw, pad, pad_x, terms;   // ksize x kw taps (kernel height x width), SAME padding pad / pad_x
   int stages, a_bytes, b_bytes, stage_bytes;
   int relu;
+  int y_bf16;           // 1: the output activation is stored as bf16 (bf16 training configuration), TMA-store epilogue only
   int tma_store;        // 1: epilogue stages 32-column chunks in swizzled shared memory and writes them with TMA stores
   // halo mode (layers whose A operand traffic is the limiter: N <= 128): the A tile is loaded ONCE per (dx, channel block) as a
   // (TH + kh - 1)-row halo patch and the kh vertical taps address it at row offsets dy*TW (a multiple of the 8-row swizzle
@@ -363,6 +364,51 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
       const uint32_t taddr0 = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
       if (p.dbg & 1) {
         // timing experiment: no stores
+      } else if (p.tma_store && p.y_bf16) {
+        // bf16 output: 64-column chunks (128-byte rows of bf16) through the same swizzled staging buffers, box {64 ch, TW, TH, 1}
+        const uint32_t stage0 = p.halo ? smem_b0 + p.b_stages * p.b_stride : smem_base + p.stages * p.stage_bytes;
+        for (int c0 = 0; c0 < p.block_n; c0 += 64) {
+          const uint32_t buf = stage0 + (uint32_t)(epi_chunk & 1) * (kTileM * 128);
+          if (threadIdx.x == 128) bulk_wait_read<1>();
+          epi_bar();
+          uint32_t v[32], u[32];
+          tc_ld32(taddr0 + c0, v);
+          tc_ld32(taddr0 + c0 + 32, u);
+          tc_ld_wait();
+          const int co0 = nt * p.block_n + c0;
+          const uint32_t rowaddr = buf + (uint32_t)row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {       // 16-byte chunk j = channels co0 + 8j .. 8j+7
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(j < 4 ? v[8 * j + e] : u[8 * (j - 4) + e]);
+            if (p.bias && co0 + 8 * j < p.Cout) {
+              const float4 b0 = *reinterpret_cast<const float4*>(p.bias + co0 + 8 * j);
+              const float4 b1 = *reinterpret_cast<const float4*>(p.bias + co0 + 8 * j + 4);
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+            }
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+              w[e] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (uint32_t)((j ^ (row & 7)) << 4)), "r"(w[0]), "r"(w[1]),
+                         "r"(w[2]), "r"(w[3])
+                         : "memory");
+          }
+          fence_proxy_async();
+          epi_bar();
+          if (threadIdx.x == 128) {
+            if (co0 < p.Cout) tma_store_4d(&map_y, buf, co0, tx * p.TW, ty * p.TH, img);
+            bulk_commit();
+          }
+          ++epi_chunk;
+        }
       } else if (p.tma_store) {
         // coalesced epilogue: 32-column chunks go through two 16 KB swizzled staging buffers and out with TMA stores (the box
         // {32 ch, TW, TH, 1} has the A operand's pixel order, so accumulator row == staging row; ragged edges are clipped by TMA)
@@ -515,7 +561,7 @@ static void pick_patch(int H, int W, int* TW, int* TH) {
 }
 
 extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
-                              float* y, int B, int H, int W, int Cin, int Cout, int Cout_pad, int ksize, int kw, int relu,
+                              void* y, int y_bf16, int B, int H, int W, int Cin, int Cout, int Cout_pad, int ksize, int kw, int relu,
                               void* stream) {
   if (kw <= 0) kw = ksize;
   JCM_CHECK_ARG(x_hi && w_hi && y, "jcm_conv2d_fwd: null pointer");
@@ -581,7 +627,10 @@ extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_
   }
   p.relu = relu;
   p.bias = bias;
-  p.y = y;
+  p.y = (float*)y;
+  p.y_bf16 = y_bf16;
+  JCM_CHECK_ARG(!y_bf16 || (p.tma_store && (Cout % 8) == 0 && (p.block_n % 64) == 0),
+                "jcm_conv2d_fwd: bf16 output needs Cout a multiple of 8 and N tiles that are multiples of 64 (Cout=%d)", Cout);
 
   const CUtensorMapSwizzle swz = p.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
@@ -608,10 +657,12 @@ extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_
   CUtensorMap my;
   memset(&my, 0, sizeof(my));
   if (p.tma_store) {
+    const uint64_t es = y_bf16 ? 2 : 4;
     uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    uint64_t str[3] = {(uint64_t)Cout * 4, (uint64_t)W * Cout * 4, (uint64_t)H * W * Cout * 4};
-    uint32_t box[4] = {32, (uint32_t)p.TW, (uint32_t)p.TH, 1};
-    int rc = make_map(&my, y, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+    uint64_t str[3] = {(uint64_t)Cout * es, (uint64_t)W * Cout * es, (uint64_t)H * W * Cout * es};
+    uint32_t box[4] = {y_bf16 ? 64u : 32u, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+    int rc = make_map(&my, y, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B,
+                      y_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
     if (rc) return rc;
   }
 

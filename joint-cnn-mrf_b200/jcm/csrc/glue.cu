@@ -17,7 +17,7 @@ constexpr int kStatThreads = 256;
 // ------------------------------------------------------------------------------------------- BN statistics
 // x [M, C]; each block reduces a contiguous slab of rows; thread t owns column group (t % G) and row lane (t / G).
 template <int VEC>
-__global__ void bn_stats_kernel(const float* __restrict__ x, long M, int C, float* __restrict__ partial /*[grid][2][C]*/) {
+__global__ void bn_stats_kernel(const void* __restrict__ x, int x_bf16, long M, int C, float* __restrict__ partial /*[grid][2][C]*/) {
   extern __shared__ float sh[];  // [kStatThreads][2*VEC]
   const int G = C / VEC;         // column groups
   const int lanes = kStatThreads / G;
@@ -32,13 +32,13 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, long M, int C, floa
   if (rl < lanes) {
     for (long r = r0 + rl; r < r1; r += lanes) {
       if (VEC == 4) {
-        const float4 v = *reinterpret_cast<const float4*>(x + r * C + g * 4);
+        const float4 v = load_act4(x, (r * C + g * 4) >> 2, x_bf16);
         s[0] += v.x; q[0] += v.x * v.x;
         s[1 % VEC] += v.y; q[1 % VEC] += v.y * v.y;
         s[2 % VEC] += v.z; q[2 % VEC] += v.z * v.z;
         s[3 % VEC] += v.w; q[3 % VEC] += v.w * v.w;
       } else {
-        const float v = x[r * C + g];
+        const float v = load_act1(x, r * C + g, x_bf16);
         s[0] += v; q[0] += v * v;
       }
     }
@@ -116,7 +116,7 @@ __device__ __forceinline__ float4 max4(float4 a, float4 b) {
   return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }
 
-__global__ void bn_apply_pool_kernel(const float* __restrict__ a, const float* __restrict__ scale, const float* __restrict__ shift,
+__global__ void bn_apply_pool_kernel(const void* __restrict__ a, int a_bf16, const float* __restrict__ scale, const float* __restrict__ shift,
                                      int B, int H, int W, int C, int pool, __nv_bfloat16* __restrict__ hi,
                                      __nv_bfloat16* __restrict__ lo, float* __restrict__ out_f32) {
   const int Ho = pool ? (H + 1) / 2 : H, Wo = pool ? (W + 1) / 2 : W;
@@ -133,15 +133,16 @@ __global__ void bn_apply_pool_kernel(const float* __restrict__ a, const float* _
     const float4 sh = reinterpret_cast<const float4*>(shift)[c4];
     float4 r;
     if (!pool) {
-      r = affine4(reinterpret_cast<const float4*>(a)[i], sc, sh);
+      r = affine4(load_act4(a, i, a_bf16), sc, sh);
     } else {
       const int y0 = 2 * yo, x0 = 2 * xo;
-      const float* base = a + (((long)n * H + y0) * W + x0) * C + c4 * 4;
-      r = affine4(*reinterpret_cast<const float4*>(base), sc, sh);
+      const long base4 = ((((long)n * H + y0) * W + x0) * C + c4 * 4) >> 2;   // index in units of 4 channels
+      const long C4l = C / 4;
+      r = affine4(load_act4(a, base4, a_bf16), sc, sh);
       const bool hx = x0 + 1 < W, hy = y0 + 1 < H;  // SAME pooling: the padded row/column never wins
-      if (hx) r = max4(r, affine4(*reinterpret_cast<const float4*>(base + C), sc, sh));
-      if (hy) r = max4(r, affine4(*reinterpret_cast<const float4*>(base + (long)W * C), sc, sh));
-      if (hx && hy) r = max4(r, affine4(*reinterpret_cast<const float4*>(base + (long)W * C + C), sc, sh));
+      if (hx) r = max4(r, affine4(load_act4(a, base4 + C4l, a_bf16), sc, sh));
+      if (hy) r = max4(r, affine4(load_act4(a, base4 + (long)W * C4l, a_bf16), sc, sh));
+      if (hx && hy) r = max4(r, affine4(load_act4(a, base4 + (long)W * C4l + C4l, a_bf16), sc, sh));
     }
     if (hi) store_planes4(hi, lo, i, r);
     if (out_f32) reinterpret_cast<float4*>(out_f32)[i] = r;
@@ -160,21 +161,22 @@ __device__ __forceinline__ void legacy_tap(int dst, int n_in, int n_out, int& lo
 __device__ __forceinline__ float4 lerp4(float4 a, float4 b, float w) {
   return make_float4(a.x + (b.x - a.x) * w, a.y + (b.y - a.y) * w, a.z + (b.z - a.z) * w, a.w + (b.w - a.w) * w);
 }
-__device__ __forceinline__ float4 resize_sample(const float* __restrict__ a, int n, int Hi, int Wi, int C, int c4, int y, int x, int Ho,
-                                                int Wo, float4 sc, float4 sh) {
+__device__ __forceinline__ float4 resize_sample(const void* __restrict__ a, int a_bf16, int n, int Hi, int Wi, int C, int c4, int y, int x,
+                                                int Ho, int Wo, float4 sc, float4 sh) {
   int ylo, yhi, xlo, xhi;
   float wy, wx;
   legacy_tap(y, Hi, Ho, ylo, yhi, wy);
   legacy_tap(x, Wi, Wo, xlo, xhi, wx);
-  const float* b = a + (long)n * Hi * Wi * C + c4 * 4;
-  const float4 tl = affine4(*reinterpret_cast<const float4*>(b + ((long)ylo * Wi + xlo) * C), sc, sh);
-  const float4 tr = affine4(*reinterpret_cast<const float4*>(b + ((long)ylo * Wi + xhi) * C), sc, sh);
-  const float4 bl = affine4(*reinterpret_cast<const float4*>(b + ((long)yhi * Wi + xlo) * C), sc, sh);
-  const float4 br = affine4(*reinterpret_cast<const float4*>(b + ((long)yhi * Wi + xhi) * C), sc, sh);
+  const long C4l = C / 4;
+  const long b4 = (long)n * Hi * Wi * C4l + c4;
+  const float4 tl = affine4(load_act4(a, b4 + ((long)ylo * Wi + xlo) * C4l, a_bf16), sc, sh);
+  const float4 tr = affine4(load_act4(a, b4 + ((long)ylo * Wi + xhi) * C4l, a_bf16), sc, sh);
+  const float4 bl = affine4(load_act4(a, b4 + ((long)yhi * Wi + xlo) * C4l, a_bf16), sc, sh);
+  const float4 br = affine4(load_act4(a, b4 + ((long)yhi * Wi + xhi) * C4l, a_bf16), sc, sh);
   return lerp4(lerp4(tl, tr, wx), lerp4(bl, br, wx), wy);
 }
 
-__global__ void upsample_avg3_kernel(const float* __restrict__ a1, const float* __restrict__ a2, const float* __restrict__ a3,
+__global__ void upsample_avg3_kernel(const void* __restrict__ a1, const void* __restrict__ a2, const void* __restrict__ a3, int a_bf16,
                                      const float* __restrict__ ss /* [6][C]: scale1, shift1, scale2, shift2, scale3, shift3 */,
                                      int B, int H, int W, int H2, int W2, int H3, int W3, int C, __nv_bfloat16* __restrict__ hi,
                                      __nv_bfloat16* __restrict__ lo, float* __restrict__ out_f32) {
@@ -188,9 +190,9 @@ __global__ void upsample_avg3_kernel(const float* __restrict__ a1, const float* 
     const int y = (int)(t % H);
     const int n = (int)(t / H);
     const float4* s4 = reinterpret_cast<const float4*>(ss);
-    const float4 v1 = affine4(reinterpret_cast<const float4*>(a1)[i], s4[0 * C4 + c4], s4[1 * C4 + c4]);
-    const float4 v2 = resize_sample(a2, n, H2, W2, C, c4, y, x, H, W, s4[2 * C4 + c4], s4[3 * C4 + c4]);
-    const float4 v3 = resize_sample(a3, n, H3, W3, C, c4, y, x, H, W, s4[4 * C4 + c4], s4[5 * C4 + c4]);
+    const float4 v1 = affine4(load_act4(a1, i, a_bf16), s4[0 * C4 + c4], s4[1 * C4 + c4]);
+    const float4 v2 = resize_sample(a2, a_bf16, n, H2, W2, C, c4, y, x, H, W, s4[2 * C4 + c4], s4[3 * C4 + c4]);
+    const float4 v3 = resize_sample(a3, a_bf16, n, H3, W3, C, c4, y, x, H, W, s4[4 * C4 + c4], s4[5 * C4 + c4]);
     float4 r;
     r.x = (v1.x + v2.x + v3.x) / 3.0f;
     r.y = (v1.y + v2.y + v3.y) / 3.0f;
@@ -319,14 +321,14 @@ extern "C" int jcm_bn_stats_blocks(long M, int C) {
 }
 
 // partial: caller-owned workspace of jcm_bn_stats_blocks(M,C) * 2 * C floats
-extern "C" int jcm_bn_stats(const float* x, long M, int C, float* partial, void* stream) {
+extern "C" int jcm_bn_stats(const void* x, int x_bf16, long M, int C, float* partial, void* stream) {
   JCM_CHECK_ARG(x && partial && M > 0 && C > 0, "jcm_bn_stats: bad arguments");
   const int blocks = jcm_bn_stats_blocks(M, C);
   if ((C % 4) == 0 && C / 4 <= kStatThreads) {
-    bn_stats_kernel<4><<<blocks, kStatThreads, kStatThreads * 8 * sizeof(float), (cudaStream_t)stream>>>(x, M, C, partial);
+    bn_stats_kernel<4><<<blocks, kStatThreads, kStatThreads * 8 * sizeof(float), (cudaStream_t)stream>>>(x, x_bf16, M, C, partial);
   } else {
     JCM_CHECK_ARG(C <= kStatThreads, "jcm_bn_stats: C=%d not supported (must be a multiple of 4 <= 1024, or <= 256)", C);
-    bn_stats_kernel<1><<<blocks, kStatThreads, kStatThreads * 2 * sizeof(float), (cudaStream_t)stream>>>(x, M, C, partial);
+    bn_stats_kernel<1><<<blocks, kStatThreads, kStatThreads * 2 * sizeof(float), (cudaStream_t)stream>>>(x, x_bf16, M, C, partial);
   }
   JCM_LAUNCH_CHECK();
   return JCM_OK;
@@ -343,7 +345,7 @@ __global__ void colsum_from_partial_kernel(const float* __restrict__ partial, in
 
 // out[c] = sum over rows of x [M,C] (bias gradient of the last conv layer); partial as for jcm_bn_stats
 extern "C" int jcm_colsum(const float* x, long M, int C, float* partial, float* out, void* stream) {
-  int rc = jcm_bn_stats(x, M, C, partial, stream);
+  int rc = jcm_bn_stats(x, 0, M, C, partial, stream);
   if (rc) return rc;
   colsum_from_partial_kernel<<<jcm_cdiv(C, 32), dim3(32, kPartY), 0, (cudaStream_t)stream>>>(partial, jcm_bn_stats_blocks(M, C), C, out);
   JCM_LAUNCH_CHECK();
@@ -362,24 +364,24 @@ extern "C" int jcm_bn_finalize(const float* partial, long M, int C, const float*
   return JCM_OK;
 }
 
-extern "C" int jcm_bn_apply_pool(const float* a, const float* scale, const float* shift, int B, int H, int W, int C, int pool,
+extern "C" int jcm_bn_apply_pool(const void* a, int a_bf16, const float* scale, const float* shift, int B, int H, int W, int C, int pool,
                                  void* out_hi, void* out_lo, float* out_f32, void* stream) {
   JCM_CHECK_ARG(a && scale && shift && (out_hi || out_f32), "jcm_bn_apply_pool: null pointer");
   JCM_CHECK_ARG((C % 4) == 0, "jcm_bn_apply_pool: C must be a multiple of 4, got %d", C);
   const int Ho = pool ? (H + 1) / 2 : H, Wo = pool ? (W + 1) / 2 : W;
   const long total = (long)B * Ho * Wo * (C / 4);
-  bn_apply_pool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a, scale, shift, B, H, W, C, pool, (__nv_bfloat16*)out_hi,
+  bn_apply_pool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a, a_bf16, scale, shift, B, H, W, C, pool, (__nv_bfloat16*)out_hi,
                                                                                (__nv_bfloat16*)out_lo, out_f32);
   JCM_LAUNCH_CHECK();
   return JCM_OK;
 }
 
-extern "C" int jcm_upsample_avg3(const float* a1, const float* a2, const float* a3, const float* scale_shift, int B, int H, int W,
+extern "C" int jcm_upsample_avg3(const void* a1, const void* a2, const void* a3, int a_bf16, const float* scale_shift, int B, int H, int W,
                                  int H2, int W2, int H3, int W3, int C, void* out_hi, void* out_lo, float* out_f32, void* stream) {
   JCM_CHECK_ARG(a1 && a2 && a3 && scale_shift && (out_hi || out_f32), "jcm_upsample_avg3: null pointer");
   JCM_CHECK_ARG((C % 4) == 0, "jcm_upsample_avg3: C must be a multiple of 4, got %d", C);
   const long total = (long)B * H * W * (C / 4);
-  upsample_avg3_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a1, a2, a3, scale_shift, B, H, W, H2, W2, H3, W3, C,
+  upsample_avg3_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a1, a2, a3, a_bf16, scale_shift, B, H, W, H2, W2, H3, W3, C,
                                                                                (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32);
   JCM_LAUNCH_CHECK();
   return JCM_OK;

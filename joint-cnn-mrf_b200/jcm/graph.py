@@ -20,7 +20,7 @@ class Context:
     """The reference's module-level globals (main.py:428-472) as one explicit object."""
 
     def __init__(self, n_joints=9, joint_names=None, flag_train=False, train_pd=True, precision='fp32', debug=False,
-                 lmbd=0.001, use_sm=True):
+                 lmbd=0.001, use_sm=True, bf16_activations=False):
         if precision not in ('fp32', 'bf16'):
             raise ValueError("precision must be 'fp32' (bf16x3 split products) or 'bf16'")
         self.n_joints = n_joints
@@ -33,11 +33,19 @@ class Context:
         self.debug = debug
         self.lmbd = lmbd
         self.use_sm = use_sm
+        self.bf16_activations = bool(bf16_activations)
         self._wcache = {}
 
     @property
     def split(self):
         return self.precision == 'fp32'
+
+    @property
+    def act_bf16(self):
+        """Opt-in (bf16_activations=True, bf16 precision only): the post-ReLU activations kept for batch norm and the backward pass
+        are stored in bf16 as well.  Off by default: measured on B200 it halves those tensors but the BN / backward glue kernels
+        (4 channels per thread) get slower with 8-byte loads, a wash at batch 64 (profiles/r01/launches_train64_v9_summary.txt)."""
+        return self.bf16_activations and self.precision == 'bf16'
 
     def packed(self, name, w, kind='fwd'):
         """Packed bf16 operand planes of a conv kernel, cached until the parameter tensor is modified in place."""
@@ -220,7 +228,8 @@ def model(x, n_joints, p, ctx, tap=None):
     def layer(xp, name, ksize, kind='fwd'):
         w, b = p[name + '/weights'], p[name + '/biases']
         a = ops.conv2d_planes(xp, ctx.packed(name, w, kind), b, w.shape[3], ksize, relu=True,
-                              alg_kdim=w.shape[0] * w.shape[1] * w.shape[2])
+                              alg_kdim=w.shape[0] * w.shape[1] * w.shape[2],
+                                  out_bf16=ctx.act_bf16 and w.shape[3] % 64 == 0)   # narrow (--debug) layers keep fp32 activations
         if tap is not None:
             tap[name + '/relu'] = a
         ss = ops.bn_scale_shift(a, *_bn_vars(p, name), train=train)

@@ -17,6 +17,13 @@ def _ptr(t):
     return ctypes.c_void_p(0 if t is None else t.data_ptr())
 
 
+def _req_act(t, name):
+    """An activation tensor: fp32, or bf16 in the bf16 training configuration."""
+    if t is None or not t.is_cuda or t.dtype not in (F32, BF16) or not t.is_contiguous():
+        raise ValueError('%s must be a contiguous fp32 or bf16 CUDA tensor (jcm has no CPU path)' % name)
+    return int(t.dtype == BF16)
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -146,7 +153,7 @@ def split_planes(x, split):
 
 
 # ------------------------------------------------------------------------------------------------ part detector
-def conv2d_planes(xp, wp, bias, cout, ksize, relu, naive=False, alg_kdim=None):
+def conv2d_planes(xp, wp, bias, cout, ksize, relu, naive=False, alg_kdim=None, out_bf16=False):
     """xp activation planes [B,H,W,Cin], wp packed weight planes [kh*kw,Cout_pad,Cin] -> fp32 [B,H,W,cout].
     ksize: int (square) or (kh, kw).  alg_kdim: contraction length of the ALGORITHMIC convolution (default kh*kw*Cin; 75 for
     the s2d conv1)."""
@@ -159,14 +166,19 @@ def conv2d_planes(xp, wp, bias, cout, ksize, relu, naive=False, alg_kdim=None):
         raise ValueError('activation and weight planes must use the same precision mode')
     if bias is not None:
         _req(bias, F32, 'bias')
-    y = torch.empty((B, H, W, cout), dtype=F32, device=xp.hi.device)
-    fn = lib().jcm_debug_conv2d_naive if naive else lib().jcm_conv2d_fwd
+    if out_bf16 and naive:
+        raise ValueError('the naive test convolution writes fp32 only')
+    y = torch.empty((B, H, W, cout), dtype=BF16 if out_bf16 else F32, device=xp.hi.device)
     prof = PROFILE.enabled and not naive
     if prof:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    check(fn(_ptr(xp.hi), _ptr(xp.lo), _ptr(wp.hi), _ptr(wp.lo), _ptr(bias), _ptr(y), B, H, W, cin, cout, cout_pad, kh, kw,
-             int(relu), _stream()), 'jcm_conv2d_fwd')
+    if naive:
+        check(lib().jcm_debug_conv2d_naive(_ptr(xp.hi), _ptr(xp.lo), _ptr(wp.hi), _ptr(wp.lo), _ptr(bias), _ptr(y), B, H, W, cin, cout,
+                                           cout_pad, kh, kw, int(relu), _stream()), 'jcm_debug_conv2d_naive')
+    else:
+        check(lib().jcm_conv2d_fwd(_ptr(xp.hi), _ptr(xp.lo), _ptr(wp.hi), _ptr(wp.lo), _ptr(bias), _ptr(y), int(out_bf16), B, H, W, cin,
+                                   cout, cout_pad, kh, kw, int(relu), _stream()), 'jcm_conv2d_fwd')
     if prof:
         e1.record()
         PROFILE.add('conv_igemm_kernel', 2.0 * B * H * W * (alg_kdim or kh * kw * cin) * cout, e0, e1)
@@ -228,8 +240,8 @@ def unpack_tap_grad(dwz, ksize, cin, cout, dw):
 
 
 def bn_scale_shift(a, gamma, beta, moving_mean, moving_var, train, update_moving=True, save=False):
-    """Per-channel (scale, shift) of tf.contrib.layers.batch_norm for a [.., C] fp32 tensor (batch stats if train)."""
-    _req(a, F32, 'a')
+    """Per-channel (scale, shift) of tf.contrib.layers.batch_norm for a [.., C] fp32 (or bf16) tensor (batch stats if train)."""
+    a_bf16 = _req_act(a, 'a')
     C = a.shape[-1]
     M = a.numel() // C
     for t, n in ((gamma, 'gamma'), (beta, 'beta'), (moving_mean, 'moving_mean'), (moving_var, 'moving_variance')):
@@ -241,7 +253,7 @@ def bn_scale_shift(a, gamma, beta, moving_mean, moving_var, train, update_moving
     if train:
         nb = lib().jcm_bn_stats_blocks(M, C)
         partial = torch.empty((nb, 2, C), dtype=F32, device=dev)
-        check(lib().jcm_bn_stats(_ptr(a), M, C, _ptr(partial), _stream()), 'jcm_bn_stats')
+        check(lib().jcm_bn_stats(_ptr(a), a_bf16, M, C, _ptr(partial), _stream()), 'jcm_bn_stats')
     check(lib().jcm_bn_finalize(_ptr(partial), M, C, _ptr(gamma), _ptr(beta), _ptr(moving_mean), _ptr(moving_var), BN_EPS, BN_DECAY,
                                 int(train), int(update_moving), _ptr(ss[0]), _ptr(ss[1]), _ptr(saved[0] if save else None),
                                 _ptr(saved[1] if save else None), _stream()), 'jcm_bn_finalize')
@@ -249,12 +261,12 @@ def bn_scale_shift(a, gamma, beta, moving_mean, moving_var, train, update_moving
 
 
 def bn_apply_pool(a, ss, pool, split, want_planes=True, want_f32=False):
-    _req(a, F32, 'a')
+    a_bf16 = _req_act(a, 'a')
     B, H, W, C = a.shape
     Ho, Wo = ((H + 1) // 2, (W + 1) // 2) if pool else (H, W)
     planes = _new_planes((B, Ho, Wo, C), a.device, split) if want_planes else None
     f32 = torch.empty((B, Ho, Wo, C), dtype=F32, device=a.device) if want_f32 else None
-    check(lib().jcm_bn_apply_pool(_ptr(a), _ptr(ss[0]), _ptr(ss[1]), B, H, W, C, int(pool), _ptr(planes.hi if planes else None),
+    check(lib().jcm_bn_apply_pool(_ptr(a), a_bf16, _ptr(ss[0]), _ptr(ss[1]), B, H, W, C, int(pool), _ptr(planes.hi if planes else None),
                                   _ptr(planes.lo if planes else None), _ptr(f32), _stream()), 'jcm_bn_apply_pool')
     if want_planes and want_f32:
         return planes, f32
@@ -262,13 +274,15 @@ def bn_apply_pool(a, ss, pool, split, want_planes=True, want_f32=False):
 
 
 def upsample_avg3(a1, a2, a3, ss6, split, want_planes=True, want_f32=False):
-    for t in (a1, a2, a3):
-        _req(t, F32, 'a')
+    flags = {_req_act(t, 'a') for t in (a1, a2, a3)}
+    if len(flags) != 1:
+        raise ValueError('the three bank outputs must have the same dtype')
+    a_bf16 = flags.pop()
     _req(ss6, F32, 'scale_shift')
     B, H, W, C = a1.shape
     planes = _new_planes((B, H, W, C), a1.device, split) if want_planes else None
     f32 = torch.empty((B, H, W, C), dtype=F32, device=a1.device) if want_f32 else None
-    check(lib().jcm_upsample_avg3(_ptr(a1), _ptr(a2), _ptr(a3), _ptr(ss6), B, H, W, a2.shape[1], a2.shape[2], a3.shape[1], a3.shape[2],
+    check(lib().jcm_upsample_avg3(_ptr(a1), _ptr(a2), _ptr(a3), a_bf16, _ptr(ss6), B, H, W, a2.shape[1], a2.shape[2], a3.shape[1], a3.shape[2],
                                   C, _ptr(planes.hi if planes else None), _ptr(planes.lo if planes else None), _ptr(f32), _stream()),
           'jcm_upsample_avg3')
     if want_planes and want_f32:

@@ -47,7 +47,7 @@ def bn_relu_bwd(a, dout, ss, saved, dy_scale, pool, split, dgamma, dbeta, dbias,
     f32 = torch.empty((B, H, W, C), dtype=F32, device=a.device) if want_f32 else None
     nb = lib().jcm_bn_relu_bwd_blocks(B * Ho * Wo, C)
     ws = torch.empty(((4 * nb + 2) * C,), dtype=F32, device=a.device)
-    check(lib().jcm_bn_relu_bwd(_ptr(a), _ptr(dout), _ptr(ss[0]), _ptr(ss[1]), _ptr(saved[0]), _ptr(saved[1]), float(dy_scale), B, H, W, C,
+    check(lib().jcm_bn_relu_bwd(_ptr(a), ops._req_act(a, 'a'), _ptr(dout), _ptr(ss[0]), _ptr(ss[1]), _ptr(saved[0]), _ptr(saved[1]), float(dy_scale), B, H, W, C,
                                 int(pool), _ptr(planes.hi), _ptr(planes.lo), _ptr(f32), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), _ptr(ws),
                                 _stream()), 'jcm_bn_relu_bwd')
     return (planes, f32) if want_f32 else planes
@@ -210,7 +210,8 @@ class Trainer:
         def fwd_layer(xp, name, ksize, kind='fwd'):
             w, b = p[name + '/weights'], p[name + '/biases']
             a = ops.conv2d_planes(xp, ctx.packed(name, w, kind), b, w.shape[3], ksize, relu=True,
-                                  alg_kdim=w.shape[0] * w.shape[1] * w.shape[2])
+                                  alg_kdim=w.shape[0] * w.shape[1] * w.shape[2],
+                                  out_bf16=ctx.act_bf16 and w.shape[3] % 64 == 0)   # narrow (--debug) layers keep fp32 activations
             ss, st = ops.bn_scale_shift(a, p[name + '/BatchNorm/gamma'], p[name + '/BatchNorm/beta'], p[name + '/BatchNorm/moving_mean'],
                                         p[name + '/BatchNorm/moving_variance'], train=True, save=True)
             saved[name] = (xp, a, ss, st)

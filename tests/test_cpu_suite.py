@@ -112,7 +112,7 @@ def test_argument_errors_do_not_need_a_gpu(built_lib):
     """Bad arguments are rejected on the host with a negative code and a message (ValueError in the Python layer)."""
     import jcm
     l = jcm.lib()
-    rc = l.jcm_conv2d_fwd(None, None, None, None, None, None, 1, 8, 8, 64, 64, 64, 3, 0, 1, None)
+    rc = l.jcm_conv2d_fwd(None, None, None, None, None, None, 0, 1, 8, 8, 64, 64, 64, 3, 0, 1, None)
     assert rc == -1 and b'null pointer' in l.jcm_last_error()
     rc = l.jcm_spatial_softmax(None, 1, 10, 7, None, None)
     assert rc == -1

@@ -87,13 +87,17 @@ def test_spatial_softmax_bwd(jcm, jtrain, accumulate):
 # ------------------------------------------------------------------------------------------------ BN / ReLU / pool / upsample
 @pytest.mark.parametrize('shape,pool', [((2, 12, 20, 64), False), ((2, 12, 20, 64), True), ((1, 15, 23, 128), True),
                                         ((3, 9, 7, 16), True), ((1, 30, 45, 512), False)])
-@pytest.mark.parametrize('split', [False, True])
+@pytest.mark.parametrize('split', [False, True, 'bf16act'])
 def test_bn_relu_pool_bwd(jcm, jtrain, shape, pool, split):
     """conv output -> ReLU -> batch norm (batch statistics) [-> 2x2 SAME max-pool]: gradients w.r.t. the conv output, gamma, beta
     and the conv bias, as TF autodiff of main.py:156-174 gives them."""
     g = torch.Generator().manual_seed(13)
     B, H, W, C = shape
     pre = torch.randn(B, H, W, C, generator=g)
+    act_bf16 = split == 'bf16act'        # activations stored in bf16 (bf16 training configuration)
+    if act_bf16:
+        split = False
+        pre = torch.where(pre > 0, bf16r(pre), pre)      # relu(pre) is then exactly representable in bf16
     gamma = torch.rand(C, generator=g) + 0.5
     beta = torch.randn(C, generator=g) * 0.2
     pre64 = pre.double().requires_grad_(True)
@@ -107,6 +111,8 @@ def test_bn_relu_pool_bwd(jcm, jtrain, shape, pool, split):
     (out * dout.double() * dy_scale).sum().backward()
 
     a = torch.relu(pre).cuda()
+    if act_bf16:
+        a = a.to(torch.bfloat16)
     mm, mv = torch.zeros(C, device='cuda'), torch.ones(C, device='cuda')
     ss, st = jcm.ops.bn_scale_shift(a, gamma.cuda(), beta.cuda(), mm, mv, train=True, save=True)
     dgamma, dbeta, dbias = (torch.empty(C, device='cuda') for _ in range(3))
@@ -301,7 +307,7 @@ def test_grad_prepare_clip_and_optimizer_steps(jcm, optimizer):
 
 
 # ------------------------------------------------------------------------------------------------ whole training step
-def _train_case(jcm, jtrain, B, H, W, K, debug, precision, use_sm, seed=4, pin_relu=True):
+def _train_case(jcm, jtrain, B, H, W, K, debug, precision, use_sm, seed=4, pin_relu=True, bf16_activations=False):
     gen = torch.Generator().manual_seed(seed)
     hm_h, hm_w = H // 8, W // 8
     names = orc.JOINT_NAMES[:K] + ['torso']
@@ -326,7 +332,8 @@ def _train_case(jcm, jtrain, B, H, W, K, debug, precision, use_sm, seed=4, pin_r
 
     p = jcm.load_params(p32)
     smp = jcm.PairwiseParams.from_dict(sm32, names, K)
-    ctx = jcm.Context(n_joints=K, joint_names=names, flag_train=True, precision=precision, debug=debug, use_sm=use_sm)
+    ctx = jcm.Context(n_joints=K, joint_names=names, flag_train=True, precision=precision, debug=debug, use_sm=use_sm,
+                      bf16_activations=bf16_activations)
     tr = jtrain.Trainer(p, smp, ctx)
     tap = {}
     res = tr.forward_backward(x.cuda(), y.cuda(), tap=tap)
@@ -365,8 +372,10 @@ def test_training_step_gradients_fp32(jcm, jtrain, cfg):
     assert not bad, bad
 
 
-def test_training_step_gradients_bf16(jcm, jtrain):
-    ref, got, out, res = _train_case(jcm, jtrain, 2, 96, 160, 4, True, 'bf16', True)
+@pytest.mark.parametrize('bf16_activations', [False, True])
+def test_training_step_gradients_bf16(jcm, jtrain, bf16_activations):
+    # debug=False for the bf16-activation variant: only layers with >= 64 output channels store bf16 activations
+    ref, got, out, res = _train_case(jcm, jtrain, 2, 96, 160, 4, not bf16_activations, 'bf16', True, bf16_activations=bf16_activations)
     assert abs(float(res['loss_pd']) - float(out['loss_pd'])) < 1e-2 * float(out['loss_pd'])
     for k, r in ref.items():
         if k.endswith('/weights') or k.startswith('energy_'):

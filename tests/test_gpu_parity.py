@@ -81,6 +81,9 @@ def test_conv2d_tcgen05_matches_oracle(jcm, case, split):
     ref = torch.relu(orc.conv2d(xr.double(), wr.double(), 1) + b.double())
     assert rel(y, ref) < 2e-4
     assert rel(y, yn) < 2e-4
+    if Cout % 64 == 0:     # bf16 activation output (bf16 training configuration): the same accumulators, rounded once
+        yb = jcm.ops.conv2d_planes(xp, wp, b.cuda(), Cout, k, relu=True, out_bf16=True)
+        assert yb.dtype == torch.bfloat16 and torch.equal(yb, y.to(torch.bfloat16))
 
 
 @pytest.mark.parametrize('split', [False, True])
@@ -130,6 +133,17 @@ def test_batch_norm_and_pool(jcm, shape, train):
         assert rel(pooled, orc.max_pool_layer(ref)) < 1e-5
     assert rel(d['moving_mean'], bn64['moving_mean']) < 1e-5          # updated in place iff train
     assert rel(d['moving_variance'], bn64['moving_variance']) < 1e-5
+    if C % 4 == 0:
+        # bf16-stored activations: identical arithmetic on the bf16-rounded input
+        ab = a.to(torch.bfloat16)
+        d2 = {k: v.cuda() for k, v in bn.items()}
+        bn64b = {k: v.double().clone() for k, v in bn.items()}
+        refb = orc.batch_norm(ab.double(), bn64b, train)
+        ssb = jcm.ops.bn_scale_shift(ab.cuda(), d2['gamma'], d2['beta'], d2['moving_mean'], d2['moving_variance'], train=train)
+        f32b = jcm.ops.bn_apply_pool(ab.cuda(), ssb, False, False, want_planes=False, want_f32=True)
+        assert rel(f32b, refb) < 1e-5
+        pooledb = jcm.ops.bn_apply_pool(ab.cuda(), ssb, True, False, want_planes=False, want_f32=True)
+        assert rel(pooledb, orc.max_pool_layer(refb)) < 1e-5
 
 
 def test_upsample_avg3(jcm):
@@ -141,6 +155,11 @@ def test_upsample_avg3(jcm):
            + orc.resize_images(d(a3) * d(ss6[4]) + d(ss6[5]), 60, 90)) / 3
     out = jcm.ops.upsample_avg3(a1.cuda(), a2.cuda(), a3.cuda(), ss6.cuda(), False, want_planes=False, want_f32=True)
     assert rel(out, ref) < 1e-5
+    b1, b2, b3 = (t.to(torch.bfloat16) for t in (a1, a2, a3))       # bf16-stored bank outputs
+    refb = (d(b1) * d(ss6[0]) + d(ss6[1]) + orc.resize_images(d(b2) * d(ss6[2]) + d(ss6[3]), 60, 90)
+            + orc.resize_images(d(b3) * d(ss6[4]) + d(ss6[5]), 60, 90)) / 3
+    outb = jcm.ops.upsample_avg3(b1.cuda(), b2.cuda(), b3.cuda(), ss6.cuda(), False, want_planes=False, want_f32=True)
+    assert rel(outb, refb) < 1e-5
 
 
 # ------------------------------------------------------------------------------------------------ heads
