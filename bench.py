@@ -332,7 +332,9 @@ def run_ours(args):
     line = {
         'metric': metric_name(args.workload), 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'bf16 operands, fp32 accumulate' if train else 'bf16x3 split products (fp32-equivalent), fp32 accumulate',
+        'dtype': 'bf16' if train else 'f32',
+        'dtype_detail': 'bf16 tensor-core operands, fp32 accumulation, fp32 master weights / activations / optimizer' if train
+                        else 'fp32-equivalent: every product is 3 bf16 tensor-core MMAs (hi*hi + lo*hi + hi*lo), fp32 accumulation',
         'data': 'synthetic', 'config': workload_config(args.workload, world),
         'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': int(x_host.numel() * 4 + y_host.numel() * 4),
                 'd2h_bytes_per_step': 4},

@@ -426,3 +426,9 @@ def test_eval_error_matches_oracle(jcm):
     want /= n // bs
     assert abs(got[0] - want[0]) < 1e-3 * want[0] and abs(got[1] - want[1]) < 1e-3 * want[1]
     assert got[2] == pytest.approx(want[2], abs=1e-4) and got[3] == pytest.approx(want[3], abs=1e-4)
+
+
+def test_graft_entry_smoke(jcm):
+    """The driver's smoke(): one small invocation of the hot path on cuda:0 checked against the oracle."""
+    import __graft_entry__ as ge
+    ge.smoke()
