@@ -28,9 +28,28 @@ sys.path.insert(0, os.path.join(ROOT, 'joint-cnn-mrf_b200'))
 import numpy as np
 import torch
 
-K_JOINTS = 7
-IMG_H, IMG_W = 480, 720
-HM_H, HM_W = 60, 90
+# workload -> (per-GPU batch, K, image H, W, training step?, precision)
+WORKLOADS = {'fwd16': (16, 7, 480, 720, False, 'fp32'), 'train64': (64, 7, 480, 720, True, 'bf16'),
+             'train_k14': (32, 14, 768, 1024, True, 'bf16')}   # BASELINE configs[4]: K=14, 96x128 maps, 32 images per GPU
+
+
+def synthetic_pairwise(names, K, H, W, rng):
+    """Pairwise-prior table for joint sets without FLIC statistics (K=14): non-negative, sum 1, smoothed histogram of 4000 displacements
+    ~ N(0, (H/6)^2) centred at (H, W), as float64 [2H,2W] arrays keyed '<joint>_<cond>'."""
+    c = np.array([1, 8, 28, 56, 70, 56, 28, 8, 1], dtype=np.float64) / 256
+    out = {}
+    for jn in names[:K]:
+        for cn in names:
+            if cn == jn:
+                continue
+            pd = np.zeros([2 * H, 2 * W])
+            mu = rng.normal(0, H / 8, size=2)
+            d = np.rint(rng.normal(mu, H / 6, size=(4000, 2))).astype(int)
+            np.add.at(pd, (np.clip(H + d[:, 0], 0, 2 * H - 1), np.clip(W + d[:, 1], 0, 2 * W - 1)), 1)
+            pd /= pd.sum()
+            pd = np.apply_along_axis(lambda v: np.convolve(v, c, mode='same'), 0, pd)      # separable 9x9 binomial smoothing
+            out[jn + '_' + cn] = np.apply_along_axis(lambda v: np.convolve(v, c, mode='same'), 1, pd)
+    return out
 PD_FWD_FLOP = 2 * 203.718e9      # per image, SURVEY Appendix A (K=7)
 SM_FWD_FLOP = 2 * 1.469e9        # per image, K^2 (H+1)(W+1)HW MACs
 
@@ -106,22 +125,26 @@ def cpu_reference_step_fn(workload, sample_b):
     import jcm_oracle as orc
     torch.set_num_threads(os.cpu_count() or 1)
     gen = torch.Generator().manual_seed(0)
-    train = workload == 'train64'
-    p = orc.init_part_detector(K_JOINTS, gen, dtype=torch.float32, requires_grad=train)
-    with np.load(os.path.join(ROOT, 'joint-cnn-mrf_b200', 'jcm', 'data', 'pairwise_distribution.npz')) as z:
-        distr = {k: z[k] for k in z.files}
-    sm = orc.init_spatial_model(distr, K_JOINTS, HM_H, HM_W, dtype=torch.float32, requires_grad=train)
-    x = torch.rand(sample_b, IMG_H, IMG_W, 3, generator=gen)
-    y = torch.from_numpy(synthetic_labels(sample_b, HM_H, HM_W, K_JOINTS + 1, np.random.default_rng(0)))
+    _, K, H, W, train, _ = WORKLOADS[workload]
+    names = orc.JOINT_NAMES[:K] + ['torso'] if K <= 9 else ['j%02d' % i for i in range(K)] + ['torso']
+    p = orc.init_part_detector(K, gen, dtype=torch.float32, requires_grad=train)
+    if K <= 9:
+        with np.load(os.path.join(ROOT, 'joint-cnn-mrf_b200', 'jcm', 'data', 'pairwise_distribution.npz')) as z:
+            distr = {k: z[k] for k in z.files}
+    else:
+        distr = synthetic_pairwise(names, K, H // 8, W // 8, np.random.default_rng(0))
+    sm = orc.init_spatial_model(distr, K, H // 8, W // 8, joint_names=names, dtype=torch.float32, requires_grad=train)
+    x = torch.rand(sample_b, H, W, 3, generator=gen)
+    y = torch.from_numpy(synthetic_labels(sample_b, H // 8, W // 8, K + 1, np.random.default_rng(0)))
 
     def step():
         if train:
-            out = orc.tower_forward(x, y, p, sm, K_JOINTS, True)
+            out = orc.tower_forward(x, y, p, sm, K, True, joint_names=names)
             params = [v for k, v in list(p.items()) + list(sm.items()) if v.requires_grad]
             torch.autograd.grad(out['loss'], params, allow_unused=True)
         else:
             with torch.no_grad():
-                orc.tower_forward(x, y, p, sm, K_JOINTS, False)
+                orc.tower_forward(x, y, p, sm, K, False, joint_names=names)
     return step
 
 
@@ -161,20 +184,21 @@ def run_reference(args):
 
 
 def metric_name(workload):
-    """BASELINE.json's metric (images/sec fwd+bwd at 720x480, K=7); the forward-only configuration is named as such."""
-    return 'images/sec fwd+bwd (720x480, K=7 joints)' if workload == 'train64' else 'images/sec fwd (720x480, K=7 joints)'
+    """BASELINE.json's metric (images/sec fwd+bwd at 720x480, K=7); the other configurations are named as such."""
+    return {'train64': 'images/sec fwd+bwd (720x480, K=7 joints)', 'fwd16': 'images/sec fwd (720x480, K=7 joints)',
+            'train_k14': 'images/sec fwd+bwd (1024x768, K=14 joints)'}[workload]
 
 
 def workload_config(workload, n_gpus):
-    if workload == 'fwd16':
-        return {'workload': 'BASELINE configs[1]: part-detector + spatial-model forward (+ softmax-CE heads), batch 16 per GPU, K=7, '
-                            '720x480x3 synthetic, fp32-equivalent (bf16x3 split) tensor-core convs, inference-mode BN',
-                'per_gpu_batch': 16, 'global_batch': 16 * n_gpus, 'K': K_JOINTS, 'image': [IMG_H, IMG_W], 'heat_map': [HM_H, HM_W],
-                'l2': 'inputs + activations per step (> 1 GB) exceed the 126 MB L2', 'parallelism': 'dp%d' % n_gpus}
-    return {'workload': 'BASELINE configs[2]: joint training fwd+bwd + grad all-reduce + clip + Adam, batch 64 per GPU, K=7, 720x480x3 '
-                        'synthetic, bf16 tensor-core operands / fp32 accumulation',
-            'per_gpu_batch': 64, 'global_batch': 64 * n_gpus, 'K': K_JOINTS, 'image': [IMG_H, IMG_W], 'heat_map': [HM_H, HM_W],
-            'l2': 'inputs + activations per step (> 4 GB) exceed the 126 MB L2', 'parallelism': 'dp%d' % n_gpus}
+    B, K, H, W, train, precision = WORKLOADS[workload]
+    what = {'fwd16': 'BASELINE configs[1]: part-detector + spatial-model forward (+ softmax-CE heads), batch 16 per GPU, K=7, 720x480x3 '
+                     'synthetic, fp32-equivalent (bf16x3 split) tensor-core convs, inference-mode BN',
+            'train64': 'BASELINE configs[2]: joint training fwd+bwd + grad all-reduce + clip + Adam, batch 64 per GPU, K=7, 720x480x3 '
+                       'synthetic, bf16 tensor-core operands / fp32 accumulation',
+            'train_k14': 'BASELINE configs[4]: joint training fwd+bwd + grad all-reduce + clip + Adam, batch 32 per GPU, K=14 (196 pairwise '
+                         'terms), 1024x768x3 synthetic, 96x128 heat maps, bf16 tensor-core operands / fp32 accumulation'}[workload]
+    return {'workload': what, 'per_gpu_batch': B, 'global_batch': B * n_gpus, 'K': K, 'image': [H, W], 'heat_map': [H // 8, W // 8],
+            'l2': 'inputs + activations per step (> 1 GB) exceed the 126 MB L2', 'parallelism': 'dp%d' % n_gpus}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -196,18 +220,21 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=dev)
     jcm.lib()  # fail loudly if libjcm.so is missing
 
-    train = args.workload == 'train64'
-    B = 64 if train else 16
-    precision = 'bf16' if train else 'fp32'
+    B, K, IH, IW, train, precision = WORKLOADS[args.workload]
     gen = torch.Generator().manual_seed(1234 + rank)
     wgen = torch.Generator().manual_seed(0)          # identical parameters on every replica
-    p = jcm.init_part_detector(K_JOINTS, wgen, device=dev)
-    names = jcm.JOINT_NAMES[:K_JOINTS] + ['torso']
-    sm = jcm.PairwiseParams.from_distribution(jcm.get_pairwise_distr(), names, K_JOINTS, HM_H, HM_W, device=dev)
-    ctx = jcm.Context(n_joints=K_JOINTS, joint_names=names, flag_train=train, precision=precision)
+    p = jcm.init_part_detector(K, wgen, device=dev)
+    if K <= 9:
+        names = jcm.JOINT_NAMES[:K] + ['torso']
+        distr = jcm.get_pairwise_distr()
+    else:
+        names = ['j%02d' % i for i in range(K)] + ['torso']
+        distr = synthetic_pairwise(names, K, IH // 8, IW // 8, np.random.default_rng(0))
+    sm = jcm.PairwiseParams.from_distribution(distr, names, K, IH // 8, IW // 8, device=dev)
+    ctx = jcm.Context(n_joints=K, joint_names=names, flag_train=train, precision=precision)
 
-    x_host = torch.rand(B, IMG_H, IMG_W, 3, generator=gen).pin_memory()
-    y_host = torch.from_numpy(synthetic_labels(B, HM_H, HM_W, K_JOINTS + 1, np.random.default_rng(rank))).pin_memory()
+    x_host = torch.rand(B, IH, IW, 3, generator=gen).pin_memory()
+    y_host = torch.from_numpy(synthetic_labels(B, IH // 8, IW // 8, K + 1, np.random.default_rng(rank))).pin_memory()
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
 
     if train:
@@ -305,7 +332,7 @@ def run_ours(args):
     try:
         with open(os.path.join(ROOT, 'profiles', 'r01', 'ncu_full_train64_v8_traffic.json')) as f:
             tj = json.load(f)
-        if train:
+        if args.workload == 'train64':
             traffic = tj['kernels']['conv_igemm_kernel']['dram_bytes_per_launch']
             traffic_src = 'profiles/r01/ncu_full_train64_v8_traffic.json (mean over the 25 launches of a step)'
     except Exception:
@@ -355,7 +382,7 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--workload', default=None, choices=['fwd16', 'train64'])
+    ap.add_argument('--workload', default=None, choices=sorted(WORKLOADS))
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

@@ -704,9 +704,15 @@ void fill_dp_dims(DpDims& dp, const SmDims& df, const SmDims& dm, int B, int H, 
   dp.LS = dp.Wm + TXD - 1;
   if ((dp.LS & 1) == 0) ++dp.LS;
   dp.npairs = 2 * df.G;
-  int nch = jcm_num_sms() / P;
-  if (nch < 1) nch = 1;
-  if (nch > dp.npairs) nch = dp.npairs;
+  // chunks of image pairs per pair (grid.y): the count (<= 8) whose P * n CTAs fill whole waves of the SMs best
+  // (K=7: 49 pairs x 3 = 147 CTAs on 148 SMs; K=14: 196 x 3 = 588 = 3.97 waves instead of 196 = 1.32 waves)
+  int nch = 1;
+  double best = -1.0;
+  for (int n = 1; n <= 8 && n <= dp.npairs; ++n) {
+    const long ctas = (long)P * n;
+    const double eff = (double)ctas / (double)(jcm_cdiv((int)ctas, jcm_num_sms()) * (long)jcm_num_sms());
+    if (eff > best + 0.02) { best = eff; nch = n; }
+  }
   dp.nchunks = nch;
   dp.lbuf = dp.Hm * dp.LS;
   dp.cbuf = (H + 1) * dp.Wm;
