@@ -1,19 +1,17 @@
 #!/bin/bash
 # Profiling pass (run on the GPU box through gpurun, from the repo root):  bash profiles/run_profile.sh [workload]
-# Produces in gpurun_out/: launches_<wl>.csv (every launch with its device time), conv_<wl>.ncu-rep / sm_<wl>.ncu-rep
-# (--set full captures of the two hot kernels) and their raw-page CSVs.  Numbers printed under ncu are never bench values.
-WL=${1:-fwd16}
+# Produces in gpurun_out/ (small files only - a full report of a whole step is ~85 MB and stays on the box):
+#   launches_<wl>.csv        every launch of the run with its device time (ncu, cold-cache, serialised: compare SHARES)
+#   prof_<wl>_raw.csv        --set full counters of every conv / spatial-model launch of the first step (raw page as CSV)
+# then here:  python profiles/launch_summary.py gpurun_out/launches_<wl>.csv 3   and   python profiles/ncu_summary.py ...
+# Numbers printed by bench.py under ncu are never bench values.
+WL=${1:-train64}
 mkdir -p gpurun_out
 NCU=$(command -v ncu || echo /usr/local/cuda/bin/ncu)
-# 1) launch list of two steady-state steps (skip the warm-up launches)
-$NCU --metrics gpu__time_duration.sum --clock-control none -s ${SKIP:-300} -c ${COUNT:-200} --csv --log-file gpurun_out/launches_${WL}.csv \
-    python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/launches_${WL}.log 2>&1
-# 2) full capture of the dominant conv kernel (conv5 + conv6 of one step) and of the spatial-model kernel
-$NCU --set full --clock-control none --import-source on -k regex:conv_igemm -s ${CONV_SKIP:-26} -c 2 -f -o gpurun_out/conv_${WL} \
-    python bench.py --workload $WL --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_conv_${WL}.log 2>&1
-$NCU --set full --clock-control none --import-source on -k regex:sm_conv -s 1 -c 1 -f -o gpurun_out/sm_${WL} \
-    python bench.py --workload $WL --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_sm_${WL}.log 2>&1
-for r in conv_${WL} sm_${WL}; do
-  $NCU -i gpurun_out/$r.ncu-rep --page raw --csv > gpurun_out/$r.raw.csv 2>/dev/null
-done
-ls -la gpurun_out/
+$NCU --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${WL}.csv \
+    python bench.py --workload $WL --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/launches_${WL}.log 2>&1
+$NCU --set full --clock-control none --import-source on -k regex:"conv_igemm_kernel|conv_wgrad_kernel|sm_conv_kernel|sm_bwd_dp_kernel" \
+    -c ${COUNT:-42} -f -o /tmp/prof_${WL} python bench.py --workload $WL --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_${WL}.log 2>&1
+$NCU -i /tmp/prof_${WL}.ncu-rep --page raw --csv > gpurun_out/prof_${WL}_raw.csv 2>/dev/null
+$NCU -i /tmp/prof_${WL}.ncu-rep --page source --csv -k regex:sm_conv_kernel -c 1 > gpurun_out/prof_${WL}_smconv_source.csv 2>/dev/null
+ls -la gpurun_out/ /tmp/prof_${WL}.ncu-rep
