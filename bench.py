@@ -231,7 +231,8 @@ def run_ours(args):
         names = ['j%02d' % i for i in range(K)] + ['torso']
         distr = synthetic_pairwise(names, K, IH // 8, IW // 8, np.random.default_rng(0))
     sm = jcm.PairwiseParams.from_distribution(distr, names, K, IH // 8, IW // 8, device=dev)
-    ctx = jcm.Context(n_joints=K, joint_names=names, flag_train=train, precision=precision)
+    ctx = jcm.Context(n_joints=K, joint_names=names, flag_train=train, precision=precision,
+                      bf16_activations=None if args.bf16_activations is None else bool(args.bf16_activations))
 
     x_host = torch.rand(B, IH, IW, 3, generator=gen).pin_memory()
     y_host = torch.from_numpy(synthetic_labels(B, IH // 8, IW // 8, K + 1, np.random.default_rng(rank))).pin_memory()
@@ -360,7 +361,7 @@ def run_ours(args):
         'metric': metric_name(args.workload), 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'bf16' if train else 'f32',
-        'dtype_detail': 'bf16 tensor-core operands, fp32 accumulation, fp32 master weights / activations / optimizer' if train
+        'dtype_detail': 'bf16 tensor-core operands and stored activations, fp32 accumulation, fp32 master weights / gradients / optimizer' if train
                         else 'fp32-equivalent: every product is 3 bf16 tensor-core MMAs (hi*hi + lo*hi + hi*lo), fp32 accumulation',
         'data': 'synthetic', 'config': workload_config(args.workload, world),
         'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': int(x_host.numel() * 4 + y_host.numel() * 4),
@@ -385,6 +386,8 @@ def main():
     ap.add_argument('--workload', default=None, choices=sorted(WORKLOADS))
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--bf16-activations', type=int, default=None,
+                    help='store the post-ReLU activations in bf16 too (bf16 workloads); default: the library default')
     args = ap.parse_args()
     if args.workload is None:
         args.workload = default_workload()

@@ -80,42 +80,47 @@ struct BnBwdArgs {
   float* partial;          // [grid][2][C]
 };
 
-template <int PASS>
+template <int PASS, int VEC>
 __global__ void bn_relu_bwd_kernel(BnBwdArgs p) {
-  extern __shared__ float sh[];  // [kThreads][8]
-  const int C4 = p.C / 4;
-  const int lanes = kThreads / C4;
-  const int g = threadIdx.x % C4, rl = threadIdx.x / C4;
+  extern __shared__ float sh[];  // [kThreads][2 * VEC]
+  const int CG = p.C / VEC;      // channel groups of VEC channels (VEC = 8 for bf16-stored activations: 16-byte loads)
+  const int lanes = kThreads / CG;
+  const int g = threadIdx.x % CG, rl = threadIdx.x / CG;
   const int Ho = p.pool ? (p.H + 1) / 2 : p.H, Wo = p.pool ? (p.W + 1) / 2 : p.W;
   const long M = (long)p.B * Ho * Wo;
   const long per_blk = (M + gridDim.x - 1) / gridDim.x;
   const long r0 = blockIdx.x * per_blk;
   long r1 = r0 + per_blk;
   if (r1 > M) r1 = M;
-  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
-  if (rl < lanes) {
-    const float4 sc = reinterpret_cast<const float4*>(p.scale)[g];
-    const float4 sf = reinterpret_cast<const float4*>(p.shift)[g];
-    const float4 mu = reinterpret_cast<const float4*>(p.mean)[g];
-    const float4 rs = reinterpret_cast<const float4*>(p.rstd)[g];
-    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, sfv[4] = {sf.x, sf.y, sf.z, sf.w};
-    const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, rsv[4] = {rs.x, rs.y, rs.z, rs.w};
-    float m_dy[4] = {0.f, 0.f, 0.f, 0.f}, m_dyx[4] = {0.f, 0.f, 0.f, 0.f};
-    if (PASS == 1) {
-      const float4 a0 = reinterpret_cast<const float4*>(p.sums)[g];
-      const float4 a1 = reinterpret_cast<const float4*>(p.sums + p.C)[g];
-      m_dy[0] = a0.x * p.inv_count; m_dy[1] = a0.y * p.inv_count; m_dy[2] = a0.z * p.inv_count; m_dy[3] = a0.w * p.inv_count;
-      m_dyx[0] = a1.x * p.inv_count; m_dyx[1] = a1.y * p.inv_count; m_dyx[2] = a1.z * p.inv_count; m_dyx[3] = a1.w * p.inv_count;
-    }
-    for (long r = r0 + rl; r < r1; r += lanes) {
-      const float4 d4 = *reinterpret_cast<const float4*>(p.dout + r * p.C + g * 4);
-      const float dv[4] = {d4.x * p.dy_scale, d4.y * p.dy_scale, d4.z * p.dy_scale, d4.w * p.dy_scale};
-      if (!p.pool) {
-        const float4 a4 = load_act4(p.a, (r * p.C + g * 4) >> 2, p.a_bf16);
-        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-        float o[4];
+  float s0[VEC], s1[VEC];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < VEC; ++c) { s0[c] = 0.f; s1[c] = 0.f; }
+  if (rl < lanes) {
+    float scv[VEC], sfv[VEC], muv[VEC], rsv[VEC], m_dy[VEC], m_dyx[VEC];
+    load_f32_vec<VEC>(p.scale, (long)g * VEC, scv);
+    load_f32_vec<VEC>(p.shift, (long)g * VEC, sfv);
+    load_f32_vec<VEC>(p.mean, (long)g * VEC, muv);
+    load_f32_vec<VEC>(p.rstd, (long)g * VEC, rsv);
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) { m_dy[c] = 0.f; m_dyx[c] = 0.f; }
+    if (PASS == 1) {
+      load_f32_vec<VEC>(p.sums, (long)g * VEC, m_dy);
+      load_f32_vec<VEC>(p.sums + p.C, (long)g * VEC, m_dyx);
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) { m_dy[c] *= p.inv_count; m_dyx[c] *= p.inv_count; }
+    }
+    if (!p.pool) {
+      // two rows in flight per thread: these loops are latency- rather than bandwidth-bound with one
+#pragma unroll 2
+      for (long r = r0 + rl; r < r1; r += lanes) {
+        float dv[VEC];
+        load_f32_vec<VEC>(p.dout, r * p.C + (long)g * VEC, dv);
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) dv[c] *= p.dy_scale;
+        float av[VEC], o[VEC];
+        load_act_vec<VEC>(p.a, r * p.C + (long)g * VEC, p.a_bf16, av);
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
           const float xh = (av[c] - muv[c]) * rsv[c];
           if (PASS == 0) {
             s0[c] += dv[c];
@@ -126,35 +131,35 @@ __global__ void bn_relu_bwd_kernel(BnBwdArgs p) {
             s0[c] += o[c];
           }
         }
-        if (PASS == 1) {
-          const long i4 = r * C4 + g;
-          __align__(8) __nv_bfloat16 h[4];
-          __align__(8) __nv_bfloat16 l[4];
+        if (PASS == 1) store_planes_vec<VEC>(p.hi, p.lo, p.d_f32, r * p.C + (long)g * VEC, o);
+      }
+    } else {
+      for (long r = r0 + rl; r < r1; r += lanes) {
+        float dv[VEC];
+        load_f32_vec<VEC>(p.dout, r * p.C + (long)g * VEC, dv);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) split_bf16(o[c], h[c], l[c]);
-          reinterpret_cast<uint2*>(p.hi)[i4] = *reinterpret_cast<uint2*>(h);
-          if (p.lo) reinterpret_cast<uint2*>(p.lo)[i4] = *reinterpret_cast<uint2*>(l);
-          if (p.d_f32) reinterpret_cast<float4*>(p.d_f32)[i4] = make_float4(o[0], o[1], o[2], o[3]);
-        }
-      } else {
+        for (int c = 0; c < VEC; ++c) dv[c] *= p.dy_scale;
         const int xo = (int)(r % Wo);
         const long t = r / Wo;
         const int yo = (int)(t % Ho);
         const int n = (int)(t / Ho);
         const int y0 = 2 * yo, x0 = 2 * xo;
-        float av[4][4];   // [window element][channel]
+        float av[4][VEC];   // [window element][channel]
         bool ok[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int yy = y0 + (e >> 1), xx = x0 + (e & 1);
           ok[e] = yy < p.H && xx < p.W;
-          float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok[e]) a4 = load_act4(p.a, ((((long)n * p.H + yy) * p.W + xx) * p.C + g * 4) >> 2, p.a_bf16);
-          av[e][0] = a4.x; av[e][1] = a4.y; av[e][2] = a4.z; av[e][3] = a4.w;
-        }
-        float o[4][4];
+          if (ok[e]) {
+            load_act_vec<VEC>(p.a, (((long)n * p.H + yy) * p.W + xx) * p.C + (long)g * VEC, p.a_bf16, av[e]);
+          } else {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < VEC; ++c) av[e][c] = 0.f;
+          }
+        }
+        float o[4][VEC];
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
           int best = 0;
           float bv = fmaf(av[0][c], scv[c], sfv[c]);
 #pragma unroll
@@ -163,7 +168,10 @@ __global__ void bn_relu_bwd_kernel(BnBwdArgs p) {
             if (ok[e] && v > bv) { bv = v; best = e; }
           }
           if (PASS == 0) {
-            const float xh = (av[best][c] - muv[c]) * rsv[c];
+            float ab = av[0][c];       // av[best][c] without dynamic register indexing
+#pragma unroll
+            for (int e = 1; e < 4; ++e) ab = (best == e) ? av[e][c] : ab;
+            const float xh = (ab - muv[c]) * rsv[c];
             s0[c] += dv[c];
             s1[c] += dv[c] * xh;
           } else {
@@ -182,31 +190,24 @@ __global__ void bn_relu_bwd_kernel(BnBwdArgs p) {
           for (int e = 0; e < 4; ++e) {
             if (!ok[e]) continue;
             const int yy = y0 + (e >> 1), xx = x0 + (e & 1);
-            const long i4 = (((long)n * p.H + yy) * p.W + xx) * C4 + g;
-            __align__(8) __nv_bfloat16 h[4];
-            __align__(8) __nv_bfloat16 l[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) split_bf16(o[e][c], h[c], l[c]);
-            reinterpret_cast<uint2*>(p.hi)[i4] = *reinterpret_cast<uint2*>(h);
-            if (p.lo) reinterpret_cast<uint2*>(p.lo)[i4] = *reinterpret_cast<uint2*>(l);
-            if (p.d_f32) reinterpret_cast<float4*>(p.d_f32)[i4] = make_float4(o[e][0], o[e][1], o[e][2], o[e][3]);
+            store_planes_vec<VEC>(p.hi, p.lo, p.d_f32, (((long)n * p.H + yy) * p.W + xx) * p.C + (long)g * VEC, o[e]);
           }
         }
       }
     }
   }
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    sh[threadIdx.x * 8 + c] = s0[c];
-    sh[threadIdx.x * 8 + 4 + c] = s1[c];
+  for (int c = 0; c < VEC; ++c) {
+    sh[threadIdx.x * 2 * VEC + c] = s0[c];
+    sh[threadIdx.x * 2 * VEC + VEC + c] = s1[c];
   }
   __syncthreads();
   for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-    const int gg = c / 4, v = c % 4;
+    const int gg = c / VEC, v = c % VEC;
     float t0 = 0.f, t1 = 0.f;
     for (int l = 0; l < lanes; ++l) {
-      t0 += sh[(l * C4 + gg) * 8 + v];
-      t1 += sh[(l * C4 + gg) * 8 + 4 + v];
+      t0 += sh[(l * CG + gg) * 2 * VEC + v];
+      t1 += sh[(l * CG + gg) * 2 * VEC + VEC + v];
     }
     p.partial[((long)blockIdx.x * 2 + 0) * p.C + c] = t0;
     p.partial[((long)blockIdx.x * 2 + 1) * p.C + c] = t1;
@@ -351,13 +352,17 @@ extern "C" int jcm_bn_relu_bwd(const void* a, int a_bf16, const float* dout, con
   p.a = a; p.a_bf16 = a_bf16; p.dout = dout; p.scale = scale; p.shift = shift; p.mean = mean; p.rstd = rstd; p.sums = sums; p.dy_scale = dy_scale;
   p.B = B; p.H = H; p.W = W; p.C = C; p.pool = pool; p.inv_count = 1.0f / (float)((long)B * H * W);
   p.hi = (__nv_bfloat16*)d_hi; p.lo = (__nv_bfloat16*)d_lo; p.d_f32 = d_f32; p.partial = part0;
-  const size_t shb = kThreads * 8 * sizeof(float);
-  bn_relu_bwd_kernel<0><<<blocks, kThreads, shb, st>>>(p);
+  // bf16-stored activations with C a multiple of 8: 8 channels per thread (16-byte loads); else 4
+  const bool v8 = a_bf16 && (C % 8) == 0 && C / 8 <= kThreads;
+  const size_t shb = kThreads * (v8 ? 16 : 8) * sizeof(float);
+  if (v8) bn_relu_bwd_kernel<0, 8><<<blocks, kThreads, shb, st>>>(p);
+  else bn_relu_bwd_kernel<0, 4><<<blocks, kThreads, shb, st>>>(p);
   JCM_LAUNCH_CHECK();
   colsum_finalize_kernel<<<jcm_cdiv(C, 32), dim3(32, kPartY), 0, st>>>(part0, blocks, C, 2, sums, dbeta, dgamma);   // dbeta = sum dy, dgamma = sum dy * xhat
   JCM_LAUNCH_CHECK();
   p.partial = part1;
-  bn_relu_bwd_kernel<1><<<blocks, kThreads, shb, st>>>(p);
+  if (v8) bn_relu_bwd_kernel<1, 8><<<blocks, kThreads, shb, st>>>(p);
+  else bn_relu_bwd_kernel<1, 4><<<blocks, kThreads, shb, st>>>(p);
   JCM_LAUNCH_CHECK();
   colsum_finalize_kernel<<<jcm_cdiv(C, 32), dim3(32, kPartY), 0, st>>>(part1, blocks, C, 1, dbias, nullptr, nullptr);
   JCM_LAUNCH_CHECK();

@@ -107,3 +107,54 @@ __device__ __forceinline__ float4 load_act4(const void* __restrict__ base, long 
 __device__ __forceinline__ float load_act1(const void* __restrict__ base, long i, int is_bf16) {
   return is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[i]) : reinterpret_cast<const float*>(base)[i];
 }
+
+// VEC (4 or 8) consecutive channels starting at element index `e` (a multiple of VEC) of an activation tensor.
+// VEC == 8 is used for bf16-stored activations (one 16-byte load).
+template <int VEC>
+__device__ __forceinline__ void load_act_vec(const void* __restrict__ base, long e, int is_bf16, float (&f)[VEC]) {
+  if (VEC == 8 && is_bf16) {
+    const uint4 r = reinterpret_cast<const uint4*>(base)[e >> 3];
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC / 4; ++i) {
+      const float4 t = load_act4(base, (e >> 2) + i, is_bf16);
+      f[4 * i] = t.x; f[4 * i + 1] = t.y; f[4 * i + 2] = t.z; f[4 * i + 3] = t.w;
+    }
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void load_f32_vec(const float* __restrict__ base, long e, float (&f)[VEC]) {
+#pragma unroll
+  for (int i = 0; i < VEC / 4; ++i) {
+    const float4 t = reinterpret_cast<const float4*>(base)[(e >> 2) + i];
+    f[4 * i] = t.x; f[4 * i + 1] = t.y; f[4 * i + 2] = t.z; f[4 * i + 3] = t.w;
+  }
+}
+// fp32 values -> bf16 hi (+ lo) planes / fp32 copy, VEC consecutive channels at element index e
+template <int VEC>
+__device__ __forceinline__ void store_planes_vec(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ f32,
+                                                 long e, const float (&v)[VEC]) {
+  __align__(16) __nv_bfloat16 h[VEC];
+  __align__(16) __nv_bfloat16 l[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) split_bf16(v[i], h[i], l[i]);
+  if (VEC == 8) {
+    if (hi) reinterpret_cast<uint4*>(hi)[e >> 3] = *reinterpret_cast<uint4*>(h);
+    if (lo) reinterpret_cast<uint4*>(lo)[e >> 3] = *reinterpret_cast<uint4*>(l);
+  } else {
+    if (hi) reinterpret_cast<uint2*>(hi)[e >> 2] = *reinterpret_cast<uint2*>(h);
+    if (lo) reinterpret_cast<uint2*>(lo)[e >> 2] = *reinterpret_cast<uint2*>(l);
+  }
+  if (f32) {
+#pragma unroll
+    for (int i = 0; i < VEC / 4; ++i)
+      reinterpret_cast<float4*>(f32)[(e >> 2) + i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
+}

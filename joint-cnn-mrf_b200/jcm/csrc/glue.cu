@@ -31,7 +31,12 @@ __global__ void bn_stats_kernel(const void* __restrict__ x, int x_bf16, long M, 
   if (r1 > M) r1 = M;
   if (rl < lanes) {
     for (long r = r0 + rl; r < r1; r += lanes) {
-      if (VEC == 4) {
+      if (VEC == 8) {
+        float f[VEC];
+        load_act_vec<VEC>(x, r * C + (long)g * VEC, x_bf16, f);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { s[v] += f[v]; q[v] += f[v] * f[v]; }
+      } else if (VEC == 4) {
         const float4 v = load_act4(x, (r * C + g * 4) >> 2, x_bf16);
         s[0] += v.x; q[0] += v.x * v.x;
         s[1 % VEC] += v.y; q[1 % VEC] += v.y * v.y;
@@ -98,54 +103,52 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblock
 }
 
 // ------------------------------------------------------------------------------------------- BN apply (+pool)
-__device__ __forceinline__ void store_planes4(__nv_bfloat16* hi, __nv_bfloat16* lo, long idx4, float4 v) {
-  __align__(8) __nv_bfloat16 h[4];
-  __align__(8) __nv_bfloat16 l[4];
-  split_bf16(v.x, h[0], l[0]);
-  split_bf16(v.y, h[1], l[1]);
-  split_bf16(v.z, h[2], l[2]);
-  split_bf16(v.w, h[3], l[3]);
-  reinterpret_cast<uint2*>(hi)[idx4] = *reinterpret_cast<uint2*>(h);
-  if (lo) reinterpret_cast<uint2*>(lo)[idx4] = *reinterpret_cast<uint2*>(l);
-}
-
-__device__ __forceinline__ float4 affine4(float4 v, float4 sc, float4 sh) {
-  return make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
-}
-__device__ __forceinline__ float4 max4(float4 a, float4 b) {
-  return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
-}
-
+template <int VEC>
 __global__ void bn_apply_pool_kernel(const void* __restrict__ a, int a_bf16, const float* __restrict__ scale, const float* __restrict__ shift,
                                      int B, int H, int W, int C, int pool, __nv_bfloat16* __restrict__ hi,
                                      __nv_bfloat16* __restrict__ lo, float* __restrict__ out_f32) {
   const int Ho = pool ? (H + 1) / 2 : H, Wo = pool ? (W + 1) / 2 : W;
-  const int C4 = C / 4;
-  const long total = (long)B * Ho * Wo * C4;
+  const int CG = C / VEC;
+  const long total = (long)B * Ho * Wo * CG;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % C4);
-    long t = i / C4;
+    const int cg = (int)(i % CG);
+    long t = i / CG;
     const int xo = (int)(t % Wo);
     t /= Wo;
     const int yo = (int)(t % Ho);
     const int n = (int)(t / Ho);
-    const float4 sc = reinterpret_cast<const float4*>(scale)[c4];
-    const float4 sh = reinterpret_cast<const float4*>(shift)[c4];
-    float4 r;
+    float sc[VEC], sh[VEC], r[VEC];
+    load_f32_vec<VEC>(scale, (long)cg * VEC, sc);
+    load_f32_vec<VEC>(shift, (long)cg * VEC, sh);
     if (!pool) {
-      r = affine4(load_act4(a, i, a_bf16), sc, sh);
+      load_act_vec<VEC>(a, i * VEC, a_bf16, r);
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) r[c] = fmaf(r[c], sc[c], sh[c]);
     } else {
       const int y0 = 2 * yo, x0 = 2 * xo;
-      const long base4 = ((((long)n * H + y0) * W + x0) * C + c4 * 4) >> 2;   // index in units of 4 channels
-      const long C4l = C / 4;
-      r = affine4(load_act4(a, base4, a_bf16), sc, sh);
+      const long base = (((long)n * H + y0) * W + x0) * C + (long)cg * VEC;
+      load_act_vec<VEC>(a, base, a_bf16, r);
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) r[c] = fmaf(r[c], sc[c], sh[c]);
       const bool hx = x0 + 1 < W, hy = y0 + 1 < H;  // SAME pooling: the padded row/column never wins
-      if (hx) r = max4(r, affine4(load_act4(a, base4 + C4l, a_bf16), sc, sh));
-      if (hy) r = max4(r, affine4(load_act4(a, base4 + (long)W * C4l, a_bf16), sc, sh));
-      if (hx && hy) r = max4(r, affine4(load_act4(a, base4 + (long)W * C4l + C4l, a_bf16), sc, sh));
+      float v[VEC];
+      if (hx) {
+        load_act_vec<VEC>(a, base + C, a_bf16, v);
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) r[c] = fmaxf(r[c], fmaf(v[c], sc[c], sh[c]));
+      }
+      if (hy) {
+        load_act_vec<VEC>(a, base + (long)W * C, a_bf16, v);
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) r[c] = fmaxf(r[c], fmaf(v[c], sc[c], sh[c]));
+      }
+      if (hx && hy) {
+        load_act_vec<VEC>(a, base + (long)W * C + C, a_bf16, v);
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) r[c] = fmaxf(r[c], fmaf(v[c], sc[c], sh[c]));
+      }
     }
-    if (hi) store_planes4(hi, lo, i, r);
-    if (out_f32) reinterpret_cast<float4*>(out_f32)[i] = r;
+    store_planes_vec<VEC>(hi, lo, out_f32, i * VEC, r);
   }
 }
 
@@ -158,48 +161,57 @@ __device__ __forceinline__ void legacy_tap(int dst, int n_in, int n_out, int& lo
   hi = min(lo + 1, n_in - 1);
   w = src - (float)lo;
 }
-__device__ __forceinline__ float4 lerp4(float4 a, float4 b, float w) {
-  return make_float4(a.x + (b.x - a.x) * w, a.y + (b.y - a.y) * w, a.z + (b.z - a.z) * w, a.w + (b.w - a.w) * w);
-}
-__device__ __forceinline__ float4 resize_sample(const void* __restrict__ a, int a_bf16, int n, int Hi, int Wi, int C, int c4, int y, int x,
-                                                int Ho, int Wo, float4 sc, float4 sh) {
+template <int VEC>
+__device__ __forceinline__ void resize_sample(const void* __restrict__ a, int a_bf16, int n, int Hi, int Wi, int C, int cg, int y, int x,
+                                              int Ho, int Wo, const float (&sc)[VEC], const float (&sh)[VEC], float (&out)[VEC]) {
   int ylo, yhi, xlo, xhi;
   float wy, wx;
   legacy_tap(y, Hi, Ho, ylo, yhi, wy);
   legacy_tap(x, Wi, Wo, xlo, xhi, wx);
-  const long C4l = C / 4;
-  const long b4 = (long)n * Hi * Wi * C4l + c4;
-  const float4 tl = affine4(load_act4(a, b4 + ((long)ylo * Wi + xlo) * C4l, a_bf16), sc, sh);
-  const float4 tr = affine4(load_act4(a, b4 + ((long)ylo * Wi + xhi) * C4l, a_bf16), sc, sh);
-  const float4 bl = affine4(load_act4(a, b4 + ((long)yhi * Wi + xlo) * C4l, a_bf16), sc, sh);
-  const float4 br = affine4(load_act4(a, b4 + ((long)yhi * Wi + xhi) * C4l, a_bf16), sc, sh);
-  return lerp4(lerp4(tl, tr, wx), lerp4(bl, br, wx), wy);
+  const long b = (long)n * Hi * Wi * C + (long)cg * VEC;
+  float tl[VEC], tr[VEC], bl[VEC], br[VEC];
+  load_act_vec<VEC>(a, b + ((long)ylo * Wi + xlo) * C, a_bf16, tl);
+  load_act_vec<VEC>(a, b + ((long)ylo * Wi + xhi) * C, a_bf16, tr);
+  load_act_vec<VEC>(a, b + ((long)yhi * Wi + xlo) * C, a_bf16, bl);
+  load_act_vec<VEC>(a, b + ((long)yhi * Wi + xhi) * C, a_bf16, br);
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) {
+    const float vtl = fmaf(tl[c], sc[c], sh[c]), vtr = fmaf(tr[c], sc[c], sh[c]);
+    const float vbl = fmaf(bl[c], sc[c], sh[c]), vbr = fmaf(br[c], sc[c], sh[c]);
+    const float top = vtl + (vtr - vtl) * wx, bot = vbl + (vbr - vbl) * wx;
+    out[c] = top + (bot - top) * wy;
+  }
 }
 
+template <int VEC>
 __global__ void upsample_avg3_kernel(const void* __restrict__ a1, const void* __restrict__ a2, const void* __restrict__ a3, int a_bf16,
                                      const float* __restrict__ ss /* [6][C]: scale1, shift1, scale2, shift2, scale3, shift3 */,
                                      int B, int H, int W, int H2, int W2, int H3, int W3, int C, __nv_bfloat16* __restrict__ hi,
                                      __nv_bfloat16* __restrict__ lo, float* __restrict__ out_f32) {
-  const int C4 = C / 4;
-  const long total = (long)B * H * W * C4;
+  const int CG = C / VEC;
+  const long total = (long)B * H * W * CG;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % C4);
-    long t = i / C4;
+    const int cg = (int)(i % CG);
+    long t = i / CG;
     const int x = (int)(t % W);
     t /= W;
     const int y = (int)(t % H);
     const int n = (int)(t / H);
-    const float4* s4 = reinterpret_cast<const float4*>(ss);
-    const float4 v1 = affine4(load_act4(a1, i, a_bf16), s4[0 * C4 + c4], s4[1 * C4 + c4]);
-    const float4 v2 = resize_sample(a2, a_bf16, n, H2, W2, C, c4, y, x, H, W, s4[2 * C4 + c4], s4[3 * C4 + c4]);
-    const float4 v3 = resize_sample(a3, a_bf16, n, H3, W3, C, c4, y, x, H, W, s4[4 * C4 + c4], s4[5 * C4 + c4]);
-    float4 r;
-    r.x = (v1.x + v2.x + v3.x) / 3.0f;
-    r.y = (v1.y + v2.y + v3.y) / 3.0f;
-    r.z = (v1.z + v2.z + v3.z) / 3.0f;
-    r.w = (v1.w + v2.w + v3.w) / 3.0f;
-    if (hi) store_planes4(hi, lo, i, r);
-    if (out_f32) reinterpret_cast<float4*>(out_f32)[i] = r;
+    float sc[VEC], sh[VEC], v1[VEC], v2[VEC], v3[VEC], r[VEC];
+    load_f32_vec<VEC>(ss + 0 * C, (long)cg * VEC, sc);
+    load_f32_vec<VEC>(ss + 1 * C, (long)cg * VEC, sh);
+    load_act_vec<VEC>(a1, i * VEC, a_bf16, v1);
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) v1[c] = fmaf(v1[c], sc[c], sh[c]);
+    load_f32_vec<VEC>(ss + 2 * C, (long)cg * VEC, sc);
+    load_f32_vec<VEC>(ss + 3 * C, (long)cg * VEC, sh);
+    resize_sample<VEC>(a2, a_bf16, n, H2, W2, C, cg, y, x, H, W, sc, sh, v2);
+    load_f32_vec<VEC>(ss + 4 * C, (long)cg * VEC, sc);
+    load_f32_vec<VEC>(ss + 5 * C, (long)cg * VEC, sh);
+    resize_sample<VEC>(a3, a_bf16, n, H3, W3, C, cg, y, x, H, W, sc, sh, v3);
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) r[c] = (v1[c] + v2[c] + v3[c]) / 3.0f;
+    store_planes_vec<VEC>(hi, lo, out_f32, i * VEC, r);
   }
 }
 
@@ -324,7 +336,9 @@ extern "C" int jcm_bn_stats_blocks(long M, int C) {
 extern "C" int jcm_bn_stats(const void* x, int x_bf16, long M, int C, float* partial, void* stream) {
   JCM_CHECK_ARG(x && partial && M > 0 && C > 0, "jcm_bn_stats: bad arguments");
   const int blocks = jcm_bn_stats_blocks(M, C);
-  if ((C % 4) == 0 && C / 4 <= kStatThreads) {
+  if (x_bf16 && (C % 8) == 0 && C / 8 <= kStatThreads) {
+    bn_stats_kernel<8><<<blocks, kStatThreads, kStatThreads * 16 * sizeof(float), (cudaStream_t)stream>>>(x, x_bf16, M, C, partial);
+  } else if ((C % 4) == 0 && C / 4 <= kStatThreads) {
     bn_stats_kernel<4><<<blocks, kStatThreads, kStatThreads * 8 * sizeof(float), (cudaStream_t)stream>>>(x, x_bf16, M, C, partial);
   } else {
     JCM_CHECK_ARG(C <= kStatThreads, "jcm_bn_stats: C=%d not supported (must be a multiple of 4 <= 1024, or <= 256)", C);
@@ -369,9 +383,15 @@ extern "C" int jcm_bn_apply_pool(const void* a, int a_bf16, const float* scale, 
   JCM_CHECK_ARG(a && scale && shift && (out_hi || out_f32), "jcm_bn_apply_pool: null pointer");
   JCM_CHECK_ARG((C % 4) == 0, "jcm_bn_apply_pool: C must be a multiple of 4, got %d", C);
   const int Ho = pool ? (H + 1) / 2 : H, Wo = pool ? (W + 1) / 2 : W;
-  const long total = (long)B * Ho * Wo * (C / 4);
-  bn_apply_pool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a, a_bf16, scale, shift, B, H, W, C, pool, (__nv_bfloat16*)out_hi,
-                                                                               (__nv_bfloat16*)out_lo, out_f32);
+  if (a_bf16 && (C % 8) == 0) {
+    const long total = (long)B * Ho * Wo * (C / 8);
+    bn_apply_pool_kernel<8><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a, a_bf16, scale, shift, B, H, W, C, pool, (__nv_bfloat16*)out_hi,
+                                                                                    (__nv_bfloat16*)out_lo, out_f32);
+  } else {
+    const long total = (long)B * Ho * Wo * (C / 4);
+    bn_apply_pool_kernel<4><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a, a_bf16, scale, shift, B, H, W, C, pool, (__nv_bfloat16*)out_hi,
+                                                                                    (__nv_bfloat16*)out_lo, out_f32);
+  }
   JCM_LAUNCH_CHECK();
   return JCM_OK;
 }
@@ -380,9 +400,15 @@ extern "C" int jcm_upsample_avg3(const void* a1, const void* a2, const void* a3,
                                  int H2, int W2, int H3, int W3, int C, void* out_hi, void* out_lo, float* out_f32, void* stream) {
   JCM_CHECK_ARG(a1 && a2 && a3 && scale_shift && (out_hi || out_f32), "jcm_upsample_avg3: null pointer");
   JCM_CHECK_ARG((C % 4) == 0, "jcm_upsample_avg3: C must be a multiple of 4, got %d", C);
-  const long total = (long)B * H * W * (C / 4);
-  upsample_avg3_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a1, a2, a3, a_bf16, scale_shift, B, H, W, H2, W2, H3, W3, C,
-                                                                               (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32);
+  if (a_bf16 && (C % 8) == 0) {
+    const long total = (long)B * H * W * (C / 8);
+    upsample_avg3_kernel<8><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a1, a2, a3, a_bf16, scale_shift, B, H, W, H2, W2, H3, W3, C,
+                                                                                    (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32);
+  } else {
+    const long total = (long)B * H * W * (C / 4);
+    upsample_avg3_kernel<4><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a1, a2, a3, a_bf16, scale_shift, B, H, W, H2, W2, H3, W3, C,
+                                                                                    (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32);
+  }
   JCM_LAUNCH_CHECK();
   return JCM_OK;
 }
