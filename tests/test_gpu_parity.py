@@ -432,3 +432,19 @@ def test_graft_entry_smoke(jcm):
     """The driver's smoke(): one small invocation of the hot path on cuda:0 checked against the oracle."""
     import __graft_entry__ as ge
     ge.smoke()
+
+
+@pytest.mark.parametrize('train', [False, True])
+def test_full_width_model_bf16_configuration(jcm, train):
+    """BASELINE config 3 arithmetic (bf16 operands AND bf16-stored activations, fp32 accumulation) at full width on one 240x360
+    image against the fp64 oracle: stated tolerance 5e-2 relative on the logits (not a 1e-3 parity claim)."""
+    K = 7
+    p, gen = _pd_params(K, False, 17)
+    x = torch.rand(1, 240, 360, 3, generator=gen)
+    ref = orc.model(x.double(), {k: v.double().clone() for k, v in p.items()}, K, train)
+    ctx = jcm.Context(n_joints=K, flag_train=train, precision='bf16')
+    assert ctx.act_bf16
+    tap = {}
+    out = jcm.model(x.cuda(), K, jcm.load_params(p), ctx, tap=tap)
+    assert tap['conv5/relu'].dtype == torch.bfloat16 and out.dtype == torch.float32
+    assert rel(out, ref) < TOL_BF16
