@@ -233,6 +233,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
       const uint32_t sbo = 8 * row_bytes;
       const uint32_t dy_bytes = (uint32_t)p.TW * row_bytes;     // one patch row of the halo tile; TW % 8 == 0 keeps the swizzle phase
       const int kk = p.kc / 16;
+      const uint64_t desc_hi = make_smem_desc(0, sbo, layout);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int acc = 0;
@@ -249,8 +250,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
           for (int dy = 0; dy < p.ksize; ++dy) {
             mbar_wait(bar_full + 8 * sb, pb);
             tc_fence_after();
-            const uint64_t adesc = make_smem_desc(a_addr + dy * dy_bytes, sbo, layout);
-            const uint64_t bdesc = make_smem_desc(smem_b0 + sb * p.b_stride, sbo, layout);
+            const uint64_t adesc = desc_hi | (uint64_t)(((a_addr + dy * dy_bytes) >> 4) & 0x3FFF);
+            const uint64_t bdesc = desc_hi | (uint64_t)(((smem_b0 + sb * p.b_stride) >> 4) & 0x3FFF);
             if (!(p.dbg & 2))
             for (int k = 0; k < kk; ++k) {
               const int j = (mcount++) & (p.nacc - 1);
@@ -304,6 +305,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
       const uint32_t layout = (p.kc == 64) ? 2u : (p.kc == 32 ? 4u : 6u);  // SWIZZLE_128B : SWIZZLE_64B : SWIZZLE_32B
       const uint32_t sbo = 8 * row_bytes;
       const int kk = p.kc / 16;
+      const uint64_t desc_hi = make_smem_desc(0, sbo, layout);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -317,8 +319,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * p.stage_bytes;
-          const uint64_t adesc = make_smem_desc(sa, sbo, layout);
-          const uint64_t bdesc = make_smem_desc(sa + p.a_bytes, sbo, layout);
+          const uint64_t adesc = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);                 // only the start address changes per stage
+          const uint64_t bdesc = desc_hi | (uint64_t)(((sa + p.a_bytes) >> 4) & 0x3FFF);
           if (p.dbg & 2) {
           } else if (p.mma_split_n) {
             // experiment: two independent half-N MMAs per K step (different TMEM columns, B rows n/2.. of the same stage)
@@ -332,6 +334,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
           } else
           for (int k = 0; k < kk; ++k) {
             // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the 16-byte address field
+            // (measured: a specialised nacc == 1 path without the round-robin bookkeeping compiles to a SLOWER issue loop - kept as is)
             const int j = (mcount++) & (p.nacc - 1);
             tc_mma_bf16(d_tmem + j * p.block_n, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (accumulate >> j) & 1u);
             accumulate |= 1u << j;
