@@ -39,6 +39,8 @@ struct ConvParams {
   // (TH + kh - 1)-row halo patch and the kh vertical taps address it at row offsets dy*TW (a multiple of the 8-row swizzle
   // period, so the UMMA descriptor just moves its start address); weights stream through their own ring, one tap at a time.
   int halo, a_stages, b_stages, a_halo_bytes, a_stride, b_stride;
+  int b_group, b_slot;  // halo mode: vertical taps per weight stage (one full/empty handshake and one tcgen05.commit per group: the
+                        // handshake costs ~350 clk, more than the MMAs of one tap when N <= 128) and bytes per tap slot
   int mma_split_n;      // measurement switch (JCM_MMA_SPLITN): issue every MMA as two independent half-N MMAs
   int nacc;             // independent accumulators per tile (K steps are dealt round-robin to them and summed in the epilogue):
                         // back-to-back tcgen05.mma into the SAME TMEM tile serialise at ~170 clk each whatever N is, so for
@@ -210,13 +212,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             mbar_expect_tx(bar_afull + 8 * sa, p.a_halo_bytes);
             tma_load_4d(smem_base + sa * p.a_stride, &map_a_lo, bar_afull + 8 * sa, cb * p.kc, x0 + dx, y0, img);
             if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
-            for (int dy = 0; dy < p.ksize; ++dy) {
+            if (p.b_group == 1) {
+              for (int dy = 0; dy < p.ksize; ++dy) {
+                mbar_wait(bar_empty + 8 * sb, pb ^ 1);
+                mbar_expect_tx(bar_full + 8 * sb, p.b_bytes);
+                tma_load_3d(smem_b0 + sb * p.b_stride, &map_b_hi, bar_full + 8 * sb, cb * p.kc, nt * p.block_n, dy * p.kw + dx);
+                if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+              }
+            } else
+            for (int dy0 = 0; dy0 < p.ksize; dy0 += p.b_group) {
+              const int gn = min(p.b_group, p.ksize - dy0);
               mbar_wait(bar_empty + 8 * sb, pb ^ 1);
               if (p.dbg & 4) {
                 mbar_arrive(bar_full + 8 * sb);
               } else {
-                mbar_expect_tx(bar_full + 8 * sb, p.b_bytes);
-                tma_load_3d(smem_b0 + sb * p.b_stride, &map_b_hi, bar_full + 8 * sb, cb * p.kc, nt * p.block_n, dy * p.kw + dx);
+                mbar_expect_tx(bar_full + 8 * sb, gn * p.b_bytes);
+                for (int i = 0; i < gn; ++i)
+                  tma_load_3d(smem_b0 + sb * p.b_stride + i * p.b_slot, &map_b_hi, bar_full + 8 * sb, cb * p.kc, nt * p.block_n,
+                              (dy0 + i) * p.kw + dx);
               }
               if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
             }
@@ -247,16 +260,36 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
           mbar_wait(bar_afull + 8 * sa, pa);
           tc_fence_after();
           const uint32_t a_addr = smem_base + sa * p.a_stride;
-          for (int dy = 0; dy < p.ksize; ++dy) {
+          if (p.b_group == 1) {
+            // one tap per weight stage (N = 128 layers: grouping does not pay there; this flat loop compiles to the tighter issue loop)
+            for (int dy = 0; dy < p.ksize; ++dy) {
+              mbar_wait(bar_full + 8 * sb, pb);
+              tc_fence_after();
+              const uint64_t adesc = desc_hi | (uint64_t)(((a_addr + dy * dy_bytes) >> 4) & 0x3FFF);
+              const uint64_t bdesc = desc_hi | (uint64_t)(((smem_b0 + sb * p.b_stride) >> 4) & 0x3FFF);
+              if (!(p.dbg & 2))
+              for (int k = 0; k < kk; ++k) {
+                const int j = (mcount++) & (p.nacc - 1);
+                tc_mma_bf16(d_tmem + j * p.block_n, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (accumulate >> j) & 1u);
+                accumulate |= 1u << j;
+              }
+              tc_commit(bar_empty + 8 * sb);
+              if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+            }
+          } else
+          for (int dy0 = 0; dy0 < p.ksize; dy0 += p.b_group) {
+            const int gn = min(p.b_group, p.ksize - dy0);
             mbar_wait(bar_full + 8 * sb, pb);
             tc_fence_after();
-            const uint64_t adesc = desc_hi | (uint64_t)(((a_addr + dy * dy_bytes) >> 4) & 0x3FFF);
-            const uint64_t bdesc = desc_hi | (uint64_t)(((smem_b0 + sb * p.b_stride) >> 4) & 0x3FFF);
-            if (!(p.dbg & 2))
-            for (int k = 0; k < kk; ++k) {
-              const int j = (mcount++) & (p.nacc - 1);
-              tc_mma_bf16(d_tmem + j * p.block_n, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (accumulate >> j) & 1u);
-              accumulate |= 1u << j;
+            for (int i = 0; i < gn; ++i) {
+              const uint64_t adesc = desc_hi | (uint64_t)(((a_addr + (dy0 + i) * dy_bytes) >> 4) & 0x3FFF);
+              const uint64_t bdesc = desc_hi | (uint64_t)(((smem_b0 + sb * p.b_stride + i * p.b_slot) >> 4) & 0x3FFF);
+              if (!(p.dbg & 2))
+              for (int k = 0; k < kk; ++k) {
+                const int j = (mcount++) & (p.nacc - 1);
+                tc_mma_bf16(d_tmem + j * p.block_n, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (accumulate >> j) & 1u);
+                accumulate |= 1u << j;
+              }
             }
             tc_commit(bar_empty + 8 * sb);
             if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
@@ -621,12 +654,20 @@ extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_
   static const int halo_env = getenv("JCM_CONV_HALO") ? atoi(getenv("JCM_CONV_HALO")) : 1;   // 0 disables (for A/B measurements)
   if (halo_env && p.terms == 1 && ksize >= 3 && p.block_n <= (halo_env > 1 ? 256 : 128) && (p.TW % 8) == 0) {
     p.a_halo_bytes = (p.TH + ksize - 1) * p.TW * p.kc * 2;
+    static const int group_env = getenv("JCM_CONV_BGROUP") ? atoi(getenv("JCM_CONV_BGROUP")) : 0;   // measurement: force taps per stage
     p.a_stride = ((p.a_halo_bytes + 1023) / 1024) * 1024;
-    p.b_stride = ((p.b_bytes + 1023) / 1024) * 1024;
+    p.b_slot = ((p.b_bytes + 1023) / 1024) * 1024;
     p.a_stages = p.a_stride > 40 * 1024 ? 2 : 3;
-    p.b_stages = (225 * 1024 - epi_bytes - p.a_stages * p.a_stride) / p.b_stride;
+    const int budget = 225 * 1024 - epi_bytes - p.a_stages * p.a_stride;
+    p.b_group = budget / (3 * p.b_slot);                 // as many vertical taps per stage as still leave 3 weight stages
+    if (p.b_group > ksize) p.b_group = ksize;
+    if (p.block_n > 64) p.b_group = 1;                   // measured: grouping pays for N <= 64 (+20 %), not for N = 128
+    if (group_env > 0 && group_env < p.b_group) p.b_group = group_env;
+    if (p.b_group < 1) p.b_group = 1;
+    p.b_stride = p.b_group * p.b_slot;
+    p.b_stages = budget / p.b_stride;
     if (p.b_stages > kMaxStages) p.b_stages = kMaxStages;
-    p.halo = p.b_stages >= (halo_env > 1 ? 3 : 4);
+    p.halo = p.b_stages >= 3;
   }
   p.relu = relu;
   p.bias = bias;
