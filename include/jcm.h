@@ -157,6 +157,21 @@ int jcm_spatial_model_bwd(const float* g, const float* heat_map, const float* bn
                           const int* pair_cond, const void* fwd_workspace, void* workspace, long workspace_bytes, float* d_heat_map,
                           float* dE, float* db, float* dgamma, float* dbeta, int B, int H, int W, int K, int P, void* stream);
 
+/* Tensor-core form of the spatial model (bf16 training configuration): same arguments, workspace protocol and results as
+ * jcm_spatial_model_fwd / _bwd (main.py:94-125 and its autodiff), with the pairwise convolutions computed as grouped Toeplitz
+ * GEMMs on tcgen05 with bf16 operands and fp32 accumulation.  The two forms keep different workspaces: pass the _tc_ forward
+ * workspace to the _tc_ backward. */
+long jcm_spatial_model_tc_workspace(int B, int H, int W, int K, int P);
+int jcm_spatial_model_tc_fwd(const float* heat_map, const float* bn_scale, const float* bn_shift, const float* energies,
+                             const float* biases, const int* pair_target, const int* pair_cond, float* out, void* workspace,
+                             long workspace_bytes, int B, int H, int W, int K, int P, void* stream);
+long jcm_spatial_model_tc_bwd_workspace(int B, int H, int W, int K, int P);
+int jcm_spatial_model_tc_bwd(const float* g, const float* heat_map, const float* bn_scale, const float* bn_shift, const float* bn_mean,
+                             const float* bn_rstd, int train, const float* energies, const float* biases, const int* pair_target,
+                             const int* pair_cond, const void* fwd_workspace, void* workspace, long workspace_bytes,
+                             float* d_heat_map, float* dE, float* db, float* dgamma, float* dbeta, int B, int H, int W, int K, int P,
+                             void* stream);
+
 /* ---- tap-expanded form of a convolution with very few output channels (conv6: 9x9, 512 -> K, main.py:72) ------------------
  * y[p,co] = b[co] + sum_tap Z[p+tap-pad, tap*KP+co] with Z = 1x1 conv (jcm_conv2d_fwd, ksize 1) of the input with the weights packed
  * by jcm_pack_weights_taps (rows n = tap*KP+co; KP = Cout padded to a multiple of 4; Npad >= k*k*KP rows, zero filled).

@@ -45,6 +45,10 @@ SIGNATURES = {
     'jcm_conv2d_wgrad': (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'jcm_unpack_s2d_grad': (_I, [_P, _I, _P, _P]),
     'jcm_spatial_model_bwd_workspace': (_L, [_I, _I, _I, _I, _I]),
+    'jcm_spatial_model_tc_workspace': (_L, [_I, _I, _I, _I, _I]),
+    'jcm_spatial_model_tc_fwd': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
+    'jcm_spatial_model_tc_bwd_workspace': (_L, [_I, _I, _I, _I, _I]),
+    'jcm_spatial_model_tc_bwd': (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     'jcm_spatial_model_bwd': (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     'jcm_pack_weights_taps': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     'jcm_tap_gather': (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),

@@ -46,6 +46,20 @@ static inline int jcm_cdiv(int a, int b) { return (a + b - 1) / b; }
 
 int jcm_num_sms();
 
+// Internal launcher of the tcgen05 implicit-GEMM kernel (conv_tcgen05.cu).  jcm_conv2d_fwd is the grp == 0 case; the grouped
+// forms serve the tensor-core spatial model (see ConvParams::grp for their meaning).
+struct ConvExArgs {
+  const void *x_hi, *x_lo, *w_hi, *w_lo;
+  const float* bias;
+  void* y;
+  int y_bf16;
+  int B, H, W, Cin, Cout, Cout_pad, ksize, kw, relu;
+  int pad_y;                                   // rows of padding above; < 0: (ksize - 1) / 2
+  int grp, a_div, w_cin, k_rows, sm_pad, sm_rows, sm_rows_in;
+  void* stream;
+};
+int jcm_conv_igemm_ex(const ConvExArgs& a);
+
 // ---------------------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------------------

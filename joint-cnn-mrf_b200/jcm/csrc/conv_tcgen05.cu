@@ -45,6 +45,12 @@ struct ConvParams {
   int nacc;             // independent accumulators per tile (K steps are dealt round-robin to them and summed in the epilogue):
                         // back-to-back tcgen05.mma into the SAME TMEM tile serialise at ~170 clk each whatever N is, so for
                         // N <= 128 the tensor pipe idles unless consecutive MMAs target different accumulators
+  // grouped forms used by the tensor-core spatial model (spatial_model.cu, "smt" section); plain mode only:
+  //   grp 1: every image has its OWN weights (tap plane = img * grp_taps + tap) and taps whose input rows all lie outside the
+  //          map are skipped (120-tap vertical kernels over 61-row maps: half of the taps of every tile)
+  //   grp 2: batched GEMM with a shifted B operand: image = (batch a_div * q + s), A image q, weight plane q, the weight's K
+  //          coordinate is offset by (s - sm_pad) * k_rows and only the k-blocks that can be non-zero are visited
+  int grp, grp_taps, a_div, k_rows, sm_pad, sm_rows, sm_rows_in;
   int dbg;              // measurement switches (JCM_CONV_DBG bit 0: epilogue releases TMEM without storing, bit 1: no MMAs issued,
                         // bit 2: producer skips the B loads) - results are garbage, timing only
   const float* bias;
@@ -147,6 +153,26 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
   d |= (uint64_t)1 << 46;                           // descriptor version = 1 (Blackwell) [46,48)
   d |= (uint64_t)(layout_type & 7) << 61;           // 2 = SWIZZLE_128B, 6 = SWIZZLE_32B
   return d;
+}
+
+// k-loop extent of one tile: taps [tap_lo, tap_hi) x channel blocks [cb_lo, cb_hi).  Whole extent for ordinary convolutions.
+struct KRange { int tap_lo, tap_hi, cb_lo, cb_hi; };
+__device__ __forceinline__ KRange tile_krange(const ConvParams& p, int img, int ty) {
+  KRange r;
+  r.tap_lo = 0; r.tap_hi = p.ksize * p.kw; r.cb_lo = 0; r.cb_hi = p.cblocks;
+  if (p.grp == 1) {             // kw == 1: tap dy reads input rows y + dy - pad, y in [y0, y0 + TH); keep those that touch [0, H)
+    const int y0 = ty * p.TH;
+    r.tap_lo = max(0, p.pad - (y0 + p.TH - 1));
+    r.tap_hi = min(p.ksize, p.H + p.pad - y0);
+    if (r.tap_hi <= r.tap_lo) r.tap_hi = r.tap_lo + 1;
+  } else if (p.grp == 2) {      // shift s: rows y of the A operand with 0 <= y + s - sm_pad < sm_rows_in, as a range of k-blocks
+    const int s = img % p.a_div;
+    const int ylo = max(0, p.sm_pad - s), yhi = min(p.sm_rows, p.sm_rows_in + p.sm_pad - s);
+    r.cb_lo = (ylo * p.k_rows) / p.kc;
+    r.cb_hi = min(p.cblocks, (yhi * p.k_rows + p.kc - 1) / p.kc);
+    if (r.cb_hi <= r.cb_lo) { r.cb_lo = 0; r.cb_hi = 1; }
+  }
+  return r;
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -312,6 +338,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         const int r = mt - img * (p.tiles_y * p.tiles_x);
         const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
         const int x0 = tx * p.TW - p.pad_x, y0 = ty * p.TH - p.pad;
+        if (p.grp) {
+          const KRange kr = tile_krange(p, img, ty);
+          const int a_img = p.grp == 2 ? img / p.a_div : img;
+          const int b_plane = p.grp == 2 ? img / p.a_div : img * p.grp_taps;
+          const int b_koff = p.grp == 2 ? (img % p.a_div - p.sm_pad) * p.k_rows : 0;
+          for (int tap = kr.tap_lo; tap < kr.tap_hi; ++tap) {
+            for (int cb = kr.cb_lo; cb < kr.cb_hi; ++cb) {
+              mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+              const uint32_t sa = smem_base + stage * p.stage_bytes;
+              const uint32_t fb = bar_full + 8 * stage;
+              mbar_expect_tx(fb, p.a_bytes + p.b_bytes);
+              tma_load_4d(sa, &map_a_hi, fb, cb * p.kc, x0, y0 + tap, a_img);
+              tma_load_3d(sa + p.a_bytes, &map_b_hi, fb, cb * p.kc + b_koff, nt * p.block_n, b_plane + (p.grp == 2 ? 0 : tap));
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+          }
+          continue;
+        }
         for (int tap = 0; tap < taps; ++tap) {
           const int dy = tap / p.kw, dx = tap - dy * p.kw;
           for (int cb = 0; cb < p.cblocks; ++cb) {
@@ -348,7 +392,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
         uint32_t accumulate = 0, mcount = 0;     // bit j: accumulator j of this tile has been written; MMAs are dealt round-robin
-        for (int kb = 0; kb < num_kb; ++kb) {
+        int tile_kb = num_kb;
+        if (p.grp) {
+          const int mt = tile % m_tiles;
+          const int img = mt / (p.tiles_y * p.tiles_x);
+          const int ty = (mt - img * (p.tiles_y * p.tiles_x)) / p.tiles_x;
+          const KRange kr = tile_krange(p, img, ty);
+          tile_kb = (kr.tap_hi - kr.tap_lo) * (kr.cb_hi - kr.cb_lo);
+        }
+        for (int kb = 0; kb < tile_kb; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * p.stage_bytes;
@@ -600,14 +652,32 @@ extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_
                               void* y, int y_bf16, int B, int H, int W, int Cin, int Cout, int Cout_pad, int ksize, int kw, int relu,
                               void* stream) {
   if (kw <= 0) kw = ksize;
+  JCM_CHECK_ARG(ksize > 0 && (ksize & 1) && (kw & 1), "jcm_conv2d_fwd: kernel extents must be odd (SAME, stride 1), got %d x %d", ksize, kw);
+  ConvExArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x_hi = x_hi; a.x_lo = x_lo; a.w_hi = w_hi; a.w_lo = w_lo; a.bias = bias; a.y = y; a.y_bf16 = y_bf16;
+  a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.Cout_pad = Cout_pad; a.ksize = ksize; a.kw = kw; a.relu = relu;
+  a.pad_y = -1;
+  a.stream = stream;
+  return jcm_conv_igemm_ex(a);
+}
+
+// The launcher behind jcm_conv2d_fwd, also called by the tensor-core spatial model (spatial_model.cu) with its grouped forms.
+int jcm_conv_igemm_ex(const ConvExArgs& a) {
+  const void *x_hi = a.x_hi, *x_lo = a.x_lo, *w_hi = a.w_hi, *w_lo = a.w_lo;
+  const float* bias = a.bias;
+  void* y = a.y;
+  void* stream = a.stream;
+  const int y_bf16 = a.y_bf16, B = a.B, H = a.H, W = a.W, Cin = a.Cin, Cout = a.Cout, Cout_pad = a.Cout_pad, ksize = a.ksize, kw = a.kw,
+            relu = a.relu;
   JCM_CHECK_ARG(x_hi && w_hi && y, "jcm_conv2d_fwd: null pointer");
   JCM_CHECK_ARG((x_lo == nullptr) == (w_lo == nullptr), "jcm_conv2d_fwd: x_lo and w_lo must both be given (bf16x3) or both NULL (bf16)");
-  JCM_CHECK_ARG(B > 0 && H > 0 && W > 0, "jcm_conv2d_fwd: bad shape B=%d H=%d W=%d", B, H, W);
-  JCM_CHECK_ARG(ksize > 0 && (ksize & 1) && (kw & 1), "jcm_conv2d_fwd: kernel extents must be odd (SAME, stride 1), got %d x %d", ksize, kw);
+  JCM_CHECK_ARG(B > 0 && H > 0 && W > 0 && ksize > 0 && kw > 0, "jcm_conv2d_fwd: bad shape B=%d H=%d W=%d k=%dx%d", B, H, W, ksize, kw);
   JCM_CHECK_ARG(Cin >= 16 && (Cin % 16) == 0, "jcm_conv2d_fwd: Cin must be a multiple of 16, got %d", Cin);
   JCM_CHECK_ARG(Cout > 0 && Cout_pad >= Cout && (Cout_pad % 16) == 0, "jcm_conv2d_fwd: Cout_pad=%d must be >= Cout=%d and a multiple of 16", Cout_pad, Cout);
   JCM_CHECK_ARG((((uintptr_t)x_hi | (uintptr_t)w_hi | (uintptr_t)x_lo | (uintptr_t)w_lo | (uintptr_t)y) & 15) == 0,
                 "jcm_conv2d_fwd: pointers must be 16-byte aligned");
+  JCM_CHECK_ARG(a.grp == 0 || (x_lo == nullptr && kw == 1), "jcm_conv_igemm_ex: grouped forms are single-term with kw == 1");
 
   ConvParams p;
   memset(&p, 0, sizeof(p));
@@ -622,8 +692,10 @@ extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_
   p.cblocks = Cin / p.kc;
   p.ksize = ksize;
   p.kw = kw;
-  p.pad = (ksize - 1) / 2;
+  p.pad = a.pad_y >= 0 ? a.pad_y : (ksize - 1) / 2;
   p.pad_x = (kw - 1) / 2;
+  p.grp = a.grp; p.grp_taps = ksize * kw; p.a_div = a.a_div > 0 ? a.a_div : 1; p.k_rows = a.k_rows;
+  p.sm_pad = a.sm_pad; p.sm_rows = a.sm_rows; p.sm_rows_in = a.sm_rows_in;
   p.terms = x_lo ? 3 : 1;
   p.a_bytes = kTileM * p.kc * 2;
   p.b_bytes = p.block_n * p.kc * 2;
@@ -652,7 +724,7 @@ extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_
   p.dbg = dbg_env;
   p.a_stages = 0; p.b_stages = 0; p.a_stride = 0; p.b_stride = 0; p.a_halo_bytes = 0;
   static const int halo_env = getenv("JCM_CONV_HALO") ? atoi(getenv("JCM_CONV_HALO")) : 1;   // 0 disables (for A/B measurements)
-  if (halo_env && p.terms == 1 && ksize >= 3 && p.block_n <= (halo_env > 1 ? 256 : 128) && (p.TW % 8) == 0) {
+  if (halo_env && p.grp == 0 && p.terms == 1 && ksize >= 3 && p.block_n <= (halo_env > 1 ? 256 : 128) && (p.TW % 8) == 0) {
     p.a_halo_bytes = (p.TH + ksize - 1) * p.TW * p.kc * 2;
     static const int group_env = getenv("JCM_CONV_BGROUP") ? atoi(getenv("JCM_CONV_BGROUP")) : 0;   // measurement: force taps per stage
     p.a_stride = ((p.a_halo_bytes + 1023) / 1024) * 1024;
@@ -679,7 +751,7 @@ extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_
   const CUtensorMapSwizzle swz = p.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   {
-    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)(a.grp == 2 ? B / p.a_div : B)};
     uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
     uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)p.TW, (uint32_t)p.TH, 1};
     int rc = make_map(&ma_hi, x_hi, 4, dims, str, box, swz);
@@ -689,8 +761,11 @@ extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_
     if (rc) return rc;
   }
   {
-    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout_pad, (uint64_t)(ksize * kw)};
-    uint64_t str[2] = {(uint64_t)Cin * 2, (uint64_t)Cout_pad * Cin * 2};
+    // weight planes: one per tap; grouped forms: B * taps planes (grp 1), B / a_div planes with their own K extent w_cin (grp 2)
+    const uint64_t wc = a.grp == 2 ? (uint64_t)a.w_cin : (uint64_t)Cin;
+    const uint64_t planes = a.grp == 1 ? (uint64_t)B * ksize * kw : (a.grp == 2 ? (uint64_t)(B / p.a_div) : (uint64_t)(ksize * kw));
+    uint64_t dims[3] = {wc, (uint64_t)Cout_pad, planes};
+    uint64_t str[2] = {wc * 2, (uint64_t)Cout_pad * wc * 2};
     uint32_t box[3] = {(uint32_t)p.kc, (uint32_t)p.block_n, 1};
     int rc = make_map(&mb_hi, w_hi, 3, dims, str, box, swz);
     if (rc) return rc;

@@ -41,6 +41,11 @@ struct SmDims {
   int NBD, TB;         // output-row bands per image and rows per band: only TB - 1 + Hp prior rows are resident at a time
   int pstride, prows;  // shared-memory layout of the prior
   int raw;             // 1: operands are used as given (conv_mrf entry point), 0: BN + softplus applied while staging
+  // addressing of the raw convolution results C[p][n][y][x] ((H+1)x(W+1)) and of the likelihood gradients dL[p][n][y][x] (HxW) as
+  // the glue kernels read them: element = base + p*sp + n*sn + y*sy + x.  The FFMA path stores [p][n][y][x] (dL flipped in y and
+  // x), the tensor-core path [p][y][n][x] with padded rows (dL not flipped).
+  long cb_sp, dl_sp;
+  int cb_sn, cb_sy, dl_sn, dl_sy, dl_flip;
 };
 
 __device__ __forceinline__ unsigned long long pack2(float a, float b) {
@@ -280,9 +285,9 @@ __global__ void sm_finish_kernel(const float* __restrict__ hm, const float* __re
     const float h = fmaf(hm[(((long)n * d.H + y) * d.W + x) * KC + i], scale[i], shift[i]);
     float m = logf(softplus5(h) + kDelta);
     for (int p = first[i]; p < first[i + 1]; ++p) {
-      const float* C = Cb + ((long)p * (4 * d.G) + n) * OH * OW;
-      const float tl = C[ylo * OW + xlo], tr = C[ylo * OW + xhi];
-      const float bl = C[yhi * OW + xlo], br = C[yhi * OW + xhi];
+      const float* C = Cb + (long)p * d.cb_sp + (long)n * d.cb_sn;
+      const float tl = C[ylo * d.cb_sy + xlo], tr = C[ylo * d.cb_sy + xhi];
+      const float bl = C[yhi * d.cb_sy + xlo], br = C[yhi * d.cb_sy + xhi];
       const float top = tl + (tr - tl) * wx;
       const float bot = bl + (br - bl) * wx;
       const float val = top + (bot - top) * wy;
@@ -349,6 +354,8 @@ int fill_dims(SmDims& d, int B, int H, int W, int K, int P, int mode = 0) {
     d.NS = jcm_cdiv(d.tiles, 32);
     if (sm_smem_bytes(d) <= (size_t)227 * 1024 - 256 || d.TB <= 1) break;
   }
+  d.cb_sp = (long)4 * d.G * (H + 1) * (W + 1); d.cb_sn = (H + 1) * (W + 1); d.cb_sy = W + 1;
+  d.dl_sp = (long)4 * d.G * H * W; d.dl_sn = H * W; d.dl_sy = W; d.dl_flip = 1;
   return 0;
 }
 
@@ -480,9 +487,9 @@ __global__ void sm_bwd_dt_kernel(const float* __restrict__ g, const float* __res
     for (int n = 0; n < 4 * d.G; ++n) {
       float tv = 0.f;
       if (n < d.B) {
-        const float* C = Cb + ((long)p * (4 * d.G) + n) * OH * OW;
-        const float tl = C[ylo * OW + xlo], tr = C[ylo * OW + xhi];
-        const float bl = C[yhi * OW + xlo], br = C[yhi * OW + xhi];
+        const float* C = Cb + (long)p * d.cb_sp + (long)n * d.cb_sn;
+        const float tl = C[ylo * d.cb_sy + xlo], tr = C[ylo * d.cb_sy + xhi];
+        const float bl = C[yhi * d.cb_sy + xlo], br = C[yhi * d.cb_sy + xhi];
         const float top = tl + (tr - tl) * wx;
         const float bot = bl + (br - bl) * wx;
         tv = g[(((long)n * d.H + y) * d.W + x) * d.K + i] / (top + (bot - top) * wy + sb);
@@ -735,7 +742,8 @@ __global__ void sm_bwd_dh_kernel(const float* __restrict__ hm, const float* __re
     const float hb = fmaf(hm[idx], scale[j], shift[j]);
     float s = 0.f;
     for (int p = 0; p < d.P; ++p)
-      if (pair_cond[p] == j) s += dLf[(((long)p * (4 * d.G) + n) * d.H + (d.H - 1 - y)) * d.W + (d.W - 1 - x)];
+      if (pair_cond[p] == j)
+        s += dLf[(long)p * d.dl_sp + (long)n * d.dl_sn + (long)(d.dl_flip ? d.H - 1 - y : y) * d.dl_sy + (d.dl_flip ? d.W - 1 - x : x)];
     if (j < d.K) s += g[(((long)n * d.H + y) * d.W + x) * d.K + j] / (softplus5(hb) + kDelta);
     dhbn[idx] = s * sigmoid5(hb);
   }
@@ -895,6 +903,373 @@ extern "C" int jcm_spatial_model_bwd(const float* g, const float* heat_map, cons
     int nb = (int)((Mr + 255) / 256);
     if (nb > 2 * jcm_num_sms()) nb = 2 * jcm_num_sms();
     float* bnpart = part;   // the dP partial buffer is free again (its finish kernel ran above): reuse its first 2*nb*(K+1) floats
+    sm_bn_bwd_partial_kernel<<<nb, BNB_THREADS, 0, st>>>(heat_map, dh, bn_mean, bn_rstd, Mr, K + 1, bnpart);
+    JCM_LAUNCH_CHECK();
+    sm_bn_bwd_apply_kernel<<<2 * jcm_num_sms(), 256, 0, st>>>(heat_map, dh, bn_scale, bn_mean, bn_rstd, bnpart, nb, Mr, K + 1, train,
+                                                             d_heat_map, dgamma, dbeta);
+    JCM_LAUNCH_CHECK();
+  }
+  return JCM_OK;
+}
+
+// =====================================================================================================================
+// Tensor-core form of the spatial model (bf16 training configuration; same interface and results to bf16 operand rounding).
+//
+// conv_mrf is a 2-D convolution of an HxW map with a 2Hx2W kernel: along x it is a Toeplitz matrix product, along y a 2H-tap
+// 1-D convolution.  With h = sp(bn(heat map)) (not flipped), P = sp(E):
+//
+//   forward   C[n][y][x]  = sum_dy sum_v  h[n][y+dy-H][v]      * P[2H-1-dy][x-v+W-1]          y <= H, x <= W
+//   dL        dL[n][u][v] = sum_dy sum_x dC[n][u+dy-(H-1)][x]  * P[dy][x-v+W-1]
+//   dP        dP[2H-1-dy][c] = sum_{x-v+W-1=c} ( sum_{n,y} dC[n][y][x] * h[n][y+dy-H][v] )
+//
+// The first two are convolutions with 2H x 1 taps over "images" [rows y][columns = the batch][channels = x or v] whose tap
+// weights are the Toeplitz blocks T_dy[x][v] of one prior row, a different set for every (target, cond) pair: the grouped form
+// grp 1 of the tcgen05 implicit-GEMM kernel (conv_tcgen05.cu).  The third is, per (pair, dy), a GEMM over (n, y) of dC^T with a
+// row-shifted h^T: form grp 2, followed by a sum along the diagonals of each block.  The Toeplitz blocks are materialised in
+// HBM as bf16 (2 x P x 2H x NP x CP: 289 MB for K = 7, written once per step at HBM speed - cheaper than any on-the-fly form
+// the UMMA descriptors could express).  Work: 3 x ~0.3 PFLOP-equivalent tiles on the tensor pipe instead of 3 x 94 GMAC of FFMA.
+// =====================================================================================================================
+namespace {
+
+struct SmtDims {
+  int B, H, W, K, P;
+  int Hc;   // H + 1: rows of the convolution output and of the zero-padded operands
+  int NP;   // GEMM N extent: W + 1 rounded up to 32
+  int CP;   // GEMM K extent (forward, dL) / M extent (dP): W + 1 rounded up to 64
+  int Bp;   // images rounded up to 16; the dP GEMM contracts over k = row * Bp + image
+};
+
+int fill_smt(SmtDims& t, int B, int H, int W, int K, int P) {
+  t.B = B; t.H = H; t.W = W; t.K = K; t.P = P;
+  t.Hc = H + 1;
+  t.NP = jcm_cdiv(W + 1, 32) * 32;
+  t.CP = jcm_cdiv(W + 1, 64) * 64;
+  t.Bp = jcm_cdiv(B, 16) * 16;
+  JCM_CHECK_ARG(t.NP <= 256, "jcm_spatial_model_tc: heat-map width %d not supported (at most 255)", W);
+  return JCM_OK;
+}
+
+inline size_t al256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+struct SmtFwdWs { size_t spE, Xh, Wf, Cb, total; };
+SmtFwdWs smt_fwd_layout(const SmtDims& t) {
+  SmtFwdWs w;
+  size_t o = 0;
+  w.spE = o; o += al256((size_t)t.P * 2 * t.H * 2 * t.W * 4);
+  w.Xh = o;  o += al256((size_t)t.P * t.Hc * t.B * t.CP * 2);
+  w.Wf = o;  o += al256((size_t)t.P * 2 * t.H * t.NP * t.CP * 2);
+  w.Cb = o;  o += al256((size_t)t.P * t.Hc * t.B * t.NP * 4);
+  w.total = o + 256;
+  return w;
+}
+struct SmtBwdWs { size_t dT, Xc, XcT, Ht, Wd, dL, blk, dh, part, total; };
+SmtBwdWs smt_bwd_layout(const SmtDims& t) {
+  SmtBwdWs w;
+  const int G4 = 4 * jcm_cdiv(t.B, NI);
+  size_t o = 0;
+  w.dT = o;   o += al256((size_t)t.P * G4 * t.H * t.W * 4);
+  w.Xc = o;   o += al256((size_t)t.P * t.Hc * t.B * t.CP * 2);
+  w.XcT = o;  o += al256((size_t)t.P * t.CP * t.Hc * t.Bp * 2);
+  w.Ht = o;   o += al256((size_t)t.P * t.NP * t.H * t.Bp * 2);
+  w.Wd = o;   o += al256((size_t)t.P * 2 * t.H * t.NP * t.CP * 2);
+  w.dL = o;   o += al256((size_t)t.P * t.Hc * t.B * t.NP * 4);
+  w.blk = o;  o += al256((size_t)t.P * 2 * t.H * t.CP * t.NP * 4);
+  w.dh = o;   o += al256((size_t)t.B * t.H * t.W * (t.K + 1) * 4);
+  w.part = o; o += al256((size_t)4 * jcm_num_sms() * (t.K + 1) * 4 + 1024);
+  w.total = o + 256;
+  return w;
+}
+
+__global__ void smt_softplus_kernel(const float* __restrict__ E, long n, float* __restrict__ spE) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) spE[i] = softplus5(E[i]);
+}
+
+// Toeplitz blocks of the prior, 8 consecutive K elements (16 bytes) per thread:
+//   Wf[p][dy][x (NP rows)][v (CP)] = spE[p][2H-1-dy][x-v+W-1]     forward  (x <= W, v < W; 0 elsewhere)
+//   Wd[p][dy][v (NP rows)][x (CP)] = spE[p][dy][x-v+W-1]          dL
+__global__ void smt_pack_prior_kernel(const float* __restrict__ spE, SmtDims t, int dl, __nv_bfloat16* __restrict__ Wt) {
+  const int C8 = t.CP / 8, H2 = 2 * t.H, W2 = 2 * t.W;
+  const long total = (long)t.P * H2 * t.NP * C8;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % C8);
+    long r = idx / C8;
+    const int row = (int)(r % t.NP);
+    r /= t.NP;
+    const int dy = (int)(r % H2);
+    const int p = (int)(r / H2);
+    const float* src = spE + ((long)p * H2 + (dl ? dy : H2 - 1 - dy)) * W2;
+    __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = c8 * 8 + e;
+      const int x = dl ? c : row, v = dl ? row : c;
+      o[e] = __float2bfloat16_rn((x <= t.W && v < t.W) ? src[x - v + t.W - 1] : 0.f);
+    }
+    reinterpret_cast<uint4*>(Wt)[idx] = *reinterpret_cast<const uint4*>(o);
+  }
+}
+
+// Xh[p][y (Hc)][n (B)][v (CP)] = h_cond(p)[n][y][v] (0 in the padding);  Ht[p][v (NP)][y*Bp + n] = the same values, transposed
+// (the dP GEMM's B operand; rows y < H only).  One CTA per (32 columns, row, pair); either output may be NULL.
+__global__ void __launch_bounds__(256)
+smt_prep_kernel(const float* __restrict__ hm, const float* __restrict__ scale, const float* __restrict__ shift,
+                const int* __restrict__ pair_cond, SmtDims t, __nv_bfloat16* __restrict__ Xh, __nv_bfloat16* __restrict__ Ht) {
+  __shared__ float tile[64][33];
+  const int v0 = blockIdx.x * 32, y = blockIdx.y, p = blockIdx.z;
+  const int j = pair_cond[p], KC = t.K + 1;
+  const float sc = scale[j], sh = shift[j];
+  const long KH = (long)t.H * t.Bp;
+  for (int nc = 0; nc < t.Bp; nc += 64) {
+    {
+      const int tx = threadIdx.x & 31, tn = threadIdx.x >> 5;
+      const int v = v0 + tx;
+      for (int pass = 0; pass < 8; ++pass) {
+        const int nn = pass * 8 + tn, n = nc + nn;
+        float val = 0.f;
+        if (n < t.B && y < t.H && v < t.W) val = softplus5(fmaf(hm[(((long)n * t.H + y) * t.W + v) * KC + j], sc, sh));
+        tile[nn][tx] = val;
+        if (Xh && n < t.B) Xh[(((long)p * t.Hc + y) * t.B + n) * t.CP + v] = __float2bfloat16_rn(val);
+      }
+    }
+    __syncthreads();
+    if (Ht && y < t.H) {
+      const int nn = threadIdx.x & 63, x0 = threadIdx.x >> 6;
+      const int n = nc + nn;
+      for (int pass = 0; pass < 8; ++pass) {
+        const int xx = pass * 4 + x0, v = v0 + xx;
+        if (v < t.NP && n < t.Bp) Ht[((long)p * t.NP + v) * KH + (long)y * t.Bp + n] = __float2bfloat16_rn(tile[nn][xx]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// dC = R_y^T dT R_x on the (H+1)x(W+1) grid (as sm_bwd_dc_kernel), written as the two bf16 operands of the backward GEMMs:
+//   Xc[p][u (Hc)][n (B)][x (CP)]   (dL: A operand)      XcT[p][x (CP)][u*Bp + n]   (dP: A operand, K-major)
+__global__ void __launch_bounds__(256)
+smt_dc_kernel(const float* __restrict__ dT, SmtDims t, int G4, __nv_bfloat16* __restrict__ Xc, __nv_bfloat16* __restrict__ XcT) {
+  __shared__ float tile[64][33];
+  const int x0 = blockIdx.x * 32, u = blockIdx.y, p = blockIdx.z;
+  const int H = t.H, W = t.W;
+  const long KA = (long)t.Hc * t.Bp;
+  int lo, hi;
+  float w;
+  float wy0 = 0.f, wy1 = 0.f;
+  if (u < H) { legacy_tap(u, H + 1, H, lo, hi, w); wy0 = 1.f - w; }
+  if (u >= 1) { legacy_tap(u - 1, H + 1, H, lo, hi, w); wy1 = w; }
+  const int tx = threadIdx.x & 31, tn = threadIdx.x >> 5;
+  const int x = x0 + tx;
+  float wx0 = 0.f, wx1 = 0.f;
+  if (x < W) { legacy_tap(x, W + 1, W, lo, hi, w); wx0 = 1.f - w; }
+  if (x >= 1 && x <= W) { legacy_tap(x - 1, W + 1, W, lo, hi, w); wx1 = w; }
+  for (int nc = 0; nc < t.Bp; nc += 64) {
+    for (int pass = 0; pass < 8; ++pass) {
+      const int nn = pass * 8 + tn, n = nc + nn;
+      float val = 0.f;
+      if (n < t.B && x <= W) {
+        const float* src = dT + ((long)p * G4 + n) * H * W;
+        if (wy0 != 0.f) {
+          if (wx0 != 0.f) val += wy0 * wx0 * src[u * W + x];
+          if (wx1 != 0.f) val += wy0 * wx1 * src[u * W + x - 1];
+        }
+        if (wy1 != 0.f) {
+          if (wx0 != 0.f) val += wy1 * wx0 * src[(u - 1) * W + x];
+          if (wx1 != 0.f) val += wy1 * wx1 * src[(u - 1) * W + x - 1];
+        }
+      }
+      tile[nn][tx] = val;
+      if (n < t.B) Xc[(((long)p * t.Hc + u) * t.B + n) * t.CP + x] = __float2bfloat16_rn(val);
+    }
+    __syncthreads();
+    {
+      const int nn = threadIdx.x & 63, xb = threadIdx.x >> 6;
+      const int n = nc + nn;
+      for (int pass = 0; pass < 8; ++pass) {
+        const int xx = pass * 4 + xb;
+        if (n < t.Bp) XcT[((long)p * t.CP + x0 + xx) * KA + (long)u * t.Bp + n] = __float2bfloat16_rn(tile[nn][xx]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// dE[p][r][c] = sigmoid(5 E[p][r][c]) * sum over the diagonal x - v + W - 1 = c of blk[p][2H-1-r][x][v]
+// One CTA per (dy, pair): the (W+1) x W block goes through shared memory (odd row stride: the diagonal walk is conflict free).
+__global__ void __launch_bounds__(256)
+smt_dp_reduce_kernel(const float* __restrict__ blk, const float* __restrict__ E, SmtDims t, float* __restrict__ dE) {
+  extern __shared__ float rsm[];
+  const int dy = blockIdx.x, p = blockIdx.y;
+  const int W = t.W, LS = W | 1;
+  const float* src = blk + ((long)p * 2 * t.H + dy) * t.CP * t.NP;
+  for (int i = threadIdx.x; i < (W + 1) * t.NP; i += blockDim.x) {
+    const int x = i / t.NP, v = i - x * t.NP;
+    if (v < W) rsm[x * LS + v] = src[i];
+  }
+  __syncthreads();
+  const int r = 2 * t.H - 1 - dy;
+  for (int c = threadIdx.x; c < 2 * W; c += blockDim.x) {
+    const int vlo = max(0, W - 1 - c), vhi = min(W - 1, 2 * W - 1 - c);
+    float s = 0.f;
+    for (int v = vlo; v <= vhi; ++v) s += rsm[(c + v - (W - 1)) * LS + v];
+    const long o = ((long)p * 2 * t.H + r) * 2 * W + c;
+    dE[o] = s * sigmoid5(E[o]);
+  }
+}
+
+int smt_conv(const void* x, const void* w, void* y, int B, int H, int W, int Cin, int Cout, int ksize, int pad_y, int grp, int a_div,
+             int w_cin, int k_rows, int sm_pad, int sm_rows, int sm_rows_in, void* stream) {
+  ConvExArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x_hi = x; a.w_hi = w; a.y = y;
+  a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.Cout_pad = Cout; a.ksize = ksize; a.kw = 1;
+  a.pad_y = pad_y; a.grp = grp; a.a_div = a_div; a.w_cin = w_cin; a.k_rows = k_rows;
+  a.sm_pad = sm_pad; a.sm_rows = sm_rows; a.sm_rows_in = sm_rows_in;
+  a.stream = stream;
+  return jcm_conv_igemm_ex(a);
+}
+
+}  // namespace
+
+extern "C" long jcm_spatial_model_tc_workspace(int B, int H, int W, int K, int P) {
+  SmtDims t;
+  if (fill_smt(t, B, H, W, K, P)) return -1;
+  return (long)smt_fwd_layout(t).total;
+}
+
+// Same arguments and result as jcm_spatial_model_fwd; the convolutions run on the tensor cores with bf16 operands.
+extern "C" int jcm_spatial_model_tc_fwd(const float* heat_map, const float* bn_scale, const float* bn_shift, const float* energies,
+                                        const float* biases, const int* pair_target, const int* pair_cond, float* out,
+                                        void* workspace, long workspace_bytes, int B, int H, int W, int K, int P, void* stream) {
+  JCM_CHECK_ARG(heat_map && bn_scale && bn_shift && energies && biases && pair_target && pair_cond && out && workspace,
+                "jcm_spatial_model_tc_fwd: null pointer");
+  JCM_CHECK_ARG(B > 0 && H > 1 && W > 1 && K > 0 && P > 0, "jcm_spatial_model_tc_fwd: bad shape");
+  SmtDims t;
+  int rc = fill_smt(t, B, H, W, K, P);
+  if (rc) return rc;
+  const SmtFwdWs L = smt_fwd_layout(t);
+  if (workspace_bytes < (long)L.total) {
+    jcm_set_error("jcm_spatial_model_tc_fwd: workspace too small (%ld < %zu bytes)", workspace_bytes, L.total);
+    return JCM_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = (uint8_t*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  float* spE = (float*)(ws + L.spE);
+  __nv_bfloat16* Xh = (__nv_bfloat16*)(ws + L.Xh);
+  __nv_bfloat16* Wf = (__nv_bfloat16*)(ws + L.Wf);
+  float* Cb = (float*)(ws + L.Cb);
+  const int cap = jcm_num_sms() * 16;
+  {
+    const long n = (long)P * 4 * H * W;
+    smt_softplus_kernel<<<(int)((n + 255) / 256 < cap ? (n + 255) / 256 : cap), 256, 0, st>>>(energies, n, spE);
+    JCM_LAUNCH_CHECK();
+    const long total = (long)P * 2 * H * t.NP * (t.CP / 8);
+    smt_pack_prior_kernel<<<(int)((total + 255) / 256 < cap ? (total + 255) / 256 : cap), 256, 0, st>>>(spE, t, 0, Wf);
+    JCM_LAUNCH_CHECK();
+    smt_prep_kernel<<<dim3(t.CP / 32, t.Hc, P), 256, 0, st>>>(heat_map, bn_scale, bn_shift, pair_cond, t, Xh, nullptr);
+    JCM_LAUNCH_CHECK();
+  }
+  // C[p][y][n][x] = sum_dy Xh[p][y+dy-H][n][:] . Wf[p][dy][x][:]
+  rc = smt_conv(Xh, Wf, Cb, P, t.Hc, B, t.CP, t.NP, 2 * H, H, 1, 1, 0, 0, 0, 0, 0, stream);
+  if (rc) return rc;
+  SmDims d;
+  fill_dims(d, B, H, W, K, P);
+  d.cb_sp = (long)t.Hc * B * t.NP; d.cb_sy = B * t.NP; d.cb_sn = t.NP;
+  {
+    int threads = ((W * K + 31) / 32) * 32;
+    if (threads > 1024) threads = 1024;
+    const size_t fsmem = ((size_t)W * K + K + 2) * sizeof(float);
+    sm_finish_kernel<<<B * H, threads, fsmem, st>>>(heat_map, bn_scale, bn_shift, Cb, biases, pair_target, d, out);
+    JCM_LAUNCH_CHECK();
+  }
+  return JCM_OK;
+}
+
+extern "C" long jcm_spatial_model_tc_bwd_workspace(int B, int H, int W, int K, int P) {
+  SmtDims t;
+  if (fill_smt(t, B, H, W, K, P)) return -1;
+  return (long)smt_bwd_layout(t).total;
+}
+
+// Same arguments and results as jcm_spatial_model_bwd; fwd_workspace = the workspace jcm_spatial_model_tc_fwd filled.
+extern "C" int jcm_spatial_model_tc_bwd(const float* g, const float* heat_map, const float* bn_scale, const float* bn_shift,
+                                        const float* bn_mean, const float* bn_rstd, int train, const float* energies,
+                                        const float* biases, const int* pair_target, const int* pair_cond, const void* fwd_workspace,
+                                        void* workspace, long workspace_bytes, float* d_heat_map, float* dE, float* db, float* dgamma,
+                                        float* dbeta, int B, int H, int W, int K, int P, void* stream) {
+  JCM_CHECK_ARG(g && heat_map && bn_scale && bn_shift && energies && biases && pair_target && pair_cond && fwd_workspace && workspace &&
+                    d_heat_map && dE && db && dgamma && dbeta, "jcm_spatial_model_tc_bwd: null pointer");
+  JCM_CHECK_ARG(!train || (bn_mean && bn_rstd), "jcm_spatial_model_tc_bwd: training mode needs the saved batch statistics");
+  JCM_CHECK_ARG(K + 1 <= 32, "jcm_spatial_model_tc_bwd: at most 31 joints are supported (got %d)", K);
+  SmtDims t;
+  int rc = fill_smt(t, B, H, W, K, P);
+  if (rc) return rc;
+  const SmtFwdWs LF = smt_fwd_layout(t);
+  const SmtBwdWs L = smt_bwd_layout(t);
+  if (workspace_bytes < (long)L.total) {
+    jcm_set_error("jcm_spatial_model_tc_bwd: workspace too small (%ld < %zu bytes)", workspace_bytes, L.total);
+    return JCM_EWORKSPACE;
+  }
+  for (int yy = 0; yy < H; ++yy) {
+    const float src = (float)yy * ((float)(H + 1) / (float)H);
+    JCM_CHECK_ARG((int)floorf(src) == yy, "jcm_spatial_model_tc_bwd: unsupported heat-map height %d", H);
+  }
+  for (int xx = 0; xx < W; ++xx) {
+    const float src = (float)xx * ((float)(W + 1) / (float)W);
+    JCM_CHECK_ARG((int)floorf(src) == xx, "jcm_spatial_model_tc_bwd: unsupported heat-map width %d", W);
+  }
+  const size_t dsmem = (size_t)(W + 1) * (W | 1) * sizeof(float);
+  JCM_CHECK_ARG(dsmem <= 227 * 1024 - 256, "jcm_spatial_model_tc_bwd: heat-map width %d not supported", W);
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint8_t* fws = (const uint8_t*)(((uintptr_t)fwd_workspace + 255) & ~(uintptr_t)255);
+  const float* spE = (const float*)(fws + LF.spE);
+  const float* Cb = (const float*)(fws + LF.Cb);
+  uint8_t* ws = (uint8_t*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  float* dT = (float*)(ws + L.dT);
+  __nv_bfloat16* Xc = (__nv_bfloat16*)(ws + L.Xc);
+  __nv_bfloat16* XcT = (__nv_bfloat16*)(ws + L.XcT);
+  __nv_bfloat16* Ht = (__nv_bfloat16*)(ws + L.Ht);
+  __nv_bfloat16* Wd = (__nv_bfloat16*)(ws + L.Wd);
+  float* dL = (float*)(ws + L.dL);
+  float* blk = (float*)(ws + L.blk);
+  float* dh = (float*)(ws + L.dh);
+  float* bnpart = (float*)(ws + L.part);
+  const int cap = jcm_num_sms() * 16;
+
+  SmDims d;
+  fill_dims(d, B, H, W, K, P);
+  d.cb_sp = (long)t.Hc * B * t.NP; d.cb_sy = B * t.NP; d.cb_sn = t.NP;
+  d.dl_sp = (long)t.Hc * B * t.NP; d.dl_sy = B * t.NP; d.dl_sn = t.NP; d.dl_flip = 0;
+  const int G4 = 4 * d.G;
+  {
+    const long total = (long)P * H * W;
+    sm_bwd_dt_kernel<<<(int)((total + 127) / 128), 128, 0, st>>>(g, Cb, biases, pair_target, d, dT, db);
+    JCM_LAUNCH_CHECK();
+    smt_dc_kernel<<<dim3(t.CP / 32, t.Hc, P), 256, 0, st>>>(dT, t, G4, Xc, XcT);
+    JCM_LAUNCH_CHECK();
+    smt_prep_kernel<<<dim3(t.CP / 32, t.Hc, P), 256, 0, st>>>(heat_map, bn_scale, bn_shift, pair_cond, t, nullptr, Ht);
+    JCM_LAUNCH_CHECK();
+    const long tw = (long)P * 2 * H * t.NP * (t.CP / 8);
+    smt_pack_prior_kernel<<<(int)((tw + 255) / 256 < cap ? (tw + 255) / 256 : cap), 256, 0, st>>>(spE, t, 1, Wd);
+    JCM_LAUNCH_CHECK();
+  }
+  // dL[p][u][n][v] = sum_dy Xc[p][u+dy-(H-1)][n][:] . Wd[p][dy][v][:]
+  rc = smt_conv(Xc, Wd, dL, P, t.Hc, B, t.CP, t.NP, 2 * H, H - 1, 1, 1, 0, 0, 0, 0, 0, stream);
+  if (rc) return rc;
+  // blk[p*2H+dy][x][v] = sum_{y,n} XcT[p][x][y*Bp+n] * Ht[p][v][(y+dy-H)*Bp+n]
+  rc = smt_conv(XcT, Ht, blk, P * 2 * H, 1, t.CP, t.Hc * t.Bp, t.NP, 1, 0, 2, 2 * H, H * t.Bp, t.Bp, H, t.Hc, H, stream);
+  if (rc) return rc;
+  {
+    if (dsmem > 48 * 1024) JCM_CUDA(cudaFuncSetAttribute(smt_dp_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
+    smt_dp_reduce_kernel<<<dim3(2 * H, P), 256, dsmem, st>>>(blk, energies, t, dE);
+    JCM_LAUNCH_CHECK();
+  }
+  {
+    const long total = (long)B * H * W * (K + 1);
+    sm_bwd_dh_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(heat_map, bn_scale, bn_shift, g, dL, pair_cond, d, dh);
+    JCM_LAUNCH_CHECK();
+    const long Mr = (long)B * H * W;
+    int nb = (int)((Mr + 255) / 256);
+    if (nb > 2 * jcm_num_sms()) nb = 2 * jcm_num_sms();
     sm_bn_bwd_partial_kernel<<<nb, BNB_THREADS, 0, st>>>(heat_map, dh, bn_mean, bn_rstd, Mr, K + 1, bnpart);
     JCM_LAUNCH_CHECK();
     sm_bn_bwd_apply_kernel<<<2 * jcm_num_sms(), 256, 0, st>>>(heat_map, dh, bn_scale, bn_mean, bn_rstd, bnpart, nb, Mr, K + 1, train,

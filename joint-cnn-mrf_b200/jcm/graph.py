@@ -20,7 +20,7 @@ class Context:
     """The reference's module-level globals (main.py:428-472) as one explicit object."""
 
     def __init__(self, n_joints=9, joint_names=None, flag_train=False, train_pd=True, precision='fp32', debug=False,
-                 lmbd=0.001, use_sm=True, bf16_activations=None):
+                 lmbd=0.001, use_sm=True, bf16_activations=None, sm_tensor_core=None):
         if precision not in ('fp32', 'bf16'):
             raise ValueError("precision must be 'fp32' (bf16x3 split products) or 'bf16'")
         self.n_joints = n_joints
@@ -34,6 +34,7 @@ class Context:
         self.lmbd = lmbd
         self.use_sm = use_sm
         self.bf16_activations = (precision == 'bf16') if bf16_activations is None else bool(bf16_activations)
+        self.sm_tensor_core = (precision == 'bf16') if sm_tensor_core is None else bool(sm_tensor_core)
         self._wcache = {}
 
     @property
@@ -47,6 +48,12 @@ class Context:
         with 16-byte loads of 8 channels (measured +1.8 % images/s at batch 64; layers narrower than 64 channels keep fp32).
         fp32 precision: always fp32."""
         return self.bf16_activations and self.precision == 'bf16'
+
+    @property
+    def sm_tc(self):
+        """bf16 precision (default on, sm_tensor_core=False turns it off): the spatial model's pairwise convolutions run as grouped
+        Toeplitz GEMMs on the tensor cores with bf16 operands instead of the fp32 FFMA kernels.  fp32 precision: always FFMA."""
+        return self.sm_tensor_core and self.precision == 'bf16'
 
     def packed(self, name, w, kind='fwd'):
         """Packed bf16 operand planes of a conv kernel, cached until the parameter tensor is modified in place."""
@@ -272,7 +279,7 @@ def spatial_model(heat_map, sm, ctx):
     """main.py:94-125.  heat_map [B,H,W,K+1] (K soft-maxed part-detector maps + the conditioning channel)."""
     bn = sm.bn
     ss = ops.bn_scale_shift(heat_map, bn['gamma'], bn['beta'], bn['moving_mean'], bn['moving_variance'], train=ctx.flag_train)
-    return ops.spatial_model_fwd(heat_map, ss, sm.energies, sm.biases, sm.pair_target, sm.pair_cond, sm.n_joints)
+    return ops.spatial_model_fwd(heat_map, ss, sm.energies, sm.biases, sm.pair_target, sm.pair_cond, sm.n_joints, tensor_core=ctx.sm_tc)
 
 
 # ----------------------------------------------------------------------------------------------------------

@@ -323,7 +323,9 @@ def argmax_hw(hm):
 
 
 # ------------------------------------------------------------------------------------------------ spatial model
-def spatial_model_fwd(heat_map, ss, energies, biases, pair_target, pair_cond, n_joints, keep_workspace=False):
+def spatial_model_fwd(heat_map, ss, energies, biases, pair_target, pair_cond, n_joints, keep_workspace=False, tensor_core=False):
+    """tensor_core=True: the pairwise convolutions run as grouped Toeplitz GEMMs on the tensor cores with bf16 operands
+    (jcm_spatial_model_tc_fwd, the bf16 configuration); False: the fp32 FFMA kernels."""
     _req(heat_map, F32, 'heat_map')
     _req(energies, F32, 'energies')
     _req(biases, F32, 'biases')
@@ -333,12 +335,16 @@ def spatial_model_fwd(heat_map, ss, energies, biases, pair_target, pair_cond, n_
         raise ValueError('heat_map must have n_joints + 1 channels')
     if tuple(energies.shape) != (P, 2 * H, 2 * W) or tuple(biases.shape) != (P, H, W):
         raise ValueError('energies/biases shapes %s %s do not match heat maps %dx%d' % (tuple(energies.shape), tuple(biases.shape), H, W))
-    nbytes = lib().jcm_spatial_model_workspace(B, H, W, n_joints, P)
+    fn_ws, fn = (lib().jcm_spatial_model_tc_workspace, lib().jcm_spatial_model_tc_fwd) if tensor_core else \
+                (lib().jcm_spatial_model_workspace, lib().jcm_spatial_model_fwd)
+    nbytes = fn_ws(B, H, W, n_joints, P)
+    if nbytes < 0:
+        check(-1, 'jcm_spatial_model_tc_workspace')
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=heat_map.device)
     out = torch.empty((B, H, W, n_joints), dtype=F32, device=heat_map.device)
-    check(lib().jcm_spatial_model_fwd(_ptr(heat_map), _ptr(ss[0]), _ptr(ss[1]), _ptr(energies), _ptr(biases), _ptr(pair_target),
-                                      _ptr(pair_cond), _ptr(out), _ptr(ws), nbytes, B, H, W, n_joints, P, _stream()),
-          'jcm_spatial_model_fwd')
+    check(fn(_ptr(heat_map), _ptr(ss[0]), _ptr(ss[1]), _ptr(energies), _ptr(biases), _ptr(pair_target),
+             _ptr(pair_cond), _ptr(out), _ptr(ws), nbytes, B, H, W, n_joints, P, _stream()),
+          'jcm_spatial_model_tc_fwd' if tensor_core else 'jcm_spatial_model_fwd')
     return (out, ws) if keep_workspace else out
 
 

@@ -108,16 +108,22 @@ def unpack_s2d_grad(g9, dw):
     return dw
 
 
-def spatial_model_bwd(g, heat_map, ss, saved, train, sm, fwd_ws, d_energies, d_biases, dgamma, dbeta):
+def spatial_model_bwd(g, heat_map, ss, saved, train, sm, fwd_ws, d_energies, d_biases, dgamma, dbeta, tensor_core=False):
+    """tensor_core must match the forward call that filled fwd_ws (the two paths keep different workspaces)."""
     B, H, W, KC = heat_map.shape
     K, P = KC - 1, sm.energies.shape[0]
-    nbytes = lib().jcm_spatial_model_bwd_workspace(B, H, W, K, P)
+    fn_ws, fn = (lib().jcm_spatial_model_tc_bwd_workspace, lib().jcm_spatial_model_tc_bwd) if tensor_core else \
+                (lib().jcm_spatial_model_bwd_workspace, lib().jcm_spatial_model_bwd)
+    nbytes = fn_ws(B, H, W, K, P)
+    if nbytes < 0:
+        check(-1, 'jcm_spatial_model_tc_bwd_workspace')
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=g.device)
     d_hm = torch.empty_like(heat_map)
-    check(lib().jcm_spatial_model_bwd(_ptr(g), _ptr(heat_map), _ptr(ss[0]), _ptr(ss[1]), _ptr(saved[0] if saved is not None else None),
+    check(fn(_ptr(g), _ptr(heat_map), _ptr(ss[0]), _ptr(ss[1]), _ptr(saved[0] if saved is not None else None),
                                       _ptr(saved[1] if saved is not None else None), int(train), _ptr(sm.energies), _ptr(sm.biases),
                                       _ptr(sm.pair_target), _ptr(sm.pair_cond), _ptr(fwd_ws), _ptr(ws), nbytes, _ptr(d_hm), _ptr(d_energies),
-                                      _ptr(d_biases), _ptr(dgamma), _ptr(dbeta), B, H, W, K, P, _stream()), 'jcm_spatial_model_bwd')
+                                      _ptr(d_biases), _ptr(dgamma), _ptr(dbeta), B, H, W, K, P, _stream()),
+          'jcm_spatial_model_tc_bwd' if tensor_core else 'jcm_spatial_model_bwd')
     return d_hm
 
 
@@ -245,10 +251,12 @@ class Trainer:
             cat = torch.cat([hm_pd, y[:, :, :, K:]], dim=3).contiguous()       # main.py:528
             ss_sm, st_sm = ops.bn_scale_shift(cat, sm.bn['gamma'], sm.bn['beta'], sm.bn['moving_mean'], sm.bn['moving_variance'],
                                               train=True, save=True)
-            logit_sm, ws_sm = ops.spatial_model_fwd(cat, ss_sm, sm.energies, sm.biases, sm.pair_target, sm.pair_cond, K, keep_workspace=True)
+            logit_sm, ws_sm = ops.spatial_model_fwd(cat, ss_sm, sm.energies, sm.biases, sm.pair_target, sm.pair_cond, K, keep_workspace=True,
+                                                    tensor_core=ctx.sm_tc)
             loss_sm, _, lse_sm = ops.softmax_ce(logit_sm, y, want_lse=True)
             g_sm = softmax_ce_bwd(logit_sm, y, lse_sm, inv_bk)
-            d_cat = spatial_model_bwd(g_sm, cat, ss_sm, st_sm, True, sm, ws_sm, g['sm/energies'], g['sm/biases'], g['sm/gamma'], g['sm/beta'])
+            d_cat = spatial_model_bwd(g_sm, cat, ss_sm, st_sm, True, sm, ws_sm, g['sm/energies'], g['sm/biases'], g['sm/gamma'], g['sm/beta'],
+                                      tensor_core=ctx.sm_tc)
             spatial_softmax_bwd(hm_pd, d_cat, d_logit, accumulate=True)
         else:
             d_logit.mul_(2.0)   # loss_sm == loss_pd when the spatial model is off (main.py:533-536)

@@ -2,7 +2,7 @@
 timings.  Not a pytest file - the pytest parity tests are tests/test_gpu_*.py; this one is for fast triage when a
 kernel is wrong (it localises the first diverging stage) and for quick timing sweeps.
 
-    python tests/gpu_diag.py [sections...]     sections: peak conv glue sm model time grad step wgtime convsweep smtime
+    python tests/gpu_diag.py [sections...]     sections: peak conv glue sm model time grad step wgtime convsweep smtime smtc
 """
 import os
 import sys
@@ -454,6 +454,45 @@ def sec_smtime():
         fl = 2 * 1.469e9 * B
         print('SMTIME spatial model fwd (bn + prep + conv + finish) B=%d: %.3f ms best %.3f median -> %.1f TFLOP/s algorithmic' % (
             B, best, med, fl / best / 1e9))
+
+
+def sec_smtc():
+    """tensor-core spatial model (jcm_spatial_model_tc_*) against the fp32 FFMA kernels on the same inputs, forward and backward."""
+    from jcm import train as jt
+    for (B, K, H, W) in [(2, 4, 12, 20), (3, 7, 60, 90), (64, 7, 60, 90)]:
+        try:
+            names, cat, sm64 = make_sm_inputs(B, K, H, W)
+            smp = jcm.PairwiseParams.from_dict(sm64, names, K)
+            catd = cat.to(dev)
+            ss, saved = ops.bn_scale_shift(catd, smp.bn['gamma'], smp.bn['beta'], smp.bn['moving_mean'], smp.bn['moving_variance'],
+                                           train=True, save=True)
+            g = torch.randn(B, H, W, K, generator=torch.Generator().manual_seed(5)).to(dev) / (B * K)
+            res = {}
+            for tc in (False, True):
+                out, ws = ops.spatial_model_fwd(catd, ss, smp.energies, smp.biases, smp.pair_target, smp.pair_cond, K, keep_workspace=True,
+                                                tensor_core=tc)
+                dE, db = torch.zeros_like(smp.energies), torch.zeros_like(smp.biases)
+                dg, dbt = torch.zeros(K + 1, device=dev), torch.zeros(K + 1, device=dev)
+                dhm = jt.spatial_model_bwd(g, catd, ss, saved, True, smp, ws, dE, db, dg, dbt, tensor_core=tc)
+                torch.cuda.synchronize()
+                res[tc] = dict(out=out, dhm=dhm, dE=dE, db=db, dgamma=dg, dbeta=dbt)
+            print('SMTC B%d K%d %dx%d  ' % (B, K, H, W) + '  '.join('%s %.2e' % (k, relerr(res[True][k], res[False][k])) for k in res[True]))
+            if B <= 3:
+                ref = orc.spatial_model(cat.double(), {k: v.clone() for k, v in sm64.items()}, K, True, joint_names=names)
+                print('   vs oracle: ffma %.2e  tc %.2e' % (relerr(res[False]['out'], ref), relerr(res[True]['out'], ref)))
+            if B == 64:
+                for tc in (False, True):
+                    f = lambda: ops.spatial_model_fwd(catd, ss, smp.energies, smp.biases, smp.pair_target, smp.pair_cond, K, keep_workspace=True,
+                                                      tensor_core=tc)
+                    _, ws = f()
+                    dE, db = torch.zeros_like(smp.energies), torch.zeros_like(smp.biases)
+                    dg, dbt = torch.zeros(K + 1, device=dev), torch.zeros(K + 1, device=dev)
+                    b = lambda: jt.spatial_model_bwd(g, catd, ss, saved, True, smp, ws, dE, db, dg, dbt, tensor_core=tc)
+                    print('   tensor_core=%d: fwd %.3f ms  bwd %.3f ms (best of 10)' % (tc, timeit(f, 10, 3)[0], timeit(b, 10, 3)[0]))
+        except Exception as e:
+            print('SMTC case', (B, K, H, W), 'FAILED', repr(e))
+            traceback.print_exc()
+        sys.stdout.flush()
 
 
 if __name__ == '__main__':

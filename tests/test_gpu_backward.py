@@ -223,8 +223,12 @@ def test_conv1_stride2_wgrad_via_space_to_depth(jcm, jtrain, split):
 # ------------------------------------------------------------------------------------------------ spatial model
 @pytest.mark.parametrize('B,K,H,W', [(2, 4, 12, 20), (5, 3, 9, 13), (2, 7, 60, 90), (6, 7, 60, 90), (3, 2, 96, 128)])
 @pytest.mark.parametrize('train', [True, False])
-def test_spatial_model_bwd(jcm, jtrain, B, K, H, W, train):
-    """dE, db, d(bn gamma/beta), d(heat map) of SURVEY Appendix D vs autograd of the oracle."""
+@pytest.mark.parametrize('tensor_core', [False, True])
+def test_spatial_model_bwd(jcm, jtrain, B, K, H, W, train, tensor_core):
+    """dE, db, d(bn gamma/beta), d(heat map) of SURVEY Appendix D vs autograd of the oracle.  tensor_core: the grouped Toeplitz
+    GEMM form of the bf16 configuration (jcm_spatial_model_tc_*): same interface, bf16 operand rounding (2^-9 per operand) in the
+    pairwise convolutions, so its bounds are the bf16 ones (stated here; measured 3e-4 forward, <= 5e-3 on the gradients)."""
+    tol_o, tol_g = (2e-3, 1.5e-2) if tensor_core else (1e-4, 3e-4)
     seed = 16
     rng = np.random.default_rng(seed)
     g = torch.Generator().manual_seed(seed)
@@ -252,18 +256,21 @@ def test_spatial_model_bwd(jcm, jtrain, B, K, H, W, train):
     bn = smp.bn
     catg = cat.cuda()
     ss, st = jcm.ops.bn_scale_shift(catg, bn['gamma'], bn['beta'], bn['moving_mean'], bn['moving_variance'], train=train, save=True)
-    o, ws = jcm.ops.spatial_model_fwd(catg, ss, smp.energies, smp.biases, smp.pair_target, smp.pair_cond, K, keep_workspace=True)
-    assert rel(o, out) < 1e-4
+    o, ws = jcm.ops.spatial_model_fwd(catg, ss, smp.energies, smp.biases, smp.pair_target, smp.pair_cond, K, keep_workspace=True,
+                                      tensor_core=tensor_core)
+    assert rel(o, out) < tol_o
     dE, db = torch.empty_like(smp.energies), torch.empty_like(smp.biases)
     dgamma, dbeta = torch.empty(K + 1, device='cuda'), torch.empty(K + 1, device='cuda')
-    d_hm = jtrain.spatial_model_bwd(gout.cuda(), catg, ss, st, train, smp, ws, dE, db, dgamma, dbeta)
+    d_hm = jtrain.spatial_model_bwd(gout.cuda(), catg, ss, st, train, smp, ws, dE, db, dgamma, dbeta, tensor_core=tensor_core)
     refE = torch.stack([so['energy_' + k].grad[0, :, :, 0] for k in smp.keys])
     refb = torch.stack([so['bias_' + k].grad[0, :, :, 0] for k in smp.keys])
-    assert rel(dE, refE) < 3e-4
-    assert rel(db, refb) < 3e-4
-    assert rel(d_hm, cat64.grad) < 3e-4
-    assert rel(dgamma, so['bn_sm/BatchNorm/gamma'].grad) < 3e-4
-    assert rel(dbeta, so['bn_sm/BatchNorm/beta'].grad) < 3e-4
+    assert rel(dE, refE) < tol_g
+    assert rel(db, refb) < tol_g
+    assert rel(d_hm, cat64.grad) < tol_g
+    assert rel(dgamma, so['bn_sm/BatchNorm/gamma'].grad) < tol_g
+    assert rel(dbeta, so['bn_sm/BatchNorm/beta'].grad) < tol_g
+    if tensor_core:   # direction of the big gradients, not just their scale
+        assert cosine(dE, refE) > 0.9995 and cosine(d_hm, cat64.grad) > 0.9995
 
 
 # ------------------------------------------------------------------------------------------------ optimizer
