@@ -232,7 +232,8 @@ def run_ours(args):
         distr = synthetic_pairwise(names, K, IH // 8, IW // 8, np.random.default_rng(0))
     sm = jcm.PairwiseParams.from_distribution(distr, names, K, IH // 8, IW // 8, device=dev)
     ctx = jcm.Context(n_joints=K, joint_names=names, flag_train=train, precision=precision,
-                      bf16_activations=None if args.bf16_activations is None else bool(args.bf16_activations))
+                      bf16_activations=None if args.bf16_activations is None else bool(args.bf16_activations),
+                      sm_tensor_core=False if args.sm_ffma else None)
 
     x_host = torch.rand(B, IH, IW, 3, generator=gen).pin_memory()
     y_host = torch.from_numpy(synthetic_labels(B, IH // 8, IW // 8, K + 1, np.random.default_rng(rank))).pin_memory()
@@ -285,6 +286,7 @@ def run_ours(args):
     conv_prof = ops.PROFILE.summary(args.steps, 'conv_igemm_kernel') if rank == 0 else None
     wgrad_prof = ops.PROFILE.summary(args.steps, 'conv_wgrad_kernel') if rank == 0 else None
     conv_big = ops.PROFILE.largest('conv_igemm_kernel') if rank == 0 else None
+    sm_prof = [ops.PROFILE.summary(args.steps, k) for k in ('spatial_model_fwd', 'spatial_model_bwd')] if rank == 0 else None
 
     # ---- end to end through the public API: every step copies its inputs from pinned host memory (jcm.DeviceFeed: the copy of
     # step i+1 runs on a side stream while step i computes) and reads the loss back to the host
@@ -357,6 +359,16 @@ def run_ours(args):
         roof['conv_wgrad_kernel'] = {'achieved': wgrad_prof['tflops'], 'frac': wgrad_prof['tflops'] / peak,
                                      'launches_per_step': wgrad_prof['launches_per_step'],
                                      'share_of_step': wgrad_prof['ms_per_step'] / (ms_total / args.steps)}
+    if sm_prof and sm_prof[0]['launches']:
+        # the spatial model (north_star's second kernel family): CUDA-event time of the whole fwd / bwd call (all of its kernels)
+        tc = bool(ctx.sm_tc)
+        roof['spatial_model'] = {
+            'form': 'tensor cores: grouped Toeplitz GEMMs through conv_igemm_kernel, bf16 operands (bf16 configuration)' if tc
+                    else 'fp32 FFMA2 kernels (sm_conv_kernel / sm_bwd_dp_kernel)',
+            'fwd_ms': sm_prof[0]['ms_per_step'], 'bwd_ms': sm_prof[1]['ms_per_step'],
+            'algorithmic_tflops_fwd': sm_prof[0]['tflops'], 'algorithmic_tflops_bwd': sm_prof[1]['tflops'] if sm_prof[1]['launches'] else None,
+            'fp32_fma_peak_tflops': 73.0,
+            'share_of_step': (sm_prof[0]['ms_per_step'] + sm_prof[1]['ms_per_step']) / (ms_total / args.steps)}
     line = {
         'metric': metric_name(args.workload), 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -386,6 +398,8 @@ def main():
     ap.add_argument('--workload', default=None, choices=sorted(WORKLOADS))
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--sm-ffma', action='store_true',
+                    help='bf16 workloads: run the spatial model on the fp32 FFMA kernels (north_star form) instead of the tensor-core form')
     ap.add_argument('--bf16-activations', type=int, default=None,
                     help='store the post-ReLU activations in bf16 too (bf16 workloads); default: the library default')
     args = ap.parse_args()

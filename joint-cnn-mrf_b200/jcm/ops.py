@@ -342,9 +342,15 @@ def spatial_model_fwd(heat_map, ss, energies, biases, pair_target, pair_cond, n_
         check(-1, 'jcm_spatial_model_tc_workspace')
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=heat_map.device)
     out = torch.empty((B, H, W, n_joints), dtype=F32, device=heat_map.device)
+    if PROFILE.enabled:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(fn(_ptr(heat_map), _ptr(ss[0]), _ptr(ss[1]), _ptr(energies), _ptr(biases), _ptr(pair_target),
              _ptr(pair_cond), _ptr(out), _ptr(ws), nbytes, B, H, W, n_joints, P, _stream()),
           'jcm_spatial_model_tc_fwd' if tensor_core else 'jcm_spatial_model_fwd')
+    if PROFILE.enabled:
+        e1.record()
+        PROFILE.add('spatial_model_fwd', 2.0 * P * B * (H + 1) * (W + 1) * H * W, e0, e1)   # algorithmic: P (H+1)(W+1)HW MAC per image
     return (out, ws) if keep_workspace else out
 
 

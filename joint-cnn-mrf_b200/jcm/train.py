@@ -119,11 +119,18 @@ def spatial_model_bwd(g, heat_map, ss, saved, train, sm, fwd_ws, d_energies, d_b
         check(-1, 'jcm_spatial_model_tc_bwd_workspace')
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=g.device)
     d_hm = torch.empty_like(heat_map)
+    prof = ops.PROFILE.enabled
+    if prof:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(fn(_ptr(g), _ptr(heat_map), _ptr(ss[0]), _ptr(ss[1]), _ptr(saved[0] if saved is not None else None),
                                       _ptr(saved[1] if saved is not None else None), int(train), _ptr(sm.energies), _ptr(sm.biases),
                                       _ptr(sm.pair_target), _ptr(sm.pair_cond), _ptr(fwd_ws), _ptr(ws), nbytes, _ptr(d_hm), _ptr(d_energies),
                                       _ptr(d_biases), _ptr(dgamma), _ptr(dbeta), B, H, W, K, P, _stream()),
           'jcm_spatial_model_tc_bwd' if tensor_core else 'jcm_spatial_model_bwd')
+    if prof:
+        e1.record()
+        ops.PROFILE.add('spatial_model_bwd', 4.0 * P * B * (H + 1) * (W + 1) * H * W, e0, e1)   # dL + dP: twice the forward MACs
     return d_hm
 
 

@@ -495,6 +495,23 @@ def sec_smtc():
         sys.stdout.flush()
 
 
+def sec_smtc64():
+    """one forward + backward of the tensor-core spatial model at the bench shape (for ncu captures of its three GEMM launches)"""
+    from jcm import train as jt
+    B, K, H, W = 64, 7, 60, 90
+    names, cat, sm64 = make_sm_inputs(B, K, H, W)
+    smp = jcm.PairwiseParams.from_dict(sm64, names, K)
+    catd = cat.to(dev)
+    ss, saved = ops.bn_scale_shift(catd, smp.bn['gamma'], smp.bn['beta'], smp.bn['moving_mean'], smp.bn['moving_variance'], train=True, save=True)
+    g = torch.randn(B, H, W, K, generator=torch.Generator().manual_seed(5)).to(dev) / (B * K)
+    out, ws = ops.spatial_model_fwd(catd, ss, smp.energies, smp.biases, smp.pair_target, smp.pair_cond, K, keep_workspace=True, tensor_core=True)
+    dE, db = torch.zeros_like(smp.energies), torch.zeros_like(smp.biases)
+    dg, dbt = torch.zeros(K + 1, device=dev), torch.zeros(K + 1, device=dev)
+    jt.spatial_model_bwd(g, catd, ss, saved, True, smp, ws, dE, db, dg, dbt, tensor_core=True)
+    torch.cuda.synchronize()
+    print('SMTC64 done', float(out.abs().max()))
+
+
 if __name__ == '__main__':
     secs = sys.argv[1:] or ['peak', 'conv', 'glue', 'sm', 'model', 'time']
     print('device:', torch.cuda.get_device_name(0), 'SMs', jcm.lib().jcm_sm_count())
