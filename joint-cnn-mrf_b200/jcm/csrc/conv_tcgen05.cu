@@ -51,6 +51,8 @@ struct ConvParams {
   //   grp 2: batched GEMM with a shifted B operand: image = (batch a_div * q + s), A image q, weight plane q, the weight's K
   //          coordinate is offset by (s - sm_pad) * k_rows and only the k-blocks that can be non-zero are visited
   int grp, grp_taps, a_div, k_rows, sm_pad, sm_rows, sm_rows_in;
+  const int* a_map;     // grp 1: A image = a_map[img] (several pairs share one conditioning map); NULL: img
+  const int* b_map;     // grp 2: weight plane = b_map[img / a_div]; NULL: img / a_div
   int dbg;              // measurement switches (JCM_CONV_DBG bit 0: epilogue releases TMEM without storing, bit 1: no MMAs issued,
                         // bit 2: producer skips the B loads) - results are garbage, timing only
   const float* bias;
@@ -340,8 +342,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         const int x0 = tx * p.TW - p.pad_x, y0 = ty * p.TH - p.pad;
         if (p.grp) {
           const KRange kr = tile_krange(p, img, ty);
-          const int a_img = p.grp == 2 ? img / p.a_div : img;
-          const int b_plane = p.grp == 2 ? img / p.a_div : img * p.grp_taps;
+          const int q = img / p.a_div;
+          const int a_img = p.grp == 2 ? q : (p.a_map ? p.a_map[img] : img);
+          const int b_plane = p.grp == 2 ? (p.b_map ? p.b_map[q] : q) : img * p.grp_taps;
           const int b_koff = p.grp == 2 ? (img % p.a_div - p.sm_pad) * p.k_rows : 0;
           for (int tap = kr.tap_lo; tap < kr.tap_hi; ++tap) {
             for (int cb = kr.cb_lo; cb < kr.cb_hi; ++cb) {
@@ -696,6 +699,9 @@ int jcm_conv_igemm_ex(const ConvExArgs& a) {
   p.pad_x = (kw - 1) / 2;
   p.grp = a.grp; p.grp_taps = ksize * kw; p.a_div = a.a_div > 0 ? a.a_div : 1; p.k_rows = a.k_rows;
   p.sm_pad = a.sm_pad; p.sm_rows = a.sm_rows; p.sm_rows_in = a.sm_rows_in;
+  p.a_map = a.grp == 1 ? a.img_map : nullptr;
+  p.b_map = a.grp == 2 ? a.img_map : nullptr;
+  JCM_CHECK_ARG(!a.img_map || a.map_images > 0, "jcm_conv_igemm_ex: img_map needs map_images");
   p.terms = x_lo ? 3 : 1;
   p.a_bytes = kTileM * p.kc * 2;
   p.b_bytes = p.block_n * p.kc * 2;
@@ -751,7 +757,7 @@ int jcm_conv_igemm_ex(const ConvExArgs& a) {
   const CUtensorMapSwizzle swz = p.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   {
-    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)(a.grp == 2 ? B / p.a_div : B)};
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)(a.grp == 2 ? B / p.a_div : (p.a_map ? a.map_images : B))};
     uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
     uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)p.TW, (uint32_t)p.TH, 1};
     int rc = make_map(&ma_hi, x_hi, 4, dims, str, box, swz);
@@ -763,7 +769,8 @@ int jcm_conv_igemm_ex(const ConvExArgs& a) {
   {
     // weight planes: one per tap; grouped forms: B * taps planes (grp 1), B / a_div planes with their own K extent w_cin (grp 2)
     const uint64_t wc = a.grp == 2 ? (uint64_t)a.w_cin : (uint64_t)Cin;
-    const uint64_t planes = a.grp == 1 ? (uint64_t)B * ksize * kw : (a.grp == 2 ? (uint64_t)(B / p.a_div) : (uint64_t)(ksize * kw));
+    const uint64_t planes = a.grp == 1 ? (uint64_t)B * ksize * kw
+                                        : (a.grp == 2 ? (uint64_t)(p.b_map ? a.map_images : B / p.a_div) : (uint64_t)(ksize * kw));
     uint64_t dims[3] = {wc, (uint64_t)Cout_pad, planes};
     uint64_t str[2] = {wc * 2, (uint64_t)Cout_pad * wc * 2};
     uint32_t box[3] = {(uint32_t)p.kc, (uint32_t)p.block_n, 1};

@@ -730,22 +730,25 @@ void fill_dp_dims(DpDims& dp, const SmDims& df, const SmDims& dm, int B, int H, 
 __global__ void sm_bwd_dh_kernel(const float* __restrict__ hm, const float* __restrict__ scale, const float* __restrict__ shift,
                                  const float* __restrict__ g, const float* __restrict__ dLf, const int* __restrict__ pair_cond, SmDims d,
                                  float* __restrict__ dhbn) {
+  // thread <-> (n, y, j, x) with x fastest: a warp reads 32 consecutive x of one pair's dL row (the big operand) coalesced and the
+  // cond(p) == j test is warp-uniform; the small [.., KC] tensors are accessed with a KC-float stride
   const int KC = d.K + 1;
   const long total = (long)d.B * d.H * d.W * KC;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int j = (int)(idx % KC);
-    long t = idx / KC;
-    const int x = (int)(t % d.W);
-    t /= d.W;
+    const int x = (int)(idx % d.W);
+    long t = idx / d.W;
+    const int j = (int)(t % KC);
+    t /= KC;
     const int y = (int)(t % d.H);
     const int n = (int)(t / d.H);
-    const float hb = fmaf(hm[idx], scale[j], shift[j]);
+    const long e = (((long)n * d.H + y) * d.W + x) * KC + j;
+    const float hb = fmaf(hm[e], scale[j], shift[j]);
+    const float* src = dLf + (long)n * d.dl_sn + (long)(d.dl_flip ? d.H - 1 - y : y) * d.dl_sy + (d.dl_flip ? d.W - 1 - x : x);
     float s = 0.f;
     for (int p = 0; p < d.P; ++p)
-      if (pair_cond[p] == j)
-        s += dLf[(long)p * d.dl_sp + (long)n * d.dl_sn + (long)(d.dl_flip ? d.H - 1 - y : y) * d.dl_sy + (d.dl_flip ? d.W - 1 - x : x)];
+      if (pair_cond[p] == j) s += src[(long)p * d.dl_sp];
     if (j < d.K) s += g[(((long)n * d.H + y) * d.W + x) * d.K + j] / (softplus5(hb) + kDelta);
-    dhbn[idx] = s * sigmoid5(hb);
+    dhbn[e] = s * sigmoid5(hb);
   }
 }
 
@@ -956,7 +959,7 @@ SmtFwdWs smt_fwd_layout(const SmtDims& t) {
   SmtFwdWs w;
   size_t o = 0;
   w.spE = o; o += al256((size_t)t.P * 2 * t.H * 2 * t.W * 4);
-  w.Xh = o;  o += al256((size_t)t.P * t.Hc * t.B * t.CP * 2);
+  w.Xh = o;  o += al256((size_t)(t.K + 1) * t.Hc * t.B * t.CP * 2);
   w.Wf = o;  o += al256((size_t)t.P * 2 * t.H * t.NP * t.CP * 2);
   w.Cb = o;  o += al256((size_t)t.P * t.Hc * t.B * t.NP * 4);
   w.total = o + 256;
@@ -970,7 +973,7 @@ SmtBwdWs smt_bwd_layout(const SmtDims& t) {
   w.dT = o;   o += al256((size_t)t.P * G4 * t.H * t.W * 4);
   w.Xc = o;   o += al256((size_t)t.P * t.Hc * t.B * t.CP * 2);
   w.XcT = o;  o += al256((size_t)t.P * t.CP * t.Hc * t.Bp * 2);
-  w.Ht = o;   o += al256((size_t)t.P * t.NP * t.H * t.Bp * 2);
+  w.Ht = o;   o += al256((size_t)(t.K + 1) * t.NP * t.H * t.Bp * 2);
   w.Wd = o;   o += al256((size_t)t.P * 2 * t.H * t.NP * t.CP * 2);
   w.dL = o;   o += al256((size_t)t.P * t.Hc * t.B * t.NP * 4);
   w.blk = o;  o += al256((size_t)t.P * 2 * t.H * t.CP * t.NP * 4);
@@ -1009,14 +1012,15 @@ __global__ void smt_pack_prior_kernel(const float* __restrict__ spE, SmtDims t, 
   }
 }
 
-// Xh[p][y (Hc)][n (B)][v (CP)] = h_cond(p)[n][y][v] (0 in the padding);  Ht[p][v (NP)][y*Bp + n] = the same values, transposed
-// (the dP GEMM's B operand; rows y < H only).  One CTA per (32 columns, row, pair); either output may be NULL.
+// Xh[j][y (Hc)][n (B)][v (CP)] = h_j[n][y][v] (0 in the padding), one "image" per heat-map channel j (the GEMM kernels pick the
+// pair's conditioning channel through pair_cond);  Ht[j][v (NP)][y*Bp + n] = the same values, transposed (the dP GEMM's B
+// operand; rows y < H only).  One CTA per (32 columns, row, channel); either output may be NULL.
 __global__ void __launch_bounds__(256)
-smt_prep_kernel(const float* __restrict__ hm, const float* __restrict__ scale, const float* __restrict__ shift,
-                const int* __restrict__ pair_cond, SmtDims t, __nv_bfloat16* __restrict__ Xh, __nv_bfloat16* __restrict__ Ht) {
+smt_prep_kernel(const float* __restrict__ hm, const float* __restrict__ scale, const float* __restrict__ shift, SmtDims t,
+                __nv_bfloat16* __restrict__ Xh, __nv_bfloat16* __restrict__ Ht) {
   __shared__ float tile[64][33];
   const int v0 = blockIdx.x * 32, y = blockIdx.y, p = blockIdx.z;
-  const int j = pair_cond[p], KC = t.K + 1;
+  const int j = p, KC = t.K + 1;
   const float sc = scale[j], sh = shift[j];
   const long KH = (long)t.H * t.Bp;
   for (int nc = 0; nc < t.Bp; nc += 64) {
@@ -1117,13 +1121,14 @@ smt_dp_reduce_kernel(const float* __restrict__ blk, const float* __restrict__ E,
 }
 
 int smt_conv(const void* x, const void* w, void* y, int B, int H, int W, int Cin, int Cout, int ksize, int pad_y, int grp, int a_div,
-             int w_cin, int k_rows, int sm_pad, int sm_rows, int sm_rows_in, void* stream) {
+             int w_cin, int k_rows, int sm_pad, int sm_rows, int sm_rows_in, const int* img_map, int map_images, void* stream) {
   ConvExArgs a;
   memset(&a, 0, sizeof(a));
   a.x_hi = x; a.w_hi = w; a.y = y;
   a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.Cout_pad = Cout; a.ksize = ksize; a.kw = 1;
   a.pad_y = pad_y; a.grp = grp; a.a_div = a_div; a.w_cin = w_cin; a.k_rows = k_rows;
   a.sm_pad = sm_pad; a.sm_rows = sm_rows; a.sm_rows_in = sm_rows_in;
+  a.img_map = img_map; a.map_images = map_images;
   a.stream = stream;
   return jcm_conv_igemm_ex(a);
 }
@@ -1165,11 +1170,11 @@ extern "C" int jcm_spatial_model_tc_fwd(const float* heat_map, const float* bn_s
     const long total = (long)P * 2 * H * t.NP * (t.CP / 8);
     smt_pack_prior_kernel<<<(int)((total + 255) / 256 < cap ? (total + 255) / 256 : cap), 256, 0, st>>>(spE, t, 0, Wf);
     JCM_LAUNCH_CHECK();
-    smt_prep_kernel<<<dim3(t.CP / 32, t.Hc, P), 256, 0, st>>>(heat_map, bn_scale, bn_shift, pair_cond, t, Xh, nullptr);
+    smt_prep_kernel<<<dim3(t.CP / 32, t.Hc, K + 1), 256, 0, st>>>(heat_map, bn_scale, bn_shift, t, Xh, nullptr);
     JCM_LAUNCH_CHECK();
   }
-  // C[p][y][n][x] = sum_dy Xh[p][y+dy-H][n][:] . Wf[p][dy][x][:]
-  rc = smt_conv(Xh, Wf, Cb, P, t.Hc, B, t.CP, t.NP, 2 * H, H, 1, 1, 0, 0, 0, 0, 0, stream);
+  // C[p][y][n][x] = sum_dy Xh[cond(p)][y+dy-H][n][:] . Wf[p][dy][x][:]
+  rc = smt_conv(Xh, Wf, Cb, P, t.Hc, B, t.CP, t.NP, 2 * H, H, 1, 1, 0, 0, 0, 0, 0, pair_cond, K + 1, stream);
   if (rc) return rc;
   SmDims d;
   fill_dims(d, B, H, W, K, P);
@@ -1246,17 +1251,17 @@ extern "C" int jcm_spatial_model_tc_bwd(const float* g, const float* heat_map, c
     JCM_LAUNCH_CHECK();
     smt_dc_kernel<<<dim3(t.CP / 32, t.Hc, P), 256, 0, st>>>(dT, t, G4, Xc, XcT);
     JCM_LAUNCH_CHECK();
-    smt_prep_kernel<<<dim3(t.CP / 32, t.Hc, P), 256, 0, st>>>(heat_map, bn_scale, bn_shift, pair_cond, t, nullptr, Ht);
+    smt_prep_kernel<<<dim3(t.CP / 32, t.Hc, K + 1), 256, 0, st>>>(heat_map, bn_scale, bn_shift, t, nullptr, Ht);
     JCM_LAUNCH_CHECK();
     const long tw = (long)P * 2 * H * t.NP * (t.CP / 8);
     smt_pack_prior_kernel<<<(int)((tw + 255) / 256 < cap ? (tw + 255) / 256 : cap), 256, 0, st>>>(spE, t, 1, Wd);
     JCM_LAUNCH_CHECK();
   }
   // dL[p][u][n][v] = sum_dy Xc[p][u+dy-(H-1)][n][:] . Wd[p][dy][v][:]
-  rc = smt_conv(Xc, Wd, dL, P, t.Hc, B, t.CP, t.NP, 2 * H, H - 1, 1, 1, 0, 0, 0, 0, 0, stream);
+  rc = smt_conv(Xc, Wd, dL, P, t.Hc, B, t.CP, t.NP, 2 * H, H - 1, 1, 1, 0, 0, 0, 0, 0, nullptr, 0, stream);
   if (rc) return rc;
-  // blk[p*2H+dy][x][v] = sum_{y,n} XcT[p][x][y*Bp+n] * Ht[p][v][(y+dy-H)*Bp+n]
-  rc = smt_conv(XcT, Ht, blk, P * 2 * H, 1, t.CP, t.Hc * t.Bp, t.NP, 1, 0, 2, 2 * H, H * t.Bp, t.Bp, H, t.Hc, H, stream);
+  // blk[p*2H+dy][x][v] = sum_{y,n} XcT[p][x][y*Bp+n] * Ht[cond(p)][v][(y+dy-H)*Bp+n]
+  rc = smt_conv(XcT, Ht, blk, P * 2 * H, 1, t.CP, t.Hc * t.Bp, t.NP, 1, 0, 2, 2 * H, H * t.Bp, t.Bp, H, t.Hc, H, pair_cond, K + 1, stream);
   if (rc) return rc;
   {
     if (dsmem > 48 * 1024) JCM_CUDA(cudaFuncSetAttribute(smt_dp_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
