@@ -139,10 +139,8 @@ __global__ void bn_relu_bwd_kernel(BnBwdArgs p) {
         load_f32_vec<VEC>(p.dout, r * p.C + (long)g * VEC, dv);
 #pragma unroll
         for (int c = 0; c < VEC; ++c) dv[c] *= p.dy_scale;
-        const int xo = (int)(r % Wo);
-        const long t = r / Wo;
-        const int yo = (int)(t % Ho);
-        const int n = (int)(t / Ho);
+        int xo, yo, n;
+        split_index3(r, Wo, Ho, xo, yo, n);
         const int y0 = 2 * yo, x0 = 2 * xo;
         float av[4][VEC];   // [window element][channel]
         bool ok[4];
@@ -244,16 +242,12 @@ __global__ void upsample_bwd_kernel(const float* __restrict__ dm, int B, int H, 
   const int C4 = C / 4;
   const long total = (long)B * Hi * Wi * C4;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % C4);
-    long t = i / C4;
-    const int q = (int)(t % Wi);
-    t /= Wi;
-    const int pp = (int)(t % Hi);
-    const int n = (int)(t / Hi);
+    int c4, q, pp, n;
+    split_index(i, C4, Wi, Hi, c4, q, pp, n);
     // destination rows whose lo or hi tap can be pp: lo(y) = floor(y*Hi/H) in {pp-1, pp}  <=>  y in [(pp-1)*H/Hi, (pp+1)*H/Hi);
     // one row of slack on each side covers the fp32 rounding of the tap computation (the weights are re-checked below)
-    const int ylo0 = max(0, (int)(((long)(pp - 1) * H) / Hi) - 1), yhi0 = min(H - 1, (int)(((long)(pp + 1) * H + Hi - 1) / Hi));
-    const int xlo0 = max(0, (int)(((long)(q - 1) * W) / Wi) - 1), xhi0 = min(W - 1, (int)(((long)(q + 1) * W + Wi - 1) / Wi));
+    const int ylo0 = max(0, ((pp - 1) * H) / Hi - 1), yhi0 = min(H - 1, ((pp + 1) * H + Hi - 1) / Hi);
+    const int xlo0 = max(0, ((q - 1) * W) / Wi - 1), xhi0 = min(W - 1, ((q + 1) * W + Wi - 1) / Wi);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int y = ylo0; y <= yhi0; ++y) {
       int lo, hi;

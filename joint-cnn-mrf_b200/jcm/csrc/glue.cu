@@ -111,12 +111,8 @@ __global__ void bn_apply_pool_kernel(const void* __restrict__ a, int a_bf16, con
   const int CG = C / VEC;
   const long total = (long)B * Ho * Wo * CG;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % CG);
-    long t = i / CG;
-    const int xo = (int)(t % Wo);
-    t /= Wo;
-    const int yo = (int)(t % Ho);
-    const int n = (int)(t / Ho);
+    int cg, xo, yo, n;
+    split_index(i, CG, Wo, Ho, cg, xo, yo, n);
     float sc[VEC], sh[VEC], r[VEC];
     load_f32_vec<VEC>(scale, (long)cg * VEC, sc);
     load_f32_vec<VEC>(shift, (long)cg * VEC, sh);
@@ -191,12 +187,8 @@ __global__ void upsample_avg3_kernel(const void* __restrict__ a1, const void* __
   const int CG = C / VEC;
   const long total = (long)B * H * W * CG;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % CG);
-    long t = i / CG;
-    const int x = (int)(t % W);
-    t /= W;
-    const int y = (int)(t % H);
-    const int n = (int)(t / H);
+    int cg, x, y, n;
+    split_index(i, CG, W, H, cg, x, y, n);
     float sc[VEC], sh[VEC], v1[VEC], v2[VEC], v3[VEC], r[VEC];
     load_f32_vec<VEC>(ss + 0 * C, (long)cg * VEC, sc);
     load_f32_vec<VEC>(ss + 1 * C, (long)cg * VEC, sh);

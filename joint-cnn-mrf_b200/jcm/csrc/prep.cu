@@ -23,10 +23,8 @@ __global__ void prep_input_kernel(const float* __restrict__ x, int B, int H, int
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int dxi = (int)(i & 3);
     const long pix = i >> 2;
-    const int X = (int)(pix % Wo);
-    const long t = pix / Wo;
-    const int Y = (int)(t % Ho);
-    const int n = (int)(t / Ho);
+    int X, Y, n;
+    split_index3(pix, Wo, Ho, X, Y, n);
     __align__(16) __nv_bfloat16 vh[16];
     __align__(16) __nv_bfloat16 vl[16];
 #pragma unroll
@@ -59,10 +57,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int taps, int C
                                     int transpose, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   const long total = (long)taps * Opad * Ipad;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int i = (int)(idx % Ipad);
-    const long t = idx / Ipad;
-    const int o = (int)(t % Opad);
-    const int tap = (int)(t / Opad);
+    int i, o, tap;
+    split_index3(idx, Ipad, Opad, i, o, tap);
     float v = 0.f;
     if (!transpose) {
       if (o < Cout && i < Cin) v = w[((long)tap * Cin + i) * Cout + o];

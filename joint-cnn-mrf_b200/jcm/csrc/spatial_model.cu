@@ -735,12 +735,8 @@ __global__ void sm_bwd_dh_kernel(const float* __restrict__ hm, const float* __re
   const int KC = d.K + 1;
   const long total = (long)d.B * d.H * d.W * KC;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int x = (int)(idx % d.W);
-    long t = idx / d.W;
-    const int j = (int)(t % KC);
-    t /= KC;
-    const int y = (int)(t % d.H);
-    const int n = (int)(t / d.H);
+    int x, j, y, n;
+    split_index(idx, d.W, KC, d.H, x, j, y, n);
     const long e = (((long)n * d.H + y) * d.W + x) * KC + j;
     const float hb = fmaf(hm[e], scale[j], shift[j]);
     const float* src = dLf + (long)n * d.dl_sn + (long)(d.dl_flip ? d.H - 1 - y : y) * d.dl_sy + (d.dl_flip ? d.W - 1 - x : x);
@@ -994,12 +990,8 @@ __global__ void smt_pack_prior_kernel(const float* __restrict__ spE, SmtDims t, 
   const int C8 = t.CP / 8, H2 = 2 * t.H, W2 = 2 * t.W;
   const long total = (long)t.P * H2 * t.NP * C8;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(idx % C8);
-    long r = idx / C8;
-    const int row = (int)(r % t.NP);
-    r /= t.NP;
-    const int dy = (int)(r % H2);
-    const int p = (int)(r / H2);
+    int c8, row, dy, p;
+    split_index(idx, C8, t.NP, H2, c8, row, dy, p);
     const float* src = spE + ((long)p * H2 + (dl ? dy : H2 - 1 - dy)) * W2;
     __align__(16) __nv_bfloat16 o[8];
 #pragma unroll

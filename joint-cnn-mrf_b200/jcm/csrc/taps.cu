@@ -44,12 +44,8 @@ __global__ void tap_gather_kernel(const float* __restrict__ z, const float* __re
   const int Q = KP / 4, pad = (ksize - 1) / 2;
   const long total = (long)B * H * W * Q;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int q = (int)(i % Q);
-    long t = i / Q;
-    const int px = (int)(t % W);
-    t /= W;
-    const int py = (int)(t % H);
-    const int n = (int)(t / H);
+    int q, px, py, n;
+    split_index(i, Q, W, H, q, px, py, n);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int dy = 0; dy < ksize; ++dy) {
       const int yy = py + dy - pad;
@@ -80,12 +76,8 @@ __global__ void tap_scatter_planes_kernel(const float* __restrict__ g, int B, in
   const int G8 = Npad / 8, pad = (ksize - 1) / 2, taps = ksize * ksize;
   const long total = (long)B * H * W * G8;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int g8 = (int)(i % G8);
-    long t = i / G8;
-    const int qx = (int)(t % W);
-    t /= W;
-    const int qy = (int)(t % H);
-    const int n = (int)(t / H);
+    int g8, qx, qy, n;
+    split_index(i, G8, W, H, g8, qx, qy, n);
     __align__(16) __nv_bfloat16 h[8];
     __align__(16) __nv_bfloat16 l[8];
     // walk the 8 channels with running (tap, co): one division per thread instead of three per element
