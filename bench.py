@@ -180,7 +180,7 @@ def run_reference(args):
         'e2e': {'value': val, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def metric_name(workload):
@@ -385,12 +385,35 @@ def run_ours(args):
     }
     if cpu is not None:
         line['cpu_baseline'] = cpu
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries print there too (NCCL's version banner under NCCL_DEBUG=VERSION, measured on
+    the GPU boxes: it ignores NCCL_DEBUG_FILE), so file descriptor 1 is pointed at stderr for everything else and the result line
+    goes to a private duplicate of the original stdout."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        fd = os.dup(1)
+        os.dup2(2, 1)
+        _RESULT_OUT = os.fdopen(fd, 'w')
+    return _RESULT_OUT
+
+
+def emit(line):
+    out = claim_stdout()
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)

@@ -177,3 +177,15 @@ def _mk_parts(jcm, names, K):
     distr = {a + '_' + b: torch.rand(16, 24, generator=gen).numpy() for a in names[:K] for b in names if a != b}
     sm = jcm.PairwiseParams.from_distribution(distr, names, K, 8, 12, device='cpu')
     return p, sm, jcm.Context(n_joints=K, joint_names=names, flag_train=True, precision='bf16', debug=True)
+
+
+def test_bench_stdout_carries_only_the_result_line():
+    """bench.py contract: ONE JSON line on stdout.  NCCL writes its version banner to file descriptor 1 on the GPU boxes
+    (NCCL_DEBUG=VERSION in their environment), so bench.py points fd 1 at stderr and keeps a private handle for the result."""
+    import subprocess
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench.claim_stdout(); os.write(1, b'NCCL version x\\n'); "
+            "print('python-level noise'); bench.emit({'a': 1})" % ROOT)
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == '{"a": 1}\n'
+    assert 'NCCL version x' in r.stderr and 'python-level noise' in r.stderr
