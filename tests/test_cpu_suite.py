@@ -124,6 +124,22 @@ def test_argument_errors_do_not_need_a_gpu(built_lib):
         jcm.Context(precision='fp16')
 
 
+def test_context_selects_the_spatial_model_form_by_precision(built_lib):
+    """fp32 configuration: always the fp32 FFMA kernels (the 1e-3 / bit-exact arg-max path).  bf16 configuration: the tensor-core
+    form unless switched off.  The workspace queries of both forms answer without a GPU."""
+    import jcm
+    assert not jcm.Context(n_joints=7).sm_tc
+    assert not jcm.Context(n_joints=7, precision='fp32', sm_tensor_core=True).sm_tc
+    assert jcm.Context(n_joints=7, precision='bf16').sm_tc
+    assert not jcm.Context(n_joints=7, precision='bf16', sm_tensor_core=False).sm_tc
+    l = jcm.lib()
+    assert l.jcm_spatial_model_tc_workspace(64, 60, 90, 7, 49) > 0 and l.jcm_spatial_model_tc_bwd_workspace(64, 60, 90, 7, 49) > 0
+    assert l.jcm_spatial_model_tc_workspace(2, 60, 300, 7, 49) < 0          # maps wider than 255 columns: not supported
+    assert b'width' in l.jcm_last_error()
+    rc = l.jcm_spatial_model_tc_fwd(None, None, None, None, None, None, None, None, None, 0, 2, 60, 90, 7, 49, None)
+    assert rc == -1 and b'null pointer' in l.jcm_last_error()
+
+
 def test_product_path_does_not_import_the_oracle():
     pkg = os.path.join(ROOT, 'joint-cnn-mrf_b200', 'jcm')
     for f in os.listdir(pkg):
