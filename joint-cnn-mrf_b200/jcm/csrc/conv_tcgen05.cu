@@ -597,6 +597,274 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
   }
 }
 
+// =====================================================================================================================
+// EXPERIMENTAL (off unless JCM_CONV_CTA2=1; written at the end of round 1 without GPU time left to run it - round 2 starts by
+// testing it): the plain-mode kernel for N = 256 layers as a CTA PAIR (`cta_group::2`).  Two CTAs of a cluster own two adjacent
+// 128-pixel M tiles of the same N tile; each loads its own A tile and HALF of the weight tile (128 of the 256 rows), the leader
+// issues one M = 256 MMA per K step that reads both CTAs' shared memory and writes each CTA's own TMEM.  Per CTA and k-block the
+// L2->SM traffic drops from 48 KB to 32 KB and the B operand's shared-memory reads halve - the step is power-capped with the
+// tensor pipe at 93 % of the sustained peak, so energy per FLOP is what is left to gain.
+// Protocol (PTX forms as in CUTLASS's sm100 2-SM collective, cute/arch/copy_sm100_tma.hpp, cutlass/arch/barrier.h):
+//   * full[s] lives in the LEADER (cluster rank 0): its producer arms it with the bytes of both CTAs; both producers' TMA
+//     loads carry `.cta_group::2` and the leader's barrier address (own address with the peer bit 24 cleared).
+//   * empty[s] / tfull[a] exist in both CTAs at the same offset and are signalled by `tcgen05.commit.cta_group::2 ...
+//     .multicast::cluster` (mask 0b11); tempty[a] lives in the leader and counts the 8 epilogue warps of both CTAs
+//     (`mbarrier.arrive.shared::cluster` on the leader's address).
+//   * TMEM: one warp of EACH CTA issues `tcgen05.alloc.cta_group::2` (same warp index, same destination offset).
+// =====================================================================================================================
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the even CTA of the pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_igemm_cta2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                       const __grid_constant__ CUtensorMap map_y, const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[kMaxStages]);
+  const uint32_t bar_tfull = smem_u32(&bars[2 * kMaxStages]);
+  const uint32_t bar_tempty = smem_u32(&bars[2 * kMaxStages + 2]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kMaxStages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_tfull + 8 * s, 1);
+      mbar_init(bar_tempty + 8 * s, 8);       // 4 epilogue warps of each CTA of the pair (used in the leader only)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                         // the peer's barriers are initialised before anything arrives on them
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int m_tiles = p.B * p.tiles_y * p.tiles_x;
+  const int m_pairs = (m_tiles + 1) / 2;
+  const int total_pairs = m_pairs * p.n_tiles;
+  const int pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
+  const int taps = p.ksize * p.kw;
+  const int num_kb = taps * p.cblocks * p.terms;
+  const int half_n = p.block_n >> 1;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair0; t < total_pairs; t += pair_step) {
+        const int nt = t / m_pairs, mt = 2 * (t - nt * m_pairs) + (int)rank;
+        // a pair's second tile may lie past the last M tile: image index B is out of bounds, TMA fills zeros / clips the store
+        const int img = mt / (p.tiles_y * p.tiles_x);
+        const int r = mt - img * (p.tiles_y * p.tiles_x);
+        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        const int x0 = tx * p.TW - p.pad_x, y0 = ty * p.TH - p.pad;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int dy = tap / p.kw, dx = tap - dy * p.kw;
+          for (int cb = 0; cb < p.cblocks; ++cb) {
+            for (int term = 0; term < p.terms; ++term) {
+              mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+              const uint32_t sa = smem_base + stage * p.stage_bytes;
+              const uint32_t fb = bar_full + 8 * stage;
+              if (rank == 0) mbar_expect_tx(fb, 2 * (p.a_bytes + p.b_bytes));          // both CTAs' tiles land on the leader's barrier
+              tma_load_4d_2sm(sa, term == 1 ? &map_a_lo : &map_a_hi, fb, cb * p.kc, x0 + dx, y0 + dy, img);
+              tma_load_3d_2sm(sa + p.a_bytes, term == 2 ? &map_b_lo : &map_b_hi, fb, cb * p.kc, nt * p.block_n + (int)rank * half_n, tap);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0 && elect_one()) {
+      // D = f32, A = B = bf16, K-major, N = block_n, M = 256 (the pair's two 128-row halves)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t row_bytes = p.kc * 2;
+      const uint32_t layout = (p.kc == 64) ? 2u : (p.kc == 32 ? 4u : 6u);
+      const uint32_t sbo = 8 * row_bytes;
+      const int kk = p.kc / 16;
+      const uint64_t desc_hi = make_smem_desc(0, sbo, layout);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = pair0; t < total_pairs; t += pair_step) {
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * p.stage_bytes;
+          const uint64_t adesc = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
+          const uint64_t bdesc = desc_hi | (uint64_t)(((sa + p.a_bytes) >> 4) & 0x3FFF);
+          for (int k = 0; k < kk; ++k)
+            tc_mma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          tc_commit_2sm(bar_empty + 8 * stage);      // frees the stage in both CTAs
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_2sm(bar_tfull + 8 * acc);          // both CTAs' epilogues may drain their half
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs; TMA-store forms only) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int epi_chunk = 0;
+    const uint32_t stage0 = smem_base + p.stages * p.stage_bytes;
+    for (int t = pair0; t < total_pairs; t += pair_step) {
+      const int nt = t / m_pairs, mt = 2 * (t - nt * m_pairs) + (int)rank;
+      const int img = mt / (p.tiles_y * p.tiles_x);
+      const int r = mt - img * (p.tiles_y * p.tiles_x);
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
+      if (p.y_bf16) {
+        for (int c0 = 0; c0 < p.block_n; c0 += 64) {
+          const uint32_t buf = stage0 + (uint32_t)(epi_chunk & 1) * (kTileM * 128);
+          if (threadIdx.x == 128) bulk_wait_read<1>();
+          epi_bar();
+          uint32_t v[32], u[32];
+          tc_ld32(taddr0 + c0, v);
+          tc_ld32(taddr0 + c0 + 32, u);
+          tc_ld_wait();
+          const int co0 = nt * p.block_n + c0;
+          const uint32_t rowaddr = buf + (uint32_t)row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(j < 4 ? v[8 * j + e] : u[8 * (j - 4) + e]);
+            if (p.bias && co0 + 8 * j < p.Cout) {
+              const float4 b0 = *reinterpret_cast<const float4*>(p.bias + co0 + 8 * j);
+              const float4 b1 = *reinterpret_cast<const float4*>(p.bias + co0 + 8 * j + 4);
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+            }
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+              w[e] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (uint32_t)((j ^ (row & 7)) << 4)), "r"(w[0]), "r"(w[1]),
+                         "r"(w[2]), "r"(w[3])
+                         : "memory");
+          }
+          fence_proxy_async();
+          epi_bar();
+          if (threadIdx.x == 128) {
+            if (co0 < p.Cout) tma_store_4d(&map_y, buf, co0, tx * p.TW, ty * p.TH, img);
+            bulk_commit();
+          }
+          ++epi_chunk;
+        }
+      } else {
+        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+          const uint32_t buf = stage0 + (uint32_t)(epi_chunk & 1) * (kTileM * 128);
+          if (threadIdx.x == 128) bulk_wait_read<1>();
+          epi_bar();
+          uint32_t v[32];
+          tc_ld32(taddr0 + c0, v);
+          tc_ld_wait();
+          const int co0 = nt * p.block_n + c0;
+          const uint32_t rowaddr = buf + (uint32_t)row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                   __uint_as_float(v[4 * j + 3]));
+            if (p.bias && co0 + 4 * j < p.Cout) {
+              const float4 b = *reinterpret_cast<const float4*>(p.bias + co0 + 4 * j);
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (uint32_t)((j ^ (row & 7)) << 4)), "f"(o.x), "f"(o.y),
+                         "f"(o.z), "f"(o.w)
+                         : "memory");
+          }
+          fence_proxy_async();
+          epi_bar();
+          if (threadIdx.x == 128) {
+            if (co0 < p.Cout) tma_store_4d(&map_y, buf, co0, tx * p.TW, ty * p.TH, img);
+            bulk_commit();
+          }
+          ++epi_chunk;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(bar_tempty + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (threadIdx.x == 128) bulk_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                         // neither CTA's shared memory / TMEM goes away while the pair still uses it
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                          const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -747,6 +1015,16 @@ int jcm_conv_igemm_ex(const ConvExArgs& a) {
     if (p.b_stages > kMaxStages) p.b_stages = kMaxStages;
     p.halo = p.b_stages >= 3;
   }
+  // experimental CTA-pair form of the plain mode for N = 256 layers (conv_igemm_cta2_kernel): off unless JCM_CONV_CTA2=1
+  static const int cta2_env = getenv("JCM_CONV_CTA2") ? atoi(getenv("JCM_CONV_CTA2")) : 0;
+  const bool cta2 = cta2_env && !p.halo && p.grp == 0 && p.block_n == 256 && p.tma_store && p.nacc == 1 && !p.mma_split_n && !p.dbg &&
+                    jcm_num_sms() >= 2;
+  if (cta2) {
+    p.b_bytes = (p.block_n / 2) * p.kc * 2;            // each CTA of the pair holds half of the weight tile
+    p.stage_bytes = ((p.a_bytes + p.b_bytes + 1023) / 1024) * 1024;
+    p.stages = (225 * 1024 - epi_bytes) / p.stage_bytes;
+    if (p.stages > kMaxStages) p.stages = kMaxStages;
+  }
   p.relu = relu;
   p.bias = bias;
   p.y = (float*)y;
@@ -773,7 +1051,7 @@ int jcm_conv_igemm_ex(const ConvExArgs& a) {
                                         : (a.grp == 2 ? (uint64_t)(p.b_map ? a.map_images : B / p.a_div) : (uint64_t)(ksize * kw));
     uint64_t dims[3] = {wc, (uint64_t)Cout_pad, planes};
     uint64_t str[2] = {wc * 2, (uint64_t)Cout_pad * wc * 2};
-    uint32_t box[3] = {(uint32_t)p.kc, (uint32_t)p.block_n, 1};
+    uint32_t box[3] = {(uint32_t)p.kc, (uint32_t)(cta2 ? p.block_n / 2 : p.block_n), 1};
     int rc = make_map(&mb_hi, w_hi, 3, dims, str, box, swz);
     if (rc) return rc;
     rc = make_map(&mb_lo, w_lo ? w_lo : w_hi, 3, dims, str, box, swz);
@@ -792,6 +1070,21 @@ int jcm_conv_igemm_ex(const ConvExArgs& a) {
     if (rc) return rc;
   }
 
+  if (cta2) {
+    const int m_tiles = B * p.tiles_x * p.tiles_y;
+    const int pairs = ((m_tiles + 1) / 2) * p.n_tiles;
+    int grid2 = jcm_num_sms() & ~1;
+    if (grid2 > 2 * pairs) grid2 = 2 * pairs;
+    const size_t smem2 = (size_t)p.stages * p.stage_bytes + epi_bytes + 1024;
+    static bool attr2_set = false;
+    if (!attr2_set) {
+      JCM_CUDA(cudaFuncSetAttribute(conv_igemm_cta2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512));
+      attr2_set = true;
+    }
+    conv_igemm_cta2_kernel<<<grid2, kThreads, smem2, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, my, p);
+    JCM_LAUNCH_CHECK();
+    return JCM_OK;
+  }
   const int total_tiles = B * p.tiles_x * p.tiles_y * p.n_tiles;
   int grid = jcm_num_sms();
   if (grid > total_tiles) grid = total_tiles;
