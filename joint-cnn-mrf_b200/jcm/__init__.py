@@ -10,3 +10,4 @@ from . import train  # noqa: F401,E402  (Trainer: the data-parallel training ste
 from .feed import DeviceFeed  # noqa: F401,E402
 from .checkpoint import save_checkpoint, load_checkpoint  # noqa: F401,E402
 from . import augment  # noqa: F401,E402  (augmentation.py: augment_train / augment_test)
+from . import dataset  # noqa: F401,E402  (data.py / prepare_pairwise_distribution.py: label, image and prior file formats)
