@@ -11,3 +11,4 @@ from .feed import DeviceFeed  # noqa: F401,E402
 from .checkpoint import save_checkpoint, load_checkpoint  # noqa: F401,E402
 from . import augment  # noqa: F401,E402  (augmentation.py: augment_train / augment_test)
 from . import dataset  # noqa: F401,E402  (data.py / prepare_pairwise_distribution.py: label, image and prior file formats)
+from . import multiscale  # noqa: F401,E402  (main.py:326-425: multi-scale test-time inference)
