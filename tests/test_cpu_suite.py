@@ -104,7 +104,10 @@ def test_sass_contains_blackwell_instructions(built_lib):
     """tcgen05.mma -> UTC*MMA, TMA -> UTMALDG, tcgen05.ld -> LDTM, packed fp32 FMA -> FFMA2 (B200_PROFILING.md)."""
     import subprocess
     sass = subprocess.run(['cuobjdump', '-sass', built_lib], capture_output=True, text=True).stdout
-    for mnemonic in ('UTCHMMA', 'UTMALDG', 'LDTM', 'FFMA2'):
+    for mnemonic in ('UTCHMMA', 'UTMALDG', 'LDTM', 'FFMA2', 'UTMASTG'):
+        assert mnemonic in sass, mnemonic
+    # the experimental CTA-pair kernel (JCM_CONV_CTA2=1, not yet run on a GPU) keeps compiling to the 2-SM forms
+    for mnemonic in ('UTCHMMA.2CTA', 'UTMALDG.4D.2CTA', 'UTCBAR.2CTA.MULTICAST'):
         assert mnemonic in sass, mnemonic
 
 
