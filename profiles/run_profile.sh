@@ -15,3 +15,7 @@ $NCU --set full --clock-control none --import-source on -k regex:"conv_igemm_ker
 $NCU -i /tmp/prof_${WL}.ncu-rep --page raw --csv > gpurun_out/prof_${WL}_raw.csv 2>/dev/null
 $NCU -i /tmp/prof_${WL}.ncu-rep --page source --csv -k regex:sm_conv_kernel -c 1 > gpurun_out/prof_${WL}_smconv_source.csv 2>/dev/null
 ls -la gpurun_out/ /tmp/prof_${WL}.ncu-rep
+# the three spatial-model GEMM launches (tensor-core form) on their own: raw page -> gpurun_out/ncu_full_smtc_raw.csv
+$NCU --set full --clock-control none --import-source on -k regex:conv_igemm_kernel -c 3 -f -o /tmp/prof_smtc python tests/gpu_diag.py smtc64 \
+    > gpurun_out/ncu_smtc.log 2>&1
+$NCU -i /tmp/prof_smtc.ncu-rep --page raw --csv > gpurun_out/ncu_full_smtc_raw.csv 2>/dev/null
