@@ -281,7 +281,7 @@ def run_ours(args):
     barrier()
     ops.PROFILE.enabled = False
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = (jcm.lib().jcm_launch_count() - launches0) // max(args.steps, 1)
+    launches = jcm.lib().jcm_launch_count() - launches0            # libjcm kernel launches inside the timed region (all K steps, this rank)
     clocks = sampler.stop() if rank == 0 else None
     conv_prof = ops.PROFILE.summary(args.steps, 'conv_igemm_kernel') if rank == 0 else None
     wgrad_prof = ops.PROFILE.summary(args.steps, 'conv_wgrad_kernel') if rank == 0 else None
@@ -379,6 +379,7 @@ def run_ours(args):
         'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': int(x_host.numel() * 4 + y_host.numel() * 4),
                 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches),
+        'gpu_launches_per_step': int(launches) // max(args.steps, 1),
         'clocks': clocks,
         'roofline': roof,
         'loss': float(loss.item()) if torch.is_tensor(loss) else float(loss),
