@@ -208,3 +208,24 @@ def test_bench_stdout_carries_only_the_result_line():
     assert r.returncode == 0, r.stderr
     assert r.stdout == '{"a": 1}\n'
     assert 'NCCL version x' in r.stderr and 'python-level noise' in r.stderr
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU stand-in: the oracle port on the host cores) prints ONE JSON line with the
+    contract's keys; under torchrun every rank but 0 exits silently."""
+    import json
+    import subprocess
+    cmd = [sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--workload', 'fwd16', '--steps', '1', '--warmup', '0']
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline',
+              'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
+        assert k in d, k
+    assert d['impl'] == 'reference' and d['value'] > 0 and d['vs_baseline'] is None and 'workload' in d['config']
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, RANK='1', WORLD_SIZE='2'))
+    assert r1.returncode == 0 and r1.stdout.strip() == ''
