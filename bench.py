@@ -173,7 +173,9 @@ def run_reference(args):
         'impl': 'reference', 'metric': metric_name(args.workload), 'value': val, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(ts), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': workload_config(args.workload, args.gpus),
+        'config': dict(workload_config(args.workload, args.gpus), per_gpu_batch=sample_b, global_batch=sample_b,
+                       sample='CPU arm: each step is a bounded sample of %d images of the workload (its batch of %d would take minutes per step '
+                              'on the host cores); images/s is per image, so the two arms compare per image' % (sample_b, WORKLOADS[args.workload][0])),
         'cpu_baseline': {'value': val, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
                          'sample': '%d images per step (%s), torch-CPU fp32 restatement of the reference TF graph '
                                    '(TensorFlow 1.x not installable)' % (sample_b, args.workload)},
@@ -204,23 +206,14 @@ def workload_config(workload, n_gpus):
 # ----------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------
-def run_ours(args):
+def measure(workload, steps, warmup, args, rank, world, local, dev, with_cpu_baseline, with_e2e=True):
+    """One leg: W warm-up steps, K timed steps (device-resident inputs), then K end-to-end steps.  Returns the result dict (rank 0)
+    or None (other ranks).  Everything allocated here is released before returning, so legs can follow each other."""
     import torch.distributed as dist
     import jcm
     from jcm import ops
 
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    if not torch.cuda.is_available():
-        raise SystemExit('bench.py: no CUDA device - the jcm kernels have no CPU fallback')
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-    jcm.lib()  # fail loudly if libjcm.so is missing
-
-    B, K, IH, IW, train, precision = WORKLOADS[args.workload]
+    B, K, IH, IW, train, precision = WORKLOADS[workload]
     gen = torch.Generator().manual_seed(1234 + rank)
     wgen = torch.Generator().manual_seed(0)          # identical parameters on every replica
     p = jcm.init_part_detector(K, wgen, device=dev)
@@ -239,6 +232,7 @@ def run_ours(args):
     y_host = torch.from_numpy(synthetic_labels(B, IH // 8, IW // 8, K + 1, np.random.default_rng(rank))).pin_memory()
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
 
+    trainer = None
     if train:
         from jcm import train as jtrain
         trainer = jtrain.Trainer(p, sm, ctx, world_size=world)
@@ -264,7 +258,7 @@ def run_ours(args):
         return float(t.item())
 
     # ---- device-resident timing
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step(x_dev, y_dev)
     barrier()
     sampler = ClockSampler(local)
@@ -274,73 +268,92 @@ def run_ours(args):
     ops.PROFILE.clear()
     ops.PROFILE.enabled = rank == 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         loss = step(x_dev, y_dev)
     e1.record()
+    host_ms = 1e3 * (time.perf_counter() - t_host0) / steps      # CPU time to ISSUE one step (no synchronisation inside the loop)
     barrier()
     ops.PROFILE.enabled = False
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = jcm.lib().jcm_launch_count() - launches0            # libjcm kernel launches inside the timed region (all K steps, this rank)
     clocks = sampler.stop() if rank == 0 else None
-    conv_prof = ops.PROFILE.summary(args.steps, 'conv_igemm_kernel') if rank == 0 else None
-    wgrad_prof = ops.PROFILE.summary(args.steps, 'conv_wgrad_kernel') if rank == 0 else None
+    conv_prof = ops.PROFILE.summary(steps, 'conv_igemm_kernel') if rank == 0 else None
+    wgrad_prof = ops.PROFILE.summary(steps, 'conv_wgrad_kernel') if rank == 0 else None
     conv_big = ops.PROFILE.largest('conv_igemm_kernel') if rank == 0 else None
-    sm_prof = [ops.PROFILE.summary(args.steps, k) for k in ('spatial_model_fwd', 'spatial_model_bwd')] if rank == 0 else None
+    conv_shapes = ops.PROFILE.by_shape('conv_igemm_kernel', steps) if rank == 0 else None
+    wgrad_shapes = ops.PROFILE.by_shape('conv_wgrad_kernel', steps) if rank == 0 else None
+    sm_prof = [ops.PROFILE.summary(steps, k) for k in ('spatial_model_fwd', 'spatial_model_bwd')] if rank == 0 else None
+    ops.PROFILE.clear()
+
+    # ---- replica consistency (N > 1, training): every replica must hold the same parameters, optimizer slots and BatchNorm
+    # moving statistics after the timed steps (each saw DIFFERENT data): bit patterns summed as integers, compared across ranks
+    replicas_identical = None
+    if world > 1 and trainer is not None:
+        sums = torch.stack([t.view(torch.int32).to(torch.int64).sum() for t in (trainer.flat, trainer.m, trainer.v, trainer.moving)])
+        gathered = [torch.empty_like(sums) for _ in range(world)]
+        dist.all_gather(gathered, sums)
+        replicas_identical = bool(all(torch.equal(gathered[0], g) for g in gathered))
 
     # ---- end to end through the public API: every step copies its inputs from pinned host memory (jcm.DeviceFeed: the copy of
     # step i+1 runs on a side stream while step i computes) and reads the loss back to the host
-    res_host = torch.empty(1, dtype=torch.float32).pin_memory()
-    feed = jcm.DeviceFeed(dev)
-    for _ in range(min(args.warmup, 2)):
-        feed.submit(x_host, y_host)
-        step(*feed.take())
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    feed.submit(x_host, y_host)                       # step 0's inputs: inside the timed region, nothing to overlap with yet
-    for i in range(args.steps):
-        xd, yd = feed.take()
-        if i + 1 < args.steps:
-            feed.submit(x_host, y_host)               # next step's inputs, overlapped with this step's kernels
-        loss = step(xd, yd)
-        res_host.copy_(loss.reshape(1), non_blocking=True)
-    e3.record()
-    barrier()
-    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
-
+    ms_e2e = None
+    if with_e2e:
+        res_host = torch.empty(1, dtype=torch.float32).pin_memory()
+        feed = jcm.DeviceFeed(dev)
+        for _ in range(min(warmup, 2)):
+            feed.submit(x_host, y_host)
+            step(*feed.take())
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        feed.submit(x_host, y_host)                       # step 0's inputs: inside the timed region, nothing to overlap with yet
+        for i in range(steps):
+            xd, yd = feed.take()
+            if i + 1 < steps:
+                feed.submit(x_host, y_host)               # next step's inputs, overlapped with this step's kernels
+            loss = step(xd, yd)
+            res_host.copy_(loss.reshape(1), non_blocking=True)
+        e3.record()
+        barrier()
+        ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    loss_value = float(loss.item()) if torch.is_tensor(loss) else float(loss)
+    h2d = int(x_host.numel() * 4 + y_host.numel() * 4)
+    sm_tc = bool(ctx.sm_tc)
+    del trainer, p, sm, x_dev, y_dev, x_host, y_host, step, loss
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     peaks = load_peaks()
-    imgs = B * world * args.steps
+    imgs = B * world * steps
     value = imgs / (ms_total / 1e3)
-    e2e_value = imgs / (ms_e2e / 1e3)
 
     # CPU baseline on a bounded sample (rank 0, N = 1 only)
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if with_cpu_baseline:
         sample_b = 2
-        st = cpu_reference_step_fn(args.workload, sample_b)
+        st = cpu_reference_step_fn(workload, sample_b)
         ts = time_cpu(st, 3, 1)
         cpu = {'value': sample_b / min(ts), 'unit': 'images/s', 'cores': os.cpu_count() or 1, 'kind': 'port',
-               'sample': 'best of 3 steps of %d images (%s) after 1 warm-up; torch-CPU fp32 restatement of the reference TF graph '
-                         '(TensorFlow 1.x not installable here)' % (sample_b, args.workload)}
+               'sample': 'best of 3 steps of %d images (a bounded sample of the %s workload, not its batch of %d) after 1 warm-up; torch-CPU '
+                         'fp32 restatement of the reference TF graph (TensorFlow 1.x not installable here)' % (sample_b, workload, B)}
 
     peak = peaks['bf16_sustained']
-    # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this same command (per launch, like achieved)
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of this same command and binary (per launch, like
+    # `achieved`): profiles/r02/ncu_full_<workload>_traffic.json is written by profiles/summarize_ncu.py from the capture
     traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, 'profiles', 'r01', 'ncu_full_train64_v8_traffic.json')) as f:
+        with open(os.path.join(ROOT, 'profiles', 'r02', 'ncu_full_%s_traffic.json' % workload)) as f:
             tj = json.load(f)
-        if args.workload == 'train64':
-            traffic = tj['kernels']['conv_igemm_kernel']['dram_bytes_per_launch']
-            traffic_src = 'profiles/r01/ncu_full_train64_v8_traffic.json (mean over the 25 launches of a step)'
+        traffic = tj['kernels']['conv_igemm_kernel']['dram_bytes_per_launch']
+        traffic_src = 'profiles/r02/ncu_full_%s_traffic.json (%s)' % (workload, tj.get('note', 'mean over the launches of a step'))
     except Exception:
         pass
-    mult = 1 if train else 3
+    mult = 1 if precision == 'bf16' else 3
     roof = {'bound': 'tensor', 'kernel': 'conv_igemm_kernel (tcgen05 implicit GEMM: forward + data-gradient convolutions, %d launches/step)'
                                           % conv_prof['launches_per_step'],
             'achieved': conv_prof['tflops'], 'peak': peak, 'unit': 'TFLOP/s', 'frac': conv_prof['tflops'] / peak,
@@ -351,42 +364,91 @@ def run_ours(args):
                     'measured live in this run; peak = bf16_tflops_sustained of %s (kernel timed inside a long power-capped step); '
                     'tensor-core MMAs executed per algorithmic MAC: %d (fp32 config = bf16x3 split products, ceiling of frac 1/3)'
                     % (peaks['source'], mult),
-            'share_of_step': conv_prof['ms_per_step'] / (ms_total / args.steps)}
+            'share_of_step': conv_prof['ms_per_step'] / (ms_total / steps)}
     if conv_big:
         roof['largest_launch'] = {'layer': 'conv5 9x9 512->512 (forward / data gradient)', 'achieved': conv_big['tflops'],
                                   'frac': conv_big['tflops'] / peak, 'ms': conv_big['ms']}
+    if conv_shapes:
+        # per launch shape ("HxW Cin->Cout kernel", forward and data-gradient launches of one shape share a row): live CUDA-event time
+        roof['shapes'] = [dict(d, frac=d['tflops'] / peak) for d in conv_shapes]
     if wgrad_prof and wgrad_prof['launches']:
         roof['conv_wgrad_kernel'] = {'achieved': wgrad_prof['tflops'], 'frac': wgrad_prof['tflops'] / peak,
                                      'launches_per_step': wgrad_prof['launches_per_step'],
-                                     'share_of_step': wgrad_prof['ms_per_step'] / (ms_total / args.steps)}
+                                     'share_of_step': wgrad_prof['ms_per_step'] / (ms_total / steps),
+                                     'shapes': [dict(d, frac=d['tflops'] / peak) for d in wgrad_shapes]}
     if sm_prof and sm_prof[0]['launches']:
         # the spatial model (north_star's second kernel family): CUDA-event time of the whole fwd / bwd call (all of its kernels)
-        tc = bool(ctx.sm_tc)
         roof['spatial_model'] = {
-            'form': 'tensor cores: grouped Toeplitz GEMMs through conv_igemm_kernel, bf16 operands (bf16 configuration)' if tc
+            'form': 'tensor cores: grouped Toeplitz GEMMs through conv_igemm_kernel, bf16 operands (bf16 configuration)' if sm_tc
                     else 'fp32 FFMA2 kernels (sm_conv_kernel / sm_bwd_dp_kernel)',
             'fwd_ms': sm_prof[0]['ms_per_step'], 'bwd_ms': sm_prof[1]['ms_per_step'],
             'algorithmic_tflops_fwd': sm_prof[0]['tflops'], 'algorithmic_tflops_bwd': sm_prof[1]['tflops'] if sm_prof[1]['launches'] else None,
             'fp32_fma_peak_tflops': 73.0,
-            'share_of_step': (sm_prof[0]['ms_per_step'] + sm_prof[1]['ms_per_step']) / (ms_total / args.steps)}
+            'share_of_step': (sm_prof[0]['ms_per_step'] + sm_prof[1]['ms_per_step']) / (ms_total / steps)}
     line = {
-        'metric': metric_name(args.workload), 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'bf16' if train else 'f32',
-        'dtype_detail': 'bf16 tensor-core operands and stored activations, fp32 accumulation, fp32 master weights / gradients / optimizer' if train
-                        else 'fp32-equivalent: every product is 3 bf16 tensor-core MMAs (hi*hi + lo*hi + hi*lo), fp32 accumulation',
-        'data': 'synthetic', 'config': workload_config(args.workload, world),
-        'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': int(x_host.numel() * 4 + y_host.numel() * 4),
-                'd2h_bytes_per_step': 4},
+        'metric': metric_name(workload), 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': steps, 'warmup': warmup,
+        'ms_per_step': ms_total / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'bf16' if precision == 'bf16' else 'f32',
+        'dtype_detail': 'bf16 tensor-core operands and stored activations, fp32 accumulation, fp32 master weights / gradients / optimizer'
+                        if precision == 'bf16' else 'fp32-equivalent: every product is 3 bf16 tensor-core MMAs (hi*hi + lo*hi + hi*lo), fp32 accumulation',
+        'data': 'synthetic', 'config': workload_config(workload, world),
         'gpu_launches': int(launches),
-        'gpu_launches_per_step': int(launches) // max(args.steps, 1),
+        'gpu_launches_per_step': int(launches) // max(steps, 1),
+        'host_ms_per_step': host_ms,
+        'host_note': 'CPU time to issue one step (Python + ctypes + tensor-map encoding), no synchronisation in the loop; the step is '
+                     'GPU-bound while this is below ms_per_step',
         'clocks': clocks,
         'roofline': roof,
-        'loss': float(loss.item()) if torch.is_tensor(loss) else float(loss),
+        'loss': loss_value,
     }
+    if ms_e2e is not None:
+        line['e2e'] = {'value': imgs / (ms_e2e / 1e3), 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4}
+    if replicas_identical is not None:
+        line['replicas_identical'] = replicas_identical
+        line['replicas_note'] = 'integer checksums of the parameter, Adam m / v and BatchNorm moving-statistic buffers compared across ranks after the timed steps'
     if cpu is not None:
         line['cpu_baseline'] = cpu
-    emit(line)
+    return line
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import jcm
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device - the jcm kernels have no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    jcm.lib()  # fail loudly if libjcm.so is missing
+
+    line = measure(args.workload, args.steps, args.warmup, args, rank, world, local, dev,
+                   with_cpu_baseline=(world == 1 and not args.no_cpu_baseline))
+    # Extra legs: the other BASELINE configurations, so that the driver's record holds them too.  Short (5 steps after 3 warm-up), after
+    # the headline measurement, never allowed to break it.  configs[1] (fwd16) is a single-GPU configuration; configs[4] (K=14) is
+    # quoted on 8 GPUs and runs at every N.
+    if args.extra_legs and args.workload == 'train64':
+        extra = {}
+        for wl in (['fwd16'] if world == 1 else []) + ['train_k14']:
+            try:
+                r = measure(wl, 5, 3, args, rank, world, local, dev, with_cpu_baseline=False, with_e2e=(world == 1))
+                if r is not None:
+                    keep = ('metric', 'value', 'unit', 'ms_per_step', 'dtype', 'config', 'e2e', 'gpu_launches_per_step', 'host_ms_per_step',
+                            'loss', 'replicas_identical', 'steps', 'warmup', 'n_gpus')
+                    extra[wl] = {k: r[k] for k in keep if k in r}
+                    extra[wl]['roofline'] = {k: r['roofline'][k] for k in ('achieved', 'peak', 'frac', 'unit', 'share_of_step', 'spatial_model')
+                                             if k in r['roofline']}
+            except Exception as e:   # noqa: BLE001
+                if rank == 0:
+                    extra[wl] = {'error': repr(e)[:300]}
+        if rank == 0:
+            line['extra_legs'] = extra
+    if rank == 0:
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -422,6 +484,8 @@ def main():
     ap.add_argument('--workload', default=None, choices=sorted(WORKLOADS))
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra-legs', dest='extra_legs', action='store_false',
+                    help='train64 only: skip the short fwd16 (configs[1], N=1) and train_k14 (configs[4]) legs reported under "extra_legs"')
     ap.add_argument('--sm-ffma', action='store_true',
                     help='bf16 workloads: run the spatial model on the fp32 FFMA kernels (north_star form) instead of the tensor-core form')
     ap.add_argument('--bf16-activations', type=int, default=None,

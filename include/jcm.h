@@ -193,6 +193,22 @@ int jcm_grad_prepare(float* g, const float* w, long n, long n_decay, float inv_w
 int jcm_clip_adam(float* w, const float* g, float* m, float* v, long n, const float* stats, float clip, float lr_t, float b1,
                   float b2, float eps, int momentum, void* stream);
 
+/* ---- stand-alone pieces of the function surface (used by jcm.conv_layer / conv2d / weight_decay / average_gradients / grad_renorm;
+ * inside the fused training step the same arithmetic lives in jcm_conv2d_fwd's epilogue, jcm_grad_prepare and jcm_clip_adam) ---- */
+/* out[0] (+)= mul * sum x^2.  weight_decay(var_pattern), main.py:195-205 = sum of tf.nn.l2_loss: mul 0.5, accumulate from the second
+ * variable on; squared global norm of tf.clip_by_global_norm, main.py:302-309: mul 1.  partial: jcm_optim_blocks(n) floats. */
+int jcm_sumsq(const float* x, long n, float mul, int accumulate, float* partial, float* out, void* stream);
+/* out = g * clip / max(sqrt(sumsq[0]), clip): grad_renorm, main.py:302-309 (sumsq[0] over the whole gradient list). */
+int jcm_clip_scale(const float* g, long n, const float* sumsq, float clip, float* out, void* stream);
+/* out = mean of n_towers (<= 16) gradient tensors on this device, summed in tower order: average_gradients, main.py:243-267.
+ * towers: HOST array of device pointers. */
+int jcm_tower_mean(const float* const* towers, int n_towers, long n, float* out, void* stream);
+/* y = x[:, oy::2, ox::2, :]: turns the stride-1 SAME convolution into tf.nn.conv2d(strides=[1,2,2,1], 'SAME'), main.py:133-135
+ * (oy/ox = 1 for an even input extent, 0 for an odd one). */
+int jcm_subsample2(const float* x, int B, int H, int W, int C, int oy, int ox, float* y, void* stream);
+/* out = [relu](x + bias) per channel of x [M,C]: `conv2d(...) + b`, tf.nn.relu of conv_layer, main.py:160-162. */
+int jcm_bias_relu(const float* x, const float* bias, long M, int C, int relu, float* out, void* stream);
+
 /* ---- training augmentation (augmentation.py:12-77, applied at main.py:495-499 before the tower forward) -------
  * NHWC fp32; prm [B][8] on the device = {flip 0/1, brightness delta, contrast factor, cos(angle), sin(angle), rh, rw, unused}:
  * the caller makes the random draws (tf.random_uniform in the reference).  src != out for the resampling kernels. */

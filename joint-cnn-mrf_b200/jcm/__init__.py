@@ -5,7 +5,8 @@ from . import ops  # noqa: F401
 from .graph import (Context, PairwiseParams, JOINT_NAMES, model, spatial_model, conv_mrf, conv2d, batch_norm,  # noqa: F401
                     max_pool_layer, weight_variable, bias_variable, spatial_softmax, softmax_cross_entropy,
                     get_joints_coords, det_rate, get_pairwise_distr, init_part_detector, load_params, tower_forward,
-                    n_filters, conv_specs, eval_error)
+                    n_filters, conv_specs, eval_error, conv_layer, weight_decay, average_gradients, grad_renorm,
+                    params_updated)
 from . import train  # noqa: F401,E402  (Trainer: the data-parallel training step, main.py:474-577)
 from .feed import DeviceFeed  # noqa: F401,E402
 from .checkpoint import save_checkpoint, load_checkpoint  # noqa: F401,E402

@@ -62,6 +62,11 @@ SIGNATURES = {
     'jcm_optim_blocks': (_I, [_L]),
     'jcm_grad_prepare': (_I, [_P, _P, _L, _L, _F, _F, _P, _P, _P]),
     'jcm_clip_adam': (_I, [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _I, _P]),
+    'jcm_sumsq': (_I, [_P, _L, _F, _I, _P, _P, _P]),
+    'jcm_clip_scale': (_I, [_P, _L, _P, _F, _P, _P]),
+    'jcm_tower_mean': (_I, [_P, _I, _L, _P, _P]),
+    'jcm_subsample2': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    'jcm_bias_relu': (_I, [_P, _P, _L, _I, _I, _P, _P]),
     'jcm_fma_peak': (_I, [_P, _I, _I, _I, _P, _P]),
     'jcm_debug_conv2d_naive': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
 }

@@ -53,7 +53,9 @@ def _flat_views(trainer):
 
 
 def save_checkpoint(path, trainer):
-    """Writes <path> (.npz).  Call on rank 0 only: the replicas hold identical state."""
+    """Writes <path> (.npz).  Call on rank 0 only: the replicas hold identical state - parameters and optimizer slots because
+    every replica applies the same all-reduced gradient, the BatchNorm moving statistics because Trainer.apply() reduces them
+    across replicas every step (bench.py reports `replicas_identical` from checksums of both)."""
     np.savez(path, **state_dict(trainer))
 
 
@@ -85,5 +87,6 @@ def load_checkpoint(path, trainer, strict=True):
             elif strict:
                 raise KeyError('checkpoint lacks optimizer slot ' + key)
     trainer.t = int(data['n_iters']) if 'n_iters' in data else trainer.t
-    trainer.ctx._wcache.clear()      # packed operand planes are stale
+    from .graph import params_updated
+    params_updated()                 # packed operand planes are stale (in every Context)
     return trainer

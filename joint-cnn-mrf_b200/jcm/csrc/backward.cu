@@ -1,6 +1,7 @@
 // Backward (HBM-bound) kernels of the part detector and the loss heads.  The reference gets these from TensorFlow's
 // autodiff of main.py:29-74,212-240 (`opt.compute_gradients(loss_tower)`, main.py:557-560); here they are written out:
-//   jcm_softmax_ce_bwd        d(mean CE)/d logits = (softmax * sum(y) - y) / (B*K)                         (main.py:239)
+//   jcm_softmax_ce_bwd        d(mean CE)/d logits = (softmax - y) / (B*K): the backprop output of TF1's
+//                             SoftmaxCrossEntropyWithLogits op, whatever sum(y) is [TF1]                     (main.py:239)
 //   jcm_spatial_softmax_bwd   dx = y * (dy - sum_s dy*y)   (joint training: spatial model input -> PD logits, main.py:523-530)
 //   jcm_bn_relu_bwd           [2x2 SAME max-pool bwd] + training-mode batch-norm bwd + ReLU bwd in two passes
 //                             (reduce: sum dy, sum dy*xhat per channel; apply: d_pre planes + per-block bias-grad partials)
@@ -27,17 +28,16 @@ __device__ float blk_sum(float v, float* sh) {
 // one block per (image, joint)
 __global__ void softmax_ce_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ labels, const float* __restrict__ lse,
                                       int S, int K, int KL, float scale, float* __restrict__ dlogits) {
-  __shared__ float sh[32];
   const int n = blockIdx.x / K, k = blockIdx.x % K;
   const float* src = logits + (long)n * S * K + k;
   const float* lab = labels + (long)n * S * KL + k;
   float* dst = dlogits + (long)n * S * K + k;
-  float sy = 0.f;
-  for (int s = threadIdx.x; s < S; s += blockDim.x) sy += lab[(long)s * KL];
-  sy = blk_sum(sy, sh);
+  // [TF1] tf.nn.softmax_cross_entropy_with_logits registers backprop = softmax - labels as the gradient (xent_op), NOT the
+  // derivative of -sum(y * log_softmax) for unnormalised y (which would be softmax * sum(y) - y).  The two differ only for label
+  // maps that do not sum to 1: the border-clipped blobs of data.py:180-186.
   const float l = lse[blockIdx.x];
   for (int s = threadIdx.x; s < S; s += blockDim.x)
-    dst[(long)s * K] = scale * (expf(src[(long)s * K] - l) * sy - lab[(long)s * KL]);
+    dst[(long)s * K] = scale * (expf(src[(long)s * K] - l) - lab[(long)s * KL]);
 }
 
 // y [B,S,K] softmax output, dy [B,S,KD] (first K channels), dx [B,S,K] (+= if accumulate)

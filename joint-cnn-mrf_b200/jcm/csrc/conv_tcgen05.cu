@@ -20,6 +20,19 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+// Measurement switches (environment variables that change tiling / skip work, and the never-adopted CTA-pair kernel) exist only in
+// builds with -DJCM_EXPERIMENTS (`python joint-cnn-mrf_b200/build.py --experiments` -> libjcm_exp.so, used by tests/gpu_diag.py).
+// The product library compiles them out: it reads no environment variable and carries no skip-the-work path.
+#ifdef JCM_EXPERIMENTS
+#define JCM_ENV_INT(name, dflt) (getenv(name) ? atoi(getenv(name)) : (dflt))
+#define JCM_DBG(p) ((p).dbg)
+#define JCM_SPLITN(p) ((p).mma_split_n)
+#else
+#define JCM_ENV_INT(name, dflt) (dflt)
+#define JCM_DBG(p) 0
+#define JCM_SPLITN(p) 0
+#endif
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -251,7 +264,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             for (int dy0 = 0; dy0 < p.ksize; dy0 += p.b_group) {
               const int gn = min(p.b_group, p.ksize - dy0);
               mbar_wait(bar_empty + 8 * sb, pb ^ 1);
-              if (p.dbg & 4) {
+              if (JCM_DBG(p) & 4) {
                 mbar_arrive(bar_full + 8 * sb);
               } else {
                 mbar_expect_tx(bar_full + 8 * sb, gn * p.b_bytes);
@@ -295,7 +308,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
               tc_fence_after();
               const uint64_t adesc = desc_hi | (uint64_t)(((a_addr + dy * dy_bytes) >> 4) & 0x3FFF);
               const uint64_t bdesc = desc_hi | (uint64_t)(((smem_b0 + sb * p.b_stride) >> 4) & 0x3FFF);
-              if (!(p.dbg & 2))
+              if (!(JCM_DBG(p) & 2))
               for (int k = 0; k < kk; ++k) {
                 const int j = (mcount++) & (p.nacc - 1);
                 tc_mma_bf16(d_tmem + j * p.block_n, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (accumulate >> j) & 1u);
@@ -312,7 +325,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             for (int i = 0; i < gn; ++i) {
               const uint64_t adesc = desc_hi | (uint64_t)(((a_addr + (dy0 + i) * dy_bytes) >> 4) & 0x3FFF);
               const uint64_t bdesc = desc_hi | (uint64_t)(((smem_b0 + sb * p.b_stride + i * p.b_slot) >> 4) & 0x3FFF);
-              if (!(p.dbg & 2))
+              if (!(JCM_DBG(p) & 2))
               for (int k = 0; k < kk; ++k) {
                 const int j = (mcount++) & (p.nacc - 1);
                 tc_mma_bf16(d_tmem + j * p.block_n, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (accumulate >> j) & 1u);
@@ -367,9 +380,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
               const uint32_t sa = smem_base + stage * p.stage_bytes;
               const uint32_t sb = sa + p.a_bytes;
               const uint32_t fb = bar_full + 8 * stage;
-              mbar_expect_tx(fb, (p.dbg & 4) ? p.a_bytes : p.a_bytes + p.b_bytes);
+              mbar_expect_tx(fb, (JCM_DBG(p) & 4) ? p.a_bytes : p.a_bytes + p.b_bytes);
               tma_load_4d(sa, term == 1 ? &map_a_lo : &map_a_hi, fb, cb * p.kc, x0 + dx, y0 + dy, img);
-              if (!(p.dbg & 4)) tma_load_3d(sb, term == 2 ? &map_b_lo : &map_b_hi, fb, cb * p.kc, nt * p.block_n, tap);
+              if (!(JCM_DBG(p) & 4)) tma_load_3d(sb, term == 2 ? &map_b_lo : &map_b_hi, fb, cb * p.kc, nt * p.block_n, tap);
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -409,8 +422,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
           const uint32_t sa = smem_base + stage * p.stage_bytes;
           const uint64_t adesc = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);                 // only the start address changes per stage
           const uint64_t bdesc = desc_hi | (uint64_t)(((sa + p.a_bytes) >> 4) & 0x3FFF);
-          if (p.dbg & 2) {
-          } else if (p.mma_split_n) {
+          if (JCM_DBG(p) & 2) {
+          } else if (JCM_SPLITN(p)) {
             // experiment: two independent half-N MMAs per K step (different TMEM columns, B rows n/2.. of the same stage)
             const uint32_t hn = p.block_n / 2;
             const uint32_t idesc_h = (idesc & ~(0x3Fu << 17)) | ((hn >> 3) << 17);
@@ -453,7 +466,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
-      if (p.dbg & 1) {
+      if (JCM_DBG(p) & 1) {
         // timing experiment: no stores
       } else if (p.tma_store && p.y_bf16) {
         // bf16 output: 64-column chunks (128-byte rows of bf16) through the same swizzled staging buffers, box {64 ch, TW, TH, 1}
@@ -597,6 +610,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
   }
 }
 
+#ifdef JCM_EXPERIMENTS
 // =====================================================================================================================
 // EXPERIMENTAL (off unless JCM_CONV_CTA2=1; written at the end of round 1 without GPU time left to run it - round 2 starts by
 // testing it): the plain-mode kernel for N = 256 layers as a CTA PAIR (`cta_group::2`).  Two CTAs of a cluster own two adjacent
@@ -865,6 +879,8 @@ conv_igemm_cta2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
   }
 }
 
+#endif  // JCM_EXPERIMENTS
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                          const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -915,7 +931,7 @@ static void pick_patch(int H, int W, int* TW, int* TH) {
   }
   *TW = bw;
   *TH = bh;
-  static const int force = getenv("JCM_CONV_PATCH_TW") ? atoi(getenv("JCM_CONV_PATCH_TW")) : 0;   // measurement switch
+  static const int force = JCM_ENV_INT("JCM_CONV_PATCH_TW", 0);   // measurement switch
   if (force > 0 && 128 % force == 0) { *TW = force; *TH = 128 / force; }
 }
 
@@ -980,10 +996,10 @@ int jcm_conv_igemm_ex(const ConvExArgs& a) {
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   // halo mode where the A operand's L2 traffic is the limiter (few output channels per A tile) and the taps have vertical extent
   p.halo = 0;
-  static const int splitn_env = getenv("JCM_MMA_SPLITN") ? atoi(getenv("JCM_MMA_SPLITN")) : 0;
+  static const int splitn_env = JCM_ENV_INT("JCM_MMA_SPLITN", 0);
   p.mma_split_n = splitn_env && (p.block_n % 32) == 0;
   {
-    static const int nacc_env = getenv("JCM_CONV_NACC") ? atoi(getenv("JCM_CONV_NACC")) : 0;   // 2 enables (measurement)
+    static const int nacc_env = JCM_ENV_INT("JCM_CONV_NACC", 0);   // 2 enables (measurement)
     const int mmas_per_tile = ksize * kw * p.cblocks * p.terms * (p.kc / 16);
     // measured (profiles/r01/conv_sweep_r01.txt): once the MMA warp issues through elect.sync the round-robin accumulators no longer
     // help (the serialisation seen before was the issuing thread, not the tensor pipe), so they stay off unless JCM_CONV_NACC=2
@@ -994,13 +1010,13 @@ int jcm_conv_igemm_ex(const ConvExArgs& a) {
     }
     if (p.mma_split_n) p.nacc = 1;
   }
-  static const int dbg_env = getenv("JCM_CONV_DBG") ? atoi(getenv("JCM_CONV_DBG")) : 0;
+  static const int dbg_env = JCM_ENV_INT("JCM_CONV_DBG", 0);
   p.dbg = dbg_env;
   p.a_stages = 0; p.b_stages = 0; p.a_stride = 0; p.b_stride = 0; p.a_halo_bytes = 0;
-  static const int halo_env = getenv("JCM_CONV_HALO") ? atoi(getenv("JCM_CONV_HALO")) : 1;   // 0 disables (for A/B measurements)
+  static const int halo_env = JCM_ENV_INT("JCM_CONV_HALO", 1);   // 0 disables (for A/B measurements)
   if (halo_env && p.grp == 0 && p.terms == 1 && ksize >= 3 && p.block_n <= (halo_env > 1 ? 256 : 128) && (p.TW % 8) == 0) {
     p.a_halo_bytes = (p.TH + ksize - 1) * p.TW * p.kc * 2;
-    static const int group_env = getenv("JCM_CONV_BGROUP") ? atoi(getenv("JCM_CONV_BGROUP")) : 0;   // measurement: force taps per stage
+    static const int group_env = JCM_ENV_INT("JCM_CONV_BGROUP", 0);   // measurement: force taps per stage
     p.a_stride = ((p.a_halo_bytes + 1023) / 1024) * 1024;
     p.b_slot = ((p.b_bytes + 1023) / 1024) * 1024;
     p.a_stages = p.a_stride > 40 * 1024 ? 2 : 3;
@@ -1016,7 +1032,7 @@ int jcm_conv_igemm_ex(const ConvExArgs& a) {
     p.halo = p.b_stages >= 3;
   }
   // experimental CTA-pair form of the plain mode for N = 256 layers (conv_igemm_cta2_kernel): off unless JCM_CONV_CTA2=1
-  static const int cta2_env = getenv("JCM_CONV_CTA2") ? atoi(getenv("JCM_CONV_CTA2")) : 0;
+  static const int cta2_env = JCM_ENV_INT("JCM_CONV_CTA2", 0);
   const bool cta2 = cta2_env && !p.halo && p.grp == 0 && p.block_n == 256 && p.tma_store && p.nacc == 1 && !p.mma_split_n && !p.dbg &&
                     jcm_num_sms() >= 2;
   if (cta2) {
@@ -1070,29 +1086,33 @@ int jcm_conv_igemm_ex(const ConvExArgs& a) {
     if (rc) return rc;
   }
 
+#ifdef JCM_EXPERIMENTS
   if (cta2) {
     const int m_tiles = B * p.tiles_x * p.tiles_y;
     const int pairs = ((m_tiles + 1) / 2) * p.n_tiles;
     int grid2 = jcm_num_sms() & ~1;
     if (grid2 > 2 * pairs) grid2 = 2 * pairs;
     const size_t smem2 = (size_t)p.stages * p.stage_bytes + epi_bytes + 1024;
-    static bool attr2_set = false;
-    if (!attr2_set) {
-      JCM_CUDA(cudaFuncSetAttribute(conv_igemm_cta2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512));
-      attr2_set = true;
-    }
+    JCM_CUDA(cudaFuncSetAttribute(conv_igemm_cta2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512));
     conv_igemm_cta2_kernel<<<grid2, kThreads, smem2, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, my, p);
     JCM_LAUNCH_CHECK();
     return JCM_OK;
   }
+#endif
   const int total_tiles = B * p.tiles_x * p.tiles_y * p.n_tiles;
   int grid = jcm_num_sms();
   if (grid > total_tiles) grid = total_tiles;
   const size_t smem = (p.halo ? (size_t)p.a_stages * p.a_stride + (size_t)p.b_stages * p.b_stride : (size_t)p.stages * p.stage_bytes) + epi_bytes + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    JCM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512));
-    attr_set = true;
+  {
+    // function attributes are per device: one flag per device ordinal (one process per GPU is the design, but a process that
+    // touches a second device must not launch there with the default 48 KB limit)
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    JCM_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      JCM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
   }
   conv_igemm_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, my, p);
   JCM_LAUNCH_CHECK();

@@ -19,13 +19,15 @@ void jcm_count_launch() { __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); 
 extern "C" long jcm_launch_count() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int jcm_num_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-      sms = 148;
+  static int sms[64] = {0};     // per device ordinal
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!sms[dev]) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    sms[dev] = v;
   }
-  return sms;
+  return sms[dev];
 }
 
 extern "C" const char* jcm_last_error() { return g_err; }

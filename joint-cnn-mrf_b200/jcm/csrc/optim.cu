@@ -65,6 +65,67 @@ __global__ void clip_adam_kernel(float* __restrict__ w, const float* __restrict_
   }
 }
 
+// partial[blk] = sum of x^2 over the block's grid-stride share (double accumulation per thread, fixed order: deterministic)
+__global__ void sumsq_kernel(const float* __restrict__ x, long n, float* __restrict__ partial) {
+  __shared__ float sh[kT / 32];
+  double s = 0.0;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) s += (double)x[i] * (double)x[i];
+  const float a = warp_sum((float)s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < kT / 32; ++i) t += sh[i];
+    partial[blockIdx.x] = t;
+  }
+}
+__global__ void sumsq_finish_kernel(const float* __restrict__ partial, int nblocks, float mul, int accumulate, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double a = 0.0;
+    for (int i = 0; i < nblocks; ++i) a += (double)partial[i];
+    out[0] = (float)(a * (double)mul) + (accumulate ? out[0] : 0.f);
+  }
+}
+// out = g * clip / max(sqrt(sumsq[0]), clip)      (tf.clip_by_global_norm, main.py:302-309)
+__global__ void clip_scale_kernel(const float* __restrict__ g, long n, const float* __restrict__ sumsq, float clip, float* __restrict__ out) {
+  const float scale = clip / fmaxf(sqrtf(sumsq[0]), clip);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) out[i] = g[i] * scale;
+}
+constexpr int kMaxTowers = 16;
+struct TowerPtrs { const float* t[kMaxTowers]; };
+// out = mean over towers, summed in tower order (expand_dims / concat / reduce_mean of main.py:253-259)
+__global__ void tower_mean_kernel(TowerPtrs tp, int n_towers, long n, float* __restrict__ out) {
+  const float inv = 1.0f / (float)n_towers;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float s = tp.t[0][i];
+    for (int k = 1; k < n_towers; ++k) s += tp.t[k][i];
+    out[i] = s * inv;
+  }
+}
+// y[b, i, j, :] = x[b, 2i + oy, 2j + ox, :]
+__global__ void subsample2_kernel(const float* __restrict__ x, int B, int H, int W, int C, int oy, int ox, int Ho, int Wo,
+                                  float* __restrict__ y) {
+  const long total = (long)B * Ho * Wo * C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long t = i / C;
+    const int j = (int)(t % Wo);
+    t /= Wo;
+    const int r = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    y[i] = x[(((long)b * H + 2 * r + oy) * W + 2 * j + ox) * C + c];
+  }
+}
+
+// out[r, c] = [relu](x[r, c] + bias[c])
+__global__ void bias_relu_kernel(const float* __restrict__ x, const float* __restrict__ bias, long M, int C, int relu, float* __restrict__ out) {
+  const long total = M * C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const float v = x[i] + bias[(int)(i % C)];
+    out[i] = relu ? fmaxf(v, 0.f) : v;
+  }
+}
+
 inline int blocks_for(long n) {
   long b = (n + kT * 4 - 1) / (kT * 4);
   long cap = (long)jcm_num_sms() * 8;
@@ -91,6 +152,63 @@ extern "C" int jcm_clip_adam(float* w, const float* g, float* m, float* v, long 
                              float b1, float b2, float eps, int momentum, void* stream) {
   JCM_CHECK_ARG(w && g && m && (v || momentum) && stats && n > 0, "jcm_clip_adam: bad arguments");
   clip_adam_kernel<<<blocks_for(n), kT, 0, (cudaStream_t)stream>>>(w, g, m, v, n, stats, clip, lr_t, b1, b2, eps, momentum);
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}
+
+// out[0] (+)= mul * sum x^2.  weight_decay(var_pattern) of main.py:195-205 is the sum of tf.nn.l2_loss = sum(w^2)/2 over the matching
+// variables: mul = 0.5, accumulate != 0 from the second variable on; the squared global norm of main.py:302-309: mul = 1.
+// partial: jcm_optim_blocks(n) floats.
+extern "C" int jcm_sumsq(const float* x, long n, float mul, int accumulate, float* partial, float* out, void* stream) {
+  JCM_CHECK_ARG(x && partial && out && n > 0, "jcm_sumsq: bad arguments");
+  const int nb = blocks_for(n);
+  sumsq_kernel<<<nb, kT, 0, (cudaStream_t)stream>>>(x, n, partial);
+  JCM_LAUNCH_CHECK();
+  sumsq_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(partial, nb, mul, accumulate, out);
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}
+
+// out = g * clip / max(sqrt(sumsq[0]), clip): grad_renorm / tf.clip_by_global_norm (main.py:302-309) for one tensor of the list,
+// sumsq[0] = squared global norm over the WHOLE list (accumulated with jcm_sumsq).  out may alias g.
+extern "C" int jcm_clip_scale(const float* g, long n, const float* sumsq, float clip, float* out, void* stream) {
+  JCM_CHECK_ARG(g && sumsq && out && n > 0 && clip > 0.f, "jcm_clip_scale: bad arguments");
+  clip_scale_kernel<<<blocks_for(n), kT, 0, (cudaStream_t)stream>>>(g, n, sumsq, clip, out);
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}
+
+// out = mean of n_towers same-sized gradient tensors that live on THIS device (average_gradients of main.py:243-267 for towers of
+// one process; across processes the mean is the NCCL all-reduce in jcm.train.Trainer).  towers: HOST array of device pointers.
+extern "C" int jcm_tower_mean(const float* const* towers, int n_towers, long n, float* out, void* stream) {
+  JCM_CHECK_ARG(towers && out && n > 0 && n_towers >= 1 && n_towers <= kMaxTowers, "jcm_tower_mean: 1..%d towers supported, got %d",
+                kMaxTowers, n_towers);
+  TowerPtrs tp;
+  for (int k = 0; k < kMaxTowers; ++k) tp.t[k] = k < n_towers ? towers[k] : nullptr;
+  for (int k = 0; k < n_towers; ++k) JCM_CHECK_ARG(tp.t[k] != nullptr, "jcm_tower_mean: null tower pointer");
+  tower_mean_kernel<<<blocks_for(n), kT, 0, (cudaStream_t)stream>>>(tp, n_towers, n, out);
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}
+
+// y [B, (H - oy + 1) / 2, (W - ox + 1) / 2, C] = x[:, oy::2, ox::2, :].  A stride-2 SAME convolution (tf.nn.conv2d strides [1,2,2,1],
+// main.py:133-135) equals the stride-1 SAME convolution sampled at rows/columns 2i + o with o = 1 for an even input extent (TF pads
+// (k-3)/2 before) and o = 0 for an odd one; the part detector's own stride-2 layers (conv1_*) do not use this - they run on the
+// space-to-depth planes of jcm_prep_input - it serves the stand-alone conv2d(x, W, 2) of the function surface.
+extern "C" int jcm_subsample2(const float* x, int B, int H, int W, int C, int oy, int ox, float* y, void* stream) {
+  JCM_CHECK_ARG(x && y && B > 0 && H > 0 && W > 0 && C > 0 && (oy == 0 || oy == 1) && (ox == 0 || ox == 1) && oy < H && ox < W,
+                "jcm_subsample2: bad arguments");
+  const int Ho = (H - oy + 1) / 2, Wo = (W - ox + 1) / 2;
+  subsample2_kernel<<<blocks_for((long)B * Ho * Wo * C), kT, 0, (cudaStream_t)stream>>>(x, B, H, W, C, oy, ox, Ho, Wo, y);
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
+}
+
+// out = [relu](x + bias) per channel of x [M, C]: the `conv2d(x, w, stride) + b` / tf.nn.relu of conv_layer (main.py:160-162) for the
+// stand-alone function surface (inside model() bias and ReLU are the convolution kernel's epilogue).  out may alias x.
+extern "C" int jcm_bias_relu(const float* x, const float* bias, long M, int C, int relu, float* out, void* stream) {
+  JCM_CHECK_ARG(x && bias && out && M > 0 && C > 0, "jcm_bias_relu: bad arguments");
+  bias_relu_kernel<<<blocks_for(M * C), kT, 0, (cudaStream_t)stream>>>(x, bias, M, C, relu, out);
   JCM_LAUNCH_CHECK();
   return JCM_OK;
 }

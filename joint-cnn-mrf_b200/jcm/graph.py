@@ -7,6 +7,7 @@ dictionaries that use the TensorFlow variable names ('conv1_fullres/weights', '.
 'energy_<a>_<b>', 'bias_<a>_<b>').  Eager execution on torch CUDA tensors; all arithmetic is in libjcm.so.
 """
 import math
+import weakref
 
 import numpy as np
 import torch
@@ -14,6 +15,26 @@ import torch
 from . import ops
 
 JOINT_NAMES = ['lsho', 'lelb', 'lwri', 'rsho', 'relb', 'rwri', 'lhip', 'rhip', 'nose', 'torso']  # main.py:18
+
+# Packed bf16 operand planes of the conv kernels, shared by every Context (training and evaluation contexts see the same
+# variables, as the reference's towers and its inference run share one set of tf.Variables, main.py:555).  An entry is valid
+# while the parameter tensor is alive, was not modified through torch (`_version`) and no raw-pointer update happened since
+# it was packed (`_PARAM_EPOCH`: Trainer.apply / load_checkpoint update the flat parameter buffer through the C ABI, which
+# torch's version counter cannot see, and call params_updated()).
+_PACKS = {}
+_PARAM_EPOCH = 0
+
+
+def params_updated():
+    """Call after parameters were written through raw pointers (jcm_clip_adam, a checkpoint load): every cached packed
+    operand plane is stale from now on, in every Context."""
+    global _PARAM_EPOCH
+    _PARAM_EPOCH += 1
+
+
+def _purge_packs():
+    for k in [k for k, e in _PACKS.items() if e[0]() is None]:
+        del _PACKS[k]
 
 
 class Context:
@@ -35,7 +56,6 @@ class Context:
         self.use_sm = use_sm
         self.bf16_activations = (precision == 'bf16') if bf16_activations is None else bool(bf16_activations)
         self.sm_tensor_core = (precision == 'bf16') if sm_tensor_core is None else bool(sm_tensor_core)
-        self._wcache = {}
 
     @property
     def split(self):
@@ -56,18 +76,20 @@ class Context:
         return self.sm_tensor_core and self.precision == 'bf16'
 
     def packed(self, name, w, kind='fwd'):
-        """Packed bf16 operand planes of a conv kernel, cached until the parameter tensor is modified in place."""
-        key = (name, kind, self.split)
-        ent = self._wcache.get(key)
-        if ent is not None and ent[0] == w.data_ptr() and ent[1] == w._version:
-            return ent[2]
+        """Packed bf16 operand planes of a conv kernel: resident, re-packed only after the variable changed (see _PACKS)."""
+        key = (w.data_ptr(), tuple(w.shape), kind, self.split)
+        ent = _PACKS.get(key)
+        if ent is not None and ent[0]() is w and ent[1] == w._version and ent[2] == _PARAM_EPOCH:
+            return ent[3]
         if kind == 's2d':
             p = ops.pack_weights_s2d(w, self.split)
         elif kind in ('taps', 'taps_dgrad'):
             p = ops.pack_weights_taps(w, self.split, transpose=(kind == 'taps_dgrad'))
         else:
             p = ops.pack_weights(w, self.split, transpose=(kind == 'dgrad'))
-        self._wcache[key] = (w.data_ptr(), w._version, p)
+        if len(_PACKS) > 256:
+            _purge_packs()
+        _PACKS[key] = (weakref.ref(w), w._version, _PARAM_EPOCH, p)
         return p
 
 
@@ -79,9 +101,9 @@ def n_filters(debug=False):
     return [v // 4 for v in f] if debug else f         # main.py:40-41
 
 
-def weight_variable(shape, gen=None, device='cuda'):
-    """main.py:138-147: He init, truncated normal (re-drawn outside +-2 sigma)."""
-    n_in = shape[0] * shape[1] * shape[2]
+def weight_variable(shape, fc=False, gen=None, device='cuda'):
+    """main.py:138-147: He init, truncated normal (re-drawn outside +-2 sigma).  fc=True: shape = [n_in, n_out] (main.py:143-145)."""
+    n_in = shape[0] if fc else shape[0] * shape[1] * shape[2]
     w = torch.empty(shape, dtype=torch.float32)
     torch.nn.init.trunc_normal_(w, mean=0.0, std=1.0, a=-2.0, b=2.0, generator=gen)
     return (w * math.sqrt(2.0 / n_in)).to(device)
@@ -105,7 +127,7 @@ def init_part_detector(n_joints, gen=None, debug=False, device='cuda'):
     """All variables of `model` under the TF names."""
     p = {}
     for name, k, cin, cout in conv_specs(n_joints, debug):
-        p[name + '/weights'] = weight_variable([k, k, cin, cout], gen, device)
+        p[name + '/weights'] = weight_variable([k, k, cin, cout], gen=gen, device=device)
         p[name + '/biases'] = bias_variable([cout], device=device)
         if name != 'conv6':
             p[name + '/BatchNorm/gamma'] = torch.ones(cout, dtype=torch.float32, device=device)
@@ -197,15 +219,41 @@ def _bn_vars(p, name):
 
 
 def conv2d(x, W, stride, ctx):
-    """main.py:133-135 on fp32 NHWC tensors (stride 1 only here; the stride-2 conv1 layers go through `model`)."""
-    if stride != 1:
-        raise ValueError('stand-alone conv2d supports stride 1; stride-2 conv1_* is fused with the input transform in model()')
-    cin = x.shape[3]
-    if cin % 16:
-        raise ValueError('conv2d needs a multiple of 16 input channels')
-    xp = ops.split_planes(x, ctx.split)
+    """main.py:133-135: tf.nn.conv2d(x NHWC fp32, W HWIO, strides [1,stride,stride,1], padding 'SAME') -> fp32 NHWC.
+    stride 1 or 2, any channel counts (input channels are zero-padded to a multiple of 16 for the tensor-core operand).
+    Stride 2 is the stride-1 SAME convolution sampled at every second position - offset 1 where the input extent is even,
+    0 where it is odd: TF's SAME rule pads (k-3)/2 resp. (k-1)/2 before [TF1].  The part detector's own stride-2 layers
+    (conv1_*) take the space-to-depth path inside model() and do 1/4 of this work; this is the general stand-alone form."""
+    if stride not in (1, 2):
+        raise ValueError('conv2d supports strides 1 and 2 (the reference uses no other, main.py:44-72)')
+    ops._req(x, torch.float32, 'x')
+    ops._req(W, torch.float32, 'W')
+    kh, kw, cin, cout = W.shape
+    if x.shape[3] != cin:
+        raise ValueError('x has %d channels, W expects %d' % (x.shape[3], cin))
+    if kh != kw or kh % 2 == 0:
+        raise ValueError('square odd kernels only')
+    cpad = ops.pad16(cin)
+    xp = ops.split_planes(x, ctx.split) if cpad == cin else ops.pad_planes(x, cpad, ctx.split)
     wp = ops.pack_weights(W, ctx.split)
-    return ops.conv2d_planes(xp, wp, None, W.shape[3], W.shape[0], relu=False)
+    y = ops.conv2d_planes(xp, wp, None, cout, kh, relu=False, alg_kdim=kh * kw * cin)
+    if stride == 2:
+        y = ops.subsample2(y, 1 - x.shape[1] % 2, 1 - x.shape[2] % 2)
+    return y
+
+
+def conv_layer(x, size, stride, n_in, n_out, name, p, ctx, last_layer=False):
+    """main.py:156-169: relu(conv2d(x, w, stride) + b) followed by batch_norm (BN AFTER the ReLU); last_layer: conv + bias only.
+    x fp32 NHWC [B,H,W,n_in]; the variables are p[name + '/weights' | '/biases' | '/BatchNorm/*'] (the reference creates them
+    inside the variable scope `name`).  Returns the fp32 NHWC activation.  The TensorBoard side effects (main.py:167-168) are
+    not reproduced."""
+    w, b = p[name + '/weights'], p[name + '/biases']
+    if tuple(w.shape) != (size, size, n_in, n_out):
+        raise ValueError('%s/weights has shape %s, expected %s' % (name, tuple(w.shape), (size, size, n_in, n_out)))
+    pre = ops.add_bias_relu(conv2d(x, w, stride, ctx), b, relu=not last_layer)
+    if last_layer:
+        return pre
+    return batch_norm(pre, _bn_vars(p, name), ctx)
 
 
 def batch_norm(x, bn_vars, ctx):
@@ -293,6 +341,32 @@ def spatial_softmax(hm):
 def softmax_cross_entropy(hm1, hm2):
     """main.py:220-240: logits hm1 [B,H,W,K], labels hm2 [B,H,W,>=K] -> scalar (0-d tensor)."""
     return ops.softmax_ce(hm1, hm2)[0][0]
+
+
+def weight_decay(var_pattern, variables):
+    """main.py:195-205: sum of tf.nn.l2_loss(v) = sum(v^2)/2 over the variables whose name contains var_pattern.
+    variables: dict name -> fp32 CUDA tensor (the reference walks tf.global_variables()).  Returns a 0-d CUDA tensor."""
+    sel = [v for k, v in variables.items() if var_pattern in k]
+    if not sel:
+        raise ValueError('no variable name contains %r' % (var_pattern,))    # tf.add_n([]) raises as well
+    return ops.l2_loss_sum(sel)
+
+
+def average_gradients(tower_grads):
+    """main.py:243-267: tower_grads = [[(grad, var), ...] per tower] (towers of THIS process, tensors on one device) ->
+    [(mean grad, var of the first tower), ...].  Across processes (one per GPU) the same mean is the NCCL all-reduce of
+    jcm.train.Trainer.reduce_gradients."""
+    out = []
+    for grad_and_vars in zip(*tower_grads):
+        out.append((ops.tower_mean([g for g, _ in grad_and_vars]), grad_and_vars[0][1]))
+    return out
+
+
+def grad_renorm(gs_vs, norm):
+    """main.py:302-309: tf.clip_by_global_norm over the gradients of the (grad, var) list -> list of (clipped grad, var)."""
+    gs_vs = list(gs_vs)
+    clipped = ops.clip_by_global_norm([g for g, _ in gs_vs], norm)
+    return [(c, v) for c, (_, v) in zip(clipped, gs_vs)]
 
 
 def get_joints_coords(hm):

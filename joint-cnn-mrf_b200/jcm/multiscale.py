@@ -63,45 +63,39 @@ def resize(image, output_shape, cval=0.0, clip=True):
     return out
 
 
+def _zoom_about_centre(img, coef, h, w):
+    """One geometry primitive for both directions of the multi-scale transform: the image content is scaled by 1/coef about the
+    image centre and the result brought back to [h, w] with `resize`.
+      coef > 1  - zero margins of round(extent * (coef - 1) / 2) pixels are added on every side (the content shrinks),
+      coef <= 1 - the centred window [round((1 - coef) / 2 * extent), ... + round(coef * extent)) is kept (the content grows).
+    The rounding (Python's round, half to even) and the use of the ORIGINAL extents h, w - not the array's own - are the
+    reference's (main.py:331-347,356-378): they decide which pixel rows survive, so they must match."""
+    if coef > 1:
+        mh, mw = round(h * (coef - 1) / 2), round(w * (coef - 1) / 2)
+        margins = ((mh, mh), (mw, mw)) + ((0, 0),) * (np.ndim(img) - 2)
+        piece = np.pad(img, margins, 'constant', constant_values=0)
+    else:
+        top, left = round((1 - coef) / 2 * h), round((1 - coef) / 2 * w)
+        piece = img[top:top + round(coef * h), left:left + round(coef * w)]
+    return resize(piece, (h, w))
+
+
 def get_different_scales(x, pad_array=PAD_ARRAY, crop_array=CROP_ARRAY, orig_h=None, orig_w=None):
-    """main.py:326-349: x [h, w, c] -> float64 [len(pad)+len(crop), h, w, c]."""
-    orig_h = x.shape[0] if orig_h is None else orig_h
-    orig_w = x.shape[1] if orig_w is None else orig_w
-    x_new = []
-    for pad_c in pad_array:
-        n_pad_h = round(orig_h * (pad_c - 1) / 2)
-        n_pad_w = round(orig_w * (pad_c - 1) / 2)
-        x_pad = np.pad(x, ((n_pad_h, n_pad_h), (n_pad_w, n_pad_w), (0, 0)), 'constant', constant_values=0)
-        x_new.append(resize(x_pad, (orig_h, orig_w)))
-    for crop_c in crop_array:
-        h1 = round((1 - crop_c) / 2 * orig_h)
-        h2 = h1 + round(crop_c * orig_h)
-        w1 = round((1 - crop_c) / 2 * orig_w)
-        w2 = w1 + round(crop_c * orig_w)
-        x_new.append(resize(x[h1:h2, w1:w2], (orig_h, orig_w)))
-    return np.array(x_new)
+    """main.py:326-349: x [h, w, c] -> float64 [len(pad) + len(crop), h, w, c]: the padded (zoomed-out) copies first, then the
+    centre crops (zoomed in)."""
+    h = x.shape[0] if orig_h is None else orig_h
+    w = x.shape[1] if orig_w is None else orig_w
+    return np.array([_zoom_about_centre(x, c, h, w) for c in tuple(pad_array) + tuple(crop_array)])
 
 
 def scale_hm_back(hms, pad_array=PAD_ARRAY, crop_array=CROP_ARRAY, orig_h=None, orig_w=None):
-    """main.py:352-381: the inverse geometry on the heat maps - maps of a padded input are centre-cropped by 1/pad, maps of a
-    cropped input are zero-padded by 1/crop, each resized back to [orig_h, orig_w]."""
-    orig_h = hms[0].shape[0] if orig_h is None else orig_h
-    orig_w = hms[0].shape[1] if orig_w is None else orig_w
-    hms_new = []
-    for i, crop_c in enumerate(pad_array):
-        crop_c = 1 / crop_c
-        h1 = round((1 - crop_c) / 2 * orig_h)
-        h2 = h1 + round(crop_c * orig_h)
-        w1 = round((1 - crop_c) / 2 * orig_w)
-        w2 = w1 + round(crop_c * orig_w)
-        hms_new.append(resize(hms[i][h1:h2, w1:w2], (orig_h, orig_w)))
-    for i, pad_c in enumerate(crop_array):
-        pad_c = 1 / pad_c
-        n_pad_h = round(orig_h * (pad_c - 1) / 2)
-        n_pad_w = round(orig_w * (pad_c - 1) / 2)
-        hm_pad = np.pad(hms[i + len(pad_array)], ((n_pad_h, n_pad_h), (n_pad_w, n_pad_w), (0, 0)), 'constant', constant_values=0)
-        hms_new.append(resize(hm_pad, (orig_h, orig_w)))
-    return np.array(hms_new)
+    """main.py:352-381: the inverse geometry on the heat maps, scale by scale: a map computed from an input zoomed by coefficient c
+    is zoomed by 1/c (maps of padded inputs are centre-cropped, maps of cropped inputs are zero-padded), back to [orig_h, orig_w]."""
+    h = hms[0].shape[0] if orig_h is None else orig_h
+    w = hms[0].shape[1] if orig_w is None else orig_w
+    coefs = tuple(pad_array) + tuple(crop_array)
+    # 1 / 1.0 == 1.0 takes the crop branch with the full window, which is what the reference's pad branch with zero margins does
+    return np.array([_zoom_about_centre(hms[i], 1 / c, h, w) for i, c in enumerate(coefs)])
 
 
 def argmax_hm(hm):

@@ -50,15 +50,15 @@ class _ConvProfile:
     def clear(self):
         self.records = []
 
-    def add(self, kernel, flops, e0, e1):
-        self.records.append((kernel, flops, e0, e1))
+    def add(self, kernel, flops, e0, e1, tag=None):
+        self.records.append((kernel, flops, e0, e1, tag))
 
     def summary(self, steps=None, kernel=None):
         """Aggregate over the recorded launches of `kernel` (all if None): algorithmic FLOPs / summed CUDA-event time."""
         torch.cuda.synchronize()
         recs = [r for r in self.records if kernel is None or r[0] == kernel]
-        ms = sum(e0.elapsed_time(e1) for _, _, e0, e1 in recs)
-        fl = sum(f for _, f, _, _ in recs)
+        ms = sum(r[2].elapsed_time(r[3]) for r in recs)
+        fl = sum(r[1] for r in recs)
         n = len(recs)
         steps = steps or 1
         return {'launches': n, 'launches_per_step': n // steps if steps else n, 'ms_total': ms, 'ms_per_step': ms / steps,
@@ -72,8 +72,25 @@ class _ConvProfile:
             return None
         fmax = max(r[1] for r in recs)
         big = [r for r in recs if r[1] == fmax]
-        ms = sum(e0.elapsed_time(e1) for _, _, e0, e1 in big) / len(big)
+        ms = sum(r[2].elapsed_time(r[3]) for r in big) / len(big)
         return {'flops': fmax, 'ms': ms, 'launches': len(big), 'tflops': fmax / (ms * 1e-3) / 1e12}
+
+    def by_shape(self, kernel, steps=1):
+        """Per launch shape (the tag given at the call site): launches per step, mean ms per launch, algorithmic TFLOP/s."""
+        torch.cuda.synchronize()
+        groups = {}
+        for r in self.records:
+            if r[0] != kernel:
+                continue
+            g = groups.setdefault(r[4] or 'untagged', [0, 0.0, 0.0])
+            g[0] += 1
+            g[1] += r[2].elapsed_time(r[3])
+            g[2] += r[1]
+        out = []
+        for tag, (n, ms, fl) in groups.items():
+            out.append({'shape': tag, 'launches_per_step': n / max(steps, 1), 'ms_per_launch': ms / n, 'ms_per_step': ms / max(steps, 1),
+                        'tflops': fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0})
+        return sorted(out, key=lambda d: -d['ms_per_step'])
 
 
 PROFILE = _ConvProfile()
@@ -152,6 +169,79 @@ def split_planes(x, split):
     return out
 
 
+def pad_planes(x, cpad, split):
+    """fp32 [..., C] -> operand planes [..., cpad] with zero-filled extra channels."""
+    _req(x, F32, 'x')
+    C = x.shape[-1]
+    M = x.numel() // C
+    out = _new_planes(tuple(x.shape[:-1]) + (cpad,), x.device, split)
+    check(lib().jcm_pad_planes(_ptr(x), M, C, cpad, _ptr(out.hi), _ptr(out.lo), _stream()), 'jcm_pad_planes')
+    return out
+
+
+def subsample2(x, oy, ox):
+    """x[:, oy::2, ox::2, :] (stride-2 SAME convolution = sampled stride-1 convolution, see graph.conv2d)."""
+    _req(x, F32, 'x')
+    B, H, W, C = x.shape
+    y = torch.empty((B, (H - oy + 1) // 2, (W - ox + 1) // 2, C), dtype=F32, device=x.device)
+    check(lib().jcm_subsample2(_ptr(x), B, H, W, C, oy, ox, _ptr(y), _stream()), 'jcm_subsample2')
+    return y
+
+
+def add_bias_relu(x, bias, relu):
+    """[relu](x + b) per channel (main.py:160-162) on an fp32 [..., C] tensor."""
+    _req(x, F32, 'x')
+    _req(bias, F32, 'bias')
+    C = x.shape[-1]
+    if bias.numel() != C:
+        raise ValueError('bias has %d elements for %d channels' % (bias.numel(), C))
+    out = torch.empty_like(x)
+    check(lib().jcm_bias_relu(_ptr(x), _ptr(bias), x.numel() // C, C, int(relu), _ptr(out), _stream()), 'jcm_bias_relu')
+    return out
+
+
+def l2_loss_sum(tensors):
+    """sum over the tensors of sum(t^2)/2 -> 0-d fp32 CUDA tensor."""
+    dev = tensors[0].device
+    out = torch.empty((1,), dtype=F32, device=dev)
+    nb = max(lib().jcm_optim_blocks(t.numel()) for t in tensors)
+    partial = torch.empty((nb,), dtype=F32, device=dev)
+    for i, t in enumerate(tensors):
+        _req(t, F32, 'variable')
+        check(lib().jcm_sumsq(_ptr(t), t.numel(), 0.5, int(i > 0), _ptr(partial), _ptr(out), _stream()), 'jcm_sumsq')
+    return out[0]
+
+
+def tower_mean(grads):
+    """mean of same-shaped fp32 CUDA tensors, summed in list order."""
+    g0 = _req(grads[0], F32, 'grad')
+    for g in grads[1:]:
+        _req(g, F32, 'grad')
+        if g.shape != g0.shape or g.device != g0.device:
+            raise ValueError('tower gradients must have one shape and live on one device')
+    out = torch.empty_like(g0)
+    arr = (ctypes.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
+    check(lib().jcm_tower_mean(arr, len(grads), g0.numel(), _ptr(out), _stream()), 'jcm_tower_mean')
+    return out
+
+
+def clip_by_global_norm(grads, clip):
+    """[g * clip / max(global norm, clip)] for a list of fp32 CUDA tensors (tf.clip_by_global_norm)."""
+    dev = grads[0].device
+    sumsq = torch.empty((1,), dtype=F32, device=dev)
+    nb = max(lib().jcm_optim_blocks(g.numel()) for g in grads)
+    partial = torch.empty((nb,), dtype=F32, device=dev)
+    for i, g in enumerate(grads):
+        _req(g, F32, 'grad')
+        check(lib().jcm_sumsq(_ptr(g), g.numel(), 1.0, int(i > 0), _ptr(partial), _ptr(sumsq), _stream()), 'jcm_sumsq')
+    out = []
+    for g in grads:
+        o = torch.empty_like(g)
+        check(lib().jcm_clip_scale(_ptr(g), g.numel(), _ptr(sumsq), float(clip), _ptr(o), _stream()), 'jcm_clip_scale')
+        out.append(o)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ part detector
 def conv2d_planes(xp, wp, bias, cout, ksize, relu, naive=False, alg_kdim=None, out_bf16=False):
     """xp activation planes [B,H,W,Cin], wp packed weight planes [kh*kw,Cout_pad,Cin] -> fp32 [B,H,W,cout].
@@ -181,7 +271,8 @@ def conv2d_planes(xp, wp, bias, cout, ksize, relu, naive=False, alg_kdim=None, o
                                    cout, cout_pad, kh, kw, int(relu), _stream()), 'jcm_conv2d_fwd')
     if prof:
         e1.record()
-        PROFILE.add('conv_igemm_kernel', 2.0 * B * H * W * (alg_kdim or kh * kw * cin) * cout, e0, e1)
+        PROFILE.add('conv_igemm_kernel', 2.0 * B * H * W * (alg_kdim or kh * kw * cin) * cout, e0, e1,
+                    tag='%dx%d %d->%d k%dx%d' % (H, W, cin, cout, kh, kw))
     return y
 
 

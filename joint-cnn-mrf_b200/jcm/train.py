@@ -71,12 +71,7 @@ def upsample_avg3_bwd(dm, shape2, shape3):
     return d2, d3
 
 
-def pad_planes(x, cpad, split):
-    C = x.shape[-1]
-    M = x.numel() // C
-    out = ops._new_planes(tuple(x.shape[:-1]) + (cpad,), x.device, split)
-    check(lib().jcm_pad_planes(_ptr(x), M, C, cpad, _ptr(out.hi), _ptr(out.lo), _stream()), 'jcm_pad_planes')
-    return out
+pad_planes = ops.pad_planes
 
 
 def conv2d_wgrad(xp, gp, dw, cout, ksize, alg_flops=None):
@@ -99,7 +94,8 @@ def conv2d_wgrad(xp, gp, dw, cout, ksize, alg_flops=None):
                                  kh, kw, _stream()), 'jcm_conv2d_wgrad')
     if prof:
         e1.record()   # includes the (small) deterministic split reduction kernel that follows the GEMM
-        ops.PROFILE.add('conv_wgrad_kernel', alg_flops if alg_flops is not None else 2.0 * B * H * W * kh * kw * cin * cout, e0, e1)
+        ops.PROFILE.add('conv_wgrad_kernel', alg_flops if alg_flops is not None else 2.0 * B * H * W * kh * kw * cin * cout, e0, e1,
+                        tag='%dx%d %d->%d k%dx%d' % (H, W, cin, cout, kh, kw))
     return dw
 
 
@@ -138,13 +134,22 @@ def spatial_model_bwd(g, heat_map, ss, saved, train, sm, fwd_ws, d_energies, d_b
 class Trainer:
     """Owns the flat parameter / gradient / optimizer-state buffers and runs the training step."""
 
-    def __init__(self, p, sm, ctx, world_size=1, lr=0.001, optimizer='adam', n_updates_total=None):
-        if not ctx.train_pd:
-            raise ValueError('train_pd=False (frozen part detector) is not implemented in the training step')
+    def __init__(self, p, sm, ctx, world_size=1, lr=0.001, optimizer='adam', n_updates_total=None, bn_moving='mean'):
+        """bn_moving: how the BatchNorm moving statistics of the replicas are combined each step.  The reference's towers all
+        update ONE shared variable (main.py:555-560), so every replica must end the step with the same values:
+          'mean'   - 0.9 * old + 0.1 * mean over replicas of the batch statistic (one tiny all-reduce; equals the reference for
+                     one tower and keeps the decay at 0.9 per step whatever the replica count),
+          'towers' - the reference's literal behaviour with its N per-tower assign_moving_average ops executed in tower order:
+                     0.9^N * old + 0.1 * sum_i 0.9^(N-1-i) * batch_i (the decay compounds with the number of towers)."""
         if optimizer not in ('adam', 'momentum'):
             raise Exception('wrong optimizer')            # same message as main.py:506
+        if bn_moving not in ('mean', 'towers'):
+            raise ValueError("bn_moving must be 'mean' or 'towers'")
+        if not ctx.train_pd and not ctx.use_sm:
+            raise ValueError('train_pd=False without the spatial model leaves no trainable variable')
         self.p, self.sm, self.ctx = p, sm, ctx
         self.world_size, self.lr, self.optimizer = world_size, lr, optimizer
+        self.bn_moving = bn_moving
         self.t = 0
         self.n_updates_total = n_updates_total
         dev = sm.energies.device
@@ -167,10 +172,16 @@ class Trainer:
         if self.n_decay % 4 or any(p[k].numel() % 4 for k in names_w):
             raise ValueError('conv kernel sizes must be multiples of 4 elements')
         self.n = n
+        # trainable range of the flat buffer: everything, or (train_pd=False, main.py:129,147,153,443: the part detector's conv
+        # kernels, biases and BN gamma/beta are created with trainable=False) only the spatial model's variables
+        self.opt_lo = 0 if ctx.train_pd else offs['sm/energies']
         # gradient buckets (element ranges of the flat buffer): 0 = conv5+conv6 kernels, 1 = full bank, 2 = half bank,
         # 3 = quarter bank kernels + every other variable (two ranges)
-        first = {b: min(offs[k] for k in names_w if bank_of(k) == b) for b in range(4)}
-        self.buckets = [[(first[0], self.n_decay)], [(first[1], first[0])], [(first[2], first[1])], [(0, first[2]), (self.n_decay, n)]]
+        if ctx.train_pd:
+            first = {b: min(offs[k] for k in names_w if bank_of(k) == b) for b in range(4)}
+            self.buckets = [[(first[0], self.n_decay)], [(first[1], first[0])], [(first[2], first[1])], [(0, first[2]), (self.n_decay, n)]]
+        else:
+            self.buckets = [[(self.opt_lo, n)]]
         self._pending = []          # async all-reduce handles of this step
         self._started = set()       # buckets whose all-reduce has been issued this step
         self._comm_stream = None
@@ -192,6 +203,23 @@ class Trainer:
                     sm.bn[k[3:]] = view
             else:
                 p[k] = view
+        # BatchNorm moving statistics: views into ONE small buffer so that the replicas can combine them with one all-reduce
+        mov = [(k, p[k]) for k in p if 'moving_' in k] + [('sm/' + k, sm.bn[k]) for k in ('moving_mean', 'moving_variance')]
+        self.moving = torch.zeros(sum((t.numel() + 3) // 4 * 4 for _, t in mov), dtype=F32, device=dev)
+        o = 0
+        for k, t in mov:
+            view = self.moving[o:o + t.numel()].view(t.shape)
+            view.copy_(t)
+            o += (t.numel() + 3) // 4 * 4
+            if k.startswith('sm/'):
+                sm.bn[k[3:]] = view
+            else:
+                p[k] = view
+        self._moving_prev = torch.empty_like(self.moving) if world_size > 1 else None
+        if world_size > 1:
+            # the reference's towers share ONE set of variables (main.py:555): start every replica from rank 0's values
+            torch.distributed.broadcast(self.flat, 0)
+            torch.distributed.broadcast(self.moving, 0)
         nb = lib().jcm_optim_blocks(n)
         self.partial = torch.empty(2 * nb, dtype=F32, device=dev)
         self.stats = torch.zeros(2, dtype=F32, device=dev)
@@ -203,6 +231,8 @@ class Trainer:
             return self.lr
         b = [round(f * self.n_updates_total) for f in (0.7, 0.8, 0.9)]
         vals = [self.lr, self.lr / 2, self.lr / 5, self.lr / 10]
+        # tf.train.piecewise_constant(n_iters_tf, ...) is evaluated with the global step BEFORE apply_gradients increments it
+        # (main.py:492,577): the k-th update (k = 1, 2, ...) sees x = k - 1.  Call this before self.t is incremented.
         for bound, v in zip(b, vals):
             if self.t <= bound:
                 return v
@@ -217,8 +247,11 @@ class Trainer:
         K, split = ctx.n_joints, ctx.split
         B = x.shape[0]
         dev = x.device
+        if self._moving_prev is not None:
+            self._moving_prev.copy_(self.moving)          # the replicas' updates of this step are combined in apply()
         banks = ops.prep_input(x, split)
         saved = {}
+        train_pd = ctx.train_pd
 
         def fwd_layer(xp, name, ksize, kind='fwd'):
             w, b = p[name + '/weights'], p[name + '/biases']
@@ -227,7 +260,8 @@ class Trainer:
                                   out_bf16=ctx.act_bf16 and w.shape[3] % 64 == 0)   # narrow (--debug) layers keep fp32 activations
             ss, st = ops.bn_scale_shift(a, p[name + '/BatchNorm/gamma'], p[name + '/BatchNorm/beta'], p[name + '/BatchNorm/moving_mean'],
                                         p[name + '/BatchNorm/moving_variance'], train=True, save=True)
-            saved[name] = (xp, a, ss, st)
+            if train_pd:
+                saved[name] = (xp, a, ss, st)
             if tap is not None:
                 tap[name + '/relu'] = a
             return a, ss
@@ -264,9 +298,14 @@ class Trainer:
             g_sm = softmax_ce_bwd(logit_sm, y, lse_sm, inv_bk)
             d_cat = spatial_model_bwd(g_sm, cat, ss_sm, st_sm, True, sm, ws_sm, g['sm/energies'], g['sm/biases'], g['sm/gamma'], g['sm/beta'],
                                       tensor_core=ctx.sm_tc)
-            spatial_softmax_bwd(hm_pd, d_cat, d_logit, accumulate=True)
+            if train_pd:
+                spatial_softmax_bwd(hm_pd, d_cat, d_logit, accumulate=True)
         else:
             d_logit.mul_(2.0)   # loss_sm == loss_pd when the spatial model is off (main.py:533-536)
+        if not train_pd:
+            # frozen part detector (train_pd = False, main.py:443): its variables are not trainable, so TF differentiates the loss
+            # only w.r.t. the pairwise energies / biases and bn_sm's gamma / beta - nothing flows back through `model`
+            return {'loss_pd': loss_pd, 'loss_sm': loss_sm, 'logit_pd': logit_pd}
 
         # ---- part-detector backward
         # conv6 in its tap-expanded form (csrc/taps.cu): one scatter of the K-channel gradient, then two 1x1 GEMMs
@@ -344,21 +383,48 @@ class Trainer:
             self._pending = []
         self._started = set()
 
+    def sync_moving_statistics(self):
+        """Combines the replicas' BatchNorm moving-statistic updates of this step (see __init__, bn_moving).  One tiny all-reduce
+        (8 K floats); no-op for a single replica."""
+        if self.world_size == 1:
+            return
+        dist = torch.distributed
+        N = self.world_size
+        if self.bn_moving == 'mean':
+            dist.all_reduce(self.moving, op=dist.ReduceOp.SUM)
+            self.moving.mul_(1.0 / N)
+        else:
+            rank = dist.get_rank()
+            d = ops.BN_DECAY
+            self.moving.sub_(self._moving_prev, alpha=d).mul_(d ** (N - 1 - rank))      # (1 - d) * batch_i * d^(N-1-i)
+            dist.all_reduce(self.moving, op=dist.ReduceOp.SUM)
+            self.moving.add_(self._moving_prev, alpha=d ** N)
+
     def apply(self):
         """Gradient mean over replicas (one NCCL all-reduce), weight decay, global-norm clip, Adam / Momentum."""
         self.reduce_gradients()
+        self.sync_moving_statistics()
+        lr = self.current_lr()          # schedule evaluated at the pre-increment step count, as tf.train.piecewise_constant is
         self.t += 1
-        check(lib().jcm_grad_prepare(_ptr(self.grads), _ptr(self.flat), self.n, self.n_decay, 1.0 / self.world_size, float(self.ctx.lmbd),
+        lo, n = self.opt_lo, self.n - self.opt_lo
+        n_decay = max(self.n_decay - lo, 0)
+        off = ctypes.c_void_p
+        ptr = lambda t: off(t.data_ptr() + 4 * lo)
+        check(lib().jcm_grad_prepare(ptr(self.grads), ptr(self.flat), n, n_decay, 1.0 / self.world_size, float(self.ctx.lmbd),
                                      _ptr(self.partial), _ptr(self.stats), _stream()), 'jcm_grad_prepare')
-        lr = self.current_lr()
+        if lo > 0:
+            # frozen part detector: its kernels still enter the loss value through lmbd * weight_decay (main.py:541 sums over
+            # tf.global_variables(), trainable or not) but receive no gradient
+            check(lib().jcm_sumsq(_ptr(self.flat), self.n_decay, 0.5, 0, _ptr(self.partial), _ptr(self.stats[1:2]), _stream()), 'jcm_sumsq')
         if self.optimizer == 'adam':
             lr_t = lr * math.sqrt(1.0 - ADAM_B2 ** self.t) / (1.0 - ADAM_B1 ** self.t)
-            check(lib().jcm_clip_adam(_ptr(self.flat), _ptr(self.grads), _ptr(self.m), _ptr(self.v), self.n, _ptr(self.stats), CLIP_NORM,
+            check(lib().jcm_clip_adam(ptr(self.flat), ptr(self.grads), ptr(self.m), ptr(self.v), n, _ptr(self.stats), CLIP_NORM,
                                       lr_t, ADAM_B1, ADAM_B2, ADAM_EPS, 0, _stream()), 'jcm_clip_adam')
         else:
-            check(lib().jcm_clip_adam(_ptr(self.flat), _ptr(self.grads), _ptr(self.m), _ptr(self.v), self.n, _ptr(self.stats), CLIP_NORM,
+            check(lib().jcm_clip_adam(ptr(self.flat), ptr(self.grads), ptr(self.m), ptr(self.v), n, _ptr(self.stats), CLIP_NORM,
                                       lr, 0.9, 0.0, 0.0, 1, _stream()), 'jcm_clip_adam')
-        self.ctx._wcache.clear()   # the kernels changed the weights in place: packed operand planes are stale
+        from .graph import params_updated
+        params_updated()    # the kernels changed the weights through raw pointers: packed operand planes are stale in every Context
 
     def step(self, x, y):
         out = self.forward_backward(x, y)

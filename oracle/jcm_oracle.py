@@ -14,6 +14,7 @@ TF1 semantics that are not visible in the reference tree ([TF1] tags; SURVEY.md 
     normalisation, unbiased variance into the moving average, applied AFTER the ReLU            [TF1]
   * max_pool SAME pads at the end with -inf                                                     [TF1]
   * Adam in the TF1 form, clip_by_global_norm, piecewise_constant                               [TF1]
+  * softmax_cross_entropy_with_logits: gradient = softmax - labels even for labels not summing to 1 [TF1]
 
 PARITY PINNING STATUS: **parity unpinned against TensorFlow itself** - TensorFlow 1.x cannot be installed in
 this image (no network) and the reference holds no tests, golden vectors or fixtures for this path.
@@ -215,20 +216,29 @@ def softplus(x):
     return F.softplus(SOFTPLUS_ALPHA * x) / SOFTPLUS_ALPHA
 
 
-def conv_mrf(A, B):
+def conv_mrf(A, B, fft=False):
     """main.py:77-91.  A [1,2H,2W,1] prior, B [b,H,W,1] likelihood -> [b,H,W,1].
     transpose+reverse+conv2d VALID == true 2-D convolution 'valid' ([1,H+1,W+1,b]); then NOT cropped but
-    legacy-bilinear resized to [H,W] (main.py:88-89)."""
+    legacy-bilinear resized to [H,W] (main.py:88-89).
+    fft=True (tests at K=14 / 96x128, where the direct form takes seconds per pair): the same 'valid' convolution through
+    torch.fft in the input precision - equal to the direct form to ~1e-13 in fp64 (tests/test_oracle_pins.py), differentiable."""
     hm_h, hm_w = B.shape[1], B.shape[2]
+    if fft:
+        a = A[0, :, :, 0]
+        s = (3 * hm_h - 1, 3 * hm_w - 1)                             # full linear convolution size
+        full = torch.fft.irfft2(torch.fft.rfft2(a, s=s).unsqueeze(0) * torch.fft.rfft2(B[:, :, :, 0], s=s), s=s)
+        C = full[:, hm_h - 1:2 * hm_h, hm_w - 1:2 * hm_w].unsqueeze(3)   # 'valid' part [b, H+1, W+1, 1]
+        return resize_images(C, hm_h, hm_w)
     Bf = torch.flip(B.permute(1, 2, 3, 0), dims=[0, 1])            # [h, w, 1, b]  (main.py:83-84)
     C = F.conv2d(A.permute(0, 3, 1, 2), Bf.permute(3, 2, 0, 1))    # [1, b, H+1, W+1] (main.py:87)
     C = resize_images(C.permute(0, 2, 3, 1), hm_h, hm_w)           # main.py:89
     return C.permute(3, 1, 2, 0)                                   # main.py:90
 
 
-def spatial_model(heat_map, sm, n_joints, flag_train, joint_names=None):
+def spatial_model(heat_map, sm, n_joints, flag_train, joint_names=None, fft=False):
     """main.py:94-125. heat_map [B,H,W,K+1]; sm = dict with 'bn_sm/BatchNorm/*', 'energy_<a>_<b>' [1,2H,2W,1],
-    'bias_<a>_<b>' [1,H,W,1].  Sum order: unary first, then cond joints ascending in joint_names (main.py:117-123)."""
+    'bias_<a>_<b>' [1,H,W,1].  Sum order: unary first, then cond joints ascending in joint_names (main.py:117-123).
+    fft: see conv_mrf."""
     names = list(joint_names if joint_names is not None else JOINT_NAMES[:n_joints] + ['torso'])
     bn = {k: sm['bn_sm/BatchNorm/' + k] for k in ('gamma', 'beta', 'moving_mean', 'moving_variance')}
     h = batch_norm(heat_map, bn, flag_train)                       # main.py:112-113
@@ -241,7 +251,7 @@ def spatial_model(heat_map, sm, n_joints, flag_train, joint_names=None):
             prior = softplus(sm['energy_' + jn + '_' + cn])        # main.py:120
             lik = softplus(h[:, :, :, j:j + 1])                    # main.py:121
             bias = softplus(sm['bias_' + jn + '_' + cn])           # main.py:122
-            m = m + torch.log(conv_mrf(prior, lik) + bias + DELTA)  # main.py:123
+            m = m + torch.log(conv_mrf(prior, lik, fft=fft) + bias + DELTA)  # main.py:123
         out.append(m)
     return torch.stack(out, dim=3)[:, :, :, :, 0]                  # main.py:125
 
@@ -278,11 +288,29 @@ def spatial_softmax(hm):
     return torch.softmax(hm.reshape(B, H * W, K), dim=1).reshape(B, H, W, K)
 
 
+class _SoftmaxXentTF1(torch.autograd.Function):
+    """[TF1] tf.nn.softmax_cross_entropy_with_logits(dim=1) on [B, S, K]: loss = -sum_s labels * log_softmax(logits) and - as the
+    op's registered gradient - backprop = softmax(logits) - labels, WHATEVER sum(labels) is (TF's xent kernel emits `backprop`
+    next to `loss` and the gradient function is grad_loss * backprop).  For label maps that sum to 1 this is the derivative of the
+    loss; for the border-clipped blobs of data.py:180-186 (sum down to 0.25) it is not: autograd of the formula would give
+    softmax * sum(labels) - labels.  No gradient flows into the labels."""
+
+    @staticmethod
+    def forward(ctx, logits, labels):
+        ls = torch.log_softmax(logits, dim=1)
+        ctx.save_for_backward(ls, labels)
+        return -(labels * ls).sum(1)
+
+    @staticmethod
+    def backward(ctx, g):
+        ls, labels = ctx.saved_tensors
+        return g.unsqueeze(1) * (ls.exp() - labels), None
+
+
 def softmax_cross_entropy(hm1, hm2):
     """main.py:220-240  mean over (n,k) of -sum_s labels*log_softmax(logits)."""
     B, H, W, K = hm1.shape
-    ls = torch.log_softmax(hm1.reshape(B, H * W, K), dim=1)
-    return (-(hm2.reshape(B, H * W, K) * ls).sum(1)).mean()
+    return _SoftmaxXentTF1.apply(hm1.reshape(B, H * W, K), hm2.reshape(B, H * W, K)).mean()
 
 
 def weight_decay(p, var_pattern='weights'):

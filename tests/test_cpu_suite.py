@@ -106,9 +106,8 @@ def test_sass_contains_blackwell_instructions(built_lib):
     sass = subprocess.run(['cuobjdump', '-sass', built_lib], capture_output=True, text=True).stdout
     for mnemonic in ('UTCHMMA', 'UTMALDG', 'LDTM', 'FFMA2', 'UTMASTG'):
         assert mnemonic in sass, mnemonic
-    # the experimental CTA-pair kernel (JCM_CONV_CTA2=1, not yet run on a GPU) keeps compiling to the 2-SM forms
-    for mnemonic in ('UTCHMMA.2CTA', 'UTMALDG.4D.2CTA', 'UTCBAR.2CTA.MULTICAST'):
-        assert mnemonic in sass, mnemonic
+    # the CTA-pair experiment lives only in the -DJCM_EXPERIMENTS build: the product library has no 2-SM forms
+    assert '.2CTA' not in sass
 
 
 def test_argument_errors_do_not_need_a_gpu(built_lib):
@@ -229,3 +228,38 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, RANK='1', WORLD_SIZE='2'))
     assert r1.returncode == 0 and r1.stdout.strip() == ''
+
+
+def test_product_library_has_no_measurement_switches(built_lib):
+    """The shipped libjcm.so reads no JCM_* environment variable and carries no skip-the-work / experimental kernel: those exist
+    only in the -DJCM_EXPERIMENTS build (build.py --experiments -> libjcm_exp.so, loaded by tests/gpu_diag.py alone)."""
+    data = open(built_lib, 'rb').read()
+    for name in (b'JCM_CONV_DBG', b'JCM_MMA_SPLITN', b'JCM_CONV_NACC', b'JCM_CONV_CTA2', b'JCM_CONV_HALO', b'JCM_CONV_BGROUP',
+                 b'JCM_CONV_PATCH_TW'):
+        assert name not in data, name
+    assert b'conv_igemm_cta2_kernel' not in data
+    src = open(os.path.join(ROOT, 'joint-cnn-mrf_b200', 'jcm', '_lib.py')).read()
+    assert 'environ' not in src                     # the package always loads jcm/libjcm.so
+
+
+def test_packed_weight_cache_is_shared_and_epoch_validated(built_lib):
+    """graph.Context.packed: one cache for every Context, invalidated by params_updated() (raw-pointer updates) and by torch's
+    version counter - checked here on the bookkeeping alone (packing itself needs the GPU: tests/test_gpu_round2.py)."""
+    import torch
+    from jcm import graph
+    calls = []
+    orig = graph.ops.pack_weights
+    graph.ops.pack_weights = lambda w, split, transpose=False: calls.append((w.data_ptr(), transpose)) or object()
+    try:
+        w = torch.zeros(3, 3, 16, 16)
+        a, b = graph.Context(precision='bf16'), graph.Context(precision='bf16', flag_train=True)
+        p1 = a.packed('l', w)
+        assert b.packed('l', w) is p1 and len(calls) == 1          # the second context reuses the first one's planes
+        graph.params_updated()
+        p2 = b.packed('l', w)
+        assert p2 is not p1 and a.packed('l', w) is p2 and len(calls) == 2
+        w.add_(1.0)                                                 # torch-visible in-place update
+        assert a.packed('l', w) is not p2 and len(calls) == 3
+        assert a.packed('l', w, 'dgrad') is not a.packed('l', w) and len(calls) == 4
+    finally:
+        graph.ops.pack_weights = orig

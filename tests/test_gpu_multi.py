@@ -46,8 +46,40 @@ def _worker(rank, world, port, out_dir):
     gathered = [torch.empty_like(multi) for _ in range(world)]
     dist.all_gather(gathered, multi)
     ok = ok and all(torch.equal(gathered[0], g) for g in gathered)
+    msg = 'ok' if ok else 'mismatch %g' % float((multi - single).abs().max())
+
+    # DIFFERENT batches per replica (the real data-parallel case, main.py:511-517): after three steps every replica must hold the same
+    # parameters, optimizer slots AND BatchNorm moving statistics (the towers of the reference update one shared variable,
+    # main.py:555-560), and the moving statistics must be the mean-combined ones, not one replica's own
+    def run_dp(bn_moving):
+        gen = torch.Generator().manual_seed(0)
+        rng = np.random.default_rng(0)
+        p = jcm.init_part_detector(K, gen, debug=True, device=dev)
+        sm = jcm.PairwiseParams.from_distribution(orc.synthetic_pairwise(names, K, 8, 12, rng), names, K, 8, 12, device=dev)
+        ctx = jcm.Context(n_joints=K, joint_names=names, flag_train=True, precision='bf16', debug=True, lmbd=0.01)
+        tr = jcm.train.Trainer(p, sm, ctx, world_size=world, lr=1e-2, optimizer='adam', bn_moving=bn_moving)
+        g2 = torch.Generator().manual_seed(50 + rank)
+        x = torch.rand(2, 64, 96, 3, generator=g2).to(dev)
+        y = torch.from_numpy(orc.synthetic_labels(2, 8, 12, K + 1, np.random.default_rng(50 + rank))).to(dev)
+        own = []
+        for _ in range(3):
+            tr.forward_backward(x, y)
+            own.append(tr.moving.clone())           # this replica's own update, before the replicas are combined
+            tr.apply()
+        torch.cuda.synchronize()
+        return tr, own
+
+    for mode in ('mean', 'towers'):
+        tr, own = run_dp(mode)
+        for name, buf in (('flat', tr.flat), ('m', tr.m), ('v', tr.v), ('moving', tr.moving)):
+            gathered = [torch.empty_like(buf) for _ in range(world)]
+            dist.all_gather(gathered, buf)
+            if not all(torch.equal(gathered[0], g) for g in gathered):
+                ok, msg = False, msg + ' | %s differs across replicas (%s)' % (name, mode)
+        if torch.equal(own[-1], tr.moving):
+            ok, msg = False, msg + ' | moving statistics were not combined (%s)' % mode
     with open(os.path.join(out_dir, 'rank%d.txt' % rank), 'w') as f:
-        f.write('ok' if ok else 'mismatch %g' % float((multi - single).abs().max()))
+        f.write('ok' if ok else msg)
     dist.destroy_process_group()
 
 

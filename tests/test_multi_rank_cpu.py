@@ -54,6 +54,33 @@ def _worker(rank, world, port, out_dir):
     gathered = [torch.empty_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
     ok = ok and all(torch.equal(gathered[0], g) for g in gathered)   # replicas hold identical reduced gradients
+    # BatchNorm moving statistics: every replica updated its copy from its own shard (0.9 * old + 0.1 * batch_i); the reference's
+    # towers update ONE shared variable (main.py:555-560), so Trainer.apply combines them - 'mean' and the literal 'towers' form
+    old = torch.linspace(0.0, 1.0, tr.moving.numel())
+    batch = [old * 0 + 3.0 * (r + 1) + torch.arange(tr.moving.numel()) * 0.01 * (r + 1) for r in range(world)]
+    for mode in ('mean', 'towers'):
+        tr.bn_moving = mode
+        tr._moving_prev.copy_(old)
+        tr.moving.copy_(0.9 * old + 0.1 * batch[rank])
+        tr.sync_moving_statistics()
+        if mode == 'mean':
+            want_m = 0.9 * old + 0.1 * sum(batch) / world
+        else:
+            want_m = old.clone()
+            for r in range(world):                                   # tower order
+                want_m = 0.9 * want_m + 0.1 * batch[r]
+        ok = ok and bool(torch.allclose(tr.moving, want_m, rtol=1e-5, atol=1e-6))
+        g2 = [torch.empty_like(tr.moving) for _ in range(world)]
+        dist.all_gather(g2, tr.moving)
+        ok = ok and all(torch.equal(g2[0], t) for t in g2)
+    # replicas built from DIFFERENT initial values start from rank 0's (the towers share one variable set, main.py:555)
+    gen2 = torch.Generator().manual_seed(100 + rank)
+    p2 = jcm.init_part_detector(K, gen2, debug=True, device='cpu')
+    sm2 = jcm.PairwiseParams.from_distribution(distr, names, K, 8, 12, device='cpu')
+    tr2 = jcm.train.Trainer(p2, sm2, ctx, world_size=world)
+    g3 = [torch.empty_like(tr2.flat) for _ in range(world)]
+    dist.all_gather(g3, tr2.flat)
+    ok = ok and all(torch.equal(g3[0], t) for t in g3)
     with open(os.path.join(out_dir, 'rank%d.json' % rank), 'w') as f:
         json.dump({'ok': bool(ok), 'n': tr.n}, f)
     dist.destroy_process_group()

@@ -112,3 +112,18 @@ def test_argmax_hm_takes_the_first_maximum(ms):
     hm[0, 1, 2, 0] = hm[0, 3, 4, 0] = 1.0      # tie: the first in row-major order wins (np.argmax, main.py:392)
     hm[0, 3, 0, 1] = 2.0
     np.testing.assert_array_equal(ms.argmax_hm(hm), [[1, 3], [2, 0]])
+
+
+@pytest.mark.parametrize('tag', ['a', 'b', 'c'])
+def test_geometry_matches_the_reference_functions(ms, tag):
+    """get_different_scales / scale_hm_back against the outputs of the reference's own two functions (main.py:326-379, executed by
+    tests/golden/make_multiscale_golden.py with skimage's resize bound to jcm.multiscale.resize): same windows, same margins, same
+    rounding for every scale, on three map sizes including the odd 15x23."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'multiscale_reference.npz'))
+    x, hms = z[tag + '_x'].astype(np.float64), z[tag + '_hms'].astype(np.float64)
+    got = ms.get_different_scales(x)
+    assert got.shape == z[tag + '_scales'].shape
+    assert np.abs(got - z[tag + '_scales']).max() < 1e-6
+    back = ms.scale_hm_back(hms)
+    assert np.abs(back - z[tag + '_back']).max() < 1e-6

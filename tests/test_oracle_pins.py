@@ -131,3 +131,36 @@ def test_adam_and_schedule_helpers():
     orc.adam_tf1_step(p, [torch.full((3,), 0.5, dtype=torch.float64)], m, vv, 1, 0.01)
     # first TF1 Adam step moves by lr * sqrt(1-b2)/(1-b1) * (0.1 g)/(sqrt(0.001 g^2)+eps) ~= lr
     np.testing.assert_allclose(p[0].numpy(), 1 - 0.01, rtol=1e-6)
+
+
+def test_fft_form_of_conv_mrf_equals_the_direct_form():
+    """The FFT evaluation used by the K=14 / 96x128 GPU test is the same function as the direct restatement of main.py:77-91:
+    values and both gradients to 1e-12 in fp64."""
+    g = torch.Generator().manual_seed(9)
+    for H, W, b in ((12, 20, 3), (7, 9, 1), (24, 32, 2)):
+        A = torch.rand(1, 2 * H, 2 * W, 1, generator=g, dtype=torch.float64, requires_grad=True)
+        L = torch.rand(b, H, W, 1, generator=g, dtype=torch.float64, requires_grad=True)
+        d, f = orc.conv_mrf(A, L), orc.conv_mrf(A, L, fft=True)
+        assert float((d - f).abs().max()) < 1e-12 * float(d.abs().max())
+        w = torch.rand(d.shape, generator=g, dtype=torch.float64)
+        gd = torch.autograd.grad((d * w).sum(), [A, L])
+        gf = torch.autograd.grad((f * w).sum(), [A, L])
+        for x, y in zip(gd, gf):
+            assert float((x - y).abs().max()) < 1e-12 * float(x.abs().max())
+
+
+def test_softmax_cross_entropy_gradient_is_the_tf1_backprop():
+    """[TF1] tf.nn.softmax_cross_entropy_with_logits: loss = -sum(labels * log_softmax), registered gradient = softmax - labels for
+    ANY labels.  Equal to autograd of the formula when the labels sum to 1; for a clipped blob (sum 9/16) it is softmax - labels, not
+    softmax * 9/16 - labels."""
+    g = torch.Generator().manual_seed(10)
+    x = torch.randn(1, 5, 6, 2, generator=g, dtype=torch.float64, requires_grad=True)
+    y = torch.zeros(1, 5, 6, 2, dtype=torch.float64)
+    y[0, 2, 3, 0] = 1.0
+    y[0, :2, :2, 1] = torch.tensor([[4., 2], [2, 1]], dtype=torch.float64) / 16
+    loss = orc.softmax_cross_entropy(x, y)
+    ls = torch.log_softmax(x.reshape(1, 30, 2), 1)
+    assert abs(float(loss) - float((-(y.reshape(1, 30, 2) * ls).sum(1)).mean())) < 1e-14
+    loss.backward()
+    want = (ls.exp() - y.reshape(1, 30, 2)).reshape(1, 5, 6, 2) / 2
+    assert float((x.grad - want).abs().max()) < 1e-14
