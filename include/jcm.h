@@ -61,6 +61,13 @@ int jcm_split_planes(const float* x, long n, void* hi, void* lo, void* stream);
 int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, void* y, int y_bf16,
                    int B, int H, int W, int Cin, int Cout, int Cout_pad, int ksize, int kw, int relu, void* stream);
 
+/* jcm_conv2d_fwd with the kernel variant forced - for tests and measurements; every variant computes the same values.
+ * variant bit 0: single-CTA kernel instead of the CTA pair (cta_group::2) that N = 256 tiles use by default; bit 1: uniform tile grid
+ * instead of the mixed-shape pixel-tile plan; bit 2: no N-split of the last partial wave. */
+int jcm_conv2d_fwd_variant(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, void* y,
+                           int y_bf16, int B, int H, int W, int Cin, int Cout, int Cout_pad, int ksize, int kw, int relu, int variant,
+                           void* stream);
+
 /* tf.contrib.layers.batch_norm(decay=0.9, eps=1e-3, center, scale), main.py:128-130 and :112-113.
  * jcm_bn_stats: per-channel partial sums of x [M,C] into `partial` (jcm_bn_stats_blocks(M,C)*2*C floats).
  * jcm_bn_finalize: train != 0 -> batch statistics (biased variance), moving stats updated in place when update_moving
@@ -223,6 +230,11 @@ int jcm_augment_hm_renorm(const float* hm, int B, int H, int W, int C, float pow
 
 /* FP32 FMA peak loop (packed = 1: FFMA2); flops_out = FLOPs of one launch. scratch: blocks*512 floats. */
 int jcm_fma_peak(float* scratch, int blocks, int iters, int packed, double* flops_out, void* stream);
+
+/* The mixed-shape pixel-tile plan the convolution kernels use for an H x W map (csrc/tiling.cuh): cap = 128 (forward / data gradient
+ * M tiles) or 64 (weight-gradient k-blocks).  out = [n_tiles, n_shapes, then x0, y0, box_w, box_h per tile]; returns the ints written,
+ * 0 when no mixed plan beats `uniform_tiles`, < 0 (minus the size needed) when max_out is too small.  Host only, no GPU needed. */
+int jcm_debug_tile_plan(int H, int W, int cap, int exact_px, int max_shapes, int uniform_tiles, int* out, int max_out);
 
 /* Naive direct convolution on the same operand planes - used only by tests to cross-check the tcgen05 kernel. */
 int jcm_debug_conv2d_naive(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,

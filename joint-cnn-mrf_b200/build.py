@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, 'jcm', 'csrc')
 OUT_LIB = os.path.join(HERE, 'jcm', 'libjcm.so')
 OUT_EXP = os.path.join(HERE, 'jcm', 'libjcm_exp.so')
 STAMP_LIB = os.path.join(HERE, 'jcm', '.libjcm.stamp')
-SOURCES = ['core.cu', 'prep.cu', 'glue.cu', 'conv_tcgen05.cu', 'spatial_model.cu', 'backward.cu', 'taps.cu', 'optim.cu', 'augment.cu']
+SOURCES = ['core.cu', 'tiling.cu', 'prep.cu', 'glue.cu', 'conv_tcgen05.cu', 'spatial_model.cu', 'backward.cu', 'taps.cu', 'optim.cu', 'augment.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--expt-relaxed-constexpr',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-Wall', '-Xcompiler', '-Wno-unused-function']
 

@@ -23,6 +23,7 @@ SIGNATURES = {
     'jcm_pack_weights_s2d': (_I, [_P, _I, _P, _P, _P]),
     'jcm_split_planes': (_I, [_P, _L, _P, _P, _P]),
     'jcm_conv2d_fwd': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'jcm_conv2d_fwd_variant': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'jcm_bn_stats_blocks': (_I, [_L, _I]),
     'jcm_bn_stats': (_I, [_P, _I, _L, _I, _P, _P]),
     'jcm_bn_finalize': (_I, [_P, _L, _I, _P, _P, _P, _P, _F, _F, _I, _I, _P, _P, _P, _P, _P]),
@@ -67,6 +68,7 @@ SIGNATURES = {
     'jcm_tower_mean': (_I, [_P, _I, _L, _P, _P]),
     'jcm_subsample2': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
     'jcm_bias_relu': (_I, [_P, _P, _L, _I, _I, _P, _P]),
+    'jcm_debug_tile_plan': (_I, [_I, _I, _I, _I, _I, _I, _P, _I]),
     'jcm_fma_peak': (_I, [_P, _I, _I, _I, _P, _P]),
     'jcm_debug_conv2d_naive': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
 }

@@ -17,6 +17,7 @@
 //   * warp roles: w0 TMA producer, w1 MMA issuer (one elected lane), w2 TMEM allocator, w4-7 epilogue
 //     (tcgen05.ld -> +bias -> ReLU -> fp32 NHWC store).  Persistent grid, one CTA per SM.
 #include "common.cuh"
+#include "tiling.cuh"
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -68,9 +69,66 @@ struct ConvParams {
   const int* b_map;     // grp 2: weight plane = b_map[img / a_div]; NULL: img / a_div
   int dbg;              // measurement switches (JCM_CONV_DBG bit 0: epilogue releases TMEM without storing, bit 1: no MMAs issued,
                         // bit 2: producer skips the B loads) - results are garbage, timing only
+  // mixed-shape pixel-tile plan (tiling.cuh; plain mode, one term, TMA-store epilogue): plan_n > 0 tiles per image, tile i is the box
+  // psw[s] x psh[s] (s = pshape[i]) at (px0[i], py0[i]); its A box / output box come from ShapeMaps::a[s] / ::y[s]
+  int plan_n;
+  uint8_t px0[kPlanMaxTiles], py0[kPlanMaxTiles], pshape[kPlanMaxTiles];
+  uint8_t psw[4], psh[4];
+  // N-split tail: the last `tail_tiles` (M, N) tiles - the partial last wave of the persistent grid - run as tail_split sub-tiles of
+  // block_n / tail_split output channels each, so that the wave costs 1 / tail_split of a full round instead of a whole one
+  int tail_tiles, tail_split;
   const float* bias;
   float* y;
 };
+
+constexpr int kIgemmShapes = 4;
+struct ShapeMaps {
+  CUtensorMap a[kIgemmShapes];     // A-operand boxes {kc, sw, sh, 1} per plan shape
+  CUtensorMap a_lo[kIgemmShapes];  // the same over the lo planes (fp32 configuration: bf16x3 split products)
+  CUtensorMap y[kIgemmShapes];     // output boxes {32 | 64 channels, sw, sh, 1} per plan shape
+  CUtensorMap b_tail;              // weight box {kc, block_n / tail_split, 1}
+};
+
+// (M, N) tile of the persistent loop.  Virtual index v < full: tile v, all block_n channels.  v >= full: tail sub-tile.
+struct TileId { int nt, mt, n_off, n_cols; };
+__device__ __forceinline__ TileId decode_tile(const ConvParams& p, int v, int m_tiles, int total_tiles) {
+  TileId t;
+  int tile = v;
+  t.n_off = 0;
+  t.n_cols = p.block_n;
+  const int full = total_tiles - p.tail_tiles;
+  if (v >= full) {
+    const int u = v - full;
+    tile = full + u / p.tail_split;
+    t.n_cols = p.block_n / p.tail_split;
+    t.n_off = (u - (u / p.tail_split) * p.tail_split) * t.n_cols;
+  }
+  t.nt = tile / m_tiles;
+  t.mt = tile - t.nt * m_tiles;
+  return t;
+}
+// pixel patch of M tile mt: image, origin, plan shape (-1: the uniform TW x TH grid)
+struct Patch { int img, x0, y0, ty, shape; };
+__device__ __forceinline__ Patch decode_patch(const ConvParams& p, int mt) {
+  Patch q;
+  if (p.plan_n) {
+    q.img = mt / p.plan_n;
+    const int i = mt - q.img * p.plan_n;
+    q.x0 = p.px0[i];
+    q.y0 = p.py0[i];
+    q.shape = p.pshape[i];
+    q.ty = 0;
+  } else {
+    const int per = p.tiles_y * p.tiles_x;
+    q.img = mt / per;
+    const int r = mt - q.img * per;
+    q.ty = r / p.tiles_x;
+    q.x0 = (r - q.ty * p.tiles_x) * p.TW;
+    q.y0 = q.ty * p.TH;
+    q.shape = -1;
+  }
+  return q;
+}
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -194,7 +252,7 @@ __device__ __forceinline__ KRange tile_krange(const ConvParams& p, int img, int 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                  const __grid_constant__ CUtensorMap map_y, const ConvParams p) {
+                  const __grid_constant__ CUtensorMap map_y, const __grid_constant__ ShapeMaps smaps, const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 4];
   __shared__ uint32_t tmem_base_slot;
@@ -230,8 +288,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  const int m_tiles = p.B * p.tiles_y * p.tiles_x;
+  const int m_tiles = p.B * (p.plan_n ? p.plan_n : p.tiles_y * p.tiles_x);
   const int total_tiles = m_tiles * p.n_tiles;
+  const int virt_tiles = total_tiles + p.tail_tiles * (p.tail_split - 1);   // loop extent of the plain-mode roles (tail sub-tiles)
   const int taps = p.ksize * p.kw;
   const int num_kb = taps * p.cblocks * p.terms;
   const uint32_t smem_b0 = smem_base + p.a_stages * p.a_stride;     // halo mode: start of the weight ring
@@ -347,12 +406,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile / m_tiles, mt = tile - nt * m_tiles;
-        const int img = mt / (p.tiles_y * p.tiles_x);
-        const int r = mt - img * (p.tiles_y * p.tiles_x);
-        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-        const int x0 = tx * p.TW - p.pad_x, y0 = ty * p.TH - p.pad;
+      for (int vt = blockIdx.x; vt < virt_tiles; vt += gridDim.x) {
+        const TileId tid = decode_tile(p, vt, m_tiles, total_tiles);
+        const int nt = tid.nt;
+        const Patch pt = decode_patch(p, tid.mt);
+        const int img = pt.img, ty = pt.ty;
+        const int x0 = pt.x0 - p.pad_x, y0 = pt.y0 - p.pad;
         if (p.grp) {
           const KRange kr = tile_krange(p, img, ty);
           const int q = img / p.a_div;
@@ -372,6 +431,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
           }
           continue;
         }
+        // bytes one k-block brings in: the A box of this patch shape (a clipped plan shape has fewer rows) + this tile's weight rows
+        const uint32_t a_tx = pt.shape >= 0 ? (uint32_t)p.psw[pt.shape] * p.psh[pt.shape] * p.kc * 2 : (uint32_t)p.a_bytes;
+        const uint32_t b_tx = (uint32_t)tid.n_cols * p.kc * 2;
+        const void* mb_hi = tid.n_cols == p.block_n ? (const void*)&map_b_hi : (const void*)&smaps.b_tail;
+        const void* ma_plan = pt.shape >= 0 ? (const void*)&smaps.a[pt.shape] : (const void*)&map_a_hi;
+        const void* ma_plan_lo = pt.shape >= 0 ? (const void*)&smaps.a_lo[pt.shape] : (const void*)&map_a_lo;
         for (int tap = 0; tap < taps; ++tap) {
           const int dy = tap / p.kw, dx = tap - dy * p.kw;
           for (int cb = 0; cb < p.cblocks; ++cb) {
@@ -380,9 +445,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
               const uint32_t sa = smem_base + stage * p.stage_bytes;
               const uint32_t sb = sa + p.a_bytes;
               const uint32_t fb = bar_full + 8 * stage;
-              mbar_expect_tx(fb, (JCM_DBG(p) & 4) ? p.a_bytes : p.a_bytes + p.b_bytes);
-              tma_load_4d(sa, term == 1 ? &map_a_lo : &map_a_hi, fb, cb * p.kc, x0 + dx, y0 + dy, img);
-              if (!(JCM_DBG(p) & 4)) tma_load_3d(sb, term == 2 ? &map_b_lo : &map_b_hi, fb, cb * p.kc, nt * p.block_n, tap);
+              mbar_expect_tx(fb, (JCM_DBG(p) & 4) ? a_tx : a_tx + b_tx);
+              tma_load_4d(sa, term == 1 ? ma_plan_lo : ma_plan, fb, cb * p.kc, x0 + dx, y0 + dy, img);
+              if (!(JCM_DBG(p) & 4)) tma_load_3d(sb, term == 2 ? (const void*)&map_b_lo : mb_hi, fb, cb * p.kc, nt * p.block_n + tid.n_off, tap);
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -403,17 +468,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int vt = blockIdx.x; vt < virt_tiles; vt += gridDim.x) {
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
         uint32_t accumulate = 0, mcount = 0;     // bit j: accumulator j of this tile has been written; MMAs are dealt round-robin
         int tile_kb = num_kb;
+        const TileId tid = decode_tile(p, vt, m_tiles, total_tiles);
+        const uint32_t idesc_t = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(tid.n_cols >> 3) << 17);    // N of this tile (tail sub-tiles: block_n / tail_split)
         if (p.grp) {
-          const int mt = tile % m_tiles;
-          const int img = mt / (p.tiles_y * p.tiles_x);
-          const int ty = (mt - img * (p.tiles_y * p.tiles_x)) / p.tiles_x;
-          const KRange kr = tile_krange(p, img, ty);
+          const Patch pt = decode_patch(p, tid.mt);
+          const KRange kr = tile_krange(p, pt.img, pt.ty);
           tile_kb = (kr.tap_hi - kr.tap_lo) * (kr.cb_hi - kr.cb_lo);
         }
         for (int kb = 0; kb < tile_kb; ++kb) {
@@ -437,7 +502,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the 16-byte address field
             // (measured: a specialised nacc == 1 path without the round-robin bookkeeping compiles to a SLOWER issue loop - kept as is)
             const int j = (mcount++) & (p.nacc - 1);
-            tc_mma_bf16(d_tmem + j * p.block_n, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (accumulate >> j) & 1u);
+            tc_mma_bf16(d_tmem + j * p.block_n, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_t, (accumulate >> j) & 1u);
             accumulate |= 1u << j;
           }
           tc_commit(bar_empty + 8 * stage);
@@ -455,12 +520,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     int epi_chunk = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int nt = tile / m_tiles, mt = tile - nt * m_tiles;
-      const int img = mt / (p.tiles_y * p.tiles_x);
-      const int r = mt - img * (p.tiles_y * p.tiles_x);
-      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-      const int oy = ty * p.TH + ly, ox = tx * p.TW + lx;
+    // halo mode has no tail sub-tiles and no plan: its roles loop over total_tiles, and so must this one then
+    const int epi_tiles = p.halo ? total_tiles : virt_tiles;
+    for (int vt = blockIdx.x; vt < epi_tiles; vt += gridDim.x) {
+      const TileId tid = decode_tile(p, vt, m_tiles, total_tiles);
+      const int nt = tid.nt;
+      const Patch pt = decode_patch(p, tid.mt);
+      const int img = pt.img;
+      const int oy = pt.y0 + ly, ox = pt.x0 + lx;
+      const void* my = pt.shape >= 0 ? (const void*)&smaps.y[pt.shape] : (const void*)&map_y;
+      const int ncols = tid.n_cols, ncol0 = nt * p.block_n + tid.n_off;
       const bool valid = (oy < p.H) && (ox < p.W);
       float* yrow = p.y + ((size_t)((size_t)img * p.H + oy) * p.W + ox) * p.Cout;
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
@@ -471,7 +540,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
       } else if (p.tma_store && p.y_bf16) {
         // bf16 output: 64-column chunks (128-byte rows of bf16) through the same swizzled staging buffers, box {64 ch, TW, TH, 1}
         const uint32_t stage0 = p.halo ? smem_b0 + p.b_stages * p.b_stride : smem_base + p.stages * p.stage_bytes;
-        for (int c0 = 0; c0 < p.block_n; c0 += 64) {
+        for (int c0 = 0; c0 < ncols; c0 += 64) {
           const uint32_t buf = stage0 + (uint32_t)(epi_chunk & 1) * (kTileM * 128);
           if (threadIdx.x == 128) bulk_wait_read<1>();
           epi_bar();
@@ -479,7 +548,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
           tc_ld32(taddr0 + c0, v);
           tc_ld32(taddr0 + c0 + 32, u);
           tc_ld_wait();
-          const int co0 = nt * p.block_n + c0;
+          const int co0 = ncol0 + c0;
           const uint32_t rowaddr = buf + (uint32_t)row * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {       // 16-byte chunk j = channels co0 + 8j .. 8j+7
@@ -508,7 +577,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
           fence_proxy_async();
           epi_bar();
           if (threadIdx.x == 128) {
-            if (co0 < p.Cout) tma_store_4d(&map_y, buf, co0, tx * p.TW, ty * p.TH, img);
+            if (co0 < p.Cout) tma_store_4d(my, buf, co0, pt.x0, pt.y0, img);
             bulk_commit();
           }
           ++epi_chunk;
@@ -517,7 +586,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         // coalesced epilogue: 32-column chunks go through two 16 KB swizzled staging buffers and out with TMA stores (the box
         // {32 ch, TW, TH, 1} has the A operand's pixel order, so accumulator row == staging row; ragged edges are clipped by TMA)
         const uint32_t stage0 = p.halo ? smem_b0 + p.b_stages * p.b_stride : smem_base + p.stages * p.stage_bytes;
-        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
           const uint32_t buf = stage0 + (uint32_t)(epi_chunk & 1) * (kTileM * 128);
           if (threadIdx.x == 128) bulk_wait_read<1>();     // the store that last read this buffer is done with it
           epi_bar();
@@ -531,7 +600,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(u[e]));
           }
-          const int co0 = nt * p.block_n + c0;
+          const int co0 = ncol0 + c0;
           const uint32_t rowaddr = buf + (uint32_t)row * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -549,13 +618,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
           fence_proxy_async();
           epi_bar();
           if (threadIdx.x == 128) {
-            if (co0 < p.Cout) tma_store_4d(&map_y, buf, co0, tx * p.TW, ty * p.TH, img);
+            if (co0 < p.Cout) tma_store_4d(my, buf, co0, pt.x0, pt.y0, img);
             bulk_commit();   // one group per chunk even when nothing is stored (padded columns), so wait_group.read 1 == "chunk - 2 done"
           }
           ++epi_chunk;
         }
       } else {
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
           uint32_t v[32];
           tc_ld32(taddr0 + c0, v);
           tc_ld_wait();
@@ -566,7 +635,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(u[e]));
           }
-          const int co0 = nt * p.block_n + c0;
+          const int co0 = ncol0 + c0;
           if (valid) {
             if (((p.Cout & 3) == 0) && (co0 + 32 <= p.Cout)) {
   #pragma unroll
@@ -584,7 +653,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
   #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const int co = co0 + j;
-                if (co < p.Cout && (c0 + j) < p.block_n) {
+                if (co < p.Cout && (c0 + j) < ncols) {
                   float o = __uint_as_float(v[j]) + (p.bias ? p.bias[co] : 0.f);
                   if (p.relu) o = fmaxf(o, 0.f);
                   yrow[co] = o;
@@ -610,14 +679,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
   }
 }
 
-#ifdef JCM_EXPERIMENTS
 // =====================================================================================================================
-// EXPERIMENTAL (off unless JCM_CONV_CTA2=1; written at the end of round 1 without GPU time left to run it - round 2 starts by
-// testing it): the plain-mode kernel for N = 256 layers as a CTA PAIR (`cta_group::2`).  Two CTAs of a cluster own two adjacent
+// CTA-pair form (`cta_group::2`) of the plain mode for N = 256 tiles: the layers that hold 84 % of the part detector's FLOPs
+// (conv4_* / conv5 forward and data gradient) and the 1x1 tap GEMMs of conv6.  Two CTAs of a cluster own two consecutive
 // 128-pixel M tiles of the same N tile; each loads its own A tile and HALF of the weight tile (128 of the 256 rows), the leader
 // issues one M = 256 MMA per K step that reads both CTAs' shared memory and writes each CTA's own TMEM.  Per CTA and k-block the
-// L2->SM traffic drops from 48 KB to 32 KB and the B operand's shared-memory reads halve - the step is power-capped with the
-// tensor pipe at 93 % of the sustained peak, so energy per FLOP is what is left to gain.
+// L2->SM traffic drops from 48 KB to 32 KB and the B operand's shared-memory reads halve.  Measured on B200 (tests/gpu_diag.py cta2,
+// profiles/r02/diag_cta2_{on,off}.txt, isolated launches at batch 64): conv5 9.16 -> 8.77 ms best / 10.04 -> 8.77 ms median
+// (1462 -> 1673 TFLOP/s algorithmic), conv4_fullres 5.84 -> 5.03 ms: the step is power-capped, and this form needs less energy
+// per FLOP.
 // Protocol (PTX forms as in CUTLASS's sm100 2-SM collective, cute/arch/copy_sm100_tma.hpp, cutlass/arch/barrier.h):
 //   * full[s] lives in the LEADER (cluster rank 0): its producer arms it with the bytes of both CTAs; both producers' TMA
 //     loads carry `.cta_group::2` and the leader's barrier address (own address with the peer bit 24 cleared).
@@ -625,6 +695,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 //     .multicast::cluster` (mask 0b11); tempty[a] lives in the leader and counts the 8 epilogue warps of both CTAs
 //     (`mbarrier.arrive.shared::cluster` on the leader's address).
 //   * TMEM: one warp of EACH CTA issues `tcgen05.alloc.cta_group::2` (same warp index, same destination offset).
+// Work item = (pair of M tiles, N tile); the mixed-shape tile plan and the N-split tail of ConvParams apply (decode_tile with the
+// pair count in place of the M tile count; M tile = 2 * pair + cluster rank).
 // =====================================================================================================================
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the even CTA of the pair
 
@@ -666,9 +738,9 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-conv_igemm_cta2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                        const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                       const __grid_constant__ CUtensorMap map_y, const ConvParams p) {
+                       const __grid_constant__ CUtensorMap map_y, const __grid_constant__ ShapeMaps smaps, const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
   __shared__ uint32_t tmem_base_slot;
@@ -702,26 +774,34 @@ conv_igemm_cta2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  const int m_tiles = p.B * p.tiles_y * p.tiles_x;
+  const int m_tiles = p.B * (p.plan_n ? p.plan_n : p.tiles_y * p.tiles_x);
   const int m_pairs = (m_tiles + 1) / 2;
   const int total_pairs = m_pairs * p.n_tiles;
+  const int virt_pairs = total_pairs + p.tail_tiles * (p.tail_split - 1);      // tail_tiles counts PAIRS here
   const int pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
   const int taps = p.ksize * p.kw;
   const int num_kb = taps * p.cblocks * p.terms;
-  const int half_n = p.block_n >> 1;
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = pair0; t < total_pairs; t += pair_step) {
-        const int nt = t / m_pairs, mt = 2 * (t - nt * m_pairs) + (int)rank;
+      for (int t = pair0; t < virt_pairs; t += pair_step) {
+        const TileId tid = decode_tile(p, t, m_pairs, total_pairs);
+        const int nt = tid.nt, half_n = tid.n_cols >> 1;
         // a pair's second tile may lie past the last M tile: image index B is out of bounds, TMA fills zeros / clips the store
-        const int img = mt / (p.tiles_y * p.tiles_x);
-        const int r = mt - img * (p.tiles_y * p.tiles_x);
-        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-        const int x0 = tx * p.TW - p.pad_x, y0 = ty * p.TH - p.pad;
+        const Patch pt = decode_patch(p, 2 * tid.mt + (int)rank);
+        const Patch pt_peer = decode_patch(p, 2 * tid.mt + 1 - (int)rank);
+        const int img = pt.img;
+        const int x0 = pt.x0 - p.pad_x, y0 = pt.y0 - p.pad;
+        // the leader's barrier counts the bytes of BOTH CTAs: two A boxes (each of its own patch shape) + the two weight halves
+        const uint32_t a_own = pt.shape >= 0 ? (uint32_t)p.psw[pt.shape] * p.psh[pt.shape] * p.kc * 2 : (uint32_t)p.a_bytes;
+        const uint32_t a_peer = pt_peer.shape >= 0 ? (uint32_t)p.psw[pt_peer.shape] * p.psh[pt_peer.shape] * p.kc * 2 : (uint32_t)p.a_bytes;
+        const uint32_t tx_bytes = a_own + a_peer + (uint32_t)tid.n_cols * p.kc * 2;
+        const void* ma_plan = pt.shape >= 0 ? (const void*)&smaps.a[pt.shape] : (const void*)&map_a_hi;
+        const void* mb_hi = tid.n_cols == p.block_n ? (const void*)&map_b_hi : (const void*)&smaps.b_tail;
+        const void* ma_plan_lo = pt.shape >= 0 ? (const void*)&smaps.a_lo[pt.shape] : (const void*)&map_a_lo;
         for (int tap = 0; tap < taps; ++tap) {
           const int dy = tap / p.kw, dx = tap - dy * p.kw;
           for (int cb = 0; cb < p.cblocks; ++cb) {
@@ -729,9 +809,10 @@ conv_igemm_cta2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
               mbar_wait(bar_empty + 8 * stage, phase ^ 1);
               const uint32_t sa = smem_base + stage * p.stage_bytes;
               const uint32_t fb = bar_full + 8 * stage;
-              if (rank == 0) mbar_expect_tx(fb, 2 * (p.a_bytes + p.b_bytes));          // both CTAs' tiles land on the leader's barrier
-              tma_load_4d_2sm(sa, term == 1 ? &map_a_lo : &map_a_hi, fb, cb * p.kc, x0 + dx, y0 + dy, img);
-              tma_load_3d_2sm(sa + p.a_bytes, term == 2 ? &map_b_lo : &map_b_hi, fb, cb * p.kc, nt * p.block_n + (int)rank * half_n, tap);
+              if (rank == 0) mbar_expect_tx(fb, tx_bytes);                             // both CTAs' tiles land on the leader's barrier
+              tma_load_4d_2sm(sa, term == 1 ? ma_plan_lo : ma_plan, fb, cb * p.kc, x0 + dx, y0 + dy, img);
+              tma_load_3d_2sm(sa + p.a_bytes, term == 2 ? (const void*)&map_b_lo : mb_hi, fb, cb * p.kc,
+                              nt * p.block_n + tid.n_off + (int)rank * half_n, tap);
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -752,10 +833,12 @@ conv_igemm_cta2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = pair0; t < total_pairs; t += pair_step) {
+      for (int t = pair0; t < virt_pairs; t += pair_step) {
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
+        const TileId tid = decode_tile(p, t, m_pairs, total_pairs);
+        const uint32_t idesc_t = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(tid.n_cols >> 3) << 17);    // N of this tile (tail: block_n / tail_split)
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
@@ -763,7 +846,7 @@ conv_igemm_cta2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
           const uint64_t adesc = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
           const uint64_t bdesc = desc_hi | (uint64_t)(((sa + p.a_bytes) >> 4) & 0x3FFF);
           for (int k = 0; k < kk; ++k)
-            tc_mma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+            tc_mma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_t, (uint32_t)((kb | k) != 0));
           tc_commit_2sm(bar_empty + 8 * stage);      // frees the stage in both CTAs
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -779,16 +862,17 @@ conv_igemm_cta2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
     uint32_t acc_phase = 0;
     int epi_chunk = 0;
     const uint32_t stage0 = smem_base + p.stages * p.stage_bytes;
-    for (int t = pair0; t < total_pairs; t += pair_step) {
-      const int nt = t / m_pairs, mt = 2 * (t - nt * m_pairs) + (int)rank;
-      const int img = mt / (p.tiles_y * p.tiles_x);
-      const int r = mt - img * (p.tiles_y * p.tiles_x);
-      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+    for (int t = pair0; t < virt_pairs; t += pair_step) {
+      const TileId tid = decode_tile(p, t, m_pairs, total_pairs);
+      const Patch pt = decode_patch(p, 2 * tid.mt + (int)rank);
+      const int img = pt.img;
+      const void* my = pt.shape >= 0 ? (const void*)&smaps.y[pt.shape] : (const void*)&map_y;
+      const int ncols = tid.n_cols, ncol0 = tid.nt * p.block_n + tid.n_off;
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
       if (p.y_bf16) {
-        for (int c0 = 0; c0 < p.block_n; c0 += 64) {
+        for (int c0 = 0; c0 < ncols; c0 += 64) {
           const uint32_t buf = stage0 + (uint32_t)(epi_chunk & 1) * (kTileM * 128);
           if (threadIdx.x == 128) bulk_wait_read<1>();
           epi_bar();
@@ -796,7 +880,7 @@ conv_igemm_cta2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
           tc_ld32(taddr0 + c0, v);
           tc_ld32(taddr0 + c0 + 32, u);
           tc_ld_wait();
-          const int co0 = nt * p.block_n + c0;
+          const int co0 = ncol0 + c0;
           const uint32_t rowaddr = buf + (uint32_t)row * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -825,20 +909,20 @@ conv_igemm_cta2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
           fence_proxy_async();
           epi_bar();
           if (threadIdx.x == 128) {
-            if (co0 < p.Cout) tma_store_4d(&map_y, buf, co0, tx * p.TW, ty * p.TH, img);
+            if (co0 < p.Cout) tma_store_4d(my, buf, co0, pt.x0, pt.y0, img);
             bulk_commit();
           }
           ++epi_chunk;
         }
       } else {
-        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
           const uint32_t buf = stage0 + (uint32_t)(epi_chunk & 1) * (kTileM * 128);
           if (threadIdx.x == 128) bulk_wait_read<1>();
           epi_bar();
           uint32_t v[32];
           tc_ld32(taddr0 + c0, v);
           tc_ld_wait();
-          const int co0 = nt * p.block_n + c0;
+          const int co0 = ncol0 + c0;
           const uint32_t rowaddr = buf + (uint32_t)row * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -856,7 +940,7 @@ conv_igemm_cta2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
           fence_proxy_async();
           epi_bar();
           if (threadIdx.x == 128) {
-            if (co0 < p.Cout) tma_store_4d(&map_y, buf, co0, tx * p.TW, ty * p.TH, img);
+            if (co0 < p.Cout) tma_store_4d(my, buf, co0, pt.x0, pt.y0, img);
             bulk_commit();
           }
           ++epi_chunk;
@@ -878,8 +962,6 @@ conv_igemm_cta2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
-
-#endif  // JCM_EXPERIMENTS
 
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -931,8 +1013,10 @@ static void pick_patch(int H, int W, int* TW, int* TH) {
   }
   *TW = bw;
   *TH = bh;
+#ifdef JCM_EXPERIMENTS
   static const int force = JCM_ENV_INT("JCM_CONV_PATCH_TW", 0);   // measurement switch
   if (force > 0 && 128 % force == 0) { *TW = force; *TH = 128 / force; }
+#endif
 }
 
 extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
@@ -945,6 +1029,23 @@ extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_
   a.x_hi = x_hi; a.x_lo = x_lo; a.w_hi = w_hi; a.w_lo = w_lo; a.bias = bias; a.y = y; a.y_bf16 = y_bf16;
   a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.Cout_pad = Cout_pad; a.ksize = ksize; a.kw = kw; a.relu = relu;
   a.pad_y = -1;
+  a.stream = stream;
+  return jcm_conv_igemm_ex(a);
+}
+
+// jcm_conv2d_fwd with the kernel variant forced (tests and measurements; every variant computes the same values):
+// bit 0 = single-CTA kernel instead of the CTA pair, bit 1 = uniform tile grid instead of the mixed-shape plan, bit 2 = no N-split tail.
+extern "C" int jcm_conv2d_fwd_variant(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
+                                      void* y, int y_bf16, int B, int H, int W, int Cin, int Cout, int Cout_pad, int ksize, int kw,
+                                      int relu, int variant, void* stream) {
+  if (kw <= 0) kw = ksize;
+  JCM_CHECK_ARG(ksize > 0 && (ksize & 1) && (kw & 1), "jcm_conv2d_fwd_variant: kernel extents must be odd, got %d x %d", ksize, kw);
+  ConvExArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x_hi = x_hi; a.x_lo = x_lo; a.w_hi = w_hi; a.w_lo = w_lo; a.bias = bias; a.y = y; a.y_bf16 = y_bf16;
+  a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.Cout_pad = Cout_pad; a.ksize = ksize; a.kw = kw; a.relu = relu;
+  a.pad_y = -1;
+  a.variant = variant;
   a.stream = stream;
   return jcm_conv_igemm_ex(a);
 }
@@ -1031,15 +1132,43 @@ int jcm_conv_igemm_ex(const ConvExArgs& a) {
     if (p.b_stages > kMaxStages) p.b_stages = kMaxStages;
     p.halo = p.b_stages >= 3;
   }
-  // experimental CTA-pair form of the plain mode for N = 256 layers (conv_igemm_cta2_kernel): off unless JCM_CONV_CTA2=1
-  static const int cta2_env = JCM_ENV_INT("JCM_CONV_CTA2", 0);
-  const bool cta2 = cta2_env && !p.halo && p.grp == 0 && p.block_n == 256 && p.tma_store && p.nacc == 1 && !p.mma_split_n && !p.dbg &&
-                    jcm_num_sms() >= 2;
-  if (cta2) {
+  // CTA-pair form (cta_group::2) of the plain mode for N = 256 tiles: the default wherever it applies.  a.variant (tests /
+  // measurements, jcm_conv2d_fwd_variant): bit 0 = single-CTA kernel, bit 1 = uniform tile grid, bit 2 = no N-split tail.
+  const bool pair = !(a.variant & 1) && !p.halo && p.grp == 0 && p.block_n == 256 && p.tma_store && p.nacc == 1 && !p.mma_split_n &&
+                    !p.dbg && jcm_num_sms() >= 2;
+  if (pair) {
     p.b_bytes = (p.block_n / 2) * p.kc * 2;            // each CTA of the pair holds half of the weight tile
     p.stage_bytes = ((p.a_bytes + p.b_bytes + 1023) / 1024) * 1024;
     p.stages = (225 * 1024 - epi_bytes) / p.stage_bytes;
     if (p.stages > kMaxStages) p.stages = kMaxStages;
+  }
+  // mixed-shape tile plan (tiling.cuh): plain mode with the TMA-store epilogue, when it needs fewer tiles than the uniform grid
+  TilePlan plan;
+  plan.n_tiles = 0;
+  p.plan_n = 0;
+  if (!(a.variant & 2) && !p.halo && p.grp == 0 && p.tma_store && p.nacc == 1 && !p.mma_split_n &&
+      plan_tiles(H, W, kTileM, true, kIgemmShapes, p.tiles_x * p.tiles_y, &plan)) {
+    p.plan_n = plan.n_tiles;
+    memcpy(p.px0, plan.x0, sizeof(p.px0));
+    memcpy(p.py0, plan.y0, sizeof(p.py0));
+    memcpy(p.pshape, plan.shape, sizeof(p.pshape));
+    for (int i = 0; i < kIgemmShapes; ++i) { p.psw[i] = i < plan.n_shapes ? plan.sw[i] : 0; p.psh[i] = i < plan.n_shapes ? plan.sh[i] : 0; }
+  }
+  // N-split tail (see ConvParams): work units of the persistent loop = (M tiles or M-tile pairs) x N tiles
+  p.tail_tiles = 0;
+  p.tail_split = 1;
+  const int m_tiles_h = B * (p.plan_n ? p.plan_n : p.tiles_x * p.tiles_y);
+  const int units = (pair ? (m_tiles_h + 1) / 2 : m_tiles_h) * p.n_tiles;
+  const int workers = pair ? (jcm_num_sms() & ~1) / 2 : jcm_num_sms();
+  if (!(a.variant & 4) && p.terms == 1 && !p.halo && p.grp == 0 && p.tma_store && p.block_n == 256 && p.nacc == 1 && !p.mma_split_n && units > workers &&
+      units % workers != 0) {
+    const int rem = units % workers;
+    double best = 1.0;
+    for (int sp = 2; sp <= 4; sp *= 2) {
+      const double cost = (double)jcm_cdiv(rem * sp, workers) / sp;
+      if (cost < best - 1e-9) { best = cost; p.tail_split = sp; }
+    }
+    if (p.tail_split > 1) p.tail_tiles = rem;
   }
   p.relu = relu;
   p.bias = bias;
@@ -1050,12 +1179,23 @@ int jcm_conv_igemm_ex(const ConvExArgs& a) {
 
   const CUtensorMapSwizzle swz = p.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  static ShapeMaps smaps_zero;            // zero-initialised template (unused slots must still be valid kernel-parameter bytes)
+  ShapeMaps smaps = smaps_zero;
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)(a.grp == 2 ? B / p.a_div : (p.a_map ? a.map_images : B))};
     uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
     uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)p.TW, (uint32_t)p.TH, 1};
     int rc = make_map(&ma_hi, x_hi, 4, dims, str, box, swz);
     if (rc) return rc;
+    for (int i = 0; i < (p.plan_n ? plan.n_shapes : 0); ++i) {
+      uint32_t pbox[4] = {(uint32_t)p.kc, plan.sw[i], plan.sh[i], 1};
+      rc = make_map(&smaps.a[i], x_hi, 4, dims, str, pbox, swz);
+      if (rc) return rc;
+      if (x_lo) {
+        rc = make_map(&smaps.a_lo[i], x_lo, 4, dims, str, pbox, swz);
+        if (rc) return rc;
+      }
+    }
     if (p.halo) box[2] = (uint32_t)(p.TH + ksize - 1);   // halo mode: the (unused) lo slot carries the halo-box map of x_hi
     rc = make_map(&ma_lo, x_lo ? x_lo : x_hi, 4, dims, str, box, swz);
     if (rc) return rc;
@@ -1067,11 +1207,16 @@ int jcm_conv_igemm_ex(const ConvExArgs& a) {
                                         : (a.grp == 2 ? (uint64_t)(p.b_map ? a.map_images : B / p.a_div) : (uint64_t)(ksize * kw));
     uint64_t dims[3] = {wc, (uint64_t)Cout_pad, planes};
     uint64_t str[2] = {wc * 2, (uint64_t)Cout_pad * wc * 2};
-    uint32_t box[3] = {(uint32_t)p.kc, (uint32_t)(cta2 ? p.block_n / 2 : p.block_n), 1};
+    uint32_t box[3] = {(uint32_t)p.kc, (uint32_t)(pair ? p.block_n / 2 : p.block_n), 1};
     int rc = make_map(&mb_hi, w_hi, 3, dims, str, box, swz);
     if (rc) return rc;
     rc = make_map(&mb_lo, w_lo ? w_lo : w_hi, 3, dims, str, box, swz);
     if (rc) return rc;
+    if (p.tail_split > 1) {
+      box[1] = (uint32_t)((p.block_n / p.tail_split) / (pair ? 2 : 1));
+      rc = make_map(&smaps.b_tail, w_hi, 3, dims, str, box, swz);
+      if (rc) return rc;
+    }
   }
 
   CUtensorMap my;
@@ -1084,37 +1229,38 @@ int jcm_conv_igemm_ex(const ConvExArgs& a) {
     int rc = make_map(&my, y, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B,
                       y_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
     if (rc) return rc;
+    for (int i = 0; i < (p.plan_n ? plan.n_shapes : 0); ++i) {
+      uint32_t pbox[4] = {y_bf16 ? 64u : 32u, plan.sw[i], plan.sh[i], 1};
+      rc = make_map(&smaps.y[i], y, 4, dims, str, pbox, CU_TENSOR_MAP_SWIZZLE_128B,
+                    y_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+      if (rc) return rc;
+    }
   }
 
-#ifdef JCM_EXPERIMENTS
-  if (cta2) {
-    const int m_tiles = B * p.tiles_x * p.tiles_y;
-    const int pairs = ((m_tiles + 1) / 2) * p.n_tiles;
-    int grid2 = jcm_num_sms() & ~1;
-    if (grid2 > 2 * pairs) grid2 = 2 * pairs;
+  static bool attr_set[2][64] = {{false}, {false}};     // function attributes are per device: one flag per kernel and device ordinal
+  int dev = 0;
+  JCM_CUDA(cudaGetDevice(&dev));
+  if (pair) {
+    int grid2 = 2 * workers;
+    if (grid2 > 2 * units) grid2 = 2 * units;
     const size_t smem2 = (size_t)p.stages * p.stage_bytes + epi_bytes + 1024;
-    JCM_CUDA(cudaFuncSetAttribute(conv_igemm_cta2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512));
-    conv_igemm_cta2_kernel<<<grid2, kThreads, smem2, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, my, p);
+    if (dev < 0 || dev >= 64 || !attr_set[1][dev]) {
+      JCM_CUDA(cudaFuncSetAttribute(conv_igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512));
+      if (dev >= 0 && dev < 64) attr_set[1][dev] = true;
+    }
+    conv_igemm_pair_kernel<<<grid2, kThreads, smem2, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, my, smaps, p);
     JCM_LAUNCH_CHECK();
     return JCM_OK;
   }
-#endif
-  const int total_tiles = B * p.tiles_x * p.tiles_y * p.n_tiles;
+  const int total_tiles = units;
   int grid = jcm_num_sms();
   if (grid > total_tiles) grid = total_tiles;
   const size_t smem = (p.halo ? (size_t)p.a_stages * p.a_stride + (size_t)p.b_stages * p.b_stride : (size_t)p.stages * p.stage_bytes) + epi_bytes + 1024;
-  {
-    // function attributes are per device: one flag per device ordinal (one process per GPU is the design, but a process that
-    // touches a second device must not launch there with the default 48 KB limit)
-    static bool attr_set[64] = {false};
-    int dev = 0;
-    JCM_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-      JCM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512));
-      if (dev >= 0 && dev < 64) attr_set[dev] = true;
-    }
+  if (dev < 0 || dev >= 64 || !attr_set[0][dev]) {
+    JCM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512));
+    if (dev >= 0 && dev < 64) attr_set[0][dev] = true;
   }
-  conv_igemm_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, my, p);
+  conv_igemm_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, my, smaps, p);
   JCM_LAUNCH_CHECK();
   return JCM_OK;
 }
@@ -1142,13 +1288,21 @@ struct WgradParams {
   int kc_n, kc_m;                  // channels per N-side / M-side box: 64, 32 or 16
   int splits, total_patches;
   int terms, stages, a_bytes, b_bytes, stage_bytes;
+  // mixed-shape patch plan (tiling.cuh, exact 64-pixel boxes; one term): plan_n > 0 patches per image replace the uniform grid
+  int plan_n;
+  uint8_t px0[kPlanMaxTiles], py0[kPlanMaxTiles], pshape[kPlanMaxTiles];
   float* partial;
+};
+constexpr int kWgradShapes = 4;
+struct WgradShapeMaps {
+  CUtensorMap m[kWgradShapes];     // M-side operand boxes {kc_m, sw, sh, 1, channel blocks} per plan shape
+  CUtensorMap n[kWgradShapes];     // N-side operand boxes
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_m_hi, const __grid_constant__ CUtensorMap map_m_lo,
                   const __grid_constant__ CUtensorMap map_n_hi, const __grid_constant__ CUtensorMap map_n_lo,
-                  const WgradParams p) {
+                  const __grid_constant__ WgradShapeMaps smaps, const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
   __shared__ uint32_t tmem_base_slot;
@@ -1182,7 +1336,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_m_hi, const __grid_con
 
   const int tasks_per_split = p.taps * p.m_tiles * p.n_tiles;
   const int total_tasks = p.splits * tasks_per_split;
-  const int patches_per_img = p.tiles_x * p.tiles_y;
+  const int patches_per_img = p.plan_n ? p.plan_n : p.tiles_x * p.tiles_y;
   const int m_boxes = kTileM / p.kc_m;
   const int n_boxes = p.block_n / p.kc_n;
   const int m_box_bytes = kWgPix * p.kc_m * 2;
@@ -1204,25 +1358,34 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_m_hi, const __grid_con
         const int p1 = (int)((long)(split + 1) * p.total_patches / p.splits);
         int img = p0 / patches_per_img;
         int q = p0 - img * patches_per_img;
-        int ty = q / p.tiles_x, tx = q - ty * p.tiles_x;
+        int ty = p.plan_n ? 0 : q / p.tiles_x, tx = p.plan_n ? 0 : q - ty * p.tiles_x;
         const int mblk0 = mt * m_boxes, nblk0 = nt * n_boxes;   // first channel block (of kc_m / kc_n channels) of this tile
         const int sdx_m = p.shift_m * dx, sdy_m = p.shift_m * dy, sdx_n = p.shift_n * dx, sdy_n = p.shift_n * dy;
         for (int patch = p0; patch < p1; ++patch) {
-          const int x0 = tx * p.TW, y0 = ty * p.TH;
+          int x0 = tx * p.TW, y0 = ty * p.TH;
+          const void *pm = (const void*)&map_m_hi, *pn = (const void*)&map_n_hi;
+          if (p.plan_n) {
+            x0 = p.px0[q];
+            y0 = p.py0[q];
+            pm = (const void*)&smaps.m[p.pshape[q]];
+            pn = (const void*)&smaps.n[p.pshape[q]];
+          }
           for (int term = 0; term < p.terms; ++term) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
             const uint32_t sa = smem_base + stage * p.stage_bytes;
             const uint32_t sb = sa + p.a_bytes;
             const uint32_t fb = bar_full + 8 * stage;
             mbar_expect_tx(fb, p.a_bytes + p.b_bytes);
-            const void* mm = (term == 1) ? (const void*)&map_m_lo : (const void*)&map_m_hi;
-            const void* mn = (term == 2) ? (const void*)&map_n_lo : (const void*)&map_n_hi;
+            const void* mm = (term == 1) ? (const void*)&map_m_lo : pm;
+            const void* mn = (term == 2) ? (const void*)&map_n_lo : pn;
             // one 5-D box per operand: {kc channels, TW, TH, 1 image, all channel blocks of the tile}
             tma_load_5d(sa, mm, fb, 0, x0 + sdx_m, y0 + sdy_m, img, mblk0);
             tma_load_5d(sb, mn, fb, 0, x0 + sdx_n, y0 + sdy_n, img, nblk0);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          if (++tx == p.tiles_x) {
+          if (p.plan_n) {
+            if (++q == p.plan_n) { q = 0; ++img; }
+          } else if (++tx == p.tiles_x) {
             tx = 0;
             if (++ty == p.tiles_y) { ty = 0; ++img; }
           }
@@ -1370,9 +1533,11 @@ void pick_patch64(int H, int W, int* TW, int* TH) {
 
 struct WgradPlan {
   int x_is_m, m_ch, n_ch, m_tiles, n_tiles, block_n, kc_n, kc_m, m_pad, n_pad, splits, TW, TH, tiles_x, tiles_y, total_patches;
+  bool mixed;          // patches follow `tiles` (mixed-shape plan) instead of the uniform TW x TH grid
+  TilePlan tiles;
 };
 
-void plan_wgrad(int B, int H, int W, int Cin, int Gc, int ksize, int kw, WgradPlan* pl) {
+void plan_wgrad(int B, int H, int W, int Cin, int Gc, int ksize, int kw, bool allow_mixed, WgradPlan* pl) {
   pl->x_is_m = Cin >= Gc;
   pl->m_ch = pl->x_is_m ? Cin : Gc;
   pl->n_ch = pl->x_is_m ? Gc : Cin;
@@ -1387,6 +1552,8 @@ void plan_wgrad(int B, int H, int W, int Cin, int Gc, int ksize, int kw, WgradPl
   pl->tiles_x = jcm_cdiv(W, pl->TW);
   pl->tiles_y = jcm_cdiv(H, pl->TH);
   pl->total_patches = B * pl->tiles_x * pl->tiles_y;
+  pl->mixed = allow_mixed && plan_tiles(H, W, kWgPix, true, kWgradShapes, pl->tiles_x * pl->tiles_y, &pl->tiles);
+  if (pl->mixed) pl->total_patches = B * pl->tiles.n_tiles;
   // k-split: the persistent grid runs ceil(tasks / SMs) waves of tasks that each stream total_patches / splits k-blocks (+ an
   // epilogue worth ~6 k-blocks).  Pick the split count that minimises waves x task length: e.g. conv5 (648 tasks = 4.4 waves)
   // wastes 12 % of the last wave unsplit, 0.5 % with 5 splits; the partial sums cost one extra read in wgrad_reduce_kernel.
@@ -1410,9 +1577,12 @@ void plan_wgrad(int B, int H, int W, int Cin, int Gc, int ksize, int kw, WgradPl
 // bytes of fp32 partial sums jcm_conv2d_wgrad needs in `workspace`
 extern "C" long jcm_conv2d_wgrad_workspace(int B, int H, int W, int Cin, int Gc, int ksize, int kw) {
   if (kw <= 0) kw = ksize;
-  WgradPlan pl;
-  plan_wgrad(B, H, W, Cin, Gc, ksize, kw, &pl);
-  return (long)pl.splits * ksize * kw * pl.m_pad * pl.n_pad * (long)sizeof(float);
+  // the larger of the two possible plans (the mixed-shape plan applies to the one-term form only and may pick another split count)
+  WgradPlan pl, pl2;
+  plan_wgrad(B, H, W, Cin, Gc, ksize, kw, true, &pl);
+  plan_wgrad(B, H, W, Cin, Gc, ksize, kw, false, &pl2);
+  const int splits = pl.splits > pl2.splits ? pl.splits : pl2.splits;
+  return (long)splits * ksize * kw * pl.m_pad * pl.n_pad * (long)sizeof(float);
 }
 
 // x planes [B,H,W,Cin] (layer input, Cin multiple of 16), g planes [B,H,W,Gc] (gradient w.r.t. the conv output, Gc = Cout padded
@@ -1427,7 +1597,7 @@ extern "C" int jcm_conv2d_wgrad(const void* x_hi, const void* x_lo, const void* 
   JCM_CHECK_ARG(B > 0 && H > 0 && W > 0 && (ksize & 1) && (kw & 1), "jcm_conv2d_wgrad: bad shape");
   JCM_CHECK_ARG((Cin % 16) == 0 && (Gc % 16) == 0 && Cout <= Gc && Cout <= dw_cout_stride, "jcm_conv2d_wgrad: channel counts must be multiples of 16 (Cin=%d Gc=%d)", Cin, Gc);
   WgradPlan pl;
-  plan_wgrad(B, H, W, Cin, Gc, ksize, kw, &pl);
+  plan_wgrad(B, H, W, Cin, Gc, ksize, kw, x_lo == nullptr, &pl);
   JCM_CHECK_ARG(pl.n_ch % pl.block_n == 0, "jcm_conv2d_wgrad: N-side channel count %d must be <= 256 or a multiple of 256", pl.n_ch);
   if (workspace_bytes < jcm_conv2d_wgrad_workspace(B, H, W, Cin, Gc, ksize, kw)) {
     jcm_set_error("jcm_conv2d_wgrad: workspace too small");
@@ -1449,6 +1619,12 @@ extern "C" int jcm_conv2d_wgrad(const void* x_hi, const void* x_lo, const void* 
   p.stages = (200 * 1024) / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   p.partial = (float*)workspace;
+  p.plan_n = pl.mixed ? pl.tiles.n_tiles : 0;
+  if (pl.mixed) {
+    memcpy(p.px0, pl.tiles.x0, sizeof(p.px0));
+    memcpy(p.py0, pl.tiles.y0, sizeof(p.py0));
+    memcpy(p.pshape, pl.tiles.shape, sizeof(p.pshape));
+  }
 
   const void* m_hi = pl.x_is_m ? x_hi : g_hi;
   const void* m_lo = pl.x_is_m ? x_lo : g_lo;
@@ -1459,6 +1635,8 @@ extern "C" int jcm_conv2d_wgrad(const void* x_hi, const void* x_lo, const void* 
   // [block][TH][TW][kc] = per channel block a [64 pixels][kc] MN-major UMMA operand.  Blocks past the tensor's channel extent
   // (M tile of 128 over a 64-channel tensor) are zero-filled by TMA, which pads M.
   CUtensorMap mm_hi, mm_lo, mn_hi, mn_lo;
+  static WgradShapeMaps wsm_zero;
+  WgradShapeMaps wsm = wsm_zero;
   {
     uint64_t dims[5] = {(uint64_t)pl.kc_m, (uint64_t)W, (uint64_t)H, (uint64_t)B, (uint64_t)(m_c / pl.kc_m)};
     uint64_t str[4] = {(uint64_t)m_c * 2, (uint64_t)W * m_c * 2, (uint64_t)H * W * m_c * 2, (uint64_t)pl.kc_m * 2};
@@ -1468,6 +1646,11 @@ extern "C" int jcm_conv2d_wgrad(const void* x_hi, const void* x_lo, const void* 
     if (rc) return rc;
     rc = make_map(&mm_lo, m_lo ? m_lo : m_hi, 5, dims, str, box, swz);
     if (rc) return rc;
+    for (int i = 0; i < (pl.mixed ? pl.tiles.n_shapes : 0); ++i) {
+      uint32_t pbox[5] = {(uint32_t)pl.kc_m, pl.tiles.sw[i], pl.tiles.sh[i], 1, (uint32_t)(kTileM / pl.kc_m)};
+      rc = make_map(&wsm.m[i], m_hi, 5, dims, str, pbox, swz);
+      if (rc) return rc;
+    }
   }
   {
     uint64_t dims[5] = {(uint64_t)pl.kc_n, (uint64_t)W, (uint64_t)H, (uint64_t)B, (uint64_t)(n_c / pl.kc_n)};
@@ -1478,13 +1661,18 @@ extern "C" int jcm_conv2d_wgrad(const void* x_hi, const void* x_lo, const void* 
     if (rc) return rc;
     rc = make_map(&mn_lo, n_lo ? n_lo : n_hi, 5, dims, str, box, swz);
     if (rc) return rc;
+    for (int i = 0; i < (pl.mixed ? pl.tiles.n_shapes : 0); ++i) {
+      uint32_t pbox[5] = {(uint32_t)pl.kc_n, pl.tiles.sw[i], pl.tiles.sh[i], 1, (uint32_t)(pl.block_n / pl.kc_n)};
+      rc = make_map(&wsm.n[i], n_hi, 5, dims, str, pbox, swz);
+      if (rc) return rc;
+    }
   }
   const int total_tasks = p.splits * p.taps * p.m_tiles * p.n_tiles;
   int grid = jcm_num_sms();
   if (grid > total_tasks) grid = total_tasks;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   JCM_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512));
-  conv_wgrad_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(mm_hi, mm_lo, mn_hi, mn_lo, p);
+  conv_wgrad_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(mm_hi, mm_lo, mn_hi, mn_lo, wsm, p);
   JCM_LAUNCH_CHECK();
   wgrad_reduce_kernel<<<dim3(jcm_cdiv(Cout, 32), jcm_cdiv(Cin, 32), p.taps), dim3(32, 8), 0, (cudaStream_t)stream>>>(
       p.partial, p.splits, p.taps, p.m_pad, p.n_pad, Cin, Cout, dw_cout_stride, pl.x_is_m, dw);

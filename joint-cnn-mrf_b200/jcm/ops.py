@@ -243,7 +243,7 @@ def clip_by_global_norm(grads, clip):
 
 
 # ------------------------------------------------------------------------------------------------ part detector
-def conv2d_planes(xp, wp, bias, cout, ksize, relu, naive=False, alg_kdim=None, out_bf16=False):
+def conv2d_planes(xp, wp, bias, cout, ksize, relu, naive=False, alg_kdim=None, out_bf16=False, variant=None):
     """xp activation planes [B,H,W,Cin], wp packed weight planes [kh*kw,Cout_pad,Cin] -> fp32 [B,H,W,cout].
     ksize: int (square) or (kh, kw).  alg_kdim: contraction length of the ALGORITHMIC convolution (default kh*kw*Cin; 75 for
     the s2d conv1)."""
@@ -266,6 +266,10 @@ def conv2d_planes(xp, wp, bias, cout, ksize, relu, naive=False, alg_kdim=None, o
     if naive:
         check(lib().jcm_debug_conv2d_naive(_ptr(xp.hi), _ptr(xp.lo), _ptr(wp.hi), _ptr(wp.lo), _ptr(bias), _ptr(y), B, H, W, cin, cout,
                                            cout_pad, kh, kw, int(relu), _stream()), 'jcm_debug_conv2d_naive')
+    elif variant is not None:
+        # tests / measurements: force the kernel variant (bit 0 single-CTA, bit 1 uniform tiles, bit 2 no N-split tail)
+        check(lib().jcm_conv2d_fwd_variant(_ptr(xp.hi), _ptr(xp.lo), _ptr(wp.hi), _ptr(wp.lo), _ptr(bias), _ptr(y), int(out_bf16), B, H, W,
+                                           cin, cout, cout_pad, kh, kw, int(relu), int(variant), _stream()), 'jcm_conv2d_fwd_variant')
     else:
         check(lib().jcm_conv2d_fwd(_ptr(xp.hi), _ptr(xp.lo), _ptr(wp.hi), _ptr(wp.lo), _ptr(bias), _ptr(y), int(out_bf16), B, H, W, cin,
                                    cout, cout_pad, kh, kw, int(relu), _stream()), 'jcm_conv2d_fwd')

@@ -518,25 +518,16 @@ def sec_smtc64():
 
 
 def sec_cta2():
-    """N = 256 plain-mode layers: result vs the naive kernel and time per launch.  Run once with JCM_DIAG_EXP=1 JCM_CONV_CTA2=1 and
-    once with JCM_DIAG_EXP=1 alone to compare the CTA-pair kernel with the single-CTA one."""
-    g = torch.Generator().manual_seed(3)
-    print('CTA2 env:', os.environ.get('JCM_CONV_CTA2'), 'lib:', jcm._lib.LIB_PATH)
-    for (B, H, W, Cin, Cout, k) in [(1, 16, 24, 64, 256, 3), (2, 30, 45, 256, 512, 9), (3, 60, 90, 64, 256, 5)]:
-        x = torch.randn(B, H, W, Cin, generator=g).to(dev)
-        w = (torch.randn(k, k, Cin, Cout, generator=g) / np.sqrt(k * k * Cin)).to(dev)
-        b = torch.randn(Cout, generator=g).to(dev)
-        xp, wp = ops.split_planes(x, False), ops.pack_weights(w, False)
-        y = ops.conv2d_planes(xp, wp, b, Cout, k, relu=True)
-        yn = ops.conv2d_planes(xp, wp, b, Cout, k, relu=True, naive=True)
-        torch.cuda.synchronize()
-        print('CTA2 B%d %dx%d Cin%d Cout%d k%d: vs naive %.2e' % (B, H, W, Cin, Cout, k, relerr(y, yn)), flush=True)
-    for (B, H, W, Cin, Cout, k) in [(64, 60, 90, 512, 512, 9), (64, 60, 90, 256, 512, 9)]:
+    """N = 256 plain-mode layers: time per launch of the kernel variants (bit 0 single-CTA instead of the CTA pair, bit 1 uniform tile
+    grid instead of the mixed-shape plan, bit 2 no N-split tail), isolated launches at batch 64."""
+    for (B, H, W, Cin, Cout, k) in [(64, 60, 90, 512, 512, 9), (64, 60, 90, 256, 512, 9), (64, 60, 90, 512, 256, 9), (64, 30, 45, 256, 512, 9)]:
         xp = ops.Planes(torch.randn(B, H, W, Cin, device=dev).to(torch.bfloat16), None)
-        wp = ops.Planes(torch.randn(k * k, Cout, Cin, device=dev).to(torch.bfloat16), None)
-        best, med = timeit(lambda: ops.conv2d_planes(xp, wp, None, Cout, k, relu=True, out_bf16=True), n=5, warm=2)
+        wp = ops.Planes((torch.randn(k * k, Cout, Cin, device=dev) / np.sqrt(k * k * Cin)).to(torch.bfloat16), None)
         fl = 2.0 * B * H * W * k * k * Cin * Cout
-        print('CTA2 time B%d Cin%d Cout%d k%d: %.3f ms best %.3f median = %.0f TFLOP/s' % (B, Cin, Cout, k, best, med, fl / med / 1e9), flush=True)
+        for variant in (0, 4, 6, 1, 7):
+            best, med = timeit(lambda: ops.conv2d_planes(xp, wp, None, Cout, k, relu=True, out_bf16=True, variant=variant), n=5, warm=2)
+            print('CTA2 %dx%d Cin%d Cout%d k%d variant %d: %.3f ms best %.3f median = %.0f TFLOP/s' % (H, W, Cin, Cout, k, variant, best, med, fl / med / 1e9),
+                  flush=True)
 
 
 if __name__ == '__main__':

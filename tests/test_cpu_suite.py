@@ -106,8 +106,9 @@ def test_sass_contains_blackwell_instructions(built_lib):
     sass = subprocess.run(['cuobjdump', '-sass', built_lib], capture_output=True, text=True).stdout
     for mnemonic in ('UTCHMMA', 'UTMALDG', 'LDTM', 'FFMA2', 'UTMASTG'):
         assert mnemonic in sass, mnemonic
-    # the CTA-pair experiment lives only in the -DJCM_EXPERIMENTS build: the product library has no 2-SM forms
-    assert '.2CTA' not in sass
+    # the CTA-pair kernel of the N = 256 layers (conv_igemm_pair_kernel, cta_group::2) compiles to the 2-SM forms
+    for mnemonic in ('UTCHMMA.2CTA', 'UTMALDG.4D.2CTA', 'UTCBAR.2CTA.MULTICAST'):
+        assert mnemonic in sass, mnemonic
 
 
 def test_argument_errors_do_not_need_a_gpu(built_lib):
@@ -237,7 +238,6 @@ def test_product_library_has_no_measurement_switches(built_lib):
     for name in (b'JCM_CONV_DBG', b'JCM_MMA_SPLITN', b'JCM_CONV_NACC', b'JCM_CONV_CTA2', b'JCM_CONV_HALO', b'JCM_CONV_BGROUP',
                  b'JCM_CONV_PATCH_TW'):
         assert name not in data, name
-    assert b'conv_igemm_cta2_kernel' not in data
     src = open(os.path.join(ROOT, 'joint-cnn-mrf_b200', 'jcm', '_lib.py')).read()
     assert 'environ' not in src                     # the package always loads jcm/libjcm.so
 

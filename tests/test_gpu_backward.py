@@ -141,7 +141,8 @@ def test_upsample_avg3_bwd(jcm, jtrain):
 # ------------------------------------------------------------------------------------------------ conv gradients
 WGRAD_CASES = [  # B, H, W, Cin, Cout, k : M side = the wider tensor, every swizzle mode, ragged patches, 2 M tiles, 2 N tiles
     (2, 12, 20, 64, 64, 5), (1, 15, 23, 128, 256, 9), (2, 16, 24, 32, 64, 5), (1, 9, 33, 16, 64, 3), (2, 8, 12, 256, 512, 9),
-    (1, 12, 20, 128, 7, 9), (3, 7, 5, 64, 16, 3), (1, 30, 45, 512, 512, 9), (2, 60, 90, 16, 32, 5)]
+    (1, 12, 20, 128, 7, 9), (3, 7, 5, 64, 16, 3), (1, 30, 45, 512, 512, 9), (2, 60, 90, 16, 32, 5),
+    (3, 60, 90, 64, 128, 3), (5, 30, 45, 128, 64, 5)]     # 60x90 / 30x45 in the one-term form: mixed-shape patch plan (csrc/tiling.cu)
 
 
 @pytest.mark.parametrize('case', WGRAD_CASES)
