@@ -127,10 +127,11 @@ int jcm_spatial_softmax_bwd(const float* y, const float* dy, int B, int S, int K
 
 /* [2x2 SAME max-pool bwd] + training-mode batch-norm bwd + ReLU bwd of one conv_layer (main.py:156-169).
  * a = ReLU output [B,H,W,C]; dout = gradient w.r.t. the layer output ([B,ceil(H/2),ceil(W/2),C] when pool), times dy_scale.
+ * dout: fp32, or bf16 when dout_bf16 (the bf16 configuration lets the data-gradient convolution write bf16).
  * Outputs: d_pre planes [B,H,W,C] (gradient w.r.t. the conv output), dgamma, dbeta, dbias [C].
  * workspace: (4 * jcm_bn_relu_bwd_blocks(M_out, C) + 2) * C floats. */
 int jcm_bn_relu_bwd_blocks(long M_out, int C);
-int jcm_bn_relu_bwd(const void* a, int a_bf16, const float* dout, const float* scale, const float* shift, const float* mean, const float* rstd,
+int jcm_bn_relu_bwd(const void* a, int a_bf16, const void* dout, int dout_bf16, const float* scale, const float* shift, const float* mean, const float* rstd,
                     float dy_scale, int B, int H, int W, int C, int pool, void* d_hi, void* d_lo, float* d_f32, float* dgamma,
                     float* dbeta, float* dbias, float* workspace, void* stream);
 
@@ -139,8 +140,8 @@ int jcm_colsum(const float* x, long M, int C, float* partial, float* out, void* 
 
 /* transpose of the up-sampling + 3-way average (main.py:58,67,69-70): d2 [B,H2,W2,C], d3 [B,H3,W3,C] (the full-resolution
  * bank's gradient is dmerged / 3, folded into jcm_bn_relu_bwd's dy_scale). */
-int jcm_upsample_avg3_bwd(const float* dmerged, int B, int H, int W, int H2, int W2, int H3, int W3, int C, float* d2, float* d3,
-                          void* stream);
+int jcm_upsample_avg3_bwd(const void* dmerged, int dm_bf16, int B, int H, int W, int H2, int W2, int H3, int W3, int C, float* d2, float* d3,
+                          void* stream);      /* dmerged: fp32, or bf16 when dm_bf16 */
 
 /* fp32 [M,C] -> bf16 planes [M,Cpad] with zero-padded channels. */
 int jcm_pad_planes(const float* x, long M, int C, int Cpad, void* hi, void* lo, void* stream);
@@ -235,6 +236,11 @@ int jcm_fma_peak(float* scratch, int blocks, int iters, int packed, double* flop
  * M tiles) or 64 (weight-gradient k-blocks).  out = [n_tiles, n_shapes, then x0, y0, box_w, box_h per tile]; returns the ints written,
  * 0 when no mixed plan beats `uniform_tiles`, < 0 (minus the size needed) when max_out is too small.  Host only, no GPU needed. */
 int jcm_debug_tile_plan(int H, int W, int cap, int exact_px, int max_shapes, int uniform_tiles, int* out, int max_out);
+
+/* Test / measurement switch of jcm_conv2d_wgrad (every variant computes the same values up to the summation order of the k-splits):
+ * bit 0 = single-CTA kernel instead of the CTA pair, bit 1 = uniform patch grid instead of the mixed-shape plan.  Returns the previous
+ * value.  Process-wide; the product path never calls it. */
+int jcm_debug_set_wgrad_variant(int variant);
 
 /* Naive direct convolution on the same operand planes - used only by tests to cross-check the tcgen05 kernel. */
 int jcm_debug_conv2d_naive(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,

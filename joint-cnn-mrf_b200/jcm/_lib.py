@@ -38,9 +38,9 @@ SIGNATURES = {
     'jcm_softmax_ce_bwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P]),
     'jcm_spatial_softmax_bwd': (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     'jcm_bn_relu_bwd_blocks': (_I, [_L, _I]),
-    'jcm_bn_relu_bwd': (_I, [_P, _I, _P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'jcm_bn_relu_bwd': (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     'jcm_colsum': (_I, [_P, _L, _I, _P, _P, _P]),
-    'jcm_upsample_avg3_bwd': (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    'jcm_upsample_avg3_bwd': (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     'jcm_pad_planes': (_I, [_P, _L, _I, _I, _P, _P, _P]),
     'jcm_conv2d_wgrad_workspace': (_L, [_I, _I, _I, _I, _I, _I, _I]),
     'jcm_conv2d_wgrad': (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
@@ -68,6 +68,7 @@ SIGNATURES = {
     'jcm_tower_mean': (_I, [_P, _I, _L, _P, _P]),
     'jcm_subsample2': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
     'jcm_bias_relu': (_I, [_P, _P, _L, _I, _I, _P, _P]),
+    'jcm_debug_set_wgrad_variant': (_I, [_I]),
     'jcm_debug_tile_plan': (_I, [_I, _I, _I, _I, _I, _I, _P, _I]),
     'jcm_fma_peak': (_I, [_P, _I, _I, _I, _P, _P]),
     'jcm_debug_conv2d_naive': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

@@ -1483,6 +1483,199 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_m_hi, const __grid_con
   }
 }
 
+// CTA-pair form (cta_group::2) of the weight-gradient kernel, for layers with an even number of 128-channel M tiles and N tiles of at
+// least 128 channels (conv3 .. conv5: 98 % of the weight-gradient FLOPs).  The two CTAs of a cluster own two adjacent M tiles of the
+// same (k-split, tap, N tile); each loads its own M-side box and HALF of the N-side box (block_n / 2 channels), the leader issues one
+// M = 256 MMA per 16 pixels that reads both CTAs' shared memory and accumulates into each CTA's own TMEM.  Per CTA and 64-pixel
+// k-block the operand traffic drops from 48 KB to 32 KB; barrier protocol as in conv_igemm_pair_kernel.
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_wgrad_pair_kernel(const __grid_constant__ CUtensorMap map_m_hi, const __grid_constant__ CUtensorMap map_m_lo,
+                       const __grid_constant__ CUtensorMap map_n_hi, const __grid_constant__ CUtensorMap map_n_lo,
+                       const __grid_constant__ WgradShapeMaps smaps, const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[kMaxStages]);
+  const uint32_t bar_tfull = smem_u32(&bars[2 * kMaxStages]);
+  const uint32_t bar_tempty = smem_u32(&bars[2 * kMaxStages + 2]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kMaxStages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_tfull + 8 * s, 1);
+      mbar_init(bar_tempty + 8 * s, 8);       // 4 epilogue warps of each CTA of the pair (used in the leader only)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int m_pairs = p.m_tiles >> 1;
+  const int tasks_per_split = p.taps * m_pairs * p.n_tiles;
+  const int total_tasks = p.splits * tasks_per_split;
+  const int task0 = blockIdx.x >> 1, task_step = gridDim.x >> 1;
+  const int patches_per_img = p.plan_n ? p.plan_n : p.tiles_x * p.tiles_y;
+  const int m_boxes = kTileM / p.kc_m;
+  const int n_boxes_half = (p.block_n / p.kc_n) >> 1;          // N-side channel blocks each CTA loads
+  const int m_box_bytes = kWgPix * p.kc_m * 2;
+  const int n_box_bytes = kWgPix * p.kc_n * 2;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int task = task0; task < total_tasks; task += task_step) {
+        const int split = task / tasks_per_split;
+        int r = task - split * tasks_per_split;
+        const int tap = r / (m_pairs * p.n_tiles);
+        r -= tap * (m_pairs * p.n_tiles);
+        const int mp = r / p.n_tiles, nt = r - mp * p.n_tiles;
+        const int dy = tap / p.kw - p.pad, dx = tap % p.kw - p.pad_x;
+        const int p0 = (int)((long)split * p.total_patches / p.splits);
+        const int p1 = (int)((long)(split + 1) * p.total_patches / p.splits);
+        int img = p0 / patches_per_img;
+        int q = p0 - img * patches_per_img;
+        int ty = p.plan_n ? 0 : q / p.tiles_x, tx = p.plan_n ? 0 : q - ty * p.tiles_x;
+        const int mblk0 = (2 * mp + (int)rank) * m_boxes;                                      // this CTA's M tile
+        const int nblk0 = nt * (p.block_n / p.kc_n) + (int)rank * n_boxes_half;               // this CTA's half of the N tile
+        const int sdx_m = p.shift_m * dx, sdy_m = p.shift_m * dy, sdx_n = p.shift_n * dx, sdy_n = p.shift_n * dy;
+        for (int patch = p0; patch < p1; ++patch) {
+          int x0 = tx * p.TW, y0 = ty * p.TH;
+          const void *pm = (const void*)&map_m_hi, *pn = (const void*)&map_n_hi;
+          if (p.plan_n) {
+            x0 = p.px0[q];
+            y0 = p.py0[q];
+            pm = (const void*)&smaps.m[p.pshape[q]];
+            pn = (const void*)&smaps.n[p.pshape[q]];
+          }
+          for (int term = 0; term < p.terms; ++term) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            const uint32_t sa = smem_base + stage * p.stage_bytes;
+            const uint32_t sb = sa + p.a_bytes;
+            const uint32_t fb = bar_full + 8 * stage;
+            if (rank == 0) mbar_expect_tx(fb, 2 * (p.a_bytes + p.b_bytes));      // both CTAs' boxes land on the leader's barrier
+            const void* mm = (term == 1) ? (const void*)&map_m_lo : pm;
+            const void* mn = (term == 2) ? (const void*)&map_n_lo : pn;
+            tma_load_5d_2sm(sa, mm, fb, 0, x0 + sdx_m, y0 + sdy_m, img, mblk0);
+            tma_load_5d_2sm(sb, mn, fb, 0, x0 + sdx_n, y0 + sdy_n, img, nblk0);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          if (p.plan_n) {
+            if (++q == p.plan_n) { q = 0; ++img; }
+          } else if (++tx == p.tiles_x) {
+            tx = 0;
+            if (++ty == p.tiles_y) { ty = 0; ++img; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0 && elect_one()) {
+      // D=f32, A=B=bf16, both MN-major (bits 15, 16), N = block_n, M = 256 (the pair's two 128-channel halves)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.block_n >> 3) << 17) |
+                             ((uint32_t)(256 >> 4) << 24);
+      const uint32_t n_row_bytes = p.kc_n * 2, m_row_bytes = p.kc_m * 2;
+      const uint32_t n_layout = (p.kc_n == 64) ? 2u : (p.kc_n == 32 ? 4u : 6u);
+      const uint32_t m_layout = (p.kc_m == 64) ? 2u : (p.kc_m == 32 ? 4u : 6u);
+      const uint64_t adesc_hi = (make_smem_desc(0, 8 * m_row_bytes, m_layout) & ~(((uint64_t)0x3FFF << 16) | 0x3FFF)) |
+                                ((uint64_t)((m_box_bytes >> 4) & 0x3FFF) << 16);
+      const uint64_t bdesc_hi = (make_smem_desc(0, 8 * n_row_bytes, n_layout) & ~(((uint64_t)0x3FFF << 16) | 0x3FFF)) |
+                                ((uint64_t)((n_box_bytes >> 4) & 0x3FFF) << 16);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int task = task0; task < total_tasks; task += task_step) {
+        const int split = task / tasks_per_split;
+        const int p0 = (int)((long)split * p.total_patches / p.splits);
+        const int p1 = (int)((long)(split + 1) * p.total_patches / p.splits);
+        const int num_kb = (p1 - p0) * p.terms;
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * p.stage_bytes;
+          const uint32_t sb = sa + p.a_bytes;
+#pragma unroll
+          for (int k = 0; k < kWgPix / 16; ++k) {
+            const uint64_t adesc = adesc_hi | (uint64_t)(((sa + k * 16 * m_row_bytes) >> 4) & 0x3FFF);
+            const uint64_t bdesc = bdesc_hi | (uint64_t)(((sb + k * 16 * n_row_bytes) >> 4) & 0x3FFF);
+            tc_mma_bf16_2sm(d_tmem, adesc, bdesc, idesc, (uint32_t)((kb | k) != 0));
+          }
+          tc_commit_2sm(bar_empty + 8 * stage);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_2sm(bar_tfull + 8 * acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs): own 128 accumulator rows -> partial[split][tap][m][n] =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int task = task0; task < total_tasks; task += task_step) {
+      const int split = task / tasks_per_split;
+      int r = task - split * tasks_per_split;
+      const int tap = r / (m_pairs * p.n_tiles);
+      r -= tap * (m_pairs * p.n_tiles);
+      const int mp = r / p.n_tiles, nt = r - mp * p.n_tiles;
+      float* orow = p.partial + (((long)split * p.taps + tap) * p.m_pad + (2 * mp + (int)rank) * kTileM + row) * p.n_pad + nt * p.block_n;
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t v[32];
+        tc_ld32(taddr0 + c0, v);
+        tc_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(orow + c0 + j) =
+              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(bar_tempty + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
 // dw[tap][ci][co] = sum_split partial[split][tap][m][n],  (m, n) = (ci, co) when the input provided M, else (co, ci).
 // 32 x 32 tiles through shared memory so that both the partial reads (n fastest) and the dw writes (co fastest) are coalesced
 // in either orientation.  grid = (ceil(Cout/32), ceil(Cin/32), taps), block = (32, 8).
@@ -1534,10 +1727,11 @@ void pick_patch64(int H, int W, int* TW, int* TH) {
 struct WgradPlan {
   int x_is_m, m_ch, n_ch, m_tiles, n_tiles, block_n, kc_n, kc_m, m_pad, n_pad, splits, TW, TH, tiles_x, tiles_y, total_patches;
   bool mixed;          // patches follow `tiles` (mixed-shape plan) instead of the uniform TW x TH grid
+  bool pair;           // CTA-pair kernel (cta_group::2): even number of M tiles, N tiles of 128 or 256 channels
   TilePlan tiles;
 };
 
-void plan_wgrad(int B, int H, int W, int Cin, int Gc, int ksize, int kw, bool allow_mixed, WgradPlan* pl) {
+void plan_wgrad(int B, int H, int W, int Cin, int Gc, int ksize, int kw, bool allow_mixed, bool allow_pair, WgradPlan* pl) {
   pl->x_is_m = Cin >= Gc;
   pl->m_ch = pl->x_is_m ? Cin : Gc;
   pl->n_ch = pl->x_is_m ? Gc : Cin;
@@ -1557,8 +1751,11 @@ void plan_wgrad(int B, int H, int W, int Cin, int Gc, int ksize, int kw, bool al
   // k-split: the persistent grid runs ceil(tasks / SMs) waves of tasks that each stream total_patches / splits k-blocks (+ an
   // epilogue worth ~6 k-blocks).  Pick the split count that minimises waves x task length: e.g. conv5 (648 tasks = 4.4 waves)
   // wastes 12 % of the last wave unsplit, 0.5 % with 5 splits; the partial sums cost one extra read in wgrad_reduce_kernel.
-  const int base = ksize * kw * pl->m_tiles * pl->n_tiles;
-  const int sms = jcm_num_sms();
+  pl->pair = allow_pair && (pl->m_tiles % 2) == 0 && (pl->block_n == 128 || pl->block_n == 256) && (pl->block_n / pl->kc_n) % 2 == 0 &&
+             jcm_num_sms() >= 2;
+  // work units and workers of the persistent loop: (tap, M tile, N tile) on every SM, or (tap, M-tile pair, N tile) on SM pairs
+  const int base = ksize * kw * (pl->pair ? pl->m_tiles / 2 : pl->m_tiles) * pl->n_tiles;
+  const int sms = pl->pair ? (jcm_num_sms() & ~1) / 2 : jcm_num_sms();
   int best_s = 1;
   double best_cost = 1e300;
   for (int s = 1; s <= 64; ++s) {
@@ -1574,14 +1771,27 @@ void plan_wgrad(int B, int H, int W, int Cin, int Gc, int ksize, int kw, bool al
 
 }  // namespace
 
+// Test / measurement switch of jcm_conv2d_wgrad (every variant computes the same values): bit 0 = single-CTA kernel instead of the
+// CTA pair, bit 1 = uniform patch grid instead of the mixed-shape plan.  Process-wide; the product never sets it.
+static int g_wgrad_variant = 0;
+extern "C" int jcm_debug_set_wgrad_variant(int variant) {
+  const int old = g_wgrad_variant;
+  g_wgrad_variant = variant & 3;
+  return old;
+}
+
 // bytes of fp32 partial sums jcm_conv2d_wgrad needs in `workspace`
 extern "C" long jcm_conv2d_wgrad_workspace(int B, int H, int W, int Cin, int Gc, int ksize, int kw) {
   if (kw <= 0) kw = ksize;
   // the larger of the two possible plans (the mixed-shape plan applies to the one-term form only and may pick another split count)
   WgradPlan pl, pl2;
-  plan_wgrad(B, H, W, Cin, Gc, ksize, kw, true, &pl);
-  plan_wgrad(B, H, W, Cin, Gc, ksize, kw, false, &pl2);
-  const int splits = pl.splits > pl2.splits ? pl.splits : pl2.splits;
+  plan_wgrad(B, H, W, Cin, Gc, ksize, kw, true, true, &pl);
+  plan_wgrad(B, H, W, Cin, Gc, ksize, kw, false, true, &pl2);
+  int splits = pl.splits > pl2.splits ? pl.splits : pl2.splits;
+  plan_wgrad(B, H, W, Cin, Gc, ksize, kw, true, false, &pl2);
+  if (pl2.splits > splits) splits = pl2.splits;
+  plan_wgrad(B, H, W, Cin, Gc, ksize, kw, false, false, &pl2);
+  if (pl2.splits > splits) splits = pl2.splits;
   return (long)splits * ksize * kw * pl.m_pad * pl.n_pad * (long)sizeof(float);
 }
 
@@ -1597,7 +1807,7 @@ extern "C" int jcm_conv2d_wgrad(const void* x_hi, const void* x_lo, const void* 
   JCM_CHECK_ARG(B > 0 && H > 0 && W > 0 && (ksize & 1) && (kw & 1), "jcm_conv2d_wgrad: bad shape");
   JCM_CHECK_ARG((Cin % 16) == 0 && (Gc % 16) == 0 && Cout <= Gc && Cout <= dw_cout_stride, "jcm_conv2d_wgrad: channel counts must be multiples of 16 (Cin=%d Gc=%d)", Cin, Gc);
   WgradPlan pl;
-  plan_wgrad(B, H, W, Cin, Gc, ksize, kw, x_lo == nullptr, &pl);
+  plan_wgrad(B, H, W, Cin, Gc, ksize, kw, x_lo == nullptr && !(g_wgrad_variant & 2), !(g_wgrad_variant & 1), &pl);
   JCM_CHECK_ARG(pl.n_ch % pl.block_n == 0, "jcm_conv2d_wgrad: N-side channel count %d must be <= 256 or a multiple of 256", pl.n_ch);
   if (workspace_bytes < jcm_conv2d_wgrad_workspace(B, H, W, Cin, Gc, ksize, kw)) {
     jcm_set_error("jcm_conv2d_wgrad: workspace too small");
@@ -1614,7 +1824,7 @@ extern "C" int jcm_conv2d_wgrad(const void* x_hi, const void* x_lo, const void* 
   p.splits = pl.splits; p.total_patches = pl.total_patches;
   p.terms = x_lo ? 3 : 1;
   p.a_bytes = kTileM * kWgPix * 2;
-  p.b_bytes = pl.block_n * kWgPix * 2;
+  p.b_bytes = (pl.pair ? pl.block_n / 2 : pl.block_n) * kWgPix * 2;      // pair: each CTA holds half of the N-side box
   p.stage_bytes = ((p.a_bytes + p.b_bytes + 1023) / 1024) * 1024;
   p.stages = (200 * 1024) / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
@@ -1655,24 +1865,33 @@ extern "C" int jcm_conv2d_wgrad(const void* x_hi, const void* x_lo, const void* 
   {
     uint64_t dims[5] = {(uint64_t)pl.kc_n, (uint64_t)W, (uint64_t)H, (uint64_t)B, (uint64_t)(n_c / pl.kc_n)};
     uint64_t str[4] = {(uint64_t)n_c * 2, (uint64_t)W * n_c * 2, (uint64_t)H * W * n_c * 2, (uint64_t)pl.kc_n * 2};
-    uint32_t box[5] = {(uint32_t)pl.kc_n, (uint32_t)pl.TW, (uint32_t)pl.TH, 1, (uint32_t)(pl.block_n / pl.kc_n)};
+    const uint32_t n_blocks = (uint32_t)(pl.block_n / pl.kc_n) / (pl.pair ? 2u : 1u);
+    uint32_t box[5] = {(uint32_t)pl.kc_n, (uint32_t)pl.TW, (uint32_t)pl.TH, 1, n_blocks};
     const CUtensorMapSwizzle swz = pl.kc_n == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (pl.kc_n == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     int rc = make_map(&mn_hi, n_hi, 5, dims, str, box, swz);
     if (rc) return rc;
     rc = make_map(&mn_lo, n_lo ? n_lo : n_hi, 5, dims, str, box, swz);
     if (rc) return rc;
     for (int i = 0; i < (pl.mixed ? pl.tiles.n_shapes : 0); ++i) {
-      uint32_t pbox[5] = {(uint32_t)pl.kc_n, pl.tiles.sw[i], pl.tiles.sh[i], 1, (uint32_t)(pl.block_n / pl.kc_n)};
+      uint32_t pbox[5] = {(uint32_t)pl.kc_n, pl.tiles.sw[i], pl.tiles.sh[i], 1, n_blocks};
       rc = make_map(&wsm.n[i], n_hi, 5, dims, str, pbox, swz);
       if (rc) return rc;
     }
   }
-  const int total_tasks = p.splits * p.taps * p.m_tiles * p.n_tiles;
-  int grid = jcm_num_sms();
-  if (grid > total_tasks) grid = total_tasks;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
-  JCM_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512));
-  conv_wgrad_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(mm_hi, mm_lo, mn_hi, mn_lo, wsm, p);
+  if (pl.pair) {
+    const int pair_tasks = p.splits * p.taps * (p.m_tiles / 2) * p.n_tiles;
+    int grid2 = jcm_num_sms() & ~1;
+    if (grid2 > 2 * pair_tasks) grid2 = 2 * pair_tasks;
+    JCM_CUDA(cudaFuncSetAttribute(conv_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512));
+    conv_wgrad_pair_kernel<<<grid2, kThreads, smem, (cudaStream_t)stream>>>(mm_hi, mm_lo, mn_hi, mn_lo, wsm, p);
+  } else {
+    const int total_tasks = p.splits * p.taps * p.m_tiles * p.n_tiles;
+    int grid = jcm_num_sms();
+    if (grid > total_tasks) grid = total_tasks;
+    JCM_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512));
+    conv_wgrad_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(mm_hi, mm_lo, mn_hi, mn_lo, wsm, p);
+  }
   JCM_LAUNCH_CHECK();
   wgrad_reduce_kernel<<<dim3(jcm_cdiv(Cout, 32), jcm_cdiv(Cin, 32), p.taps), dim3(32, 8), 0, (cudaStream_t)stream>>>(
       p.partial, p.splits, p.taps, p.m_pad, p.n_pad, Cin, Cout, dw_cout_stride, pl.x_is_m, dw);

@@ -47,7 +47,7 @@ def bn_relu_bwd(a, dout, ss, saved, dy_scale, pool, split, dgamma, dbeta, dbias,
     f32 = torch.empty((B, H, W, C), dtype=F32, device=a.device) if want_f32 else None
     nb = lib().jcm_bn_relu_bwd_blocks(B * Ho * Wo, C)
     ws = torch.empty(((4 * nb + 2) * C,), dtype=F32, device=a.device)
-    check(lib().jcm_bn_relu_bwd(_ptr(a), ops._req_act(a, 'a'), _ptr(dout), _ptr(ss[0]), _ptr(ss[1]), _ptr(saved[0]), _ptr(saved[1]), float(dy_scale), B, H, W, C,
+    check(lib().jcm_bn_relu_bwd(_ptr(a), ops._req_act(a, 'a'), _ptr(dout), ops._req_act(dout, 'dout'), _ptr(ss[0]), _ptr(ss[1]), _ptr(saved[0]), _ptr(saved[1]), float(dy_scale), B, H, W, C,
                                 int(pool), _ptr(planes.hi), _ptr(planes.lo), _ptr(f32), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), _ptr(ws),
                                 _stream()), 'jcm_bn_relu_bwd')
     return (planes, f32) if want_f32 else planes
@@ -66,7 +66,7 @@ def upsample_avg3_bwd(dm, shape2, shape3):
     B, H, W, C = dm.shape
     d2 = torch.empty((B, shape2[0], shape2[1], C), dtype=F32, device=dm.device)
     d3 = torch.empty((B, shape3[0], shape3[1], C), dtype=F32, device=dm.device)
-    check(lib().jcm_upsample_avg3_bwd(_ptr(dm), B, H, W, shape2[0], shape2[1], shape3[0], shape3[1], C, _ptr(d2), _ptr(d3), _stream()),
+    check(lib().jcm_upsample_avg3_bwd(_ptr(dm), ops._req_act(dm, 'dm'), B, H, W, shape2[0], shape2[1], shape3[0], shape3[1], C, _ptr(d2), _ptr(d3), _stream()),
           'jcm_upsample_avg3_bwd')
     return d2, d3
 
@@ -316,7 +316,9 @@ class Trainer:
         conv2d_wgrad(h5, gt6, dwz, zc, 1, alg_flops=2.0 * B * h5.shape[1] * h5.shape[2] * 81 * c5 * K)
         ops.unpack_tap_grad(dwz, 9, c5, K, g['conv6/weights'])
         colsum(d_logit, g['conv6/biases'])
-        dh = ops.conv2d_planes(gt6, ctx.packed('conv6', w6, 'taps_dgrad'), None, c5, 1, relu=False, alg_kdim=81 * K)
+        # data gradients (inputs of the BN / ReLU backward kernels): bf16 in the bf16 configuration, like the activations
+        dg_bf16 = lambda c: ctx.act_bf16 and c % 64 == 0
+        dh = ops.conv2d_planes(gt6, ctx.packed('conv6', w6, 'taps_dgrad'), None, c5, 1, relu=False, alg_kdim=81 * K, out_bf16=dg_bf16(c5))
 
         def bwd_layer(name, dout, dy_scale, pool, ksize, need_dx):
             xp, a, ss, st = saved.pop(name)
@@ -331,7 +333,7 @@ class Trainer:
             else:
                 conv2d_wgrad(xp, d_pre, g[name + '/weights'].view(ksize * ksize, cin, cout), cout, ksize)
             if need_dx:
-                return ops.conv2d_planes(d_pre, ctx.packed(name, w, 'dgrad'), None, cin, ksize, relu=False)
+                return ops.conv2d_planes(d_pre, ctx.packed(name, w, 'dgrad'), None, cin, ksize, relu=False, out_bf16=dg_bf16(cin))
             return None
 
         dmerged = bwd_layer('conv5', dh, 1.0, False, 9, True)

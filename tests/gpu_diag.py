@@ -517,17 +517,53 @@ def sec_smtc64():
     print('SMTC64 done', float(out.abs().max()))
 
 
+def _interleaved(fns, rounds=7, warm=2):
+    """median ms of each callable, timed round-robin so that every candidate sees the same thermal / power-cap state"""
+    for _ in range(warm):
+        for f in fns:
+            f()
+    torch.cuda.synchronize()
+    ts = [[] for _ in fns]
+    for _ in range(rounds):
+        for i, f in enumerate(fns):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            f()
+            e1.record()
+            torch.cuda.synchronize()
+            ts[i].append(e0.elapsed_time(e1))
+    return [float(np.median(t)) for t in ts]
+
+
 def sec_cta2():
     """N = 256 plain-mode layers: time per launch of the kernel variants (bit 0 single-CTA instead of the CTA pair, bit 1 uniform tile
-    grid instead of the mixed-shape plan, bit 2 no N-split tail), isolated launches at batch 64."""
+    grid instead of the mixed-shape plan, bit 2 no N-split tail), batch 64, variants interleaved launch by launch."""
+    variants = (0, 4, 6, 1, 7)
     for (B, H, W, Cin, Cout, k) in [(64, 60, 90, 512, 512, 9), (64, 60, 90, 256, 512, 9), (64, 60, 90, 512, 256, 9), (64, 30, 45, 256, 512, 9)]:
         xp = ops.Planes(torch.randn(B, H, W, Cin, device=dev).to(torch.bfloat16), None)
         wp = ops.Planes((torch.randn(k * k, Cout, Cin, device=dev) / np.sqrt(k * k * Cin)).to(torch.bfloat16), None)
         fl = 2.0 * B * H * W * k * k * Cin * Cout
-        for variant in (0, 4, 6, 1, 7):
-            best, med = timeit(lambda: ops.conv2d_planes(xp, wp, None, Cout, k, relu=True, out_bf16=True, variant=variant), n=5, warm=2)
-            print('CTA2 %dx%d Cin%d Cout%d k%d variant %d: %.3f ms best %.3f median = %.0f TFLOP/s' % (H, W, Cin, Cout, k, variant, best, med, fl / med / 1e9),
-                  flush=True)
+        med = _interleaved([(lambda v=v: ops.conv2d_planes(xp, wp, None, Cout, k, relu=True, out_bf16=True, variant=v)) for v in variants])
+        print('IGEMM %dx%d Cin%d Cout%d k%d: ' % (H, W, Cin, Cout, k) + '  '.join('v%d %.3f ms (%.0f TF)' % (v, m, fl / m / 1e9) for v, m in zip(variants, med)),
+              flush=True)
+
+
+def sec_wgpair():
+    """weight gradient: CTA-pair kernel / mixed-shape patch plan variants (bit 0 single-CTA, bit 1 uniform grid), batch 64, interleaved"""
+    from jcm import train as jt
+    for (B, H, W, Cin, Cout, k) in [(64, 60, 90, 512, 512, 9), (64, 60, 90, 256, 512, 9), (64, 30, 45, 256, 512, 9), (64, 60, 90, 128, 256, 5)]:
+        xp = ops.Planes(torch.randn(B, H, W, Cin, device=dev).to(torch.bfloat16), None)
+        gp = ops.Planes(torch.randn(B, H, W, Cout, device=dev).to(torch.bfloat16), None)
+        dw = torch.empty(k * k, Cin, Cout, device=dev)
+        fl = 2.0 * B * H * W * k * k * Cin * Cout
+
+        def run(v):
+            jcm.lib().jcm_debug_set_wgrad_variant(v)
+            jt.conv2d_wgrad(xp, gp, dw, Cout, k)
+        med = _interleaved([(lambda v=v: run(v)) for v in (0, 1, 2, 3)])
+        jcm.lib().jcm_debug_set_wgrad_variant(0)
+        print('WGRAD %dx%d Cin%d Cout%d k%d: ' % (H, W, Cin, Cout, k) + '  '.join('v%d %.3f ms (%.0f TF)' % (v, m, fl / m / 1e9) for v, m in zip((0, 1, 2, 3), med)),
+              flush=True)
 
 
 if __name__ == '__main__':

@@ -107,6 +107,8 @@ def test_bn_relu_pool_bwd(jcm, jtrain, shape, pool, split):
     if pool:
         out = orc.max_pool_layer(out)
     dout = torch.randn(out.shape, generator=g)
+    if act_bf16:
+        dout = bf16r(dout)               # the bf16 configuration feeds the data-gradient convolution's bf16 output
     dy_scale = 1.0 / 3.0
     (out * dout.double() * dy_scale).sum().backward()
 
@@ -116,7 +118,8 @@ def test_bn_relu_pool_bwd(jcm, jtrain, shape, pool, split):
     mm, mv = torch.zeros(C, device='cuda'), torch.ones(C, device='cuda')
     ss, st = jcm.ops.bn_scale_shift(a, gamma.cuda(), beta.cuda(), mm, mv, train=True, save=True)
     dgamma, dbeta, dbias = (torch.empty(C, device='cuda') for _ in range(3))
-    planes, f32 = jtrain.bn_relu_bwd(a, dout.cuda(), ss, st, dy_scale, pool, split, dgamma, dbeta, dbias, want_f32=True)
+    dout_g = dout.cuda().to(torch.bfloat16) if act_bf16 else dout.cuda()
+    planes, f32 = jtrain.bn_relu_bwd(a, dout_g, ss, st, dy_scale, pool, split, dgamma, dbeta, dbias, want_f32=True)
     assert rel(f32, pre64.grad) < 2e-5
     rec = planes.hi.float() + (planes.lo.float() if split else 0)
     assert rel(rec, pre64.grad) < (2e-5 if split else 5e-3)
@@ -136,6 +139,13 @@ def test_upsample_avg3_bwd(jcm, jtrain):
     d2, d3 = jtrain.upsample_avg3_bwd(dm.cuda(), (30, 45), (15, 23))
     assert rel(d2, a2.grad) < 1e-5
     assert rel(d3, a3.grad) < 1e-5
+    # bf16 dm (the bf16 configuration's conv5 data gradient): identical arithmetic on the rounded input
+    dmb = bf16r(dm)
+    a2b = a2.detach().clone().requires_grad_(True)
+    a3b = a3.detach().clone().requires_grad_(True)
+    (((orc.resize_images(a2b, 60, 90) + orc.resize_images(a3b, 60, 90)) / 3) * dmb.double()).sum().backward()
+    d2b, d3b = jtrain.upsample_avg3_bwd(dmb.cuda().to(torch.bfloat16), (30, 45), (15, 23))
+    assert rel(d2b, a2b.grad) < 1e-5 and rel(d3b, a3b.grad) < 1e-5
 
 
 # ------------------------------------------------------------------------------------------------ conv gradients

@@ -241,6 +241,36 @@ def test_conv_pair_plan_tail_variants_are_bit_identical(jcm, case, split):
     assert torch.equal(jcm.ops.conv2d_planes(xp, wp, b.cuda(), Cout, k, relu=True), base)   # the default entry point
 
 
+@pytest.mark.parametrize('case', [(2, 60, 90, 256, 512, 3), (1, 30, 45, 512, 512, 3), (3, 60, 90, 128, 256, 3), (2, 16, 24, 256, 256, 5),
+                                  (4, 60, 90, 512, 128, 1)])
+@pytest.mark.parametrize('split', [False, True])
+def test_wgrad_pair_and_plan_variants_agree(jcm, jtrain, case, split):
+    """Weight gradient: CTA-pair kernel (even M-tile count, N tiles >= 128) and mixed-shape patch plan against the single-CTA kernel on
+    the uniform grid and against the oracle.  The variants differ only in how the pixel sum is split, so they agree to fp32
+    summation-order noise."""
+    B, H, W, Cin, Cout, k = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, H, W, Cin, generator=g)
+    dy = torch.randn(B, H, W, Cout, generator=g)
+    r = (lambda t: t) if split else (lambda t: t.to(torch.bfloat16).float())
+    w64 = torch.zeros(k, k, Cin, Cout, dtype=torch.float64, requires_grad=True)
+    (orc.conv2d(r(x).double(), w64, 1) * r(dy).double()).sum().backward()
+    xp = jcm.ops.split_planes(x.cuda(), split)
+    gp = jcm.ops.split_planes(dy.cuda(), split)
+    outs = []
+    try:
+        for variant in (0, 1, 2, 3):
+            jcm.lib().jcm_debug_set_wgrad_variant(variant)
+            dw = torch.empty(k * k, Cin, Cout, device='cuda')
+            jtrain.conv2d_wgrad(xp, gp, dw, Cout, k)
+            outs.append(dw)
+    finally:
+        jcm.lib().jcm_debug_set_wgrad_variant(0)
+    assert rel(outs[0].view(k, k, Cin, Cout), w64.grad) < 2e-4
+    for v, o in enumerate(outs[1:], 1):
+        assert rel(o, outs[0]) < 1e-5, v
+
+
 def test_tile_plan_covers_every_pixel_once(jcm):
     """csrc/tiling.cu through jcm_debug_tile_plan: the plans the kernels use for the part detector's map sizes."""
     import ctypes
