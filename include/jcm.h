@@ -45,6 +45,16 @@ int jcm_prep_input(const float* x, int B, int H, int W, void* full_hi, void* ful
 int jcm_pack_weights(const float* w, int ksize, int Cin, int Cout, int Opad, int Ipad, int transpose, void* out_hi,
                      void* out_lo, void* stream);
 
+/* Both layouts of up to 16 conv kernels in ONE launch (the re-pack after an optimizer step): layer i reads w [k,k,Cin,Cout] once and
+ * writes fwd = [k*k][Cout][Cin] (as jcm_pack_weights transpose 0) and dgrad = [k*k][Cin][Cout] (as transpose 1).  Cin, Cout multiples
+ * of 32 that need no padding (<= 256 or a multiple of 256).  lo pointers NULL: plain bf16.  layers: HOST array. */
+typedef struct {
+  const float* w;
+  void *fwd_hi, *fwd_lo, *dgrad_hi, *dgrad_lo;
+  int ksize, Cin, Cout;
+} jcm_pack_desc;
+int jcm_pack_weights_batch(const jcm_pack_desc* layers, int n, void* stream);
+
 /* conv1_* kernels [5,5,3,Cout] -> [3][Cout][64] matching jcm_prep_input's channel order (5x5 s2 SAME == 3x1 s1 over x-folded s2d). */
 int jcm_pack_weights_s2d(const float* w, int Cout, void* out_hi, void* out_lo, void* stream);
 

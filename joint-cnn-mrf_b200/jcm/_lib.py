@@ -20,6 +20,7 @@ SIGNATURES = {
     'jcm_launch_count': (_L, []),
     'jcm_prep_input': (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     'jcm_pack_weights': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    'jcm_pack_weights_batch': (_I, [_P, _I, _P]),
     'jcm_pack_weights_s2d': (_I, [_P, _I, _P, _P, _P]),
     'jcm_split_planes': (_I, [_P, _L, _P, _P, _P]),
     'jcm_conv2d_fwd': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

@@ -75,7 +75,7 @@ struct ConvParams {
   uint8_t px0[kPlanMaxTiles], py0[kPlanMaxTiles], pshape[kPlanMaxTiles];
   uint8_t psw[4], psh[4];
   // N-split tail: the last `tail_tiles` (M, N) tiles - the partial last wave of the persistent grid - run as tail_split sub-tiles of
-  // block_n / tail_split output channels each, so that the wave costs 1 / tail_split of a full round instead of a whole one
+  // block_n / tail_split output channels each on twice as many SMs (set only when the halves fit ONE sub-round, see the launcher)
   int tail_tiles, tail_split;
   const float* bias;
   float* y;
@@ -1163,11 +1163,10 @@ int jcm_conv_igemm_ex(const ConvExArgs& a) {
   if (!(a.variant & 4) && p.terms == 1 && !p.halo && p.grp == 0 && p.tma_store && p.block_n == 256 && p.nacc == 1 && !p.mma_split_n && units > workers &&
       units % workers != 0) {
     const int rem = units % workers;
-    double best = 1.0;
-    for (int sp = 2; sp <= 4; sp *= 2) {
-      const double cost = (double)jcm_cdiv(rem * sp, workers) / sp;
-      if (cost < best - 1e-9) { best = cost; p.tail_split = sp; }
-    }
+    // Measured (tests/gpu_diag.py cta2, profiles/r02/diag_variants2.txt): a quarter tile (N = 64) costs far more than a quarter of a
+    // full tile - the per-k-block handshake and the A-operand reads do not shrink with N - so splitting pays only as ONE sub-round
+    // of half tiles (N = 128): the partial wave then costs ~0.6 of a round instead of 1.  Anything else is left unsplit.
+    if (2 * rem <= workers) p.tail_split = 2;
     if (p.tail_split > 1) p.tail_tiles = rem;
   }
   p.relu = relu;
@@ -1686,25 +1685,34 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int split
   const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 32;
   const long split_stride = (long)taps * m_pad * n_pad;
   const float* base = partial + (long)tap * m_pad * n_pad;
+  // four rows per thread, the split loop unrolled: 16 independent loads in flight (the rolled one-row-at-a-time version ran at a
+  // quarter of HBM speed: 0.83 ms per step for 1.2 GB); the additions of one element keep their split order
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  long off[4];
+  bool ok[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int r = threadIdx.y + 8 * j;
+    // x_is_m: rows m = ci, columns n = co (already co-fastest).  else: rows m = co, columns n = ci (read ci-fastest, transpose below)
+    const int m = (x_is_m ? ci0 : co0) + r, n = (x_is_m ? co0 : ci0) + threadIdx.x;
+    ok[j] = x_is_m ? (m < Cin && n < Cout) : (m < Cout && n < Cin);
+    off[j] = (long)m * n_pad + n;
+  }
+#pragma unroll 4
+  for (int sp = 0; sp < splits; ++sp) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (ok[j]) s[j] += base[sp * split_stride + off[j]];
+  }
   if (x_is_m) {
-    // rows m = ci, columns n = co: already co-fastest, no transpose needed
-    for (int r = threadIdx.y; r < 32; r += 8) {
-      const int ci = ci0 + r, co = co0 + threadIdx.x;
-      if (ci < Cin && co < Cout) {
-        float s = 0.f;
-        for (int sp = 0; sp < splits; ++sp) s += base[sp * split_stride + (long)ci * n_pad + co];
-        dw[((long)tap * Cin + ci) * dw_cout_stride + co] = s;
-      }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ci = ci0 + threadIdx.y + 8 * j, co = co0 + threadIdx.x;
+      if (ok[j]) dw[((long)tap * Cin + ci) * dw_cout_stride + co] = s[j];
     }
   } else {
-    // rows m = co, columns n = ci: read ci-fastest, transpose, write co-fastest
-    for (int r = threadIdx.y; r < 32; r += 8) {
-      const int co = co0 + r, ci = ci0 + threadIdx.x;
-      float s = 0.f;
-      if (ci < Cin && co < Cout)
-        for (int sp = 0; sp < splits; ++sp) s += base[sp * split_stride + (long)co * n_pad + ci];
-      tile[r][threadIdx.x] = s;
-    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tile[threadIdx.y + 8 * j][threadIdx.x] = s[j];
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += 8) {
       const int ci = ci0 + r, co = co0 + threadIdx.x;

@@ -32,6 +32,12 @@ def params_updated():
     _PARAM_EPOCH += 1
 
 
+def register_packed(w, kind, split, planes):
+    """Stores externally packed operand planes of `w` as current (Trainer.apply re-packs every kernel in one launch right after the
+    optimizer step, into planes that stay resident)."""
+    _PACKS[(w.data_ptr(), tuple(w.shape), kind, split)] = (weakref.ref(w), w._version, _PARAM_EPOCH, planes)
+
+
 def _purge_packs():
     for k in [k for k, e in _PACKS.items() if e[0]() is None]:
         del _PACKS[k]

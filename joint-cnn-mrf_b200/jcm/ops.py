@@ -152,6 +152,36 @@ def pack_weights(w, split, transpose=False):
     return out
 
 
+class _PackDesc(ctypes.Structure):
+    _fields_ = [('w', ctypes.c_void_p), ('fwd_hi', ctypes.c_void_p), ('fwd_lo', ctypes.c_void_p), ('dgrad_hi', ctypes.c_void_p),
+                ('dgrad_lo', ctypes.c_void_p), ('ksize', ctypes.c_int), ('Cin', ctypes.c_int), ('Cout', ctypes.c_int)]
+
+
+def batch_packable(w):
+    """True when jcm_pack_weights_batch can write both layouts of this kernel without padding."""
+    k, k2, cin, cout = w.shape
+    ok = lambda c: c % 32 == 0 and (c <= 256 or c % 256 == 0)
+    return k == k2 and ok(cin) and ok(cout)
+
+
+def pack_weights_batch(entries, split):
+    """entries: list of (w fp32 HWIO, fwd Planes [k*k,Cout,Cin], dgrad Planes [k*k,Cin,Cout]); re-packs all of them in place with
+    launches of up to 16 layers."""
+    for i in range(0, len(entries), 16):
+        chunk = entries[i:i + 16]
+        arr = (_PackDesc * len(chunk))()
+        for d, (w, fwd, dg) in zip(arr, chunk):
+            _req(w, F32, 'w')
+            k, _, cin, cout = w.shape
+            if tuple(fwd.shape) != (k * k, cout, cin) or tuple(dg.shape) != (k * k, cin, cout):
+                raise ValueError('packed planes %s / %s do not match kernel %s' % (fwd.shape, dg.shape, tuple(w.shape)))
+            d.w, d.fwd_hi, d.dgrad_hi = w.data_ptr(), fwd.hi.data_ptr(), dg.hi.data_ptr()
+            d.fwd_lo = fwd.lo.data_ptr() if split else None
+            d.dgrad_lo = dg.lo.data_ptr() if split else None
+            d.ksize, d.Cin, d.Cout = k, cin, cout
+        check(lib().jcm_pack_weights_batch(arr, len(chunk), _stream()), 'jcm_pack_weights_batch')
+
+
 def pack_weights_s2d(w, split):
     """conv1 kernels [5,5,3,Cout] -> [3, Cout, 64] (use with ksize = S2D_KSIZE)."""
     _req(w, F32, 'w')

@@ -182,6 +182,7 @@ class Trainer:
             self.buckets = [[(first[0], self.n_decay)], [(first[1], first[0])], [(first[2], first[1])], [(0, first[2]), (self.n_decay, n)]]
         else:
             self.buckets = [[(self.opt_lo, n)]]
+        self._packs = None          # resident packed operand planes of the regular conv kernels (filled at the first apply())
         self._pending = []          # async all-reduce handles of this step
         self._started = set()       # buckets whose all-reduce has been issued this step
         self._comm_stream = None
@@ -425,8 +426,24 @@ class Trainer:
         else:
             check(lib().jcm_clip_adam(ptr(self.flat), ptr(self.grads), ptr(self.m), ptr(self.v), n, _ptr(self.stats), CLIP_NORM,
                                       lr, 0.9, 0.0, 0.0, 1, _stream()), 'jcm_clip_adam')
-        from .graph import params_updated
+        from .graph import params_updated, register_packed
         params_updated()    # the kernels changed the weights through raw pointers: packed operand planes are stale in every Context
+        # ... and are re-packed right here, all regular kernels in one launch into resident planes (both layouts from one read of the
+        # fp32 master copy); the three conv1_* and conv6 (special layouts, 0.1 % of the weights) re-pack lazily at their next use
+        if self.flat.is_cuda and self.ctx.train_pd:
+            if self._packs is None:
+                self._packs = []
+                for k in self.p:
+                    w = self.p[k]
+                    if k.endswith('/weights') and k != 'conv6/weights' and ops.batch_packable(w):
+                        kk, _, cin, cout = w.shape
+                        self._packs.append((w, ops._new_planes((kk * kk, cout, cin), w.device, self.ctx.split),
+                                            ops._new_planes((kk * kk, cin, cout), w.device, self.ctx.split)))
+            if self._packs:
+                ops.pack_weights_batch(self._packs, self.ctx.split)
+                for w, fwd, dg in self._packs:
+                    register_packed(w, 'fwd', self.ctx.split, fwd)
+                    register_packed(w, 'dgrad', self.ctx.split, dg)
 
     def step(self, x, y):
         out = self.forward_backward(x, y)

@@ -271,6 +271,45 @@ def test_wgrad_pair_and_plan_variants_agree(jcm, jtrain, case, split):
         assert rel(o, outs[0]) < 1e-5, v
 
 
+@pytest.mark.parametrize('split', [False, True])
+def test_batched_weight_repack_equals_the_per_layer_pack(jcm, split):
+    """jcm_pack_weights_batch (one launch, both layouts of every regular kernel; what Trainer.apply runs after the optimizer step)
+    writes exactly the planes of jcm_pack_weights."""
+    g = torch.Generator().manual_seed(3)
+    ws = [torch.randn(k, k, cin, cout, generator=g).cuda() for (k, cin, cout) in [(5, 64, 128), (3, 32, 32), (9, 256, 512), (1, 512, 256)]]
+    assert all(jcm.ops.batch_packable(w) for w in ws) and not jcm.ops.batch_packable(torch.zeros(5, 5, 3, 64)) \
+        and not jcm.ops.batch_packable(torch.zeros(9, 9, 512, 7))
+    entries = [(w, jcm.ops._new_planes((w.shape[0] ** 2, w.shape[3], w.shape[2]), 'cuda', split),
+                jcm.ops._new_planes((w.shape[0] ** 2, w.shape[2], w.shape[3]), 'cuda', split)) for w in ws]
+    jcm.ops.pack_weights_batch(entries, split)
+    for w, fwd, dg in entries:
+        rf, rd = jcm.ops.pack_weights(w, split), jcm.ops.pack_weights(w, split, transpose=True)
+        assert torch.equal(fwd.hi, rf.hi) and torch.equal(dg.hi, rd.hi)
+        if split:
+            assert torch.equal(fwd.lo, rf.lo) and torch.equal(dg.lo, rd.lo)
+
+
+def test_trainer_keeps_packed_weights_resident(jcm, jtrain):
+    """After Trainer.apply every Context finds the re-packed planes of the regular kernels (no lazy re-pack), and they hold the
+    UPDATED weights."""
+    K = 3
+    gen = torch.Generator().manual_seed(2)
+    names = orc.JOINT_NAMES[:K] + ['torso']
+    p = jcm.init_part_detector(K, gen)
+    sm = jcm.PairwiseParams.from_distribution(orc.synthetic_pairwise(names, K, 8, 12, np.random.default_rng(2)), names, K, 8, 12)
+    ctx = jcm.Context(n_joints=K, joint_names=names, flag_train=True, precision='bf16')
+    tr = jtrain.Trainer(p, sm, ctx, lr=1e-2)
+    x = torch.rand(1, 64, 96, 3, generator=gen).cuda()
+    y = torch.from_numpy(orc.synthetic_labels(1, 8, 12, K + 1, np.random.default_rng(2))).cuda()
+    tr.step(x, y)
+    w = tr.p['conv5/weights']
+    other = jcm.Context(n_joints=K, joint_names=names, flag_train=False, precision='bf16')
+    for kind in ('fwd', 'dgrad'):
+        planes = other.packed('conv5', w, kind)
+        assert any(planes is e[1] or planes is e[2] for e in tr._packs)
+        assert torch.equal(planes.hi, jcm.ops.pack_weights(w, False, transpose=(kind == 'dgrad')).hi)
+
+
 def test_tile_plan_covers_every_pixel_once(jcm):
     """csrc/tiling.cu through jcm_debug_tile_plan: the plans the kernels use for the part detector's map sizes."""
     import ctypes
