@@ -154,11 +154,19 @@ class Trainer:
         self.n_updates_total = n_updates_total
         dev = sm.energies.device
         # conv kernels first (the weight-decayed prefix), ordered by when the backward pass finishes them - LAST finished first - so
-        # that the gradient all-reduce can start on the tail of the prefix while earlier layers are still being differentiated:
-        #   [quarter bank | half bank | full bank | conv5 conv6]  ->  buckets 3, 2, 1, 0 (bucket 3 also carries everything else)
+        # that the gradient all-reduce can be issued in contiguous buckets while earlier layers are still being differentiated.  The
+        # backward pass finishes conv6, conv5, then bank by bank (full, half, quarter) conv4, conv3, conv2, conv1; conv5 (21 M) and the
+        # three conv4_* (10.6 M each) hold 94 % of the parameters, so each of them closes a bucket:
+        #   [q_small | conv4_q | h_small | conv4_h | f_small | conv4_f | conv5 conv6]      (x_small = conv1_x, conv2_x, conv3_x)
+        #    bucket 4   \--- bucket 3 ---/ \--- bucket 2 ---/  bucket 1   bucket 0         (bucket 4 also carries everything else)
         def bank_of(k):
             return 3 if 'quarterres' in k else 2 if 'halfres' in k else 1 if 'fullres' in k else 0
-        names_w = sorted([k for k in p if k.endswith('/weights')], key=lambda k: -bank_of(k))     # stable: spec order inside a bank
+
+        def slot(k):      # position in the layout above, left to right
+            if bank_of(k) == 0:
+                return 6
+            return {3: 0, 2: 2, 1: 4}[bank_of(k)] + (1 if k.startswith('conv4_') else 0)
+        names_w = sorted([k for k in p if k.endswith('/weights')], key=slot)     # stable: spec order inside a slot
         names_rest = [k for k in p if not k.endswith('/weights') and 'moving_' not in k]
         entries = [(k, p[k]) for k in names_w]
         self.n_decay = sum(t.numel() for _, t in entries)
@@ -175,13 +183,17 @@ class Trainer:
         # trainable range of the flat buffer: everything, or (train_pd=False, main.py:129,147,153,443: the part detector's conv
         # kernels, biases and BN gamma/beta are created with trainable=False) only the spatial model's variables
         self.opt_lo = 0 if ctx.train_pd else offs['sm/energies']
-        # gradient buckets (element ranges of the flat buffer): 0 = conv5+conv6 kernels, 1 = full bank, 2 = half bank,
-        # 3 = quarter bank kernels + every other variable (two ranges)
+        # gradient buckets (element ranges of the flat buffer), in the order the backward pass completes them
         if ctx.train_pd:
-            first = {b: min(offs[k] for k in names_w if bank_of(k) == b) for b in range(4)}
-            self.buckets = [[(first[0], self.n_decay)], [(first[1], first[0])], [(first[2], first[1])], [(0, first[2]), (self.n_decay, n)]]
+            start = {sl: min(offs[k] for k in names_w if slot(k) == sl) for sl in range(7) if any(slot(k) == sl for k in names_w)}
+            edge = lambda sl: start.get(sl, min([v for s2, v in start.items() if s2 > sl] + [self.n_decay]))
+            self.buckets = [[(edge(6), self.n_decay)], [(edge(5), edge(6))], [(edge(3), edge(5))], [(edge(1), edge(3))],
+                            [(0, edge(1)), (self.n_decay, n)]]
+            # the layer whose weight gradient completes each bucket (Trainer.forward_backward issues the all-reduce right after it)
+            self.bucket_after = {'conv5': 0, 'conv4_fullres': 1, 'conv4_halfres': 2, 'conv4_quarterres': 3}
         else:
             self.buckets = [[(self.opt_lo, n)]]
+            self.bucket_after = {}
         self._packs = None          # resident packed operand planes of the regular conv kernels (filled at the first apply())
         self._pending = []          # async all-reduce handles of this step
         self._started = set()       # buckets whose all-reduce has been issued this step
@@ -333,12 +345,13 @@ class Trainer:
                 unpack_s2d_grad(g9, g[name + '/weights'])
             else:
                 conv2d_wgrad(xp, d_pre, g[name + '/weights'].view(ksize * ksize, cin, cout), cout, ksize)
+            if name in self.bucket_after:
+                self.reduce_bucket(self.bucket_after[name])       # this kernel's gradient closes a bucket: overlap its all-reduce
             if need_dx:
                 return ops.conv2d_planes(d_pre, ctx.packed(name, w, 'dgrad'), None, cin, ksize, relu=False, out_bf16=dg_bf16(cin))
             return None
 
         dmerged = bwd_layer('conv5', dh, 1.0, False, 9, True)
-        self.reduce_bucket(0)                                     # conv5 + conv6 kernels are final: overlap their all-reduce
         a4_2, a4_3 = outs[1][0], outs[2][0]
         d2, d3 = upsample_avg3_bwd(dmerged, a4_2.shape[1:3], a4_3.shape[1:3])
         for sfx, dout, sc in zip(sfxs, (dmerged, d2, d3), (1.0 / 3.0, 1.0, 1.0)):
@@ -346,8 +359,6 @@ class Trainer:
             d = bwd_layer('conv3_' + sfx, d, 1.0, False, 5, True)
             d = bwd_layer('conv2_' + sfx, d, 1.0, True, 5, True)
             bwd_layer('conv1_' + sfx, d, 1.0, True, 5, False)
-            if sfx != 'quarterres':
-                self.reduce_bucket(1 if sfx == 'fullres' else 2)  # this bank's kernels are final
         return {'loss_pd': loss_pd, 'loss_sm': loss_sm, 'logit_pd': logit_pd}
 
     # ---------------------------------------------------------------------------------------- optimizer
@@ -376,7 +387,7 @@ class Trainer:
 
     def reduce_gradients(self):
         """The one exchange step of the path (main.py:243-267 averages tower gradients on the CPU): an all-reduce (sum) of the flat
-        gradient buffer over NCCL / NVLink, issued in four buckets as the backward pass completes them; the division by the
+        gradient buffer over NCCL / NVLink, issued in five buckets as the backward pass completes them; the division by the
         replica count is folded into jcm_grad_prepare.  Buckets not started yet are started here; then all are awaited."""
         if self.world_size > 1:
             for b in range(len(self.buckets)):
