@@ -81,13 +81,13 @@ struct BnBwdArgs {
   float* partial;          // [grid][2][C]
 };
 
-template <int PASS, int VEC>
-__global__ void bn_relu_bwd_kernel(BnBwdArgs p) {
+template <int PASS, int VEC, int POOL>
+__global__ void __launch_bounds__(kThreads, 2) bn_relu_bwd_kernel(BnBwdArgs p) {
   extern __shared__ float sh[];  // [kThreads][2 * VEC]
   const int CG = p.C / VEC;      // channel groups of VEC channels (VEC = 8 for bf16-stored activations: 16-byte loads)
   const int lanes = kThreads / CG;
   const int g = threadIdx.x % CG, rl = threadIdx.x / CG;
-  const int Ho = p.pool ? (p.H + 1) / 2 : p.H, Wo = p.pool ? (p.W + 1) / 2 : p.W;
+  const int Ho = POOL ? (p.H + 1) / 2 : p.H, Wo = POOL ? (p.W + 1) / 2 : p.W;
   const long M = (long)p.B * Ho * Wo;
   const long per_blk = (M + gridDim.x - 1) / gridDim.x;
   const long r0 = blockIdx.x * per_blk;
@@ -110,29 +110,53 @@ __global__ void bn_relu_bwd_kernel(BnBwdArgs p) {
 #pragma unroll
       for (int c = 0; c < VEC; ++c) { m_dy[c] *= p.inv_count; m_dyx[c] *= p.inv_count; }
     }
-    if (!p.pool) {
-      // two rows in flight per thread: these loops are latency- rather than bandwidth-bound with one
-#pragma unroll 2
-      for (long r = r0 + rl; r < r1; r += lanes) {
-        float dv[VEC];
-        load_act_vec<VEC>(p.dout, r * p.C + (long)g * VEC, p.dout_bf16, dv);
+    if (!POOL) {
+      // The loop body needs three per-channel constants, not six: with xhat = (a - mean) * rstd
+      //   PASS 0:  sum dy * xhat            = sum dy * (a - mean) * rstd                  -> (mean, rstd)
+      //   PASS 1:  scale * (dy - m_dy - xhat * m_dyx) = ca * dy + cb + cc * a             -> (ca, cb, cc)
+      // and four rows are in flight per thread (all loads first): at 126 registers the first version kept two blocks of 8 warps with
+      // two 32-byte loads each per SM - a third of the bytes in flight that HBM latency x bandwidth asks for.
+      float ca[VEC], cb[VEC], cc[VEC];
 #pragma unroll
-        for (int c = 0; c < VEC; ++c) dv[c] *= p.dy_scale;
-        float av[VEC], o[VEC];
-        load_act_vec<VEC>(p.a, r * p.C + (long)g * VEC, p.a_bf16, av);
+      for (int c = 0; c < VEC; ++c) {
+        ca[c] = scv[c] * p.dy_scale;
+        cc[c] = -scv[c] * m_dyx[c] * rsv[c];
+        cb[c] = -scv[c] * m_dy[c] - cc[c] * muv[c];
+        if (PASS == 0) { ca[c] = muv[c]; cb[c] = rsv[c] * p.dy_scale; }      // PASS 0 reuses the slots: ca = mean, cb = rstd * dy_scale
+      }
+      constexpr int R = (PASS == 1 && VEC == 8) ? 3 : 4;      // rows in flight (PASS 1 with 8 channels also holds the output row: 3 fit 128 registers)
+      for (long r = r0 + rl; r < r1; r += (long)R * lanes) {
+        float dv[R][VEC], av[R][VEC];
 #pragma unroll
-        for (int c = 0; c < VEC; ++c) {
-          const float xh = (av[c] - muv[c]) * rsv[c];
-          if (PASS == 0) {
-            s0[c] += dv[c];
-            s1[c] += dv[c] * xh;
-          } else {
-            const float da = scv[c] * (dv[c] - m_dy[c] - xh * m_dyx[c]);
-            o[c] = av[c] > 0.f ? da : 0.f;
-            s0[c] += o[c];
+        for (int i = 0; i < R; ++i) {
+          const long rr = r + (long)i * lanes;
+          if (rr < r1) {
+            load_act_vec<VEC>(p.dout, rr * p.C + (long)g * VEC, p.dout_bf16, dv[i]);
+            load_act_vec<VEC>(p.a, rr * p.C + (long)g * VEC, p.a_bf16, av[i]);
           }
         }
-        if (PASS == 1) store_planes_vec<VEC>(p.hi, p.lo, p.d_f32, r * p.C + (long)g * VEC, o);
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          const long rr = r + (long)i * lanes;
+          if (rr >= r1) break;
+          float o[VEC];
+#pragma unroll
+          for (int c = 0; c < VEC; ++c) {
+            if (PASS == 0) {
+              s0[c] += dv[i][c];
+              s1[c] = fmaf(dv[i][c], (av[i][c] - ca[c]) * cb[c], s1[c]);
+            } else {
+              const float da = fmaf(ca[c], dv[i][c], fmaf(cc[c], av[i][c], cb[c]));
+              o[c] = av[i][c] > 0.f ? da : 0.f;
+              s0[c] += o[c];
+            }
+          }
+          if (PASS == 1) store_planes_vec<VEC>(p.hi, p.lo, p.d_f32, rr * p.C + (long)g * VEC, o);
+        }
+      }
+      if (PASS == 0) {
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) s0[c] *= p.dy_scale;      // s1 already carries dy_scale through cb
       }
     } else {
       for (long r = r0 + rl; r < r1; r += lanes) {
@@ -377,14 +401,21 @@ extern "C" int jcm_bn_relu_bwd(const void* a, int a_bf16, const void* dout, int 
   // bf16-stored activations with C a multiple of 8: 8 channels per thread (16-byte loads); else 4
   const bool v8 = a_bf16 && (C % 8) == 0 && C / 8 <= kThreads;
   const size_t shb = kThreads * (v8 ? 16 : 8) * sizeof(float);
-  if (v8) bn_relu_bwd_kernel<0, 8><<<blocks, kThreads, shb, st>>>(p);
-  else bn_relu_bwd_kernel<0, 4><<<blocks, kThreads, shb, st>>>(p);
+  auto launch = [&](int pass) {
+    if (pass == 0) {
+      if (v8) { if (pool) bn_relu_bwd_kernel<0, 8, 1><<<blocks, kThreads, shb, st>>>(p); else bn_relu_bwd_kernel<0, 8, 0><<<blocks, kThreads, shb, st>>>(p); }
+      else { if (pool) bn_relu_bwd_kernel<0, 4, 1><<<blocks, kThreads, shb, st>>>(p); else bn_relu_bwd_kernel<0, 4, 0><<<blocks, kThreads, shb, st>>>(p); }
+    } else {
+      if (v8) { if (pool) bn_relu_bwd_kernel<1, 8, 1><<<blocks, kThreads, shb, st>>>(p); else bn_relu_bwd_kernel<1, 8, 0><<<blocks, kThreads, shb, st>>>(p); }
+      else { if (pool) bn_relu_bwd_kernel<1, 4, 1><<<blocks, kThreads, shb, st>>>(p); else bn_relu_bwd_kernel<1, 4, 0><<<blocks, kThreads, shb, st>>>(p); }
+    }
+  };
+  launch(0);
   JCM_LAUNCH_CHECK();
   colsum_finalize_kernel<<<jcm_cdiv(C, 32), dim3(32, kPartY), 0, st>>>(part0, blocks, C, 2, sums, dbeta, dgamma);   // dbeta = sum dy, dgamma = sum dy * xhat
   JCM_LAUNCH_CHECK();
   p.partial = part1;
-  if (v8) bn_relu_bwd_kernel<1, 8><<<blocks, kThreads, shb, st>>>(p);
-  else bn_relu_bwd_kernel<1, 4><<<blocks, kThreads, shb, st>>>(p);
+  launch(1);
   JCM_LAUNCH_CHECK();
   colsum_finalize_kernel<<<jcm_cdiv(C, 32), dim3(32, kPartY), 0, st>>>(part1, blocks, C, 1, dbias, nullptr, nullptr);
   JCM_LAUNCH_CHECK();
