@@ -273,7 +273,7 @@ def measure(workload, steps, warmup, args, rank, world, local, dev, with_cpu_bas
     for _ in range(steps):
         loss = step(x_dev, y_dev)
     e1.record()
-    host_ms = 1e3 * (time.perf_counter() - t_host0) / steps      # CPU time to ISSUE one step (no synchronisation inside the loop)
+    host_ms = 1e3 * (time.perf_counter() - t_host0) / steps      # CPU time per step of the issuing loop (no synchronisation inside it)
     barrier()
     ops.PROFILE.enabled = False
     ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -286,6 +286,12 @@ def measure(workload, steps, warmup, args, rank, world, local, dev, with_cpu_bas
     wgrad_shapes = ops.PROFILE.by_shape('conv_wgrad_kernel', steps) if rank == 0 else None
     sm_prof = [ops.PROFILE.summary(steps, k) for k in ('spatial_model_fwd', 'spatial_model_bwd')] if rank == 0 else None
     ops.PROFILE.clear()
+    # CPU time to issue ONE step into an empty stream (outside the timed region): in the loop above the launch queue fills up and the
+    # CPU waits for the GPU, so host_ms_per_step there is a mix of both; this one is Python + ctypes + tensor-map encoding alone
+    t1 = time.perf_counter()
+    step(x_dev, y_dev)
+    host_issue_ms = 1e3 * (time.perf_counter() - t1)
+    barrier()
 
     # ---- replica consistency (N > 1, training): every replica must hold the same parameters, optimizer slots and BatchNorm
     # moving statistics after the timed steps (each saw DIFFERENT data): bit patterns summed as integers, compared across ranks
@@ -400,8 +406,10 @@ def measure(workload, steps, warmup, args, rank, world, local, dev, with_cpu_bas
         'gpu_launches': int(launches),
         'gpu_launches_per_step': int(launches) // max(steps, 1),
         'host_ms_per_step': host_ms,
-        'host_note': 'CPU time to issue one step (Python + ctypes + tensor-map encoding), no synchronisation in the loop; the step is '
-                     'GPU-bound while this is below ms_per_step',
+        'host_issue_ms': host_issue_ms,
+        'host_note': 'host_issue_ms = CPU time to issue ONE step into an empty stream (Python + ctypes + tensor-map encoding; measured after '
+                     'the timed region); host_ms_per_step = CPU time per step of the timed loop, where the CPU also waits for launch-queue '
+                     'slots; the step is GPU-bound while host_issue_ms is below ms_per_step',
         'clocks': clocks,
         'roofline': roof,
         'loss': loss_value,
@@ -442,7 +450,7 @@ def run_ours(args):
             try:
                 r = measure(wl, 5, 3, args, rank, world, local, dev, with_cpu_baseline=False, with_e2e=(world == 1))
                 if r is not None:
-                    keep = ('metric', 'value', 'unit', 'ms_per_step', 'dtype', 'config', 'e2e', 'gpu_launches_per_step', 'host_ms_per_step',
+                    keep = ('metric', 'value', 'unit', 'ms_per_step', 'dtype', 'config', 'e2e', 'gpu_launches_per_step', 'host_ms_per_step', 'host_issue_ms',
                             'loss', 'replicas_identical', 'steps', 'warmup', 'n_gpus')
                     extra[wl] = {k: r[k] for k in keep if k in r}
                     extra[wl]['roofline'] = {k: r['roofline'][k] for k in ('achieved', 'peak', 'frac', 'unit', 'share_of_step', 'spatial_model')

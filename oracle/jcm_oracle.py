@@ -18,7 +18,12 @@ TF1 semantics that are not visible in the reference tree ([TF1] tags; SURVEY.md 
 
 PARITY PINNING STATUS: **parity unpinned against TensorFlow itself** - TensorFlow 1.x cannot be installed in
 this image (no network) and the reference holds no tests, golden vectors or fixtures for this path.
-What the oracle IS pinned against (tests/test_oracle_pins.py, tests/test_pairwise_prior.py):
+What the oracle IS pinned against (tests/test_oracle_pins.py, tests/test_tf_semantics_opencv.py, tests/test_cpu_suite.py):
+  * an INDEPENDENT engine written to reproduce TensorFlow graphs - OpenCV's TensorFlow importer (cv2.dnn), fed
+    hand-encoded frozen GraphDefs of the reference's call sites: conv2d 'SAME' with strides 1 and 2 (the asymmetric
+    padding), max_pool 2x2 'SAME' on odd extents, tf.image.resize_images for every size pair the graph uses (incl.
+    conv_mrf's 61x91 -> 60x90), the inference-mode batch-norm formula, and the whole conv1 layer chain
+    (conv + bias + ReLU + BN-after-ReLU + pool).  This is a third party's reading of TF, not TF.
   * `conv_mrf` == scipy.signal.convolve2d(prior, likelihood, 'valid') + legacy resize (independent library)
   * softmax-CE of both heads at initialisation == ln(H*W) = 8.594, the value the reference logs
     (`hps_opt:2,37,102`)
