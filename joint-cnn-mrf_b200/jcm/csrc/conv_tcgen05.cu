@@ -53,6 +53,8 @@ struct ConvParams {
   // (TH + kh - 1)-row halo patch and the kh vertical taps address it at row offsets dy*TW (a multiple of the 8-row swizzle
   // period, so the UMMA descriptor just moves its start address); weights stream through their own ring, one tap at a time.
   int halo, a_stages, b_stages, a_halo_bytes, a_stride, b_stride;
+  int mgroup;           // halo mode: M tiles that share every weight stage (2 where shared memory and TMEM allow: the weights are then
+                        // streamed from L2 once per PAIR of tiles - for the 5x5 layers they are 3/4 of a tile's L2->SM traffic)
   int b_group, b_slot;  // halo mode: vertical taps per weight stage (one full/empty handshake and one tcgen05.commit per group: the
                         // handshake costs ~350 clk, more than the MMAs of one tap when N <= 128) and bytes per tap slot
   int mma_split_n;      // measurement switch (JCM_MMA_SPLITN): issue every MMA as two independent half-N MMAs
@@ -300,18 +302,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     if (elect_one()) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile / m_tiles, mt = tile - nt * m_tiles;
-        const int img = mt / (p.tiles_y * p.tiles_x);
-        const int r = mt - img * (p.tiles_y * p.tiles_x);
-        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-        const int x0 = tx * p.TW - p.pad_x, y0 = ty * p.TH - p.pad;
+      const int m_groups = (m_tiles + p.mgroup - 1) / p.mgroup;
+      for (int tg = blockIdx.x; tg < m_groups * p.n_tiles; tg += gridDim.x) {
+        const int nt = tg / m_groups, mt0 = (tg - nt * m_groups) * p.mgroup;
+        const int n_in = min(p.mgroup, m_tiles - mt0);       // tiles of this group (the last group may hold one)
+        const Patch pt0 = decode_patch(p, mt0), pt1 = decode_patch(p, mt0 + n_in - 1);
         for (int dx = 0; dx < p.kw; ++dx) {
           for (int cb = 0; cb < p.cblocks; ++cb) {
-            mbar_wait(bar_aempty + 8 * sa, pa ^ 1);
-            mbar_expect_tx(bar_afull + 8 * sa, p.a_halo_bytes);
-            tma_load_4d(smem_base + sa * p.a_stride, &map_a_lo, bar_afull + 8 * sa, cb * p.kc, x0 + dx, y0, img);
-            if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+            for (int i = 0; i < n_in; ++i) {
+              const Patch& pt = i ? pt1 : pt0;
+              mbar_wait(bar_aempty + 8 * sa, pa ^ 1);
+              mbar_expect_tx(bar_afull + 8 * sa, p.a_halo_bytes);
+              tma_load_4d(smem_base + sa * p.a_stride, &map_a_lo, bar_afull + 8 * sa, cb * p.kc, pt.x0 - p.pad_x + dx, pt.y0 - p.pad, pt.img);
+              if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+            }
             if (p.b_group == 1) {
               for (int dy = 0; dy < p.ksize; ++dy) {
                 mbar_wait(bar_empty + 8 * sb, pb ^ 1);
@@ -351,51 +355,44 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
       uint32_t pa = 0, pb = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_groups = (m_tiles + p.mgroup - 1) / p.mgroup;
+      for (int tg = blockIdx.x; tg < m_groups * p.n_tiles; tg += gridDim.x) {
+        const int mt0 = (tg % m_groups) * p.mgroup;
+        const int n_in = min(p.mgroup, m_tiles - mt0);
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 256;
-        uint32_t accumulate = 0, mcount = 0;
+        const uint32_t d_tmem = tmem_base + acc * 256;          // tile i of the group accumulates in columns [i * block_n, (i+1) * block_n)
         for (int it = 0; it < p.kw * p.cblocks; ++it) {
-          mbar_wait(bar_afull + 8 * sa, pa);
+          // the group's halo patches of this (dx, channel block): stage sa (and sa + 1)
+          uint32_t a_addr[2];
+          int sa_it = sa;
+          uint32_t pa_it = pa;
+          for (int i = 0; i < n_in; ++i) {
+            mbar_wait(bar_afull + 8 * sa_it, pa_it);
+            a_addr[i] = smem_base + sa_it * p.a_stride;
+            if (++sa_it == p.a_stages) { sa_it = 0; pa_it ^= 1; }
+          }
           tc_fence_after();
-          const uint32_t a_addr = smem_base + sa * p.a_stride;
-          if (p.b_group == 1) {
-            // one tap per weight stage (N = 128 layers: grouping does not pay there; this flat loop compiles to the tighter issue loop)
-            for (int dy = 0; dy < p.ksize; ++dy) {
-              mbar_wait(bar_full + 8 * sb, pb);
-              tc_fence_after();
-              const uint64_t adesc = desc_hi | (uint64_t)(((a_addr + dy * dy_bytes) >> 4) & 0x3FFF);
-              const uint64_t bdesc = desc_hi | (uint64_t)(((smem_b0 + sb * p.b_stride) >> 4) & 0x3FFF);
-              if (!(JCM_DBG(p) & 2))
-              for (int k = 0; k < kk; ++k) {
-                const int j = (mcount++) & (p.nacc - 1);
-                tc_mma_bf16(d_tmem + j * p.block_n, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (accumulate >> j) & 1u);
-                accumulate |= 1u << j;
-              }
-              tc_commit(bar_empty + 8 * sb);
-              if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
-            }
-          } else
           for (int dy0 = 0; dy0 < p.ksize; dy0 += p.b_group) {
             const int gn = min(p.b_group, p.ksize - dy0);
             mbar_wait(bar_full + 8 * sb, pb);
             tc_fence_after();
             for (int i = 0; i < gn; ++i) {
-              const uint64_t adesc = desc_hi | (uint64_t)(((a_addr + (dy0 + i) * dy_bytes) >> 4) & 0x3FFF);
               const uint64_t bdesc = desc_hi | (uint64_t)(((smem_b0 + sb * p.b_stride + i * p.b_slot) >> 4) & 0x3FFF);
               if (!(JCM_DBG(p) & 2))
-              for (int k = 0; k < kk; ++k) {
-                const int j = (mcount++) & (p.nacc - 1);
-                tc_mma_bf16(d_tmem + j * p.block_n, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (accumulate >> j) & 1u);
-                accumulate |= 1u << j;
+              for (int t = 0; t < n_in; ++t) {      // every weight stage feeds all tiles of the group before it is released
+                const uint64_t adesc = desc_hi | (uint64_t)(((a_addr[t] + (dy0 + i) * dy_bytes) >> 4) & 0x3FFF);
+                for (int k = 0; k < kk; ++k)
+                  tc_mma_bf16(d_tmem + t * p.block_n, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((it | dy0 | i | k) != 0));
               }
             }
             tc_commit(bar_empty + 8 * sb);
             if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
           }
-          tc_commit(bar_aempty + 8 * sa);
-          if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+          for (int i = 0; i < n_in; ++i) {
+            tc_commit(bar_aempty + 8 * sa);
+            if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+          }
         }
         tc_commit(bar_tfull + 8 * acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -520,21 +517,34 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     int epi_chunk = 0;
-    // halo mode has no tail sub-tiles and no plan: its roles loop over total_tiles, and so must this one then
-    const int epi_tiles = p.halo ? total_tiles : virt_tiles;
-    for (int vt = blockIdx.x; vt < epi_tiles; vt += gridDim.x) {
-      const TileId tid = decode_tile(p, vt, m_tiles, total_tiles);
+    // work items of this kernel's roles: tile groups in halo mode (mgroup tiles share the weight stages and one accumulator
+    // stage), virtual tiles (N-split tail) otherwise
+    const int m_groups = (m_tiles + p.mgroup - 1) / p.mgroup;
+    const int epi_items = p.halo ? m_groups * p.n_tiles : virt_tiles;
+    for (int wi = blockIdx.x; wi < epi_items; wi += gridDim.x) {
+      TileId tid;
+      int n_in = 1;
+      if (p.halo) {
+        tid.nt = wi / m_groups;
+        tid.mt = (wi - tid.nt * m_groups) * p.mgroup;
+        tid.n_off = 0;
+        tid.n_cols = p.block_n;
+        n_in = min(p.mgroup, m_tiles - tid.mt);
+      } else {
+        tid = decode_tile(p, wi, m_tiles, total_tiles);
+      }
       const int nt = tid.nt;
-      const Patch pt = decode_patch(p, tid.mt);
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      for (int gt = 0; gt < n_in; ++gt) {
+      const Patch pt = decode_patch(p, tid.mt + gt);
       const int img = pt.img;
       const int oy = pt.y0 + ly, ox = pt.x0 + lx;
       const void* my = pt.shape >= 0 ? (const void*)&smaps.y[pt.shape] : (const void*)&map_y;
       const int ncols = tid.n_cols, ncol0 = nt * p.block_n + tid.n_off;
       const bool valid = (oy < p.H) && (ox < p.W);
       float* yrow = p.y + ((size_t)((size_t)img * p.H + oy) * p.W + ox) * p.Cout;
-      mbar_wait(bar_tfull + 8 * acc, acc_phase);
-      tc_fence_after();
-      const uint32_t taddr0 = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr0 = tmem_base + acc * 256 + gt * p.block_n + ((uint32_t)(q * 32) << 16);
       if (JCM_DBG(p) & 1) {
         // timing experiment: no stores
       } else if (p.tma_store && p.y_bf16) {
@@ -663,6 +673,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
           }
         }
       }
+      }   // tiles of the group
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
@@ -1034,7 +1045,8 @@ extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_
 }
 
 // jcm_conv2d_fwd with the kernel variant forced (tests and measurements; every variant computes the same values):
-// bit 0 = single-CTA kernel instead of the CTA pair, bit 1 = uniform tile grid instead of the mixed-shape plan, bit 2 = no N-split tail.
+// bit 0 = single-CTA kernel instead of the CTA pair, bit 1 = uniform tile grid instead of the mixed-shape plan, bit 2 = no N-split tail,
+// bit 3 = halo mode with one M tile per weight stage instead of two.
 extern "C" int jcm_conv2d_fwd_variant(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
                                       void* y, int y_bf16, int B, int H, int W, int Cin, int Cout, int Cout_pad, int ksize, int kw,
                                       int relu, int variant, void* stream) {
@@ -1097,6 +1109,7 @@ int jcm_conv_igemm_ex(const ConvExArgs& a) {
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   // halo mode where the A operand's L2 traffic is the limiter (few output channels per A tile) and the taps have vertical extent
   p.halo = 0;
+  p.mgroup = 1;
   static const int splitn_env = JCM_ENV_INT("JCM_MMA_SPLITN", 0);
   p.mma_split_n = splitn_env && (p.block_n % 32) == 0;
   {
@@ -1131,6 +1144,19 @@ int jcm_conv_igemm_ex(const ConvExArgs& a) {
     p.b_stages = budget / p.b_stride;
     if (p.b_stages > kMaxStages) p.b_stages = kMaxStages;
     p.halo = p.b_stages >= 3;
+    // two M tiles per weight stage when four halo patches (two tiles, double-buffered) still leave three weight stages and both
+    // tiles' accumulators fit one 256-column TMEM stage
+    if (p.halo && !(a.variant & 8) && p.block_n <= 128) {
+      const int a4 = 4 * p.a_stride;
+      const int budget2 = 225 * 1024 - epi_bytes - a4;
+      if (budget2 >= 3 * p.b_stride) {
+        p.mgroup = 2;
+        p.a_stages = 4;
+        p.b_stages = budget2 / p.b_stride;
+        if (p.b_stages > kMaxStages) p.b_stages = kMaxStages;
+      }
+    }
+    if (p.halo) p.nacc = 1;
   }
   // CTA-pair form (cta_group::2) of the plain mode for N = 256 tiles: the default wherever it applies.  a.variant (tests /
   // measurements, jcm_conv2d_fwd_variant): bit 0 = single-CTA kernel, bit 1 = uniform tile grid, bit 2 = no N-split tail.
@@ -1251,7 +1277,7 @@ int jcm_conv_igemm_ex(const ConvExArgs& a) {
     JCM_LAUNCH_CHECK();
     return JCM_OK;
   }
-  const int total_tiles = units;
+  const int total_tiles = p.halo ? jcm_cdiv(m_tiles_h, p.mgroup) * p.n_tiles : units;
   int grid = jcm_num_sms();
   if (grid > total_tiles) grid = total_tiles;
   const size_t smem = (p.halo ? (size_t)p.a_stages * p.a_stride + (size_t)p.b_stages * p.b_stride : (size_t)p.stages * p.stage_bytes) + epi_bytes + 1024;

@@ -241,6 +241,28 @@ def test_conv_pair_plan_tail_variants_are_bit_identical(jcm, case, split):
     assert torch.equal(jcm.ops.conv2d_planes(xp, wp, b.cuda(), Cout, k, relu=True), base)   # the default entry point
 
 
+@pytest.mark.parametrize('case', [(3, 24, 32, 64, 128, 5), (1, 20, 33, 64, 64, 5), (5, 60, 90, 128, 64, 5), (1, 120, 180, 64, 128, 5), (3, 9, 200, 64, 16, 3),
+                                  (2, 30, 45, 256, 128, 5)])
+def test_conv_halo_two_tiles_per_weight_stage_is_bit_identical(jcm, case):
+    """Halo mode (N <= 128 layers: the 5x5 convolutions): by default two M tiles share every weight stage (the weights stream from L2
+    once per pair of tiles).  Same bits as one tile per stage (variant bit 3) and as the oracle; odd tile counts leave a last group of one."""
+    B, H, W, Cin, Cout, k = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, H, W, Cin, generator=g)
+    w = torch.randn(k, k, Cin, Cout, generator=g) / math.sqrt(k * k * Cin)
+    b = torch.randn(Cout, generator=g)
+    xp = jcm.ops.split_planes(x.cuda(), False)
+    wp = jcm.ops.pack_weights(w.cuda(), False)
+    one = jcm.ops.conv2d_planes(xp, wp, b.cuda(), Cout, k, relu=True, variant=8)
+    two = jcm.ops.conv2d_planes(xp, wp, b.cuda(), Cout, k, relu=True)
+    bf = lambda t: t.to(torch.bfloat16).float()
+    ref = torch.relu(orc.conv2d(bf(x).double(), bf(w).double(), 1) + b.double())
+    assert rel(one, ref) < 2e-4
+    assert torch.equal(one, two)
+    if Cout % 64 == 0:
+        assert torch.equal(jcm.ops.conv2d_planes(xp, wp, b.cuda(), Cout, k, relu=True, out_bf16=True), one.to(torch.bfloat16))
+
+
 @pytest.mark.parametrize('case', [(2, 60, 90, 256, 512, 3), (1, 30, 45, 512, 512, 3), (3, 60, 90, 128, 256, 3), (2, 16, 24, 256, 256, 5),
                                   (4, 60, 90, 512, 128, 1)])
 @pytest.mark.parametrize('split', [False, True])
