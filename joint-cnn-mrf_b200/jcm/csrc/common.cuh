@@ -203,15 +203,19 @@ template <int VEC>
 __device__ __forceinline__ void store_planes_vec(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ f32,
                                                  long e, const float (&v)[VEC]) {
   __align__(16) __nv_bfloat16 h[VEC];
-  __align__(16) __nv_bfloat16 l[VEC];
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) split_bf16(v[i], h[i], l[i]);
+  for (int i = 0; i < VEC; ++i) h[i] = __float2bfloat16_rn(v[i]);
   if (VEC == 8) {
     if (hi) reinterpret_cast<uint4*>(hi)[e >> 3] = *reinterpret_cast<uint4*>(h);
-    if (lo) reinterpret_cast<uint4*>(lo)[e >> 3] = *reinterpret_cast<uint4*>(l);
   } else {
     if (hi) reinterpret_cast<uint2*>(hi)[e >> 2] = *reinterpret_cast<uint2*>(h);
-    if (lo) reinterpret_cast<uint2*>(lo)[e >> 2] = *reinterpret_cast<uint2*>(l);
+  }
+  if (lo) {      // the residual plane exists in the fp32 configuration only: its conversions are skipped otherwise (uniform branch)
+    __align__(16) __nv_bfloat16 l[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) l[i] = __float2bfloat16_rn(v[i] - __bfloat162float(h[i]));
+    if (VEC == 8) reinterpret_cast<uint4*>(lo)[e >> 3] = *reinterpret_cast<uint4*>(l);
+    else reinterpret_cast<uint2*>(lo)[e >> 2] = *reinterpret_cast<uint2*>(l);
   }
   if (f32) {
 #pragma unroll

@@ -355,47 +355,98 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
       uint32_t pa = 0, pb = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const int m_groups = (m_tiles + p.mgroup - 1) / p.mgroup;
-      for (int tg = blockIdx.x; tg < m_groups * p.n_tiles; tg += gridDim.x) {
-        const int mt0 = (tg % m_groups) * p.mgroup;
-        const int n_in = min(p.mgroup, m_tiles - mt0);
+      if (p.mgroup == 1) {
+      // one M tile per weight stage: the issue loops below are kept exactly as tuned (the single issuing thread sets the pace of the
+      // small-K layers; restructuring them for the two-tile case cost 20 % on those layers)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 256;          // tile i of the group accumulates in columns [i * block_n, (i+1) * block_n)
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        uint32_t accumulate = 0, mcount = 0;
         for (int it = 0; it < p.kw * p.cblocks; ++it) {
-          // the group's halo patches of this (dx, channel block): stage sa (and sa + 1)
-          uint32_t a_addr[2];
-          int sa_it = sa;
-          uint32_t pa_it = pa;
-          for (int i = 0; i < n_in; ++i) {
-            mbar_wait(bar_afull + 8 * sa_it, pa_it);
-            a_addr[i] = smem_base + sa_it * p.a_stride;
-            if (++sa_it == p.a_stages) { sa_it = 0; pa_it ^= 1; }
-          }
+          mbar_wait(bar_afull + 8 * sa, pa);
           tc_fence_after();
+          const uint32_t a_addr = smem_base + sa * p.a_stride;
+          if (p.b_group == 1) {
+            // one tap per weight stage (N = 128 layers: grouping does not pay there; this flat loop compiles to the tighter issue loop)
+            for (int dy = 0; dy < p.ksize; ++dy) {
+              mbar_wait(bar_full + 8 * sb, pb);
+              tc_fence_after();
+              const uint64_t adesc = desc_hi | (uint64_t)(((a_addr + dy * dy_bytes) >> 4) & 0x3FFF);
+              const uint64_t bdesc = desc_hi | (uint64_t)(((smem_b0 + sb * p.b_stride) >> 4) & 0x3FFF);
+              if (!(JCM_DBG(p) & 2))
+              for (int k = 0; k < kk; ++k) {
+                const int j = (mcount++) & (p.nacc - 1);
+                tc_mma_bf16(d_tmem + j * p.block_n, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (accumulate >> j) & 1u);
+                accumulate |= 1u << j;
+              }
+              tc_commit(bar_empty + 8 * sb);
+              if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+            }
+          } else
           for (int dy0 = 0; dy0 < p.ksize; dy0 += p.b_group) {
             const int gn = min(p.b_group, p.ksize - dy0);
             mbar_wait(bar_full + 8 * sb, pb);
             tc_fence_after();
             for (int i = 0; i < gn; ++i) {
+              const uint64_t adesc = desc_hi | (uint64_t)(((a_addr + (dy0 + i) * dy_bytes) >> 4) & 0x3FFF);
               const uint64_t bdesc = desc_hi | (uint64_t)(((smem_b0 + sb * p.b_stride + i * p.b_slot) >> 4) & 0x3FFF);
               if (!(JCM_DBG(p) & 2))
-              for (int t = 0; t < n_in; ++t) {      // every weight stage feeds all tiles of the group before it is released
-                const uint64_t adesc = desc_hi | (uint64_t)(((a_addr[t] + (dy0 + i) * dy_bytes) >> 4) & 0x3FFF);
-                for (int k = 0; k < kk; ++k)
-                  tc_mma_bf16(d_tmem + t * p.block_n, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((it | dy0 | i | k) != 0));
+              for (int k = 0; k < kk; ++k) {
+                const int j = (mcount++) & (p.nacc - 1);
+                tc_mma_bf16(d_tmem + j * p.block_n, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (accumulate >> j) & 1u);
+                accumulate |= 1u << j;
               }
             }
             tc_commit(bar_empty + 8 * sb);
             if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
           }
-          for (int i = 0; i < n_in; ++i) {
+          tc_commit(bar_aempty + 8 * sa);
+          if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+        }
+        tc_commit(bar_tfull + 8 * acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      } else {
+      // two M tiles per weight stage (one tap per stage): tile 0 accumulates in columns [0, block_n), tile 1 in [block_n, 2 block_n)
+      const int m_groups = (m_tiles + 1) / 2;
+      for (int tg = blockIdx.x; tg < m_groups * p.n_tiles; tg += gridDim.x) {
+        const bool two = 2 * (tg % m_groups) + 1 < m_tiles;
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * 256, d1 = d0 + p.block_n;
+        for (int it = 0; it < p.kw * p.cblocks; ++it) {
+          mbar_wait(bar_afull + 8 * sa, pa);
+          const uint32_t a0 = smem_base + sa * p.a_stride;
+          int sa1 = sa + 1;
+          uint32_t pa1 = pa;
+          if (sa1 == p.a_stages) { sa1 = 0; pa1 ^= 1; }
+          if (two) mbar_wait(bar_afull + 8 * sa1, pa1);
+          const uint32_t a1 = smem_base + sa1 * p.a_stride;
+          tc_fence_after();
+          for (int dy = 0; dy < p.ksize; ++dy) {
+            mbar_wait(bar_full + 8 * sb, pb);
+            tc_fence_after();
+            const uint64_t bdesc = desc_hi | (uint64_t)(((smem_b0 + sb * p.b_stride) >> 4) & 0x3FFF);
+            const uint64_t adesc0 = desc_hi | (uint64_t)(((a0 + dy * dy_bytes) >> 4) & 0x3FFF);
+            const uint64_t adesc1 = desc_hi | (uint64_t)(((a1 + dy * dy_bytes) >> 4) & 0x3FFF);
+            const uint32_t accf = (uint32_t)((it | dy) != 0);
+            for (int k = 0; k < kk; ++k) tc_mma_bf16(d0, adesc0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accf | (uint32_t)(k != 0));
+            if (two)
+              for (int k = 0; k < kk; ++k) tc_mma_bf16(d1, adesc1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accf | (uint32_t)(k != 0));
+            tc_commit(bar_empty + 8 * sb);
+            if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+          }
+          tc_commit(bar_aempty + 8 * sa);
+          sa = sa1; pa = pa1;
+          if (two) {
             tc_commit(bar_aempty + 8 * sa);
             if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
           }
         }
         tc_commit(bar_tfull + 8 * acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
       }
     }
   } else if (warp == 0) {
@@ -1046,7 +1097,7 @@ extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_
 
 // jcm_conv2d_fwd with the kernel variant forced (tests and measurements; every variant computes the same values):
 // bit 0 = single-CTA kernel instead of the CTA pair, bit 1 = uniform tile grid instead of the mixed-shape plan, bit 2 = no N-split tail,
-// bit 3 = halo mode with one M tile per weight stage instead of two.
+// bit 3 = halo mode with two M tiles per weight stage (N = 128 layers) instead of one.
 extern "C" int jcm_conv2d_fwd_variant(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
                                       void* y, int y_bf16, int B, int H, int W, int Cin, int Cout, int Cout_pad, int ksize, int kw,
                                       int relu, int variant, void* stream) {
@@ -1144,9 +1195,9 @@ int jcm_conv_igemm_ex(const ConvExArgs& a) {
     p.b_stages = budget / p.b_stride;
     if (p.b_stages > kMaxStages) p.b_stages = kMaxStages;
     p.halo = p.b_stages >= 3;
-    // two M tiles per weight stage when four halo patches (two tiles, double-buffered) still leave three weight stages and both
-    // tiles' accumulators fit one 256-column TMEM stage
-    if (p.halo && !(a.variant & 8) && p.block_n <= 128) {
+    // two M tiles per weight stage (variant bit 3; measurement): needs four halo patches (two tiles, double-buffered) next to three
+    // weight stages, and both tiles' accumulators in one 256-column TMEM stage
+    if (p.halo && (a.variant & 8) && p.block_n <= 128 && p.b_group == 1) {
       const int a4 = 4 * p.a_stride;
       const int budget2 = 225 * 1024 - epi_bytes - a4;
       if (budget2 >= 3 * p.b_stride) {

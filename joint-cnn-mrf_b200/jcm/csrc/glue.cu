@@ -168,9 +168,11 @@ __device__ __forceinline__ void legacy_tap(int dst, int n_in, int n_out, int& lo
 // `(float)n_in / n_out` divisions and two floors per sample: 0.75 ms for 0.82 GB of traffic, six times its HBM time).
 struct TapTab { int lo, hi; float w; };
 
+// legacy-bilinear sample of the RAW activation (the batch-norm affine is applied by the caller AFTER the interpolation: the four
+// weights sum to 1, so  interp(scale * a + shift) == scale * interp(a) + shift  - one FMA per channel instead of four)
 template <int VEC>
 __device__ __forceinline__ void resize_sample(const void* __restrict__ a, int a_bf16, long img_base, int Wi, int C, const TapTab ty,
-                                              const TapTab tx, const float (&sc)[VEC], const float (&sh)[VEC], float (&out)[VEC]) {
+                                              const TapTab tx, float (&out)[VEC]) {
   float tl[VEC], tr[VEC], bl[VEC], br[VEC];
   load_act_vec<VEC>(a, img_base + ((long)ty.lo * Wi + tx.lo) * C, a_bf16, tl);
   load_act_vec<VEC>(a, img_base + ((long)ty.lo * Wi + tx.hi) * C, a_bf16, tr);
@@ -178,13 +180,15 @@ __device__ __forceinline__ void resize_sample(const void* __restrict__ a, int a_
   load_act_vec<VEC>(a, img_base + ((long)ty.hi * Wi + tx.hi) * C, a_bf16, br);
 #pragma unroll
   for (int c = 0; c < VEC; ++c) {
-    const float vtl = fmaf(tl[c], sc[c], sh[c]), vtr = fmaf(tr[c], sc[c], sh[c]);
-    const float vbl = fmaf(bl[c], sc[c], sh[c]), vbr = fmaf(br[c], sc[c], sh[c]);
-    const float top = vtl + (vtr - vtl) * tx.w, bot = vbl + (vbr - vbl) * tx.w;
+    const float top = tl[c] + (tr[c] - tl[c]) * tx.w, bot = bl[c] + (br[c] - bl[c]) * tx.w;
     out[c] = top + (bot - top) * ty.w;
   }
 }
 
+// out = (bn1(a1) + resize(bn2(a2)) + resize(bn3(a3))) / 3 = s1 * a1 + s2 * resize(a2) + s3 * resize(a3) + t, with s_k = scale_k / 3 and
+// t = (shift1 + shift2 + shift3) / 3: three FMAs per channel after the two interpolations.  (The first version applied the affine to
+// all nine taps, divided by 3 in IEEE and converted the unused residual plane: 638 instructions per 8-channel item, instruction-bound
+// at 0.82 ms for 0.82 GB of traffic.)
 template <int VEC>
 __global__ void upsample_avg3_kernel(const void* __restrict__ a1, const void* __restrict__ a2, const void* __restrict__ a3, int a_bf16,
                                      const float* __restrict__ ss /* [6][C]: scale1, shift1, scale2, shift2, scale3, shift3 */,
@@ -207,29 +211,37 @@ __global__ void upsample_avg3_kernel(const void* __restrict__ a1, const void* __
   const int CG = C / VEC;
   const long total = (long)B * H * W * CG;
   const long step = (long)gridDim.x * blockDim.x;
-  // when the grid stride is a multiple of the channel-group count every thread keeps ONE channel group: its six scale / shift
-  // vectors stay in registers for the whole loop
+  // when the grid stride is a multiple of the channel-group count every thread keeps ONE channel group: its constants stay in
+  // registers for the whole loop
   const bool fixed_cg = (step % CG) == 0;
-  float sc1[VEC], sh1[VEC], sc2[VEC], sh2[VEC], sc3[VEC], sh3[VEC];
+  float s1[VEC], s2[VEC], s3[VEC], t0[VEC];
   int cg_loaded = -1;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += step) {
     int cg, x, y, n;
     split_index(i, CG, W, H, cg, x, y, n);
     if (!fixed_cg || cg_loaded != cg) {
-      load_f32_vec<VEC>(ss + 0 * C, (long)cg * VEC, sc1);
-      load_f32_vec<VEC>(ss + 1 * C, (long)cg * VEC, sh1);
-      load_f32_vec<VEC>(ss + 2 * C, (long)cg * VEC, sc2);
-      load_f32_vec<VEC>(ss + 3 * C, (long)cg * VEC, sh2);
-      load_f32_vec<VEC>(ss + 4 * C, (long)cg * VEC, sc3);
-      load_f32_vec<VEC>(ss + 5 * C, (long)cg * VEC, sh3);
+      float u[VEC];
+      load_f32_vec<VEC>(ss + 0 * C, (long)cg * VEC, s1);
+      load_f32_vec<VEC>(ss + 2 * C, (long)cg * VEC, s2);
+      load_f32_vec<VEC>(ss + 4 * C, (long)cg * VEC, s3);
+      load_f32_vec<VEC>(ss + 1 * C, (long)cg * VEC, t0);
+      load_f32_vec<VEC>(ss + 3 * C, (long)cg * VEC, u);
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) t0[c] += u[c];
+      load_f32_vec<VEC>(ss + 5 * C, (long)cg * VEC, u);
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) {
+        t0[c] = (t0[c] + u[c]) * (1.0f / 3.0f);
+        s1[c] *= (1.0f / 3.0f); s2[c] *= (1.0f / 3.0f); s3[c] *= (1.0f / 3.0f);
+      }
       cg_loaded = cg;
     }
     float v1[VEC], v2[VEC], v3[VEC], r[VEC];
     load_act_vec<VEC>(a1, i * VEC, a_bf16, v1);
-    resize_sample<VEC>(a2, a_bf16, (long)n * H2 * W2 * C + (long)cg * VEC, W2, C, ty2[y], tx2[x], sc2, sh2, v2);
-    resize_sample<VEC>(a3, a_bf16, (long)n * H3 * W3 * C + (long)cg * VEC, W3, C, ty3[y], tx3[x], sc3, sh3, v3);
+    resize_sample<VEC>(a2, a_bf16, (long)n * H2 * W2 * C + (long)cg * VEC, W2, C, ty2[y], tx2[x], v2);
+    resize_sample<VEC>(a3, a_bf16, (long)n * H3 * W3 * C + (long)cg * VEC, W3, C, ty3[y], tx3[x], v3);
 #pragma unroll
-    for (int c = 0; c < VEC; ++c) r[c] = (fmaf(v1[c], sc1[c], sh1[c]) + v2[c] + v3[c]) * (1.0f / 3.0f);
+    for (int c = 0; c < VEC; ++c) r[c] = fmaf(s1[c], v1[c], fmaf(s2[c], v2[c], fmaf(s3[c], v3[c], t0[c])));
     store_planes_vec<VEC>(hi, lo, out_f32, i * VEC, r);
   }
 }

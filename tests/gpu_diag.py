@@ -548,6 +548,17 @@ def sec_cta2():
               flush=True)
 
 
+def sec_halo2():
+    """halo-mode layers with N = 128: one M tile per weight stage (default) vs two (variant bit 3), interleaved, batch 64"""
+    for (B, H, W, Cin, Cout, k) in [(64, 120, 180, 64, 128, 5), (64, 60, 90, 256, 128, 5), (64, 60, 90, 64, 128, 5), (64, 30, 45, 256, 128, 5)]:
+        xp = ops.Planes(torch.randn(B, H, W, Cin, device=dev).to(torch.bfloat16), None)
+        wp = ops.Planes((torch.randn(k * k, Cout, Cin, device=dev) / np.sqrt(k * k * Cin)).to(torch.bfloat16), None)
+        fl = 2.0 * B * H * W * k * k * Cin * Cout
+        med = _interleaved([(lambda v=v: ops.conv2d_planes(xp, wp, None, Cout, k, relu=True, out_bf16=True, variant=v)) for v in (0, 8)])
+        print('HALO %dx%d Cin%d Cout%d k%d: ' % (H, W, Cin, Cout, k) + '  '.join('v%d %.3f ms (%.0f TF)' % (v, m, fl / m / 1e9) for v, m in zip((0, 8), med)),
+              flush=True)
+
+
 def sec_wgpair():
     """weight gradient: CTA-pair kernel / mixed-shape patch plan variants (bit 0 single-CTA, bit 1 uniform grid), batch 64, interleaved"""
     from jcm import train as jt
