@@ -305,9 +305,22 @@ def measure(workload, steps, warmup, args, rank, world, local, dev, with_cpu_bas
     # ---- end to end through the public API: every step copies its inputs from pinned host memory (jcm.DeviceFeed: the copy of
     # step i+1 runs on a side stream while step i computes) and reads the loss back to the host
     ms_e2e = None
+    h2d_gbs = None
     if with_e2e:
         res_host = torch.empty(1, dtype=torch.float32).pin_memory()
         feed = jcm.DeviceFeed(dev)
+        # the host->device link of this box, measured alone (one batch, nothing else running): when a step's inputs take longer to
+        # copy than the step takes to compute, e2e is bounded by this and not by the kernels
+        feed.submit(x_host, y_host)
+        feed.take()
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        feed.submit(x_host, y_host)
+        feed.take()
+        c1.record()
+        barrier()
+        h2d_gbs = (x_host.numel() * 4 + y_host.numel() * 4) / (c0.elapsed_time(c1) * 1e-3) / 1e9
         for _ in range(min(warmup, 2)):
             feed.submit(x_host, y_host)
             step(*feed.take())
@@ -415,7 +428,10 @@ def measure(workload, steps, warmup, args, rank, world, local, dev, with_cpu_bas
         'loss': loss_value,
     }
     if ms_e2e is not None:
-        line['e2e'] = {'value': imgs / (ms_e2e / 1e3), 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4}
+        line['e2e'] = {'value': imgs / (ms_e2e / 1e3), 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
+                       'h2d_link_gbs': h2d_gbs, 'h2d_ms_per_step_alone': h2d / (h2d_gbs * 1e9) * 1e3 if h2d_gbs else None,
+                       'note': 'inputs copied from pinned host memory every step (overlapped with the previous step), loss read back; '
+                               'h2d_link_gbs = this box\'s pinned host->device rate measured alone'}
     if replicas_identical is not None:
         line['replicas_identical'] = replicas_identical
         line['replicas_note'] = 'integer checksums of the parameter, Adam m / v and BatchNorm moving-statistic buffers compared across ranks after the timed steps'

@@ -367,6 +367,154 @@ __global__ void __launch_bounds__(kThreads, 2) bn_relu_bwd_bf16_kernel(BnBwdArgs
   }
 }
 
+// The pooled layers (conv1_*, conv2_*: the largest activations) of the bf16 configuration, with the same prefetching scheme: the work
+// item is one POOLED position x 8 channels = one 16-byte load of the data gradient + the four 16-byte loads of its 2x2 window; the
+// next item's five loads are in flight while the current one is processed.  Arithmetic and partial sums as bn_relu_bwd_kernel<PASS, 8, 1>.
+template <int PASS>
+__global__ void __launch_bounds__(kThreads, 2) bn_relu_bwd_pool_bf16_kernel(BnBwdArgs p) {
+  extern __shared__ float sh[];  // [kThreads][16]
+  constexpr int VEC = 8;
+  const int CG = p.C / VEC;
+  const int lanes = kThreads / CG;
+  const int g = threadIdx.x % CG, rl = threadIdx.x / CG;
+  const int Ho = (p.H + 1) / 2, Wo = (p.W + 1) / 2;
+  const long M = (long)p.B * Ho * Wo;
+  const long per_blk = (M + gridDim.x - 1) / gridDim.x;
+  const long r0 = blockIdx.x * per_blk;
+  long r1 = r0 + per_blk;
+  if (r1 > M) r1 = M;
+  float s0[VEC], s1[VEC];
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) { s0[c] = 0.f; s1[c] = 0.f; }
+  if (rl < lanes) {
+    float scv[VEC], sfv[VEC], ca[VEC], cb[VEC], cc[VEC];
+    {
+      float muv[VEC], rsv[VEC], m_dy[VEC], m_dyx[VEC];
+      load_f32_vec<VEC>(p.scale, (long)g * VEC, scv);
+      load_f32_vec<VEC>(p.shift, (long)g * VEC, sfv);
+      load_f32_vec<VEC>(p.mean, (long)g * VEC, muv);
+      load_f32_vec<VEC>(p.rstd, (long)g * VEC, rsv);
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) { m_dy[c] = 0.f; m_dyx[c] = 0.f; }
+      if (PASS == 1) {
+        load_f32_vec<VEC>(p.sums, (long)g * VEC, m_dy);
+        load_f32_vec<VEC>(p.sums + p.C, (long)g * VEC, m_dyx);
+      }
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) {
+        if (PASS == 0) {
+          ca[c] = muv[c];                 // sum dy * xhat = sum dy * (a - mean) * rstd
+          cb[c] = rsv[c] * p.dy_scale;
+          cc[c] = 0.f;
+        } else {
+          // d_pre(e) = scale * (dy(e) - m_dy - xhat(e) * m_dyx) = ca * dy(e) + cb + cc * a(e),  dy(e) = dout for the arg-max element, else 0
+          const float mdy = m_dy[c] * p.inv_count, mdyx = m_dyx[c] * p.inv_count;
+          ca[c] = scv[c] * p.dy_scale;
+          cc[c] = -scv[c] * mdyx * rsv[c];
+          cb[c] = -scv[c] * mdy - cc[c] * muv[c];
+        }
+      }
+    }
+    const uint4* dptr = reinterpret_cast<const uint4*>(p.dout);
+    const uint4* aptr = reinterpret_cast<const uint4*>(p.a);
+    uint4* optr = reinterpret_cast<uint4*>(p.hi);
+    const int c8 = p.C >> 3;
+    // window of pooled position r: index (in 16-byte units) of its top-left element and a 4-bit mask of the elements inside the map
+    // (32-bit indices: the launcher routes tensors of 2^31 or more 16-byte units to the generic kernel)
+    const int row8 = p.W * c8;
+    auto locate = [&](long r, int& base, unsigned& okm) {
+      int xo, yo, n;
+      split_index3(r, Wo, Ho, xo, yo, n);
+      const int y0 = 2 * yo, x0 = 2 * xo;
+      base = ((n * p.H + y0) * p.W + x0) * c8 + g;
+      okm = 1u | (x0 + 1 < p.W ? 2u : 0u) | (y0 + 1 < p.H ? 4u : 0u) | ((x0 + 1 < p.W && y0 + 1 < p.H) ? 8u : 0u);
+    };
+    uint4 nd, na[4];
+    int nbase = 0;
+    unsigned nokm = 0;
+    long r = r0 + rl;
+    if (r < r1) {
+      locate(r, nbase, nokm);
+      nd = dptr[r * c8 + g];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) na[e] = ((nokm >> e) & 1u) ? aptr[nbase + (e & 1) * c8 + (e >> 1) * row8] : make_uint4(0u, 0u, 0u, 0u);
+    }
+    for (; r < r1; r += lanes) {
+      const uint4 cd = nd;
+      uint4 cu[4];
+      const int base = nbase;
+      const unsigned okm = nokm;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) cu[e] = na[e];
+      const long rn = r + lanes;
+      if (rn < r1) {                      // the next item's loads fly while this one is processed
+        locate(rn, nbase, nokm);
+        nd = dptr[rn * c8 + g];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) na[e] = ((nokm >> e) & 1u) ? aptr[nbase + (e & 1) * c8 + (e >> 1) * row8] : make_uint4(0u, 0u, 0u, 0u);
+      }
+      bool ok[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) ok[e] = (okm >> e) & 1u;
+      float dv[VEC], av[4][VEC];
+      unpack_bf16x8(cd, dv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) unpack_bf16x8(cu[e], av[e]);
+      __align__(16) __nv_bfloat16 h[4][VEC];
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) {
+        int best = 0;
+        float bv = fmaf(av[0][c], scv[c], sfv[c]);
+#pragma unroll
+        for (int e = 1; e < 4; ++e) {
+          const float v = fmaf(av[e][c], scv[c], sfv[c]);
+          if (ok[e] && v > bv) { bv = v; best = e; }
+        }
+        if (PASS == 0) {
+          float ab = av[0][c];
+#pragma unroll
+          for (int e = 1; e < 4; ++e) ab = (best == e) ? av[e][c] : ab;
+          s0[c] += dv[c];
+          s1[c] = fmaf(dv[c], (ab - ca[c]) * cb[c], s1[c]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float da = fmaf(cc[c], av[e][c], cb[c]) + ((e == best) ? ca[c] * dv[c] : 0.f);
+            const float o = (ok[e] && av[e][c] > 0.f) ? da : 0.f;
+            s0[c] += o;
+            h[e][c] = __float2bfloat16_rn(o);
+          }
+        }
+      }
+      if (PASS == 1) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (ok[e]) optr[base + (e & 1) * c8 + (e >> 1) * row8] = *reinterpret_cast<uint4*>(h[e]);
+      }
+    }
+    if (PASS == 0) {
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) s0[c] *= p.dy_scale;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) {
+    sh[threadIdx.x * 2 * VEC + c] = s0[c];
+    sh[threadIdx.x * 2 * VEC + VEC + c] = s1[c];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    const int gg = c / VEC, v = c % VEC;
+    float t0 = 0.f, t1 = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      t0 += sh[(l * CG + gg) * 2 * VEC + v];
+      t1 += sh[(l * CG + gg) * 2 * VEC + VEC + v];
+    }
+    p.partial[((long)blockIdx.x * 2 + 0) * p.C + c] = t0;
+    p.partial[((long)blockIdx.x * 2 + 1) * p.C + c] = t1;
+  }
+}
+
 // sums[j][c] = sum over blocks of partial[blk][j][c] (double accumulation); optionally scaled by mul[c]
 __global__ void colsum_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, int rows, float* __restrict__ sums,
                                        float* __restrict__ copy0, float* __restrict__ copy1) {
@@ -531,11 +679,14 @@ extern "C" int jcm_bn_relu_bwd(const void* a, int a_bf16, const void* dout, int 
   // bf16-stored activations with C a multiple of 8: 8 channels per thread (16-byte loads); else 4
   const bool v8 = a_bf16 && (C % 8) == 0 && C / 8 <= kThreads;
   const size_t shb = kThreads * (v8 ? 16 : 8) * sizeof(float);
-  const bool fast = v8 && dout_bf16 && !pool && !d_lo && !d_f32;      // bf16 configuration, non-pooled layers: prefetching kernel
+  const bool fast = v8 && dout_bf16 && !d_lo && !d_f32 && (long)B * H * W * (C / 8) < (1L << 31);      // bf16 configuration: the prefetching kernels
   auto launch = [&](int pass) {
-    if (fast) {
+    if (fast && !pool) {
       if (pass == 0) bn_relu_bwd_bf16_kernel<0><<<blocks, kThreads, shb, st>>>(p);
       else bn_relu_bwd_bf16_kernel<1><<<blocks, kThreads, shb, st>>>(p);
+    } else if (fast) {
+      if (pass == 0) bn_relu_bwd_pool_bf16_kernel<0><<<blocks, kThreads, shb, st>>>(p);
+      else bn_relu_bwd_pool_bf16_kernel<1><<<blocks, kThreads, shb, st>>>(p);
     } else if (pass == 0) {
       if (v8) { if (pool) bn_relu_bwd_kernel<0, 8, 1><<<blocks, kThreads, shb, st>>>(p); else bn_relu_bwd_kernel<0, 8, 0><<<blocks, kThreads, shb, st>>>(p); }
       else { if (pool) bn_relu_bwd_kernel<0, 4, 1><<<blocks, kThreads, shb, st>>>(p); else bn_relu_bwd_kernel<0, 4, 0><<<blocks, kThreads, shb, st>>>(p); }

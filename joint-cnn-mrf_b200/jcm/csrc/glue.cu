@@ -104,9 +104,10 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblock
 
 // ------------------------------------------------------------------------------------------- BN apply (+pool)
 template <int VEC>
-__global__ void bn_apply_pool_kernel(const void* __restrict__ a, int a_bf16, const float* __restrict__ scale, const float* __restrict__ shift,
-                                     int B, int H, int W, int C, int pool, __nv_bfloat16* __restrict__ hi,
-                                     __nv_bfloat16* __restrict__ lo, float* __restrict__ out_f32) {
+__global__ void __launch_bounds__(256, 2)
+bn_apply_pool_kernel(const void* __restrict__ a, int a_bf16, const float* __restrict__ scale, const float* __restrict__ shift,
+                     int B, int H, int W, int C, int pool, __nv_bfloat16* __restrict__ hi,
+                     __nv_bfloat16* __restrict__ lo, float* __restrict__ out_f32) {
   const int Ho = pool ? (H + 1) / 2 : H, Wo = pool ? (W + 1) / 2 : W;
   const int CG = C / VEC;
   const long total = (long)B * Ho * Wo * CG;
@@ -114,44 +115,63 @@ __global__ void bn_apply_pool_kernel(const void* __restrict__ a, int a_bf16, con
   const bool fixed_cg = (step % CG) == 0;      // every thread then keeps one channel group: scale / shift stay in registers
   float sc[VEC], sh[VEC];
   int cg_loaded = -1;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += step) {
-    int cg, xo, yo, n;
-    split_index(i, CG, Wo, Ho, cg, xo, yo, n);
-    float r[VEC];
-    if (!fixed_cg || cg_loaded != cg) {
-      load_f32_vec<VEC>(scale, (long)cg * VEC, sc);
-      load_f32_vec<VEC>(shift, (long)cg * VEC, sh);
-      cg_loaded = cg;
-    }
-    if (!pool) {
-      load_act_vec<VEC>(a, i * VEC, a_bf16, r);
+  // U work items per thread and iteration, all loads issued before the first use (one item at a time left this kernel waiting on
+  // the long scoreboard at 3.7 TB/s)
+  constexpr int U = 2;
+  for (long i0 = blockIdx.x * (long)blockDim.x + threadIdx.x; i0 < total; i0 += U * step) {
+    float v[U][4][VEC];
+    bool hx[U], hy[U], live[U];
+    int cgs[U];
 #pragma unroll
-      for (int c = 0; c < VEC; ++c) r[c] = fmaf(r[c], sc[c], sh[c]);
-    } else {
-      const int y0 = 2 * yo, x0 = 2 * xo;
-      const long base = (((long)n * H + y0) * W + x0) * C + (long)cg * VEC;
-      load_act_vec<VEC>(a, base, a_bf16, r);
-#pragma unroll
-      for (int c = 0; c < VEC; ++c) r[c] = fmaf(r[c], sc[c], sh[c]);
-      const bool hx = x0 + 1 < W, hy = y0 + 1 < H;  // SAME pooling: the padded row/column never wins
-      float v[VEC];
-      if (hx) {
-        load_act_vec<VEC>(a, base + C, a_bf16, v);
-#pragma unroll
-        for (int c = 0; c < VEC; ++c) r[c] = fmaxf(r[c], fmaf(v[c], sc[c], sh[c]));
-      }
-      if (hy) {
-        load_act_vec<VEC>(a, base + (long)W * C, a_bf16, v);
-#pragma unroll
-        for (int c = 0; c < VEC; ++c) r[c] = fmaxf(r[c], fmaf(v[c], sc[c], sh[c]));
-      }
-      if (hx && hy) {
-        load_act_vec<VEC>(a, base + (long)W * C + C, a_bf16, v);
-#pragma unroll
-        for (int c = 0; c < VEC; ++c) r[c] = fmaxf(r[c], fmaf(v[c], sc[c], sh[c]));
+    for (int u = 0; u < U; ++u) {
+      const long i = i0 + u * step;
+      live[u] = i < total;
+      hx[u] = hy[u] = false;
+      cgs[u] = 0;
+      if (!live[u]) continue;
+      int cg, xo, yo, n;
+      split_index(i, CG, Wo, Ho, cg, xo, yo, n);
+      cgs[u] = cg;
+      if (!pool) {
+        load_act_vec<VEC>(a, i * VEC, a_bf16, v[u][0]);
+      } else {
+        const int y0 = 2 * yo, x0 = 2 * xo;
+        const long base = (((long)n * H + y0) * W + x0) * C + (long)cg * VEC;
+        hx[u] = x0 + 1 < W;       // SAME pooling: the padded row/column never wins
+        hy[u] = y0 + 1 < H;
+        load_act_vec<VEC>(a, base, a_bf16, v[u][0]);
+        if (hx[u]) load_act_vec<VEC>(a, base + C, a_bf16, v[u][1]);
+        if (hy[u]) load_act_vec<VEC>(a, base + (long)W * C, a_bf16, v[u][2]);
+        if (hx[u] && hy[u]) load_act_vec<VEC>(a, base + (long)W * C + C, a_bf16, v[u][3]);
       }
     }
-    store_planes_vec<VEC>(hi, lo, out_f32, i * VEC, r);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!live[u]) break;
+      if (!fixed_cg || cg_loaded != cgs[u]) {
+        load_f32_vec<VEC>(scale, (long)cgs[u] * VEC, sc);
+        load_f32_vec<VEC>(shift, (long)cgs[u] * VEC, sh);
+        cg_loaded = cgs[u];
+      }
+      float r[VEC];
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) r[c] = fmaf(v[u][0][c], sc[c], sh[c]);
+      if (pool) {
+        if (hx[u]) {
+#pragma unroll
+          for (int c = 0; c < VEC; ++c) r[c] = fmaxf(r[c], fmaf(v[u][1][c], sc[c], sh[c]));
+        }
+        if (hy[u]) {
+#pragma unroll
+          for (int c = 0; c < VEC; ++c) r[c] = fmaxf(r[c], fmaf(v[u][2][c], sc[c], sh[c]));
+        }
+        if (hx[u] && hy[u]) {
+#pragma unroll
+          for (int c = 0; c < VEC; ++c) r[c] = fmaxf(r[c], fmaf(v[u][3][c], sc[c], sh[c]));
+        }
+      }
+      store_planes_vec<VEC>(hi, lo, out_f32, (i0 + u * step) * VEC, r);
+    }
   }
 }
 
@@ -190,7 +210,7 @@ __device__ __forceinline__ void resize_sample(const void* __restrict__ a, int a_
 // all nine taps, divided by 3 in IEEE and converted the unused residual plane: 638 instructions per 8-channel item, instruction-bound
 // at 0.82 ms for 0.82 GB of traffic.)
 template <int VEC>
-__global__ void upsample_avg3_kernel(const void* __restrict__ a1, const void* __restrict__ a2, const void* __restrict__ a3, int a_bf16,
+__global__ void __launch_bounds__(256, 2) upsample_avg3_kernel(const void* __restrict__ a1, const void* __restrict__ a2, const void* __restrict__ a3, int a_bf16,
                                      const float* __restrict__ ss /* [6][C]: scale1, shift1, scale2, shift2, scale3, shift3 */,
                                      int B, int H, int W, int H2, int W2, int H3, int W3, int C, __nv_bfloat16* __restrict__ hi,
                                      __nv_bfloat16* __restrict__ lo, float* __restrict__ out_f32) {

@@ -95,7 +95,8 @@ __global__ void tap_scatter_planes_kernel(const float* __restrict__ g, int B, in
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float v = (src != nullptr && co < Cout) ? src[co] : 0.f;
-      split_bf16(v, h[e], l[e]);
+      h[e] = __float2bfloat16_rn(v);
+      if (lo) l[e] = __float2bfloat16_rn(v - __bfloat162float(h[e]));      // residual plane: fp32 configuration only
       if (++co == KP) { co = 0; ++tap; locate(); }
     }
     reinterpret_cast<uint4*>(hi)[i] = *reinterpret_cast<uint4*>(h);

@@ -549,13 +549,16 @@ def sec_cta2():
 
 
 def sec_halo2():
-    """halo-mode layers with N = 128: one M tile per weight stage (default) vs two (variant bit 3), interleaved, batch 64"""
-    for (B, H, W, Cin, Cout, k) in [(64, 120, 180, 64, 128, 5), (64, 60, 90, 256, 128, 5), (64, 60, 90, 64, 128, 5), (64, 30, 45, 256, 128, 5)]:
+    """halo-mode layers: default (two M tiles per weight stage for N = 128, tap groups for N <= 64) vs one tile per stage (variant 8) vs
+    two tiles with one tap per stage for N <= 64 too (variant 16), interleaved, batch 64"""
+    for (B, H, W, Cin, Cout, k) in [(64, 120, 180, 64, 128, 5), (64, 60, 90, 256, 128, 5), (64, 120, 180, 128, 64, 5), (64, 60, 90, 128, 64, 5),
+                                    (64, 240, 360, 64, 64, (3, 1))]:
         xp = ops.Planes(torch.randn(B, H, W, Cin, device=dev).to(torch.bfloat16), None)
-        wp = ops.Planes((torch.randn(k * k, Cout, Cin, device=dev) / np.sqrt(k * k * Cin)).to(torch.bfloat16), None)
-        fl = 2.0 * B * H * W * k * k * Cin * Cout
-        med = _interleaved([(lambda v=v: ops.conv2d_planes(xp, wp, None, Cout, k, relu=True, out_bf16=True, variant=v)) for v in (0, 8)])
-        print('HALO %dx%d Cin%d Cout%d k%d: ' % (H, W, Cin, Cout, k) + '  '.join('v%d %.3f ms (%.0f TF)' % (v, m, fl / m / 1e9) for v, m in zip((0, 8), med)),
+        kh, kw = ops._khw(k)
+        wp = ops.Planes((torch.randn(kh * kw, Cout, Cin, device=dev) / np.sqrt(kh * kw * Cin)).to(torch.bfloat16), None)
+        fl = 2.0 * B * H * W * kh * kw * Cin * Cout
+        med = _interleaved([(lambda v=v: ops.conv2d_planes(xp, wp, None, Cout, k, relu=True, out_bf16=True, variant=v)) for v in (0, 8, 16)])
+        print('HALO %dx%d Cin%d Cout%d k%s: ' % (H, W, Cin, Cout, k) + '  '.join('v%d %.3f ms (%.0f TF)' % (v, m, fl / m / 1e9) for v, m in zip((0, 8, 16), med)),
               flush=True)
 
 
