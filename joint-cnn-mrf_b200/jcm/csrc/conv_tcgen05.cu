@@ -1097,7 +1097,7 @@ extern "C" int jcm_conv2d_fwd(const void* x_hi, const void* x_lo, const void* w_
 
 // jcm_conv2d_fwd with the kernel variant forced (tests and measurements; every variant computes the same values):
 // bit 0 = single-CTA kernel instead of the CTA pair, bit 1 = uniform tile grid instead of the mixed-shape plan, bit 2 = no N-split tail,
-// bit 3 = halo mode with one M tile per weight stage (N = 128 layers) instead of two, bit 4 = two tiles per stage for N <= 64 too.
+// bit 3 = halo mode with one M tile per weight stage instead of two, bit 4 = one tile per stage (tap groups) for N <= 64 only.
 extern "C" int jcm_conv2d_fwd_variant(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
                                       void* y, int y_bf16, int B, int H, int W, int Cin, int Cout, int Cout_pad, int ksize, int kw,
                                       int relu, int variant, void* stream) {
@@ -1198,9 +1198,10 @@ int jcm_conv_igemm_ex(const ConvExArgs& a) {
     // Two M tiles per weight stage: the weights then stream from L2 once per PAIR of tiles (for the 5x5 layers they are 3/4 of a
     // tile's L2->SM traffic).  Needs four halo patches (two tiles, double-buffered) next to three weight stages, and both tiles'
     // accumulators in one 256-column TMEM stage.  Measured (tests/gpu_diag.py halo2, profiles/r02/diag_halo2.txt, isolated, batch 64):
-    // 0.576 -> 0.440 ms on the 64->128 5x5 layer at 120x180, -23 .. -24 % on the other N = 128 layers.  Default for N = 128 (one tap
-    // per weight stage); variant bit 3 turns it off, bit 4 extends it to N <= 64 with one tap per stage instead of a tap group.
-    if (p.halo && !(a.variant & 8) && p.block_n <= 128 && (p.b_group == 1 || (a.variant & 16))) {
+    // 0.576 -> 0.440 ms on the 64->128 5x5 layer at 120x180, -23 % on the other N = 128 layers; for N <= 64 (one tap per weight
+    // stage instead of a tap group) 0.843 -> 0.717 ms on 128->64 at 120x180, 0.430 -> 0.382 ms on conv1_fullres.  Variant bit 3 turns
+    // it off; bit 4 keeps the tap groups of the N <= 64 layers instead (one tile per stage there).
+    if (p.halo && !(a.variant & 8) && p.block_n <= 128 && (p.b_group == 1 || !(a.variant & 16))) {
       const int b_stride1 = p.b_slot;
       const int budget2 = 225 * 1024 - epi_bytes - 4 * p.a_stride;
       if (budget2 >= 3 * b_stride1) {

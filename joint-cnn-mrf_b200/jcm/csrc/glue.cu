@@ -104,10 +104,9 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblock
 
 // ------------------------------------------------------------------------------------------- BN apply (+pool)
 template <int VEC>
-__global__ void __launch_bounds__(256, 2)
-bn_apply_pool_kernel(const void* __restrict__ a, int a_bf16, const float* __restrict__ scale, const float* __restrict__ shift,
-                     int B, int H, int W, int C, int pool, __nv_bfloat16* __restrict__ hi,
-                     __nv_bfloat16* __restrict__ lo, float* __restrict__ out_f32) {
+__global__ void bn_apply_pool_kernel(const void* __restrict__ a, int a_bf16, const float* __restrict__ scale, const float* __restrict__ shift,
+                                     int B, int H, int W, int C, int pool, __nv_bfloat16* __restrict__ hi,
+                                     __nv_bfloat16* __restrict__ lo, float* __restrict__ out_f32) {
   const int Ho = pool ? (H + 1) / 2 : H, Wo = pool ? (W + 1) / 2 : W;
   const int CG = C / VEC;
   const long total = (long)B * Ho * Wo * CG;
@@ -115,63 +114,118 @@ bn_apply_pool_kernel(const void* __restrict__ a, int a_bf16, const float* __rest
   const bool fixed_cg = (step % CG) == 0;      // every thread then keeps one channel group: scale / shift stay in registers
   float sc[VEC], sh[VEC];
   int cg_loaded = -1;
-  // U work items per thread and iteration, all loads issued before the first use (one item at a time left this kernel waiting on
-  // the long scoreboard at 3.7 TB/s)
-  constexpr int U = 2;
-  for (long i0 = blockIdx.x * (long)blockDim.x + threadIdx.x; i0 < total; i0 += U * step) {
-    float v[U][4][VEC];
-    bool hx[U], hy[U], live[U];
-    int cgs[U];
+  // (measured: two items per thread with all loads first took this kernel from 54 to 116 registers and from 0.77 to 1.27 ms per
+  // step - four resident blocks of one item each keep more bytes in flight than two blocks of two)
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += step) {
+    int cg, xo, yo, n;
+    split_index(i, CG, Wo, Ho, cg, xo, yo, n);
+    float r[VEC];
+    if (!fixed_cg || cg_loaded != cg) {
+      load_f32_vec<VEC>(scale, (long)cg * VEC, sc);
+      load_f32_vec<VEC>(shift, (long)cg * VEC, sh);
+      cg_loaded = cg;
+    }
+    if (!pool) {
+      load_act_vec<VEC>(a, i * VEC, a_bf16, r);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long i = i0 + u * step;
-      live[u] = i < total;
-      hx[u] = hy[u] = false;
-      cgs[u] = 0;
-      if (!live[u]) continue;
-      int cg, xo, yo, n;
-      split_index(i, CG, Wo, Ho, cg, xo, yo, n);
-      cgs[u] = cg;
-      if (!pool) {
-        load_act_vec<VEC>(a, i * VEC, a_bf16, v[u][0]);
-      } else {
-        const int y0 = 2 * yo, x0 = 2 * xo;
-        const long base = (((long)n * H + y0) * W + x0) * C + (long)cg * VEC;
-        hx[u] = x0 + 1 < W;       // SAME pooling: the padded row/column never wins
-        hy[u] = y0 + 1 < H;
-        load_act_vec<VEC>(a, base, a_bf16, v[u][0]);
-        if (hx[u]) load_act_vec<VEC>(a, base + C, a_bf16, v[u][1]);
-        if (hy[u]) load_act_vec<VEC>(a, base + (long)W * C, a_bf16, v[u][2]);
-        if (hx[u] && hy[u]) load_act_vec<VEC>(a, base + (long)W * C + C, a_bf16, v[u][3]);
+      for (int c = 0; c < VEC; ++c) r[c] = fmaf(r[c], sc[c], sh[c]);
+    } else {
+      const int y0 = 2 * yo, x0 = 2 * xo;
+      const long base = (((long)n * H + y0) * W + x0) * C + (long)cg * VEC;
+      const bool hx = x0 + 1 < W, hy = y0 + 1 < H;  // SAME pooling: the padded row/column never wins
+      float v1[VEC], v2[VEC], v3[VEC];
+      load_act_vec<VEC>(a, base, a_bf16, r);
+      if (hx) load_act_vec<VEC>(a, base + C, a_bf16, v1);
+      if (hy) load_act_vec<VEC>(a, base + (long)W * C, a_bf16, v2);
+      if (hx && hy) load_act_vec<VEC>(a, base + (long)W * C + C, a_bf16, v3);
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) r[c] = fmaf(r[c], sc[c], sh[c]);
+      if (hx) {
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) r[c] = fmaxf(r[c], fmaf(v1[c], sc[c], sh[c]));
+      }
+      if (hy) {
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) r[c] = fmaxf(r[c], fmaf(v2[c], sc[c], sh[c]));
+      }
+      if (hx && hy) {
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) r[c] = fmaxf(r[c], fmaf(v3[c], sc[c], sh[c]));
       }
     }
+    store_planes_vec<VEC>(hi, lo, out_f32, i * VEC, r);
+  }
+}
+
+// bf16 configuration (bf16 activation in, bf16 hi plane out, grid stride a multiple of the channel-group count): the next item's
+// loads (one 16-byte word, or the four of a pooling window) are in flight while the current item is processed.
+__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (!live[u]) break;
-      if (!fixed_cg || cg_loaded != cgs[u]) {
-        load_f32_vec<VEC>(scale, (long)cgs[u] * VEC, sc);
-        load_f32_vec<VEC>(shift, (long)cgs[u] * VEC, sh);
-        cg_loaded = cgs[u];
-      }
-      float r[VEC];
-#pragma unroll
-      for (int c = 0; c < VEC; ++c) r[c] = fmaf(v[u][0][c], sc[c], sh[c]);
-      if (pool) {
-        if (hx[u]) {
-#pragma unroll
-          for (int c = 0; c < VEC; ++c) r[c] = fmaxf(r[c], fmaf(v[u][1][c], sc[c], sh[c]));
-        }
-        if (hy[u]) {
-#pragma unroll
-          for (int c = 0; c < VEC; ++c) r[c] = fmaxf(r[c], fmaf(v[u][2][c], sc[c], sh[c]));
-        }
-        if (hx[u] && hy[u]) {
-#pragma unroll
-          for (int c = 0; c < VEC; ++c) r[c] = fmaxf(r[c], fmaf(v[u][3][c], sc[c], sh[c]));
-        }
-      }
-      store_planes_vec<VEC>(hi, lo, out_f32, (i0 + u * step) * VEC, r);
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+template <int POOL>
+__global__ void __launch_bounds__(256, 3)
+bn_apply_pool_bf16_kernel(const uint4* __restrict__ a, const float* __restrict__ scale, const float* __restrict__ shift, int B, int H, int W,
+                          int C, uint4* __restrict__ hi) {
+  constexpr int VEC = 8;
+  const int Ho = POOL ? (H + 1) / 2 : H, Wo = POOL ? (W + 1) / 2 : W;
+  const int CG = C / VEC;
+  const long total = (long)B * Ho * Wo * CG;
+  const long step = (long)gridDim.x * blockDim.x;
+  long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cg = (int)(i % CG);
+  float sc[VEC], sh[VEC];
+  load_f32_vec<VEC>(scale, (long)cg * VEC, sc);
+  load_f32_vec<VEC>(shift, (long)cg * VEC, sh);
+  uint4 nraw[POOL ? 4 : 1];
+  unsigned nokm = 1u;
+  const long row8 = (long)W * CG;
+  auto fetch = [&](long it) {
+    if (!POOL) {
+      nraw[0] = a[it];
+    } else {
+      int cgi, xo, yo, n;
+      split_index(it, CG, Wo, Ho, cgi, xo, yo, n);
+      const int y0 = 2 * yo, x0 = 2 * xo;
+      const long base = (((long)n * H + y0) * W + x0) * CG + cg;
+      const bool hx = x0 + 1 < W, hy = y0 + 1 < H;      // SAME pooling: the padded row / column never wins
+      nokm = 1u | (hx ? 2u : 0u) | (hy ? 4u : 0u) | ((hx && hy) ? 8u : 0u);
+      nraw[0] = a[base];
+      if (hx) nraw[POOL ? 1 : 0] = a[base + CG];
+      if (hy) nraw[POOL ? 2 : 0] = a[base + row8];
+      if (hx && hy) nraw[POOL ? 3 : 0] = a[base + row8 + CG];
     }
+  };
+  fetch(i);
+  for (; i < total; i += step) {
+    uint4 raw[POOL ? 4 : 1];
+#pragma unroll
+    for (int k = 0; k < (POOL ? 4 : 1); ++k) raw[k] = nraw[k];
+    const unsigned okm = nokm;
+    if (i + step < total) fetch(i + step);
+    float r[VEC], v[VEC];
+    unpack8(raw[0], v);
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) r[c] = fmaf(v[c], sc[c], sh[c]);
+    if (POOL) {
+#pragma unroll
+      for (int e = 1; e < 4; ++e) {
+        if ((okm >> e) & 1u) {
+          unpack8(raw[POOL ? e : 0], v);
+#pragma unroll
+          for (int c = 0; c < VEC; ++c) r[c] = fmaxf(r[c], fmaf(v[c], sc[c], sh[c]));
+        }
+      }
+    }
+    __align__(16) __nv_bfloat16 h[VEC];
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) h[c] = __float2bfloat16_rn(r[c]);
+    hi[i] = *reinterpret_cast<uint4*>(h);
   }
 }
 
@@ -263,6 +317,105 @@ __global__ void __launch_bounds__(256, 2) upsample_avg3_kernel(const void* __res
 #pragma unroll
     for (int c = 0; c < VEC; ++c) r[c] = fmaf(s1[c], v1[c], fmaf(s2[c], v2[c], fmaf(s3[c], v3[c], t0[c])));
     store_planes_vec<VEC>(hi, lo, out_f32, i * VEC, r);
+  }
+}
+
+// bf16 configuration (bf16 bank outputs, bf16 hi plane only, grid stride a multiple of the channel-group count): the same arithmetic
+// with the NEXT item's nine 16-byte loads in flight while the current item is interpolated (the kernel above waits on the long
+// scoreboard with 16 warps per SM: 0.78 ms for 0.82 GB).
+__global__ void __launch_bounds__(256, 2)
+upsample_avg3_bf16_kernel(const uint4* __restrict__ a1, const uint4* __restrict__ a2, const uint4* __restrict__ a3,
+                          const float* __restrict__ ss, int B, int H, int W, int H2, int W2, int H3, int W3, int C, uint4* __restrict__ hi) {
+  extern __shared__ TapTab tabs[];
+  TapTab* ty2 = tabs;
+  TapTab* tx2 = ty2 + H;
+  TapTab* ty3 = tx2 + W;
+  TapTab* tx3 = ty3 + H;
+  for (int i = threadIdx.x; i < 2 * (H + W); i += blockDim.x) {
+    const int bank3 = i >= H + W, j = bank3 ? i - (H + W) : i;
+    const bool row = j < H;
+    const int d = row ? j : j - H;
+    TapTab t;
+    legacy_tap(d, row ? (bank3 ? H3 : H2) : (bank3 ? W3 : W2), row ? H : W, t.lo, t.hi, t.w);
+    tabs[i] = t;
+  }
+  __syncthreads();
+  constexpr int VEC = 8;
+  const int CG = C / VEC;
+  const long total = (long)B * H * W * CG;
+  const long step = (long)gridDim.x * blockDim.x;     // a multiple of CG (checked by the launcher): one channel group per thread
+  long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cg = (int)(i % CG);
+  float s1[VEC], s2[VEC], s3[VEC], t0[VEC];
+  {
+    float u[VEC];
+    load_f32_vec<VEC>(ss + 0 * C, (long)cg * VEC, s1);
+    load_f32_vec<VEC>(ss + 2 * C, (long)cg * VEC, s2);
+    load_f32_vec<VEC>(ss + 4 * C, (long)cg * VEC, s3);
+    load_f32_vec<VEC>(ss + 1 * C, (long)cg * VEC, t0);
+    load_f32_vec<VEC>(ss + 3 * C, (long)cg * VEC, u);
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) t0[c] += u[c];
+    load_f32_vec<VEC>(ss + 5 * C, (long)cg * VEC, u);
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) {
+      t0[c] = (t0[c] + u[c]) * (1.0f / 3.0f);
+      s1[c] *= (1.0f / 3.0f); s2[c] *= (1.0f / 3.0f); s3[c] *= (1.0f / 3.0f);
+    }
+  }
+  uint4 nraw[9];
+  float nw[4];      // wx2, wy2, wx3, wy3 of the prefetched item
+  auto fetch = [&](long it) {
+    int cgi, x, y, n;
+    split_index(it, CG, W, H, cgi, x, y, n);
+    const TapTab y2 = ty2[y], x2 = tx2[x], y3 = ty3[y], x3 = tx3[x];
+    const long b2 = ((long)n * H2 * W2) * CG + cg, b3 = ((long)n * H3 * W3) * CG + cg;
+    nraw[0] = a1[it];
+    nraw[1] = a2[b2 + ((long)y2.lo * W2 + x2.lo) * CG];
+    nraw[2] = a2[b2 + ((long)y2.lo * W2 + x2.hi) * CG];
+    nraw[3] = a2[b2 + ((long)y2.hi * W2 + x2.lo) * CG];
+    nraw[4] = a2[b2 + ((long)y2.hi * W2 + x2.hi) * CG];
+    nraw[5] = a3[b3 + ((long)y3.lo * W3 + x3.lo) * CG];
+    nraw[6] = a3[b3 + ((long)y3.lo * W3 + x3.hi) * CG];
+    nraw[7] = a3[b3 + ((long)y3.hi * W3 + x3.lo) * CG];
+    nraw[8] = a3[b3 + ((long)y3.hi * W3 + x3.hi) * CG];
+    nw[0] = x2.w; nw[1] = y2.w; nw[2] = x3.w; nw[3] = y3.w;
+  };
+  fetch(i);
+  for (; i < total; i += step) {
+    uint4 raw[9];
+    float w[4];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) raw[k] = nraw[k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = nw[k];
+    if (i + step < total) fetch(i + step);
+    float r[VEC];
+    {
+      float v[VEC];
+      unpack8(raw[0], v);
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) r[c] = fmaf(s1[c], v[c], t0[c]);
+    }
+#pragma unroll
+    for (int bank = 0; bank < 2; ++bank) {
+      float tl[VEC], tr[VEC], bl[VEC], br[VEC];
+      unpack8(raw[1 + 4 * bank], tl);
+      unpack8(raw[2 + 4 * bank], tr);
+      unpack8(raw[3 + 4 * bank], bl);
+      unpack8(raw[4 + 4 * bank], br);
+      const float wx = w[2 * bank], wy = w[2 * bank + 1];
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) {
+        const float top = tl[c] + (tr[c] - tl[c]) * wx, bot = bl[c] + (br[c] - bl[c]) * wx;
+        r[c] = fmaf(bank ? s3[c] : s2[c], top + (bot - top) * wy, r[c]);
+      }
+    }
+    __align__(16) __nv_bfloat16 h[VEC];
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) h[c] = __float2bfloat16_rn(r[c]);
+    hi[i] = *reinterpret_cast<uint4*>(h);
   }
 }
 
@@ -434,7 +587,13 @@ extern "C" int jcm_bn_apply_pool(const void* a, int a_bf16, const float* scale, 
   JCM_CHECK_ARG(a && scale && shift && (out_hi || out_f32), "jcm_bn_apply_pool: null pointer");
   JCM_CHECK_ARG((C % 4) == 0, "jcm_bn_apply_pool: C must be a multiple of 4, got %d", C);
   const int Ho = pool ? (H + 1) / 2 : H, Wo = pool ? (W + 1) / 2 : W;
-  if (a_bf16 && (C % 8) == 0) {
+  if (a_bf16 && (C % 8) == 0 && out_hi && !out_lo && !out_f32 && ((long)grid_for((long)B * Ho * Wo * (C / 8), 256) * 256) % (C / 8) == 0) {
+    const long total = (long)B * Ho * Wo * (C / 8);
+    if (pool)
+      bn_apply_pool_bf16_kernel<1><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, scale, shift, B, H, W, C, (uint4*)out_hi);
+    else
+      bn_apply_pool_bf16_kernel<0><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, scale, shift, B, H, W, C, (uint4*)out_hi);
+  } else if (a_bf16 && (C % 8) == 0) {
     const long total = (long)B * Ho * Wo * (C / 8);
     bn_apply_pool_kernel<8><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a, a_bf16, scale, shift, B, H, W, C, pool, (__nv_bfloat16*)out_hi,
                                                                                     (__nv_bfloat16*)out_lo, out_f32);
@@ -453,7 +612,11 @@ extern "C" int jcm_upsample_avg3(const void* a1, const void* a2, const void* a3,
   JCM_CHECK_ARG((C % 4) == 0, "jcm_upsample_avg3: C must be a multiple of 4, got %d", C);
   const size_t tab_bytes = (size_t)2 * (H + W) * sizeof(TapTab);
   JCM_CHECK_ARG(tab_bytes <= 40 * 1024, "jcm_upsample_avg3: map %dx%d too large for the tap tables", H, W);
-  if (a_bf16 && (C % 8) == 0) {
+  if (a_bf16 && (C % 8) == 0 && out_hi && !out_lo && !out_f32 && ((long)grid_for((long)B * H * W * (C / 8), 256) * 256) % (C / 8) == 0) {
+    const long total = (long)B * H * W * (C / 8);
+    upsample_avg3_bf16_kernel<<<grid_for(total, 256), 256, tab_bytes, (cudaStream_t)stream>>>(
+        (const uint4*)a1, (const uint4*)a2, (const uint4*)a3, scale_shift, B, H, W, H2, W2, H3, W3, C, (uint4*)out_hi);
+  } else if (a_bf16 && (C % 8) == 0) {
     const long total = (long)B * H * W * (C / 8);
     upsample_avg3_kernel<8><<<grid_for(total, 256), 256, tab_bytes, (cudaStream_t)stream>>>(a1, a2, a3, a_bf16, scale_shift, B, H, W, H2, W2, H3, W3, C,
                                                                                     (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32);

@@ -549,8 +549,8 @@ def sec_cta2():
 
 
 def sec_halo2():
-    """halo-mode layers: default (two M tiles per weight stage for N = 128, tap groups for N <= 64) vs one tile per stage (variant 8) vs
-    two tiles with one tap per stage for N <= 64 too (variant 16), interleaved, batch 64"""
+    """halo-mode layers: default (two M tiles per weight stage) vs one tile per stage (variant 8) vs one tile per stage with tap groups
+    for N <= 64 only (variant 16), interleaved, batch 64"""
     for (B, H, W, Cin, Cout, k) in [(64, 120, 180, 64, 128, 5), (64, 60, 90, 256, 128, 5), (64, 120, 180, 128, 64, 5), (64, 60, 90, 128, 64, 5),
                                     (64, 240, 360, 64, 64, (3, 1))]:
         xp = ops.Planes(torch.randn(B, H, W, Cin, device=dev).to(torch.bfloat16), None)

@@ -146,6 +146,20 @@ def test_batch_norm_and_pool(jcm, shape, train):
         assert rel(pooledb, orc.max_pool_layer(refb)) < 1e-5
 
 
+@pytest.mark.parametrize('shape', [(2, 45, 31, 64), (1, 15, 23, 512), (3, 24, 36, 128)])
+@pytest.mark.parametrize('pool', [False, True])
+def test_bn_apply_pool_bf16_operand_plane(jcm, shape, pool):
+    """The bf16 configuration's form of BN-apply (+ 2x2 SAME max-pool): bf16 activation in, bf16 operand plane out (the prefetching
+    kernel).  Equal to the fp32-output kernel's result rounded to bf16."""
+    g = torch.Generator().manual_seed(4)
+    a = torch.relu(torch.randn(*shape, generator=g)).to(torch.bfloat16)
+    ss = torch.stack([torch.rand(shape[3], generator=g) + 0.5, torch.randn(shape[3], generator=g)]).cuda()
+    want = jcm.ops.bn_apply_pool(a.cuda(), ss, pool, False, want_planes=False, want_f32=True)
+    planes = jcm.ops.bn_apply_pool(a.cuda(), ss, pool, False)
+    assert planes.lo is None and tuple(planes.hi.shape) == tuple(want.shape)
+    assert torch.equal(planes.hi, want.to(torch.bfloat16))
+
+
 def test_upsample_avg3(jcm):
     g = torch.Generator().manual_seed(2)
     a1, a2, a3 = (torch.randn(2, h, w, 64, generator=g) for h, w in ((60, 90), (30, 45), (15, 23)))
@@ -160,6 +174,11 @@ def test_upsample_avg3(jcm):
             + orc.resize_images(d(b3) * d(ss6[4]) + d(ss6[5]), 60, 90)) / 3
     outb = jcm.ops.upsample_avg3(b1.cuda(), b2.cuda(), b3.cuda(), ss6.cuda(), False, want_planes=False, want_f32=True)
     assert rel(outb, refb) < 1e-5
+    # the bf16 configuration's form (bf16 in, bf16 operand plane out: the prefetching kernel): the same values rounded to bf16
+    planes = jcm.ops.upsample_avg3(b1.cuda(), b2.cuda(), b3.cuda(), ss6.cuda(), False)
+    assert planes.lo is None and planes.hi.dtype == torch.bfloat16
+    got = planes.hi.float().cpu().double()
+    assert float(((got - refb).abs() / (refb.abs() + 1e-2)).max()) < 2.0 ** -7          # one bf16 rounding (2^-9) + fp32 reassociation
 
 
 # ------------------------------------------------------------------------------------------------ heads

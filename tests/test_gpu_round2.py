@@ -244,9 +244,9 @@ def test_conv_pair_plan_tail_variants_are_bit_identical(jcm, case, split):
 @pytest.mark.parametrize('case', [(3, 24, 32, 64, 128, 5), (1, 20, 33, 64, 64, 5), (5, 60, 90, 128, 64, 5), (1, 120, 180, 64, 128, 5), (3, 9, 200, 64, 16, 3),
                                   (2, 30, 45, 256, 128, 5)])
 def test_conv_halo_two_tiles_per_weight_stage_is_bit_identical(jcm, case):
-    """Halo mode (N <= 128 layers: the 5x5 convolutions): two M tiles share every weight stage of the N = 128 layers (the weights
-    stream from L2 once per pair of tiles; variant bit 4 does the same for N <= 64).  Same bits as one tile per stage (variant bit 3)
-    and as the oracle; odd tile counts leave a last group of one."""
+    """Halo mode (N <= 128 layers: the 5x5 convolutions and conv1): two M tiles share every weight stage (the weights stream from L2
+    once per pair of tiles).  Same bits as one tile per stage (variant bits 3 / 4) and as the oracle; odd tile counts leave a last
+    group of one."""
     B, H, W, Cin, Cout, k = case
     g = torch.Generator().manual_seed(sum(case))
     x = torch.randn(B, H, W, Cin, generator=g)
