@@ -248,7 +248,8 @@ int jcm_fma_peak(float* scratch, int blocks, int iters, int packed, double* flop
 int jcm_debug_tile_plan(int H, int W, int cap, int exact_px, int max_shapes, int uniform_tiles, int* out, int max_out);
 
 /* Test / measurement switch of jcm_conv2d_wgrad (every variant computes the same values up to the summation order of the k-splits):
- * bit 0 = single-CTA kernel instead of the CTA pair, bit 1 = uniform patch grid instead of the mixed-shape plan.  Returns the previous
+ * bit 0 = single-CTA kernel instead of the CTA pair, bit 1 = uniform patch grid instead of the mixed-shape plan, bit 2 = one tap per task
+ * instead of tap groups on the narrow layers.  Returns the previous
  * value.  Process-wide; the product path never calls it. */
 int jcm_debug_set_wgrad_variant(int variant);
 

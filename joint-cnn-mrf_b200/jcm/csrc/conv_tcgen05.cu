@@ -1370,6 +1370,7 @@ struct WgradParams {
   int kc_n, kc_m;                  // channels per N-side / M-side box: 64, 32 or 16
   int splits, total_patches;
   int terms, stages, a_bytes, b_bytes, stage_bytes;
+  int tgroup;          // conv_wgrad_taps_kernel: taps per task (1 elsewhere)
   // mixed-shape patch plan (tiling.cuh, exact 64-pixel boxes; one term): plan_n > 0 patches per image replace the uniform grid
   int plan_n;
   uint8_t px0[kPlanMaxTiles], py0[kPlanMaxTiles], pshape[kPlanMaxTiles];
@@ -1548,6 +1549,198 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_m_hi, const __grid_con
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (c0 + j < p.block_n) orow[c0 + j] = __uint_as_float(v[j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// Tap-group form of the weight-gradient kernel for the narrow layers (N tile <= 64 channels: conv1_*, conv2_*; one term).  Per
+// 64-pixel k-block the plain kernel loads a gradient box and an input box (24 KB for conv2) for 128 clocks of MMA - far more than
+// L2 delivers - and every tap task re-reads the SAME gradient box.  Here one task owns `tgroup` consecutive taps: the unshifted
+// operand (the gradient G) is loaded once per k-block, the shifted operand (the layer input X) once per tap, and the taps accumulate
+// side by side in TMEM (tgroup x block_n <= 256 columns per accumulator stage).
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_taps_kernel(const __grid_constant__ CUtensorMap map_m_hi, const __grid_constant__ CUtensorMap map_n_hi,
+                       const __grid_constant__ WgradShapeMaps smaps, const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[kMaxStages]);
+  const uint32_t bar_tfull = smem_u32(&bars[2 * kMaxStages]);
+  const uint32_t bar_tempty = smem_u32(&bars[2 * kMaxStages + 2]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_tfull + 8 * s, 1);
+      mbar_init(bar_tempty + 8 * s, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int tap_groups = (p.taps + p.tgroup - 1) / p.tgroup;
+  const int tasks_per_split = tap_groups * p.m_tiles * p.n_tiles;
+  const int total_tasks = p.splits * tasks_per_split;
+  const int patches_per_img = p.plan_n ? p.plan_n : p.tiles_x * p.tiles_y;
+  const int m_boxes = kTileM / p.kc_m;
+  const int n_boxes = p.block_n / p.kc_n;
+  const int m_box_bytes = kWgPix * p.kc_m * 2;
+  const int n_box_bytes = kWgPix * p.kc_n * 2;
+  // stage layout: [M-side boxes][N-side boxes]; the shifted side (the layer input) has one box per tap of the group
+  const uint32_t n_off = (uint32_t)(p.shift_m ? p.tgroup : 1) * p.a_bytes;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int task = blockIdx.x; task < total_tasks; task += gridDim.x) {
+        const int split = task / tasks_per_split;
+        int r = task - split * tasks_per_split;
+        const int tg = r / (p.m_tiles * p.n_tiles);
+        r -= tg * (p.m_tiles * p.n_tiles);
+        const int mt = r / p.n_tiles, nt = r - mt * p.n_tiles;
+        const int tap0 = tg * p.tgroup, ntap = min(p.tgroup, p.taps - tap0);
+        const int p0 = (int)((long)split * p.total_patches / p.splits);
+        const int p1 = (int)((long)(split + 1) * p.total_patches / p.splits);
+        int img = p0 / patches_per_img;
+        int q = p0 - img * patches_per_img;
+        int ty = p.plan_n ? 0 : q / p.tiles_x, tx = p.plan_n ? 0 : q - ty * p.tiles_x;
+        const int mblk0 = mt * m_boxes, nblk0 = nt * n_boxes;
+        const uint32_t tx_bytes = (uint32_t)(p.shift_m ? ntap : 1) * p.a_bytes + (uint32_t)(p.shift_n ? ntap : 1) * p.b_bytes;
+        for (int patch = p0; patch < p1; ++patch) {
+          int x0 = tx * p.TW, y0 = ty * p.TH;
+          const void *pm = (const void*)&map_m_hi, *pn = (const void*)&map_n_hi;
+          if (p.plan_n) {
+            x0 = p.px0[q];
+            y0 = p.py0[q];
+            pm = (const void*)&smaps.m[p.pshape[q]];
+            pn = (const void*)&smaps.n[p.pshape[q]];
+          }
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t sa = smem_base + stage * p.stage_bytes;
+          const uint32_t fb = bar_full + 8 * stage;
+          mbar_expect_tx(fb, tx_bytes);
+          if (!p.shift_m) tma_load_5d(sa, pm, fb, 0, x0, y0, img, mblk0);
+          if (!p.shift_n) tma_load_5d(sa + n_off, pn, fb, 0, x0, y0, img, nblk0);
+          for (int j = 0; j < ntap; ++j) {
+            const int tap = tap0 + j;
+            const int dy = tap / p.kw - p.pad, dx = tap % p.kw - p.pad_x;
+            if (p.shift_m) tma_load_5d(sa + j * p.a_bytes, pm, fb, 0, x0 + dx, y0 + dy, img, mblk0);
+            else tma_load_5d(sa + n_off + j * p.b_bytes, pn, fb, 0, x0 + dx, y0 + dy, img, nblk0);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (p.plan_n) {
+            if (++q == p.plan_n) { q = 0; ++img; }
+          } else if (++tx == p.tiles_x) {
+            tx = 0;
+            if (++ty == p.tiles_y) { ty = 0; ++img; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.block_n >> 3) << 17) |
+                             ((uint32_t)(kTileM >> 4) << 24);
+      const uint32_t n_row_bytes = p.kc_n * 2, m_row_bytes = p.kc_m * 2;
+      const uint32_t n_layout = (p.kc_n == 64) ? 2u : (p.kc_n == 32 ? 4u : 6u);
+      const uint32_t m_layout = (p.kc_m == 64) ? 2u : (p.kc_m == 32 ? 4u : 6u);
+      const uint64_t adesc_hi = (make_smem_desc(0, 8 * m_row_bytes, m_layout) & ~(((uint64_t)0x3FFF << 16) | 0x3FFF)) |
+                                ((uint64_t)((m_box_bytes >> 4) & 0x3FFF) << 16);
+      const uint64_t bdesc_hi = (make_smem_desc(0, 8 * n_row_bytes, n_layout) & ~(((uint64_t)0x3FFF << 16) | 0x3FFF)) |
+                                ((uint64_t)((n_box_bytes >> 4) & 0x3FFF) << 16);
+      const uint32_t a_step = p.shift_m ? (uint32_t)p.a_bytes : 0u, b_step = p.shift_n ? (uint32_t)p.b_bytes : 0u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int task = blockIdx.x; task < total_tasks; task += gridDim.x) {
+        const int split = task / tasks_per_split;
+        const int tg = (task - split * tasks_per_split) / (p.m_tiles * p.n_tiles);
+        const int ntap = min(p.tgroup, p.taps - tg * p.tgroup);
+        const int p0 = (int)((long)split * p.total_patches / p.splits);
+        const int p1 = (int)((long)(split + 1) * p.total_patches / p.splits);
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = 0; kb < p1 - p0; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * p.stage_bytes;
+          const uint32_t sb = sa + n_off;
+          for (int j = 0; j < ntap; ++j) {
+#pragma unroll
+            for (int k = 0; k < kWgPix / 16; ++k) {
+              const uint64_t adesc = adesc_hi | (uint64_t)(((sa + j * a_step + k * 16 * m_row_bytes) >> 4) & 0x3FFF);
+              const uint64_t bdesc = bdesc_hi | (uint64_t)(((sb + j * b_step + k * 16 * n_row_bytes) >> 4) & 0x3FFF);
+              tc_mma_bf16(d_tmem + j * p.block_n, adesc, bdesc, idesc, (kb | k) != 0);
+            }
+          }
+          tc_commit(bar_empty + 8 * stage);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(bar_tfull + 8 * acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int task = blockIdx.x; task < total_tasks; task += gridDim.x) {
+      const int split = task / tasks_per_split;
+      int r = task - split * tasks_per_split;
+      const int tg = r / (p.m_tiles * p.n_tiles);
+      r -= tg * (p.m_tiles * p.n_tiles);
+      const int mt = r / p.n_tiles, nt = r - mt * p.n_tiles;
+      const int tap0 = tg * p.tgroup, ntap = min(p.tgroup, p.taps - tap0);
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      for (int j = 0; j < ntap; ++j) {
+        float* orow = p.partial + (((long)split * p.taps + tap0 + j) * p.m_pad + mt * kTileM + row) * p.n_pad + nt * p.block_n;
+        const uint32_t taddr0 = tmem_base + acc * 256 + j * p.block_n + ((uint32_t)(q * 32) << 16);
+        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+          uint32_t v[32];
+          tc_ld32(taddr0 + c0, v);
+          tc_ld_wait();
+          if (c0 + 32 <= p.block_n) {
+#pragma unroll
+            for (int jj = 0; jj < 32; jj += 4)
+              *reinterpret_cast<float4*>(orow + c0 + jj) =
+                  make_float4(__uint_as_float(v[jj]), __uint_as_float(v[jj + 1]), __uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3]));
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj)
+              if (c0 + jj < p.block_n) orow[c0 + jj] = __uint_as_float(v[jj]);
+          }
         }
       }
       tc_fence_before();
@@ -1819,10 +2012,13 @@ struct WgradPlan {
   int x_is_m, m_ch, n_ch, m_tiles, n_tiles, block_n, kc_n, kc_m, m_pad, n_pad, splits, TW, TH, tiles_x, tiles_y, total_patches;
   bool mixed;          // patches follow `tiles` (mixed-shape plan) instead of the uniform TW x TH grid
   bool pair;           // CTA-pair kernel (cta_group::2): even number of M tiles, N tiles of 128 or 256 channels
+  int tgroup;          // > 1: tap-group kernel (narrow layers, one term): taps per task
   TilePlan tiles;
 };
 
-void plan_wgrad(int B, int H, int W, int Cin, int Gc, int ksize, int kw, bool allow_mixed, bool allow_pair, WgradPlan* pl) {
+// variant: bit 0 = single-CTA kernel instead of the CTA pair, bit 1 = uniform patch grid, bit 2 = no tap groups
+void plan_wgrad(int B, int H, int W, int Cin, int Gc, int ksize, int kw, bool one_term, int variant, WgradPlan* pl) {
+  const bool allow_mixed = one_term && !(variant & 2), allow_pair = !(variant & 1), allow_taps = one_term && !(variant & 4);
   pl->x_is_m = Cin >= Gc;
   pl->m_ch = pl->x_is_m ? Cin : Gc;
   pl->n_ch = pl->x_is_m ? Gc : Cin;
@@ -1844,8 +2040,15 @@ void plan_wgrad(int B, int H, int W, int Cin, int Gc, int ksize, int kw, bool al
   // wastes 12 % of the last wave unsplit, 0.5 % with 5 splits; the partial sums cost one extra read in wgrad_reduce_kernel.
   pl->pair = allow_pair && (pl->m_tiles % 2) == 0 && (pl->block_n == 128 || pl->block_n == 256) && (pl->block_n / pl->kc_n) % 2 == 0 &&
              jcm_num_sms() >= 2;
-  // work units and workers of the persistent loop: (tap, M tile, N tile) on every SM, or (tap, M-tile pair, N tile) on SM pairs
-  const int base = ksize * kw * (pl->pair ? pl->m_tiles / 2 : pl->m_tiles) * pl->n_tiles;
+  // narrow layers (N tile <= 64, one term, several taps): tap groups that fill one 256-column TMEM stage
+  pl->tgroup = 1;
+  if (!pl->pair && allow_taps && pl->block_n <= 64 && ksize * kw > 1) {
+    pl->tgroup = 256 / pl->block_n;
+    if (pl->tgroup > 4) pl->tgroup = 4;
+    if (pl->tgroup > ksize * kw) pl->tgroup = ksize * kw;
+  }
+  // work units and workers of the persistent loop: (tap [group], M tile, N tile) on every SM, or (tap, M-tile pair, N tile) on SM pairs
+  const int base = jcm_cdiv(ksize * kw, pl->tgroup) * (pl->pair ? pl->m_tiles / 2 : pl->m_tiles) * pl->n_tiles;
   const int sms = pl->pair ? (jcm_num_sms() & ~1) / 2 : jcm_num_sms();
   int best_s = 1;
   double best_cost = 1e300;
@@ -1863,26 +2066,26 @@ void plan_wgrad(int B, int H, int W, int Cin, int Gc, int ksize, int kw, bool al
 }  // namespace
 
 // Test / measurement switch of jcm_conv2d_wgrad (every variant computes the same values): bit 0 = single-CTA kernel instead of the
-// CTA pair, bit 1 = uniform patch grid instead of the mixed-shape plan.  Process-wide; the product never sets it.
+// CTA pair, bit 1 = uniform patch grid instead of the mixed-shape plan, bit 2 = one tap per task instead of tap groups on the narrow
+// layers.  Process-wide; the product never sets it.
 static int g_wgrad_variant = 0;
 extern "C" int jcm_debug_set_wgrad_variant(int variant) {
   const int old = g_wgrad_variant;
-  g_wgrad_variant = variant & 3;
+  g_wgrad_variant = variant & 7;
   return old;
 }
 
 // bytes of fp32 partial sums jcm_conv2d_wgrad needs in `workspace`
 extern "C" long jcm_conv2d_wgrad_workspace(int B, int H, int W, int Cin, int Gc, int ksize, int kw) {
   if (kw <= 0) kw = ksize;
-  // the larger of the two possible plans (the mixed-shape plan applies to the one-term form only and may pick another split count)
-  WgradPlan pl, pl2;
-  plan_wgrad(B, H, W, Cin, Gc, ksize, kw, true, true, &pl);
-  plan_wgrad(B, H, W, Cin, Gc, ksize, kw, false, true, &pl2);
-  int splits = pl.splits > pl2.splits ? pl.splits : pl2.splits;
-  plan_wgrad(B, H, W, Cin, Gc, ksize, kw, true, false, &pl2);
-  if (pl2.splits > splits) splits = pl2.splits;
-  plan_wgrad(B, H, W, Cin, Gc, ksize, kw, false, false, &pl2);
-  if (pl2.splits > splits) splits = pl2.splits;
+  // the largest split count over all kernel variants (one- / three-term form, test variants): they pick different split counts
+  WgradPlan pl;
+  int splits = 1;
+  for (int one_term = 0; one_term < 2; ++one_term)
+    for (int variant = 0; variant < 8; ++variant) {
+      plan_wgrad(B, H, W, Cin, Gc, ksize, kw, one_term != 0, variant, &pl);
+      if (pl.splits > splits) splits = pl.splits;
+    }
   return (long)splits * ksize * kw * pl.m_pad * pl.n_pad * (long)sizeof(float);
 }
 
@@ -1898,7 +2101,7 @@ extern "C" int jcm_conv2d_wgrad(const void* x_hi, const void* x_lo, const void* 
   JCM_CHECK_ARG(B > 0 && H > 0 && W > 0 && (ksize & 1) && (kw & 1), "jcm_conv2d_wgrad: bad shape");
   JCM_CHECK_ARG((Cin % 16) == 0 && (Gc % 16) == 0 && Cout <= Gc && Cout <= dw_cout_stride, "jcm_conv2d_wgrad: channel counts must be multiples of 16 (Cin=%d Gc=%d)", Cin, Gc);
   WgradPlan pl;
-  plan_wgrad(B, H, W, Cin, Gc, ksize, kw, x_lo == nullptr && !(g_wgrad_variant & 2), !(g_wgrad_variant & 1), &pl);
+  plan_wgrad(B, H, W, Cin, Gc, ksize, kw, x_lo == nullptr, g_wgrad_variant, &pl);
   JCM_CHECK_ARG(pl.n_ch % pl.block_n == 0, "jcm_conv2d_wgrad: N-side channel count %d must be <= 256 or a multiple of 256", pl.n_ch);
   if (workspace_bytes < jcm_conv2d_wgrad_workspace(B, H, W, Cin, Gc, ksize, kw)) {
     jcm_set_error("jcm_conv2d_wgrad: workspace too small");
@@ -1916,9 +2119,12 @@ extern "C" int jcm_conv2d_wgrad(const void* x_hi, const void* x_lo, const void* 
   p.terms = x_lo ? 3 : 1;
   p.a_bytes = kTileM * kWgPix * 2;
   p.b_bytes = (pl.pair ? pl.block_n / 2 : pl.block_n) * kWgPix * 2;      // pair: each CTA holds half of the N-side box
-  p.stage_bytes = ((p.a_bytes + p.b_bytes + 1023) / 1024) * 1024;
+  p.tgroup = pl.tgroup;
+  // tap groups: the shifted side (the layer input) has one box per tap in every stage
+  p.stage_bytes = (((p.shift_m ? p.tgroup : 1) * p.a_bytes + (p.shift_n ? p.tgroup : 1) * p.b_bytes + 1023) / 1024) * 1024;
   p.stages = (200 * 1024) / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
+  JCM_CHECK_ARG(p.stages >= 2, "jcm_conv2d_wgrad: tap group of %d does not fit shared memory", p.tgroup);
   p.partial = (float*)workspace;
   p.plan_n = pl.mixed ? pl.tiles.n_tiles : 0;
   if (pl.mixed) {
@@ -1976,6 +2182,12 @@ extern "C" int jcm_conv2d_wgrad(const void* x_hi, const void* x_lo, const void* 
     if (grid2 > 2 * pair_tasks) grid2 = 2 * pair_tasks;
     JCM_CUDA(cudaFuncSetAttribute(conv_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512));
     conv_wgrad_pair_kernel<<<grid2, kThreads, smem, (cudaStream_t)stream>>>(mm_hi, mm_lo, mn_hi, mn_lo, wsm, p);
+  } else if (p.tgroup > 1) {
+    const int total_tasks = p.splits * jcm_cdiv(p.taps, p.tgroup) * p.m_tiles * p.n_tiles;
+    int grid = jcm_num_sms();
+    if (grid > total_tasks) grid = total_tasks;
+    JCM_CUDA(cudaFuncSetAttribute(conv_wgrad_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512));
+    conv_wgrad_taps_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(mm_hi, mn_hi, wsm, p);
   } else {
     const int total_tasks = p.splits * p.taps * p.m_tiles * p.n_tiles;
     int grid = jcm_num_sms();

@@ -565,18 +565,20 @@ def sec_halo2():
 def sec_wgpair():
     """weight gradient: CTA-pair kernel / mixed-shape patch plan variants (bit 0 single-CTA, bit 1 uniform grid), batch 64, interleaved"""
     from jcm import train as jt
-    for (B, H, W, Cin, Cout, k) in [(64, 60, 90, 512, 512, 9), (64, 60, 90, 256, 512, 9), (64, 30, 45, 256, 512, 9), (64, 60, 90, 128, 256, 5)]:
+    for (B, H, W, Cin, Cout, k) in [(64, 60, 90, 512, 512, 9), (64, 60, 90, 256, 512, 9), (64, 120, 180, 64, 128, 5), (64, 60, 90, 64, 128, 5),
+                                    (64, 240, 360, 64, 64, (3, 1))]:
+        kh, kw = ops._khw(k)
         xp = ops.Planes(torch.randn(B, H, W, Cin, device=dev).to(torch.bfloat16), None)
         gp = ops.Planes(torch.randn(B, H, W, Cout, device=dev).to(torch.bfloat16), None)
-        dw = torch.empty(k * k, Cin, Cout, device=dev)
-        fl = 2.0 * B * H * W * k * k * Cin * Cout
+        dw = torch.empty(kh * kw, Cin, Cout, device=dev)
+        fl = 2.0 * B * H * W * kh * kw * Cin * Cout
 
         def run(v):
             jcm.lib().jcm_debug_set_wgrad_variant(v)
             jt.conv2d_wgrad(xp, gp, dw, Cout, k)
-        med = _interleaved([(lambda v=v: run(v)) for v in (0, 1, 2, 3)])
+        med = _interleaved([(lambda v=v: run(v)) for v in (0, 1, 2, 4)])
         jcm.lib().jcm_debug_set_wgrad_variant(0)
-        print('WGRAD %dx%d Cin%d Cout%d k%d: ' % (H, W, Cin, Cout, k) + '  '.join('v%d %.3f ms (%.0f TF)' % (v, m, fl / m / 1e9) for v, m in zip((0, 1, 2, 3), med)),
+        print('WGRAD %dx%d Cin%d Cout%d k%s: ' % (H, W, Cin, Cout, k) + '  '.join('v%d %.3f ms (%.0f TF)' % (v, m, fl / m / 1e9) for v, m in zip((0, 1, 2, 4), med)),
               flush=True)
 
 

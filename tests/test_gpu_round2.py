@@ -266,31 +266,33 @@ def test_conv_halo_two_tiles_per_weight_stage_is_bit_identical(jcm, case):
 
 
 @pytest.mark.parametrize('case', [(2, 60, 90, 256, 512, 3), (1, 30, 45, 512, 512, 3), (3, 60, 90, 128, 256, 3), (2, 16, 24, 256, 256, 5),
-                                  (4, 60, 90, 512, 128, 1)])
+                                  (4, 60, 90, 512, 128, 1), (2, 60, 90, 64, 128, 5), (3, 24, 36, 64, 64, (3, 1)), (2, 30, 45, 128, 64, 5),
+                                  (1, 20, 33, 32, 16, 3)])     # the last four: narrow N tiles -> tap-group kernel
 @pytest.mark.parametrize('split', [False, True])
 def test_wgrad_pair_and_plan_variants_agree(jcm, jtrain, case, split):
-    """Weight gradient: CTA-pair kernel (even M-tile count, N tiles >= 128) and mixed-shape patch plan against the single-CTA kernel on
-    the uniform grid and against the oracle.  The variants differ only in how the pixel sum is split, so they agree to fp32
-    summation-order noise."""
+    """Weight gradient: CTA-pair kernel (even M-tile count, N tiles >= 128), tap-group kernel (N tiles <= 64) and mixed-shape patch
+    plan against the plain single-CTA kernel on the uniform grid and against the oracle.  The variants differ only in how the pixel
+    sum is split, so they agree to fp32 summation-order noise."""
     B, H, W, Cin, Cout, k = case
-    g = torch.Generator().manual_seed(sum(case))
+    kh, kw = jcm.ops._khw(k)
+    g = torch.Generator().manual_seed(B + H + W + Cin + Cout + kh)
     x = torch.randn(B, H, W, Cin, generator=g)
     dy = torch.randn(B, H, W, Cout, generator=g)
     r = (lambda t: t) if split else (lambda t: t.to(torch.bfloat16).float())
-    w64 = torch.zeros(k, k, Cin, Cout, dtype=torch.float64, requires_grad=True)
+    w64 = torch.zeros(kh, kw, Cin, Cout, dtype=torch.float64, requires_grad=True)
     (orc.conv2d(r(x).double(), w64, 1) * r(dy).double()).sum().backward()
     xp = jcm.ops.split_planes(x.cuda(), split)
     gp = jcm.ops.split_planes(dy.cuda(), split)
     outs = []
     try:
-        for variant in (0, 1, 2, 3):
+        for variant in range(8):
             jcm.lib().jcm_debug_set_wgrad_variant(variant)
-            dw = torch.empty(k * k, Cin, Cout, device='cuda')
+            dw = torch.empty(kh * kw, Cin, Cout, device='cuda')
             jtrain.conv2d_wgrad(xp, gp, dw, Cout, k)
             outs.append(dw)
     finally:
         jcm.lib().jcm_debug_set_wgrad_variant(0)
-    assert rel(outs[0].view(k, k, Cin, Cout), w64.grad) < 2e-4
+    assert rel(outs[0].view(kh, kw, Cin, Cout), w64.grad) < 2e-4
     for v, o in enumerate(outs[1:], 1):
         assert rel(o, outs[0]) < 1e-5, v
 
