@@ -652,9 +652,11 @@ extern "C" int jcm_spatial_softmax_bwd(const float* y, const float* dy, int B, i
 
 extern "C" int jcm_bn_relu_bwd_blocks(long M_out, int C) {
   (void)C;
+  // two blocks per SM: that is what the kernels' register budgets keep resident, so the grid is one wave - and the deterministic
+  // finalize kernels that follow read 296 partial rows per channel instead of 1184 (they cost 13 us each, 26 per step)
   long b = M_out / 32;
   if (b < 1) b = 1;
-  long cap = (long)jcm_num_sms() * 8;
+  long cap = (long)jcm_num_sms() * 2;
   return (int)(b < cap ? b : cap);
 }
 

@@ -2040,9 +2040,12 @@ void plan_wgrad(int B, int H, int W, int Cin, int Gc, int ksize, int kw, bool on
   // wastes 12 % of the last wave unsplit, 0.5 % with 5 splits; the partial sums cost one extra read in wgrad_reduce_kernel.
   pl->pair = allow_pair && (pl->m_tiles % 2) == 0 && (pl->block_n == 128 || pl->block_n == 256) && (pl->block_n / pl->kc_n) % 2 == 0 &&
              jcm_num_sms() >= 2;
-  // narrow layers (N tile <= 64, one term, several taps): tap groups that fill one 256-column TMEM stage
+  // narrow layers (N tile <= 64, one term, several taps) whose SHIFTED operand - the layer input - is the narrow N side: tap groups
+  // that fill one 256-column TMEM stage.  Measured (tests/gpu_diag.py wgpair, profiles/r02/diag_wgtaps.txt): conv2 at 120x180
+  // 1.135 -> 1.066 ms, at 60x90 0.364 -> 0.320 ms; with the shifted operand on the (zero-padded, 128-row) M side - conv1's 64 -> 64
+  // layers - the group's extra boxes cost more than the shared gradient box saves (0.496 -> 0.966 ms), so those keep one tap per task.
   pl->tgroup = 1;
-  if (!pl->pair && allow_taps && pl->block_n <= 64 && ksize * kw > 1) {
+  if (!pl->pair && allow_taps && !pl->x_is_m && pl->block_n <= 64 && ksize * kw > 1) {
     pl->tgroup = 256 / pl->block_n;
     if (pl->tgroup > 4) pl->tgroup = 4;
     if (pl->tgroup > ksize * kw) pl->tgroup = ksize * kw;

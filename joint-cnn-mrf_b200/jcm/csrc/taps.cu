@@ -104,6 +104,34 @@ __global__ void tap_scatter_planes_kernel(const float* __restrict__ g, int B, in
   }
 }
 
+// The same for KP a multiple of 8 (K = 5..8, 13..16 joints): a group of 8 plane channels then lies inside ONE tap, so a thread locates
+// its source pixel once and converts 8 values straight away (the generic kernel above walks (tap, co) element by element with a
+// branch per channel: 277 instructions per thread, 0.33 ms for 531 MB written).  bf16 hi plane only.
+__global__ void tap_scatter_planes8_kernel(const float* __restrict__ g, int B, int H, int W, int ksize, int Cout, int KP, int Npad,
+                                           uint4* __restrict__ hi) {
+  const int G8 = Npad / 8, pad = (ksize - 1) / 2, taps = ksize * ksize, per_tap = KP / 8;
+  const long total = (long)B * H * W * G8;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int g8, qx, qy, n;
+    split_index(i, G8, W, H, g8, qx, qy, n);
+    const int tap = g8 / per_tap, co0 = (g8 - tap * per_tap) * 8;
+    __align__(16) __nv_bfloat16 h[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h[e] = __float2bfloat16_rn(0.f);
+    if (tap < taps) {
+      const int dy = tap / ksize, dx = tap - dy * ksize;
+      const int sy = qy - (dy - pad), sx = qx - (dx - pad);
+      if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+        const float* src = g + (((long)n * H + sy) * W + sx) * Cout + co0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (co0 + e < Cout) h[e] = __float2bfloat16_rn(src[e]);
+      }
+    }
+    hi[i] = *reinterpret_cast<uint4*>(h);
+  }
+}
+
 // dwz [Cin][ZC] (column n = tap*KP+co) -> dw [taps][Cin][Cout]
 __global__ void unpack_tap_grad_kernel(const float* __restrict__ dwz, int taps, int Cin, int Cout, int KP, int ZC, float* __restrict__ dw) {
   const long total = (long)taps * Cin * Cout;
@@ -142,8 +170,12 @@ extern "C" int jcm_tap_scatter_planes(const float* g, int B, int H, int W, int k
                                       void* stream) {
   JCM_CHECK_ARG(g && hi && B > 0 && H > 0 && W > 0 && (ksize & 1), "jcm_tap_scatter_planes: bad arguments");
   JCM_CHECK_ARG(KP >= Cout && (Npad % 8) == 0 && Npad >= ksize * ksize * KP, "jcm_tap_scatter_planes: bad channel layout (KP=%d Npad=%d)", KP, Npad);
-  tap_scatter_planes_kernel<<<grid_for((long)B * H * W * (Npad / 8), 256), 256, 0, (cudaStream_t)stream>>>(
-      g, B, H, W, ksize, Cout, KP, Npad, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  if (!lo && (KP % 8) == 0)
+    tap_scatter_planes8_kernel<<<grid_for((long)B * H * W * (Npad / 8), 256), 256, 0, (cudaStream_t)stream>>>(g, B, H, W, ksize, Cout, KP, Npad,
+                                                                                                          (uint4*)hi);
+  else
+    tap_scatter_planes_kernel<<<grid_for((long)B * H * W * (Npad / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+        g, B, H, W, ksize, Cout, KP, Npad, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
   JCM_LAUNCH_CHECK();
   return JCM_OK;
 }
