@@ -28,3 +28,42 @@ ctx2 = jcm.Context(n_joints=K, joint_names=names, flag_train=False, precision='f
 o = jcm.tower_forward(x, y, tr.p, tr.sm, ctx2)
 torch.cuda.synchronize()
 print('fp32 forward ok', float(o['loss_pd']), float(o['loss_sm']))
+
+# ---- round 2: the kernels debug width never reaches.  Full-width channel counts on small maps: CTA-pair forward / data gradient
+# (N = 256 tiles, mixed-shape tile plan on a 60x90 map, partial last wave -> N-split tail), two-tile halo mode (N = 128 and 64), CTA-pair
+# and tap-group weight gradients, the prefetching glue kernels of the bf16 configuration, batched weight re-pack, fast tap scatter.
+from jcm import ops, train as jt
+g = torch.Generator().manual_seed(1)
+
+
+def planes(*shape):
+    return ops.Planes(torch.randn(*shape, generator=g).cuda().to(torch.bfloat16), None)
+
+
+for (B, H, W, Cin, Cout, k) in [(2, 60, 90, 64, 512, 3), (3, 15, 23, 128, 256, 3), (2, 24, 32, 64, 128, 5), (3, 20, 33, 128, 64, 5)]:
+    xp, wp = planes(B, H, W, Cin), planes(k * k, Cout, Cin)
+    y1 = ops.conv2d_planes(xp, wp, None, Cout, k, relu=True, out_bf16=True)
+    y2 = ops.conv2d_planes(xp, wp, None, Cout, k, relu=True, out_bf16=True, variant=15)
+    assert torch.equal(y1, y2)
+    gp = planes(B, H, W, Cout)
+    dw = torch.empty(k * k, Cin, Cout, device='cuda')
+    jt.conv2d_wgrad(xp, gp, dw, Cout, k)
+torch.cuda.synchronize()
+print('conv variants ok')
+a = torch.relu(torch.randn(2, 45, 31, 64, generator=g)).cuda().to(torch.bfloat16)
+mm, mv = torch.zeros(64, device='cuda'), torch.ones(64, device='cuda')
+ss, st = ops.bn_scale_shift(a, torch.ones(64, device='cuda'), torch.zeros(64, device='cuda'), mm, mv, train=True, save=True)
+for pool in (False, True):
+    pl = ops.bn_apply_pool(a, ss, pool, False)
+    dout = torch.randn(pl.shape, generator=g).cuda().to(torch.bfloat16)
+    dg, db_, dbias = (torch.empty(64, device='cuda') for _ in range(3))
+    jt.bn_relu_bwd(a, dout, ss, st, 1.0, pool, False, dg, db_, dbias)
+b1, b2, b3 = (torch.randn(2, h, w, 64, generator=g).cuda().to(torch.bfloat16) for h, w in ((60, 90), (30, 45), (15, 23)))
+ops.upsample_avg3(b1, b2, b3, torch.randn(6, 64, generator=g).cuda(), False)
+jt.upsample_avg3_bwd(b1, (30, 45), (15, 23))
+ops.tap_scatter_planes(torch.randn(2, 20, 30, 7, generator=g).cuda(), 9, False)
+ws = [torch.randn(3, 3, 64, 128, generator=g).cuda(), torch.randn(5, 5, 32, 32, generator=g).cuda()]
+ops.pack_weights_batch([(w, ops._new_planes((w.shape[0] ** 2, w.shape[3], w.shape[2]), 'cuda', False),
+                         ops._new_planes((w.shape[0] ** 2, w.shape[2], w.shape[3]), 'cuda', False)) for w in ws], False)
+torch.cuda.synchronize()
+print('round-2 kernels ok')
