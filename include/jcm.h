@@ -13,6 +13,10 @@
  *     selects plain bf16 arithmetic (training config), passing lo selects the 3-term split product ("bf16x3", fp32 config).
  *   - return value: 0 = ok, < 0 = bad argument / unsupported shape (JCM_E*), > 0 = cudaError_t.  jcm_last_error()
  *     returns a thread-local message.  There is no CPU fallback anywhere.
+ *   - devices: the design is one process per GPU (data parallelism = one replica per process, jcm.train.Trainer); calls act on the
+ *     CUDA device that is current in the calling thread.  Per-device state (SM count, kernel attributes) is cached per device
+ *     ordinal, so a process that switches devices stays correct; kernels of one call never span devices.
+ *   - the library reads no environment variable (measurement switches exist only in builds with -DJCM_EXPERIMENTS).
  */
 #ifndef JCM_H_
 #define JCM_H_
