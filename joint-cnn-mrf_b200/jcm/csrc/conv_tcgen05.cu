@@ -1677,6 +1677,20 @@ conv_wgrad_taps_kernel(const __grid_constant__ CUtensorMap map_m_hi, const __gri
       const uint64_t bdesc_hi = (make_smem_desc(0, 8 * n_row_bytes, n_layout) & ~(((uint64_t)0x3FFF << 16) | 0x3FFF)) |
                                 ((uint64_t)((n_box_bytes >> 4) & 0x3FFF) << 16);
       const uint32_t a_step = p.shift_m ? (uint32_t)p.a_bytes : 0u, b_step = p.shift_n ? (uint32_t)p.b_bytes : 0u;
+      // The MMAs of the narrow layers are short (N <= 64: 32-48 clocks each) and ONE thread issues 16 of them per k-block, so the
+      // address arithmetic of that thread is on the critical path.  Everything that does not depend on the stage is tabulated here:
+      // the descriptors' high words are constant, their low words are (stage base >> 4) + a per-(tap, K step) offset - one 32-bit add
+      // per operand and MMA (the 14-bit address field cannot carry: shared-memory addresses stay below 256 KB).
+      const uint32_t a_hi = (uint32_t)(adesc_hi >> 32), b_hi = (uint32_t)(bdesc_hi >> 32);
+      const uint32_t a_lo0 = (uint32_t)adesc_hi, b_lo0 = (uint32_t)bdesc_hi;       // low words without the start address
+      uint32_t aoff[4][kWgPix / 16], boff[4][kWgPix / 16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < kWgPix / 16; ++k) {
+          aoff[j][k] = (j * a_step + k * 16 * m_row_bytes) >> 4;
+          boff[j][k] = (j * b_step + k * 16 * n_row_bytes) >> 4;
+        }
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -1690,19 +1704,25 @@ conv_wgrad_taps_kernel(const __grid_constant__ CUtensorMap map_m_hi, const __gri
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
+        uint32_t accf = 0;
         for (int kb = 0; kb < p1 - p0; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * p.stage_bytes;
-          const uint32_t sb = sa + n_off;
-          for (int j = 0; j < ntap; ++j) {
+          const uint32_t a_lo = a_lo0 | (sa >> 4), b_lo = b_lo0 | ((sa + n_off) >> 4);
 #pragma unroll
-            for (int k = 0; k < kWgPix / 16; ++k) {
-              const uint64_t adesc = adesc_hi | (uint64_t)(((sa + j * a_step + k * 16 * m_row_bytes) >> 4) & 0x3FFF);
-              const uint64_t bdesc = bdesc_hi | (uint64_t)(((sb + j * b_step + k * 16 * n_row_bytes) >> 4) & 0x3FFF);
-              tc_mma_bf16(d_tmem + j * p.block_n, adesc, bdesc, idesc, (kb | k) != 0);
+          for (int j = 0; j < 4; ++j) {
+            if (j < ntap) {
+#pragma unroll
+              for (int k = 0; k < kWgPix / 16; ++k) {
+                uint64_t adesc, bdesc;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(adesc) : "r"(a_lo + aoff[j][k]), "r"(a_hi));
+                asm("mov.b64 %0, {%1, %2};" : "=l"(bdesc) : "r"(b_lo + boff[j][k]), "r"(b_hi));
+                tc_mma_bf16(d_tmem + j * p.block_n, adesc, bdesc, idesc, k ? 1u : accf);
+              }
             }
           }
+          accf = 1u;
           tc_commit(bar_empty + 8 * stage);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -2019,7 +2039,7 @@ struct WgradPlan {
 // variant: bit 0 = single-CTA kernel instead of the CTA pair, bit 1 = uniform patch grid, bit 2 = no tap groups
 void plan_wgrad(int B, int H, int W, int Cin, int Gc, int ksize, int kw, bool one_term, int variant, WgradPlan* pl) {
   const bool allow_mixed = one_term && !(variant & 2), allow_pair = !(variant & 1), allow_taps = one_term && !(variant & 4);
-  pl->x_is_m = Cin >= Gc;
+  pl->x_is_m = Cin > Gc;       // ties (conv1's 64 -> 64 layers): the shifted operand X on the narrow N side, so that tap groups apply
   pl->m_ch = pl->x_is_m ? Cin : Gc;
   pl->n_ch = pl->x_is_m ? Gc : Cin;
   pl->m_tiles = jcm_cdiv(pl->m_ch, kTileM);
