@@ -408,32 +408,50 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       } else {
-      // two M tiles per weight stage (one tap per stage): tile 0 accumulates in columns [0, block_n), tile 1 in [block_n, 2 block_n)
+      // two M tiles per weight stage (one tap per stage): tile 0 accumulates in columns [0, block_n), tile 1 in [block_n, 2 block_n).
+      // The MMAs here are short (N <= 128: 32-64 clocks) and one thread issues eight per tap, so its address arithmetic is kept
+      // minimal: the descriptors' high word is constant, the low word is a base (per halo patch / weight stage) plus small offsets.
       const int m_groups = (m_tiles + 1) / 2;
+      const uint32_t d_hi = (uint32_t)(desc_hi >> 32), d_lo0 = (uint32_t)desc_hi;
+      const uint32_t dy4 = dy_bytes >> 4, bstr4 = (uint32_t)p.b_stride >> 4, b04 = smem_b0 >> 4;
       for (int tg = blockIdx.x; tg < m_groups * p.n_tiles; tg += gridDim.x) {
         const bool two = 2 * (tg % m_groups) + 1 < m_tiles;
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d0 = tmem_base + acc * 256, d1 = d0 + p.block_n;
+        uint32_t accf = 0;
         for (int it = 0; it < p.kw * p.cblocks; ++it) {
           mbar_wait(bar_afull + 8 * sa, pa);
-          const uint32_t a0 = smem_base + sa * p.a_stride;
+          uint32_t a0l = d_lo0 | ((smem_base + sa * p.a_stride) >> 4);
           int sa1 = sa + 1;
           uint32_t pa1 = pa;
           if (sa1 == p.a_stages) { sa1 = 0; pa1 ^= 1; }
           if (two) mbar_wait(bar_afull + 8 * sa1, pa1);
-          const uint32_t a1 = smem_base + sa1 * p.a_stride;
+          uint32_t a1l = d_lo0 | ((smem_base + sa1 * p.a_stride) >> 4);
           tc_fence_after();
           for (int dy = 0; dy < p.ksize; ++dy) {
             mbar_wait(bar_full + 8 * sb, pb);
             tc_fence_after();
-            const uint64_t bdesc = desc_hi | (uint64_t)(((smem_b0 + sb * p.b_stride) >> 4) & 0x3FFF);
-            const uint64_t adesc0 = desc_hi | (uint64_t)(((a0 + dy * dy_bytes) >> 4) & 0x3FFF);
-            const uint64_t adesc1 = desc_hi | (uint64_t)(((a1 + dy * dy_bytes) >> 4) & 0x3FFF);
-            const uint32_t accf = (uint32_t)((it | dy) != 0);
-            for (int k = 0; k < kk; ++k) tc_mma_bf16(d0, adesc0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accf | (uint32_t)(k != 0));
-            if (two)
-              for (int k = 0; k < kk; ++k) tc_mma_bf16(d1, adesc1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accf | (uint32_t)(k != 0));
+            const uint32_t bl = d_lo0 | (b04 + sb * bstr4);
+#pragma unroll 4
+            for (int k = 0; k < kk; ++k) {
+              uint64_t ad, bd;
+              asm("mov.b64 %0, {%1, %2};" : "=l"(ad) : "r"(a0l + 2 * k), "r"(d_hi));
+              asm("mov.b64 %0, {%1, %2};" : "=l"(bd) : "r"(bl + 2 * k), "r"(d_hi));
+              tc_mma_bf16(d0, ad, bd, idesc, k ? 1u : accf);
+            }
+            if (two) {
+#pragma unroll 4
+              for (int k = 0; k < kk; ++k) {
+                uint64_t ad, bd;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(ad) : "r"(a1l + 2 * k), "r"(d_hi));
+                asm("mov.b64 %0, {%1, %2};" : "=l"(bd) : "r"(bl + 2 * k), "r"(d_hi));
+                tc_mma_bf16(d1, ad, bd, idesc, k ? 1u : accf);
+              }
+            }
+            accf = 1u;
+            a0l += dy4;
+            a1l += dy4;
             tc_commit(bar_empty + 8 * sb);
             if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
           }
@@ -2075,7 +2093,9 @@ void plan_wgrad(int B, int H, int W, int Cin, int Gc, int ksize, int kw, bool on
   const int sms = pl->pair ? (jcm_num_sms() & ~1) / 2 : jcm_num_sms();
   int best_s = 1;
   double best_cost = 1e300;
-  for (int s = 1; s <= 64; ++s) {
+  // (up to 2 x SMs splits: a layer with few (tap group, tile) units - conv1 with its three taps in one group has ONE - must still
+  // fill the machine)
+  for (int s = 1; s <= 2 * sms; ++s) {
     if (s > 1 && s > pl->total_patches / 8) break;
     const double waves = (double)jcm_cdiv(base * s, sms);
     // + the reduction pass over s partial copies (HBM-bound), in units of one k-block (~0.5 us)
