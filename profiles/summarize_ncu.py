@@ -127,6 +127,21 @@ def cmd_full(a):
         print(js)
 
 
+def cmd_table(a):
+    """per kernel of a *_traffic.json: launches, time, DRAM bytes, achieved GB/s and its fraction of the measured HBM peak"""
+    d = json.load(open(a.path))
+    agg = {}
+    for l in d['launches']:
+        g = agg.setdefault(l['kernel'], [0, 0.0, 0.0])
+        g[0] += 1
+        g[1] += l.get('time_us', 0.0)
+        g[2] += l['dram_bytes']
+    print('%-44s %4s %10s %10s %9s %6s' % ('kernel', 'n', 'time us', 'DRAM MB', 'GB/s', 'of HBM'))
+    for k, (n, us, by) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        gbs = by / us / 1e3 if us else 0.0
+        print('%-44s %4d %10.1f %10.0f %9.0f %6.2f' % (k[:44], n, us, by / 1e6, gbs, gbs / a.peak))
+
+
 def main():
     ap = argparse.ArgumentParser()
     sub = ap.add_subparsers(dest='cmd', required=True)
@@ -138,8 +153,11 @@ def main():
     f.add_argument('path')
     f.add_argument('--out', default=None)
     f.add_argument('--note', default='mean over the launches captured')
+    t = sub.add_parser('table')
+    t.add_argument('path')
+    t.add_argument('--peak', type=float, default=6455.9, help='HBM GB/s (MEASURED_PEAKS.json)')
     a = ap.parse_args()
-    {'launches': cmd_launches, 'full': cmd_full}[a.cmd](a)
+    {'launches': cmd_launches, 'full': cmd_full, 'table': cmd_table}[a.cmd](a)
 
 
 if __name__ == '__main__':
