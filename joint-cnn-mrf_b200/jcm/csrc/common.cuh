@@ -58,6 +58,7 @@ struct ConvExArgs {
   int grp, a_div, w_cin, k_rows, sm_pad, sm_rows, sm_rows_in;
   const int* img_map;                          // device array: grp 1: A image of conv image i; grp 2: weight plane of batch q
   int map_images;                              // number of distinct images / planes img_map points into
+  int map_on_a;                                // grp 2 only: img_map selects the A image of batch q instead of its weight plane
   int variant;                                 // 0: automatic; bit 0 single-CTA kernel, bit 1 uniform tiles, bit 2 no N-split tail
   void* stream;
 };

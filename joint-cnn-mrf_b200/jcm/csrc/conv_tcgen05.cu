@@ -65,9 +65,10 @@ struct ConvParams {
   //   grp 1: every image has its OWN weights (tap plane = img * grp_taps + tap) and taps whose input rows all lie outside the
   //          map are skipped (120-tap vertical kernels over 61-row maps: half of the taps of every tile)
   //   grp 2: batched GEMM with a shifted B operand: image = (batch a_div * q + s), A image q, weight plane q, the weight's K
-  //          coordinate is offset by (s - sm_pad) * k_rows and only the k-blocks that can be non-zero are visited
+  //          coordinate is offset by (s - sm_pad) * k_rows and only the k-blocks that can be non-zero are visited; an image map
+  //          redirects either the weight plane (b_map) or the A image (a_map) of batch q
   int grp, grp_taps, a_div, k_rows, sm_pad, sm_rows, sm_rows_in;
-  const int* a_map;     // grp 1: A image = a_map[img] (several pairs share one conditioning map); NULL: img
+  const int* a_map;     // grp 1: A image = a_map[img] (several pairs share one conditioning map); grp 2: a_map[img / a_div]; NULL: img
   const int* b_map;     // grp 2: weight plane = b_map[img / a_div]; NULL: img / a_div
   int dbg;              // measurement switches (JCM_CONV_DBG bit 0: epilogue releases TMEM without storing, bit 1: no MMAs issued,
                         // bit 2: producer skips the B loads) - results are garbage, timing only
@@ -481,7 +482,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         if (p.grp) {
           const KRange kr = tile_krange(p, img, ty);
           const int q = img / p.a_div;
-          const int a_img = p.grp == 2 ? q : (p.a_map ? p.a_map[img] : img);
+          const int a_img = p.grp == 2 ? (p.a_map ? p.a_map[q] : q) : (p.a_map ? p.a_map[img] : img);
           const int b_plane = p.grp == 2 ? (p.b_map ? p.b_map[q] : q) : img * p.grp_taps;
           const int b_koff = p.grp == 2 ? (img % p.a_div - p.sm_pad) * p.k_rows : 0;
           for (int tap = kr.tap_lo; tap < kr.tap_hi; ++tap) {
@@ -1165,8 +1166,8 @@ int jcm_conv_igemm_ex(const ConvExArgs& a) {
   p.pad_x = (kw - 1) / 2;
   p.grp = a.grp; p.grp_taps = ksize * kw; p.a_div = a.a_div > 0 ? a.a_div : 1; p.k_rows = a.k_rows;
   p.sm_pad = a.sm_pad; p.sm_rows = a.sm_rows; p.sm_rows_in = a.sm_rows_in;
-  p.a_map = a.grp == 1 ? a.img_map : nullptr;
-  p.b_map = a.grp == 2 ? a.img_map : nullptr;
+  p.a_map = (a.grp == 1 || (a.grp == 2 && a.map_on_a)) ? a.img_map : nullptr;
+  p.b_map = (a.grp == 2 && !a.map_on_a) ? a.img_map : nullptr;
   JCM_CHECK_ARG(!a.img_map || a.map_images > 0, "jcm_conv_igemm_ex: img_map needs map_images");
   p.terms = x_lo ? 3 : 1;
   p.a_bytes = kTileM * p.kc * 2;
@@ -1282,7 +1283,7 @@ int jcm_conv_igemm_ex(const ConvExArgs& a) {
   static ShapeMaps smaps_zero;            // zero-initialised template (unused slots must still be valid kernel-parameter bytes)
   ShapeMaps smaps = smaps_zero;
   {
-    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)(a.grp == 2 ? B / p.a_div : (p.a_map ? a.map_images : B))};
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)(p.a_map ? a.map_images : (a.grp == 2 ? B / p.a_div : B))};
     uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
     uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)p.TW, (uint32_t)p.TH, 1};
     int rc = make_map(&ma_hi, x_hi, 4, dims, str, box, swz);

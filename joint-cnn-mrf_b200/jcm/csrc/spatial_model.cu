@@ -934,7 +934,8 @@ struct SmtDims {
   int B, H, W, K, P;
   int Hc;   // H + 1: rows of the convolution output and of the zero-padded operands
   int NP;   // GEMM N extent: W + 1 rounded up to 32
-  int CP;   // GEMM K extent (forward, dL) / M extent (dP): W + 1 rounded up to 64
+  int CP;   // GEMM K extent of dL (x <= W): W + 1 rounded up to 64
+  int CPf;  // GEMM K extent of the forward pass (v < W): W rounded up to 64 (one k-block less than CP when W is a multiple of 64)
   int Bp;   // images rounded up to 16; the dP GEMM contracts over k = row * Bp + image
 };
 
@@ -943,6 +944,7 @@ int fill_smt(SmtDims& t, int B, int H, int W, int K, int P) {
   t.Hc = H + 1;
   t.NP = jcm_cdiv(W + 1, 32) * 32;
   t.CP = jcm_cdiv(W + 1, 64) * 64;
+  t.CPf = jcm_cdiv(W, 64) * 64;
   t.Bp = jcm_cdiv(B, 16) * 16;
   JCM_CHECK_ARG(t.NP <= 256, "jcm_spatial_model_tc: heat-map width %d not supported (at most 255)", W);
   return JCM_OK;
@@ -955,8 +957,8 @@ SmtFwdWs smt_fwd_layout(const SmtDims& t) {
   SmtFwdWs w;
   size_t o = 0;
   w.spE = o; o += al256((size_t)t.P * 2 * t.H * 2 * t.W * 4);
-  w.Xh = o;  o += al256((size_t)(t.K + 1) * t.Hc * t.B * t.CP * 2);
-  w.Wf = o;  o += al256((size_t)t.P * 2 * t.H * t.NP * t.CP * 2);
+  w.Xh = o;  o += al256((size_t)(t.K + 1) * t.Hc * t.B * t.CPf * 2);
+  w.Wf = o;  o += al256((size_t)t.P * 2 * t.H * t.NP * t.CPf * 2);
   w.Cb = o;  o += al256((size_t)t.P * t.Hc * t.B * t.NP * 4);
   w.total = o + 256;
   return w;
@@ -968,11 +970,11 @@ SmtBwdWs smt_bwd_layout(const SmtDims& t) {
   size_t o = 0;
   w.dT = o;   o += al256((size_t)t.P * G4 * t.H * t.W * 4);
   w.Xc = o;   o += al256((size_t)t.P * t.Hc * t.B * t.CP * 2);
-  w.XcT = o;  o += al256((size_t)t.P * t.CP * t.Hc * t.Bp * 2);
-  w.Ht = o;   o += al256((size_t)(t.K + 1) * t.NP * t.H * t.Bp * 2);
+  w.XcT = o;  o += al256((size_t)t.P * t.NP * t.Hc * t.Bp * 2);
+  w.Ht = o;   o += al256((size_t)(t.K + 1) * t.W * t.H * t.Bp * 2);
   w.Wd = o;   o += al256((size_t)t.P * 2 * t.H * t.NP * t.CP * 2);
   w.dL = o;   o += al256((size_t)t.P * t.Hc * t.B * t.NP * 4);
-  w.blk = o;  o += al256((size_t)t.P * 2 * t.H * t.CP * t.NP * 4);
+  w.blk = o;  o += al256((size_t)t.P * 2 * t.H * t.W * t.NP * 4);
   w.dh = o;   o += al256((size_t)t.B * t.H * t.W * (t.K + 1) * 4);
   w.part = o; o += al256((size_t)4 * jcm_num_sms() * (t.K + 1) * 4 + 1024);
   w.total = o + 256;
@@ -984,10 +986,10 @@ __global__ void smt_softplus_kernel(const float* __restrict__ E, long n, float* 
 }
 
 // Toeplitz blocks of the prior, 8 consecutive K elements (16 bytes) per thread:
-//   Wf[p][dy][x (NP rows)][v (CP)] = spE[p][2H-1-dy][x-v+W-1]     forward  (x <= W, v < W; 0 elsewhere)
-//   Wd[p][dy][v (NP rows)][x (CP)] = spE[p][dy][x-v+W-1]          dL
+//   Wf[p][dy][x (NP rows)][v (CPf)] = spE[p][2H-1-dy][x-v+W-1]    forward  (x <= W, v < W; 0 elsewhere)
+//   Wd[p][dy][v (NP rows)][x (CP)]  = spE[p][dy][x-v+W-1]         dL
 __global__ void smt_pack_prior_kernel(const float* __restrict__ spE, SmtDims t, int dl, __nv_bfloat16* __restrict__ Wt) {
-  const int C8 = t.CP / 8, H2 = 2 * t.H, W2 = 2 * t.W;
+  const int C8 = (dl ? t.CP : t.CPf) / 8, H2 = 2 * t.H, W2 = 2 * t.W;
   const long total = (long)t.P * H2 * t.NP * C8;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     int c8, row, dy, p;
@@ -1004,9 +1006,9 @@ __global__ void smt_pack_prior_kernel(const float* __restrict__ spE, SmtDims t, 
   }
 }
 
-// Xh[j][y (Hc)][n (B)][v (CP)] = h_j[n][y][v] (0 in the padding), one "image" per heat-map channel j (the GEMM kernels pick the
-// pair's conditioning channel through pair_cond);  Ht[j][v (NP)][y*Bp + n] = the same values, transposed (the dP GEMM's B
-// operand; rows y < H only).  One CTA per (32 columns, row, channel); either output may be NULL.
+// Xh[j][y (Hc)][n (B)][v (CPf)] = h_j[n][y][v] (0 in the padding), one "image" per heat-map channel j (the GEMM kernels pick the
+// pair's conditioning channel through pair_cond);  Ht[j][v (W)][y*Bp + n] = the same values, transposed (the dP GEMM's A
+// operand: pixel rows v, rows y < H only).  One CTA per (32 columns, row, channel); either output may be NULL.
 __global__ void __launch_bounds__(256)
 smt_prep_kernel(const float* __restrict__ hm, const float* __restrict__ scale, const float* __restrict__ shift, SmtDims t,
                 __nv_bfloat16* __restrict__ Xh, __nv_bfloat16* __restrict__ Ht) {
@@ -1024,7 +1026,7 @@ smt_prep_kernel(const float* __restrict__ hm, const float* __restrict__ scale, c
         float val = 0.f;
         if (n < t.B && y < t.H && v < t.W) val = softplus5(fmaf(hm[(((long)n * t.H + y) * t.W + v) * KC + j], sc, sh));
         tile[nn][tx] = val;
-        if (Xh && n < t.B) Xh[(((long)p * t.Hc + y) * t.B + n) * t.CP + v] = __float2bfloat16_rn(val);
+        if (Xh && n < t.B && v < t.CPf) Xh[(((long)p * t.Hc + y) * t.B + n) * t.CPf + v] = __float2bfloat16_rn(val);
       }
     }
     __syncthreads();
@@ -1033,7 +1035,7 @@ smt_prep_kernel(const float* __restrict__ hm, const float* __restrict__ scale, c
       const int n = nc + nn;
       for (int pass = 0; pass < 8; ++pass) {
         const int xx = pass * 4 + x0, v = v0 + xx;
-        if (v < t.NP && n < t.Bp) Ht[((long)p * t.NP + v) * KH + (long)y * t.Bp + n] = __float2bfloat16_rn(tile[nn][xx]);
+        if (v < t.W && n < t.Bp) Ht[((long)p * t.W + v) * KH + (long)y * t.Bp + n] = __float2bfloat16_rn(tile[nn][xx]);
       }
     }
     __syncthreads();
@@ -1041,7 +1043,7 @@ smt_prep_kernel(const float* __restrict__ hm, const float* __restrict__ scale, c
 }
 
 // dC = R_y^T dT R_x on the (H+1)x(W+1) grid (as sm_bwd_dc_kernel), written as the two bf16 operands of the backward GEMMs:
-//   Xc[p][u (Hc)][n (B)][x (CP)]   (dL: A operand)      XcT[p][x (CP)][u*Bp + n]   (dP: A operand, K-major)
+//   Xc[p][u (Hc)][n (B)][x (CP)]   (dL: A operand)      XcT[p][x (NP)][u*Bp + n]   (dP: weight rows x, K-major)
 __global__ void __launch_bounds__(256)
 smt_dc_kernel(const float* __restrict__ dT, SmtDims t, int G4, __nv_bfloat16* __restrict__ Xc, __nv_bfloat16* __restrict__ XcT) {
   __shared__ float tile[64][33];
@@ -1082,45 +1084,49 @@ smt_dc_kernel(const float* __restrict__ dT, SmtDims t, int G4, __nv_bfloat16* __
       const int n = nc + nn;
       for (int pass = 0; pass < 8; ++pass) {
         const int xx = pass * 4 + xb;
-        if (n < t.Bp) XcT[((long)p * t.CP + x0 + xx) * KA + (long)u * t.Bp + n] = __float2bfloat16_rn(tile[nn][xx]);
+        if (n < t.Bp && x0 + xx < t.NP) XcT[((long)p * t.NP + x0 + xx) * KA + (long)u * t.Bp + n] = __float2bfloat16_rn(tile[nn][xx]);
       }
     }
     __syncthreads();
   }
 }
 
-// dE[p][r][c] = sigmoid(5 E[p][r][c]) * sum over the diagonal x - v + W - 1 = c of blk[p][2H-1-r][x][v]
-// One CTA per (dy, pair): the (W+1) x W block goes through shared memory (odd row stride: the diagonal walk is conflict free).
+// dE[p][r][c] = sigmoid(5 E[p][r][c]) * sum over the diagonal x - v + W - 1 = c of blk[p][r][v][x]   (blk rows v, NP columns x)
+// One CTA per (r, pair), one thread per c: for a fixed v the threads of a warp read consecutive x, so the walk down the diagonal is
+// a sequence of coalesced 128-byte reads; eight of them are in flight per thread.
 __global__ void __launch_bounds__(256)
 smt_dp_reduce_kernel(const float* __restrict__ blk, const float* __restrict__ E, SmtDims t, float* __restrict__ dE) {
-  extern __shared__ float rsm[];
-  const int dy = blockIdx.x, p = blockIdx.y;
-  const int W = t.W, LS = W | 1;
-  const float* src = blk + ((long)p * 2 * t.H + dy) * t.CP * t.NP;
-  for (int i = threadIdx.x; i < (W + 1) * t.NP; i += blockDim.x) {
-    const int x = i / t.NP, v = i - x * t.NP;
-    if (v < W) rsm[x * LS + v] = src[i];
-  }
-  __syncthreads();
-  const int r = 2 * t.H - 1 - dy;
+  const int r = blockIdx.x, p = blockIdx.y;
+  const int W = t.W;
+  const float* src = blk + ((long)p * 2 * t.H + r) * W * t.NP;
   for (int c = threadIdx.x; c < 2 * W; c += blockDim.x) {
     const int vlo = max(0, W - 1 - c), vhi = min(W - 1, 2 * W - 1 - c);
-    float s = 0.f;
-    for (int v = vlo; v <= vhi; ++v) s += rsm[(c + v - (W - 1)) * LS + v];
+    const float* q = src + (long)vlo * t.NP + (c + vlo - (W - 1));
+    const int step = t.NP + 1;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int n = vhi - vlo + 1;
+    for (; n >= 8; n -= 8, q += 8 * step) {
+      const float a0 = q[0], a1 = q[step], a2 = q[2 * step], a3 = q[3 * step];
+      const float a4 = q[4 * step], a5 = q[5 * step], a6 = q[6 * step], a7 = q[7 * step];
+      s0 += a0; s1 += a1; s2 += a2; s3 += a3;
+      s0 += a4; s1 += a5; s2 += a6; s3 += a7;
+    }
+    for (; n > 0; --n, q += step) s0 += q[0];
     const long o = ((long)p * 2 * t.H + r) * 2 * W + c;
-    dE[o] = s * sigmoid5(E[o]);
+    dE[o] = ((s0 + s1) + (s2 + s3)) * sigmoid5(E[o]);
   }
 }
 
 int smt_conv(const void* x, const void* w, void* y, int B, int H, int W, int Cin, int Cout, int ksize, int pad_y, int grp, int a_div,
-             int w_cin, int k_rows, int sm_pad, int sm_rows, int sm_rows_in, const int* img_map, int map_images, void* stream) {
+             int w_cin, int k_rows, int sm_pad, int sm_rows, int sm_rows_in, const int* img_map, int map_images, void* stream,
+             int map_on_a = 0) {
   ConvExArgs a;
   memset(&a, 0, sizeof(a));
   a.x_hi = x; a.w_hi = w; a.y = y;
   a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.Cout_pad = Cout; a.ksize = ksize; a.kw = 1;
   a.pad_y = pad_y; a.grp = grp; a.a_div = a_div; a.w_cin = w_cin; a.k_rows = k_rows;
   a.sm_pad = sm_pad; a.sm_rows = sm_rows; a.sm_rows_in = sm_rows_in;
-  a.img_map = img_map; a.map_images = map_images;
+  a.img_map = img_map; a.map_images = map_images; a.map_on_a = map_on_a;
   a.stream = stream;
   return jcm_conv_igemm_ex(a);
 }
@@ -1159,14 +1165,14 @@ extern "C" int jcm_spatial_model_tc_fwd(const float* heat_map, const float* bn_s
     const long n = (long)P * 4 * H * W;
     smt_softplus_kernel<<<(int)((n + 255) / 256 < cap ? (n + 255) / 256 : cap), 256, 0, st>>>(energies, n, spE);
     JCM_LAUNCH_CHECK();
-    const long total = (long)P * 2 * H * t.NP * (t.CP / 8);
+    const long total = (long)P * 2 * H * t.NP * (t.CPf / 8);
     smt_pack_prior_kernel<<<(int)((total + 255) / 256 < cap ? (total + 255) / 256 : cap), 256, 0, st>>>(spE, t, 0, Wf);
     JCM_LAUNCH_CHECK();
-    smt_prep_kernel<<<dim3(t.CP / 32, t.Hc, K + 1), 256, 0, st>>>(heat_map, bn_scale, bn_shift, t, Xh, nullptr);
+    smt_prep_kernel<<<dim3(t.CPf / 32, t.Hc, K + 1), 256, 0, st>>>(heat_map, bn_scale, bn_shift, t, Xh, nullptr);
     JCM_LAUNCH_CHECK();
   }
   // C[p][y][n][x] = sum_dy Xh[cond(p)][y+dy-H][n][:] . Wf[p][dy][x][:]
-  rc = smt_conv(Xh, Wf, Cb, P, t.Hc, B, t.CP, t.NP, 2 * H, H, 1, 1, 0, 0, 0, 0, 0, pair_cond, K + 1, stream);
+  rc = smt_conv(Xh, Wf, Cb, P, t.Hc, B, t.CPf, t.NP, 2 * H, H, 1, 1, 0, 0, 0, 0, 0, pair_cond, K + 1, stream);
   if (rc) return rc;
   SmDims d;
   fill_dims(d, B, H, W, K, P);
@@ -1214,8 +1220,6 @@ extern "C" int jcm_spatial_model_tc_bwd(const float* g, const float* heat_map, c
     const float src = (float)xx * ((float)(W + 1) / (float)W);
     JCM_CHECK_ARG((int)floorf(src) == xx, "jcm_spatial_model_tc_bwd: unsupported heat-map width %d", W);
   }
-  const size_t dsmem = (size_t)(W + 1) * (W | 1) * sizeof(float);
-  JCM_CHECK_ARG(dsmem <= 227 * 1024 - 256, "jcm_spatial_model_tc_bwd: heat-map width %d not supported", W);
   cudaStream_t st = (cudaStream_t)stream;
   const uint8_t* fws = (const uint8_t*)(((uintptr_t)fwd_workspace + 255) & ~(uintptr_t)255);
   const float* spE = (const float*)(fws + LF.spE);
@@ -1243,7 +1247,7 @@ extern "C" int jcm_spatial_model_tc_bwd(const float* g, const float* heat_map, c
     JCM_LAUNCH_CHECK();
     smt_dc_kernel<<<dim3(t.CP / 32, t.Hc, P), 256, 0, st>>>(dT, t, G4, Xc, XcT);
     JCM_LAUNCH_CHECK();
-    smt_prep_kernel<<<dim3(t.CP / 32, t.Hc, K + 1), 256, 0, st>>>(heat_map, bn_scale, bn_shift, t, nullptr, Ht);
+    smt_prep_kernel<<<dim3(jcm_cdiv(W, 32), t.Hc, K + 1), 256, 0, st>>>(heat_map, bn_scale, bn_shift, t, nullptr, Ht);
     JCM_LAUNCH_CHECK();
     const long tw = (long)P * 2 * H * t.NP * (t.CP / 8);
     smt_pack_prior_kernel<<<(int)((tw + 255) / 256 < cap ? (tw + 255) / 256 : cap), 256, 0, st>>>(spE, t, 1, Wd);
@@ -1252,12 +1256,14 @@ extern "C" int jcm_spatial_model_tc_bwd(const float* g, const float* heat_map, c
   // dL[p][u][n][v] = sum_dy Xc[p][u+dy-(H-1)][n][:] . Wd[p][dy][v][:]
   rc = smt_conv(Xc, Wd, dL, P, t.Hc, B, t.CP, t.NP, 2 * H, H - 1, 1, 1, 0, 0, 0, 0, 0, nullptr, 0, stream);
   if (rc) return rc;
-  // blk[p*2H+dy][x][v] = sum_{y,n} XcT[p][x][y*Bp+n] * Ht[cond(p)][v][(y+dy-H)*Bp+n]
-  rc = smt_conv(XcT, Ht, blk, P * 2 * H, 1, t.CP, t.Hc * t.Bp, t.NP, 1, 0, 2, 2 * H, H * t.Bp, t.Bp, H, t.Hc, H, pair_cond, K + 1, stream);
+  // blk[p*2H+r][v][x] = sum_{y',n} Ht[cond(p)][v][y'*Bp+n] * XcT[p][x][(y'+r-(H-1))*Bp+n]      (r = 2H-1-dy: the prior row)
+  // the M side is v: exactly W pixel rows (ONE 128-row tile for W <= 128, where x = W + 1 rows would need two), N = x
+  rc = smt_conv(Ht, XcT, blk, P * 2 * H, 1, W, H * t.Bp, t.NP, 1, 0, 2, 2 * H, t.Hc * t.Bp, t.Bp, H - 1, H, t.Hc, pair_cond, K + 1, stream, 1);
   if (rc) return rc;
   {
-    if (dsmem > 48 * 1024) JCM_CUDA(cudaFuncSetAttribute(smt_dp_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
-    smt_dp_reduce_kernel<<<dim3(2 * H, P), 256, dsmem, st>>>(blk, energies, t, dE);
+    int threads = jcm_cdiv(2 * W, 32) * 32;
+    if (threads > 256) threads = 256;
+    smt_dp_reduce_kernel<<<dim3(2 * H, P), threads, 0, st>>>(blk, energies, t, dE);
     JCM_LAUNCH_CHECK();
   }
   {
