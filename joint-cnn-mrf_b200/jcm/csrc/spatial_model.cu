@@ -46,6 +46,12 @@ struct SmDims {
   // x), the tensor-core path [p][y][n][x] with padded rows (dL not flipped).
   long cb_sp, dl_sp;
   int cb_sn, cb_sy, dl_sn, dl_sy, dl_flip;
+  // tensor-core path only (NULL otherwise): the GEMMs run on sp(E) - c0[pair] (bf16 operands resolve the prior's variation, not its
+  // common level), so c0[p] * hsum[n][cond(p)] is added to every convolution result and c0[p] * dtsum[p][n] to every dL value
+  const float* cm_c0;     // [P]
+  const float* cm_hsum;   // [B][K+1]: sum over the map of sp(bn(heat map))
+  const float* cm_dtsum;  // [P][4G]:  sum over the map of dT  (= the sum of dC: the resize matrices have unit row sums)
+  const int* cm_cond;     // [P] conditioning channel of each pair
 };
 
 __device__ __forceinline__ unsigned long long pack2(float a, float b) {
@@ -290,7 +296,8 @@ __global__ void sm_finish_kernel(const float* __restrict__ hm, const float* __re
       const float bl = C[yhi * d.cb_sy + xlo], br = C[yhi * d.cb_sy + xhi];
       const float top = tl + (tr - tl) * wx;
       const float bot = bl + (br - bl) * wx;
-      const float val = top + (bot - top) * wy;
+      float val = top + (bot - top) * wy;
+      if (d.cm_c0) val += d.cm_c0[p] * d.cm_hsum[n * KC + d.cm_cond[p]];
       m += logf(val + softplus5(biases[((long)p * d.H + y) * d.W + x]) + kDelta);
     }
     fsm[x * d.K + i] = m;
@@ -329,6 +336,7 @@ size_t sm_smem_bytes(const SmDims& d) {
 // mode 0: forward  (output (H+1)x(W+1), streamed kernel HxW);  mode 1: d/d likelihood (output HxW, streamed kernel (H+1)x(W+1))
 int fill_dims(SmDims& d, int B, int H, int W, int K, int P, int mode = 0) {
   d.raw = 0;
+  d.cm_c0 = nullptr; d.cm_hsum = nullptr; d.cm_dtsum = nullptr; d.cm_cond = nullptr;
   d.B = B; d.H = H; d.W = W; d.K = K; d.P = P;
   d.G = jcm_cdiv(B, NI);
   const int KH = mode ? H + 1 : H, KW = mode ? W + 1 : W;
@@ -492,7 +500,9 @@ __global__ void sm_bwd_dt_kernel(const float* __restrict__ g, const float* __res
         const float bl = C[yhi * d.cb_sy + xlo], br = C[yhi * d.cb_sy + xhi];
         const float top = tl + (tr - tl) * wx;
         const float bot = bl + (br - bl) * wx;
-        tv = g[(((long)n * d.H + y) * d.W + x) * d.K + i] / (top + (bot - top) * wy + sb);
+        float cv = top + (bot - top) * wy;
+        if (d.cm_c0) cv += d.cm_c0[p] * d.cm_hsum[n * (d.K + 1) + d.cm_cond[p]];
+        tv = g[(((long)n * d.H + y) * d.W + x) * d.K + i] / (cv + sb);
         acc += tv;
       }
       dT[(((long)p * (4 * d.G) + n) * d.H + y) * d.W + x] = tv;
@@ -742,7 +752,10 @@ __global__ void sm_bwd_dh_kernel(const float* __restrict__ hm, const float* __re
     const float* src = dLf + (long)n * d.dl_sn + (long)(d.dl_flip ? d.H - 1 - y : y) * d.dl_sy + (d.dl_flip ? d.W - 1 - x : x);
     float s = 0.f;
     for (int p = 0; p < d.P; ++p)
-      if (pair_cond[p] == j) s += src[(long)p * d.dl_sp];
+      if (pair_cond[p] == j) {
+        s += src[(long)p * d.dl_sp];
+        if (d.cm_c0) s += d.cm_c0[p] * d.cm_dtsum[(long)p * (4 * d.G) + n];
+      }
     if (j < d.K) s += g[(((long)n * d.H + y) * d.W + x) * d.K + j] / (softplus5(hb) + kDelta);
     dhbn[e] = s * sigmoid5(hb);
   }
@@ -934,8 +947,8 @@ struct SmtDims {
   int B, H, W, K, P;
   int Hc;   // H + 1: rows of the convolution output and of the zero-padded operands
   int NP;   // GEMM N extent: W + 1 rounded up to 32
-  int CP;   // GEMM K extent of dL (x <= W): W + 1 rounded up to 64
-  int CPf;  // GEMM K extent of the forward pass (v < W): W rounded up to 64 (one k-block less than CP when W is a multiple of 64)
+  int CPf;  // GEMM K extent of the forward pass (v < W) and of dL (x' < W: the x half of the resize is folded into the dL
+            // weights, see smt_pack_prior_kernel): W rounded up to 64 - for W = 128 one k-block less than W + 1 would need
   int Bp;   // images rounded up to 16; the dP GEMM contracts over k = row * Bp + image
 };
 
@@ -943,7 +956,6 @@ int fill_smt(SmtDims& t, int B, int H, int W, int K, int P) {
   t.B = B; t.H = H; t.W = W; t.K = K; t.P = P;
   t.Hc = H + 1;
   t.NP = jcm_cdiv(W + 1, 32) * 32;
-  t.CP = jcm_cdiv(W + 1, 64) * 64;
   t.CPf = jcm_cdiv(W, 64) * 64;
   t.Bp = jcm_cdiv(B, 16) * 16;
   JCM_CHECK_ARG(t.NP <= 256, "jcm_spatial_model_tc: heat-map width %d not supported (at most 255)", W);
@@ -952,27 +964,30 @@ int fill_smt(SmtDims& t, int B, int H, int W, int K, int P) {
 
 inline size_t al256(size_t n) { return (n + 255) & ~(size_t)255; }
 
-struct SmtFwdWs { size_t spE, Xh, Wf, Cb, total; };
+struct SmtFwdWs { size_t spE, c0, hsum, Xh, Wf, Cb, total; };
 SmtFwdWs smt_fwd_layout(const SmtDims& t) {
   SmtFwdWs w;
   size_t o = 0;
   w.spE = o; o += al256((size_t)t.P * 2 * t.H * 2 * t.W * 4);
+  w.c0 = o;  o += al256((size_t)t.P * 4);
+  w.hsum = o; o += al256((size_t)t.B * (t.K + 1) * 4);
   w.Xh = o;  o += al256((size_t)(t.K + 1) * t.Hc * t.B * t.CPf * 2);
   w.Wf = o;  o += al256((size_t)t.P * 2 * t.H * t.NP * t.CPf * 2);
   w.Cb = o;  o += al256((size_t)t.P * t.Hc * t.B * t.NP * 4);
   w.total = o + 256;
   return w;
 }
-struct SmtBwdWs { size_t dT, Xc, XcT, Ht, Wd, dL, blk, dh, part, total; };
+struct SmtBwdWs { size_t dT, dtsum, Xc, XcT, Ht, Wd, dL, blk, dh, part, total; };
 SmtBwdWs smt_bwd_layout(const SmtDims& t) {
   SmtBwdWs w;
   const int G4 = 4 * jcm_cdiv(t.B, NI);
   size_t o = 0;
   w.dT = o;   o += al256((size_t)t.P * G4 * t.H * t.W * 4);
-  w.Xc = o;   o += al256((size_t)t.P * t.Hc * t.B * t.CP * 2);
+  w.dtsum = o; o += al256((size_t)t.P * G4 * 4);
+  w.Xc = o;   o += al256((size_t)t.P * t.Hc * t.B * t.CPf * 2);
   w.XcT = o;  o += al256((size_t)t.P * t.NP * t.Hc * t.Bp * 2);
   w.Ht = o;   o += al256((size_t)(t.K + 1) * t.W * t.H * t.Bp * 2);
-  w.Wd = o;   o += al256((size_t)t.P * 2 * t.H * t.NP * t.CP * 2);
+  w.Wd = o;   o += al256((size_t)t.P * 2 * t.H * t.NP * t.CPf * 2);
   w.dL = o;   o += al256((size_t)t.P * t.Hc * t.B * t.NP * 4);
   w.blk = o;  o += al256((size_t)t.P * 2 * t.H * t.W * t.NP * 4);
   w.dh = o;   o += al256((size_t)t.B * t.H * t.W * (t.K + 1) * 4);
@@ -981,15 +996,74 @@ SmtBwdWs smt_bwd_layout(const SmtDims& t) {
   return w;
 }
 
-__global__ void smt_softplus_kernel(const float* __restrict__ E, long n, float* __restrict__ spE) {
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) spE[i] = softplus5(E[i]);
+// deterministic block sum (fixed shuffle tree, then the warp sums in order); every thread gets the result.  blockDim.x multiple of 32
+__device__ __forceinline__ float smt_block_sum(float v, float* red /*[33]*/) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+// one CTA per pair: c0[p] = mean of sp(E_p), spE[p] = sp(E_p) - c0[p].  The prior is nearly flat (sp(0) = ln2/5 = 0.1386 plus a
+// variation of a few 1e-3), so rounding sp(E) itself to bf16 (steps of 1e-3 at this magnitude) would lose most of its structure;
+// the residual is resolved to 2^-9 of ITS magnitude and the common level is added back exactly, in fp32, by the glue kernels.
+__global__ void __launch_bounds__(1024)
+smt_softplus_center_kernel(const float* __restrict__ E, int n, float* __restrict__ spE, float* __restrict__ c0) {
+  __shared__ float red[33];
+  const float* src = E + (long)blockIdx.x * n;
+  float* dst = spE + (long)blockIdx.x * n;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = softplus5(src[i]);
+    dst[i] = v;
+    s += v;
+  }
+  const float mean = smt_block_sum(s, red) / (float)n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] -= mean;   // re-reads this thread's own writes
+  if (threadIdx.x == 0) c0[blockIdx.x] = mean;
+}
+
+// hsum[n][j] = sum over the map of sp(bn(hm[n, :, :, j])): one CTA per image, a thread per pixel stripe with K+1 <= 32 accumulators
+__global__ void __launch_bounds__(256)
+smt_hsum_kernel(const float* __restrict__ hm, const float* __restrict__ scale, const float* __restrict__ shift, int HW, int KC,
+                float* __restrict__ hsum) {
+  __shared__ float red[33];
+  const float* src = hm + (long)blockIdx.x * HW * KC;
+  for (int j = 0; j < KC; ++j) {
+    const float sc = scale[j], sh = shift[j];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) s += softplus5(fmaf(src[(long)i * KC + j], sc, sh));
+    const float t = smt_block_sum(s, red);
+    if (threadIdx.x == 0) hsum[blockIdx.x * KC + j] = t;
+  }
+}
+
+// dtsum[q] = sum of the HW values of dT[q], q = pair * 4G + image: one CTA per q
+__global__ void __launch_bounds__(256)
+smt_dtsum_kernel(const float* __restrict__ dT, int HW, float* __restrict__ dtsum) {
+  __shared__ float red[33];
+  const float* src = dT + (long)blockIdx.x * HW;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) s += src[i];
+  const float t = smt_block_sum(s, red);
+  if (threadIdx.x == 0) dtsum[blockIdx.x] = t;
 }
 
 // Toeplitz blocks of the prior, 8 consecutive K elements (16 bytes) per thread:
-//   Wf[p][dy][x (NP rows)][v (CPf)] = spE[p][2H-1-dy][x-v+W-1]    forward  (x <= W, v < W; 0 elsewhere)
-//   Wd[p][dy][v (NP rows)][x (CP)]  = spE[p][dy][x-v+W-1]         dL
+//   Wf[p][dy][x (NP rows)][v (CPf)]  = spE[p][2H-1-dy][x-v+W-1]    forward  (x <= W, v < W; 0 elsewhere)
+//   Wd[p][dy][v (NP rows)][x' (CPf)] = (1-w(x')) spE[p][dy][x'-v+W-1] + w(x') spE[p][dy][x'-v+W]     dL  (v < W, x' < W)
+// The dL weights carry the x half of the transposed resize: dC[y][x] = (1-w(x)) T[y][x] + w(x-1) T[y][x-1] with T = R_y^T dT, so
+// sum_{x<=W} dC[y][x] P[x-v+W-1] = sum_{x'<W} T[y][x'] Wd[v][x'] - a contraction over W instead of W + 1 columns.
 __global__ void smt_pack_prior_kernel(const float* __restrict__ spE, SmtDims t, int dl, __nv_bfloat16* __restrict__ Wt) {
-  const int C8 = (dl ? t.CP : t.CPf) / 8, H2 = 2 * t.H, W2 = 2 * t.W;
+  const int C8 = t.CPf / 8, H2 = 2 * t.H, W2 = 2 * t.W;
   const long total = (long)t.P * H2 * t.NP * C8;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     int c8, row, dy, p;
@@ -999,8 +1073,19 @@ __global__ void smt_pack_prior_kernel(const float* __restrict__ spE, SmtDims t, 
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int c = c8 * 8 + e;
-      const int x = dl ? c : row, v = dl ? row : c;
-      o[e] = __float2bfloat16_rn((x <= t.W && v < t.W) ? src[x - v + t.W - 1] : 0.f);
+      float val = 0.f;
+      if (dl) {
+        if (row < t.W && c < t.W) {
+          int lo, hi;
+          float w;
+          legacy_tap(c, t.W + 1, t.W, lo, hi, w);
+          const float a = src[c - row + t.W - 1], b = src[c - row + t.W];
+          val = a + (b - a) * w;
+        }
+      } else if (row <= t.W && c < t.W) {
+        val = src[row - c + t.W - 1];
+      }
+      o[e] = __float2bfloat16_rn(val);
     }
     reinterpret_cast<uint4*>(Wt)[idx] = *reinterpret_cast<const uint4*>(o);
   }
@@ -1042,8 +1127,9 @@ smt_prep_kernel(const float* __restrict__ hm, const float* __restrict__ scale, c
   }
 }
 
-// dC = R_y^T dT R_x on the (H+1)x(W+1) grid (as sm_bwd_dc_kernel), written as the two bf16 operands of the backward GEMMs:
-//   Xc[p][u (Hc)][n (B)][x (CP)]   (dL: A operand)      XcT[p][x (NP)][u*Bp + n]   (dP: weight rows x, K-major)
+// The two bf16 operands of the backward GEMMs from dT (P x images x H x W):
+//   Xc[p][u (Hc)][n (B)][x' (CPf)] = T = R_y^T dT  (rows resized back to H + 1, columns still W)     dL: A operand
+//   XcT[p][x (NP)][u*Bp + n]       = dC = T R_x  on the (H+1) x (W+1) grid (as sm_bwd_dc_kernel)     dP: weight rows x, K-major
 __global__ void __launch_bounds__(256)
 smt_dc_kernel(const float* __restrict__ dT, SmtDims t, int G4, __nv_bfloat16* __restrict__ Xc, __nv_bfloat16* __restrict__ XcT) {
   __shared__ float tile[64][33];
@@ -1063,20 +1149,20 @@ smt_dc_kernel(const float* __restrict__ dT, SmtDims t, int G4, __nv_bfloat16* __
   for (int nc = 0; nc < t.Bp; nc += 64) {
     for (int pass = 0; pass < 8; ++pass) {
       const int nn = pass * 8 + tn, n = nc + nn;
-      float val = 0.f;
+      float t0 = 0.f, t1 = 0.f;            // T[u][x], T[u][x-1]
       if (n < t.B && x <= W) {
         const float* src = dT + ((long)p * G4 + n) * H * W;
-        if (wy0 != 0.f) {
-          if (wx0 != 0.f) val += wy0 * wx0 * src[u * W + x];
-          if (wx1 != 0.f) val += wy0 * wx1 * src[u * W + x - 1];
+        if (x < W) {
+          if (wy0 != 0.f) t0 += wy0 * src[u * W + x];
+          if (wy1 != 0.f) t0 += wy1 * src[(u - 1) * W + x];
         }
-        if (wy1 != 0.f) {
-          if (wx0 != 0.f) val += wy1 * wx0 * src[(u - 1) * W + x];
-          if (wx1 != 0.f) val += wy1 * wx1 * src[(u - 1) * W + x - 1];
+        if (x >= 1) {
+          if (wy0 != 0.f) t1 += wy0 * src[u * W + x - 1];
+          if (wy1 != 0.f) t1 += wy1 * src[(u - 1) * W + x - 1];
         }
       }
-      tile[nn][tx] = val;
-      if (n < t.B) Xc[(((long)p * t.Hc + u) * t.B + n) * t.CP + x] = __float2bfloat16_rn(val);
+      tile[nn][tx] = wx0 * t0 + wx1 * t1;
+      if (n < t.B && x < t.CPf) Xc[(((long)p * t.Hc + u) * t.B + n) * t.CPf + x] = __float2bfloat16_rn(t0);
     }
     __syncthreads();
     {
@@ -1094,7 +1180,7 @@ smt_dc_kernel(const float* __restrict__ dT, SmtDims t, int G4, __nv_bfloat16* __
 // dE[p][r][c] = sigmoid(5 E[p][r][c]) * sum over the diagonal x - v + W - 1 = c of blk[p][r][v][x]   (blk rows v, NP columns x)
 // One CTA per (r, pair), one thread per c: for a fixed v the threads of a warp read consecutive x, so the walk down the diagonal is
 // a sequence of coalesced 128-byte reads; eight of them are in flight per thread.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 smt_dp_reduce_kernel(const float* __restrict__ blk, const float* __restrict__ E, SmtDims t, float* __restrict__ dE) {
   const int r = blockIdx.x, p = blockIdx.y;
   const int W = t.W;
@@ -1105,12 +1191,14 @@ smt_dp_reduce_kernel(const float* __restrict__ blk, const float* __restrict__ E,
     const int step = t.NP + 1;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     int n = vhi - vlo + 1;
+#pragma unroll 1
     for (; n >= 8; n -= 8, q += 8 * step) {
       const float a0 = q[0], a1 = q[step], a2 = q[2 * step], a3 = q[3 * step];
       const float a4 = q[4 * step], a5 = q[5 * step], a6 = q[6 * step], a7 = q[7 * step];
       s0 += a0; s1 += a1; s2 += a2; s3 += a3;
       s0 += a4; s1 += a5; s2 += a6; s3 += a7;
     }
+#pragma unroll 1
     for (; n > 0; --n, q += step) s0 += q[0];
     const long o = ((long)p * 2 * t.H + r) * 2 * W + c;
     dE[o] = ((s0 + s1) + (s2 + s3)) * sigmoid5(E[o]);
@@ -1146,6 +1234,7 @@ extern "C" int jcm_spatial_model_tc_fwd(const float* heat_map, const float* bn_s
   JCM_CHECK_ARG(heat_map && bn_scale && bn_shift && energies && biases && pair_target && pair_cond && out && workspace,
                 "jcm_spatial_model_tc_fwd: null pointer");
   JCM_CHECK_ARG(B > 0 && H > 1 && W > 1 && K > 0 && P > 0, "jcm_spatial_model_tc_fwd: bad shape");
+  JCM_CHECK_ARG(K + 1 <= 32, "jcm_spatial_model_tc_fwd: at most 31 joints are supported (got %d)", K);
   SmtDims t;
   int rc = fill_smt(t, B, H, W, K, P);
   if (rc) return rc;
@@ -1157,13 +1246,16 @@ extern "C" int jcm_spatial_model_tc_fwd(const float* heat_map, const float* bn_s
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* ws = (uint8_t*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   float* spE = (float*)(ws + L.spE);
+  float* c0 = (float*)(ws + L.c0);
+  float* hsum = (float*)(ws + L.hsum);
   __nv_bfloat16* Xh = (__nv_bfloat16*)(ws + L.Xh);
   __nv_bfloat16* Wf = (__nv_bfloat16*)(ws + L.Wf);
   float* Cb = (float*)(ws + L.Cb);
   const int cap = jcm_num_sms() * 16;
   {
-    const long n = (long)P * 4 * H * W;
-    smt_softplus_kernel<<<(int)((n + 255) / 256 < cap ? (n + 255) / 256 : cap), 256, 0, st>>>(energies, n, spE);
+    smt_softplus_center_kernel<<<P, 1024, 0, st>>>(energies, 4 * H * W, spE, c0);
+    JCM_LAUNCH_CHECK();
+    smt_hsum_kernel<<<B, 256, 0, st>>>(heat_map, bn_scale, bn_shift, H * W, K + 1, hsum);
     JCM_LAUNCH_CHECK();
     const long total = (long)P * 2 * H * t.NP * (t.CPf / 8);
     smt_pack_prior_kernel<<<(int)((total + 255) / 256 < cap ? (total + 255) / 256 : cap), 256, 0, st>>>(spE, t, 0, Wf);
@@ -1177,6 +1269,7 @@ extern "C" int jcm_spatial_model_tc_fwd(const float* heat_map, const float* bn_s
   SmDims d;
   fill_dims(d, B, H, W, K, P);
   d.cb_sp = (long)t.Hc * B * t.NP; d.cb_sy = B * t.NP; d.cb_sn = t.NP;
+  d.cm_c0 = c0; d.cm_hsum = hsum; d.cm_cond = pair_cond;
   {
     int threads = ((W * K + 31) / 32) * 32;
     if (threads > 1024) threads = 1024;
@@ -1223,9 +1316,12 @@ extern "C" int jcm_spatial_model_tc_bwd(const float* g, const float* heat_map, c
   cudaStream_t st = (cudaStream_t)stream;
   const uint8_t* fws = (const uint8_t*)(((uintptr_t)fwd_workspace + 255) & ~(uintptr_t)255);
   const float* spE = (const float*)(fws + LF.spE);
+  const float* c0 = (const float*)(fws + LF.c0);
+  const float* hsum = (const float*)(fws + LF.hsum);
   const float* Cb = (const float*)(fws + LF.Cb);
   uint8_t* ws = (uint8_t*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   float* dT = (float*)(ws + L.dT);
+  float* dtsum = (float*)(ws + L.dtsum);
   __nv_bfloat16* Xc = (__nv_bfloat16*)(ws + L.Xc);
   __nv_bfloat16* XcT = (__nv_bfloat16*)(ws + L.XcT);
   __nv_bfloat16* Ht = (__nv_bfloat16*)(ws + L.Ht);
@@ -1240,21 +1336,24 @@ extern "C" int jcm_spatial_model_tc_bwd(const float* g, const float* heat_map, c
   fill_dims(d, B, H, W, K, P);
   d.cb_sp = (long)t.Hc * B * t.NP; d.cb_sy = B * t.NP; d.cb_sn = t.NP;
   d.dl_sp = (long)t.Hc * B * t.NP; d.dl_sy = B * t.NP; d.dl_sn = t.NP; d.dl_flip = 0;
+  d.cm_c0 = c0; d.cm_hsum = hsum; d.cm_dtsum = dtsum; d.cm_cond = pair_cond;
   const int G4 = 4 * d.G;
   {
     const long total = (long)P * H * W;
     sm_bwd_dt_kernel<<<(int)((total + 127) / 128), 128, 0, st>>>(g, Cb, biases, pair_target, d, dT, db);
     JCM_LAUNCH_CHECK();
-    smt_dc_kernel<<<dim3(t.CP / 32, t.Hc, P), 256, 0, st>>>(dT, t, G4, Xc, XcT);
+    smt_dtsum_kernel<<<P * G4, 256, 0, st>>>(dT, H * W, dtsum);
+    JCM_LAUNCH_CHECK();
+    smt_dc_kernel<<<dim3((t.NP > t.CPf ? t.NP : t.CPf) / 32, t.Hc, P), 256, 0, st>>>(dT, t, G4, Xc, XcT);
     JCM_LAUNCH_CHECK();
     smt_prep_kernel<<<dim3(jcm_cdiv(W, 32), t.Hc, K + 1), 256, 0, st>>>(heat_map, bn_scale, bn_shift, t, nullptr, Ht);
     JCM_LAUNCH_CHECK();
-    const long tw = (long)P * 2 * H * t.NP * (t.CP / 8);
+    const long tw = (long)P * 2 * H * t.NP * (t.CPf / 8);
     smt_pack_prior_kernel<<<(int)((tw + 255) / 256 < cap ? (tw + 255) / 256 : cap), 256, 0, st>>>(spE, t, 1, Wd);
     JCM_LAUNCH_CHECK();
   }
   // dL[p][u][n][v] = sum_dy Xc[p][u+dy-(H-1)][n][:] . Wd[p][dy][v][:]
-  rc = smt_conv(Xc, Wd, dL, P, t.Hc, B, t.CP, t.NP, 2 * H, H - 1, 1, 1, 0, 0, 0, 0, 0, nullptr, 0, stream);
+  rc = smt_conv(Xc, Wd, dL, P, t.Hc, B, t.CPf, t.NP, 2 * H, H - 1, 1, 1, 0, 0, 0, 0, 0, nullptr, 0, stream);
   if (rc) return rc;
   // blk[p*2H+r][v][x] = sum_{y',n} Ht[cond(p)][v][y'*Bp+n] * XcT[p][x][(y'+r-(H-1))*Bp+n]      (r = 2H-1-dy: the prior row)
   // the M side is v: exactly W pixel rows (ONE 128-row tile for W <= 128, where x = W + 1 rows would need two), N = x

@@ -159,7 +159,7 @@ def sec_glue():
 
 def make_sm_inputs(B, K, H, W, seed=0):
     rng = np.random.default_rng(seed)
-    names = orc.JOINT_NAMES[:K] + ['torso']
+    names = (orc.JOINT_NAMES[:K] if K <= len(orc.JOINT_NAMES) - 1 else ['j%02d' % i for i in range(K)]) + ['torso']
     if (H, W) == (60, 90):
         distr = jcm.get_pairwise_distr()
     else:
@@ -498,6 +498,23 @@ def sec_smtc():
             print('SMTC case', (B, K, H, W), 'FAILED', repr(e))
             traceback.print_exc()
         sys.stdout.flush()
+
+
+def sec_smtck14():
+    """timing of the tensor-core spatial model at the K=14 / 96x128 configuration (BASELINE configs[4] per-GPU shape: batch 32)"""
+    from jcm import train as jt
+    B, K, H, W = 32, 14, 96, 128
+    names, cat, sm64 = make_sm_inputs(B, K, H, W)
+    smp = jcm.PairwiseParams.from_dict(sm64, names, K)
+    catd = cat.to(dev)
+    ss, saved = ops.bn_scale_shift(catd, smp.bn['gamma'], smp.bn['beta'], smp.bn['moving_mean'], smp.bn['moving_variance'], train=True, save=True)
+    g = torch.randn(B, H, W, K, generator=torch.Generator().manual_seed(5)).to(dev) / (B * K)
+    f = lambda: ops.spatial_model_fwd(catd, ss, smp.energies, smp.biases, smp.pair_target, smp.pair_cond, K, keep_workspace=True, tensor_core=True)
+    _, ws = f()
+    dE, db = torch.zeros_like(smp.energies), torch.zeros_like(smp.biases)
+    dg, dbt = torch.zeros(K + 1, device=dev), torch.zeros(K + 1, device=dev)
+    b = lambda: jt.spatial_model_bwd(g, catd, ss, saved, True, smp, ws, dE, db, dg, dbt, tensor_core=True)
+    print('SMTC K=14 96x128 B=32: fwd %.3f ms  bwd %.3f ms (best of 10)' % (timeit(f, 10, 3)[0], timeit(b, 10, 3)[0]))
 
 
 def sec_smtc64():
