@@ -48,10 +48,9 @@ struct SmDims {
   int cb_sn, cb_sy, dl_sn, dl_sy, dl_flip;
   // tensor-core path only (NULL otherwise): the GEMMs run on sp(E) - c0[pair] (bf16 operands resolve the prior's variation, not its
   // common level), so c0[p] * hsum[n][cond(p)] is added to every convolution result and c0[p] * dtsum[p][n] to every dL value
-  const float* cm_c0;     // [P]
-  const float* cm_hsum;   // [B][K+1]: sum over the map of sp(bn(heat map))
-  const float* cm_dtsum;  // [P][4G]:  sum over the map of dT  (= the sum of dC: the resize matrices have unit row sums)
-  const int* cm_cond;     // [P] conditioning channel of each pair
+  const float* cm_c;      // [P][B]:   c0[p] * (sum over the map of sp(bn(heat map[n, :, :, cond(p)])))
+  const float* cm_dl;     // [B][K+1]: sum over the pairs conditioned on channel j of c0[p] * (sum over the map of dT[p][n])  (the sum
+                          //           of dT equals the sum of dC: the resize matrices have unit row sums)
 };
 
 __device__ __forceinline__ unsigned long long pack2(float a, float b) {
@@ -297,7 +296,7 @@ __global__ void sm_finish_kernel(const float* __restrict__ hm, const float* __re
       const float top = tl + (tr - tl) * wx;
       const float bot = bl + (br - bl) * wx;
       float val = top + (bot - top) * wy;
-      if (d.cm_c0) val += d.cm_c0[p] * d.cm_hsum[n * KC + d.cm_cond[p]];
+      if (d.cm_c) val += d.cm_c[p * d.B + n];
       m += logf(val + softplus5(biases[((long)p * d.H + y) * d.W + x]) + kDelta);
     }
     fsm[x * d.K + i] = m;
@@ -336,7 +335,7 @@ size_t sm_smem_bytes(const SmDims& d) {
 // mode 0: forward  (output (H+1)x(W+1), streamed kernel HxW);  mode 1: d/d likelihood (output HxW, streamed kernel (H+1)x(W+1))
 int fill_dims(SmDims& d, int B, int H, int W, int K, int P, int mode = 0) {
   d.raw = 0;
-  d.cm_c0 = nullptr; d.cm_hsum = nullptr; d.cm_dtsum = nullptr; d.cm_cond = nullptr;
+  d.cm_c = nullptr; d.cm_dl = nullptr;
   d.B = B; d.H = H; d.W = W; d.K = K; d.P = P;
   d.G = jcm_cdiv(B, NI);
   const int KH = mode ? H + 1 : H, KW = mode ? W + 1 : W;
@@ -501,7 +500,7 @@ __global__ void sm_bwd_dt_kernel(const float* __restrict__ g, const float* __res
         const float top = tl + (tr - tl) * wx;
         const float bot = bl + (br - bl) * wx;
         float cv = top + (bot - top) * wy;
-        if (d.cm_c0) cv += d.cm_c0[p] * d.cm_hsum[n * (d.K + 1) + d.cm_cond[p]];
+        if (d.cm_c) cv += d.cm_c[p * d.B + n];
         tv = g[(((long)n * d.H + y) * d.W + x) * d.K + i] / (cv + sb);
         acc += tv;
       }
@@ -752,10 +751,8 @@ __global__ void sm_bwd_dh_kernel(const float* __restrict__ hm, const float* __re
     const float* src = dLf + (long)n * d.dl_sn + (long)(d.dl_flip ? d.H - 1 - y : y) * d.dl_sy + (d.dl_flip ? d.W - 1 - x : x);
     float s = 0.f;
     for (int p = 0; p < d.P; ++p)
-      if (pair_cond[p] == j) {
-        s += src[(long)p * d.dl_sp];
-        if (d.cm_c0) s += d.cm_c0[p] * d.cm_dtsum[(long)p * (4 * d.G) + n];
-      }
+      if (pair_cond[p] == j) s += src[(long)p * d.dl_sp];
+    if (d.cm_dl) s += d.cm_dl[n * KC + j];
     if (j < d.K) s += g[(((long)n * d.H + y) * d.W + x) * d.K + j] / (softplus5(hb) + kDelta);
     dhbn[e] = s * sigmoid5(hb);
   }
@@ -943,6 +940,8 @@ extern "C" int jcm_spatial_model_bwd(const float* g, const float* heat_map, cons
 // =====================================================================================================================
 namespace {
 
+constexpr int kHsumChunks = 16;   // pixel chunks per image of the heat-map sums (smt_hsum_partial_kernel)
+
 struct SmtDims {
   int B, H, W, K, P;
   int Hc;   // H + 1: rows of the convolution output and of the zero-padded operands
@@ -964,26 +963,28 @@ int fill_smt(SmtDims& t, int B, int H, int W, int K, int P) {
 
 inline size_t al256(size_t n) { return (n + 255) & ~(size_t)255; }
 
-struct SmtFwdWs { size_t spE, c0, hsum, Xh, Wf, Cb, total; };
+struct SmtFwdWs { size_t spE, c0, hsum, cmc, Xh, Wf, Cb, total; };
 SmtFwdWs smt_fwd_layout(const SmtDims& t) {
   SmtFwdWs w;
   size_t o = 0;
   w.spE = o; o += al256((size_t)t.P * 2 * t.H * 2 * t.W * 4);
   w.c0 = o;  o += al256((size_t)t.P * 4);
-  w.hsum = o; o += al256((size_t)t.B * (t.K + 1) * 4);
+  w.hsum = o; o += al256((size_t)t.B * kHsumChunks * (t.K + 1) * 4);
+  w.cmc = o;  o += al256((size_t)t.P * t.B * 4);
   w.Xh = o;  o += al256((size_t)(t.K + 1) * t.Hc * t.B * t.CPf * 2);
   w.Wf = o;  o += al256((size_t)t.P * 2 * t.H * t.NP * t.CPf * 2);
   w.Cb = o;  o += al256((size_t)t.P * t.Hc * t.B * t.NP * 4);
   w.total = o + 256;
   return w;
 }
-struct SmtBwdWs { size_t dT, dtsum, Xc, XcT, Ht, Wd, dL, blk, dh, part, total; };
+struct SmtBwdWs { size_t dT, dtsum, cmdl, Xc, XcT, Ht, Wd, dL, blk, dh, part, total; };
 SmtBwdWs smt_bwd_layout(const SmtDims& t) {
   SmtBwdWs w;
   const int G4 = 4 * jcm_cdiv(t.B, NI);
   size_t o = 0;
   w.dT = o;   o += al256((size_t)t.P * G4 * t.H * t.W * 4);
   w.dtsum = o; o += al256((size_t)t.P * G4 * 4);
+  w.cmdl = o; o += al256((size_t)t.B * (t.K + 1) * 4);
   w.Xc = o;   o += al256((size_t)t.P * t.Hc * t.B * t.CPf * 2);
   w.XcT = o;  o += al256((size_t)t.P * t.NP * t.Hc * t.Bp * 2);
   w.Ht = o;   o += al256((size_t)(t.K + 1) * t.W * t.H * t.Bp * 2);
@@ -1031,19 +1032,57 @@ smt_softplus_center_kernel(const float* __restrict__ E, int n, float* __restrict
   if (threadIdx.x == 0) c0[blockIdx.x] = mean;
 }
 
-// hsum[n][j] = sum over the map of sp(bn(hm[n, :, :, j])): one CTA per image, a thread per pixel stripe with K+1 <= 32 accumulators
+// hpart[n][chunk][j] = sum over the chunk's pixels of sp(bn(hm[n, pixel, j])): grid (chunks, images); a thread walks its pixels with
+// K+1 <= 32 running sums (one 4(K+1)-byte read per pixel), then the block adds them up channel by channel in a fixed order
 __global__ void __launch_bounds__(256)
-smt_hsum_kernel(const float* __restrict__ hm, const float* __restrict__ scale, const float* __restrict__ shift, int HW, int KC,
-                float* __restrict__ hsum) {
+smt_hsum_partial_kernel(const float* __restrict__ hm, const float* __restrict__ scale, const float* __restrict__ shift, int HW, int KC,
+                        float* __restrict__ hpart) {
   __shared__ float red[33];
-  const float* src = hm + (long)blockIdx.x * HW * KC;
-  for (int j = 0; j < KC; ++j) {
-    const float sc = scale[j], sh = shift[j];
-    float s = 0.f;
-    for (int i = threadIdx.x; i < HW; i += blockDim.x) s += softplus5(fmaf(src[(long)i * KC + j], sc, sh));
-    const float t = smt_block_sum(s, red);
-    if (threadIdx.x == 0) hsum[blockIdx.x * KC + j] = t;
+  __shared__ float sc[32], sh[32];
+  if (threadIdx.x < KC) { sc[threadIdx.x] = scale[threadIdx.x]; sh[threadIdx.x] = shift[threadIdx.x]; }
+  __syncthreads();
+  const int per = (HW + kHsumChunks - 1) / kHsumChunks;
+  const int lo = blockIdx.x * per, hi = min(HW, lo + per);
+  const float* src = hm + (long)blockIdx.y * HW * KC;
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < KC) acc[j] += softplus5(fmaf(src[(long)i * KC + j], sc[j], sh[j]));
   }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (j < KC) {
+      const float t = smt_block_sum(acc[j], red);
+      if (threadIdx.x == 0) hpart[((long)blockIdx.y * kHsumChunks + blockIdx.x) * KC + j] = t;
+    }
+  }
+}
+
+// cm_c[p][n] = c0[p] * sum_chunks hpart[n][chunk][cond(p)]      (thread per (p, n))
+__global__ void smt_cmc_kernel(const float* __restrict__ hpart, const float* __restrict__ c0, const int* __restrict__ pair_cond, int P, int B,
+                               int KC, float* __restrict__ cmc) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P * B) return;
+  const int p = idx / B, n = idx - p * B;
+  const int j = pair_cond[p];
+  float h = 0.f;
+  for (int c = 0; c < kHsumChunks; ++c) h += hpart[((long)n * kHsumChunks + c) * KC + j];
+  cmc[idx] = c0[p] * h;
+}
+
+// cm_dl[n][j] = sum_{p: cond(p) = j, in list order} c0[p] * dtsum[p][n]      (thread per (n, j))
+__global__ void smt_cmdl_kernel(const float* __restrict__ dtsum, const float* __restrict__ c0, const int* __restrict__ pair_cond, int P, int B,
+                                int G4, int KC, float* __restrict__ cmdl) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * KC) return;
+  const int n = idx / KC, j = idx - n * KC;
+  float s = 0.f;
+  for (int p = 0; p < P; ++p)
+    if (pair_cond[p] == j) s += c0[p] * dtsum[(long)p * G4 + n];
+  cmdl[idx] = s;
 }
 
 // dtsum[q] = sum of the HW values of dT[q], q = pair * 4G + image: one CTA per q
@@ -1062,32 +1101,56 @@ smt_dtsum_kernel(const float* __restrict__ dT, int HW, float* __restrict__ dtsum
 //   Wd[p][dy][v (NP rows)][x' (CPf)] = (1-w(x')) spE[p][dy][x'-v+W-1] + w(x') spE[p][dy][x'-v+W]     dL  (v < W, x' < W)
 // The dL weights carry the x half of the transposed resize: dC[y][x] = (1-w(x)) T[y][x] + w(x-1) T[y][x-1] with T = R_y^T dT, so
 // sum_{x<=W} dC[y][x] P[x-v+W-1] = sum_{x'<W} T[y][x'] Wd[v][x'] - a contraction over W instead of W + 1 columns.
-__global__ void smt_pack_prior_kernel(const float* __restrict__ spE, SmtDims t, int dl, __nv_bfloat16* __restrict__ Wt) {
-  const int C8 = t.CPf / 8, H2 = 2 * t.H, W2 = 2 * t.W;
-  const long total = (long)t.P * H2 * t.NP * C8;
-  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    int c8, row, dy, p;
-    split_index(idx, C8, t.NP, H2, c8, row, dy, p);
-    const float* src = spE + ((long)p * H2 + (dl ? dy : H2 - 1 - dy)) * W2;
-    __align__(16) __nv_bfloat16 o[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int c = c8 * 8 + e;
-      float val = 0.f;
-      if (dl) {
-        if (row < t.W && c < t.W) {
-          int lo, hi;
-          float w;
-          legacy_tap(c, t.W + 1, t.W, lo, hi, w);
-          const float a = src[c - row + t.W - 1], b = src[c - row + t.W];
-          val = a + (b - a) * w;
-        }
-      } else if (row <= t.W && c < t.W) {
-        val = src[row - c + t.W - 1];
-      }
-      o[e] = __float2bfloat16_rn(val);
+// One CTA per (dy, pair): the prior row (2W floats) and the interpolation weights w(x') go through shared memory; a thread owns one
+// 16-byte column group c8 and walks down the NP rows.
+__global__ void __launch_bounds__(256)
+smt_pack_prior_kernel(const float* __restrict__ spE, SmtDims t, int dl, __nv_bfloat16* __restrict__ Wt) {
+  extern __shared__ float psm[];            // [2W] prior row, [W] w(x')
+  float* srow = psm;
+  float* wtab = psm + 2 * t.W;
+  const int dy = blockIdx.x, p = blockIdx.y;
+  const int C8 = t.CPf / 8, H2 = 2 * t.H, W2 = 2 * t.W, W = t.W;
+  const float* src = spE + ((long)p * H2 + (dl ? dy : H2 - 1 - dy)) * W2;
+  for (int i = threadIdx.x; i < W2; i += blockDim.x) srow[i] = src[i];
+  if (dl)
+    for (int i = threadIdx.x; i < W; i += blockDim.x) {
+      int lo, hi;
+      float w;
+      legacy_tap(i, W + 1, W, lo, hi, w);
+      wtab[i] = w;
     }
-    reinterpret_cast<uint4*>(Wt)[idx] = *reinterpret_cast<const uint4*>(o);
+  __syncthreads();
+  const int rows_per_pass = blockDim.x / C8;
+  const int c8 = threadIdx.x % C8, r0 = threadIdx.x / C8;
+  if (r0 >= rows_per_pass) return;
+  uint4* dst = reinterpret_cast<uint4*>(Wt) + ((long)p * H2 + dy) * t.NP * C8;
+  const int cbase = c8 * 8;
+  for (int row = r0; row < t.NP; row += rows_per_pass) {
+    uint32_t o[4] = {0u, 0u, 0u, 0u};
+    if (cbase < W && row < W + (dl ? 0 : 1)) {
+      float v[8];
+      if (dl) {
+        const float* q = srow + (cbase - row + W - 1);      // q[e] = a, q[e + 1] = b of column cbase + e
+        float prev = q[0];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const bool ok = cbase + e < W;
+          const float nxt = ok ? q[e + 1] : 0.f;
+          v[e] = ok ? prev + (nxt - prev) * wtab[cbase + e] : 0.f;
+          prev = nxt;
+        }
+      } else {
+        const float* q = srow + (row - cbase + W - 1);      // column cbase + e reads q[-e]
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = (cbase + e < W) ? q[-e] : 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+        o[e] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+    }
+    dst[(long)row * C8 + c8] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -1178,30 +1241,40 @@ smt_dc_kernel(const float* __restrict__ dT, SmtDims t, int G4, __nv_bfloat16* __
 }
 
 // dE[p][r][c] = sigmoid(5 E[p][r][c]) * sum over the diagonal x - v + W - 1 = c of blk[p][r][v][x]   (blk rows v, NP columns x)
-// One CTA per (r, pair), one thread per c: for a fixed v the threads of a warp read consecutive x, so the walk down the diagonal is
-// a sequence of coalesced 128-byte reads; eight of them are in flight per thread.
+// One CTA per (r, pair), one thread per c.  All lanes of a warp walk the SAME rows v (from the first row any of its diagonals touches
+// to the last), each reading its own column x = c + v - (W - 1) when that lies in [0, W]: every warp load is one contiguous run
+// of a row, eight rows in flight per thread.
 __global__ void __launch_bounds__(256, 4)
 smt_dp_reduce_kernel(const float* __restrict__ blk, const float* __restrict__ E, SmtDims t, float* __restrict__ dE) {
   const int r = blockIdx.x, p = blockIdx.y;
-  const int W = t.W;
-  const float* src = blk + ((long)p * 2 * t.H + r) * W * t.NP;
-  for (int c = threadIdx.x; c < 2 * W; c += blockDim.x) {
-    const int vlo = max(0, W - 1 - c), vhi = min(W - 1, 2 * W - 1 - c);
-    const float* q = src + (long)vlo * t.NP + (c + vlo - (W - 1));
-    const int step = t.NP + 1;
+  const int W = t.W, NP = t.NP;
+  const float* src = blk + ((long)p * 2 * t.H + r) * W * NP;
+  for (int cb = threadIdx.x & ~31; cb < 2 * W; cb += blockDim.x) {          // warp-uniform loop: cb = the warp's first diagonal
+    const int c = cb + (threadIdx.x & 31);
+    const int v_lo = max(0, W - 1 - (cb + 31)), v_hi = min(W - 1, 2 * W - 1 - cb);
+    const int x0 = c - (W - 1);                                              // x = x0 + v
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int n = vhi - vlo + 1;
+    int v = v_lo;
 #pragma unroll 1
-    for (; n >= 8; n -= 8, q += 8 * step) {
-      const float a0 = q[0], a1 = q[step], a2 = q[2 * step], a3 = q[3 * step];
-      const float a4 = q[4 * step], a5 = q[5 * step], a6 = q[6 * step], a7 = q[7 * step];
-      s0 += a0; s1 += a1; s2 += a2; s3 += a3;
-      s0 += a4; s1 += a5; s2 += a6; s3 += a7;
+    for (; v + 8 <= v_hi + 1; v += 8) {
+      float a[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int x = x0 + v + k;
+        a[k] = ((unsigned)x <= (unsigned)W) ? src[(long)(v + k) * NP + x] : 0.f;
+      }
+      s0 += a[0]; s1 += a[1]; s2 += a[2]; s3 += a[3];
+      s0 += a[4]; s1 += a[5]; s2 += a[6]; s3 += a[7];
     }
 #pragma unroll 1
-    for (; n > 0; --n, q += step) s0 += q[0];
-    const long o = ((long)p * 2 * t.H + r) * 2 * W + c;
-    dE[o] = ((s0 + s1) + (s2 + s3)) * sigmoid5(E[o]);
+    for (; v <= v_hi; ++v) {
+      const int x = x0 + v;
+      if ((unsigned)x <= (unsigned)W) s0 += src[(long)v * NP + x];
+    }
+    if (c < 2 * W) {
+      const long o = ((long)p * 2 * t.H + r) * 2 * W + c;
+      dE[o] = ((s0 + s1) + (s2 + s3)) * sigmoid5(E[o]);
+    }
   }
 }
 
@@ -1248,6 +1321,7 @@ extern "C" int jcm_spatial_model_tc_fwd(const float* heat_map, const float* bn_s
   float* spE = (float*)(ws + L.spE);
   float* c0 = (float*)(ws + L.c0);
   float* hsum = (float*)(ws + L.hsum);
+  float* cmc = (float*)(ws + L.cmc);
   __nv_bfloat16* Xh = (__nv_bfloat16*)(ws + L.Xh);
   __nv_bfloat16* Wf = (__nv_bfloat16*)(ws + L.Wf);
   float* Cb = (float*)(ws + L.Cb);
@@ -1255,10 +1329,11 @@ extern "C" int jcm_spatial_model_tc_fwd(const float* heat_map, const float* bn_s
   {
     smt_softplus_center_kernel<<<P, 1024, 0, st>>>(energies, 4 * H * W, spE, c0);
     JCM_LAUNCH_CHECK();
-    smt_hsum_kernel<<<B, 256, 0, st>>>(heat_map, bn_scale, bn_shift, H * W, K + 1, hsum);
+    smt_hsum_partial_kernel<<<dim3(kHsumChunks, B), 256, 0, st>>>(heat_map, bn_scale, bn_shift, H * W, K + 1, hsum);
     JCM_LAUNCH_CHECK();
-    const long total = (long)P * 2 * H * t.NP * (t.CPf / 8);
-    smt_pack_prior_kernel<<<(int)((total + 255) / 256 < cap ? (total + 255) / 256 : cap), 256, 0, st>>>(spE, t, 0, Wf);
+    smt_cmc_kernel<<<(P * B + 255) / 256, 256, 0, st>>>(hsum, c0, pair_cond, P, B, K + 1, cmc);
+    JCM_LAUNCH_CHECK();
+    smt_pack_prior_kernel<<<dim3(2 * H, P), 256, (size_t)3 * W * sizeof(float), st>>>(spE, t, 0, Wf);
     JCM_LAUNCH_CHECK();
     smt_prep_kernel<<<dim3(t.CPf / 32, t.Hc, K + 1), 256, 0, st>>>(heat_map, bn_scale, bn_shift, t, Xh, nullptr);
     JCM_LAUNCH_CHECK();
@@ -1269,7 +1344,7 @@ extern "C" int jcm_spatial_model_tc_fwd(const float* heat_map, const float* bn_s
   SmDims d;
   fill_dims(d, B, H, W, K, P);
   d.cb_sp = (long)t.Hc * B * t.NP; d.cb_sy = B * t.NP; d.cb_sn = t.NP;
-  d.cm_c0 = c0; d.cm_hsum = hsum; d.cm_cond = pair_cond;
+  d.cm_c = cmc;
   {
     int threads = ((W * K + 31) / 32) * 32;
     if (threads > 1024) threads = 1024;
@@ -1317,11 +1392,12 @@ extern "C" int jcm_spatial_model_tc_bwd(const float* g, const float* heat_map, c
   const uint8_t* fws = (const uint8_t*)(((uintptr_t)fwd_workspace + 255) & ~(uintptr_t)255);
   const float* spE = (const float*)(fws + LF.spE);
   const float* c0 = (const float*)(fws + LF.c0);
-  const float* hsum = (const float*)(fws + LF.hsum);
+  const float* cmc = (const float*)(fws + LF.cmc);
   const float* Cb = (const float*)(fws + LF.Cb);
   uint8_t* ws = (uint8_t*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   float* dT = (float*)(ws + L.dT);
   float* dtsum = (float*)(ws + L.dtsum);
+  float* cmdl = (float*)(ws + L.cmdl);
   __nv_bfloat16* Xc = (__nv_bfloat16*)(ws + L.Xc);
   __nv_bfloat16* XcT = (__nv_bfloat16*)(ws + L.XcT);
   __nv_bfloat16* Ht = (__nv_bfloat16*)(ws + L.Ht);
@@ -1336,7 +1412,7 @@ extern "C" int jcm_spatial_model_tc_bwd(const float* g, const float* heat_map, c
   fill_dims(d, B, H, W, K, P);
   d.cb_sp = (long)t.Hc * B * t.NP; d.cb_sy = B * t.NP; d.cb_sn = t.NP;
   d.dl_sp = (long)t.Hc * B * t.NP; d.dl_sy = B * t.NP; d.dl_sn = t.NP; d.dl_flip = 0;
-  d.cm_c0 = c0; d.cm_hsum = hsum; d.cm_dtsum = dtsum; d.cm_cond = pair_cond;
+  d.cm_c = cmc; d.cm_dl = cmdl;
   const int G4 = 4 * d.G;
   {
     const long total = (long)P * H * W;
@@ -1344,12 +1420,13 @@ extern "C" int jcm_spatial_model_tc_bwd(const float* g, const float* heat_map, c
     JCM_LAUNCH_CHECK();
     smt_dtsum_kernel<<<P * G4, 256, 0, st>>>(dT, H * W, dtsum);
     JCM_LAUNCH_CHECK();
+    smt_cmdl_kernel<<<(B * (K + 1) + 127) / 128, 128, 0, st>>>(dtsum, c0, pair_cond, P, B, G4, K + 1, cmdl);
+    JCM_LAUNCH_CHECK();
     smt_dc_kernel<<<dim3((t.NP > t.CPf ? t.NP : t.CPf) / 32, t.Hc, P), 256, 0, st>>>(dT, t, G4, Xc, XcT);
     JCM_LAUNCH_CHECK();
     smt_prep_kernel<<<dim3(jcm_cdiv(W, 32), t.Hc, K + 1), 256, 0, st>>>(heat_map, bn_scale, bn_shift, t, nullptr, Ht);
     JCM_LAUNCH_CHECK();
-    const long tw = (long)P * 2 * H * t.NP * (t.CPf / 8);
-    smt_pack_prior_kernel<<<(int)((tw + 255) / 256 < cap ? (tw + 255) / 256 : cap), 256, 0, st>>>(spE, t, 1, Wd);
+    smt_pack_prior_kernel<<<dim3(2 * H, P), 256, (size_t)3 * W * sizeof(float), st>>>(spE, t, 1, Wd);
     JCM_LAUNCH_CHECK();
   }
   // dL[p][u][n][v] = sum_dy Xc[p][u+dy-(H-1)][n][:] . Wd[p][dy][v][:]
