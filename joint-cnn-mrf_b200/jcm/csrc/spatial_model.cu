@@ -1209,8 +1209,9 @@ smt_dc_kernel(const float* __restrict__ dT, SmtDims t, int G4, __nv_bfloat16* __
   float wx0 = 0.f, wx1 = 0.f;
   if (x < W) { legacy_tap(x, W + 1, W, lo, hi, w); wx0 = 1.f - w; }
   if (x >= 1 && x <= W) { legacy_tap(x - 1, W + 1, W, lo, hi, w); wx1 = w; }
-  for (int nc = 0; nc < t.Bp; nc += 64) {
-    for (int pass = 0; pass < 8; ++pass) {
+  const int rows = t.Bp < 64 ? t.Bp : 64;           // images per tile pass (a multiple of 16): no idle half tile for batches of 16 / 32 / 48
+  for (int nc = 0; nc < t.Bp; nc += rows) {
+    for (int pass = 0; pass * 8 < rows; ++pass) {
       const int nn = pass * 8 + tn, n = nc + nn;
       float t0 = 0.f, t1 = 0.f;            // T[u][x], T[u][x-1]
       if (n < t.B && x <= W) {
@@ -1229,12 +1230,11 @@ smt_dc_kernel(const float* __restrict__ dT, SmtDims t, int G4, __nv_bfloat16* __
     }
     __syncthreads();
     {
-      const int nn = threadIdx.x & 63, xb = threadIdx.x >> 6;
+      const int nn = threadIdx.x % rows, xb = threadIdx.x / rows, xper = 256 / rows;   // rows in {16, 32, 48, 64}: 48 leaves 16 threads idle
       const int n = nc + nn;
-      for (int pass = 0; pass < 8; ++pass) {
-        const int xx = pass * 4 + xb;
-        if (n < t.Bp && x0 + xx < t.NP) XcT[((long)p * t.NP + x0 + xx) * KA + (long)u * t.Bp + n] = __float2bfloat16_rn(tile[nn][xx]);
-      }
+      if (xb < xper)
+        for (int xx = xb; xx < 32; xx += xper)
+          if (n < t.Bp && x0 + xx < t.NP) XcT[((long)p * t.NP + x0 + xx) * KA + (long)u * t.Bp + n] = __float2bfloat16_rn(tile[nn][xx]);
     }
     __syncthreads();
   }

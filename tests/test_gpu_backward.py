@@ -37,6 +37,18 @@ def jtrain(jcm):
     return train
 
 
+def _note(line):
+    """measured values go to gpurun_out/round2_parity.txt (copied to profiles/ by hand) as well as to the captured stdout"""
+    print(line)
+    try:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        os.makedirs(os.path.join(root, 'gpurun_out'), exist_ok=True)
+        with open(os.path.join(root, 'gpurun_out', 'round2_parity.txt'), 'a') as fh:
+            fh.write(line + '\n')
+    except OSError:
+        pass
+
+
 def rel(a, b, floor=0.0):
     a = a.detach().double().cpu()
     b = torch.as_tensor(np.asarray(b)).double() if not torch.is_tensor(b) else b.detach().double().cpu()
@@ -234,12 +246,20 @@ def test_conv1_stride2_wgrad_via_space_to_depth(jcm, jtrain, split):
 # ------------------------------------------------------------------------------------------------ spatial model
 @pytest.mark.parametrize('B,K,H,W', [(2, 4, 12, 20), (5, 3, 9, 13), (2, 7, 60, 90), (6, 7, 60, 90), (3, 2, 96, 128)])
 @pytest.mark.parametrize('train', [True, False])
-@pytest.mark.parametrize('tensor_core', [False, True])
+@pytest.mark.parametrize('tensor_core', [False, True, 'rough'])
 def test_spatial_model_bwd(jcm, jtrain, B, K, H, W, train, tensor_core):
     """dE, db, d(bn gamma/beta), d(heat map) of SURVEY Appendix D vs autograd of the oracle.  tensor_core: the grouped Toeplitz
-    GEMM form of the bf16 configuration (jcm_spatial_model_tc_*): same interface, bf16 operand rounding (2^-9 per operand) in the
-    pairwise convolutions, so its bounds are the bf16 ones (stated here; measured 3e-4 forward, <= 5e-3 on the gradients)."""
-    tol_o, tol_g = (2e-3, 1.5e-2) if tensor_core else (1e-4, 3e-4)
+    GEMM form of the bf16 configuration (jcm_spatial_model_tc_*): same interface, bf16 operands in the pairwise convolutions.  The
+    prior operand is centred per pair (sp(E) - its mean; the common level is added back in fp32), so on priors like the
+    reference's (nearly flat: sp(0) = 0.1386 plus a few 1e-3 of structure) everything that is linear in the prior comes out at the
+    fp32 kernels' bounds - measured logits 2e-7..1.2e-5, d(heat map) / db / d(gamma, beta) <= 5e-5; stated 1e-4 / 3e-4.  The prior
+    gradient is a product of two bf16-rounded activations: measured 2.5e-3..4.5e-3 of max, cosine 0.999998; stated 1.5e-2 / 0.9995.
+    'rough': energies perturbed by N(0, 0.3^2) (sp(E) between 0.03 and 0.6, the centring no longer helps): the plain bf16 bounds,
+    2e-3 on the logits and 1.5e-2 on every gradient."""
+    rough = tensor_core == 'rough'
+    tensor_core = bool(tensor_core)
+    tol_o, tol_g = ((2e-3, 1.5e-2) if rough else (1e-4, 3e-4))
+    tol_e = 1.5e-2 if tensor_core else tol_g
     seed = 16
     rng = np.random.default_rng(seed)
     g = torch.Generator().manual_seed(seed)
@@ -253,6 +273,8 @@ def test_spatial_model_bwd(jcm, jtrain, B, K, H, W, train, tensor_core):
             v.add_(torch.randn(v.shape, generator=g).double() * 0.1)
         if 'moving_variance' in k:
             v.add_(torch.rand(v.shape, generator=g).double())
+        if rough and k.startswith('energy_'):
+            v.add_(torch.randn(v.shape, generator=g).double() * 0.3)
     sm32 = {k: v.float() for k, v in sm64.items()}
     hm = torch.softmax(3 * torch.randn(B, H * W, K, generator=g), dim=1).reshape(B, H, W, K)
     cat = torch.cat([hm, torch.from_numpy(orc.synthetic_labels(B, H, W, 1, rng))], dim=3).contiguous()
@@ -269,17 +291,21 @@ def test_spatial_model_bwd(jcm, jtrain, B, K, H, W, train, tensor_core):
     ss, st = jcm.ops.bn_scale_shift(catg, bn['gamma'], bn['beta'], bn['moving_mean'], bn['moving_variance'], train=train, save=True)
     o, ws = jcm.ops.spatial_model_fwd(catg, ss, smp.energies, smp.biases, smp.pair_target, smp.pair_cond, K, keep_workspace=True,
                                       tensor_core=tensor_core)
-    assert rel(o, out) < tol_o
+    err_o = rel(o, out)
+    assert err_o < tol_o, err_o
     dE, db = torch.empty_like(smp.energies), torch.empty_like(smp.biases)
     dgamma, dbeta = torch.empty(K + 1, device='cuda'), torch.empty(K + 1, device='cuda')
     d_hm = jtrain.spatial_model_bwd(gout.cuda(), catg, ss, st, train, smp, ws, dE, db, dgamma, dbeta, tensor_core=tensor_core)
     refE = torch.stack([so['energy_' + k].grad[0, :, :, 0] for k in smp.keys])
     refb = torch.stack([so['bias_' + k].grad[0, :, :, 0] for k in smp.keys])
-    assert rel(dE, refE) < tol_g
-    assert rel(db, refb) < tol_g
-    assert rel(d_hm, cat64.grad) < tol_g
-    assert rel(dgamma, so['bn_sm/BatchNorm/gamma'].grad) < tol_g
-    assert rel(dbeta, so['bn_sm/BatchNorm/beta'].grad) < tol_g
+    errs = dict(out=err_o, dE=rel(dE, refE), db=rel(db, refb), d_hm=rel(d_hm, cat64.grad),
+                dgamma=rel(dgamma, so['bn_sm/BatchNorm/gamma'].grad), dbeta=rel(dbeta, so['bn_sm/BatchNorm/beta'].grad))
+    if tensor_core:
+        _note('spatial model bwd %s B%d K%d %dx%d train=%d: %s' % ('tc-rough' if rough else 'tc', B, K, H, W, train,
+                                                                  ', '.join('%s %.2e' % kv for kv in errs.items())))
+    assert errs['dE'] < tol_e, errs
+    for k in ('db', 'd_hm', 'dgamma', 'dbeta'):
+        assert errs[k] < tol_g, (k, errs)
     if tensor_core:   # direction of the big gradients, not just their scale
         assert cosine(dE, refE) > 0.9995 and cosine(d_hm, cat64.grad) > 0.9995
 

@@ -129,8 +129,9 @@ def test_spatial_model_tensor_core_k14_96x128(jcm, jtrain):
     """BASELINE config 5 shapes (K=14 joints + torso, 96x128 maps, 196 pairwise terms), B=5 (odd: ragged batch tile), training-mode
     bn_sm: forward and every gradient of the tensor-core form (grouped Toeplitz GEMMs, N = 160 tiles, two M tiles in the dP GEMM)
     against the fp64 oracle (its 'valid' convolutions evaluated through FFT, equal to the direct form to 1e-13).  Same bounds as
-    the 60x90 case: logits 2e-3, gradients 1.5e-2 of max with cosine > 0.9995.  The fp32 FFMA form is checked on the same inputs
-    at its own bounds (1e-4 / 3e-4)."""
+    the 60x90 case: with the prior centred per pair the logits and every gradient that is linear in the prior meet the fp32
+    kernels' bounds (1e-4 / 3e-4; measured 3e-7 / <= 3e-6), the prior gradient 1.5e-2 of max with cosine > 0.9995 (measured
+    2.7e-3).  The fp32 FFMA form is checked on the same inputs at 1e-4 / 3e-4."""
     B, K, H, W = 5, 14, 96, 128
     seed = 44
     rng = np.random.default_rng(seed)
@@ -152,7 +153,7 @@ def test_spatial_model_tensor_core_k14_96x128(jcm, jtrain):
     out = orc.spatial_model(cat64, so, K, True, joint_names=names, fft=True)
     (out * gout.double()).sum().backward()
 
-    for tensor_core, tol_o, tol_g in ((True, 2e-3, 1.5e-2), (False, 1e-4, 3e-4)):
+    for tensor_core, tol_o, tol_g in ((True, 1e-4, 3e-4), (False, 1e-4, 3e-4)):
         smp = jcm.PairwiseParams.from_dict(sm32, names, K)
         bn = smp.bn
         catg = cat.cuda()
@@ -169,7 +170,8 @@ def test_spatial_model_tensor_core_k14_96x128(jcm, jtrain):
                     cos_dE=cosine(dE, refE), cos_dhm=cosine(d_hm, cat64.grad))
         note('K=14 96x128 spatial model (%s): %s' % ('tensor-core' if tensor_core else 'FFMA', ', '.join('%s %.2e' % (k, v) if not k.startswith('cos') else '%s %.6f' % (k, v) for k, v in vals.items())))
         assert vals['out'] < tol_o
-        for k in ('dE', 'db', 'd_hm', 'dgamma', 'dbeta'):
+        assert vals['dE'] < (1.5e-2 if tensor_core else tol_g), (tensor_core, vals['dE'])
+        for k in ('db', 'd_hm', 'dgamma', 'dbeta'):
             assert vals[k] < tol_g, (tensor_core, k, vals[k])
         assert vals['cos_dE'] > 0.9995 and vals['cos_dhm'] > 0.9995
         del ws, o, d_hm, dE, db
