@@ -226,7 +226,7 @@ def measure(workload, steps, warmup, args, rank, world, local, dev, with_cpu_bas
     sm = jcm.PairwiseParams.from_distribution(distr, names, K, IH // 8, IW // 8, device=dev)
     ctx = jcm.Context(n_joints=K, joint_names=names, flag_train=train, precision=precision,
                       bf16_activations=None if args.bf16_activations is None else bool(args.bf16_activations),
-                      sm_tensor_core=False if args.sm_ffma else None)
+                      sm_tensor_core=False if args.sm_ffma else (True if args.sm_tc else None))
 
     x_host = torch.rand(B, IH, IW, 3, generator=gen).pin_memory()
     y_host = torch.from_numpy(synthetic_labels(B, IH // 8, IW // 8, K + 1, np.random.default_rng(rank))).pin_memory()
@@ -403,11 +403,14 @@ def measure(workload, steps, warmup, args, rank, world, local, dev, with_cpu_bas
     if sm_prof and sm_prof[0]['launches']:
         # the spatial model (north_star's second kernel family): CUDA-event time of the whole fwd / bwd call (all of its kernels)
         roof['spatial_model'] = {
-            'form': 'tensor cores: grouped Toeplitz GEMMs through conv_igemm_kernel, bf16 operands (bf16 configuration)' if sm_tc
+            'form': ('tensor cores: grouped Toeplitz GEMMs through conv_igemm_kernel, bf16 operands with the prior centred per pair (%s)'
+                     % ('bf16 configuration' if precision == 'bf16' else 'opt-in for fp32 inference, --sm-tc')) if sm_tc
                     else 'fp32 FFMA2 kernels (sm_conv_kernel / sm_bwd_dp_kernel)',
             'fwd_ms': sm_prof[0]['ms_per_step'], 'bwd_ms': sm_prof[1]['ms_per_step'],
             'algorithmic_tflops_fwd': sm_prof[0]['tflops'], 'algorithmic_tflops_bwd': sm_prof[1]['tflops'] if sm_prof[1]['launches'] else None,
             'fp32_fma_peak_tflops': 73.0,
+            'fp32_ffma2_attainable': 'register-operand FFMA2 streams reach 0.92-0.95 of that peak and every load or integer instruction takes an '
+                                     'FMA issue cycle: 0.81 is the bound of this kernel\'s blocking (profiles/r02/ffma_probes/README.md)',
             'share_of_step': (sm_prof[0]['ms_per_step'] + sm_prof[1]['ms_per_step']) / (ms_total / steps)}
     line = {
         'metric': metric_name(workload), 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': steps, 'warmup': warmup,
@@ -515,6 +518,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extra-legs', dest='extra_legs', action='store_false',
                     help='train64 only: skip the short fwd16 (configs[1], N=1) and train_k14 (configs[4]) legs reported under "extra_legs"')
+    ap.add_argument('--sm-tc', action='store_true',
+                    help='fp32 inference workloads: run the spatial model in its centred tensor-core form (opt-in; default FFMA)')
     ap.add_argument('--sm-ffma', action='store_true',
                     help='bf16 workloads: run the spatial model on the fp32 FFMA kernels (north_star form) instead of the tensor-core form')
     ap.add_argument('--bf16-activations', type=int, default=None,

@@ -78,8 +78,11 @@ class Context:
     @property
     def sm_tc(self):
         """bf16 precision (default on, sm_tensor_core=False turns it off): the spatial model's pairwise convolutions run as grouped
-        Toeplitz GEMMs on the tensor cores with bf16 operands instead of the fp32 FFMA kernels.  fp32 precision: always FFMA."""
-        return self.sm_tensor_core and self.precision == 'bf16'
+        Toeplitz GEMMs on the tensor cores with bf16 operands (prior centred per pair) instead of the fp32 FFMA kernels.
+        fp32 precision: the FFMA kernels, unless sm_tensor_core=True is given AND the context is an inference one
+        (flag_train=False): the centred tensor-core forward meets the fp32 bound (1e-4 on the logits, measured 2e-7 on the
+        reference's priors, 3e-5 on rough ones) - its prior gradient (2.5e-3) does not, so fp32 training always stays on FFMA."""
+        return self.sm_tensor_core and (self.precision == 'bf16' or not self.flag_train)
 
     def packed(self, name, w, kind='fwd'):
         """Packed bf16 operand planes of a conv kernel: resident, re-packed only after the variable changed (see _PACKS)."""

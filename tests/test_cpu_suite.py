@@ -132,7 +132,8 @@ def test_context_selects_the_spatial_model_form_by_precision(built_lib):
     form unless switched off.  The workspace queries of both forms answer without a GPU."""
     import jcm
     assert not jcm.Context(n_joints=7).sm_tc
-    assert not jcm.Context(n_joints=7, precision='fp32', sm_tensor_core=True).sm_tc
+    assert jcm.Context(n_joints=7, precision='fp32', sm_tensor_core=True).sm_tc                      # opt-in, inference context
+    assert not jcm.Context(n_joints=7, precision='fp32', sm_tensor_core=True, flag_train=True).sm_tc   # fp32 training: always FFMA
     assert jcm.Context(n_joints=7, precision='bf16').sm_tc
     assert not jcm.Context(n_joints=7, precision='bf16', sm_tensor_core=False).sm_tc
     l = jcm.lib()

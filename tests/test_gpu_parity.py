@@ -239,6 +239,25 @@ def test_spatial_model_60x90_matches_oracle(jcm, B, K, train, precision):
     assert torch.equal(jcm.get_joints_coords(jcm.spatial_softmax(out)).cpu(), orc.get_joints_coords(orc.spatial_softmax(ref)))
 
 
+@pytest.mark.parametrize('K', [7, 9])
+def test_spatial_model_fp32_inference_on_tensor_cores_opt_in(jcm, K):
+    """fp32 context with sm_tensor_core=True (inference only): the centred tensor-core forward at the fp32 kernels' bound - 1e-4 on
+    the logits and the same arg-max coordinates as the oracle."""
+    names, cat, rng, g = _sm_inputs(3, K, 60, 90, 21)
+    sm64 = orc.init_spatial_model(jcm.get_pairwise_distr(), K, 60, 90, joint_names=names)
+    for k, v in sm64.items():
+        if k.startswith('bias_'):
+            v.add_(torch.rand(v.shape, generator=g).double() * 0.01)
+    sm32 = {k: v.float() for k, v in sm64.items()}
+    ref = orc.spatial_model(cat.double(), {k: v.double().clone() for k, v in sm32.items()}, K, False, joint_names=names)
+    smp = jcm.PairwiseParams.from_dict(sm32, names, K)
+    ctx = jcm.Context(n_joints=K, joint_names=names, flag_train=False, precision='fp32', sm_tensor_core=True)
+    assert ctx.sm_tc
+    out = jcm.spatial_model(cat.cuda(), smp, ctx)
+    assert rel(out, ref) < 1e-4
+    assert torch.equal(jcm.get_joints_coords(jcm.spatial_softmax(out)).cpu(), orc.get_joints_coords(orc.spatial_softmax(ref)))
+
+
 def test_spatial_model_tensor_core_is_batch_independent(jcm):
     """Size-independent property of the tensor-core form at the BASELINE batch size: in inference mode a batch of 16 (two distinct
     heat maps repeated) gives exactly the 2-image results - the M tiles, the skipped taps and the store clipping differ between
