@@ -474,9 +474,21 @@ def run_ours(args):
                     extra[wl] = {k: r[k] for k in keep if k in r}
                     extra[wl]['roofline'] = {k: r['roofline'][k] for k in ('achieved', 'peak', 'frac', 'unit', 'share_of_step', 'spatial_model')
                                              if k in r['roofline']}
+                    if wl == 'fwd16' and not args.sm_ffma and not args.sm_tc:
+                        # the same leg with the spatial model in its centred tensor-core form (opt-in for fp32 inference)
+                        import copy
+                        a2 = copy.copy(args)
+                        a2.sm_tc = True
+                        r2 = measure(wl, 5, 3, a2, rank, world, local, dev, with_cpu_baseline=False, with_e2e=False)
+                        if r2 is not None:
+                            extra[wl]['sm_tensor_core_opt_in'] = {
+                                'value': r2['value'], 'unit': r2['unit'], 'ms_per_step': r2['ms_per_step'],
+                                'spatial_model': r2['roofline'].get('spatial_model'),
+                                'note': 'Context(sm_tensor_core=True): bf16 Toeplitz GEMMs with the prior centred per pair; logits within 1e-4 of the '
+                                        'oracle like the FFMA form (tests/test_gpu_parity.py::test_spatial_model_fp32_inference_on_tensor_cores_opt_in)'}
             except Exception as e:   # noqa: BLE001
                 if rank == 0:
-                    extra[wl] = {'error': repr(e)[:300]}
+                    extra[wl] = dict(extra.get(wl, {}), error=repr(e)[:300])
         if rank == 0:
             line['extra_legs'] = extra
     if rank == 0:

@@ -922,21 +922,26 @@ extern "C" int jcm_spatial_model_bwd(const float* g, const float* heat_map, cons
 }
 
 // =====================================================================================================================
-// Tensor-core form of the spatial model (bf16 training configuration; same interface and results to bf16 operand rounding).
+// Tensor-core form of the spatial model (bf16 training configuration, opt-in for fp32 inference; same interface).  The prior
+// operand is centred per pair (P = sp(E) - c0[pair]) and the common level is added back in fp32 by the glue kernels, so everything
+// that is linear in the prior comes out at fp32 accuracy on nearly flat priors; the prior gradient (a product of two bf16-rounded
+// activations) at the plain bf16 level.
 //
 // conv_mrf is a 2-D convolution of an HxW map with a 2Hx2W kernel: along x it is a Toeplitz matrix product, along y a 2H-tap
 // 1-D convolution.  With h = sp(bn(heat map)) (not flipped), P = sp(E):
 //
 //   forward   C[n][y][x]  = sum_dy sum_v  h[n][y+dy-H][v]      * P[2H-1-dy][x-v+W-1]          y <= H, x <= W
 //   dL        dL[n][u][v] = sum_dy sum_x dC[n][u+dy-(H-1)][x]  * P[dy][x-v+W-1]
-//   dP        dP[2H-1-dy][c] = sum_{x-v+W-1=c} ( sum_{n,y} dC[n][y][x] * h[n][y+dy-H][v] )
+//                         = sum_dy sum_x' T[n][u+dy-(H-1)][x'] * ((1-w(x')) P[dy][x'-v+W-1] + w(x') P[dy][x'-v+W])     T = R_y^T dT, x' < W
+//   dP        dP[r][c] = sum_{x-v+W-1=c} ( sum_{n,y'} h[n][y'][v] * dC[n][y'+r-(H-1)][x] )                              r = 2H-1-dy
 //
 // The first two are convolutions with 2H x 1 taps over "images" [rows y][columns = the batch][channels = x or v] whose tap
 // weights are the Toeplitz blocks T_dy[x][v] of one prior row, a different set for every (target, cond) pair: the grouped form
-// grp 1 of the tcgen05 implicit-GEMM kernel (conv_tcgen05.cu).  The third is, per (pair, dy), a GEMM over (n, y) of dC^T with a
-// row-shifted h^T: form grp 2, followed by a sum along the diagonals of each block.  The Toeplitz blocks are materialised in
-// HBM as bf16 (2 x P x 2H x NP x CP: 289 MB for K = 7, written once per step at HBM speed - cheaper than any on-the-fly form
-// the UMMA descriptors could express).  Work: 3 x ~0.3 PFLOP-equivalent tiles on the tensor pipe instead of 3 x 94 GMAC of FFMA.
+// grp 1 of the tcgen05 implicit-GEMM kernel (conv_tcgen05.cu).  The third is, per (pair, r), a GEMM over (n, y') of h^T (M = v:
+// exactly W rows) with a row-shifted dC^T (N = x): form grp 2, followed by a sum along the diagonals of each block.  The Toeplitz
+// blocks are materialised in HBM as bf16 (2 x P x 2H x NP x CPf: 289 MB for K = 7, written once per step at HBM speed - cheaper than
+// any on-the-fly form the UMMA descriptors could express).  Work: 3 x ~0.3 PFLOP-equivalent tiles on the tensor pipe instead of
+// 3 x 94 GMAC of FFMA.
 // =====================================================================================================================
 namespace {
 
@@ -1325,7 +1330,6 @@ extern "C" int jcm_spatial_model_tc_fwd(const float* heat_map, const float* bn_s
   __nv_bfloat16* Xh = (__nv_bfloat16*)(ws + L.Xh);
   __nv_bfloat16* Wf = (__nv_bfloat16*)(ws + L.Wf);
   float* Cb = (float*)(ws + L.Cb);
-  const int cap = jcm_num_sms() * 16;
   {
     smt_softplus_center_kernel<<<P, 1024, 0, st>>>(energies, 4 * H * W, spE, c0);
     JCM_LAUNCH_CHECK();
@@ -1406,7 +1410,6 @@ extern "C" int jcm_spatial_model_tc_bwd(const float* g, const float* heat_map, c
   float* blk = (float*)(ws + L.blk);
   float* dh = (float*)(ws + L.dh);
   float* bnpart = (float*)(ws + L.part);
-  const int cap = jcm_num_sms() * 16;
 
   SmDims d;
   fill_dims(d, B, H, W, K, P);

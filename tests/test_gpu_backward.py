@@ -244,7 +244,10 @@ def test_conv1_stride2_wgrad_via_space_to_depth(jcm, jtrain, split):
 
 
 # ------------------------------------------------------------------------------------------------ spatial model
-@pytest.mark.parametrize('B,K,H,W', [(2, 4, 12, 20), (5, 3, 9, 13), (2, 7, 60, 90), (6, 7, 60, 90), (3, 2, 96, 128)])
+# (2, 2, 20, 136): W > 128 - two M tiles in the dP GEMM, 24 column groups in the Toeplitz pack, 2W > 256 diagonals per reduce CTA;
+# (48, 2, 12, 20): a padded batch of 48 - the 48-row tile pass of smt_dc_kernel
+@pytest.mark.parametrize('B,K,H,W', [(2, 4, 12, 20), (5, 3, 9, 13), (2, 7, 60, 90), (6, 7, 60, 90), (3, 2, 96, 128), (2, 2, 20, 136),
+                                     (48, 2, 12, 20)])
 @pytest.mark.parametrize('train', [True, False])
 @pytest.mark.parametrize('tensor_core', [False, True, 'rough'])
 def test_spatial_model_bwd(jcm, jtrain, B, K, H, W, train, tensor_core):
