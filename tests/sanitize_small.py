@@ -67,3 +67,23 @@ ops.pack_weights_batch([(w, ops._new_planes((w.shape[0] ** 2, w.shape[3], w.shap
                          ops._new_planes((w.shape[0] ** 2, w.shape[2], w.shape[3]), 'cuda', False)) for w in ws], False)
 torch.cuda.synchronize()
 print('round-2 kernels ok')
+
+# ---- tensor-core spatial model (centred prior operand, swapped dP GEMM, row-uniform diagonal reduce, staged Toeplitz pack) at the
+# shapes that take its different paths: 60x90 (K extent 128, N = 96), a 20x136 map (W > 128: two M tiles in the dP GEMM, 24 column
+# groups in the pack, more than 256 diagonals per reduce CTA) and a padded batch of 48 (48-row tile pass of smt_dc_kernel); FFMA form
+# of the first shape next to it
+for (B, Ks, H, W) in [(3, 3, 60, 90), (2, 2, 20, 136), (48, 2, 12, 20)]:
+    nm = orc.JOINT_NAMES[:Ks] + ['torso']
+    smp = jcm.PairwiseParams.from_distribution(orc.synthetic_pairwise(nm, Ks, H, W, rng), nm, Ks, H, W)
+    hm = torch.softmax(3 * torch.randn(B, H * W, Ks + 1, generator=g), dim=1).reshape(B, H, W, Ks + 1).cuda()
+    bn = smp.bn
+    ss, st = ops.bn_scale_shift(hm, bn['gamma'], bn['beta'], bn['moving_mean'], bn['moving_variance'], train=True, save=True)
+    gout = (torch.randn(B, H, W, Ks, generator=g) / (B * Ks)).cuda()
+    for tc in ((True, False) if (H, W) == (60, 90) else (True,)):
+        o, wsp = ops.spatial_model_fwd(hm, ss, smp.energies, smp.biases, smp.pair_target, smp.pair_cond, Ks, keep_workspace=True, tensor_core=tc)
+        dE, db2 = torch.empty_like(smp.energies), torch.empty_like(smp.biases)
+        dgm, dbt = torch.empty(Ks + 1, device='cuda'), torch.empty(Ks + 1, device='cuda')
+        jt.spatial_model_bwd(gout, hm, ss, st, True, smp, wsp, dE, db2, dgm, dbt, tensor_core=tc)
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(o).all()) and bool(torch.isfinite(dE).all())
+print('spatial model (tensor-core / FFMA) ok')
