@@ -1173,7 +1173,9 @@ int jcm_conv_igemm_ex(const ConvExArgs& a) {
   p.a_bytes = kTileM * p.kc * 2;
   p.b_bytes = p.block_n * p.kc * 2;
   p.stage_bytes = ((p.a_bytes + p.b_bytes + 1023) / 1024) * 1024;
-  p.tma_store = (Cout % 4) == 0 && Cout >= 32 && (p.block_n % 32) == 0;
+  // (grouped forms only: a block_n that is a multiple of 16 but not of 32 - the 144-column tiles of the tensor-core spatial model at W = 128 - ends in a
+  // half chunk: the TMEM read runs into unused accumulator columns and the TMA store clips at Cout)
+  p.tma_store = (Cout % 4) == 0 && Cout >= 32 && ((p.block_n % 32) == 0 || (a.grp != 0 && (p.block_n % 16) == 0));
   const int epi_bytes = p.tma_store ? 2 * kTileM * 128 : 0;     // two staging buffers of 128 rows x 32 fp32
   p.stages = (225 * 1024 - epi_bytes) / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;

@@ -950,7 +950,7 @@ constexpr int kHsumChunks = 16;   // pixel chunks per image of the heat-map sums
 struct SmtDims {
   int B, H, W, K, P;
   int Hc;   // H + 1: rows of the convolution output and of the zero-padded operands
-  int NP;   // GEMM N extent: W + 1 rounded up to 32
+  int NP;   // GEMM N extent: W + 1 rounded up to 16 (at least 32)
   int CPf;  // GEMM K extent of the forward pass (v < W) and of dL (x' < W: the x half of the resize is folded into the dL
             // weights, see smt_pack_prior_kernel): W rounded up to 64 - for W = 128 one k-block less than W + 1 would need
   int Bp;   // images rounded up to 16; the dP GEMM contracts over k = row * Bp + image
@@ -959,7 +959,8 @@ struct SmtDims {
 int fill_smt(SmtDims& t, int B, int H, int W, int K, int P) {
   t.B = B; t.H = H; t.W = W; t.K = K; t.P = P;
   t.Hc = H + 1;
-  t.NP = jcm_cdiv(W + 1, 32) * 32;
+  t.NP = jcm_cdiv(W + 1, 16) * 16;          // UMMA N granularity at M = 128 (W = 128: 144 columns, not 160)
+  if (t.NP < 32) t.NP = 32;
   t.CPf = jcm_cdiv(W, 64) * 64;
   t.Bp = jcm_cdiv(B, 16) * 16;
   JCM_CHECK_ARG(t.NP <= 256, "jcm_spatial_model_tc: heat-map width %d not supported (at most 255)", W);
@@ -1425,7 +1426,7 @@ extern "C" int jcm_spatial_model_tc_bwd(const float* g, const float* heat_map, c
     JCM_LAUNCH_CHECK();
     smt_cmdl_kernel<<<(B * (K + 1) + 127) / 128, 128, 0, st>>>(dtsum, c0, pair_cond, P, B, G4, K + 1, cmdl);
     JCM_LAUNCH_CHECK();
-    smt_dc_kernel<<<dim3((t.NP > t.CPf ? t.NP : t.CPf) / 32, t.Hc, P), 256, 0, st>>>(dT, t, G4, Xc, XcT);
+    smt_dc_kernel<<<dim3(jcm_cdiv(t.NP > t.CPf ? t.NP : t.CPf, 32), t.Hc, P), 256, 0, st>>>(dT, t, G4, Xc, XcT);
     JCM_LAUNCH_CHECK();
     smt_prep_kernel<<<dim3(jcm_cdiv(W, 32), t.Hc, K + 1), 256, 0, st>>>(heat_map, bn_scale, bn_shift, t, nullptr, Ht);
     JCM_LAUNCH_CHECK();
