@@ -133,6 +133,49 @@ def test_adam_and_schedule_helpers():
     np.testing.assert_allclose(p[0].numpy(), 1 - 0.01, rtol=1e-6)
 
 
+def test_adam_restatement_against_torch_optim_adam():
+    """Independent engine: torch.optim.Adam applies the bias corrections as  lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps), TF1's
+    AdamOptimizer as  lr*sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps)  ("epsilon hat" of the Adam paper, main.py:501-506).  The two are
+    the same update when torch's eps is eps_tf / sqrt(1-b2^t) (with the same eps they differ by ~eps/sqrt(v): 5e-3 of a step on the
+    smallest of these gradients).  Five steps on gradients of magnitude 1e-2: the restatement equals torch's optimizer run with the
+    per-step rescaled eps to 1e-12 of a step - i.e. moments, bias corrections and the step-count convention (t from 1) are those of
+    a third-party Adam, and the only TF1-specific reading left is where eps enters."""
+    g = torch.Generator().manual_seed(3)
+    w0 = torch.randn(50, generator=g, dtype=torch.float64)
+    grads = [0.01 * torch.randn(50, generator=g, dtype=torch.float64) for _ in range(5)]
+    lr, b1, b2, eps = 1e-3, 0.9, 0.999, 1e-8
+    p = [w0.clone()]
+    m, v = [torch.zeros(50, dtype=torch.float64)], [torch.zeros(50, dtype=torch.float64)]
+    for t, gr in enumerate(grads, 1):
+        orc.adam_tf1_step(p, [gr], m, v, t, lr, b1, b2, eps)
+    for rescale, tol in ((True, 1e-12), (False, 2e-2)):
+        q = torch.nn.Parameter(w0.clone())
+        opt = torch.optim.Adam([q], lr=lr, betas=(b1, b2), eps=eps)
+        for t, gr in enumerate(grads, 1):
+            if rescale:
+                opt.param_groups[0]['eps'] = eps / math.sqrt(1 - b2 ** t)
+            q.grad = gr.clone()
+            opt.step()
+        step = (w0 - p[0]).abs().max()
+        assert float((q.detach() - p[0]).abs().max() / step) < tol, (rescale, float((q.detach() - p[0]).abs().max() / step))
+
+
+def test_grad_renorm_against_torch_clip_grad_norm():
+    """tf.clip_by_global_norm(g, c) = g * c / max(||g||, c) (main.py:302-309); torch.nn.utils.clip_grad_norm_ scales by
+    min(1, c / (||g|| + 1e-6)): the same to 1e-6 relative, above and below the threshold."""
+    g = torch.Generator().manual_seed(4)
+    for scale in (10.0, 0.01):
+        gs = [scale * torch.randn(7, 5, generator=g, dtype=torch.float64), scale * torch.randn(11, generator=g, dtype=torch.float64)]
+        out, gn = orc.grad_renorm(gs, 4.0)
+        ps = [torch.nn.Parameter(torch.zeros_like(x)) for x in gs]
+        for p_, x in zip(ps, gs):
+            p_.grad = x.clone()
+        total = torch.nn.utils.clip_grad_norm_(ps, 4.0)
+        assert abs(float(total) - gn) < 1e-12 * max(gn, 1.0)
+        for p_, o in zip(ps, out):
+            assert float((p_.grad - o).abs().max() / o.abs().max()) < 2e-6
+
+
 def test_fft_form_of_conv_mrf_equals_the_direct_form():
     """The FFT evaluation used by the K=14 / 96x128 GPU test is the same function as the direct restatement of main.py:77-91:
     values and both gradients to 1e-12 in fp64."""
