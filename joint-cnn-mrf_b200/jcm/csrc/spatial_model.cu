@@ -264,13 +264,16 @@ __device__ __forceinline__ void legacy_tap(int dst, int n_in, int n_out, int& lo
 }
 
 // out[n,y,x,i] = log(sp(bn(hm[n,y,x,i])) + d) + sum over pairs with target i (in list order) log(resize(C) + sp(b) + d)
-// One CTA per (image, output row): thread t -> (i = t / W, x = t % W) so that the reads of C and of the biases are
-// coalesced along x; the [W][K] output row is transposed through shared memory and written contiguously.
+// One CTA per (image, output row).  Phase 1: the P x W pairwise terms log(...) are independent - thread t -> (pair = t / W, x = t % W),
+// reads of C and of the biases coalesced along x, many loads in flight per thread - and go to shared memory.  Phase 2: thread
+// (i, x) adds the unary term and its pairs' terms IN LIST ORDER (the reference's summation order, main.py:114-123; the result does
+// not depend on how phase 1 was scheduled); the [W][K] output row is transposed through shared memory and written contiguously.
 __global__ void sm_finish_kernel(const float* __restrict__ hm, const float* __restrict__ scale, const float* __restrict__ shift,
                                  const float* __restrict__ Cb, const float* __restrict__ biases /*[P][H][W]*/,
                                  const int* __restrict__ pair_target, SmDims d, float* __restrict__ out) {
-  extern __shared__ float fsm[];           // [W*K] output row + [K+1] first-pair table (as ints)
+  extern __shared__ float fsm[];           // [W*K] output row, [K+2] first-pair table (as ints), [P*W] pairwise terms
   int* first = reinterpret_cast<int*>(fsm + d.W * d.K);
+  float* terms = fsm + d.W * d.K + d.K + 2;
   const int n = blockIdx.x / d.H, y = blockIdx.x % d.H;
   const int KC = d.K + 1, OH = d.H + 1, OW = d.W + 1;
   if (threadIdx.x <= d.K) {                // pairs are sorted by target: first[i] = index of the first pair of target i
@@ -278,32 +281,49 @@ __global__ void sm_finish_kernel(const float* __restrict__ hm, const float* __re
     while (f < d.P && pair_target[f] < (int)threadIdx.x) ++f;
     first[threadIdx.x] = f;
   }
-  __syncthreads();
   int ylo, yhi;
   float wy;
   legacy_tap(y, OH, d.H, ylo, yhi, wy);
-  for (int t = threadIdx.x; t < d.W * d.K; t += blockDim.x) {
-    const int i = t / d.W, x = t - i * d.W;
+  for (int t = threadIdx.x; t < d.P * d.W; t += blockDim.x) {
+    const int p = t / d.W, x = t - p * d.W;
     int xlo, xhi;
     float wx;
     legacy_tap(x, OW, d.W, xlo, xhi, wx);
+    const float* C = Cb + (long)p * d.cb_sp + (long)n * d.cb_sn;
+    const float tl = C[ylo * d.cb_sy + xlo], tr = C[ylo * d.cb_sy + xhi];
+    const float bl = C[yhi * d.cb_sy + xlo], br = C[yhi * d.cb_sy + xhi];
+    const float top = tl + (tr - tl) * wx;
+    const float bot = bl + (br - bl) * wx;
+    float val = top + (bot - top) * wy;
+    if (d.cm_c) val += d.cm_c[p * d.B + n];
+    terms[t] = logf(val + softplus5(biases[((long)p * d.H + y) * d.W + x]) + kDelta);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < d.W * d.K; t += blockDim.x) {
+    const int i = t / d.W, x = t - i * d.W;
     const float h = fmaf(hm[(((long)n * d.H + y) * d.W + x) * KC + i], scale[i], shift[i]);
     float m = logf(softplus5(h) + kDelta);
-    for (int p = first[i]; p < first[i + 1]; ++p) {
-      const float* C = Cb + (long)p * d.cb_sp + (long)n * d.cb_sn;
-      const float tl = C[ylo * d.cb_sy + xlo], tr = C[ylo * d.cb_sy + xhi];
-      const float bl = C[yhi * d.cb_sy + xlo], br = C[yhi * d.cb_sy + xhi];
-      const float top = tl + (tr - tl) * wx;
-      const float bot = bl + (br - bl) * wx;
-      float val = top + (bot - top) * wy;
-      if (d.cm_c) val += d.cm_c[p * d.B + n];
-      m += logf(val + softplus5(biases[((long)p * d.H + y) * d.W + x]) + kDelta);
-    }
+    for (int p = first[i]; p < first[i + 1]; ++p) m += terms[p * d.W + x];
     fsm[x * d.K + i] = m;
   }
   __syncthreads();
   float* orow = out + ((long)n * d.H + y) * d.W * d.K;
   for (int t = threadIdx.x; t < d.W * d.K; t += blockDim.x) orow[t] = fsm[t];
+}
+
+int launch_sm_finish(const float* hm, const float* scale, const float* shift, const float* Cb, const float* biases, const int* pair_target,
+                     const SmDims& d, float* out, cudaStream_t st) {
+  int threads = (((d.P > d.K ? d.P : d.K) * d.W + 31) / 32) * 32;
+  if (threads > 512) threads = 512;          // two CTAs per SM: one's loads overlap the other's logarithms and its ordered sum
+  const size_t fsmem = ((size_t)d.W * d.K + d.K + 2 + (size_t)d.P * d.W) * sizeof(float);
+  if (fsmem > 227 * 1024) {
+    jcm_set_error("spatial model: %d pairs on %d-wide heat maps need %zu B of shared memory in the finishing kernel", d.P, d.W, fsmem);
+    return JCM_ENOTSUP;
+  }
+  if (fsmem > 48 * 1024) JCM_CUDA(cudaFuncSetAttribute(sm_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+  sm_finish_kernel<<<d.B * d.H, threads, fsmem, st>>>(hm, scale, shift, Cb, biases, pair_target, d, out);
+  JCM_LAUNCH_CHECK();
+  return JCM_OK;
 }
 
 // out[n,y,x] = legacy-bilinear resize of C[n] (H+1 x W+1) to H x W   (conv_mrf's tf.image.resize_images, main.py:89)
@@ -418,11 +438,8 @@ extern "C" int jcm_spatial_model_fwd(const float* heat_map, const float* bn_scal
     JCM_LAUNCH_CHECK();
   }
   {
-    int threads = ((W * K + 31) / 32) * 32;
-    if (threads > 1024) threads = 1024;
-    const size_t fsmem = ((size_t)W * K + K + 2) * sizeof(float);
-    sm_finish_kernel<<<B * H, threads, fsmem, st>>>(heat_map, bn_scale, bn_shift, Cb, biases, pair_target, d, out);
-    JCM_LAUNCH_CHECK();
+    const int rc_f = launch_sm_finish(heat_map, bn_scale, bn_shift, Cb, biases, pair_target, d, out, st);
+    if (rc_f) return rc_f;
   }
   return JCM_OK;
 }
@@ -1131,6 +1148,9 @@ smt_pack_prior_kernel(const float* __restrict__ spE, SmtDims t, int dl, __nv_bfl
   if (r0 >= rows_per_pass) return;
   uint4* dst = reinterpret_cast<uint4*>(Wt) + ((long)p * H2 + dy) * t.NP * C8;
   const int cbase = c8 * 8;
+  float wcol[8];                            // w(x') of this thread's eight columns (dL form)
+#pragma unroll
+  for (int e = 0; e < 8; ++e) wcol[e] = (dl && cbase + e < W) ? wtab[cbase + e] : 0.f;
   for (int row = r0; row < t.NP; row += rows_per_pass) {
     uint32_t o[4] = {0u, 0u, 0u, 0u};
     if (cbase < W && row < W + (dl ? 0 : 1)) {
@@ -1142,7 +1162,7 @@ smt_pack_prior_kernel(const float* __restrict__ spE, SmtDims t, int dl, __nv_bfl
         for (int e = 0; e < 8; ++e) {
           const bool ok = cbase + e < W;
           const float nxt = ok ? q[e + 1] : 0.f;
-          v[e] = ok ? prev + (nxt - prev) * wtab[cbase + e] : 0.f;
+          v[e] = ok ? prev + (nxt - prev) * wcol[e] : 0.f;
           prev = nxt;
         }
       } else {
@@ -1351,11 +1371,8 @@ extern "C" int jcm_spatial_model_tc_fwd(const float* heat_map, const float* bn_s
   d.cb_sp = (long)t.Hc * B * t.NP; d.cb_sy = B * t.NP; d.cb_sn = t.NP;
   d.cm_c = cmc;
   {
-    int threads = ((W * K + 31) / 32) * 32;
-    if (threads > 1024) threads = 1024;
-    const size_t fsmem = ((size_t)W * K + K + 2) * sizeof(float);
-    sm_finish_kernel<<<B * H, threads, fsmem, st>>>(heat_map, bn_scale, bn_shift, Cb, biases, pair_target, d, out);
-    JCM_LAUNCH_CHECK();
+    const int rc_f = launch_sm_finish(heat_map, bn_scale, bn_shift, Cb, biases, pair_target, d, out, st);
+    if (rc_f) return rc_f;
   }
   return JCM_OK;
 }
