@@ -181,8 +181,10 @@ int jcm_spatial_model_bwd(const float* g, const float* heat_map, const float* bn
 
 /* Tensor-core form of the spatial model (bf16 training configuration): same arguments, workspace protocol and results as
  * jcm_spatial_model_fwd / _bwd (main.py:94-125 and its autodiff), with the pairwise convolutions computed as grouped Toeplitz
- * GEMMs on tcgen05 with bf16 operands and fp32 accumulation.  The two forms keep different workspaces: pass the _tc_ forward
- * workspace to the _tc_ backward. */
+ * GEMMs on tcgen05 with bf16 operands and fp32 accumulation.  The prior operand is sp(E) minus its per-pair mean; the common level
+ * is added back in fp32, so on nearly flat priors (the reference's) the logits and every gradient that is linear in the prior
+ * agree with the fp32 form to ~1e-6, the prior gradient dE to ~3e-3 of its maximum (K + 1 <= 32).  The two forms keep different
+ * workspaces: pass the _tc_ forward workspace to the _tc_ backward. */
 long jcm_spatial_model_tc_workspace(int B, int H, int W, int K, int P);
 int jcm_spatial_model_tc_fwd(const float* heat_map, const float* bn_scale, const float* bn_shift, const float* energies,
                              const float* biases, const int* pair_target, const int* pair_cond, float* out, void* workspace,
