@@ -13,7 +13,10 @@
 #ifndef NWARPS
 #define NWARPS 20
 #endif
-constexpr int TX = 7, NI = 4, NW = NWARPS;
+#ifndef NIMG
+#define NIMG 4
+#endif
+constexpr int TX = 7, NI = NIMG, NW = NWARPS;   // NIMG = 8: two LDS.128 per step for 28 FFMA2 (0.107 loads per FFMA2 instead of 0.143)
 #ifndef ST
 #define ST 4
 #endif
@@ -28,17 +31,11 @@ constexpr int TX = 7, NI = 4, NW = NWARPS;
 #define VARIANT 3
 #endif
 // the 14 FFMA2 of one step: window slots (sft + k) % RING, k = 0..6, against the two image pairs of l
-#if ORDER == 1
-#define STEP_FMAS(win, sft, RING, l)                                                          \
-  _Pragma("unroll") for (int k = 0; k < TX; ++k) ffma2s(acc[k][0], win[((sft) + k) % (RING)], l.x); \
-  _Pragma("unroll") for (int k = 0; k < TX; ++k) ffma2s(acc[TX - 1 - k][1], win[((sft) + TX - 1 - k) % (RING)], l.y);
-#else
-#define STEP_FMAS(win, sft, RING, l)                                                          \
-  _Pragma("unroll") for (int k = 0; k < TX; ++k) {                                            \
-    if ((k & 1) == 0) { ffma2s(acc[k][0], win[((sft) + k) % (RING)], l.x); ffma2s(acc[k][1], win[((sft) + k) % (RING)], l.y); } \
-    else { ffma2s(acc[k][1], win[((sft) + k) % (RING)], l.y); ffma2s(acc[k][0], win[((sft) + k) % (RING)], l.x); }              \
+#define STEP_FMAS(win, sft, RING, l)                                                                     \
+  _Pragma("unroll") for (int q4 = 0; q4 < NI / 4; ++q4) {                                                \
+    _Pragma("unroll") for (int k = 0; k < TX; ++k) ffma2s(acc[k][2 * q4], win[((sft) + k) % (RING)], l[q4].x); \
+    _Pragma("unroll") for (int k = 0; k < TX; ++k) ffma2s(acc[TX - 1 - k][2 * q4 + 1], win[((sft) + TX - 1 - k) % (RING)], l[q4].y); \
   }
-#endif
 
 struct Dims {
   int B, H, W, P, G, OH, OW, KH, Hp, Wp, XG, tiles, NS, NBD, TB, pstride, prows;
@@ -75,7 +72,7 @@ sm_conv2_kernel(const float* __restrict__ energies, const float* __restrict__ Lt
   extern __shared__ __align__(16) float smem[];
   float* Ps = smem;
   const int ps_floats = (d.prows * d.pstride + 3) & ~3;
-  const int rowf = d.Wp * 4;                                   // floats per likelihood row (4 images interleaved)
+  const int rowf = d.Wp * NI;                                  // floats per likelihood row (NI images interleaved)
   float* Lw = smem + ps_floats;                                // [NW][ST][rowf]
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(Lw + (size_t)NW * ST * rowf);  // [NW][ST]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -123,11 +120,11 @@ sm_conv2_kernel(const float* __restrict__ energies, const float* __restrict__ Lt
     const long first = t + warp;
     const int ntask = first < seg_end ? (int)((seg_end - first + NW - 1) / NW) : 0;
     const int R = ntask * d.KH;                                // row items of this warp in this segment
-    const float* Lj = Lt + (long)j * d.G * d.Hp * d.Wp * 4;
+    const float* Lj = Lt + (long)j * d.G * d.Hp * d.Wp * NI;
     auto row_src = [&](int ti, int u) {
       const long rel = first + (long)ti * NW - seg_base;
       const int g = (int)(rel / d.NS);
-      return Lj + (((long)g * d.Hp + u) * d.Wp) * 4;
+      return Lj + (((long)g * d.Hp + u) * d.Wp) * NI;
     };
     // producer state (lane 0): next row item to issue
     int p_ti = 0, p_u = 0, p_issued = 0;
@@ -153,9 +150,11 @@ sm_conv2_kernel(const float* __restrict__ energies, const float* __restrict__ Lt
       const int y = tile / d.XG, x0 = (tile - y * d.XG) * TX;
       lane_valid = lane_valid && (yb + y) < d.OH;
 
-      unsigned long long acc[TX][2];
+      unsigned long long acc[TX][NI / 2];
 #pragma unroll
-      for (int k = 0; k < TX; ++k) { acc[k][0] = 0ull; acc[k][1] = 0ull; }
+      for (int k = 0; k < TX; ++k)
+#pragma unroll
+        for (int e = 0; e < NI / 2; ++e) acc[k][e] = 0ull;
 
 #pragma unroll 1
       for (int u = 0; u < d.KH; ++u) {
@@ -179,16 +178,23 @@ sm_conv2_kernel(const float* __restrict__ energies, const float* __restrict__ Lt
 #pragma unroll
         for (int k = 0; k < 2 * TX; ++k) win[k] = prow[k];
         const int npair = (d.Wp / TX) >> 1;
-        const ulonglong2 l0 = lrow[lane & 1]; (void)l0;
+        ulonglong2 l0[NI / 4];
+#pragma unroll
+        for (int q4 = 0; q4 < NI / 4; ++q4) l0[q4] = lrow[(lane & 1) * (NI / 4) + q4];
+        (void)l0;
 #pragma unroll 1
         for (int it = 0; it < npair; ++it) {
           const int vb = it * 2 * TX;
 #pragma unroll
           for (int sft = 0; sft < 2 * TX; ++sft) {
 #if (EXP & 1)
-            const ulonglong2 l = l0;
+            ulonglong2 l[NI / 4];
+#pragma unroll
+            for (int q4 = 0; q4 < NI / 4; ++q4) l[q4] = l0[q4];
 #else
-            const ulonglong2 l = lrow[vb + sft];
+            ulonglong2 l[NI / 4];
+#pragma unroll
+            for (int q4 = 0; q4 < NI / 4; ++q4) l[q4] = lrow[(vb + sft) * (NI / 4) + q4];
 #endif
             STEP_FMAS(win, sft, 2 * TX, l)
 #if !(EXP & 2)
@@ -200,7 +206,9 @@ sm_conv2_kernel(const float* __restrict__ energies, const float* __restrict__ Lt
           const int vb = npair * 2 * TX;
 #pragma unroll
           for (int sft = 0; sft < TX; ++sft) {
-            const ulonglong2 l = lrow[vb + sft];
+            ulonglong2 l[NI / 4];
+#pragma unroll
+            for (int q4 = 0; q4 < NI / 4; ++q4) l[q4] = lrow[(vb + sft) * (NI / 4) + q4];
             STEP_FMAS(win, sft, 2 * TX, l)
           }
         }
@@ -213,7 +221,9 @@ sm_conv2_kernel(const float* __restrict__ energies, const float* __restrict__ Lt
 #pragma unroll
           for (int sft = 0; sft < TX; ++sft) {
             win[(sft + TX - 1) % TX] = prow[vb + sft + TX - 1];
-            const ulonglong2 l = lrow[vb + sft];
+            ulonglong2 l[NI / 4];
+#pragma unroll
+            for (int q4 = 0; q4 < NI / 4; ++q4) l[q4] = lrow[(vb + sft) * (NI / 4) + q4];
             STEP_FMAS(win, sft, TX, l)
           }
         }
@@ -226,12 +236,14 @@ sm_conv2_kernel(const float* __restrict__ energies, const float* __restrict__ Lt
         for (int k = 0; k < TX; ++k) {
           const int x = x0 + k;
           if (x < OW) {
-            float a0, a1, a2, a3;
-            unpack2(acc[k][0], a0, a1);
-            unpack2(acc[k][1], a2, a3);
-            float* o = Cb + (((long)pair * (4 * d.G) + 4 * g) * OH + yb + y) * OW + x;
+            float* o = Cb + (((long)pair * (NI * d.G) + NI * g) * OH + yb + y) * OW + x;
             const long istr = (long)OH * OW;
-            o[0] = a0; o[istr] = a1; o[2 * istr] = a2; o[3 * istr] = a3;
+#pragma unroll
+            for (int e = 0; e < NI / 2; ++e) {
+              float a0, a1;
+              unpack2(acc[k][e], a0, a1);
+              o[(2 * e) * istr] = a0; o[(2 * e + 1) * istr] = a1;
+            }
           }
         }
       }
@@ -247,12 +259,12 @@ __global__ void naive_kernel(const float* E, const float* Lt, const int* pair_co
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= d.OH * d.OW) return;
   const int y = idx / d.OW, x = idx % d.OW;
-  const int j = pair_cond[pair], g = n / 4, e = n % 4;
+  const int j = pair_cond[pair], g = n / NI, e = n % NI;
   const float* P = E + (long)pair * (2 * d.H) * (2 * d.W);
   double s = 0;
   for (int u = 0; u < d.H; ++u)
     for (int v = 0; v < d.W; ++v)
-      s += (double)P[(y + u) * (2 * d.W) + x + v] * (double)Lt[((((long)j * d.G + g) * d.Hp + u) * d.Wp + v) * 4 + e];
+      s += (double)P[(y + u) * (2 * d.W) + x + v] * (double)Lt[((((long)j * d.G + g) * d.Hp + u) * d.Wp + v) * NI + e];
   out[idx] = (float)s;
 }
 
@@ -268,10 +280,10 @@ int main(int argc, char** argv) {
   int need = d.XG * TX + d.Wp + TX; if (need < 2 * W) need = 2 * W;
   const int want = (TX * d.XG) % 32; int ps = need; while (ps % 32 != want) ++ps; d.pstride = ps;
   d.NBD = 1; d.TB = d.OH; d.prows = d.TB - 1 + d.KH; d.tiles = d.TB * d.XG; d.NS = cdiv(d.tiles, 32);
-  const size_t smem = ((size_t)((d.prows * d.pstride + 3) & ~3) + (size_t)NW * ST * d.Wp * 4) * 4 + NW * ST * 8;
-  printf("B=%d G=%d tiles=%d NS=%d pstride=%d prows=%d smem=%zu B  ST=%d ORDER=%d VARIANT=%d\n", B, d.G, d.tiles, d.NS, d.pstride, d.prows, smem, ST, ORDER, VARIANT);
+  const size_t smem = ((size_t)((d.prows * d.pstride + 3) & ~3) + (size_t)NW * ST * d.Wp * NI) * 4 + NW * ST * 8;
+  printf("B=%d G=%d tiles=%d NS=%d pstride=%d prows=%d smem=%zu B  ST=%d NI=%d NW=%d VARIANT=%d\n", B, d.G, d.tiles, d.NS, d.pstride, d.prows, smem, ST, NI, NW, VARIANT);
 
-  const long nE = (long)P * 2 * H * 2 * W, nL = (long)(K + 1) * d.G * d.Hp * d.Wp * 4, nC = (long)P * 4 * d.G * d.OH * d.OW;
+  const long nE = (long)P * 2 * H * 2 * W, nL = (long)(K + 1) * d.G * d.Hp * d.Wp * NI, nC = (long)P * NI * d.G * d.OH * d.OW;
   std::vector<float> hE(nE), hL(nL, 0.f);
   std::vector<int> hcond(P);
   uint32_t s = 12345u;
@@ -281,8 +293,8 @@ int main(int argc, char** argv) {
     for (int g = 0; g < d.G; ++g)
       for (int u = 0; u < H; ++u)
         for (int v = 0; v < W; ++v)
-          for (int e = 0; e < 4; ++e)
-            if (4 * g + e < B) hL[((((long)j * d.G + g) * d.Hp + u) * d.Wp + v) * 4 + e] = rnd() * 1e-3f;
+          for (int e = 0; e < NI; ++e)
+            if (NI * g + e < B) hL[((((long)j * d.G + g) * d.Hp + u) * d.Wp + v) * NI + e] = rnd() * 1e-3f;
   for (int p = 0; p < P; ++p) { int i = p / K, c = p % K; hcond[p] = c >= i ? c + 1 : c; }
   float *E, *L, *C, *ref; int* cond;
   CK(cudaMalloc(&E, nE * 4)); CK(cudaMalloc(&L, nL * 4)); CK(cudaMalloc(&C, nC * 4)); CK(cudaMalloc(&ref, d.OH * d.OW * 4)); CK(cudaMalloc(&cond, P * 4));
@@ -306,7 +318,7 @@ int main(int argc, char** argv) {
   double cavg = 0, cmax = 0; for (int i = 0; i < sms; ++i) { cavg += (double)hc[i]; if ((double)hc[i] > cmax) cmax = (double)hc[i]; } cavg /= sms;
   const double mac = (double)P * B * (double)d.OH * d.OW * H * W;
   const double T = (double)P * d.G * d.NS;
-  const double ideal_cyc = T / (sms * 4.0) * (double)d.KH * d.Wp * 14 * 2;   // FFMA2 pipe cycles per SM sub-partition, executed work
+  const double ideal_cyc = T / (sms * 4.0) * (double)d.KH * d.Wp * (TX * NI / 2) * 2;   // FFMA2 pipe cycles per SM sub-partition, executed work
   const double alg_cyc = mac / (sms * 128.0);                                // algorithmic MACs at 128 FMA/clk/SM
   printf("v2 kernel: %.3f ms  %.2f TFLOP/s algorithmic   clock %.0f MHz   cycles avg %.0f max %.0f   executed-FFMA2 pipe eff %.4f   algorithmic eff %.4f\n",
          best, 2 * mac / best / 1e9, cmax / best / 1e3, cavg, cmax, ideal_cyc / cmax, alg_cyc / cmax);
@@ -318,7 +330,7 @@ int main(int argc, char** argv) {
   for (auto& c : checks) {
     naive_kernel<<<cdiv(d.OH * d.OW, 128), 128>>>(E, L, cond, d, c[0], c[1], ref);
     CK(cudaMemcpy(hR.data(), ref, d.OH * d.OW * 4, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(hC.data(), C + ((long)c[0] * 4 * d.G + c[1]) * d.OH * d.OW, d.OH * d.OW * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hC.data(), C + ((long)c[0] * NI * d.G + c[1]) * d.OH * d.OW, d.OH * d.OW * 4, cudaMemcpyDeviceToHost));
     double mx = 0, mr = 0;
     for (int i = 0; i < d.OH * d.OW; ++i) { mx = fmax(mx, fabs((double)hC[i] - hR[i])); mr = fmax(mr, fabs((double)hR[i])); }
     if (!(mx / mr < 1e30)) mx = 1e30;
