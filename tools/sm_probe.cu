@@ -1,6 +1,8 @@
 // Development harness for the FFMA2 spatial-model kernel (measurement tool, not part of libjcm.so): the kernel under test on
 // synthetic operands at the bench shape, checked against a naive kernel, timed with CUDA events and with clock64 per CTA.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o tools/sm_probe tools/sm_probe.cu ; ./tools/sm_probe [B]
+// Compile-time switches: -DNIMG=4|8 (images per task), -DNWARPS=n, -DST=n (ring stages), -DVARIANT=3|0 (14-register window ring /
+// the round-1 window), -DEXP=1|2|3 (timing only: likelihood / window / both loads hoisted out of the inner loop).
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
