@@ -270,8 +270,8 @@ __device__ __forceinline__ void legacy_tap(int dst, int n_in, int n_out, int& lo
 // not depend on how phase 1 was scheduled); the [W][K] output row is transposed through shared memory and written contiguously.
 __global__ void sm_finish_kernel(const float* __restrict__ hm, const float* __restrict__ scale, const float* __restrict__ shift,
                                  const float* __restrict__ Cb, const float* __restrict__ biases /*[P][H][W]*/,
-                                 const int* __restrict__ pair_target, SmDims d, float* __restrict__ out) {
-  extern __shared__ float fsm[];           // [W*K] output row, [K+2] first-pair table (as ints), [P*W] pairwise terms
+                                 const int* __restrict__ pair_target, SmDims d, int pc, float* __restrict__ out) {
+  extern __shared__ float fsm[];           // [W*K] output row, [K+2] first-pair table (as ints), [pc*W] pairwise terms of one chunk
   int* first = reinterpret_cast<int*>(fsm + d.W * d.K);
   float* terms = fsm + d.W * d.K + d.K + 2;
   const int n = blockIdx.x / d.H, y = blockIdx.x % d.H;
@@ -281,32 +281,40 @@ __global__ void sm_finish_kernel(const float* __restrict__ hm, const float* __re
     while (f < d.P && pair_target[f] < (int)threadIdx.x) ++f;
     first[threadIdx.x] = f;
   }
+  __syncthreads();
   int ylo, yhi;
   float wy;
   legacy_tap(y, OH, d.H, ylo, yhi, wy);
-  for (int t = threadIdx.x; t < d.P * d.W; t += blockDim.x) {
-    const int p = t / d.W, x = t - p * d.W;
-    int xlo, xhi;
-    float wx;
-    legacy_tap(x, OW, d.W, xlo, xhi, wx);
-    const float* C = Cb + (long)p * d.cb_sp + (long)n * d.cb_sn;
-    const float tl = C[ylo * d.cb_sy + xlo], tr = C[ylo * d.cb_sy + xhi];
-    const float bl = C[yhi * d.cb_sy + xlo], br = C[yhi * d.cb_sy + xhi];
-    const float top = tl + (tr - tl) * wx;
-    const float bot = bl + (br - bl) * wx;
-    float val = top + (bot - top) * wy;
-    if (d.cm_c) val += d.cm_c[p * d.B + n];
-    terms[t] = logf(val + softplus5(biases[((long)p * d.H + y) * d.W + x]) + kDelta);
+  // chunks of whole targets whose pairs fit the term buffer (pc >= the pairs of any one target; one chunk for K = 7 at 60x90)
+  for (int i0 = 0; i0 < d.K;) {
+    int i1 = i0 + 1;
+    while (i1 < d.K && first[i1 + 1] - first[i0] <= pc) ++i1;
+    const int p0 = first[i0], np = first[i1] - p0;
+    for (int t = threadIdx.x; t < np * d.W; t += blockDim.x) {
+      const int pl = t / d.W, x = t - pl * d.W, p = p0 + pl;
+      int xlo, xhi;
+      float wx;
+      legacy_tap(x, OW, d.W, xlo, xhi, wx);
+      const float* C = Cb + (long)p * d.cb_sp + (long)n * d.cb_sn;
+      const float tl = C[ylo * d.cb_sy + xlo], tr = C[ylo * d.cb_sy + xhi];
+      const float bl = C[yhi * d.cb_sy + xlo], br = C[yhi * d.cb_sy + xhi];
+      const float top = tl + (tr - tl) * wx;
+      const float bot = bl + (br - bl) * wx;
+      float val = top + (bot - top) * wy;
+      if (d.cm_c) val += d.cm_c[p * d.B + n];
+      terms[t] = logf(val + softplus5(biases[((long)p * d.H + y) * d.W + x]) + kDelta);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < (i1 - i0) * d.W; t += blockDim.x) {
+      const int il = t / d.W, x = t - il * d.W, i = i0 + il;
+      const float h = fmaf(hm[(((long)n * d.H + y) * d.W + x) * KC + i], scale[i], shift[i]);
+      float m = logf(softplus5(h) + kDelta);
+      for (int p = first[i]; p < first[i + 1]; ++p) m += terms[(p - p0) * d.W + x];
+      fsm[x * d.K + i] = m;
+    }
+    __syncthreads();                       // the term buffer is reused by the next chunk; the last pass also orders fsm[] before the copy-out
+    i0 = i1;
   }
-  __syncthreads();
-  for (int t = threadIdx.x; t < d.W * d.K; t += blockDim.x) {
-    const int i = t / d.W, x = t - i * d.W;
-    const float h = fmaf(hm[(((long)n * d.H + y) * d.W + x) * KC + i], scale[i], shift[i]);
-    float m = logf(softplus5(h) + kDelta);
-    for (int p = first[i]; p < first[i + 1]; ++p) m += terms[p * d.W + x];
-    fsm[x * d.K + i] = m;
-  }
-  __syncthreads();
   float* orow = out + ((long)n * d.H + y) * d.W * d.K;
   for (int t = threadIdx.x; t < d.W * d.K; t += blockDim.x) orow[t] = fsm[t];
 }
@@ -315,13 +323,18 @@ int launch_sm_finish(const float* hm, const float* scale, const float* shift, co
                      const SmDims& d, float* out, cudaStream_t st) {
   int threads = (((d.P > d.K ? d.P : d.K) * d.W + 31) / 32) * 32;
   if (threads > 512) threads = 512;          // two CTAs per SM: one's loads overlap the other's logarithms and its ordered sum
-  const size_t fsmem = ((size_t)d.W * d.K + d.K + 2 + (size_t)d.P * d.W) * sizeof(float);
+  // pairwise terms of as many whole targets as fit 96 KB next to the output row (two CTAs per SM); a target has at most K + 1 pairs
+  const size_t fixed = ((size_t)d.W * d.K + d.K + 2) * sizeof(float);
+  long pc = ((long)96 * 1024 - (long)fixed) / ((long)d.W * (long)sizeof(float));
+  if (pc > d.P) pc = d.P;
+  if (pc < d.K + 1) pc = d.K + 1;
+  const size_t fsmem = fixed + (size_t)pc * d.W * sizeof(float);
   if (fsmem > 227 * 1024) {
-    jcm_set_error("spatial model: %d pairs on %d-wide heat maps need %zu B of shared memory in the finishing kernel", d.P, d.W, fsmem);
+    jcm_set_error("spatial model: %d joints on %d-wide heat maps need %zu B of shared memory in the finishing kernel", d.K, d.W, fsmem);
     return JCM_ENOTSUP;
   }
   if (fsmem > 48 * 1024) JCM_CUDA(cudaFuncSetAttribute(sm_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-  sm_finish_kernel<<<d.B * d.H, threads, fsmem, st>>>(hm, scale, shift, Cb, biases, pair_target, d, out);
+  sm_finish_kernel<<<d.B * d.H, threads, fsmem, st>>>(hm, scale, shift, Cb, biases, pair_target, d, (int)pc, out);
   JCM_LAUNCH_CHECK();
   return JCM_OK;
 }
