@@ -19,3 +19,7 @@ ls -la gpurun_out/ /tmp/prof_${WL}.ncu-rep
 $NCU --set full --clock-control none --import-source on -k regex:conv_igemm_kernel -c 3 -f -o /tmp/prof_smtc python tests/gpu_diag.py smtc64 \
     > gpurun_out/ncu_smtc.log 2>&1
 $NCU -i /tmp/prof_smtc.ncu-rep --page raw --csv > gpurun_out/ncu_full_smtc_raw.csv 2>/dev/null
+# the same at the K=14 / 96x128 / batch 32 shape (configs[4]): launch 14 = the forward GEMM after warm-up, then dL and dP of the first backward
+$NCU --set full --clock-control none -k regex:conv_igemm_kernel -s 13 -c 3 -f -o /tmp/prof_smtc_k14 python tests/gpu_diag.py smtck14 \
+    > gpurun_out/ncu_smtc_k14.log 2>&1
+$NCU -i /tmp/prof_smtc_k14.ncu-rep --page raw --csv > gpurun_out/ncu_full_smtc_k14_raw.csv 2>/dev/null

@@ -2,7 +2,7 @@
 timings.  Not a pytest file - the pytest parity tests are tests/test_gpu_*.py; this one is for fast triage when a
 kernel is wrong (it localises the first diverging stage) and for quick timing sweeps.
 
-    python tests/gpu_diag.py [sections...]     sections: peak conv glue sm model time grad step wgtime convsweep smtime smtc
+    python tests/gpu_diag.py [sections...]     sections: peak conv glue sm model time grad step wgtime convsweep smtime smtc smtck14 (K=14 / 96x128 tensor-core spatial model timing)
 """
 import os
 import sys
