@@ -111,6 +111,29 @@ def test_sass_contains_blackwell_instructions(built_lib):
         assert mnemonic in sass, mnemonic
 
 
+def test_register_budgets_of_the_bandwidth_bound_kernels(built_lib):
+    """Occupancy guard: the HBM-bound glue kernels depend on many resident warps, and a small source change can make ptxas unroll one of
+    them into a 255-register kernel (it happened to the diagonal reduce of the tensor-core spatial model: 2.3 ms instead of 0.8).
+    No spills, and at most 64 registers per thread for the kernels launched with 256..1024 threads per block."""
+    import re
+    import subprocess
+    out = subprocess.run(['cuobjdump', '--dump-resource-usage', built_lib], capture_output=True, text=True).stdout
+    usage = {}
+    for m in re.finditer(r'Function ([^:\n]+):\s*\n\s*REG:(\d+) STACK:(\d+)', out):
+        usage[m.group(1)] = (int(m.group(2)), int(m.group(3)))
+    assert len(usage) > 50, 'cuobjdump --dump-resource-usage gave no per-function lines'
+    budget = {'smt_dp_reduce_kernel': 64, 'smt_pack_prior_kernel': 64, 'smt_dc_kernel': 64, 'smt_prep_kernel': 64, 'sm_finish_kernel': 64,
+              'sm_bwd_dt_kernel': 64, 'sm_bwd_dh_kernel': 64, 'smt_dtsum_kernel': 64, 'smt_softplus_center_kernel': 64,
+              'bn_stats_kernel': 64, 'clip_adam_kernel': 64, 'grad_prepare_kernel': 64, 'spatial_softmax_kernel': 64}
+    seen = set()
+    for name, (reg, stack) in usage.items():
+        for k, lim in budget.items():
+            if k in name:
+                seen.add(k)
+                assert reg <= lim and stack == 0, (name, reg, stack)
+    assert seen == set(budget), set(budget) - seen
+
+
 def test_argument_errors_do_not_need_a_gpu(built_lib):
     """Bad arguments are rejected on the host with a negative code and a message (ValueError in the Python layer)."""
     import jcm
